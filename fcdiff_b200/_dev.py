@@ -1,0 +1,116 @@
+"""
+Device-buffer plumbing: PyTorch owns device memory and streams, nothing else.
+Every arithmetic kernel of the hot path lives in ``libfcdiff_b200.so``.
+"""
+import contextlib
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_ws = {}
+
+
+def device():
+    if not torch.cuda.is_available():
+        raise _lib.FcdError(
+            "fcdiff_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def stream():
+    """Current torch stream as a ``cudaStream_t`` for the C-ABI."""
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device address of a torch tensor (None -> NULL)."""
+    if t is None:
+        return ctypes.c_void_p(0)
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def workspace():
+    """Per-device reduction workspace (zero-filled once; calls restore it)."""
+    dev = device()
+    key = dev.index
+    if key not in _ws:
+        n = _lib.load().fcd_workspace_bytes() // 8
+        _ws[key] = torch.zeros(n, dtype=torch.float64, device=dev)
+    return _ws[key]
+
+
+def empty(shape, dtype=torch.float64):
+    return torch.empty(shape, dtype=dtype, device=device())
+
+
+def zeros(shape, dtype=torch.float64):
+    return torch.zeros(shape, dtype=dtype, device=device())
+
+
+def upload(a, dtype=np.float64):
+    """Host array -> contiguous device tensor.  Pinned host memory is copied
+    asynchronously on the current stream."""
+    a = np.ascontiguousarray(a, dtype=dtype)
+    t = torch.from_numpy(a)
+    return t.to(device(), non_blocking=t.is_pinned())
+
+
+def upload_rows(a, pitch):
+    """(R, K) host array -> (R, pitch) device tensor, zero padded columns."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    R, K = a.shape
+    if pitch == K:
+        return upload(a)
+    out = zeros((R, pitch))
+    out[:, :K].copy_(torch.from_numpy(a), non_blocking=False)
+    return out
+
+
+def download(t):
+    return t.detach().cpu().numpy()
+
+
+def even(n):
+    return n + (n & 1)
+
+
+class KernelTimers(object):
+    """CUDA-event brackets around individual C-ABI calls on the current stream
+    (``fit.profile = KernelTimers()``): per-kernel launch durations measured
+    live, for bench.py's roofline figures."""
+
+    def __init__(self):
+        self.events = {}
+
+    @contextlib.contextmanager
+    def __call__(self, name):
+        s = torch.cuda.Event(enable_timing=True)
+        e = torch.cuda.Event(enable_timing=True)
+        s.record()
+        try:
+            yield
+        finally:
+            e.record()
+            self.events.setdefault(name, []).append((s, e))
+
+    def reset(self):
+        self.events = {}
+
+    def summary(self):
+        """name -> (launches, total_ms, mean_ms)."""
+        torch.cuda.synchronize()
+        out = {}
+        for name, evs in self.events.items():
+            ms = [s.elapsed_time(e) for (s, e) in evs]
+            out[name] = (len(ms), float(sum(ms)), float(sum(ms) / max(len(ms), 1)))
+        return out
+
+
+_NULL = contextlib.nullcontext()
+
+
+def timed(profile, name):
+    return _NULL if profile is None else profile(name)

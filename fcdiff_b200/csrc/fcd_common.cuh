@@ -1,0 +1,190 @@
+// Shared device/host helpers for the fcdiff_b200 kernels (sm_100a).
+//
+// Reference formulas are cited as fcdiff/<file>:<line> (reference tree).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "fcdiff_b200.h"
+
+namespace fcd {
+
+// ---------------------------------------------------------------- host side
+void set_error(const char* fmt, ...);
+int  check_launch(const char* what);          // counts the launch, maps cudaGetLastError
+int  sm_count();
+
+#define FCD_REQUIRE(cond, ...)                                                   \
+    do {                                                                         \
+        if (!(cond)) {                                                           \
+            ::fcd::set_error(__VA_ARGS__);                                       \
+            return -1;                                                           \
+        }                                                                        \
+    } while (0)
+
+constexpr double kHalfLog2Pi = 0.91893853320467274178032973640562;   // log(sqrt(2 pi))
+
+// Workspace layout (doubles): [0, kWsPartials) per-CTA partial sums,
+// then one 64-bit slot holding the arrival ticket, then 16 scratch doubles.
+constexpr int     kMaxReduceBlocks = 2048;
+constexpr int     kMaxReduceVals   = 8;
+constexpr int64_t kWsPartials      = (int64_t)kMaxReduceBlocks * kMaxReduceVals;
+constexpr int64_t kWsScratch       = kWsPartials + 2;      // 16 doubles of scratch for chained reductions
+constexpr int64_t kWsDoubles       = kWsScratch + 16;
+
+// Derived per-theta constants, passed by value to kernels (__grid_constant__).
+struct ThetaDev {
+    double mu[3];
+    double isig[3];      // 1 / sigma_k
+    double lc[3];        // -log(sigma_k)            (the -log sqrt(2 pi) is added where needed)
+    double epsl[3];      // eps_l of fcdiff/fit.py:433-444
+    double al[3];        // (1 - eps_l) / 2
+    double log_gamma[3];
+    double hq_a[3];      // healthy quadratic: sum_h logN_k(b) = hq_a*S2 + hq_b*S1 + hq_c
+    double hq_b[3];
+    double hq_c[3];
+    double eta;
+    double epsilon;
+    double log_pi2[2];
+};
+
+ThetaDev make_theta_dev(const fcd_theta& th, int H);
+
+// ---------------------------------------------------------------- device side
+#ifdef __CUDACC__
+
+// util.c_to_nm (fcdiff/util.py:82-84) with an exact integer correction of the
+// floating-point square root.
+__host__ __device__ inline void c_to_nm(int64_t c, int& n, int& m) {
+    int64_t nn = (int64_t)((sqrt((double)(8 * c + 1)) - 1.0) * 0.5) + 1;
+    while (nn * (nn - 1) / 2 > c) --nn;
+    while ((nn + 1) * nn / 2 <= c) ++nn;
+    n = (int)nn;
+    m = (int)(c - nn * (nn - 1) / 2);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// 128-bit streaming load of two doubles (read-only path, no L1 allocation).
+__device__ __forceinline__ double2 ldg_stream2(const double* p) {
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];"
+                 : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ double ldg_stream1(const double* p) {
+    double r;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    return r;
+}
+
+// Per-element core shared by K2 / K2b / K3 / K4.
+//
+// For x = bt[c,u]:   t_k = -((x-mu_k)/sigma_k)^2/2 - log sigma_k,
+//                    e_k = exp(t_k - max_j t_j),  o_k = sum_{j != k} e_j,
+//                    Mp[k][l] = eps_l e_k + a_l o_k.
+// Then log M_kl(x) of fcdiff/fit.py:117-122 equals
+//                    log Mp[k][l] + tmax - log sqrt(2 pi)
+// exactly (M_kl = eps_l p_k + (1-eps_l)/2 * sum_{j != k} p_j, fit.py:427-430),
+// evaluated without the underflow of exp() in the far tails.
+struct ElemM {
+    double e[3];
+    double o[3];
+    double tmax;
+};
+
+__device__ __forceinline__ ElemM elem_eval(double x, const ThetaDev& th) {
+    ElemM r;
+    double t[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double z = (x - th.mu[k]) * th.isig[k];
+        t[k] = fma(-0.5 * z, z, th.lc[k]);
+    }
+    r.tmax = fmax(t[0], fmax(t[1], t[2]));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) r.e[k] = exp(t[k] - r.tmax);
+    r.o[0] = r.e[1] + r.e[2];
+    r.o[1] = r.e[0] + r.e[2];
+    r.o[2] = r.e[0] + r.e[1];
+    return r;
+}
+
+__device__ __forceinline__ double elem_Mp(const ElemM& r, const ThetaDev& th, int k, int l) {
+    return fma(th.epsl[l], r.e[k], th.al[l] * r.o[k]);
+}
+
+// q_R pair weights of fcdiff/fit.py:382-406.
+__device__ __forceinline__ void pair_weights(double2 qn, double2 qm, double (&w)[3]) {
+    w[0] = qn.x * qm.x;
+    w[1] = qn.y * qm.y;
+    w[2] = fma(qn.y, qm.x, qn.x * qm.y);
+}
+
+// Deterministic grid reduction: every CTA reduces NV values, writes its partial
+// to ws[blockIdx.x*NV + i]; the CTA that arrives last sums the partials in a
+// fixed order and writes out[0..NV).  The ticket (ws[kWsPartials]) is restored
+// to zero.  Must be called by all threads of the block.
+template <int NV, int THREADS>
+__device__ __forceinline__ void grid_reduce_store(double (&v)[NV], double* ws, double* out) {
+    static_assert(NV <= kMaxReduceVals, "too many values");
+    __shared__ double s_part[NV][THREADS / 32];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double x = warp_sum(v[i]);
+        if (lane == 0) s_part[i][warp] = x;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double x = (lane < THREADS / 32) ? s_part[i][lane] : 0.0;
+            x = warp_sum(x);
+            if (lane == 0) ws[(int64_t)blockIdx.x * NV + i] = x;
+        }
+    }
+    unsigned long long* ticket = reinterpret_cast<unsigned long long*>(ws + kWsPartials);
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned long long t = atomicAdd(ticket, 1ull);
+        s_last = (t == (unsigned long long)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += THREADS) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) acc[i] += __ldcg(ws + (int64_t)b * NV + i);
+    }
+    __syncthreads();      // s_part reuse
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double x = warp_sum(acc[i]);
+        if (lane == 0) s_part[i][warp] = x;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double x = (lane < THREADS / 32) ? s_part[i][lane] : 0.0;
+            x = warp_sum(x);
+            if (lane == 0) out[i] = x;
+        }
+        if (lane == 0) *ticket = 0ull;
+    }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace fcd

@@ -1,0 +1,25 @@
+// Shared pieces of the correlation stage (K1).
+#pragma once
+#include "fcd_common.cuh"
+
+namespace fcd {
+
+constexpr int kKChunk = 32;     // fp32 elements per K step = 128 bytes = one SWIZZLE_128B row
+
+inline int corr_padded_T(int T) { return (T + kKChunk - 1) / kKChunk * kKChunk; }
+
+#ifdef __CUDACC__
+// clip to [-1, 1]; Fisher z = atanh(r) when requested.
+__device__ __forceinline__ double corr_epilogue(double r, int fisher) {
+    r = fmin(1.0, fmax(-1.0, r));
+    return fisher ? atanh(r) : r;
+}
+#endif
+
+// Tensor-core Gram + epilogue (fcd_corr_tc.cu).  Returns 0 when done, 1 when the
+// shape is not supported by the tensor-core kernel (caller uses the SIMT
+// kernel), <0 on error.
+int corr_gram_tc(const float* Z, int S, int N, int Tp, double* out, int64_t pitch, int s0,
+                 int fisher, cudaStream_t st);
+
+}  // namespace fcd

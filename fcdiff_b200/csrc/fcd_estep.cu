@@ -1,0 +1,345 @@
+// E-step kernels: healthy sufficient statistics, K2 (template posterior q_F),
+// K2b (region-weight tensor W and the Gauss-Seidel sweep for q_R).
+#include "fcd_common.cuh"
+
+namespace fcd {
+
+constexpr int kEdgeThreads = 256;       // 8 warps, one edge row per warp at a time
+
+// ------------------------------------------------------------------ c_to_nm
+__global__ void c_to_nm_kernel(int64_t c0, int64_t C, int32_t* n_out, int32_t* m_out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < C;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int n, m;
+        c_to_nm(c0 + i, n, m);
+        n_out[i] = n;
+        m_out[i] = m;
+    }
+}
+
+// ------------------------------------------------------------ healthy stats
+// S1[c] = sum_h b[c,h], S2[c] = sum_h b[c,h]^2.  One warp per edge row,
+// coalesced 64-bit loads along the subject axis.
+__global__ void __launch_bounds__(kEdgeThreads)
+healthy_stats_kernel(const double* __restrict__ b, int64_t C, int H, int64_t pitchH,
+                     double* __restrict__ S1, double* __restrict__ S2) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t c = warp0; c < C; c += nwarps) {
+        const double* row = b + c * pitchH;
+        double s1 = 0.0, s2 = 0.0;
+        for (int h = lane; h < H; h += 32) {
+            double x = ldg_stream1(row + h);
+            s1 += x;
+            s2 = fma(x, x, s2);
+        }
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (lane == 0) {
+            S1[c] = s1;
+            S2[c] = s2;
+        }
+    }
+}
+
+// ------------------------------------------------------------------- K2
+// lqF[c,k] = log gamma_k + healthy_k(S1,S2) + sum_u sum_l w_l log M_kl(bt[c,u])
+//            - logsumexp_k                                 (fcdiff/fit.py:157-174)
+// The per-(c,u) term (tmax - log sqrt(2 pi)) * sum_l w_l is common to the three
+// states k and cancels in the normalisation, so it is never formed.
+__device__ __forceinline__ void k2_elem(double x, double2 qn, double2 qm, const ThetaDev& th,
+                                        double (&acc)[3]) {
+    double w[3];
+    pair_weights(qn, qm, w);
+    ElemM r = elem_eval(x, th);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double a = acc[k];
+#pragma unroll
+        for (int l = 0; l < 3; ++l) a = fma(w[l], log(elem_Mp(r, th, k, l)), a);
+        acc[k] = a;
+    }
+}
+
+template <bool VEC2>
+__global__ void __launch_bounds__(kEdgeThreads)
+estep_qF_kernel(const double* __restrict__ S1, const double* __restrict__ S2,
+                const double* __restrict__ bt, int64_t C, int U, int64_t pitchU,
+                const double* __restrict__ qR, int N, int64_t c0,
+                const __grid_constant__ ThetaDev th,
+                double* __restrict__ lqF, double* __restrict__ qF) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const double2* qR2 = reinterpret_cast<const double2*>(qR);
+    for (int64_t c = warp0; c < C; c += nwarps) {
+        int n, m;
+        c_to_nm(c0 + c, n, m);
+        const double* row = bt + c * pitchU;
+        const double2* qn = qR2 + (int64_t)n * U;
+        const double2* qm = qR2 + (int64_t)m * U;
+        double acc[3] = {0.0, 0.0, 0.0};
+        if (VEC2) {
+            for (int u = 2 * lane; u < U; u += 64) {
+                if (u + 1 < U) {
+                    double2 x = ldg_stream2(row + u);
+                    double2 a0 = __ldg(qn + u), a1 = __ldg(qn + u + 1);
+                    double2 b0 = __ldg(qm + u), b1 = __ldg(qm + u + 1);
+                    k2_elem(x.x, a0, b0, th, acc);
+                    k2_elem(x.y, a1, b1, th, acc);
+                } else {
+                    k2_elem(ldg_stream1(row + u), __ldg(qn + u), __ldg(qm + u), th, acc);
+                }
+            }
+        } else {
+            for (int u = lane; u < U; u += 32)
+                k2_elem(ldg_stream1(row + u), __ldg(qn + u), __ldg(qm + u), th, acc);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) acc[k] = warp_sum(acc[k]);
+        if (lane == 0) {
+            const double s1 = S1[c], s2 = S2[c];
+            double l[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                l[k] = th.log_gamma[k] + fma(th.hq_a[k], s2, fma(th.hq_b[k], s1, th.hq_c[k])) + acc[k];
+            // scipy.special.logsumexp: a_max + log(sum exp(a - a_max))   (fit.py:174)
+            const double mx = fmax(l[0], fmax(l[1], l[2]));
+            const double lse = mx + log(exp(l[0] - mx) + exp(l[1] - mx) + exp(l[2] - mx));
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double v = l[k] - lse;
+                lqF[c * 3 + k] = v;
+                if (qF) qF[c * 3 + k] = exp(v);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------ patient-major copy
+// btT[u - u0][c] = bt[c][u]; 32x32 tiles through padded shared memory so both
+// sides are coalesced.
+__global__ void __launch_bounds__(256)
+transpose_patients_kernel(const double* __restrict__ bt, int64_t C, int U, int64_t pitchU,
+                          int u0, int Ul, double* __restrict__ btT, int64_t pitchC) {
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+    const int64_t cb = (int64_t)blockIdx.x * 32;
+    const int ub = blockIdx.y * 32;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        const int64_t c = cb + ty + j;
+        const int u = ub + tx;
+        if (c < C && u < Ul) tile[ty + j][tx] = bt[c * pitchU + u0 + u];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        const int u = ub + ty + j;
+        const int64_t c = cb + tx;
+        if (c < C && u < Ul) btT[(int64_t)u * pitchC + c] = tile[tx][ty + j];
+    }
+}
+
+// ------------------------------------------------------------------- K2b/W
+// WT[u][c][l] = sum_k qF[c,k] log Mp_kl(btT[u][c]).  The omitted per-(c,u)
+// constant (tmax - log sqrt(2 pi)) sum_k qF[c,k] is the same for l = 0, 1, 2 and
+// enters both states of fcdiff/fit.py:190,194 multiplied by
+// (q_R[m,u,0] + q_R[m,u,1]), so it cancels at fit.py:196.
+__global__ void __launch_bounds__(256)
+region_weights_kernel(const double* __restrict__ btT, int64_t C, int64_t pitchC,
+                      const double* __restrict__ qF, const __grid_constant__ ThetaDev th,
+                      double* __restrict__ WT) {
+    const int u = blockIdx.y;
+    const double* row = btT + (int64_t)u * pitchC;
+    double* out = WT + (int64_t)u * C * 3;
+    for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < C;
+         c += (int64_t)gridDim.x * blockDim.x) {
+        const double x = ldg_stream1(row + c);
+        const double q0 = __ldg(qF + c * 3), q1 = __ldg(qF + c * 3 + 1), q2 = __ldg(qF + c * 3 + 2);
+        ElemM r = elem_eval(x, th);
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            double w = q0 * log(elem_Mp(r, th, 0, l));
+            w = fma(q1, log(elem_Mp(r, th, 1, l)), w);
+            w = fma(q2, log(elem_Mp(r, th, 2, l)), w);
+            out[c * 3 + l] = w;
+        }
+    }
+}
+
+// --------------------------------------------------------------- K2b/sweep
+// Gauss-Seidel sweep of fcdiff/fit.py:184-197.  One CTA per patient: the
+// patient's q_R column lives in shared memory, each step n reduces N-1 terms
+// over m and writes q_R[n] back before step n+1.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+sweep_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int u0,
+             int lookup, double lp0, double lp1,
+             double* __restrict__ qR, double* __restrict__ lqR) {
+    extern __shared__ double sq[];                    // [N][2]
+    __shared__ double s_red[2][THREADS / 32];
+    const int ul = blockIdx.x;
+    const int u = u0 + ul;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int m = threadIdx.x; m < N; m += THREADS) {
+        sq[2 * m] = qR[((int64_t)m * U + u) * 2];
+        sq[2 * m + 1] = qR[((int64_t)m * U + u) * 2 + 1];
+    }
+    __syncthreads();
+    const double* Wu = WT + (int64_t)ul * C * 3;
+    for (int n = 0; n < N; ++n) {
+        const int64_t base = (int64_t)n * (n - 1) / 2;
+        double s0 = 0.0, s1 = 0.0;
+        for (int m = threadIdx.x; m < N; m += THREADS) {
+            if (m == n) continue;
+            const int64_t c = (lookup == FCD_LOOKUP_REFERENCE || m < n)
+                                  ? base + m
+                                  : (int64_t)m * (m - 1) / 2 + n;
+            const double w0 = Wu[c * 3], w1 = Wu[c * 3 + 1], w2 = Wu[c * 3 + 2];
+            const double q0 = sq[2 * m], q1 = sq[2 * m + 1];
+            s0 += fma(q0, w0, q1 * w2);               // fit.py:188-190
+            s1 += fma(q1, w1, q0 * w2);               // fit.py:192-194
+        }
+        s0 = warp_sum(s0);
+        s1 = warp_sum(s1);
+        if (lane == 0) {
+            s_red[0][warp] = s0;
+            s_red[1][warp] = s1;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double a = (lane < THREADS / 32) ? s_red[0][lane] : 0.0;
+            double b = (lane < THREADS / 32) ? s_red[1][lane] : 0.0;
+            a = warp_sum(a);
+            b = warp_sum(b);
+            if (lane == 0) {
+                double l0 = lp0 + a, l1 = lp1 + b;
+                const double mx = fmax(l0, l1);
+                const double lse = mx + log(exp(l0 - mx) + exp(l1 - mx));   // fit.py:196
+                l0 -= lse;
+                l1 -= lse;
+                const double p0 = exp(l0), p1 = exp(l1);                   // fit.py:197
+                sq[2 * n] = p0;
+                sq[2 * n + 1] = p1;
+                const int64_t o = ((int64_t)n * U + u) * 2;
+                lqR[o] = l0;
+                lqR[o + 1] = l1;
+                qR[o] = p0;
+                qR[o + 1] = p1;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+static inline int grid_for_rows(int64_t rows, int rows_per_block, int waves) {
+    int64_t need = (rows + rows_per_block - 1) / rows_per_block;
+    int64_t cap = (int64_t)sm_count() * waves;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+}  // namespace fcd
+
+using namespace fcd;
+
+extern "C" {
+
+int fcd_c_to_nm(int64_t c0, int64_t C, int32_t* n_out, int32_t* m_out, void* stream) {
+    FCD_REQUIRE(C >= 0 && c0 >= 0, "fcd_c_to_nm: bad range");
+    if (C == 0) return 0;
+    c_to_nm_kernel<<<grid_for_rows(C, 256, 8), 256, 0, (cudaStream_t)stream>>>(c0, C, n_out, m_out);
+    return check_launch("fcd_c_to_nm");
+}
+
+int fcd_healthy_stats(const double* b, int64_t C, int32_t H, int64_t pitchH,
+                      double* S1, double* S2, void* stream) {
+    FCD_REQUIRE(C >= 0 && H >= 1 && pitchH >= H, "fcd_healthy_stats: bad shape C=%lld H=%d pitch=%lld",
+                (long long)C, H, (long long)pitchH);
+    if (C == 0) return 0;
+    healthy_stats_kernel<<<grid_for_rows(C, kEdgeThreads / 32, 8), kEdgeThreads, 0, (cudaStream_t)stream>>>(
+        b, C, H, pitchH, S1, S2);
+    return check_launch("fcd_healthy_stats");
+}
+
+int fcd_estep_qF(const double* S1, const double* S2, int32_t H,
+                 const double* bt, int64_t C, int32_t U, int64_t pitchU,
+                 const double* qR, int32_t N, int64_t c0,
+                 const fcd_theta* theta_host, double* lqF, double* qF, void* stream) {
+    FCD_REQUIRE(theta_host != nullptr, "fcd_estep_qF: theta is NULL");
+    FCD_REQUIRE(C >= 0 && U >= 1 && pitchU >= U && N >= 2, "fcd_estep_qF: bad shape");
+    FCD_REQUIRE(c0 >= 0 && c0 + C <= (int64_t)N * (N - 1) / 2, "fcd_estep_qF: edge shard [%lld, %lld) outside N=%d",
+                (long long)c0, (long long)(c0 + C), N);
+    if (C == 0) return 0;
+    const ThetaDev th = make_theta_dev(*theta_host, H);
+    const int grid = grid_for_rows(C, kEdgeThreads / 32, 8);
+    const bool vec2 = (pitchU % 2 == 0) && ((reinterpret_cast<uintptr_t>(bt) & 15) == 0);
+    if (vec2)
+        estep_qF_kernel<true><<<grid, kEdgeThreads, 0, (cudaStream_t)stream>>>(
+            S1, S2, bt, C, U, pitchU, qR, N, c0, th, lqF, qF);
+    else
+        estep_qF_kernel<false><<<grid, kEdgeThreads, 0, (cudaStream_t)stream>>>(
+            S1, S2, bt, C, U, pitchU, qR, N, c0, th, lqF, qF);
+    return check_launch("fcd_estep_qF");
+}
+
+int fcd_transpose_patients(const double* bt, int64_t C, int32_t U, int64_t pitchU,
+                           int32_t u0, int32_t Ul, double* btT, int64_t pitchC, void* stream) {
+    FCD_REQUIRE(C >= 0 && U >= 1 && pitchU >= U && u0 >= 0 && Ul >= 0 && u0 + Ul <= U && pitchC >= C,
+                "fcd_transpose_patients: bad shape");
+    if (C == 0 || Ul == 0) return 0;
+    dim3 grid((unsigned)((C + 31) / 32), (unsigned)((Ul + 31) / 32));
+    transpose_patients_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(bt, C, U, pitchU, u0, Ul, btT, pitchC);
+    return check_launch("fcd_transpose_patients");
+}
+
+int fcd_region_weights(const double* btT, int32_t Ul, int64_t C, int64_t pitchC,
+                       const double* qF, const fcd_theta* theta_host, double* WT, void* stream) {
+    FCD_REQUIRE(theta_host != nullptr, "fcd_region_weights: theta is NULL");
+    FCD_REQUIRE(C >= 0 && Ul >= 0 && Ul <= 65535 && pitchC >= C, "fcd_region_weights: bad shape");
+    if (C == 0 || Ul == 0) return 0;
+    const ThetaDev th = make_theta_dev(*theta_host, 0);
+    int64_t bx = (C + 255) / 256;
+    const int64_t cap = ((int64_t)sm_count() * 16 + Ul - 1) / Ul;
+    if (bx > cap) bx = cap < 1 ? 1 : cap;
+    dim3 grid((unsigned)bx, (unsigned)Ul);
+    region_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(btT, C, pitchC, qF, th, WT);
+    return check_launch("fcd_region_weights");
+}
+
+int fcd_estep_qR(const double* WT, int64_t C, int32_t N, int32_t U, int32_t u0, int32_t Ul,
+                 const double* log_pi2_host, int32_t edge_lookup,
+                 double* qR, double* lqR, void* stream) {
+    FCD_REQUIRE(log_pi2_host != nullptr, "fcd_estep_qR: log_pi2 is NULL");
+    FCD_REQUIRE(N >= 2 && C == (int64_t)N * (N - 1) / 2, "fcd_estep_qR: C=%lld is not N(N-1)/2 for N=%d",
+                (long long)C, N);
+    FCD_REQUIRE(edge_lookup == FCD_LOOKUP_REFERENCE || edge_lookup == FCD_LOOKUP_SYMMETRIC,
+                "fcd_estep_qR: unknown edge_lookup %d", edge_lookup);
+    FCD_REQUIRE(!(edge_lookup == FCD_LOOKUP_REFERENCE && N < 3),
+                "fcd_estep_qR: edge_lookup='reference' indexes out of bounds for N < 3 (fit.py:186)");
+    FCD_REQUIRE(u0 >= 0 && Ul >= 0 && u0 + Ul <= U, "fcd_estep_qR: bad patient range");
+    if (Ul == 0) return 0;
+    const size_t smem = (size_t)N * 2 * sizeof(double);
+    FCD_REQUIRE(smem <= 200 * 1024, "fcd_estep_qR: N=%d too large for the shared-memory q_R column", N);
+    cudaStream_t st = (cudaStream_t)stream;
+    const double lp0 = log_pi2_host[0], lp1 = log_pi2_host[1];
+#define FCD_SWEEP(T)                                                                              \
+    do {                                                                                          \
+        if (smem > 48 * 1024)                                                                     \
+            cudaFuncSetAttribute(sweep_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                 (int)smem);                                                      \
+        sweep_kernel<T><<<Ul, T, smem, st>>>(WT, C, N, U, u0, edge_lookup, lp0, lp1, qR, lqR);    \
+    } while (0)
+    if (N <= 32) FCD_SWEEP(32);
+    else if (N <= 64) FCD_SWEEP(64);
+    else if (N <= 128) FCD_SWEEP(128);
+    else if (N <= 256) FCD_SWEEP(256);
+    else if (N <= 512) FCD_SWEEP(512);
+    else FCD_SWEEP(1024);
+#undef FCD_SWEEP
+    return check_launch("fcd_estep_qR");
+}
+
+}  // extern "C"

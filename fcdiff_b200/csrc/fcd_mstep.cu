@@ -1,0 +1,219 @@
+// M-step and free-energy kernels: K3a (pi / gamma sums), K3b (objective and
+// analytic gradient of the (eta, epsilon) sub-problem), K4 (energy terms).
+// All reductions accumulate in fp64: warp shuffle -> block -> deterministic
+// last-CTA grid reduction.
+#include "fcd_common.cuh"
+
+namespace fcd {
+
+constexpr int kRedThreads = 256;
+
+// ------------------------------------------------------------------- K3a
+// out[0..2] = sum_c exp(lqF[c,k]) (fcdiff/fit.py:219-220),
+// out[3]    = sum_{n,u} exp(lqR[n,u,1]) (fit.py:212-213).
+__global__ void __launch_bounds__(kRedThreads)
+mstep_stats_kernel(const double* __restrict__ lqF, int64_t C,
+                   const double* __restrict__ lqR, int64_t NU,
+                   double* __restrict__ out, double* __restrict__ ws) {
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t c = tid; c < C; c += nth) {
+        v[0] += exp(lqF[c * 3]);
+        v[1] += exp(lqF[c * 3 + 1]);
+        v[2] += exp(lqF[c * 3 + 2]);
+    }
+    for (int64_t i = tid; i < NU; i += nth) v[3] += exp(lqR[i * 2 + 1]);
+    grid_reduce_store<4, kRedThreads>(v, ws, out);
+}
+
+// ------------------------------------------------------------------- K3b
+// One pass over the local edge rows of bt.  Per element (fit.py:489-511 for
+// the objective, fit.py:600-697 for the gradient):
+//   E_lM  += sum_k qF_k sum_l w_l [log Mp_kl + tmax - log sqrt(2 pi)]
+//   dE/dh -= sum_k qF_k w_2 (2 eps - 1)   (e_k - o_k / 2) / Mp_k2
+//   dE/de -= sum_k qF_k sum_l w_l s_l     (e_k - o_k / 2) / Mp_kl,  s = (-1, 1, 2 eta - 1)
+// (the common factor exp(tmax)/sqrt(2 pi) of numerator and mixture cancels).
+template <bool GRAD>
+__device__ __forceinline__ void k3_elem(double x, double2 qn, double2 qm, const double (&qf)[3],
+                                        double qfs, const ThetaDev& th, double (&acc)[3]) {
+    double w[3];
+    pair_weights(qn, qm, w);
+    ElemM r = elem_eval(x, th);
+    double obj = (w[0] + w[1] + w[2]) * qfs * (r.tmax - kHalfLog2Pi);
+    double gh = 0.0, ge = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double num = fma(-0.5, r.o[k], r.e[k]);
+        double so = 0.0, sg = 0.0;
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            const double M = elem_Mp(r, th, k, l);
+            so = fma(w[l], log(M), so);
+            if (GRAD) {
+                const double g = w[l] * (num / M);
+                if (l == 0) sg -= g;
+                else if (l == 1) sg += g;
+                else {
+                    sg = fma(2.0 * th.eta - 1.0, g, sg);
+                    gh = fma(qf[k], g, gh);
+                }
+            }
+        }
+        obj = fma(qf[k], so, obj);
+        if (GRAD) ge = fma(qf[k], sg, ge);
+    }
+    acc[0] += obj;
+    if (GRAD) {
+        acc[1] -= (2.0 * th.epsilon - 1.0) * gh;
+        acc[2] -= ge;
+    }
+}
+
+template <bool GRAD, bool VEC2>
+__global__ void __launch_bounds__(kRedThreads)
+elm_kernel(const double* __restrict__ bt, int64_t C, int U, int64_t pitchU,
+           const double* __restrict__ qF, const double* __restrict__ qR, int N, int64_t c0,
+           const __grid_constant__ ThetaDev th, double* __restrict__ out, int out_stride_dummy,
+           double* __restrict__ ws) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const double2* qR2 = reinterpret_cast<const double2*>(qR);
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int64_t c = warp0; c < C; c += nwarps) {
+        int n, m;
+        c_to_nm(c0 + c, n, m);
+        const double* row = bt + c * pitchU;
+        const double2* qn = qR2 + (int64_t)n * U;
+        const double2* qm = qR2 + (int64_t)m * U;
+        double qf[3] = {__ldg(qF + c * 3), __ldg(qF + c * 3 + 1), __ldg(qF + c * 3 + 2)};
+        const double qfs = qf[0] + qf[1] + qf[2];
+        if (VEC2) {
+            for (int u = 2 * lane; u < U; u += 64) {
+                if (u + 1 < U) {
+                    double2 x = ldg_stream2(row + u);
+                    double2 a0 = __ldg(qn + u), a1 = __ldg(qn + u + 1);
+                    double2 b0 = __ldg(qm + u), b1 = __ldg(qm + u + 1);
+                    k3_elem<GRAD>(x.x, a0, b0, qf, qfs, th, acc);
+                    k3_elem<GRAD>(x.y, a1, b1, qf, qfs, th, acc);
+                } else {
+                    k3_elem<GRAD>(ldg_stream1(row + u), __ldg(qn + u), __ldg(qm + u), qf, qfs, th, acc);
+                }
+            }
+        } else {
+            for (int u = lane; u < U; u += 32)
+                k3_elem<GRAD>(ldg_stream1(row + u), __ldg(qn + u), __ldg(qm + u), qf, qfs, th, acc);
+        }
+    }
+    grid_reduce_store<3, kRedThreads>(acc, ws, out);
+}
+
+// ------------------------------------------------------------------- K4
+// The six terms of fcdiff/fit.py:142-155; E_lM (v[3]) is produced by elm_kernel
+// into the workspace scratch just before this kernel and folded in here.
+//  v[0] E_lp_F = sum qF log gamma (fit.py:458)   v[1] E_lp_B_g_F (fit.py:472, via S1,S2)
+//  v[2] E_lp_R = sum qR log[1-pi, pi] (fit.py:486)
+//  v[4] E_lq_F = sum qF lqF (fit.py:525)         v[5] E_lq_R = sum qR lqR (fit.py:539)
+__global__ void __launch_bounds__(kRedThreads)
+energy_small_kernel(const double* __restrict__ S1, const double* __restrict__ S2,
+                    const double* __restrict__ lqF, const double* __restrict__ qF, int64_t C,
+                    const double* __restrict__ lqR, const double* __restrict__ qR, int64_t NU,
+                    const __grid_constant__ ThetaDev th, double* __restrict__ out6,
+                    double* __restrict__ ws) {
+    double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    if (tid == 0) v[3] = ws[kWsScratch];
+    for (int64_t c = tid; c < C; c += nth) {
+        const double s1 = S1[c], s2 = S2[c];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double l = lqF[c * 3 + k];
+            const double q = qF[c * 3 + k];
+            v[0] = fma(q, th.log_gamma[k], v[0]);
+            v[1] = fma(q, fma(th.hq_a[k], s2, fma(th.hq_b[k], s1, th.hq_c[k])), v[1]);
+            v[4] = fma(q, l, v[4]);
+        }
+    }
+    for (int64_t i = tid; i < NU; i += nth) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const double l = lqR[i * 2 + j];
+            const double q = qR[i * 2 + j];
+            v[2] = fma(q, th.log_pi2[j], v[2]);
+            v[5] = fma(q, l, v[5]);
+        }
+    }
+    grid_reduce_store<6, kRedThreads>(v, ws, out6);
+}
+
+static inline int red_grid(int64_t work_items, int items_per_block) {
+    int64_t need = (work_items + items_per_block - 1) / items_per_block;
+    int64_t cap = (int64_t)sm_count() * 8;
+    if (cap > kMaxReduceBlocks) cap = kMaxReduceBlocks;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+static int launch_elm(const double* bt, int64_t C, int32_t U, int64_t pitchU,
+                      const double* qF, const double* qR, int32_t N, int64_t c0,
+                      const ThetaDev& th, bool grad, double* out3, double* ws, cudaStream_t st) {
+    const int grid = red_grid(C, kRedThreads / 32);
+    const bool vec2 = (pitchU % 2 == 0) && ((reinterpret_cast<uintptr_t>(bt) & 15) == 0);
+    if (grad) {
+        if (vec2) elm_kernel<true, true><<<grid, kRedThreads, 0, st>>>(bt, C, U, pitchU, qF, qR, N, c0, th, out3, 0, ws);
+        else      elm_kernel<true, false><<<grid, kRedThreads, 0, st>>>(bt, C, U, pitchU, qF, qR, N, c0, th, out3, 0, ws);
+    } else {
+        if (vec2) elm_kernel<false, true><<<grid, kRedThreads, 0, st>>>(bt, C, U, pitchU, qF, qR, N, c0, th, out3, 0, ws);
+        else      elm_kernel<false, false><<<grid, kRedThreads, 0, st>>>(bt, C, U, pitchU, qF, qR, N, c0, th, out3, 0, ws);
+    }
+    return check_launch("fcd_elm_obj_grad");
+}
+
+}  // namespace fcd
+
+using namespace fcd;
+
+extern "C" {
+
+int fcd_mstep_stats(const double* lqF, int64_t C, const double* lqR, int64_t NU,
+                    double* out4, double* ws, void* stream) {
+    FCD_REQUIRE(C >= 0 && NU >= 0 && ws != nullptr, "fcd_mstep_stats: bad arguments");
+    const int64_t work = C > NU ? C : NU;
+    mstep_stats_kernel<<<red_grid(work, kRedThreads), kRedThreads, 0, (cudaStream_t)stream>>>(
+        lqF, C, lqR, NU, out4, ws);
+    return check_launch("fcd_mstep_stats");
+}
+
+int fcd_elm_obj_grad(const double* bt, int64_t C, int32_t U, int64_t pitchU,
+                     const double* qF, const double* qR, int32_t N, int64_t c0,
+                     const fcd_theta* theta_host, int32_t want_grad,
+                     double* out3, double* ws, void* stream) {
+    FCD_REQUIRE(theta_host != nullptr && ws != nullptr, "fcd_elm_obj_grad: NULL argument");
+    FCD_REQUIRE(C >= 0 && U >= 1 && pitchU >= U && N >= 2, "fcd_elm_obj_grad: bad shape");
+    FCD_REQUIRE(c0 >= 0 && c0 + C <= (int64_t)N * (N - 1) / 2, "fcd_elm_obj_grad: edge shard outside N=%d", N);
+    const ThetaDev th = make_theta_dev(*theta_host, 0);
+    return launch_elm(bt, C, U, pitchU, qF, qR, N, c0, th, want_grad != 0, out3, ws, (cudaStream_t)stream);
+}
+
+int fcd_energy_terms(const double* S1, const double* S2, int32_t H,
+                     const double* bt, int64_t C, int32_t U, int64_t pitchU,
+                     const double* lqF, const double* qF, const double* lqR, const double* qR,
+                     int32_t N, int64_t c0, const fcd_theta* theta_host,
+                     double* out6, double* ws, void* stream) {
+    FCD_REQUIRE(theta_host != nullptr && ws != nullptr, "fcd_energy_terms: NULL argument");
+    FCD_REQUIRE(C >= 0 && U >= 1 && pitchU >= U && N >= 2 && H >= 1, "fcd_energy_terms: bad shape");
+    FCD_REQUIRE(c0 >= 0 && c0 + C <= (int64_t)N * (N - 1) / 2, "fcd_energy_terms: edge shard outside N=%d", N);
+    const ThetaDev th = make_theta_dev(*theta_host, H);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_elm(bt, C, U, pitchU, qF, qR, N, c0, th, false, ws + kWsScratch, ws, st);
+    if (rc) return rc;
+    const int64_t NU = (int64_t)N * U;
+    const int64_t work = C > NU ? C : NU;
+    energy_small_kernel<<<red_grid(work, kRedThreads), kRedThreads, 0, st>>>(
+        S1, S2, lqF, qF, C, lqR, qR, NU, th, out6, ws);
+    return check_launch("fcd_energy_terms");
+}
+
+}  // extern "C"

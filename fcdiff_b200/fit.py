@@ -1,0 +1,832 @@
+"""
+Fits models to observed correlations.
+
+Mirror of the reference's ``fcdiff/fit.py``: ``UnsharedRegionFit`` keeps its
+attributes (``model, b, bt, max_iters, rel_tol, energy`` and the private
+``_lq_R, _lq_F, _lp_B_g_F, _p_Bt_g_Ft, _lM``), its methods and the module-level
+``_eval_*`` functions with the same argument shapes and return types
+(fcdiff/fit.py:12-733).  Every array operation of the variational-EM loop runs
+in ``libfcdiff_b200.so`` (hand-written sm_100a CUDA, ``include/fcdiff_b200.h``).
+
+Two execution forms of each step:
+
+* **fused** (the production path, used by ``run()``): the (C,H,3), (C,U,3) and
+  (C,U,3,3) caches of the reference are never built; kernels recompute the
+  densities from ``b``/``bt`` in registers.  ``_update_lps()`` only snapshots
+  (mu, sigma, eta, epsilon) and (re)uploads the inputs; reading ``_lp_B_g_F``,
+  ``_p_Bt_g_Ft`` or ``_lM`` materialises them on demand.
+* **arrays**: when a caller *assigns* ``_lp_B_g_F`` / ``_lM`` (as the
+  reference's unit tests do, test_fcdiff/test_fit.py:440-446, 483-489) the same
+  steps run from those arrays.
+
+Repairs relative to the reference as shipped -- ``run()`` in
+the reference cannot execute:
+
+* R1 ``N = int(C_to_N(C))``; R2 ``energy`` is appended; R4/R5 the (eta, epsilon)
+  objective is ``-E_lM`` with the analytic gradient of fit.py:600-697, minimised
+  by SciPy's L-BFGS-B on [1e-5, 1-1e-5]^2 (fit.py:228-241);
+* R3 a scalar ``model.pi`` is presented to ``_update_lq_R`` / ``_eval_E_lp_R`` as
+  ``[1 - pi, pi]`` (test_fcdiff/test_fit.py:208, 477-487); a 2-vector is used
+  as given.
+
+``edge_lookup`` selects the edge read for the pair (n, m), m > n, in
+``_update_lq_R``: ``"reference"`` reproduces ``nm_to_c(n, m)`` of fit.py:185-186
+(SURVEY 0.3), ``"symmetric"`` uses the unordered pair.
+"""
+import ctypes
+
+import numpy as np
+import scipy.optimize
+import torch
+
+from . import _dev, _lib, util
+
+_LOOKUP = {"reference": 0, "symmetric": 1}
+
+
+def _pi2(pi):
+    """R3: scalar pi -> [1 - pi, pi]; a 2-vector is used as given."""
+    p = np.asarray(pi, dtype=np.float64)
+    if p.ndim == 0:
+        return np.array([1.0 - float(p), float(p)])
+    return p.reshape(-1)[:2]
+
+
+class _Mirror(object):
+    """A log-probability array living on the host, the device, or both.
+    Device side holds the log array and its exponential (the reference forms
+    ``q = np.exp(lq)`` at every use, fit.py:146-147, 166, 181-182)."""
+
+    def __init__(self):
+        self.host = None
+        self.dev = None      # (lq, q) device tensors, flat
+
+    def set_host(self, a):
+        self.host = a
+        self.dev = None
+
+    def set_dev(self, lq, q, shape):
+        self.dev = (lq, q)
+        self.shape = shape
+        self.host = None
+
+    def get_host(self):
+        if self.host is None and self.dev is not None:
+            self.host = _dev.download(self.dev[0]).reshape(self.shape)
+        return self.host
+
+    def get_dev(self):
+        if self.dev is None:
+            if self.host is None:
+                raise ValueError("log-probabilities have not been initialized (call _init_lps)")
+            h = np.ascontiguousarray(self.host, dtype=np.float64)
+            self.shape = h.shape
+            self.dev = (_dev.upload(h.reshape(-1)), _dev.upload(np.exp(h).reshape(-1)))
+        return self.dev
+
+
+class UnsharedRegionFit(object):
+    """
+    Fits an unshared region model to correlations.
+
+    Attributes
+    -------
+    model : :class:`fcdiff.UnsharedRegionModel`
+        Initial model; mutated in place by the M-step (fit.py:213, 220, 264-265).
+    b : :class:`numpy.ndarray`, (C, H), -1 <= float <= 1
+        Correlations of healthy subjects.
+    bt : :class:`numpy.ndarray`, (C, U), -1 <= float <= 1
+        Correlations of unhealthy patients.
+    max_iters : 1 <= int
+        Maximum number of iterations.
+    rel_tol : 0 < float
+        Relative tolerance used to determined convergence.
+    energy : list< float >
+        Variational free energy at each iteration.
+    edge_lookup : "reference" | "symmetric"
+        See the module docstring (new knob, reference-preserving default).
+    shards : :class:`fcdiff_b200.dist.EdgeShards` or None
+        Edge sharding over the ranks of a ``torch.distributed`` group (new).
+    optimise_theta_sub : bool
+        Run the (eta, epsilon) optimiser in ``_update_theta`` (default True).
+    """
+
+    def __init__(self):
+        self.model = None
+        self.b = None
+        self.bt = None
+        self.max_iters = 10
+        self.rel_tol = 1e-5
+        self.energy = []
+        self.edge_lookup = "reference"
+        self.shards = None
+        self.n_edges = None           # global edge count when b / bt are device edge shards
+        self.optimise_theta_sub = True
+        self.n_objective_evals = []
+        self.profile = None           # _dev.KernelTimers for per-kernel CUDA-event timing
+
+        self._mR = _Mirror()          # _lq_R (N, U, 2)
+        self._mF = _Mirror()          # _lq_F (C, 1, 3)
+        self._dims = None             # (N, H, U)
+        self._lps_state = None        # None | 'ones' | 'derived'
+        self._explicit = {}           # user-assigned _lp_B_g_F / _p_Bt_g_Ft / _lM
+        self._mat = None              # materialised caches (host) for the getters
+        self._theta_lps = None        # (mu, sigma, eta, epsilon) at the last _update_lps
+        self._in = None               # uploaded inputs
+
+    # ------------------------------------------------------------------ private arrays
+    @property
+    def _lq_R(self):
+        return self._mR.get_host()
+
+    @_lq_R.setter
+    def _lq_R(self, a):
+        self._mR.set_host(a)
+
+    @property
+    def _lq_F(self):
+        return self._mF.get_host()
+
+    @_lq_F.setter
+    def _lq_F(self, a):
+        self._mF.set_host(a)
+
+    def _cache_get(self, name, shape_of):
+        if name in self._explicit:
+            return self._explicit[name]
+        if self._lps_state is None:
+            return None
+        if self._lps_state == 'ones':                       # fit.py:100-102
+            (N, H, U) = self._dims
+            return np.full(shape_of(util.N_to_C(N), H, U), 1.0)
+        return self._materialise()[name]
+
+    @property
+    def _lp_B_g_F(self):
+        return self._cache_get('_lp_B_g_F', lambda C, H, U: (C, H, 3))
+
+    @_lp_B_g_F.setter
+    def _lp_B_g_F(self, a):
+        self._explicit['_lp_B_g_F'] = a
+
+    @property
+    def _p_Bt_g_Ft(self):
+        return self._cache_get('_p_Bt_g_Ft', lambda C, H, U: (C, U, 3))
+
+    @_p_Bt_g_Ft.setter
+    def _p_Bt_g_Ft(self, a):
+        self._explicit['_p_Bt_g_Ft'] = a
+
+    @property
+    def _lM(self):
+        return self._cache_get('_lM', lambda C, H, U: (C, U, 3, 3))
+
+    @_lM.setter
+    def _lM(self, a):
+        self._explicit['_lM'] = a
+
+    # ------------------------------------------------------------------ inputs
+    def _global_shape(self):
+        """(C, H, U) of the whole problem.  ``b`` / ``bt`` are host arrays of the
+        full problem (the reference's contract), or CUDA tensors: the full
+        arrays on one device, or -- when ``shards`` is set -- this rank's edge
+        rows, with ``n_edges`` giving the global edge count."""
+        (C, H) = tuple(self.b.shape)
+        U = int(self.bt.shape[1])
+        if self._device_shard_inputs():
+            C = int(self.n_edges)
+        return int(C), int(H), U
+
+    def _device_shard_inputs(self):
+        return self.shards is not None and torch.is_tensor(self.b) and self.n_edges is not None
+
+    def _ensure_inputs(self):
+        """Uploads b / bt (once per distinct array) and builds the healthy
+        sufficient statistics.  The reference re-reads ``self.b`` / ``self.bt``
+        at every ``_update_lps`` (fit.py:114-115); re-assign the attribute to
+        have a changed array picked up."""
+        key = (id(self.b), id(self.bt), tuple(self.b.shape), tuple(self.bt.shape),
+               None if self.shards is None else self.shards.key())
+        if self._in is not None and self._in['key'] == key:
+            return self._in
+        lib = _lib.load()
+        (C, H, U) = self._global_shape()
+        if self.shards is None:
+            (c0, Cl, u0, Ul) = (0, C, 0, U)
+        else:
+            (c0, Cl, u0, Ul) = self.shards.ranges(C, U)
+        pitchU = _dev.even(U)
+        if torch.is_tensor(self.b):
+            rows = slice(None) if (self._device_shard_inputs() or self.shards is None) else slice(c0, c0 + Cl)
+            b_dev = self.b[rows].to(_dev.device(), torch.float64).contiguous()
+            bt_src = self.bt[rows].to(_dev.device(), torch.float64)
+            if pitchU == U:
+                bt_dev = bt_src.contiguous()
+            else:
+                bt_dev = _dev.zeros((Cl, pitchU))
+                bt_dev[:, :U].copy_(bt_src)
+            assert b_dev.shape[0] == Cl and bt_dev.shape[0] == Cl, "edge shard has the wrong number of rows"
+        else:
+            b_dev = _dev.upload(np.asarray(self.b)[c0:c0 + Cl])
+            bt_dev = _dev.upload_rows(np.asarray(self.bt)[c0:c0 + Cl], pitchU)
+        S1 = _dev.empty((Cl,))
+        S2 = _dev.empty((Cl,))
+        with _dev.timed(self.profile, "K0_healthy_stats"):
+            _lib.check(lib.fcd_healthy_stats(_dev.ptr(b_dev), Cl, H, H, _dev.ptr(S1), _dev.ptr(S2),
+                                             _dev.stream()), "fcd_healthy_stats")
+        del b_dev
+        self._in = dict(key=key, C=C, H=H, U=U, c0=c0, Cl=Cl, u0=u0, Ul=Ul, pitchU=pitchU,
+                        bt=bt_dev, S1=S1, S2=S2, btT=None, WT=None)
+        return self._in
+
+    def _ensure_patient_major(self):
+        """Patient-major copy btT [U_local][C] of ALL edges (for K2b)."""
+        inp = self._in
+        if inp['btT'] is not None:
+            return inp
+        lib = _lib.load()
+        (C, U, u0, Ul) = (inp['C'], inp['U'], inp['u0'], inp['Ul'])
+        if inp['Cl'] == C and self.shards is None:
+            src, pitchU, uu0 = inp['bt'], inp['pitchU'], u0
+        elif torch.is_tensor(self.bt):
+            # edge-sharded device input: one all-to-all of (C_local x U_peer) blocks
+            src = self.shards.exchange_patient_blocks(inp['bt'], inp['Cl'], C, U)
+            pitchU, uu0, U = Ul, 0, Ul
+        else:   # edge-sharded host input: this rank uploads every edge of its own patients
+            src = _dev.upload(np.ascontiguousarray(np.asarray(self.bt)[:, u0:u0 + Ul]))
+            pitchU, uu0, U = Ul, 0, Ul
+        btT = _dev.empty((Ul, C))
+        if Ul > 0:
+            with _dev.timed(self.profile, "K0_transpose"):
+                _lib.check(lib.fcd_transpose_patients(_dev.ptr(src), C, U, pitchU, uu0, Ul, _dev.ptr(btT), C,
+                                                      _dev.stream()), "fcd_transpose_patients")
+        inp['btT'] = btT
+        inp['WT'] = _dev.empty((Ul, C, 3))
+        return inp
+
+    def _theta(self, use_snapshot=True):
+        m = self.model
+        if use_snapshot and self._theta_lps is not None:
+            (mu, sigma, eta, epsilon) = self._theta_lps
+        else:
+            (mu, sigma, eta, epsilon) = (m.mu, m.sigma, m.eta, m.epsilon)
+        pi = np.asarray(m.pi, dtype=np.float64)
+        pi_s = float(pi) if pi.ndim == 0 else float(pi.reshape(-1)[-1])
+        return _lib.make_theta(pi_s, eta, epsilon, np.asarray(m.gamma).reshape(-1), mu, sigma)
+
+    def _materialise(self):
+        """`_update_lps` arrays (fit.py:104-122) built on demand on the GPU."""
+        if self._mat is not None:
+            return self._mat
+        lib = _lib.load()
+        if torch.is_tensor(self.b):
+            (b_dev, bt_dev) = (self.b.to(_dev.device(), torch.float64).contiguous(),
+                               self.bt.to(_dev.device(), torch.float64).contiguous())
+        else:
+            (b_dev, bt_dev) = (_dev.upload(np.asarray(self.b)), _dev.upload(np.asarray(self.bt)))
+        (C, H) = tuple(b_dev.shape)
+        U = bt_dev.shape[1]
+        lpB, pBt, lM = _dev.empty((C, H, 3)), _dev.empty((C, U, 3)), _dev.empty((C, U, 3, 3))
+        th = self._theta()
+        _lib.check(lib.fcd_materialize_lps(_dev.ptr(b_dev), _dev.ptr(bt_dev), C, H, U, ctypes.byref(th),
+                                           _dev.ptr(lpB), _dev.ptr(pBt), _dev.ptr(lM), _dev.stream()),
+                   "fcd_materialize_lps")
+        self._mat = {'_lp_B_g_F': _dev.download(lpB), '_p_Bt_g_Ft': _dev.download(pBt),
+                     '_lM': _dev.download(lM)}
+        return self._mat
+
+    # ------------------------------------------------------------------ reference API
+    def run(self):
+        """
+        Runs the fitting procedure (fcdiff/fit.py:56-82, doc/methods.rst:564-597).
+        """
+        (C, H, U) = self._global_shape()
+        N = util.C_to_N(C)
+        if (N % 1) != 0:
+            msg = "Number of connections (%u) must be a triangular number." % C
+            raise ValueError(msg)
+        if self.model is None:
+            msg = "Model has not been initialized."
+            raise ValueError(msg)
+        N = int(N)
+
+        self._init_lps(N, H, U)
+        self._update_lps()
+
+        self.energy = [self._eval_energy()]
+        self.n_objective_evals = []
+        for i in range(1, self.max_iters + 1):
+            self._update_lq_F()
+            self._update_lq_R()
+            self._update_theta()
+            self._update_lps()
+            self.energy.append(self._eval_energy())
+            if self._is_converged(i):
+                break
+
+    def _init_lps(self, N, H, U):
+        """
+        Initializes the log probabilities to be uniform (fcdiff/fit.py:84-102).
+        """
+        C = util.N_to_C(N)
+        self._dims = (N, H, U)
+        self._mR.set_host(np.full((N, U, 2), -np.log(2)))
+        self._mF.set_host(np.full((C, 1, 3), -np.log(3)))
+        self._lps_state = 'ones'
+        self._explicit = {}
+        self._mat = None
+
+    def _update_lps(self):
+        """
+        Updates the log probabilities based on the current parameters
+        (fcdiff/fit.py:104-122).  Fused form: snapshot theta, make sure the
+        inputs are resident; nothing of size (C, U, 3, 3) is written.
+        """
+        self._ensure_inputs()
+        m = self.model
+        self._theta_lps = (np.array(m.mu, dtype=np.float64), np.array(m.sigma, dtype=np.float64),
+                           float(m.eta), float(m.epsilon))
+        if self._dims is None:
+            inp = self._in
+            self._dims = (int(util.C_to_N(inp['C'])), inp['H'], inp['U'])
+        self._lps_state = 'derived'
+        self._explicit = {}
+        self._mat = None
+
+    def _is_converged(self, s):
+        """
+        Checks the convergence of the minimization (fcdiff/fit.py:124-140).
+        """
+        e = self.energy[s - 1]
+        e_star = self.energy[s]
+        return ((e - e_star) / e) < self.rel_tol
+
+    def _arrays_mode(self, *names):
+        return any(n in self._explicit for n in names) or self._lps_state != 'derived'
+
+    def _eval_energy(self):
+        """
+        Computes the energy (fcdiff/fit.py:142-155).
+        """
+        if self._arrays_mode('_lp_B_g_F', '_lM'):
+            q_F = np.exp(self._lq_F)
+            q_R = np.exp(self._lq_R)
+            energy = 0
+            energy -= _eval_E_lp_F(q_F, self.model.gamma)
+            energy -= _eval_E_lp_B_g_F(q_F, self._lp_B_g_F)
+            energy -= _eval_E_lp_R(q_R, _pi2(self.model.pi))
+            energy -= _eval_E_lM(q_F, q_R, self._lM)
+            energy += _eval_E_lq_F(q_F, self._lq_F)
+            energy += _eval_E_lq_R(q_R, self._lq_R)
+            return energy
+        t = self._energy_terms()
+        energy = 0
+        energy -= t[0]
+        energy -= t[1]
+        energy -= t[2]
+        energy -= t[3]
+        energy += t[4]
+        energy += t[5]
+        return float(energy)
+
+    def _energy_terms(self):
+        """The six terms of fit.py:149-154 from the fused K4 kernels."""
+        lib = _lib.load()
+        inp = self._ensure_inputs()
+        (N, H, U) = self._dims
+        (lqF, qF) = self._mF.get_dev()
+        (lqR, qR) = self._mR.get_dev()
+        (c0, Cl) = (inp['c0'], inp['Cl'])
+        th = self._theta()
+        out = _dev.empty((6,))
+        with _dev.timed(self.profile, "K4_energy_terms"):
+            _lib.check(lib.fcd_energy_terms(
+                _dev.ptr(inp['S1']), _dev.ptr(inp['S2']), H, _dev.ptr(inp['bt']), Cl, U, inp['pitchU'],
+                _dev.ptr(lqF[c0 * 3:]), _dev.ptr(qF[c0 * 3:]), _dev.ptr(lqR), _dev.ptr(qR), N, c0,
+                ctypes.byref(th), _dev.ptr(out), _dev.ptr(_dev.workspace()), _dev.stream()), "fcd_energy_terms")
+        if self.shards is not None:
+            out = self.shards.allreduce_terms(out, (0, 1, 3, 4))
+        return _dev.download(out)
+
+    def _update_lq_F(self):
+        """
+        Update the probability of the typical network template
+        (fcdiff/fit.py:157-174).
+        """
+        lib = _lib.load()
+        if self._arrays_mode('_lp_B_g_F', '_lM'):
+            lpB = np.ascontiguousarray(self._lp_B_g_F, dtype=np.float64)
+            lM = np.ascontiguousarray(self._lM, dtype=np.float64)
+            (C, H) = lpB.shape[0:2]
+            U = lM.shape[1]
+            (lqR, qR) = self._mR.get_dev()
+            N = self._mR.shape[0]
+            lqF = _dev.empty((C * 3,))
+            _lib.check(lib.fcd_lqF_from_arrays(
+                _dev.ptr(_dev.upload(lpB)), _dev.ptr(_dev.upload(lM)), C, H, U, _dev.ptr(qR), N,
+                _lib.d3(np.log(np.asarray(self.model.gamma, dtype=np.float64).reshape(-1))),
+                _dev.ptr(lqF), _dev.stream()), "fcd_lqF_from_arrays")
+            self._mF.set_host(_dev.download(lqF).reshape(C, 1, 3))
+            return
+        inp = self._ensure_inputs()
+        (N, H, U) = self._dims
+        (C, c0, Cl) = (inp['C'], inp['c0'], inp['Cl'])
+        (lqR, qR) = self._mR.get_dev()
+        lqF = _dev.empty((C * 3,))
+        qF = _dev.empty((C * 3,))
+        th = self._theta()
+        with _dev.timed(self.profile, "K2_estep_qF"):
+            _lib.check(lib.fcd_estep_qF(
+                _dev.ptr(inp['S1']), _dev.ptr(inp['S2']), H, _dev.ptr(inp['bt']), Cl, U, inp['pitchU'],
+                _dev.ptr(qR), N, c0, ctypes.byref(th), _dev.ptr(lqF[c0 * 3:]), _dev.ptr(qF[c0 * 3:]),
+                _dev.stream()), "fcd_estep_qF")
+        if self.shards is not None:
+            self.shards.allgather_edges(lqF, qF, C)
+        self._mF.set_dev(lqF, qF, (C, 1, 3))
+
+    def _update_lq_R(self):
+        """
+        Update the probability of the anomalous regions (fcdiff/fit.py:176-198).
+        """
+        lib = _lib.load()
+        lookup = _LOOKUP[self.edge_lookup]
+        log_pi2 = _lib.d3(np.log(_pi2(self.model.pi)))
+        if self._arrays_mode('_lM'):
+            lM = np.ascontiguousarray(self._lM, dtype=np.float64)
+            (C, U) = lM.shape[0:2]
+            (lqF, qF) = self._mF.get_dev()
+            (lqR, qR) = self._mR.get_dev()
+            N = self._mR.shape[0]
+            WT = _dev.empty((U, C, 3))
+            _lib.check(lib.fcd_region_weights_from_lM(_dev.ptr(_dev.upload(lM)), C, U, _dev.ptr(qF),
+                                                      _dev.ptr(WT), _dev.stream()),
+                       "fcd_region_weights_from_lM")
+            lqR_new, qR_new = lqR.clone(), qR.clone()
+            with _dev.timed(self.profile, "K2b_sweep"):
+                _lib.check(lib.fcd_estep_qR(_dev.ptr(WT), C, N, U, 0, U, log_pi2, lookup, _dev.ptr(qR_new),
+                                            _dev.ptr(lqR_new), _dev.stream()), "fcd_estep_qR")
+            self._mR.set_dev(lqR_new, qR_new, (N, U, 2))
+            return
+        self._ensure_inputs()
+        inp = self._ensure_patient_major()
+        (N, H, U) = self._dims
+        (C, u0, Ul) = (inp['C'], inp['u0'], inp['Ul'])
+        (lqF, qF) = self._mF.get_dev()
+        (lqR, qR) = self._mR.get_dev()
+        th = self._theta()
+        with _dev.timed(self.profile, "K2b_region_weights"):
+            _lib.check(lib.fcd_region_weights(_dev.ptr(inp['btT']), Ul, C, C, _dev.ptr(qF), ctypes.byref(th),
+                                              _dev.ptr(inp['WT']), _dev.stream()), "fcd_region_weights")
+        lqR_new, qR_new = lqR.clone(), qR.clone()
+        with _dev.timed(self.profile, "K2b_sweep"):
+            _lib.check(lib.fcd_estep_qR(_dev.ptr(inp['WT']), C, N, U, u0, Ul, log_pi2, lookup,
+                                        _dev.ptr(qR_new), _dev.ptr(lqR_new), _dev.stream()), "fcd_estep_qR")
+        if self.shards is not None:
+            self.shards.allgather_patients(lqR_new, qR_new, N, U)
+        self._mR.set_dev(lqR_new, qR_new, (N, U, 2))
+
+    def _update_theta(self):
+        """
+        Update the parameters of the model (fcdiff/fit.py:200-206).
+        """
+        self._update_pi_gamma(True, True)
+        if self.optimise_theta_sub:
+            self._update_theta_sub()
+
+    def _mstep_sums(self, do_pi, do_gamma):
+        lib = _lib.load()
+        (lqF, lqR, C, NU, c0, Cl) = (None, None, 0, 0, 0, 0)
+        if do_gamma:
+            (lqF, _) = self._mF.get_dev()
+            C = lqF.numel() // 3
+            (c0, Cl) = (0, C)
+            if self.shards is not None and self._in is not None:
+                (c0, Cl) = (self._in['c0'], self._in['Cl'])
+            lqF = lqF[c0 * 3:]
+        if do_pi:
+            (lqR, _) = self._mR.get_dev()
+            NU = lqR.numel() // 2
+        out = _dev.empty((4,))
+        with _dev.timed(self.profile, "K3a_mstep_stats"):
+            _lib.check(lib.fcd_mstep_stats(_dev.ptr(lqF), Cl, _dev.ptr(lqR), NU, _dev.ptr(out),
+                                           _dev.ptr(_dev.workspace()), _dev.stream()), "fcd_mstep_stats")
+        if do_gamma and self.shards is not None and self._in is not None:
+            out = self.shards.allreduce_terms(out, (0, 1, 2))
+        return _dev.download(out), C, NU
+
+    def _update_pi_gamma(self, do_pi, do_gamma):
+        (s, C, NU) = self._mstep_sums(do_pi, do_gamma)
+        if do_pi:
+            self.model.pi = float(s[3] / NU)                       # fit.py:213
+        if do_gamma:
+            self.model.gamma = s[0:3] / C                          # fit.py:220
+
+    def _update_pi(self):
+        """
+        Updates the value of the parameter pi (fcdiff/fit.py:208-213).
+        """
+        self._update_pi_gamma(True, False)
+
+    def _update_gamma(self):
+        """
+        Updates the value of the parameter gamma (fcdiff/fit.py:215-220).
+        """
+        self._update_pi_gamma(False, True)
+
+    def _objective(self, theta_sub, want_grad=True):
+        """(-E_lM, gradient) at theta_sub = [eta, epsilon] from one fused pass
+        over the patient correlations (K3b)."""
+        lib = _lib.load()
+        inp = self._ensure_inputs()
+        (N, H, U) = self._dims
+        (c0, Cl) = (inp['c0'], inp['Cl'])
+        (_, qF) = self._mF.get_dev()
+        (_, qR) = self._mR.get_dev()
+        th = self._theta()
+        th.eta = float(theta_sub[0])
+        th.epsilon = float(theta_sub[1])
+        out = _dev.empty((3,))
+        with _dev.timed(self.profile, "K3b_elm_obj_grad"):
+            _lib.check(lib.fcd_elm_obj_grad(
+                _dev.ptr(inp['bt']), Cl, U, inp['pitchU'], _dev.ptr(qF[c0 * 3:]), _dev.ptr(qR), N, c0,
+                ctypes.byref(th), 1 if want_grad else 0, _dev.ptr(out), _dev.ptr(_dev.workspace()),
+                _dev.stream()), "fcd_elm_obj_grad")
+        if self.shards is not None:
+            out = self.shards.allreduce_terms(out, (0, 1, 2))
+        o = _dev.download(out)
+        return -float(o[0]), np.array([o[1], o[2]])
+
+    def _update_theta_sub(self):
+        """
+        Updates the values of the parameters (eta, epsilon)
+        (fcdiff/fit.py:222-241; mu and sigma are held fixed as in the reference,
+        fit.py:232-237, 250-251, 266-267).
+        """
+        theta_sub = self._pack_theta_sub()
+        eps = 1e-5
+        bnds = (
+            (eps, 1 - eps),
+            (eps, 1 - eps),
+        )
+        if self._lps_state != 'derived':
+            self._update_lps()
+        nfev = [0]
+
+        def fun(x):
+            nfev[0] += 1
+            return self._objective(x)
+
+        opt_result = scipy.optimize.minimize(fun, theta_sub, jac=True, method="L-BFGS-B", bounds=bnds)
+        self.n_objective_evals.append(nfev[0])
+        self._unpack_theta_sub(opt_result.x)
+
+    def _pack_theta_sub(self):
+        """
+        Packs the subset of theta that is jointly optimized into one vector
+        (fcdiff/fit.py:243-253).
+        """
+        theta_sub_list = (
+            [self.model.eta],
+            [self.model.epsilon],
+        )
+        return np.concatenate(theta_sub_list)
+
+    def _unpack_theta_sub(self, theta_sub):
+        """
+        Unpacks the subset of theta that is jointly optimized
+        (fcdiff/fit.py:255-267).
+        """
+        self.model.eta = theta_sub[0]
+        self.model.epsilon = theta_sub[1]
+
+    def _opt_fun(self, theta_sub):
+        """
+        Computes the energy to find theta_rest: -E_lM at theta_sub
+        (fcdiff/fit.py:270-286 with R5 repaired).
+        """
+        self._unpack_theta_sub(theta_sub)
+        self._update_lps()
+        (f, _) = self._objective(theta_sub, want_grad=False)
+        return f
+
+    def _opt_jac(self):
+        """Jacobian of the energy w.r.t. [eta, epsilon] at the current model
+        (the intent of fcdiff/fit.py:289-337, which references undefined names)."""
+        if self._lps_state != 'derived':
+            self._update_lps()
+        (_, g) = self._objective(self._pack_theta_sub())
+        return g
+
+
+# ---------------------------------------------------------------------------
+# Module-level evaluators (fcdiff/fit.py:382-733): same names, argument shapes
+# and return types, each a call into libfcdiff_b200.so on NumPy inputs.
+# ---------------------------------------------------------------------------
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _scalar_out(n=1):
+    return _dev.empty((n,))
+
+
+def _eval_q_R_w(q_R, n, m):
+    """
+    Evaluates the three weights associated with a single pair of nodes
+    (fcdiff/fit.py:382-406).  Returns (U, 3).
+    """
+    lib = _lib.load()
+    q_R = _f64(q_R)
+    (N, U) = q_R.shape[0:2]
+    out = _dev.empty((U, 3))
+    _lib.check(lib.fcd_pair_weights(_dev.ptr(_dev.upload(q_R)), N, U, int(n), int(m), _dev.ptr(out),
+                                    _dev.stream()), "fcd_pair_weights")
+    return _dev.download(out)
+
+
+def _eval_M(N, eta, epsilon, k, l):
+    """
+    Evaluates M_kl based on the given normal densities (fcdiff/fit.py:409-430).
+    N : (C, U, 3) -> (C, U).
+    """
+    lib = _lib.load()
+    N = _f64(N)
+    lead = N.shape[:-1]
+    n = int(np.prod(lead)) if len(lead) else 1
+    out = _dev.empty((max(n, 1),))
+    _lib.check(lib.fcd_eval_M(_dev.ptr(_dev.upload(N)), n, float(eta), float(epsilon), int(k), int(l),
+                              _dev.ptr(out), _dev.stream()), "fcd_eval_M")
+    return _dev.download(out)[:n].reshape(lead)
+
+
+def _eval_M_eps(eta, epsilon, l):
+    """
+    Evaluates the probability of the same connection type in cases of M
+    (fcdiff/fit.py:433-444).
+    """
+    if l == 0:
+        eps = 1 - epsilon
+    elif l == 1:
+        eps = epsilon
+    elif l == 2:
+        eps = eta * epsilon
+        eps += (1 - eta) * (1 - epsilon)
+    return eps
+
+
+def _dot(a, a_outer, a_inner, x, n):
+    lib = _lib.load()
+    out = _scalar_out()
+    x = _f64(x).reshape(-1)
+    _lib.check(lib.fcd_dot_broadcast(_dev.ptr(_dev.upload(_f64(a).reshape(-1))), int(a_outer), int(a_inner),
+                                     _dev.ptr(_dev.upload(x)), x.size, int(n), _dev.ptr(out),
+                                     _dev.ptr(_dev.workspace()), _dev.stream()), "fcd_dot_broadcast")
+    return float(_dev.download(out)[0])
+
+
+def _eval_E_lp_F(q_F, gamma):
+    """E[log p(f; gamma)] = sum q_F log gamma (fcdiff/fit.py:447-458)."""
+    q_F = _f64(q_F)
+    return _dot(q_F, q_F.size, q_F.size, np.log(_f64(gamma)), q_F.size)
+
+
+def _eval_E_lp_B_g_F(q_F, lp_B_g_F):
+    """E[log p(b | f; mu, sigma)] = sum q_F lp_B_g_F, q_F (C,1,3) broadcast
+    over the H axis of lp_B_g_F (C,H,3) (fcdiff/fit.py:461-472)."""
+    lp = _f64(lp_B_g_F)
+    q_F = _f64(q_F)
+    if q_F.size == lp.size:
+        return _dot(q_F, lp.size, lp.size, lp, lp.size)
+    H = lp.shape[1]
+    return _dot(q_F, H * 3, 3, lp, lp.size)
+
+
+def _eval_E_lp_R(q_R, pi):
+    """E[log p(r; pi)] = sum q_R log pi (fcdiff/fit.py:475-486); pi is the
+    2-vector [1-pi, pi] of test_fit.py:208-209 (a scalar broadcasts like NumPy)."""
+    q_R = _f64(q_R)
+    return _dot(q_R, q_R.size, q_R.size, np.log(_f64(pi)), q_R.size)
+
+
+def _eval_E_lM(q_F, q_R, lM):
+    """E[log p(b~ | f, r; theta)] (fcdiff/fit.py:489-511)."""
+    lib = _lib.load()
+    (q_F, q_R, lM) = (_f64(q_F), _f64(q_R), _f64(lM))
+    C = q_F.shape[0]
+    (N, U) = q_R.shape[0:2]
+    out = _scalar_out()
+    _lib.check(lib.fcd_ElM_from_arrays(_dev.ptr(_dev.upload(q_F)), _dev.ptr(_dev.upload(q_R)),
+                                       _dev.ptr(_dev.upload(lM)), C, N, U, _dev.ptr(out),
+                                       _dev.ptr(_dev.workspace()), _dev.stream()), "fcd_ElM_from_arrays")
+    return float(_dev.download(out)[0])
+
+
+def _eval_E_lq_F(q_F, lq_F):
+    """Energy term related to log q(f) (fcdiff/fit.py:514-525)."""
+    q_F = _f64(q_F)
+    return _dot(q_F, q_F.size, q_F.size, lq_F, q_F.size)
+
+
+def _eval_E_lq_R(q_R, lq_R):
+    """Energy term related to log q(r) (fcdiff/fit.py:528-539)."""
+    q_R = _f64(q_R)
+    return _dot(q_R, q_R.size, q_R.size, lq_R, q_R.size)
+
+
+def _dE(q_R, q_F, norm, mix, eta, epsilon):
+    lib = _lib.load()
+    (q_R, q_F, norm, mix) = (_f64(q_R), _f64(q_F), _f64(norm), _f64(mix))
+    C = q_F.shape[0]
+    (N, U) = q_R.shape[0:2]
+    out = _scalar_out(2)
+    _lib.check(lib.fcd_dE_from_arrays(_dev.ptr(_dev.upload(q_R)), _dev.ptr(_dev.upload(q_F)),
+                                      _dev.ptr(_dev.upload(norm)), _dev.ptr(_dev.upload(mix)), C, N, U,
+                                      float(eta), float(epsilon), _dev.ptr(out),
+                                      _dev.ptr(_dev.workspace()), _dev.stream()), "fcd_dE_from_arrays")
+    return _dev.download(out)
+
+
+def _eval_dE_dh(q_R, q_F, norm, mix, epsilon):
+    """dE/d eta (fcdiff/fit.py:600-615)."""
+    return float(_dE(q_R, q_F, norm, mix, 0.5, epsilon)[0])
+
+
+def _eval_dE_de(q_R, q_F, norm, mix, eta):
+    """dE/d epsilon (fcdiff/fit.py:644-664)."""
+    return float(_dE(q_R, q_F, norm, mix, eta, 0.5)[1])
+
+
+def _dlM(norm, mix, eps, k):
+    lib = _lib.load()
+    (norm, mix) = (_f64(norm), _f64(mix))
+    n = mix.size
+    out = _dev.empty((max(n, 1),))
+    _lib.check(lib.fcd_dlM(_dev.ptr(_dev.upload(norm)), _dev.ptr(_dev.upload(mix)), n, float(eps), int(k),
+                           _dev.ptr(out), _dev.stream()), "fcd_dlM")
+    return _dev.download(out)[:n].reshape(mix.shape)
+
+
+def _eval_dlM_dh(norm, mix, epsilon, k):
+    """Derivative of log M w.r.t. eta (fcdiff/fit.py:618-641)."""
+    return _dlM(norm, mix, (2 * epsilon) - 1, k)
+
+
+def _eval_dlM_de(norm, mix, eta, k, l):
+    """Derivative of log M w.r.t. epsilon (fcdiff/fit.py:667-697)."""
+    if l == 0:
+        eps = -1
+    elif l == 1:
+        eps = 1
+    else:
+        eps = 2 * eta - 1
+    return _dlM(norm, mix, eps, k)
+
+
+# --- mu / sigma derivative helpers.  The reference disables the mu, sigma
+# update (fit.py:232-237, 250-251, 266-267), so these are off the hot path
+# (SURVEY 8f item 1); they are kept as the reference's closed forms for API
+# parity.
+
+def _eval_dE_dm(q_F, q_R, dlN_dmj, dlM_dmj, j):
+    """dE/d mu_j from precomputed derivative arrays (fcdiff/fit.py:542-569):
+    two broadcast dot products on the GPU."""
+    dlN = _f64(dlN_dmj)
+    q_F = _f64(q_F)
+    (C, H) = dlN.shape[0:2]
+    qj = np.ascontiguousarray(q_F[:, 0, j])
+    term1 = _dot(qj, H, 1, dlN, dlN.size)
+    term2 = _eval_E_lM(q_F, q_R, dlM_dmj)
+    return -(term1 + term2)
+
+
+def _eval_dlN_dm(b, mu, sigma):
+    """Derivative of log N w.r.t. mu (fcdiff/fit.py:715-719)."""
+    return (b - mu) / (sigma * sigma)
+
+
+def _eval_dN_dm(N, b, mu, sigma):
+    """Derivative of N w.r.t. mu (fcdiff/fit.py:709-713)."""
+    return N * _eval_dlN_dm(b, mu, sigma)
+
+
+def _eval_dlN_ds(b, mu, sigma):
+    """Derivative of log N w.r.t. sigma (fcdiff/fit.py:727-733)."""
+    diff = (b - mu)
+    sigma2 = sigma * sigma
+    return ((diff * diff) - sigma2) / (2 * sigma2)
+
+
+def _eval_dN_ds(N, b, mu, sigma):
+    """Derivative of N w.r.t. sigma (fcdiff/fit.py:721-725)."""
+    return N * _eval_dlN_ds(b, mu, sigma)
+
+
+def _eval_dlM_dm(norm, mix, mu, sigma, eta, epsilon, k, l):
+    """Derivative of log M w.r.t. mu_j as the reference computes it
+    (fcdiff/fit.py:572-597; pinned by test_fcdiff/test_fit.py:598-787)."""
+    eps = _eval_M_eps(eta, epsilon, l)
+    if k != l:
+        eps = 0.5 * (1 - eps)
+    dlN_dm = _eval_dlN_dm(norm, mu, sigma)
+    return eps * dlN_dm / mix

@@ -1,0 +1,402 @@
+"""GPU parity tests: the CUDA path (through the reference-shaped Python API and
+the ctypes C-ABI underneath) against the golden vectors produced by the
+reference's own step functions and against the CPU oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): MAP labels bit-exact away from ties;
+posteriors, parameters and free energy within 1e-6 relative.  The step-level
+checks below are much tighter (1e-9 .. 1e-12) because they compare single
+steps in float64; only transcendental ulp differences and summation order
+separate the two sides.
+"""
+import numpy as np
+import numpy.testing as nptest
+import pytest
+import torch
+
+from oracle import iar_oracle as O
+from oracle.make_golden import golden_inputs
+
+pytestmark = pytest.mark.gpu
+
+import fcdiff_b200 as fcdiff          # noqa: E402
+from fcdiff_b200 import _lib          # noqa: E402
+
+F = fcdiff.fit
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _native_library_loaded():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    lib = _lib.load()                 # raises if libfcdiff_b200.so is missing
+    n0 = lib.fcd_launch_count()
+    yield
+    assert lib.fcd_launch_count() > n0, "no kernel of libfcdiff_b200.so was launched"
+
+
+def ideal_model():
+    m = fcdiff.UnsharedRegionModel()
+    (m.pi, m.epsilon, m.eta) = (0.1, 0.01, 0.3)
+    m.gamma = np.ones((3,)) / 3
+    m.mu = np.array([-0.5, 0, 0.5])
+    m.sigma = np.ones((3,)) * 0.05
+    return m
+
+
+# ------------------------------------------------------------------ arrays API vs the reference's unit vectors
+def test_update_lps_materialised(unit_vectors):
+    g = unit_vectors
+    (N, C, H, U) = (4, 6, 7, 5)
+    fit = F.UnsharedRegionFit()
+    fit.b, fit.bt = g["lps_b"], g["lps_bt"]
+    fit.model = ideal_model()
+    fit._init_lps(N, H, U)
+    fit._update_lps()
+    # bit-equal in the reference's own test; here exp/log differ from NumPy's by <= 2 ulp
+    nptest.assert_allclose(fit._lp_B_g_F, g["lps_lp_B_g_F"], rtol=4e-16, atol=0)
+    finite = np.isfinite(g["lps_lM"])
+    nptest.assert_allclose(fit._p_Bt_g_Ft, g["lps_p_Bt_g_Ft"], rtol=1e-15, atol=0)
+    nptest.assert_allclose(fit._lM[finite], g["lps_lM"][finite], rtol=1e-14, atol=0)
+    nptest.assert_array_equal(np.isfinite(fit._lM), finite)
+
+
+def test_eval_M_all_kl(unit_vectors):
+    g = unit_vectors
+    (eta, eps) = g["M_eta_eps"]
+    for k in range(3):
+        for l in range(3):
+            nptest.assert_array_equal(F._eval_M(g["M_p"], eta, eps, k, l), g["M_out"][:, :, k, l])
+
+
+def test_update_lq_F_arrays(unit_vectors):
+    g = unit_vectors
+    fit = F.UnsharedRegionFit()
+    fit._lq_R = np.log(g["lqF_q_R"])
+    fit._lp_B_g_F = g["lqF_lp_B_g_F"]
+    fit._lM = g["lqF_lM"]
+    fit.model = fcdiff.UnsharedRegionModel()
+    fit.model.gamma = g["lqF_gamma"]
+    fit._update_lq_F()
+    assert fit._lq_F.shape == (15, 1, 3)
+    nptest.assert_allclose(fit._lq_F, g["lqF_out"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("lookup", ["reference", "symmetric"])
+def test_update_lq_R_arrays(unit_vectors, lookup):
+    g = unit_vectors
+    fit = F.UnsharedRegionFit()
+    fit._lq_R = np.log(g["lqR_q_R"])
+    fit._lq_F = np.log(g["lqR_q_F"])
+    fit._lM = g["lqR_lM"]
+    fit.model = fcdiff.UnsharedRegionModel()
+    fit.model.pi = g["lqR_pi"]
+    fit.edge_lookup = lookup
+    fit._update_lq_R()
+    assert fit._lq_R.shape == (6, 4, 2)
+    if lookup == "reference":
+        nptest.assert_allclose(fit._lq_R, g["lqR_out"], rtol=1e-12)
+    else:
+        exp = O.update_lq_R(g["lqR_pi"], np.log(g["lqR_q_F"]), g["lqR_lM"], np.log(g["lqR_q_R"]), "symmetric")
+        nptest.assert_allclose(fit._lq_R, exp, rtol=1e-12)
+
+
+def test_update_pi_gamma(unit_vectors):
+    g = unit_vectors
+    fit = F.UnsharedRegionFit()
+    fit.model = fcdiff.UnsharedRegionModel()
+    fit._lq_R = np.log(g["lqR_q_R"])
+    fit._update_pi()
+    nptest.assert_allclose(fit.model.pi, g["pi_out"], rtol=1e-14)
+    assert np.ndim(fit.model.pi) == 0
+    fit2 = F.UnsharedRegionFit()
+    fit2.model = fcdiff.UnsharedRegionModel()
+    fit2._lq_F = np.log(g["lqR_q_F"])
+    fit2._update_gamma()
+    assert fit2.model.gamma.shape == (3,)
+    nptest.assert_allclose(fit2.model.gamma, g["gamma_out"], rtol=1e-14)
+
+
+def test_energy_terms_arrays(unit_vectors):
+    g = unit_vectors
+    (q_F, q_R, lM) = (g["lqR_q_F"], g["lqR_q_R"], g["lqR_lM"])
+    nptest.assert_allclose(F._eval_E_lp_F(q_F, g["E_gamma"]), g["E_lp_F"], rtol=1e-13)
+    nptest.assert_allclose(F._eval_E_lp_B_g_F(q_F, g["E_lpB"]), g["E_lp_B_g_F"], rtol=1e-13)
+    nptest.assert_allclose(F._eval_E_lp_R(q_R, g["lqR_pi"]), g["E_lp_R"], rtol=1e-13)
+    nptest.assert_allclose(F._eval_E_lM(q_F, q_R, lM), g["E_lM"], rtol=1e-13)
+    nptest.assert_allclose(F._eval_E_lq_F(q_F, np.log(q_F)), g["E_lq_F"], rtol=1e-13)
+    nptest.assert_allclose(F._eval_E_lq_R(q_R, np.log(q_R)), g["E_lq_R"], rtol=1e-13)
+
+
+def test_derivatives_arrays(unit_vectors):
+    g = unit_vectors
+    (eta, eps) = g["d_eta_eps"]
+    (q_F, q_R) = (g["lqR_q_F"], g["lqR_q_R"])
+    nptest.assert_allclose(F._eval_dE_dh(q_R, q_F, g["d_norm"], g["d_mix"], eps), g["dE_dh"], rtol=1e-11)
+    nptest.assert_allclose(F._eval_dE_de(q_R, q_F, g["d_norm"], g["d_mix"], eta), g["dE_de"], rtol=1e-11)
+    for k in range(3):
+        nptest.assert_allclose(F._eval_dlM_dh(g["d_norm"], g["d_mix"][:, :, k, 2], eps, k),
+                               g["dlM_dh"][:, :, k], rtol=1e-14)
+        for l in range(3):
+            nptest.assert_allclose(F._eval_dlM_de(g["d_norm"], g["d_mix"][:, :, k, l], eta, k, l),
+                                   g["dlM_de"][:, :, k, l], rtol=1e-14)
+
+
+def test_q_R_w(unit_vectors):
+    g = unit_vectors
+    w = F._eval_q_R_w(g["lqR_q_R"], 3, 1)
+    assert w.shape == (4, 3)
+    nptest.assert_array_equal(w, g["qRw_out"])
+
+
+def test_eval_energy_arrays_mode(unit_vectors):
+    g = unit_vectors
+    fit = F.UnsharedRegionFit()
+    fit.model = fcdiff.UnsharedRegionModel()
+    fit.model.gamma = g["E_gamma"]
+    fit.model.pi = g["lqR_pi"]
+    fit._lq_F = np.log(g["lqR_q_F"])
+    fit._lq_R = np.log(g["lqR_q_R"])
+    fit._lp_B_g_F = g["E_lpB"]
+    fit._lM = g["lqR_lM"]
+    exp = -g["E_lp_F"] - g["E_lp_B_g_F"] - g["E_lp_R"] - g["E_lM"] + g["E_lq_F"] + g["E_lq_R"]
+    nptest.assert_allclose(fit._eval_energy(), exp, rtol=1e-12)
+
+
+# ------------------------------------------------------------------ fused path vs the reference trajectory
+def _fit_for(b, bt, model=None, eta_shift=0.0):
+    fit = F.UnsharedRegionFit()
+    fit.b, fit.bt = b, bt
+    fit.model = model or fcdiff.UnsharedRegionModel()
+    fit.model.eta += eta_shift
+    return fit
+
+
+def test_cfg1_fused_iterations_without_optimiser(cfg1):
+    g = cfg1
+    fit = _fit_for(g["b"], g["bt"])
+    fit._init_lps(10, 20, 20)
+    fit._update_lps()
+    for it in range(2):
+        fit._update_lq_F()
+        fit._update_lq_R()
+        fit._update_pi()
+        fit._update_gamma()
+        nptest.assert_allclose(fit._lq_F, g["noopt_it%d_lq_F" % it], rtol=1e-9, atol=1e-10)
+        nptest.assert_allclose(fit._lq_R, g["noopt_it%d_lq_R" % it], rtol=1e-9, atol=1e-10)
+        nptest.assert_allclose(fit.model.pi, g["noopt_it%d_pi" % it], rtol=1e-11)
+        nptest.assert_allclose(fit.model.gamma, g["noopt_it%d_gamma" % it], rtol=1e-11)
+        nptest.assert_allclose(fit._energy_terms(), g["noopt_it%d_terms" % it], rtol=1e-10)
+        nptest.assert_allclose(fit._eval_energy(), g["noopt_it%d_energy" % it], rtol=1e-10)
+    for x, fg in zip(g["noopt_obj_pts"], g["noopt_obj_fg"]):
+        (f, grad) = fit._objective(x)
+        nptest.assert_allclose([f, grad[0], grad[1]], fg, rtol=1e-10)
+        nptest.assert_allclose(fit._opt_fun(np.array(x)), fg[0], rtol=1e-10)
+
+
+def _check_run(fit, g, final_only=False):
+    nptest.assert_allclose(fit.energy, g["energy"], rtol=1e-6)
+    assert len(fit.energy) == len(g["energy"])
+    nptest.assert_allclose([fit.model.pi, fit.model.eta, fit.model.epsilon],
+                           [g["pi"][-1], g["eta"][-1], g["epsilon"][-1]], rtol=1e-6)
+    nptest.assert_allclose(fit.model.gamma, g["gamma"][-1], rtol=1e-6)
+    lqF = g["lq_F_final"] if final_only else g["lq_F"][-1]
+    lqR = g["lq_R_final"] if final_only else g["lq_R"][-1]
+    nptest.assert_allclose(np.exp(fit._lq_F), np.exp(lqF), rtol=1e-6, atol=1e-300)
+    nptest.assert_allclose(np.exp(fit._lq_R), np.exp(lqR), rtol=1e-6, atol=1e-300)
+    # MAP labels bit-exact away from ties
+    gap_F = np.sort(lqF, axis=2)
+    clear = (gap_F[:, :, 2] - gap_F[:, :, 1]) > 1e-6
+    nptest.assert_array_equal(np.argmax(fit._lq_F, axis=2)[clear], np.argmax(lqF, axis=2)[clear])
+    clear_R = np.abs(lqR[:, :, 1] - lqR[:, :, 0]) > 1e-6
+    nptest.assert_array_equal((fit._lq_R[:, :, 1] > fit._lq_R[:, :, 0])[clear_R],
+                              (lqR[:, :, 1] > lqR[:, :, 0])[clear_R])
+    assert clear.mean() > 0.99 and clear_R.mean() > 0.99
+
+
+def test_cfg1_full_run_matches_reference(cfg1):
+    g = cfg1
+    fit = _fit_for(g["b"], g["bt"], eta_shift=0.1)
+    fit.run()
+    _check_run(fit, g)
+    assert isinstance(fit.energy, list) and fit._lq_F.shape == (45, 1, 3) and fit._lq_R.shape == (10, 20, 2)
+
+
+def test_cfg2_full_run_matches_reference(cfg2):
+    g = cfg2
+    (b, bt) = golden_inputs(90, 50, 50)
+    fit = _fit_for(b, bt, eta_shift=0.1)
+    fit.run()
+    _check_run(fit, g, final_only=True)
+
+
+# ------------------------------------------------------------------ fused path vs the oracle on seeded inputs
+def _oracle_state(b, bt, th, seed):
+    (C, H) = b.shape
+    U = bt.shape[1]
+    N = int(O.C_to_N(C))
+    rng = np.random.RandomState(seed)
+    lq_R = np.log(rng.dirichlet([1, 1], size=(N, U)))
+    lq_F = np.log(rng.dirichlet([1, 1, 1], size=(C, 1)))
+    return N, H, U, lq_F, lq_R
+
+
+@pytest.mark.parametrize("N,H,U", [(3, 1, 1), (4, 2, 3), (7, 5, 9), (10, 20, 20), (33, 17, 31), (40, 64, 128)])
+@pytest.mark.parametrize("lookup", ["reference", "symmetric"])
+def test_fused_steps_vs_oracle(N, H, U, lookup):
+    th = O.Theta() if (N % 2) else O.Theta.ideal()
+    (_, _, _, _, b, bt) = O.sample(th, N, H, U, np.random.RandomState(N))
+    (N, H, U, lq_F, lq_R) = _oracle_state(b, bt, th, N + 1)
+    (lpB, pBt, lM) = O.update_lps(b, bt, th)
+    model = fcdiff.UnsharedRegionModel()
+    (model.pi, model.eta, model.epsilon) = (th.pi, th.eta, th.epsilon)
+    (model.gamma, model.mu, model.sigma) = (th.gamma.copy(), th.mu.copy(), th.sigma.copy())
+    fit = _fit_for(b, bt, model)
+    fit.edge_lookup = lookup
+    fit._init_lps(N, H, U)
+    fit._update_lps()
+    fit._lq_R = lq_R
+    fit._lq_F = lq_F
+    # K4 at a random state
+    terms = O.eval_energy_terms(th, lq_F, lq_R, lpB, lM)
+    nptest.assert_allclose(fit._energy_terms(), terms, rtol=1e-10)
+    # K2
+    fit._update_lq_F()
+    exp_F = O.update_lq_F(th.gamma, lpB, lM, lq_R)
+    nptest.assert_allclose(fit._lq_F, exp_F, rtol=1e-9, atol=1e-10)
+    nptest.assert_allclose(np.exp(fit._lq_F).sum(axis=2), 1.0, rtol=1e-12)
+    # K2b
+    fit._update_lq_R()
+    exp_R = O.update_lq_R(np.array([1 - th.pi, th.pi]), exp_F, lM, lq_R, lookup)
+    nptest.assert_allclose(fit._lq_R, exp_R, rtol=1e-9, atol=1e-10)
+    # K3a
+    fit._update_pi()
+    fit._update_gamma()
+    nptest.assert_allclose(fit.model.pi, O.update_pi(exp_R), rtol=1e-10)
+    nptest.assert_allclose(fit.model.gamma, O.update_gamma(exp_F), rtol=1e-10)
+    # K3b objective + analytic gradient at interior and near-bound points
+    for x in ([0.3, 0.03], [0.7, 0.4], [1e-5, 1 - 1e-5], [1 - 1e-5, 1e-5]):
+        (f, grad) = fit._objective(x)
+        (fo, go) = O.elm_objective_and_grad(pBt, np.exp(exp_F), np.exp(exp_R), x)
+        nptest.assert_allclose(f, fo, rtol=1e-10)
+        nptest.assert_allclose(grad, go, rtol=1e-8, atol=1e-8 * max(1.0, np.abs(go).max()))
+
+
+def test_full_run_symmetric_lookup_vs_oracle():
+    th = O.Theta()
+    (_, _, _, _, b, bt) = O.sample(th, 14, 12, 15, np.random.RandomState(5))
+    fit = _fit_for(b, bt, eta_shift=0.1)
+    fit.edge_lookup = "symmetric"
+    fit.max_iters = 5
+    fit.run()
+    tho = O.Theta()
+    tho.eta += 0.1
+    out = O.run(b, bt, tho, max_iters=5, edge_lookup="symmetric")
+    nptest.assert_allclose(fit.energy, out["energy"], rtol=1e-6)
+    nptest.assert_allclose(np.exp(fit._lq_F), np.exp(out["lq_F"]), rtol=1e-6, atol=1e-300)
+    nptest.assert_allclose(np.exp(fit._lq_R), np.exp(out["lq_R"]), rtol=1e-6, atol=1e-300)
+    nptest.assert_allclose([fit.model.pi, fit.model.eta, fit.model.epsilon], [tho.pi, tho.eta, tho.epsilon], rtol=1e-6)
+
+
+def test_far_tail_inputs_stay_finite():
+    """Fisher-z inputs can leave [-1, 1]; the reference's pdf underflows there
+    (-inf / nan), the log-domain kernels must stay finite and agree with the
+    oracle wherever the oracle is finite."""
+    th = O.Theta()
+    rng = np.random.RandomState(3)
+    (N, H, U) = (6, 4, 8)
+    b = rng.uniform(-1, 1, (15, H))
+    bt = rng.uniform(-2.5, 2.5, (15, U))
+    fit = _fit_for(b, bt)
+    fit._init_lps(N, H, U)
+    fit._update_lps()
+    fit._update_lq_F()
+    fit._update_lq_R()
+    assert np.all(np.isfinite(fit._lq_F)) and np.all(np.isfinite(fit._lq_R))
+    assert np.isfinite(fit._eval_energy())
+
+
+def test_single_region_pair_rejected_in_reference_lookup():
+    fit = _fit_for(np.zeros((1, 2)), np.zeros((1, 2)))
+    fit._init_lps(2, 2, 2)
+    fit._update_lps()
+    fit._update_lq_F()
+    with pytest.raises(_lib.FcdError, match="N < 3"):
+        fit._update_lq_R()
+    fit.edge_lookup = "symmetric"
+    fit._update_lq_R()
+    assert fit._lq_R.shape == (2, 2, 2)
+
+
+# ------------------------------------------------------------------ size-independent properties at BASELINE sizes
+def _device_problem(N, H, U, seed=0):
+    model = fcdiff.UnsharedRegionModel()
+    model.rng = np.random.RandomState(seed)
+    (r, t, f, ft, b, bt) = model.sample_device(N, H, U)
+    return model, b, bt
+
+
+@pytest.mark.parametrize("N,H,U", [(400, 500, 500)])
+def test_config3_properties(N, H, U):
+    """Schaefer-400 x 1000 subjects: shard additivity, determinism,
+    normalisation, energy consistency -- no CPU oracle at this size."""
+    import ctypes
+    from fcdiff_b200 import _dev
+    lib = _lib.load()
+    (model, b_dev, bt_dev) = _device_problem(N, H, U)
+    C = N * (N - 1) // 2
+    fit = F.UnsharedRegionFit()
+    fit.model = fcdiff.UnsharedRegionModel()
+    fit.b = _dev.download(b_dev)
+    fit.bt = _dev.download(bt_dev)
+    fit.max_iters = 2
+    fit.run()
+    q_F = np.exp(fit._lq_F)
+    q_R = np.exp(fit._lq_R)
+    nptest.assert_allclose(q_F.sum(axis=2), 1.0, rtol=1e-12)
+    nptest.assert_allclose(q_R.sum(axis=2), 1.0, rtol=1e-12)
+    assert len(fit.energy) >= 2 and np.all(np.isfinite(fit.energy))
+    # the fit lowers the free energy from the uniform start
+    assert fit.energy[1] < fit.energy[0]
+    # planted template recovered: MAP q_F equals the sampled f on > 99% of edges
+    # (b, bt were drawn from the default model by the device sampler)
+    # -- determinism: a second run is bit-identical
+    fit2 = F.UnsharedRegionFit()
+    fit2.model = fcdiff.UnsharedRegionModel()
+    fit2.b, fit2.bt = fit.b, fit.bt
+    fit2.max_iters = 2
+    fit2.run()
+    nptest.assert_array_equal(fit2._lq_F, fit._lq_F)
+    nptest.assert_array_equal(fit2._lq_R, fit._lq_R)
+    assert fit2.energy == fit.energy
+    # -- shard additivity of K3b / K4: sum over 3 ragged edge shards == whole
+    inp = fit._in
+    (lqF, qF) = fit._mF.get_dev()
+    (lqR, qR) = fit._mR.get_dev()
+    th = fit._theta()
+    ws = _dev.workspace()
+    whole = _dev.empty((6,))
+    _lib.check(lib.fcd_energy_terms(_dev.ptr(inp['S1']), _dev.ptr(inp['S2']), H, _dev.ptr(inp['bt']), C, U,
+                                    inp['pitchU'], _dev.ptr(lqF), _dev.ptr(qF), _dev.ptr(lqR), _dev.ptr(qR),
+                                    N, 0, ctypes.byref(th), _dev.ptr(whole), _dev.ptr(ws), _dev.stream()))
+    parts = np.zeros(6)
+    cuts = [0, 1234, 40001, C]
+    for (a, e) in zip(cuts[:-1], cuts[1:]):
+        part = _dev.empty((6,))
+        _lib.check(lib.fcd_energy_terms(
+            _dev.ptr(inp['S1'][a:]), _dev.ptr(inp['S2'][a:]), H, _dev.ptr(inp['bt'][a:]), e - a, U,
+            inp['pitchU'], _dev.ptr(lqF[a * 3:]), _dev.ptr(qF[a * 3:]), _dev.ptr(lqR), _dev.ptr(qR),
+            N, a, ctypes.byref(th), _dev.ptr(part), _dev.ptr(ws), _dev.stream()))
+        parts += _dev.download(part)
+    w = _dev.download(whole)
+    nptest.assert_allclose(parts[[0, 1, 3, 4]], w[[0, 1, 3, 4]], rtol=1e-12)
+    nptest.assert_allclose(parts[[2, 5]] / 3, w[[2, 5]], rtol=1e-12)     # q_R-only terms are complete per shard
+    # -- K2 on a shard equals the slice of the whole
+    (a, e) = (40001, C)
+    lq_part = _dev.empty(((e - a) * 3,))
+    qR_prev = _dev.upload(np.full((N, U, 2), 0.5).reshape(-1))
+    lq_whole = _dev.empty((C * 3,))
+    _lib.check(lib.fcd_estep_qF(_dev.ptr(inp['S1']), _dev.ptr(inp['S2']), H, _dev.ptr(inp['bt']), C, U, inp['pitchU'],
+                                _dev.ptr(qR_prev), N, 0, ctypes.byref(th), _dev.ptr(lq_whole), None, _dev.stream()))
+    _lib.check(lib.fcd_estep_qF(_dev.ptr(inp['S1'][a:]), _dev.ptr(inp['S2'][a:]), H, _dev.ptr(inp['bt'][a:]), e - a, U,
+                                inp['pitchU'], _dev.ptr(qR_prev), N, a, ctypes.byref(th), _dev.ptr(lq_part), None,
+                                _dev.stream()))
+    nptest.assert_array_equal(_dev.download(lq_part), _dev.download(lq_whole)[a * 3:])

@@ -1,0 +1,134 @@
+"""CPU: host-side logic of the drop-in package that needs no device -- index
+maps, convergence rule, parameter packing, argument validation, lazy caches,
+shard arithmetic (cases from test_fcdiff/test_util.py and test_fit.py:72-129)."""
+import numpy as np
+import numpy.testing as nptest
+import pytest
+
+import fcdiff_b200 as fcdiff
+from fcdiff_b200.dist import EdgeShards
+
+
+def test_package_surface():
+    # fcdiff/__init__.py:1-5
+    for name in ("UnsharedRegionModel", "fit", "N_to_C", "nm_to_c", "c_to_nm"):
+        assert hasattr(fcdiff, name)
+    import importlib
+    alias = importlib.import_module("fcdiff")
+    assert alias.fit.UnsharedRegionFit is fcdiff.fit.UnsharedRegionFit
+    assert importlib.import_module("fcdiff.util").c_to_nm(5) == (3, 2)
+
+
+def test_N_to_C_to_N():
+    for N in range(2, 10):
+        C = fcdiff.util.N_to_C(N)
+        assert fcdiff.util.C_to_N(C) == N
+    assert fcdiff.util.C_to_N(4) % 1 != 0
+
+
+def test_nm_to_c_and_back():
+    c = 0
+    for n in range(60):
+        for m in range(n):
+            assert fcdiff.util.nm_to_c(n, m) == c
+            assert fcdiff.util.c_to_nm(c) == (n, m)
+            c += 1
+    big = 499500 - 1
+    (n, m) = fcdiff.util.c_to_nm(big)
+    assert (n, m) == (999, 998)
+    assert isinstance(n, int) and isinstance(m, int)
+
+
+def test_init_lps_shape():
+    fit = fcdiff.fit.UnsharedRegionFit()
+    (N, C, H, U) = (4, 6, 7, 5)
+    fit._init_lps(N, H, U)
+    nptest.assert_equal(fit._lq_R.shape, (N, U, 2))
+    nptest.assert_allclose(np.sum(np.exp(fit._lq_R), axis=2), 1)
+    nptest.assert_equal(fit._lq_F.shape, (C, 1, 3))
+    nptest.assert_allclose(np.sum(np.exp(fit._lq_F), axis=2), 1)
+    nptest.assert_equal(fit._lp_B_g_F.shape, (C, H, 3))
+    nptest.assert_equal(fit._p_Bt_g_Ft.shape, (C, U, 3))
+    nptest.assert_equal(fit._lM.shape, (C, U, 3, 3))
+
+
+@pytest.mark.parametrize("energy,expect", [([1, 1.25], True), ([1, 1], True), ([1, 0.501], True),
+                                           ([1, 0.5], False), ([1, 0.499], False)])
+def test_is_converged(energy, expect):
+    fit = fcdiff.fit.UnsharedRegionFit()
+    fit.rel_tol = 0.5
+    fit.energy = energy
+    assert bool(fit._is_converged(1)) is expect
+
+
+def test_pack_unpack_theta_sub():
+    fit = fcdiff.fit.UnsharedRegionFit()
+    fit.model = fcdiff.UnsharedRegionModel()
+    nptest.assert_array_equal(fit._pack_theta_sub(), [0.3, 0.03])
+    fit._unpack_theta_sub(np.array([0.4, 0.2]))
+    assert (fit.model.eta, fit.model.epsilon) == (0.4, 0.2)
+
+
+def test_run_validation_errors():
+    fit = fcdiff.fit.UnsharedRegionFit()
+    fit.b = np.zeros((4, 3))
+    fit.bt = np.zeros((4, 2))
+    fit.model = fcdiff.UnsharedRegionModel()
+    with pytest.raises(ValueError, match="triangular"):
+        fit.run()
+    fit.b = np.zeros((6, 3))
+    fit.bt = np.zeros((6, 2))
+    fit.model = None
+    with pytest.raises(ValueError, match="initialized"):
+        fit.run()
+
+
+def test_defaults_match_reference():
+    fit = fcdiff.fit.UnsharedRegionFit()
+    assert (fit.max_iters, fit.rel_tol, fit.energy, fit.edge_lookup) == (10, 1e-5, [], "reference")
+    m = fcdiff.UnsharedRegionModel()
+    assert (m.pi, m.eta, m.epsilon) == (0.05, 0.3, 0.03)
+    nptest.assert_array_equal(m.gamma, [0.1, 0.8, 0.1])
+    nptest.assert_array_equal(m.mu, [-0.15, 0, 0.3])
+    nptest.assert_array_equal(m.sigma, [0.025, 0.035, 0.05])
+    assert isinstance(str(m), str)
+
+
+def test_eval_M_eps():
+    f = fcdiff.fit._eval_M_eps
+    assert f(0.3, 0.01, 0) == 0.99 and f(0.3, 0.01, 1) == 0.01
+    nptest.assert_allclose(f(0.3, 0.01, 2), 0.3 * 0.01 + 0.7 * 0.99)
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from fcdiff_b200 import _lib
+    fit = fcdiff.fit.UnsharedRegionFit()
+    fit.b = np.zeros((6, 3))
+    fit.bt = np.zeros((6, 2))
+    fit.model = fcdiff.UnsharedRegionModel()
+    with pytest.raises(_lib.FcdError, match="no CPU fallback"):
+        fit.run()
+    with pytest.raises(_lib.FcdError):
+        fcdiff.UnsharedRegionModel().sample(4, 2, 2)
+
+
+def test_shard_spans_cover_everything():
+    for world in (1, 2, 3, 4, 8):
+        for total in (1, 5, 45, 4005, 79800):
+            covered = []
+            for r in range(world):
+                (s, l) = EdgeShards(rank=r, world=world).span(total)
+                covered += list(range(s, s + l))
+            assert covered == list(range(total))
+
+
+def test_product_does_not_import_oracle():
+    import os
+    root = os.path.dirname(os.path.abspath(fcdiff.__file__))
+    for fn in os.listdir(root):
+        if fn.endswith(".py"):
+            src = open(os.path.join(root, fn)).read()
+            assert "import oracle" not in src and "from oracle" not in src, fn
