@@ -414,6 +414,7 @@ class UnsharedRegionFit(object):
         (fcdiff/fit.py:157-174).
         """
         lib = _lib.load()
+        keep = _Keep()
         if self._arrays_mode('_lp_B_g_F', '_lM'):
             lpB = np.ascontiguousarray(self._lp_B_g_F, dtype=np.float64)
             lM = np.ascontiguousarray(self._lM, dtype=np.float64)
@@ -423,7 +424,7 @@ class UnsharedRegionFit(object):
             N = self._mR.shape[0]
             lqF = _dev.empty((C * 3,))
             _lib.check(lib.fcd_lqF_from_arrays(
-                _dev.ptr(_dev.upload(lpB)), _dev.ptr(_dev.upload(lM)), C, H, U, _dev.ptr(qR), N,
+                keep.up(lpB), keep.up(lM), C, H, U, _dev.ptr(qR), N,
                 _lib.d3(np.log(np.asarray(self.model.gamma, dtype=np.float64).reshape(-1))),
                 _dev.ptr(lqF), _dev.stream()), "fcd_lqF_from_arrays")
             self._mF.set_host(_dev.download(lqF).reshape(C, 1, 3))
@@ -449,6 +450,7 @@ class UnsharedRegionFit(object):
         Update the probability of the anomalous regions (fcdiff/fit.py:176-198).
         """
         lib = _lib.load()
+        keep = _Keep()
         lookup = _LOOKUP[self.edge_lookup]
         log_pi2 = _lib.d3(np.log(_pi2(self.model.pi)))
         if self._arrays_mode('_lM'):
@@ -458,7 +460,7 @@ class UnsharedRegionFit(object):
             (lqR, qR) = self._mR.get_dev()
             N = self._mR.shape[0]
             WT = _dev.empty((U, C, 3))
-            _lib.check(lib.fcd_region_weights_from_lM(_dev.ptr(_dev.upload(lM)), C, U, _dev.ptr(qF),
+            _lib.check(lib.fcd_region_weights_from_lM(keep.up(lM), C, U, _dev.ptr(qF),
                                                       _dev.ptr(WT), _dev.stream()),
                        "fcd_region_weights_from_lM")
             lqR_new, qR_new = lqR.clone(), qR.clone()
@@ -627,6 +629,17 @@ def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+class _Keep(list):
+    """Holds device temporaries alive until the call that reads them has been
+    enqueued (a tensor freed earlier could be recycled by the caching allocator
+    for the next upload)."""
+
+    def up(self, a, dtype=np.float64):
+        t = _dev.upload(a, dtype)
+        self.append(t)
+        return _dev.ptr(t)
+
+
 def _scalar_out(n=1):
     return _dev.empty((n,))
 
@@ -637,10 +650,11 @@ def _eval_q_R_w(q_R, n, m):
     (fcdiff/fit.py:382-406).  Returns (U, 3).
     """
     lib = _lib.load()
+    keep = _Keep()
     q_R = _f64(q_R)
     (N, U) = q_R.shape[0:2]
     out = _dev.empty((U, 3))
-    _lib.check(lib.fcd_pair_weights(_dev.ptr(_dev.upload(q_R)), N, U, int(n), int(m), _dev.ptr(out),
+    _lib.check(lib.fcd_pair_weights(keep.up(q_R), N, U, int(n), int(m), _dev.ptr(out),
                                     _dev.stream()), "fcd_pair_weights")
     return _dev.download(out)
 
@@ -651,11 +665,12 @@ def _eval_M(N, eta, epsilon, k, l):
     N : (C, U, 3) -> (C, U).
     """
     lib = _lib.load()
+    keep = _Keep()
     N = _f64(N)
     lead = N.shape[:-1]
     n = int(np.prod(lead)) if len(lead) else 1
     out = _dev.empty((max(n, 1),))
-    _lib.check(lib.fcd_eval_M(_dev.ptr(_dev.upload(N)), n, float(eta), float(epsilon), int(k), int(l),
+    _lib.check(lib.fcd_eval_M(keep.up(N), n, float(eta), float(epsilon), int(k), int(l),
                               _dev.ptr(out), _dev.stream()), "fcd_eval_M")
     return _dev.download(out)[:n].reshape(lead)
 
@@ -677,10 +692,11 @@ def _eval_M_eps(eta, epsilon, l):
 
 def _dot(a, a_outer, a_inner, x, n):
     lib = _lib.load()
+    keep = _Keep()
     out = _scalar_out()
     x = _f64(x).reshape(-1)
-    _lib.check(lib.fcd_dot_broadcast(_dev.ptr(_dev.upload(_f64(a).reshape(-1))), int(a_outer), int(a_inner),
-                                     _dev.ptr(_dev.upload(x)), x.size, int(n), _dev.ptr(out),
+    _lib.check(lib.fcd_dot_broadcast(keep.up(_f64(a).reshape(-1)), int(a_outer), int(a_inner),
+                                     keep.up(x), x.size, int(n), _dev.ptr(out),
                                      _dev.ptr(_dev.workspace()), _dev.stream()), "fcd_dot_broadcast")
     return float(_dev.download(out)[0])
 
@@ -712,12 +728,13 @@ def _eval_E_lp_R(q_R, pi):
 def _eval_E_lM(q_F, q_R, lM):
     """E[log p(b~ | f, r; theta)] (fcdiff/fit.py:489-511)."""
     lib = _lib.load()
+    keep = _Keep()
     (q_F, q_R, lM) = (_f64(q_F), _f64(q_R), _f64(lM))
     C = q_F.shape[0]
     (N, U) = q_R.shape[0:2]
     out = _scalar_out()
-    _lib.check(lib.fcd_ElM_from_arrays(_dev.ptr(_dev.upload(q_F)), _dev.ptr(_dev.upload(q_R)),
-                                       _dev.ptr(_dev.upload(lM)), C, N, U, _dev.ptr(out),
+    _lib.check(lib.fcd_ElM_from_arrays(keep.up(q_F), keep.up(q_R),
+                                       keep.up(lM), C, N, U, _dev.ptr(out),
                                        _dev.ptr(_dev.workspace()), _dev.stream()), "fcd_ElM_from_arrays")
     return float(_dev.download(out)[0])
 
@@ -736,12 +753,13 @@ def _eval_E_lq_R(q_R, lq_R):
 
 def _dE(q_R, q_F, norm, mix, eta, epsilon):
     lib = _lib.load()
+    keep = _Keep()
     (q_R, q_F, norm, mix) = (_f64(q_R), _f64(q_F), _f64(norm), _f64(mix))
     C = q_F.shape[0]
     (N, U) = q_R.shape[0:2]
     out = _scalar_out(2)
-    _lib.check(lib.fcd_dE_from_arrays(_dev.ptr(_dev.upload(q_R)), _dev.ptr(_dev.upload(q_F)),
-                                      _dev.ptr(_dev.upload(norm)), _dev.ptr(_dev.upload(mix)), C, N, U,
+    _lib.check(lib.fcd_dE_from_arrays(keep.up(q_R), keep.up(q_F),
+                                      keep.up(norm), keep.up(mix), C, N, U,
                                       float(eta), float(epsilon), _dev.ptr(out),
                                       _dev.ptr(_dev.workspace()), _dev.stream()), "fcd_dE_from_arrays")
     return _dev.download(out)
@@ -759,10 +777,11 @@ def _eval_dE_de(q_R, q_F, norm, mix, eta):
 
 def _dlM(norm, mix, eps, k):
     lib = _lib.load()
+    keep = _Keep()
     (norm, mix) = (_f64(norm), _f64(mix))
     n = mix.size
     out = _dev.empty((max(n, 1),))
-    _lib.check(lib.fcd_dlM(_dev.ptr(_dev.upload(norm)), _dev.ptr(_dev.upload(mix)), n, float(eps), int(k),
+    _lib.check(lib.fcd_dlM(keep.up(norm), keep.up(mix), n, float(eps), int(k),
                            _dev.ptr(out), _dev.stream()), "fcd_dlM")
     return _dev.download(out)[:n].reshape(mix.shape)
 

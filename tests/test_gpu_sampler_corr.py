@@ -78,12 +78,12 @@ def test_sample_B_moments_and_ks(k):
     assert b.min() >= -1 and b.max() <= 1
     nptest.assert_allclose(b.mean(), model.mu[k], atol=0.002)
     nptest.assert_allclose(b.std(), model.sigma[k], atol=0.002)
-    (_, p) = scipy.stats.kstest(b[0], 'norm', args=(model.mu[k], model.sigma[k]))
+    (_, p) = scipy.stats.kstest(b[0], scipy.stats.norm(model.mu[k], model.sigma[k]).cdf)
     assert p > 1e-3
     ft = np.zeros((1, 50000, 3), dtype=bool)
     ft[0, :, k] = True
     bt = model.sample_B_tilde(ft)
-    (_, p) = scipy.stats.kstest(bt[0], 'norm', args=(model.mu[k], model.sigma[k]))
+    (_, p) = scipy.stats.kstest(bt[0], scipy.stats.norm(model.mu[k], model.sigma[k]).cdf)
     assert p > 1e-3
 
 
