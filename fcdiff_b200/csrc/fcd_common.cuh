@@ -8,6 +8,7 @@
 #include <math.h>
 
 #include "fcdiff_b200.h"
+#include "fcd_math.cuh"
 
 namespace fcd {
 
@@ -107,9 +108,18 @@ __device__ __forceinline__ ElemM elem_eval(double x, const ThetaDev& th) {
         double z = (x - th.mu[k]) * th.isig[k];
         t[k] = fma(-0.5 * z, z, th.lc[k]);
     }
-    r.tmax = fmax(t[0], fmax(t[1], t[2]));
-#pragma unroll
-    for (int k = 0; k < 3; ++k) r.e[k] = exp(t[k] - r.tmax);
+    // The maximal component has e = exp(0) = 1 exactly: only the two others
+    // need an exponential (selects run on the ALU pipe, the fp64 pipe is the
+    // bottleneck).
+    const bool m0 = (t[0] >= t[1]) && (t[0] >= t[2]);
+    const bool m1 = !m0 && (t[1] >= t[2]);
+    const bool m01 = m0 || m1;
+    r.tmax = m0 ? t[0] : (m1 ? t[1] : t[2]);
+    const double ea = exp_nonpos((m0 ? t[1] : t[0]) - r.tmax);
+    const double eb = exp_nonpos((m01 ? t[2] : t[1]) - r.tmax);
+    r.e[0] = m0 ? 1.0 : ea;
+    r.e[1] = m1 ? 1.0 : (m0 ? ea : eb);
+    r.e[2] = m01 ? eb : 1.0;
     r.o[0] = r.e[1] + r.e[2];
     r.o[1] = r.e[0] + r.e[2];
     r.o[2] = r.e[0] + r.e[1];

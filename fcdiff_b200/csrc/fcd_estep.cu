@@ -48,8 +48,9 @@ healthy_stats_kernel(const double* __restrict__ b, int64_t C, int H, int64_t pit
 //            - logsumexp_k                                 (fcdiff/fit.py:157-174)
 // The per-(c,u) term (tmax - log sqrt(2 pi)) * sum_l w_l is common to the three
 // states k and cancels in the normalisation, so it is never formed.
+template <bool FAST>
 __device__ __forceinline__ void k2_elem(double x, double2 qn, double2 qm, const ThetaDev& th,
-                                        double (&acc)[3]) {
+                                        const double* s_tab, double (&acc)[3]) {
     double w[3];
     pair_weights(qn, qm, w);
     ElemM r = elem_eval(x, th);
@@ -57,18 +58,20 @@ __device__ __forceinline__ void k2_elem(double x, double2 qn, double2 qm, const 
     for (int k = 0; k < 3; ++k) {
         double a = acc[k];
 #pragma unroll
-        for (int l = 0; l < 3; ++l) a = fma(w[l], log(elem_Mp(r, th, k, l)), a);
+        for (int l = 0; l < 3; ++l) a = fma(w[l], fast_log<FAST>(elem_Mp(r, th, k, l), s_tab), a);
         acc[k] = a;
     }
 }
 
-template <bool VEC2>
+template <bool VEC2, bool FAST>
 __global__ void __launch_bounds__(kEdgeThreads)
 estep_qF_kernel(const double* __restrict__ S1, const double* __restrict__ S2,
                 const double* __restrict__ bt, int64_t C, int U, int64_t pitchU,
                 const double* __restrict__ qR, int N, int64_t c0,
-                const __grid_constant__ ThetaDev th,
+                const __grid_constant__ ThetaDev th, const double* __restrict__ g_tab,
                 double* __restrict__ lqF, double* __restrict__ qF) {
+    __shared__ double s_tab[FAST ? kLogTabSize : 1];
+    load_log_table<FAST>(g_tab, s_tab);
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -86,15 +89,15 @@ estep_qF_kernel(const double* __restrict__ S1, const double* __restrict__ S2,
                     double2 x = ldg_stream2(row + u);
                     double2 a0 = __ldg(qn + u), a1 = __ldg(qn + u + 1);
                     double2 b0 = __ldg(qm + u), b1 = __ldg(qm + u + 1);
-                    k2_elem(x.x, a0, b0, th, acc);
-                    k2_elem(x.y, a1, b1, th, acc);
+                    k2_elem<FAST>(x.x, a0, b0, th, s_tab, acc);
+                    k2_elem<FAST>(x.y, a1, b1, th, s_tab, acc);
                 } else {
-                    k2_elem(ldg_stream1(row + u), __ldg(qn + u), __ldg(qm + u), th, acc);
+                    k2_elem<FAST>(ldg_stream1(row + u), __ldg(qn + u), __ldg(qm + u), th, s_tab, acc);
                 }
             }
         } else {
             for (int u = lane; u < U; u += 32)
-                k2_elem(ldg_stream1(row + u), __ldg(qn + u), __ldg(qm + u), th, acc);
+                k2_elem<FAST>(ldg_stream1(row + u), __ldg(qn + u), __ldg(qm + u), th, s_tab, acc);
         }
 #pragma unroll
         for (int k = 0; k < 3; ++k) acc[k] = warp_sum(acc[k]);
@@ -147,10 +150,13 @@ transpose_patients_kernel(const double* __restrict__ bt, int64_t C, int U, int64
 // constant (tmax - log sqrt(2 pi)) sum_k qF[c,k] is the same for l = 0, 1, 2 and
 // enters both states of fcdiff/fit.py:190,194 multiplied by
 // (q_R[m,u,0] + q_R[m,u,1]), so it cancels at fit.py:196.
+template <bool FAST>
 __global__ void __launch_bounds__(256)
 region_weights_kernel(const double* __restrict__ btT, int64_t C, int64_t pitchC,
                       const double* __restrict__ qF, const __grid_constant__ ThetaDev th,
-                      double* __restrict__ WT) {
+                      const double* __restrict__ g_tab, double* __restrict__ WT) {
+    __shared__ double s_tab[FAST ? kLogTabSize : 1];
+    load_log_table<FAST>(g_tab, s_tab);
     const int u = blockIdx.y;
     const double* row = btT + (int64_t)u * pitchC;
     double* out = WT + (int64_t)u * C * 3;
@@ -161,9 +167,9 @@ region_weights_kernel(const double* __restrict__ btT, int64_t C, int64_t pitchC,
         ElemM r = elem_eval(x, th);
 #pragma unroll
         for (int l = 0; l < 3; ++l) {
-            double w = q0 * log(elem_Mp(r, th, 0, l));
-            w = fma(q1, log(elem_Mp(r, th, 1, l)), w);
-            w = fma(q2, log(elem_Mp(r, th, 2, l)), w);
+            double w = q0 * fast_log<FAST>(elem_Mp(r, th, 0, l), s_tab);
+            w = fma(q1, fast_log<FAST>(elem_Mp(r, th, 1, l), s_tab), w);
+            w = fma(q2, fast_log<FAST>(elem_Mp(r, th, 2, l), s_tab), w);
             out[c * 3 + l] = w;
         }
     }
@@ -274,14 +280,17 @@ int fcd_estep_qF(const double* S1, const double* S2, int32_t H,
                 (long long)c0, (long long)(c0 + C), N);
     if (C == 0) return 0;
     const ThetaDev th = make_theta_dev(*theta_host, H);
-    const int grid = grid_for_rows(C, kEdgeThreads / 32, 8);
+    const double* tab = log_table((cudaStream_t)stream);
+    FCD_REQUIRE(tab != nullptr, "fcd_estep_qF: log table initialisation failed");
+    const int grid = grid_for_rows(C, kEdgeThreads / 32, 4);
     const bool vec2 = (pitchU % 2 == 0) && ((reinterpret_cast<uintptr_t>(bt) & 15) == 0);
-    if (vec2)
-        estep_qF_kernel<true><<<grid, kEdgeThreads, 0, (cudaStream_t)stream>>>(
-            S1, S2, bt, C, U, pitchU, qR, N, c0, th, lqF, qF);
-    else
-        estep_qF_kernel<false><<<grid, kEdgeThreads, 0, (cudaStream_t)stream>>>(
-            S1, S2, bt, C, U, pitchU, qR, N, c0, th, lqF, qF);
+    const bool fast = log_table_covers(th.epsl, th.al);
+#define FCD_K2(V, F)                                                              \
+    estep_qF_kernel<V, F><<<grid, kEdgeThreads, 0, (cudaStream_t)stream>>>(       \
+        S1, S2, bt, C, U, pitchU, qR, N, c0, th, tab, lqF, qF)
+    if (vec2) { if (fast) FCD_K2(true, true); else FCD_K2(true, false); }
+    else      { if (fast) FCD_K2(false, true); else FCD_K2(false, false); }
+#undef FCD_K2
     return check_launch("fcd_estep_qF");
 }
 
@@ -301,11 +310,16 @@ int fcd_region_weights(const double* btT, int32_t Ul, int64_t C, int64_t pitchC,
     FCD_REQUIRE(C >= 0 && Ul >= 0 && Ul <= 65535 && pitchC >= C, "fcd_region_weights: bad shape");
     if (C == 0 || Ul == 0) return 0;
     const ThetaDev th = make_theta_dev(*theta_host, 0);
+    const double* tab = log_table((cudaStream_t)stream);
+    FCD_REQUIRE(tab != nullptr, "fcd_region_weights: log table initialisation failed");
     int64_t bx = (C + 255) / 256;
-    const int64_t cap = ((int64_t)sm_count() * 16 + Ul - 1) / Ul;
+    const int64_t cap = ((int64_t)sm_count() * 4 + Ul - 1) / Ul;
     if (bx > cap) bx = cap < 1 ? 1 : cap;
     dim3 grid((unsigned)bx, (unsigned)Ul);
-    region_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(btT, C, pitchC, qF, th, WT);
+    if (log_table_covers(th.epsl, th.al))
+        region_weights_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(btT, C, pitchC, qF, th, tab, WT);
+    else
+        region_weights_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(btT, C, pitchC, qF, th, tab, WT);
     return check_launch("fcd_region_weights");
 }
 

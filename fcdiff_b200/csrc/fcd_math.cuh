@@ -1,0 +1,131 @@
+// Lean fp64 transcendental building blocks for the per-element core.
+//
+// The hot kernels are bound by the fp64 pipe (64 DFMA/clk/SM on B200), not by
+// HBM: per edge-patient element the reference needs 3 exp and 9 log
+// (fcdiff/fit.py:115, 122).  CUDA's general-purpose exp()/log() cost ~450 fp64
+// instructions per element (ncu, profiles/r01a_*); the routines below exploit
+// what is known about the arguments:
+//
+//  * fast_log(y): y is a mixture weight in (0, 1].  MUFU.RCP64H gives r ~ 1/y;
+//    r is rounded to 8 mantissa bits (r8, exactly representable), so that
+//    u = y*r8 - 1 is one exact FMA with |u| <= 2^-9, and
+//        log y = -log r8 + log1p(u),
+//    -log r8 from a 5376-entry table in shared memory (indexed by the
+//    exponent/mantissa bits of r8), log1p(u) = u - u^2/2 + u^3/3 - u^4/4
+//    (truncation < 6e-15).  6 fp64 ops + 1 MUFU + 1 LDS instead of ~40.
+//  * fast_log_rcp additionally returns 1/y = r8 * (1 - u + u^2 - u^3 + u^4)
+//    for the analytic gradient (5 more fp64 ops, no second MUFU/Newton).
+//  * exp_nonpos(d): d <= 0, argument reduction with the 1.5*2^52 trick (no
+//    F2I/I2F conversions), degree-11 polynomial, exponent patched in the ALU.
+//
+// Absolute error of fast_log < 1e-14, relative error of exp_nonpos < 1e-14:
+// five orders of magnitude inside the 1e-9 per-term budget that 1e-6 parity of
+// the posteriors needs (DESIGN.md "Numerics").
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fcd {
+
+constexpr int kLogTabBits    = 8;                       // mantissa bits kept in r8
+constexpr int kLogTabMinExp  = -1;                      // r8 in [2^-1, 2^20)  <=>  y in (2^-20, 2]
+constexpr int kLogTabBinades = 21;
+constexpr int kLogTabSize    = kLogTabBinades << kLogTabBits;      // 5376 doubles = 43,008 bytes
+constexpr int kLogTabBase    = (1023 + kLogTabMinExp) << kLogTabBits;
+
+// Host: device address of the table for the current device (built on first use).
+const double* log_table(cudaStream_t st);
+// True when every mixture weight eps_l e_k + a_l o_k (max_k e_k = 1) lies inside the table's range.
+bool log_table_covers(const double epsl[3], const double al[3]);
+
+#ifdef __CUDACC__
+
+// -log(r8) for table slot i.
+__device__ __forceinline__ double log_table_r8(int i) {
+    return __hiloint2double((i + kLogTabBase) << (20 - kLogTabBits), 0);
+}
+
+template <bool FAST>
+__device__ __forceinline__ void load_log_table(const double* __restrict__ g_tab, double* s_tab) {
+    if (FAST)
+        for (int i = threadIdx.x; i < kLogTabSize; i += blockDim.x) s_tab[i] = g_tab[i];
+    __syncthreads();
+}
+
+struct LogParts {
+    double r8;      // 8-bit reciprocal
+    double u;       // y * r8 - 1
+    int idx;        // table slot
+};
+
+// Requires 2^-20 < y <= 1 (+ rounding): guaranteed by the host for the mixture
+// weights when min(eps_l, (1-eps_l)/2) > 2^-19 (log_table_covers); otherwise the
+// host launches the SAFE kernel variants, which use log() and division.
+__device__ __forceinline__ LogParts log_reduce(double y) {
+    LogParts p;
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(y));            // MUFU.RCP64H
+    const int hi = (__double2hiint(r0) + (1 << (19 - kLogTabBits))) & ~((1 << (20 - kLogTabBits)) - 1);
+    p.r8 = __hiloint2double(hi, 0);
+    p.idx = (hi >> (20 - kLogTabBits)) - kLogTabBase;
+    p.u = fma(y, p.r8, -1.0);
+    return p;
+}
+
+__device__ __forceinline__ double log1p_small(double u) {
+    double q = fma(u, -0.25, 1.0 / 3.0);
+    q = fma(u, q, -0.5);
+    return fma(u * u, q, u);
+}
+
+template <bool FAST>
+__device__ __forceinline__ double fast_log(double y, const double* s_tab) {
+    if (!FAST) return log(y);
+    const LogParts p = log_reduce(y);
+    return s_tab[p.idx] + log1p_small(p.u);
+}
+
+template <bool FAST>
+__device__ __forceinline__ double fast_log_rcp(double y, const double* s_tab, double& rcp) {
+    if (!FAST) {
+        rcp = 1.0 / y;
+        return log(y);
+    }
+    const LogParts p = log_reduce(y);
+    double g = p.u - 1.0;
+    g = fma(p.u, g, 1.0);                    // 1 - u + u^2
+    g = fma(p.u, -g, 1.0);                   // 1 - u + u^2 - u^3
+    g = fma(p.u, -g, 1.0);                   // 1 - u + u^2 - u^3 + u^4   (|u|^5 <= 3e-14)
+    rcp = p.r8 * g;
+    return s_tab[p.idx] + log1p_small(p.u);
+}
+
+// e^d for d <= 0 (d is clamped at -700: e^-700 ~ 1e-304 is far below any
+// weight that can matter next to the maximal component e = 1).
+__device__ __forceinline__ double exp_nonpos(double d) {
+    d = fmax(d, -700.0);
+    const double kMagic = 6755399441055744.0;                 // 1.5 * 2^52
+    const double t = fma(d, 1.4426950408889634074, kMagic);
+    const int n = __double2loint(t);
+    const double nd = t - kMagic;
+    double r = fma(nd, -6.93147180369123816490e-01, d);       // ln2 hi (32 trailing zero bits)
+    r = fma(nd, -1.90821492927058770002e-10, r);              // ln2 lo
+    double p = 2.50521083854417187751e-08;                    // 1/11!
+    p = fma(p, r, 2.75573192239858906526e-07);                // 1/10!
+    p = fma(p, r, 2.75573192239858906526e-06);                // 1/9!
+    p = fma(p, r, 2.48015873015873015873e-05);                // 1/8!
+    p = fma(p, r, 1.98412698412698412698e-04);                // 1/7!
+    p = fma(p, r, 1.38888888888888888889e-03);                // 1/6!
+    p = fma(p, r, 8.33333333333333333333e-03);                // 1/5!
+    p = fma(p, r, 4.16666666666666666667e-02);                // 1/4!
+    p = fma(p, r, 1.66666666666666666667e-01);                // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+
+#endif  // __CUDACC__
+
+}  // namespace fcd

@@ -34,9 +34,10 @@ mstep_stats_kernel(const double* __restrict__ lqF, int64_t C,
 //   dE/dh -= sum_k qF_k w_2 (2 eps - 1)   (e_k - o_k / 2) / Mp_k2
 //   dE/de -= sum_k qF_k sum_l w_l s_l     (e_k - o_k / 2) / Mp_kl,  s = (-1, 1, 2 eta - 1)
 // (the common factor exp(tmax)/sqrt(2 pi) of numerator and mixture cancels).
-template <bool GRAD>
+template <bool GRAD, bool FAST>
 __device__ __forceinline__ void k3_elem(double x, double2 qn, double2 qm, const double (&qf)[3],
-                                        double qfs, const ThetaDev& th, double (&acc)[3]) {
+                                        double qfs, const ThetaDev& th, const double* s_tab,
+                                        double (&acc)[3]) {
     double w[3];
     pair_weights(qn, qm, w);
     ElemM r = elem_eval(x, th);
@@ -49,9 +50,11 @@ __device__ __forceinline__ void k3_elem(double x, double2 qn, double2 qm, const 
 #pragma unroll
         for (int l = 0; l < 3; ++l) {
             const double M = elem_Mp(r, th, k, l);
-            so = fma(w[l], log(M), so);
+            double rcpM = 0.0;
+            const double lM = GRAD ? fast_log_rcp<FAST>(M, s_tab, rcpM) : fast_log<FAST>(M, s_tab);
+            so = fma(w[l], lM, so);
             if (GRAD) {
-                const double g = w[l] * (num / M);
+                const double g = w[l] * (num * rcpM);
                 if (l == 0) sg -= g;
                 else if (l == 1) sg += g;
                 else {
@@ -70,12 +73,14 @@ __device__ __forceinline__ void k3_elem(double x, double2 qn, double2 qm, const 
     }
 }
 
-template <bool GRAD, bool VEC2>
+template <bool GRAD, bool VEC2, bool FAST>
 __global__ void __launch_bounds__(kRedThreads)
 elm_kernel(const double* __restrict__ bt, int64_t C, int U, int64_t pitchU,
            const double* __restrict__ qF, const double* __restrict__ qR, int N, int64_t c0,
-           const __grid_constant__ ThetaDev th, double* __restrict__ out, int out_stride_dummy,
-           double* __restrict__ ws) {
+           const __grid_constant__ ThetaDev th, const double* __restrict__ g_tab,
+           double* __restrict__ out, int out_stride_dummy, double* __restrict__ ws) {
+    __shared__ double s_tab[FAST ? kLogTabSize : 1];
+    load_log_table<FAST>(g_tab, s_tab);
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -95,15 +100,15 @@ elm_kernel(const double* __restrict__ bt, int64_t C, int U, int64_t pitchU,
                     double2 x = ldg_stream2(row + u);
                     double2 a0 = __ldg(qn + u), a1 = __ldg(qn + u + 1);
                     double2 b0 = __ldg(qm + u), b1 = __ldg(qm + u + 1);
-                    k3_elem<GRAD>(x.x, a0, b0, qf, qfs, th, acc);
-                    k3_elem<GRAD>(x.y, a1, b1, qf, qfs, th, acc);
+                    k3_elem<GRAD, FAST>(x.x, a0, b0, qf, qfs, th, s_tab, acc);
+                    k3_elem<GRAD, FAST>(x.y, a1, b1, qf, qfs, th, s_tab, acc);
                 } else {
-                    k3_elem<GRAD>(ldg_stream1(row + u), __ldg(qn + u), __ldg(qm + u), qf, qfs, th, acc);
+                    k3_elem<GRAD, FAST>(ldg_stream1(row + u), __ldg(qn + u), __ldg(qm + u), qf, qfs, th, s_tab, acc);
                 }
             }
         } else {
             for (int u = lane; u < U; u += 32)
-                k3_elem<GRAD>(ldg_stream1(row + u), __ldg(qn + u), __ldg(qm + u), qf, qfs, th, acc);
+                k3_elem<GRAD, FAST>(ldg_stream1(row + u), __ldg(qn + u), __ldg(qm + u), qf, qfs, th, s_tab, acc);
         }
     }
     grid_reduce_store<3, kRedThreads>(acc, ws, out);
@@ -159,15 +164,19 @@ static inline int red_grid(int64_t work_items, int items_per_block) {
 static int launch_elm(const double* bt, int64_t C, int32_t U, int64_t pitchU,
                       const double* qF, const double* qR, int32_t N, int64_t c0,
                       const ThetaDev& th, bool grad, double* out3, double* ws, cudaStream_t st) {
-    const int grid = red_grid(C, kRedThreads / 32);
+    const double* tab = log_table(st);
+    FCD_REQUIRE(tab != nullptr, "fcd_elm_obj_grad: log table initialisation failed");
+    int grid = red_grid(C, kRedThreads / 32);
+    if (grid > sm_count() * 4) grid = sm_count() * 4;
     const bool vec2 = (pitchU % 2 == 0) && ((reinterpret_cast<uintptr_t>(bt) & 15) == 0);
-    if (grad) {
-        if (vec2) elm_kernel<true, true><<<grid, kRedThreads, 0, st>>>(bt, C, U, pitchU, qF, qR, N, c0, th, out3, 0, ws);
-        else      elm_kernel<true, false><<<grid, kRedThreads, 0, st>>>(bt, C, U, pitchU, qF, qR, N, c0, th, out3, 0, ws);
-    } else {
-        if (vec2) elm_kernel<false, true><<<grid, kRedThreads, 0, st>>>(bt, C, U, pitchU, qF, qR, N, c0, th, out3, 0, ws);
-        else      elm_kernel<false, false><<<grid, kRedThreads, 0, st>>>(bt, C, U, pitchU, qF, qR, N, c0, th, out3, 0, ws);
-    }
+    const bool fast = log_table_covers(th.epsl, th.al);
+#define FCD_ELM(G, V, F)                                                          \
+    elm_kernel<G, V, F><<<grid, kRedThreads, 0, st>>>(bt, C, U, pitchU, qF, qR, N, c0, th, tab, out3, 0, ws)
+#define FCD_ELM_F(G, V) do { if (fast) FCD_ELM(G, V, true); else FCD_ELM(G, V, false); } while (0)
+    if (grad) { if (vec2) FCD_ELM_F(true, true); else FCD_ELM_F(true, false); }
+    else      { if (vec2) FCD_ELM_F(false, true); else FCD_ELM_F(false, false); }
+#undef FCD_ELM_F
+#undef FCD_ELM
     return check_launch("fcd_elm_obj_grad");
 }
 

@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "fcd_common.cuh"
+#include "fcd_math.cuh"
 
 namespace fcd {
 
@@ -39,6 +40,38 @@ int sm_count() {
         cached[dev] = n;
     }
     return cached[dev];
+}
+
+// -log(r8) table of fast_log (fcd_math.cuh): theta-independent, built once per
+// device in static device memory (no runtime allocation).
+__device__ double g_log_tab[kLogTabSize];
+
+__global__ void build_log_table_kernel() {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kLogTabSize; i += gridDim.x * blockDim.x)
+        g_log_tab[i] = -log(log_table_r8(i));
+}
+
+const double* log_table(cudaStream_t st) {
+    static double* addr[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (addr[dev] == nullptr) {
+        double* p = nullptr;
+        if (cudaGetSymbolAddress((void**)&p, g_log_tab) != cudaSuccess) return nullptr;
+        build_log_table_kernel<<<21, 256, 0, st>>>();
+        if (check_launch("build_log_table") != 0) return nullptr;
+        if (cudaStreamSynchronize(st) != cudaSuccess) return nullptr;
+        addr[dev] = p;
+    }
+    return addr[dev];
+}
+
+bool log_table_covers(const double epsl[3], const double al[3]) {
+    for (int l = 0; l < 3; ++l) {
+        const double lo = epsl[l] < al[l] ? epsl[l] : al[l];
+        if (!(lo > 1.9073486328125e-06) || !(epsl[l] <= 1.0)) return false;      // 2^-19
+    }
+    return true;
 }
 
 ThetaDev make_theta_dev(const fcd_theta& th, int H) {
