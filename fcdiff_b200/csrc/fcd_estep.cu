@@ -176,67 +176,99 @@ region_weights_kernel(const double* __restrict__ btT, int64_t C, int64_t pitchC,
 }
 
 // --------------------------------------------------------------- K2b/sweep
-// Gauss-Seidel sweep of fcdiff/fit.py:184-197.  One CTA per patient: the
-// patient's q_R column lives in shared memory, each step n reduces N-1 terms
-// over m and writes q_R[n] back before step n+1.
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS)
+// Gauss-Seidel sweep of fcdiff/fit.py:184-197.  One CTA per patient; thread t
+// owns the regions m = t, t+T, ... and keeps their q_R in registers.  Step n:
+// every thread forms its partial sums over its m != n from the WT window that
+// was prefetched during step n-1 (the loads do not depend on q_R), one warp
+// shuffle reduction, ONE block barrier; then only the owner of region n
+// finishes the reduction, normalises (fit.py:196) and updates its register
+// copy of q_R[n] (fit.py:197) while the other threads already run step n+1.
+// The two-slot s_red buffer makes the single barrier per step sufficient.
+template <int T, int MPT>
+__global__ void __launch_bounds__(T)
 sweep_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int u0,
              int lookup, double lp0, double lp1,
              double* __restrict__ qR, double* __restrict__ lqR) {
-    extern __shared__ double sq[];                    // [N][2]
-    __shared__ double s_red[2][THREADS / 32];
+    constexpr int NW = T / 32;
+    __shared__ double s_red[2][NW][2];
     const int ul = blockIdx.x;
     const int u = u0 + ul;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int m = threadIdx.x; m < N; m += THREADS) {
-        sq[2 * m] = qR[((int64_t)m * U + u) * 2];
-        sq[2 * m + 1] = qR[((int64_t)m * U + u) * 2 + 1];
-    }
-    __syncthreads();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double* Wu = WT + (int64_t)ul * C * 3;
-    for (int n = 0; n < N; ++n) {
+    double q0[MPT], q1[MPT], w[MPT][3], wn[MPT][3];
+#pragma unroll
+    for (int j = 0; j < MPT; ++j) {
+        const int m = tid + j * T;
+        q0[j] = q1[j] = 0.0;
+        if (m < N) {
+            q0[j] = qR[((int64_t)m * U + u) * 2];
+            q1[j] = qR[((int64_t)m * U + u) * 2 + 1];
+        }
+    }
+    auto load_w = [&](int n, double (&dst)[MPT][3]) {
         const int64_t base = (int64_t)n * (n - 1) / 2;
+#pragma unroll
+        for (int j = 0; j < MPT; ++j) {
+            const int m = tid + j * T;
+            dst[j][0] = dst[j][1] = dst[j][2] = 0.0;
+            if (m < N && m != n && n < N) {
+                const int64_t c = (lookup == FCD_LOOKUP_REFERENCE || m < n)
+                                      ? base + m
+                                      : (int64_t)m * (m - 1) / 2 + n;
+                dst[j][0] = __ldg(Wu + c * 3);
+                dst[j][1] = __ldg(Wu + c * 3 + 1);
+                dst[j][2] = __ldg(Wu + c * 3 + 2);
+            }
+        }
+    };
+    load_w(0, w);
+    for (int n = 0; n < N; ++n) {
+        load_w(n + 1, wn);                            // prefetch the next window
         double s0 = 0.0, s1 = 0.0;
-        for (int m = threadIdx.x; m < N; m += THREADS) {
-            if (m == n) continue;
-            const int64_t c = (lookup == FCD_LOOKUP_REFERENCE || m < n)
-                                  ? base + m
-                                  : (int64_t)m * (m - 1) / 2 + n;
-            const double w0 = Wu[c * 3], w1 = Wu[c * 3 + 1], w2 = Wu[c * 3 + 2];
-            const double q0 = sq[2 * m], q1 = sq[2 * m + 1];
-            s0 += fma(q0, w0, q1 * w2);               // fit.py:188-190
-            s1 += fma(q1, w1, q0 * w2);               // fit.py:192-194
+#pragma unroll
+        for (int j = 0; j < MPT; ++j) {               // zero weights for m == n / m >= N
+            s0 += fma(q0[j], w[j][0], q1[j] * w[j][2]);       // fit.py:188-190
+            s1 += fma(q1[j], w[j][1], q0[j] * w[j][2]);       // fit.py:192-194
         }
         s0 = warp_sum(s0);
         s1 = warp_sum(s1);
         if (lane == 0) {
-            s_red[0][warp] = s0;
-            s_red[1][warp] = s1;
+            s_red[n & 1][warp][0] = s0;
+            s_red[n & 1][warp][1] = s1;
         }
         __syncthreads();
-        if (warp == 0) {
-            double a = (lane < THREADS / 32) ? s_red[0][lane] : 0.0;
-            double b = (lane < THREADS / 32) ? s_red[1][lane] : 0.0;
-            a = warp_sum(a);
-            b = warp_sum(b);
-            if (lane == 0) {
-                double l0 = lp0 + a, l1 = lp1 + b;
-                const double mx = fmax(l0, l1);
-                const double lse = mx + log(exp(l0 - mx) + exp(l1 - mx));   // fit.py:196
-                l0 -= lse;
-                l1 -= lse;
-                const double p0 = exp(l0), p1 = exp(l1);                   // fit.py:197
-                sq[2 * n] = p0;
-                sq[2 * n + 1] = p1;
-                const int64_t o = ((int64_t)n * U + u) * 2;
-                lqR[o] = l0;
-                lqR[o + 1] = l1;
-                qR[o] = p0;
-                qR[o + 1] = p1;
+        if (tid == n % T) {                           // owner of region n
+            double a = 0.0, b = 0.0;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+                a += s_red[n & 1][i][0];
+                b += s_red[n & 1][i][1];
             }
+            double l0 = lp0 + a, l1 = lp1 + b;
+            const double mx = fmax(l0, l1);
+            const double lse = mx + log(exp(l0 - mx) + exp(l1 - mx));       // fit.py:196
+            l0 -= lse;
+            l1 -= lse;
+            const double p0 = exp(l0), p1 = exp(l1);                        // fit.py:197
+            const int slot = n / T;
+#pragma unroll
+            for (int j = 0; j < MPT; ++j)
+                if (j == slot) {
+                    q0[j] = p0;
+                    q1[j] = p1;
+                }
+            const int64_t o = ((int64_t)n * U + u) * 2;
+            lqR[o] = l0;
+            lqR[o + 1] = l1;
+            qR[o] = p0;
+            qR[o + 1] = p1;
         }
-        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < MPT; ++j) {
+            w[j][0] = wn[j][0];
+            w[j][1] = wn[j][1];
+            w[j][2] = wn[j][2];
+        }
     }
 }
 
@@ -335,23 +367,20 @@ int fcd_estep_qR(const double* WT, int64_t C, int32_t N, int32_t U, int32_t u0, 
                 "fcd_estep_qR: edge_lookup='reference' indexes out of bounds for N < 3 (fit.py:186)");
     FCD_REQUIRE(u0 >= 0 && Ul >= 0 && u0 + Ul <= U, "fcd_estep_qR: bad patient range");
     if (Ul == 0) return 0;
-    const size_t smem = (size_t)N * 2 * sizeof(double);
-    FCD_REQUIRE(smem <= 200 * 1024, "fcd_estep_qR: N=%d too large for the shared-memory q_R column", N);
+    FCD_REQUIRE(N <= 8192, "fcd_estep_qR: N=%d exceeds the 8192 regions the sweep kernel supports", N);
     cudaStream_t st = (cudaStream_t)stream;
     const double lp0 = log_pi2_host[0], lp1 = log_pi2_host[1];
-#define FCD_SWEEP(T)                                                                              \
-    do {                                                                                          \
-        if (smem > 48 * 1024)                                                                     \
-            cudaFuncSetAttribute(sweep_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                 (int)smem);                                                      \
-        sweep_kernel<T><<<Ul, T, smem, st>>>(WT, C, N, U, u0, edge_lookup, lp0, lp1, qR, lqR);    \
-    } while (0)
-    if (N <= 32) FCD_SWEEP(32);
-    else if (N <= 64) FCD_SWEEP(64);
-    else if (N <= 128) FCD_SWEEP(128);
-    else if (N <= 256) FCD_SWEEP(256);
-    else if (N <= 512) FCD_SWEEP(512);
-    else FCD_SWEEP(1024);
+#define FCD_SWEEP(T, M)                                                                            \
+    sweep_kernel<T, M><<<Ul, T, 0, st>>>(WT, C, N, U, u0, edge_lookup, lp0, lp1, qR, lqR)
+    if (N <= 32) FCD_SWEEP(32, 1);
+    else if (N <= 64) FCD_SWEEP(32, 2);
+    else if (N <= 128) FCD_SWEEP(64, 2);
+    else if (N <= 256) FCD_SWEEP(128, 2);
+    else if (N <= 512) FCD_SWEEP(128, 4);
+    else if (N <= 1024) FCD_SWEEP(256, 4);
+    else if (N <= 2048) FCD_SWEEP(256, 8);
+    else if (N <= 4096) FCD_SWEEP(512, 8);
+    else FCD_SWEEP(1024, 8);
 #undef FCD_SWEEP
     return check_launch("fcd_estep_qR");
 }
