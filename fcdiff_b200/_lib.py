@@ -32,16 +32,18 @@ SIGNATURES = {
     "fcd_launch_count_reset": (None, []),
     "fcd_c_to_nm": (c_int, [c_int64, c_int64, _P, _P, _P]),
     "fcd_healthy_stats": (c_int, [_P, c_int64, c_int32, c_int64, _P, _P, _P]),
-    "fcd_estep_qF": (c_int, [_P, _P, c_int32, _P, c_int64, c_int32, c_int64, _P, c_int32, c_int64,
+    "fcd_gauss_cache": (c_int, [_P, c_int64, c_int32, c_int64, POINTER(FcdTheta), _P, _P, _P, _P]),
+    "fcd_estep_qF": (c_int, [_P, _P, c_int32, _P, _P, c_int64, c_int32, c_int64, _P, c_int32, c_int64,
                              POINTER(FcdTheta), _P, _P, _P]),
+    "fcd_estep_qF_finish": (c_int, [_P, _P, c_int32, _P, c_int64, POINTER(FcdTheta), _P, _P, _P]),
     "fcd_transpose_patients": (c_int, [_P, c_int64, c_int32, c_int64, c_int32, c_int32, _P, c_int64, _P]),
-    "fcd_region_weights": (c_int, [_P, c_int32, c_int64, c_int64, _P, POINTER(FcdTheta), _P, _P]),
+    "fcd_region_weights": (c_int, [_P, _P, c_int32, c_int64, c_int64, _P, POINTER(FcdTheta), _P, _P]),
     "fcd_estep_qR": (c_int, [_P, c_int64, c_int32, c_int32, c_int32, c_int32, _D3, c_int32, _P, _P, _P]),
     "fcd_mstep_stats": (c_int, [_P, c_int64, _P, c_int64, _P, _P, _P]),
-    "fcd_elm_obj_grad": (c_int, [_P, c_int64, c_int32, c_int64, _P, _P, c_int32, c_int64,
-                                 POINTER(FcdTheta), c_int32, _P, _P, _P]),
-    "fcd_energy_terms": (c_int, [_P, _P, c_int32, _P, c_int64, c_int32, c_int64, _P, _P, _P, _P,
-                                 c_int32, c_int64, POINTER(FcdTheta), _P, _P, _P]),
+    "fcd_elm_obj_grad": (c_int, [_P, _P, _P, c_int64, c_int32, c_int64, _P, _P, c_int32, c_int64,
+                                 POINTER(FcdTheta), c_int32, _P, _P, _P, _P]),
+    "fcd_energy_terms": (c_int, [_P, _P, c_int32, _P, _P, _P, c_int64, c_int32, c_int64, _P, _P, _P, _P,
+                                 c_int32, c_int64, POINTER(FcdTheta), POINTER(c_double), _P, _P, _P]),
     "fcd_materialize_lps": (c_int, [_P, _P, c_int64, c_int32, c_int32, POINTER(FcdTheta), _P, _P, _P, _P]),
     "fcd_eval_M": (c_int, [_P, c_int64, c_double, c_double, c_int32, c_int32, _P, _P]),
     "fcd_lqF_from_arrays": (c_int, [_P, _P, c_int64, c_int32, c_int32, _P, c_int32, _D3, _P, _P]),

@@ -94,32 +94,49 @@ __device__ __forceinline__ double ldg_stream1(const double* p) {
 //                    log Mp[k][l] + tmax - log sqrt(2 pi)
 // exactly (M_kl = eps_l p_k + (1-eps_l)/2 * sum_{j != k} p_j, fit.py:427-430),
 // evaluated without the underflow of exp() in the far tails.
+//
+// e_k depends on (x, mu, sigma) only, and the reference never re-estimates mu,
+// sigma (fit.py:232-237): the E/M/energy kernels therefore read a per-element
+// *Gaussian cache* built once per fit by gauss_cache_kernel instead of x:
+//   Ea = e of the first non-maximal component, Eb = e of the second one with the
+//   index of the maximal component (whose e is exactly 1) in its two lowest
+//   mantissa bits, Tm = max_k t_k.
 struct ElemM {
     double e[3];
     double o[3];
-    double tmax;
 };
 
-__device__ __forceinline__ ElemM elem_eval(double x, const ThetaDev& th) {
-    ElemM r;
+struct GaussElem {
+    double ea, ebc, tmax;
+};
+
+__device__ __forceinline__ GaussElem gauss_eval(double x, const ThetaDev& th) {
     double t[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         double z = (x - th.mu[k]) * th.isig[k];
         t[k] = fma(-0.5 * z, z, th.lc[k]);
     }
-    // The maximal component has e = exp(0) = 1 exactly: only the two others
-    // need an exponential (selects run on the ALU pipe, the fp64 pipe is the
-    // bottleneck).
+    // the maximal component has e = exp(0) = 1 exactly: only two exponentials
     const bool m0 = (t[0] >= t[1]) && (t[0] >= t[2]);
     const bool m1 = !m0 && (t[1] >= t[2]);
     const bool m01 = m0 || m1;
-    r.tmax = m0 ? t[0] : (m1 ? t[1] : t[2]);
-    const double ea = exp_nonpos((m0 ? t[1] : t[0]) - r.tmax);
-    const double eb = exp_nonpos((m01 ? t[2] : t[1]) - r.tmax);
+    GaussElem g;
+    g.tmax = m0 ? t[0] : (m1 ? t[1] : t[2]);
+    g.ea = exp_nonpos((m0 ? t[1] : t[0]) - g.tmax);
+    const double eb = exp_nonpos((m01 ? t[2] : t[1]) - g.tmax);
+    const int code = m0 ? 0 : (m1 ? 1 : 2);
+    g.ebc = __hiloint2double(__double2hiint(eb), (__double2loint(eb) & ~3) | code);
+    return g;
+}
+
+__device__ __forceinline__ ElemM elem_from_cache(double ea, double ebc) {
+    const int code = __double2loint(ebc) & 3;
+    const bool m0 = code == 0, m1 = code == 1;
+    ElemM r;
     r.e[0] = m0 ? 1.0 : ea;
-    r.e[1] = m1 ? 1.0 : (m0 ? ea : eb);
-    r.e[2] = m01 ? eb : 1.0;
+    r.e[1] = m1 ? 1.0 : (m0 ? ea : ebc);
+    r.e[2] = (m0 || m1) ? ebc : 1.0;
     r.o[0] = r.e[1] + r.e[2];
     r.o[1] = r.e[0] + r.e[2];
     r.o[2] = r.e[0] + r.e[1];

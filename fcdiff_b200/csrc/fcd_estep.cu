@@ -43,17 +43,38 @@ healthy_stats_kernel(const double* __restrict__ b, int64_t C, int H, int64_t pit
     }
 }
 
+// ------------------------------------------------------------ Gaussian cache
+// Ea / Eb / Tm planes (see fcd_common.cuh) from the patient correlations; the
+// only place where exponentials of the data are taken.  Elementwise over the
+// padded [C][pitchU] rows (padding columns are written as zeros).
+__global__ void __launch_bounds__(256)
+gauss_cache_kernel(const double* __restrict__ bt, int64_t C, int U, int64_t pitchU,
+                   const __grid_constant__ ThetaDev th,
+                   double* __restrict__ Ea, double* __restrict__ Eb, double* __restrict__ Tm) {
+    const int64_t total = C * pitchU;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int u = (int)(i % pitchU);
+        GaussElem g;
+        g.ea = g.ebc = g.tmax = 0.0;
+        if (u < U) g = gauss_eval(ldg_stream1(bt + i), th);
+        Ea[i] = g.ea;
+        Eb[i] = g.ebc;
+        if (Tm) Tm[i] = g.tmax;
+    }
+}
+
 // ------------------------------------------------------------------- K2
 // lqF[c,k] = log gamma_k + healthy_k(S1,S2) + sum_u sum_l w_l log M_kl(bt[c,u])
 //            - logsumexp_k                                 (fcdiff/fit.py:157-174)
 // The per-(c,u) term (tmax - log sqrt(2 pi)) * sum_l w_l is common to the three
 // states k and cancels in the normalisation, so it is never formed.
 template <bool FAST>
-__device__ __forceinline__ void k2_elem(double x, double2 qn, double2 qm, const ThetaDev& th,
+__device__ __forceinline__ void k2_elem(double ea, double ebc, double2 qn, double2 qm, const ThetaDev& th,
                                         const double* s_tab, double (&acc)[3]) {
     double w[3];
     pair_weights(qn, qm, w);
-    ElemM r = elem_eval(x, th);
+    const ElemM r = elem_from_cache(ea, ebc);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         double a = acc[k];
@@ -63,10 +84,30 @@ __device__ __forceinline__ void k2_elem(double x, double2 qn, double2 qm, const 
     }
 }
 
+// lane 0 of the warp that owns edge c: log gamma + healthy quadratic + A, then
+// scipy.special.logsumexp: a_max + log(sum exp(a - a_max))           (fit.py:165-174)
+__device__ __forceinline__ void k2_finish(int64_t c, const double (&A)[3], double s1, double s2,
+                                          const ThetaDev& th, double* __restrict__ lqF,
+                                          double* __restrict__ qF) {
+    double l[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        l[k] = th.log_gamma[k] + fma(th.hq_a[k], s2, fma(th.hq_b[k], s1, th.hq_c[k])) + A[k];
+    const double mx = fmax(l[0], fmax(l[1], l[2]));
+    const double lse = mx + log(exp(l[0] - mx) + exp(l[1] - mx) + exp(l[2] - mx));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double v = l[k] - lse;
+        lqF[c * 3 + k] = v;
+        if (qF) qF[c * 3 + k] = exp(v);
+    }
+}
+
 template <bool VEC2, bool FAST>
 __global__ void __launch_bounds__(kEdgeThreads)
 estep_qF_kernel(const double* __restrict__ S1, const double* __restrict__ S2,
-                const double* __restrict__ bt, int64_t C, int U, int64_t pitchU,
+                const double* __restrict__ Ea, const double* __restrict__ Eb,
+                int64_t C, int U, int64_t pitchU,
                 const double* __restrict__ qR, int N, int64_t c0,
                 const __grid_constant__ ThetaDev th, const double* __restrict__ g_tab,
                 double* __restrict__ lqF, double* __restrict__ qF) {
@@ -79,44 +120,46 @@ estep_qF_kernel(const double* __restrict__ S1, const double* __restrict__ S2,
     for (int64_t c = warp0; c < C; c += nwarps) {
         int n, m;
         c_to_nm(c0 + c, n, m);
-        const double* row = bt + c * pitchU;
+        const double* ra = Ea + c * pitchU;
+        const double* rb = Eb + c * pitchU;
         const double2* qn = qR2 + (int64_t)n * U;
         const double2* qm = qR2 + (int64_t)m * U;
         double acc[3] = {0.0, 0.0, 0.0};
         if (VEC2) {
             for (int u = 2 * lane; u < U; u += 64) {
                 if (u + 1 < U) {
-                    double2 x = ldg_stream2(row + u);
-                    double2 a0 = __ldg(qn + u), a1 = __ldg(qn + u + 1);
-                    double2 b0 = __ldg(qm + u), b1 = __ldg(qm + u + 1);
-                    k2_elem<FAST>(x.x, a0, b0, th, s_tab, acc);
-                    k2_elem<FAST>(x.y, a1, b1, th, s_tab, acc);
+                    const double2 xa = ldg_stream2(ra + u), xb = ldg_stream2(rb + u);
+                    const double2 a0 = __ldg(qn + u), a1 = __ldg(qn + u + 1);
+                    const double2 b0 = __ldg(qm + u), b1 = __ldg(qm + u + 1);
+                    k2_elem<FAST>(xa.x, xb.x, a0, b0, th, s_tab, acc);
+                    k2_elem<FAST>(xa.y, xb.y, a1, b1, th, s_tab, acc);
                 } else {
-                    k2_elem<FAST>(ldg_stream1(row + u), __ldg(qn + u), __ldg(qm + u), th, s_tab, acc);
+                    k2_elem<FAST>(ldg_stream1(ra + u), ldg_stream1(rb + u), __ldg(qn + u), __ldg(qm + u),
+                                  th, s_tab, acc);
                 }
             }
         } else {
             for (int u = lane; u < U; u += 32)
-                k2_elem<FAST>(ldg_stream1(row + u), __ldg(qn + u), __ldg(qm + u), th, s_tab, acc);
+                k2_elem<FAST>(ldg_stream1(ra + u), ldg_stream1(rb + u), __ldg(qn + u), __ldg(qm + u),
+                              th, s_tab, acc);
         }
 #pragma unroll
         for (int k = 0; k < 3; ++k) acc[k] = warp_sum(acc[k]);
-        if (lane == 0) {
-            const double s1 = S1[c], s2 = S2[c];
-            double l[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k)
-                l[k] = th.log_gamma[k] + fma(th.hq_a[k], s2, fma(th.hq_b[k], s1, th.hq_c[k])) + acc[k];
-            // scipy.special.logsumexp: a_max + log(sum exp(a - a_max))   (fit.py:174)
-            const double mx = fmax(l[0], fmax(l[1], l[2]));
-            const double lse = mx + log(exp(l[0] - mx) + exp(l[1] - mx) + exp(l[2] - mx));
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const double v = l[k] - lse;
-                lqF[c * 3 + k] = v;
-                if (qF) qF[c * 3 + k] = exp(v);
-            }
-        }
+        if (lane == 0) k2_finish(c, acc, S1[c], S2[c], th, lqF, qF);
+    }
+}
+
+// K2 from per-edge sums A[c][k] = sum_u sum_l w_l log Mp_kl that a K3b pass has
+// already produced with the same q_R and (eta, epsilon): no pass over the data.
+__global__ void __launch_bounds__(256)
+estep_qF_finish_kernel(const double* __restrict__ S1, const double* __restrict__ S2,
+                       const double* __restrict__ A, int64_t C,
+                       const __grid_constant__ ThetaDev th,
+                       double* __restrict__ lqF, double* __restrict__ qF) {
+    for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < C;
+         c += (int64_t)gridDim.x * blockDim.x) {
+        const double a[3] = {A[c * 3], A[c * 3 + 1], A[c * 3 + 2]};
+        k2_finish(c, a, S1[c], S2[c], th, lqF, qF);
     }
 }
 
@@ -146,25 +189,26 @@ transpose_patients_kernel(const double* __restrict__ bt, int64_t C, int U, int64
 }
 
 // ------------------------------------------------------------------- K2b/W
-// WT[u][c][l] = sum_k qF[c,k] log Mp_kl(btT[u][c]).  The omitted per-(c,u)
-// constant (tmax - log sqrt(2 pi)) sum_k qF[c,k] is the same for l = 0, 1, 2 and
-// enters both states of fcdiff/fit.py:190,194 multiplied by
-// (q_R[m,u,0] + q_R[m,u,1]), so it cancels at fit.py:196.
+// WT[u][c][l] = sum_k qF[c,k] log Mp_kl(u, c) from the patient-major cache planes.
+// The omitted per-(c,u) constant (tmax - log sqrt(2 pi)) sum_k qF[c,k] is the
+// same for l = 0, 1, 2 and enters both states of fcdiff/fit.py:190,194 multiplied
+// by (q_R[m,u,0] + q_R[m,u,1]), so it cancels at fit.py:196.
 template <bool FAST>
 __global__ void __launch_bounds__(256)
-region_weights_kernel(const double* __restrict__ btT, int64_t C, int64_t pitchC,
+region_weights_kernel(const double* __restrict__ EaT, const double* __restrict__ EbT,
+                      int64_t C, int64_t pitchC,
                       const double* __restrict__ qF, const __grid_constant__ ThetaDev th,
                       const double* __restrict__ g_tab, double* __restrict__ WT) {
     __shared__ double s_tab[FAST ? kLogTabSize : 1];
     load_log_table<FAST>(g_tab, s_tab);
     const int u = blockIdx.y;
-    const double* row = btT + (int64_t)u * pitchC;
+    const double* ra = EaT + (int64_t)u * pitchC;
+    const double* rb = EbT + (int64_t)u * pitchC;
     double* out = WT + (int64_t)u * C * 3;
     for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < C;
          c += (int64_t)gridDim.x * blockDim.x) {
-        const double x = ldg_stream1(row + c);
+        const ElemM r = elem_from_cache(ldg_stream1(ra + c), ldg_stream1(rb + c));
         const double q0 = __ldg(qF + c * 3), q1 = __ldg(qF + c * 3 + 1), q2 = __ldg(qF + c * 3 + 2);
-        ElemM r = elem_eval(x, th);
 #pragma unroll
         for (int l = 0; l < 3; ++l) {
             double w = q0 * fast_log<FAST>(elem_Mp(r, th, 0, l), s_tab);
@@ -302,8 +346,20 @@ int fcd_healthy_stats(const double* b, int64_t C, int32_t H, int64_t pitchH,
     return check_launch("fcd_healthy_stats");
 }
 
+int fcd_gauss_cache(const double* bt, int64_t C, int32_t U, int64_t pitchU,
+                    const fcd_theta* theta_host, double* Ea, double* Eb, double* Tm, void* stream) {
+    FCD_REQUIRE(theta_host != nullptr && bt != nullptr && Ea != nullptr && Eb != nullptr,
+                "fcd_gauss_cache: NULL argument");
+    FCD_REQUIRE(C >= 0 && U >= 1 && pitchU >= U, "fcd_gauss_cache: bad shape");
+    if (C == 0) return 0;
+    const ThetaDev th = make_theta_dev(*theta_host, 0);
+    gauss_cache_kernel<<<grid_for_rows(C * pitchU, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+        bt, C, U, pitchU, th, Ea, Eb, Tm);
+    return check_launch("fcd_gauss_cache");
+}
+
 int fcd_estep_qF(const double* S1, const double* S2, int32_t H,
-                 const double* bt, int64_t C, int32_t U, int64_t pitchU,
+                 const double* Ea, const double* Eb, int64_t C, int32_t U, int64_t pitchU,
                  const double* qR, int32_t N, int64_t c0,
                  const fcd_theta* theta_host, double* lqF, double* qF, void* stream) {
     FCD_REQUIRE(theta_host != nullptr, "fcd_estep_qF: theta is NULL");
@@ -315,15 +371,25 @@ int fcd_estep_qF(const double* S1, const double* S2, int32_t H,
     const double* tab = log_table((cudaStream_t)stream);
     FCD_REQUIRE(tab != nullptr, "fcd_estep_qF: log table initialisation failed");
     const int grid = grid_for_rows(C, kEdgeThreads / 32, 4);
-    const bool vec2 = (pitchU % 2 == 0) && ((reinterpret_cast<uintptr_t>(bt) & 15) == 0);
+    const bool vec2 = (pitchU % 2 == 0) && (((reinterpret_cast<uintptr_t>(Ea) | reinterpret_cast<uintptr_t>(Eb)) & 15) == 0);
     const bool fast = log_table_covers(th.epsl, th.al);
 #define FCD_K2(V, F)                                                              \
     estep_qF_kernel<V, F><<<grid, kEdgeThreads, 0, (cudaStream_t)stream>>>(       \
-        S1, S2, bt, C, U, pitchU, qR, N, c0, th, tab, lqF, qF)
+        S1, S2, Ea, Eb, C, U, pitchU, qR, N, c0, th, tab, lqF, qF)
     if (vec2) { if (fast) FCD_K2(true, true); else FCD_K2(true, false); }
     else      { if (fast) FCD_K2(false, true); else FCD_K2(false, false); }
 #undef FCD_K2
     return check_launch("fcd_estep_qF");
+}
+
+int fcd_estep_qF_finish(const double* S1, const double* S2, int32_t H, const double* A, int64_t C,
+                        const fcd_theta* theta_host, double* lqF, double* qF, void* stream) {
+    FCD_REQUIRE(theta_host != nullptr && A != nullptr && lqF != nullptr, "fcd_estep_qF_finish: NULL argument");
+    FCD_REQUIRE(C >= 0 && H >= 1, "fcd_estep_qF_finish: bad shape");
+    if (C == 0) return 0;
+    const ThetaDev th = make_theta_dev(*theta_host, H);
+    estep_qF_finish_kernel<<<grid_for_rows(C, 256, 8), 256, 0, (cudaStream_t)stream>>>(S1, S2, A, C, th, lqF, qF);
+    return check_launch("fcd_estep_qF_finish");
 }
 
 int fcd_transpose_patients(const double* bt, int64_t C, int32_t U, int64_t pitchU,
@@ -336,7 +402,7 @@ int fcd_transpose_patients(const double* bt, int64_t C, int32_t U, int64_t pitch
     return check_launch("fcd_transpose_patients");
 }
 
-int fcd_region_weights(const double* btT, int32_t Ul, int64_t C, int64_t pitchC,
+int fcd_region_weights(const double* EaT, const double* EbT, int32_t Ul, int64_t C, int64_t pitchC,
                        const double* qF, const fcd_theta* theta_host, double* WT, void* stream) {
     FCD_REQUIRE(theta_host != nullptr, "fcd_region_weights: theta is NULL");
     FCD_REQUIRE(C >= 0 && Ul >= 0 && Ul <= 65535 && pitchC >= C, "fcd_region_weights: bad shape");
@@ -349,9 +415,9 @@ int fcd_region_weights(const double* btT, int32_t Ul, int64_t C, int64_t pitchC,
     if (bx > cap) bx = cap < 1 ? 1 : cap;
     dim3 grid((unsigned)bx, (unsigned)Ul);
     if (log_table_covers(th.epsl, th.al))
-        region_weights_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(btT, C, pitchC, qF, th, tab, WT);
+        region_weights_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(EaT, EbT, C, pitchC, qF, th, tab, WT);
     else
-        region_weights_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(btT, C, pitchC, qF, th, tab, WT);
+        region_weights_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(EaT, EbT, C, pitchC, qF, th, tab, WT);
     return check_launch("fcd_region_weights");
 }
 

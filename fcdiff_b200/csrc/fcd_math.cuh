@@ -13,8 +13,9 @@
 //    -log r8 from a 5376-entry table in shared memory (indexed by the
 //    exponent/mantissa bits of r8), log1p(u) = u - u^2/2 + u^3/3 - u^4/4
 //    (truncation < 6e-15).  6 fp64 ops + 1 MUFU + 1 LDS instead of ~40.
-//  * fast_log_rcp additionally returns 1/y = r8 * (1 - u + u^2 - u^3 + u^4)
-//    for the analytic gradient (5 more fp64 ops, no second MUFU/Newton).
+//  * fast_log_rcp additionally returns 1/y = r8 * (1 - u + u^2 - u^3), rel. error
+//    <= u^4 = 1.5e-11, for the analytic gradient (4 more fp64 ops, no second
+//    MUFU / Newton iteration).
 //  * exp_nonpos(d): d <= 0, argument reduction with the 1.5*2^52 trick (no
 //    F2I/I2F conversions), degree-11 polynomial, exponent patched in the ALU.
 //
@@ -93,10 +94,9 @@ __device__ __forceinline__ double fast_log_rcp(double y, const double* s_tab, do
         return log(y);
     }
     const LogParts p = log_reduce(y);
-    double g = p.u - 1.0;
-    g = fma(p.u, g, 1.0);                    // 1 - u + u^2
-    g = fma(p.u, -g, 1.0);                   // 1 - u + u^2 - u^3
-    g = fma(p.u, -g, 1.0);                   // 1 - u + u^2 - u^3 + u^4   (|u|^5 <= 3e-14)
+    double g = 1.0 - p.u;
+    g = fma(-p.u, g, 1.0);                   // 1 - u + u^2
+    g = fma(-p.u, g, 1.0);                   // 1 - u + u^2 - u^3   (u^4 <= 1.5e-11 relative)
     rcp = p.r8 * g;
     return s_tab[p.idx] + log1p_small(p.u);
 }

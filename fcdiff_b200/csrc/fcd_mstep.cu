@@ -28,90 +28,121 @@ mstep_stats_kernel(const double* __restrict__ lqF, int64_t C,
 }
 
 // ------------------------------------------------------------------- K3b
-// One pass over the local edge rows of bt.  Per element (fit.py:489-511 for
-// the objective, fit.py:600-697 for the gradient):
-//   E_lM  += sum_k qF_k sum_l w_l [log Mp_kl + tmax - log sqrt(2 pi)]
-//   dE/dh -= sum_k qF_k w_2 (2 eps - 1)   (e_k - o_k / 2) / Mp_k2
-//   dE/de -= sum_k qF_k sum_l w_l s_l     (e_k - o_k / 2) / Mp_kl,  s = (-1, 1, 2 eta - 1)
-// (the common factor exp(tmax)/sqrt(2 pi) of numerator and mixture cancels).
+// One pass over the Gaussian-cache planes of the local edge rows.  With
+// A_k(c) = sum_u sum_l w_l log Mp_kl (fit.py:489-511 for the objective) and
+// num_k = e_k - o_k / 2 (fit.py:600-697 for the gradient; the common factor
+// exp(tmax)/sqrt(2 pi) of numerator and mixture cancels):
+//   out[0] = sum_c sum_k qF_k A_k                         (theta-dependent part of E_lM)
+//   out[1] = dE/d eta = -(2 eps - 1) sum_c sum_k qF_k sum_u w_2 num_k / Mp_k2
+//   out[2] = dE/d eps = -sum_c sum_k qF_k sum_u sum_l s_l w_l num_k / Mp_kl,  s = (-1, 1, 2 eta - 1)
+//   out[3] = sum_c (sum_k qF_k) sum_u (sum_l w_l)(tmax - log sqrt(2 pi))      (CONST; theta-free part)
+// E_lM = out[0] + out[3].  When Aout != NULL the per-edge sums A_k(c) are also
+// written: they are exactly what the next K2 and the energy need (no extra pass).
 template <bool GRAD, bool FAST>
-__device__ __forceinline__ void k3_elem(double x, double2 qn, double2 qm, const double (&qf)[3],
-                                        double qfs, const ThetaDev& th, const double* s_tab,
-                                        double (&acc)[3]) {
-    double w[3];
+__device__ __forceinline__ void k3_elem(double ea, double ebc, double2 qn, double2 qm, double (&w)[3],
+                                        const ThetaDev& th, double s2, const double* s_tab,
+                                        double (&A)[3], double (&G)[3], double (&Hh)[3]) {
     pair_weights(qn, qm, w);
-    ElemM r = elem_eval(x, th);
-    double obj = (w[0] + w[1] + w[2]) * qfs * (r.tmax - kHalfLog2Pi);
-    double gh = 0.0, ge = 0.0;
+    const ElemM r = elem_from_cache(ea, ebc);
+    const double sw2 = s2 * w[2];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const double num = fma(-0.5, r.o[k], r.e[k]);
-        double so = 0.0, sg = 0.0;
+        double a = A[k], ds = 0.0, hs = 0.0;
 #pragma unroll
         for (int l = 0; l < 3; ++l) {
             const double M = elem_Mp(r, th, k, l);
-            double rcpM = 0.0;
-            const double lM = GRAD ? fast_log_rcp<FAST>(M, s_tab, rcpM) : fast_log<FAST>(M, s_tab);
-            so = fma(w[l], lM, so);
             if (GRAD) {
-                const double g = w[l] * (num * rcpM);
-                if (l == 0) sg -= g;
-                else if (l == 1) sg += g;
+                double rcp;
+                a = fma(w[l], fast_log_rcp<FAST>(M, s_tab, rcp), a);
+                if (l == 0) ds = -w[0] * rcp;
+                else if (l == 1) ds = fma(w[1], rcp, ds);
                 else {
-                    sg = fma(2.0 * th.eta - 1.0, g, sg);
-                    gh = fma(qf[k], g, gh);
+                    ds = fma(sw2, rcp, ds);
+                    hs = w[2] * rcp;
                 }
+            } else {
+                a = fma(w[l], fast_log<FAST>(M, s_tab), a);
             }
         }
-        obj = fma(qf[k], so, obj);
-        if (GRAD) ge = fma(qf[k], sg, ge);
-    }
-    acc[0] += obj;
-    if (GRAD) {
-        acc[1] -= (2.0 * th.epsilon - 1.0) * gh;
-        acc[2] -= ge;
+        A[k] = a;
+        if (GRAD) {
+            const double num = fma(-0.5, r.o[k], r.e[k]);
+            G[k] = fma(num, ds, G[k]);
+            Hh[k] = fma(num, hs, Hh[k]);
+        }
     }
 }
 
-template <bool GRAD, bool VEC2, bool FAST>
+template <bool GRAD, bool CONST, bool VEC2, bool FAST>
 __global__ void __launch_bounds__(kRedThreads)
-elm_kernel(const double* __restrict__ bt, int64_t C, int U, int64_t pitchU,
+elm_kernel(const double* __restrict__ Ea, const double* __restrict__ Eb, const double* __restrict__ Tm,
+           int64_t C, int U, int64_t pitchU,
            const double* __restrict__ qF, const double* __restrict__ qR, int N, int64_t c0,
            const __grid_constant__ ThetaDev th, const double* __restrict__ g_tab,
-           double* __restrict__ out, int out_stride_dummy, double* __restrict__ ws) {
+           double* __restrict__ Aout, double* __restrict__ out, double* __restrict__ ws) {
     __shared__ double s_tab[FAST ? kLogTabSize : 1];
     load_log_table<FAST>(g_tab, s_tab);
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const double2* qR2 = reinterpret_cast<const double2*>(qR);
-    double acc[3] = {0.0, 0.0, 0.0};
+    const double s2 = 2.0 * th.eta - 1.0;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
     for (int64_t c = warp0; c < C; c += nwarps) {
         int n, m;
         c_to_nm(c0 + c, n, m);
-        const double* row = bt + c * pitchU;
+        const double* ra = Ea + c * pitchU;
+        const double* rb = Eb + c * pitchU;
+        const double* rt = CONST ? Tm + c * pitchU : nullptr;
         const double2* qn = qR2 + (int64_t)n * U;
         const double2* qm = qR2 + (int64_t)m * U;
-        double qf[3] = {__ldg(qF + c * 3), __ldg(qF + c * 3 + 1), __ldg(qF + c * 3 + 2)};
-        const double qfs = qf[0] + qf[1] + qf[2];
+        const double qf[3] = {__ldg(qF + c * 3), __ldg(qF + c * 3 + 1), __ldg(qF + c * 3 + 2)};
+        double A[3] = {0.0, 0.0, 0.0}, G[3] = {0.0, 0.0, 0.0}, Hh[3] = {0.0, 0.0, 0.0};
+        double cs = 0.0, w[3];
         if (VEC2) {
             for (int u = 2 * lane; u < U; u += 64) {
                 if (u + 1 < U) {
-                    double2 x = ldg_stream2(row + u);
-                    double2 a0 = __ldg(qn + u), a1 = __ldg(qn + u + 1);
-                    double2 b0 = __ldg(qm + u), b1 = __ldg(qm + u + 1);
-                    k3_elem<GRAD, FAST>(x.x, a0, b0, qf, qfs, th, s_tab, acc);
-                    k3_elem<GRAD, FAST>(x.y, a1, b1, qf, qfs, th, s_tab, acc);
+                    const double2 xa = ldg_stream2(ra + u), xb = ldg_stream2(rb + u);
+                    const double2 a0 = __ldg(qn + u), a1 = __ldg(qn + u + 1);
+                    const double2 b0 = __ldg(qm + u), b1 = __ldg(qm + u + 1);
+                    double2 tm;
+                    if (CONST) tm = ldg_stream2(rt + u);
+                    k3_elem<GRAD, FAST>(xa.x, xb.x, a0, b0, w, th, s2, s_tab, A, G, Hh);
+                    if (CONST) cs = fma(w[0] + w[1] + w[2], tm.x - kHalfLog2Pi, cs);
+                    k3_elem<GRAD, FAST>(xa.y, xb.y, a1, b1, w, th, s2, s_tab, A, G, Hh);
+                    if (CONST) cs = fma(w[0] + w[1] + w[2], tm.y - kHalfLog2Pi, cs);
                 } else {
-                    k3_elem<GRAD, FAST>(ldg_stream1(row + u), __ldg(qn + u), __ldg(qm + u), qf, qfs, th, s_tab, acc);
+                    k3_elem<GRAD, FAST>(ldg_stream1(ra + u), ldg_stream1(rb + u), __ldg(qn + u), __ldg(qm + u),
+                                        w, th, s2, s_tab, A, G, Hh);
+                    if (CONST) cs = fma(w[0] + w[1] + w[2], ldg_stream1(rt + u) - kHalfLog2Pi, cs);
                 }
             }
         } else {
-            for (int u = lane; u < U; u += 32)
-                k3_elem<GRAD, FAST>(ldg_stream1(row + u), __ldg(qn + u), __ldg(qm + u), qf, qfs, th, s_tab, acc);
+            for (int u = lane; u < U; u += 32) {
+                k3_elem<GRAD, FAST>(ldg_stream1(ra + u), ldg_stream1(rb + u), __ldg(qn + u), __ldg(qm + u),
+                                    w, th, s2, s_tab, A, G, Hh);
+                if (CONST) cs = fma(w[0] + w[1] + w[2], ldg_stream1(rt + u) - kHalfLog2Pi, cs);
+            }
         }
+        if (Aout != nullptr) {                        // warp-uniform
+#pragma unroll
+            for (int k = 0; k < 3; ++k) A[k] = warp_sum(A[k]);
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) Aout[c * 3 + k] = A[k];
+                acc[0] += fma(qf[0], A[0], fma(qf[1], A[1], qf[2] * A[2]));
+            }
+        } else {
+            acc[0] += fma(qf[0], A[0], fma(qf[1], A[1], qf[2] * A[2]));
+        }
+        if (GRAD) {
+            acc[1] -= fma(qf[0], Hh[0], fma(qf[1], Hh[1], qf[2] * Hh[2]));
+            acc[2] -= fma(qf[0], G[0], fma(qf[1], G[1], qf[2] * G[2]));
+        }
+        if (CONST) acc[3] = fma(qf[0] + qf[1] + qf[2], cs, acc[3]);
     }
-    grid_reduce_store<3, kRedThreads>(acc, ws, out);
+    if (GRAD) acc[1] *= (2.0 * th.epsilon - 1.0);
+    grid_reduce_store<4, kRedThreads>(acc, ws, out);
 }
 
 // ------------------------------------------------------------------- K4
@@ -124,12 +155,12 @@ __global__ void __launch_bounds__(kRedThreads)
 energy_small_kernel(const double* __restrict__ S1, const double* __restrict__ S2,
                     const double* __restrict__ lqF, const double* __restrict__ qF, int64_t C,
                     const double* __restrict__ lqR, const double* __restrict__ qR, int64_t NU,
-                    const __grid_constant__ ThetaDev th, double* __restrict__ out6,
-                    double* __restrict__ ws) {
+                    const __grid_constant__ ThetaDev th, int elm_known, double elm_value,
+                    double* __restrict__ out6, double* __restrict__ ws) {
     double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t nth = (int64_t)gridDim.x * blockDim.x;
-    if (tid == 0) v[3] = ws[kWsScratch];
+    if (tid == 0) v[3] = elm_known ? elm_value : ws[kWsScratch] + ws[kWsScratch + 3];
     for (int64_t c = tid; c < C; c += nth) {
         const double s1 = S1[c], s2 = S2[c];
 #pragma unroll
@@ -161,21 +192,29 @@ static inline int red_grid(int64_t work_items, int items_per_block) {
     return (int)(need < cap ? need : cap);
 }
 
-static int launch_elm(const double* bt, int64_t C, int32_t U, int64_t pitchU,
+static int launch_elm(const double* Ea, const double* Eb, const double* Tm,
+                      int64_t C, int32_t U, int64_t pitchU,
                       const double* qF, const double* qR, int32_t N, int64_t c0,
-                      const ThetaDev& th, bool grad, double* out3, double* ws, cudaStream_t st) {
+                      const ThetaDev& th, bool grad, double* Aout, double* out4, double* ws, cudaStream_t st) {
     const double* tab = log_table(st);
     FCD_REQUIRE(tab != nullptr, "fcd_elm_obj_grad: log table initialisation failed");
+    FCD_REQUIRE(grad || Tm != nullptr, "fcd_elm_obj_grad: nothing to compute (no gradient, no Tm)");
     int grid = red_grid(C, kRedThreads / 32);
     if (grid > sm_count() * 4) grid = sm_count() * 4;
-    const bool vec2 = (pitchU % 2 == 0) && ((reinterpret_cast<uintptr_t>(bt) & 15) == 0);
+    uintptr_t al = reinterpret_cast<uintptr_t>(Ea) | reinterpret_cast<uintptr_t>(Eb) | reinterpret_cast<uintptr_t>(Tm);
+    const bool vec2 = (pitchU % 2 == 0) && ((al & 15) == 0);
     const bool fast = log_table_covers(th.epsl, th.al);
-#define FCD_ELM(G, V, F)                                                          \
-    elm_kernel<G, V, F><<<grid, kRedThreads, 0, st>>>(bt, C, U, pitchU, qF, qR, N, c0, th, tab, out3, 0, ws)
-#define FCD_ELM_F(G, V) do { if (fast) FCD_ELM(G, V, true); else FCD_ELM(G, V, false); } while (0)
-    if (grad) { if (vec2) FCD_ELM_F(true, true); else FCD_ELM_F(true, false); }
-    else      { if (vec2) FCD_ELM_F(false, true); else FCD_ELM_F(false, false); }
-#undef FCD_ELM_F
+#define FCD_ELM(G, K, V, F)                                                                        \
+    elm_kernel<G, K, V, F><<<grid, kRedThreads, 0, st>>>(Ea, Eb, Tm, C, U, pitchU, qF, qR, N, c0, th, tab, \
+                                                         Aout, out4, ws)
+#define FCD_ELM_VF(G, K)                                                                           \
+    do {                                                                                           \
+        if (vec2) { if (fast) FCD_ELM(G, K, true, true); else FCD_ELM(G, K, true, false); }        \
+        else      { if (fast) FCD_ELM(G, K, false, true); else FCD_ELM(G, K, false, false); }      \
+    } while (0)
+    if (grad) { if (Tm != nullptr) FCD_ELM_VF(true, true); else FCD_ELM_VF(true, false); }
+    else      FCD_ELM_VF(false, true);
+#undef FCD_ELM_VF
 #undef FCD_ELM
     return check_launch("fcd_elm_obj_grad");
 }
@@ -195,33 +234,40 @@ int fcd_mstep_stats(const double* lqF, int64_t C, const double* lqR, int64_t NU,
     return check_launch("fcd_mstep_stats");
 }
 
-int fcd_elm_obj_grad(const double* bt, int64_t C, int32_t U, int64_t pitchU,
+int fcd_elm_obj_grad(const double* Ea, const double* Eb, const double* Tm,
+                     int64_t C, int32_t U, int64_t pitchU,
                      const double* qF, const double* qR, int32_t N, int64_t c0,
                      const fcd_theta* theta_host, int32_t want_grad,
-                     double* out3, double* ws, void* stream) {
-    FCD_REQUIRE(theta_host != nullptr && ws != nullptr, "fcd_elm_obj_grad: NULL argument");
+                     double* Aout, double* out4, double* ws, void* stream) {
+    FCD_REQUIRE(theta_host != nullptr && ws != nullptr && Ea != nullptr && Eb != nullptr,
+                "fcd_elm_obj_grad: NULL argument");
     FCD_REQUIRE(C >= 0 && U >= 1 && pitchU >= U && N >= 2, "fcd_elm_obj_grad: bad shape");
     FCD_REQUIRE(c0 >= 0 && c0 + C <= (int64_t)N * (N - 1) / 2, "fcd_elm_obj_grad: edge shard outside N=%d", N);
     const ThetaDev th = make_theta_dev(*theta_host, 0);
-    return launch_elm(bt, C, U, pitchU, qF, qR, N, c0, th, want_grad != 0, out3, ws, (cudaStream_t)stream);
+    return launch_elm(Ea, Eb, Tm, C, U, pitchU, qF, qR, N, c0, th, want_grad != 0, Aout, out4, ws,
+                      (cudaStream_t)stream);
 }
 
 int fcd_energy_terms(const double* S1, const double* S2, int32_t H,
-                     const double* bt, int64_t C, int32_t U, int64_t pitchU,
+                     const double* Ea, const double* Eb, const double* Tm,
+                     int64_t C, int32_t U, int64_t pitchU,
                      const double* lqF, const double* qF, const double* lqR, const double* qR,
-                     int32_t N, int64_t c0, const fcd_theta* theta_host,
+                     int32_t N, int64_t c0, const fcd_theta* theta_host, const double* elm_host,
                      double* out6, double* ws, void* stream) {
     FCD_REQUIRE(theta_host != nullptr && ws != nullptr, "fcd_energy_terms: NULL argument");
     FCD_REQUIRE(C >= 0 && U >= 1 && pitchU >= U && N >= 2 && H >= 1, "fcd_energy_terms: bad shape");
     FCD_REQUIRE(c0 >= 0 && c0 + C <= (int64_t)N * (N - 1) / 2, "fcd_energy_terms: edge shard outside N=%d", N);
     const ThetaDev th = make_theta_dev(*theta_host, H);
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = launch_elm(bt, C, U, pitchU, qF, qR, N, c0, th, false, ws + kWsScratch, ws, st);
-    if (rc) return rc;
+    if (elm_host == nullptr) {      // otherwise E_lM of this shard is known from the last K3b evaluation
+        FCD_REQUIRE(Ea != nullptr && Eb != nullptr && Tm != nullptr, "fcd_energy_terms: cache planes are NULL");
+        int rc = launch_elm(Ea, Eb, Tm, C, U, pitchU, qF, qR, N, c0, th, false, nullptr, ws + kWsScratch, ws, st);
+        if (rc) return rc;
+    }
     const int64_t NU = (int64_t)N * U;
     const int64_t work = C > NU ? C : NU;
     energy_small_kernel<<<red_grid(work, kRedThreads), kRedThreads, 0, st>>>(
-        S1, S2, lqF, qF, C, lqR, qR, NU, th, out6, ws);
+        S1, S2, lqF, qF, C, lqR, qR, NU, th, elm_host != nullptr, elm_host ? *elm_host : 0.0, out6, ws);
     return check_launch("fcd_energy_terms");
 }
 

@@ -55,20 +55,24 @@ def _pi2(pi):
 class _Mirror(object):
     """A log-probability array living on the host, the device, or both.
     Device side holds the log array and its exponential (the reference forms
-    ``q = np.exp(lq)`` at every use, fit.py:146-147, 166, 181-182)."""
+    ``q = np.exp(lq)`` at every use, fit.py:146-147, 166, 181-182).  ``version``
+    counts assignments (used to know when cached per-edge sums are still valid)."""
 
     def __init__(self):
         self.host = None
         self.dev = None      # (lq, q) device tensors, flat
+        self.version = 0
 
     def set_host(self, a):
         self.host = a
         self.dev = None
+        self.version += 1
 
     def set_dev(self, lq, q, shape):
         self.dev = (lq, q)
         self.shape = shape
         self.host = None
+        self.version += 1
 
     def get_host(self):
         if self.host is None and self.dev is not None:
@@ -133,6 +137,9 @@ class UnsharedRegionFit(object):
         self._mat = None              # materialised caches (host) for the getters
         self._theta_lps = None        # (mu, sigma, eta, epsilon) at the last _update_lps
         self._in = None               # uploaded inputs
+        self._evals = []              # recent K3b evaluations (per-edge sums reusable by K2 / K4)
+        self._const = None            # theta-free part of E_lM for the current (q_F, q_R)
+        self.reuse_evaluations = True
 
     # ------------------------------------------------------------------ private arrays
     @property
@@ -236,32 +243,67 @@ class UnsharedRegionFit(object):
                                              _dev.stream()), "fcd_healthy_stats")
         del b_dev
         self._in = dict(key=key, C=C, H=H, U=U, c0=c0, Cl=Cl, u0=u0, Ul=Ul, pitchU=pitchU,
-                        bt=bt_dev, S1=S1, S2=S2, btT=None, WT=None)
+                        bt=bt_dev, S1=S1, S2=S2, cache_key=None, Ea=None, Eb=None, Tm=None,
+                        EaT=None, EbT=None, WT=None, A=[None, None, None], A_next=0)
+        self._evals = []
+        self._const = None
         return self._in
 
+    def _ensure_cache(self):
+        """Gaussian cache planes Ea / Eb / Tm of the local edge rows for the
+        (mu, sigma) of the last ``_update_lps`` (rebuilt only when they change;
+        the reference never changes them, fit.py:232-237)."""
+        inp = self._ensure_inputs()
+        (mu, sigma, _, _) = self._theta_lps
+        ckey = (tuple(float(v) for v in mu), tuple(float(v) for v in sigma))
+        if inp['cache_key'] == ckey:
+            return inp
+        lib = _lib.load()
+        (Cl, U, pitchU) = (inp['Cl'], inp['U'], inp['pitchU'])
+        for name in ('Ea', 'Eb', 'Tm'):
+            if inp[name] is None:
+                inp[name] = _dev.empty((Cl, pitchU))
+        th = self._theta()
+        with _dev.timed(self.profile, "K0_gauss_cache"):
+            _lib.check(lib.fcd_gauss_cache(_dev.ptr(inp['bt']), Cl, U, pitchU, ctypes.byref(th),
+                                           _dev.ptr(inp['Ea']), _dev.ptr(inp['Eb']), _dev.ptr(inp['Tm']),
+                                           _dev.stream()), "fcd_gauss_cache")
+        inp['cache_key'] = ckey
+        inp['EaT'] = inp['EbT'] = None
+        self._evals = []
+        self._const = None
+        return inp
+
     def _ensure_patient_major(self):
-        """Patient-major copy btT [U_local][C] of ALL edges (for K2b)."""
-        inp = self._in
-        if inp['btT'] is not None:
+        """Patient-major cache planes EaT / EbT [U_local][C] of ALL edges (K2b)."""
+        inp = self._ensure_cache()
+        if inp['EaT'] is not None:
             return inp
         lib = _lib.load()
         (C, U, u0, Ul) = (inp['C'], inp['U'], inp['u0'], inp['Ul'])
-        if inp['Cl'] == C and self.shards is None:
-            src, pitchU, uu0 = inp['bt'], inp['pitchU'], u0
-        elif torch.is_tensor(self.bt):
-            # edge-sharded device input: one all-to-all of (C_local x U_peer) blocks
-            src = self.shards.exchange_patient_blocks(inp['bt'], inp['Cl'], C, U)
-            pitchU, uu0, U = Ul, 0, Ul
-        else:   # edge-sharded host input: this rank uploads every edge of its own patients
-            src = _dev.upload(np.ascontiguousarray(np.asarray(self.bt)[:, u0:u0 + Ul]))
-            pitchU, uu0, U = Ul, 0, Ul
-        btT = _dev.empty((Ul, C))
+        if self.shards is None:
+            (srcA, srcB, pitchU, uu0, Us) = (inp['Ea'], inp['Eb'], inp['pitchU'], u0, U)
+        else:
+            if torch.is_tensor(self.bt):
+                # edge-sharded device input: one all-to-all of (C_local x U_peer) blocks of bt
+                blk = self.shards.exchange_patient_blocks(inp['bt'], inp['Cl'], C, U)
+            else:   # edge-sharded host input: this rank uploads every edge of its own patients
+                blk = _dev.upload(np.ascontiguousarray(np.asarray(self.bt)[:, u0:u0 + Ul]))
+            (srcA, srcB) = (_dev.empty((C, max(Ul, 1))), _dev.empty((C, max(Ul, 1))))
+            if Ul > 0:
+                th = self._theta()
+                _lib.check(lib.fcd_gauss_cache(_dev.ptr(blk), C, Ul, Ul, ctypes.byref(th), _dev.ptr(srcA),
+                                               _dev.ptr(srcB), None, _dev.stream()), "fcd_gauss_cache")
+            (pitchU, uu0, Us) = (Ul, 0, Ul)
+        (EaT, EbT) = (_dev.empty((Ul, C)), _dev.empty((Ul, C)))
         if Ul > 0:
             with _dev.timed(self.profile, "K0_transpose"):
-                _lib.check(lib.fcd_transpose_patients(_dev.ptr(src), C, U, pitchU, uu0, Ul, _dev.ptr(btT), C,
-                                                      _dev.stream()), "fcd_transpose_patients")
-        inp['btT'] = btT
-        inp['WT'] = _dev.empty((Ul, C, 3))
+                for (src, dst) in ((srcA, EaT), (srcB, EbT)):
+                    _lib.check(lib.fcd_transpose_patients(_dev.ptr(src), C, Us, pitchU, uu0, Ul, _dev.ptr(dst), C,
+                                                          _dev.stream()), "fcd_transpose_patients")
+        inp['EaT'], inp['EbT'] = EaT, EbT
+        if inp['WT'] is None:
+            inp['WT'] = _dev.empty((Ul, C, 3))
         return inp
 
     def _theta(self, use_snapshot=True):
@@ -389,21 +431,38 @@ class UnsharedRegionFit(object):
         energy += t[5]
         return float(energy)
 
+    def _find_eval(self, need_F):
+        """A recent K3b evaluation made at the current (eta, epsilon) snapshot with
+        the current q_R (and q_F when ``need_F``): its per-edge sums A[c][k] and
+        its E_lM are exactly what K2 / K4 would recompute."""
+        if not self.reuse_evaluations or self._theta_lps is None:
+            return None
+        (_, _, eta, epsilon) = self._theta_lps
+        for ev in reversed(self._evals):
+            if ev['x'] == (eta, epsilon) and ev['verR'] == self._mR.version and \
+                    (not need_F or ev['verF'] == self._mF.version):
+                return ev
+        return None
+
     def _energy_terms(self):
         """The six terms of fit.py:149-154 from the fused K4 kernels."""
         lib = _lib.load()
-        inp = self._ensure_inputs()
+        inp = self._ensure_cache()
         (N, H, U) = self._dims
         (lqF, qF) = self._mF.get_dev()
         (lqR, qR) = self._mR.get_dev()
         (c0, Cl) = (inp['c0'], inp['Cl'])
         th = self._theta()
         out = _dev.empty((6,))
-        with _dev.timed(self.profile, "K4_energy_terms"):
+        ev = self._find_eval(need_F=True)
+        elm = None if ev is None else ctypes.byref(ctypes.c_double(ev['elm_local']))
+        with _dev.timed(self.profile, "K4_energy_terms" if ev is None else "K4_energy_small"):
             _lib.check(lib.fcd_energy_terms(
-                _dev.ptr(inp['S1']), _dev.ptr(inp['S2']), H, _dev.ptr(inp['bt']), Cl, U, inp['pitchU'],
+                _dev.ptr(inp['S1']), _dev.ptr(inp['S2']), H, _dev.ptr(inp['Ea']), _dev.ptr(inp['Eb']),
+                _dev.ptr(inp['Tm']), Cl, U, inp['pitchU'],
                 _dev.ptr(lqF[c0 * 3:]), _dev.ptr(qF[c0 * 3:]), _dev.ptr(lqR), _dev.ptr(qR), N, c0,
-                ctypes.byref(th), _dev.ptr(out), _dev.ptr(_dev.workspace()), _dev.stream()), "fcd_energy_terms")
+                ctypes.byref(th), elm, _dev.ptr(out), _dev.ptr(_dev.workspace()), _dev.stream()),
+                "fcd_energy_terms")
         if self.shards is not None:
             out = self.shards.allreduce_terms(out, (0, 1, 3, 4))
         return _dev.download(out)
@@ -429,18 +488,25 @@ class UnsharedRegionFit(object):
                 _dev.ptr(lqF), _dev.stream()), "fcd_lqF_from_arrays")
             self._mF.set_host(_dev.download(lqF).reshape(C, 1, 3))
             return
-        inp = self._ensure_inputs()
+        inp = self._ensure_cache()
         (N, H, U) = self._dims
         (C, c0, Cl) = (inp['C'], inp['c0'], inp['Cl'])
         (lqR, qR) = self._mR.get_dev()
         lqF = _dev.empty((C * 3,))
         qF = _dev.empty((C * 3,))
         th = self._theta()
-        with _dev.timed(self.profile, "K2_estep_qF"):
-            _lib.check(lib.fcd_estep_qF(
-                _dev.ptr(inp['S1']), _dev.ptr(inp['S2']), H, _dev.ptr(inp['bt']), Cl, U, inp['pitchU'],
-                _dev.ptr(qR), N, c0, ctypes.byref(th), _dev.ptr(lqF[c0 * 3:]), _dev.ptr(qF[c0 * 3:]),
-                _dev.stream()), "fcd_estep_qF")
+        ev = self._find_eval(need_F=False)
+        if ev is not None:
+            with _dev.timed(self.profile, "K2_estep_qF_finish"):
+                _lib.check(lib.fcd_estep_qF_finish(
+                    _dev.ptr(inp['S1']), _dev.ptr(inp['S2']), H, _dev.ptr(ev['A']), Cl, ctypes.byref(th),
+                    _dev.ptr(lqF[c0 * 3:]), _dev.ptr(qF[c0 * 3:]), _dev.stream()), "fcd_estep_qF_finish")
+        else:
+            with _dev.timed(self.profile, "K2_estep_qF"):
+                _lib.check(lib.fcd_estep_qF(
+                    _dev.ptr(inp['S1']), _dev.ptr(inp['S2']), H, _dev.ptr(inp['Ea']), _dev.ptr(inp['Eb']),
+                    Cl, U, inp['pitchU'], _dev.ptr(qR), N, c0, ctypes.byref(th),
+                    _dev.ptr(lqF[c0 * 3:]), _dev.ptr(qF[c0 * 3:]), _dev.stream()), "fcd_estep_qF")
         if self.shards is not None:
             self.shards.allgather_edges(lqF, qF, C)
         self._mF.set_dev(lqF, qF, (C, 1, 3))
@@ -469,7 +535,6 @@ class UnsharedRegionFit(object):
                                             _dev.ptr(lqR_new), _dev.stream()), "fcd_estep_qR")
             self._mR.set_dev(lqR_new, qR_new, (N, U, 2))
             return
-        self._ensure_inputs()
         inp = self._ensure_patient_major()
         (N, H, U) = self._dims
         (C, u0, Ul) = (inp['C'], inp['u0'], inp['Ul'])
@@ -477,8 +542,9 @@ class UnsharedRegionFit(object):
         (lqR, qR) = self._mR.get_dev()
         th = self._theta()
         with _dev.timed(self.profile, "K2b_region_weights"):
-            _lib.check(lib.fcd_region_weights(_dev.ptr(inp['btT']), Ul, C, C, _dev.ptr(qF), ctypes.byref(th),
-                                              _dev.ptr(inp['WT']), _dev.stream()), "fcd_region_weights")
+            _lib.check(lib.fcd_region_weights(_dev.ptr(inp['EaT']), _dev.ptr(inp['EbT']), Ul, C, C,
+                                              _dev.ptr(qF), ctypes.byref(th), _dev.ptr(inp['WT']),
+                                              _dev.stream()), "fcd_region_weights")
         lqR_new, qR_new = lqR.clone(), qR.clone()
         with _dev.timed(self.profile, "K2b_sweep"):
             _lib.check(lib.fcd_estep_qR(_dev.ptr(inp['WT']), C, N, U, u0, Ul, log_pi2, lookup,
@@ -537,9 +603,11 @@ class UnsharedRegionFit(object):
 
     def _objective(self, theta_sub, want_grad=True):
         """(-E_lM, gradient) at theta_sub = [eta, epsilon] from one fused pass
-        over the patient correlations (K3b)."""
+        over the cache planes (K3b).  The pass also leaves the per-edge sums
+        A[c][k], which the next K2 and the energy reuse when (eta, epsilon) ends
+        up being the optimiser's answer."""
         lib = _lib.load()
-        inp = self._ensure_inputs()
+        inp = self._ensure_cache()
         (N, H, U) = self._dims
         (c0, Cl) = (inp['c0'], inp['Cl'])
         (_, qF) = self._mF.get_dev()
@@ -547,15 +615,31 @@ class UnsharedRegionFit(object):
         th = self._theta()
         th.eta = float(theta_sub[0])
         th.epsilon = float(theta_sub[1])
-        out = _dev.empty((3,))
+        ckey = (self._mF.version, self._mR.version, inp['cache_key'])
+        need_const = self._const is None or self._const[0] != ckey
+        slot = inp['A_next']
+        inp['A_next'] = (slot + 1) % len(inp['A'])
+        if inp['A'][slot] is None:
+            inp['A'][slot] = _dev.empty((max(Cl, 1) * 3,))
+        A = inp['A'][slot]
+        self._evals = [ev for ev in self._evals if ev['A'] is not A]
+        out = _dev.empty((4,))
         with _dev.timed(self.profile, "K3b_elm_obj_grad"):
             _lib.check(lib.fcd_elm_obj_grad(
-                _dev.ptr(inp['bt']), Cl, U, inp['pitchU'], _dev.ptr(qF[c0 * 3:]), _dev.ptr(qR), N, c0,
-                ctypes.byref(th), 1 if want_grad else 0, _dev.ptr(out), _dev.ptr(_dev.workspace()),
-                _dev.stream()), "fcd_elm_obj_grad")
+                _dev.ptr(inp['Ea']), _dev.ptr(inp['Eb']),
+                _dev.ptr(inp['Tm']) if (need_const or not want_grad) else None,
+                Cl, U, inp['pitchU'], _dev.ptr(qF[c0 * 3:]), _dev.ptr(qR), N, c0,
+                ctypes.byref(th), 1 if want_grad else 0, _dev.ptr(A), _dev.ptr(out),
+                _dev.ptr(_dev.workspace()), _dev.stream()), "fcd_elm_obj_grad")
+        o_local = _dev.download(out)
+        if need_const or not want_grad:
+            self._const = (ckey, float(o_local[3]))
+        elm_local = float(o_local[0]) + self._const[1]
+        self._evals.append(dict(x=(th.eta, th.epsilon), verF=self._mF.version, verR=self._mR.version,
+                                A=A, elm_local=elm_local))
+        o = np.array([elm_local, o_local[1], o_local[2]])
         if self.shards is not None:
-            out = self.shards.allreduce_terms(out, (0, 1, 2))
-        o = _dev.download(out)
+            o = _dev.download(self.shards.allreduce_terms(_dev.upload(o), (0, 1, 2)))
         return -float(o[0]), np.array([o[1], o[2]])
 
     def _update_theta_sub(self):

@@ -369,35 +369,48 @@ def test_config3_properties(N, H, U):
     nptest.assert_array_equal(fit2._lq_R, fit._lq_R)
     assert fit2.energy == fit.energy
     # -- shard additivity of K3b / K4: sum over 3 ragged edge shards == whole
-    inp = fit._in
+    inp = fit._ensure_cache()
     (lqF, qF) = fit._mF.get_dev()
     (lqR, qR) = fit._mR.get_dev()
     th = fit._theta()
     ws = _dev.workspace()
-    whole = _dev.empty((6,))
-    _lib.check(lib.fcd_energy_terms(_dev.ptr(inp['S1']), _dev.ptr(inp['S2']), H, _dev.ptr(inp['bt']), C, U,
-                                    inp['pitchU'], _dev.ptr(lqF), _dev.ptr(qF), _dev.ptr(lqR), _dev.ptr(qR),
-                                    N, 0, ctypes.byref(th), _dev.ptr(whole), _dev.ptr(ws), _dev.stream()))
-    parts = np.zeros(6)
-    cuts = [0, 1234, 40001, C]
-    for (a, e) in zip(cuts[:-1], cuts[1:]):
-        part = _dev.empty((6,))
+    P = inp['pitchU']
+
+    def energy_terms(a, e):
+        out = _dev.empty((6,))
         _lib.check(lib.fcd_energy_terms(
-            _dev.ptr(inp['S1'][a:]), _dev.ptr(inp['S2'][a:]), H, _dev.ptr(inp['bt'][a:]), e - a, U,
-            inp['pitchU'], _dev.ptr(lqF[a * 3:]), _dev.ptr(qF[a * 3:]), _dev.ptr(lqR), _dev.ptr(qR),
-            N, a, ctypes.byref(th), _dev.ptr(part), _dev.ptr(ws), _dev.stream()))
-        parts += _dev.download(part)
-    w = _dev.download(whole)
+            _dev.ptr(inp['S1'][a:]), _dev.ptr(inp['S2'][a:]), H, _dev.ptr(inp['Ea'][a:]), _dev.ptr(inp['Eb'][a:]),
+            _dev.ptr(inp['Tm'][a:]), e - a, U, P, _dev.ptr(lqF[a * 3:]), _dev.ptr(qF[a * 3:]), _dev.ptr(lqR),
+            _dev.ptr(qR), N, a, ctypes.byref(th), None, _dev.ptr(out), _dev.ptr(ws), _dev.stream()))
+        return _dev.download(out)
+
+    w = energy_terms(0, C)
+    cuts = [0, 1234, 40001, C]
+    parts = sum(energy_terms(a, e) for (a, e) in zip(cuts[:-1], cuts[1:]))
     nptest.assert_allclose(parts[[0, 1, 3, 4]], w[[0, 1, 3, 4]], rtol=1e-12)
     nptest.assert_allclose(parts[[2, 5]] / 3, w[[2, 5]], rtol=1e-12)     # q_R-only terms are complete per shard
-    # -- K2 on a shard equals the slice of the whole
+    # -- the energy from a reused K3b evaluation equals the energy from a fresh K4 pass
+    nptest.assert_allclose(energy_terms(0, C)[3], fit._energy_terms()[3], rtol=1e-13)
+    fit.reuse_evaluations = False
+    e_fresh = fit._eval_energy()
+    fit.reuse_evaluations = True
+    nptest.assert_allclose(fit._eval_energy(), e_fresh, rtol=1e-13)
+    nptest.assert_allclose(fit.energy[-1], e_fresh, rtol=1e-13)
+    # -- K2 on a shard equals the slice of the whole; K2 from reused per-edge sums equals a fresh pass
     (a, e) = (40001, C)
-    lq_part = _dev.empty(((e - a) * 3,))
     qR_prev = _dev.upload(np.full((N, U, 2), 0.5).reshape(-1))
-    lq_whole = _dev.empty((C * 3,))
-    _lib.check(lib.fcd_estep_qF(_dev.ptr(inp['S1']), _dev.ptr(inp['S2']), H, _dev.ptr(inp['bt']), C, U, inp['pitchU'],
-                                _dev.ptr(qR_prev), N, 0, ctypes.byref(th), _dev.ptr(lq_whole), None, _dev.stream()))
-    _lib.check(lib.fcd_estep_qF(_dev.ptr(inp['S1'][a:]), _dev.ptr(inp['S2'][a:]), H, _dev.ptr(inp['bt'][a:]), e - a, U,
-                                inp['pitchU'], _dev.ptr(qR_prev), N, a, ctypes.byref(th), _dev.ptr(lq_part), None,
-                                _dev.stream()))
-    nptest.assert_array_equal(_dev.download(lq_part), _dev.download(lq_whole)[a * 3:])
+
+    def estep(a, e):
+        lq = _dev.empty(((e - a) * 3,))
+        _lib.check(lib.fcd_estep_qF(_dev.ptr(inp['S1'][a:]), _dev.ptr(inp['S2'][a:]), H, _dev.ptr(inp['Ea'][a:]),
+                                    _dev.ptr(inp['Eb'][a:]), e - a, U, P, _dev.ptr(qR_prev), N, a,
+                                    ctypes.byref(th), _dev.ptr(lq), None, _dev.stream()))
+        return _dev.download(lq)
+
+    nptest.assert_array_equal(estep(a, e), estep(0, C)[a * 3:])
+    assert fit._find_eval(need_F=False) is not None
+    fit._update_lq_F()                       # finish kernel from the cached per-edge sums
+    lq_reused = fit._lq_F.copy()
+    fit.reuse_evaluations = False
+    fit._update_lq_F()                       # full K2 pass
+    nptest.assert_allclose(lq_reused, fit._lq_F, rtol=1e-12, atol=1e-12)
