@@ -154,6 +154,83 @@ __device__ __forceinline__ void pair_weights(double2 qn, double2 qm, double (&w)
     w[2] = fma(qn.y, qm.x, qn.x * qm.y);
 }
 
+// Row walker shared by K2 / K3b / K4: every warp takes edge rows c = warp0,
+// warp0 + nwarps, ...; within a row each lane owns the patients u = 2*lane,
+// 2*lane + 1 (+64 per chunk), loaded with 128-bit requests (cache planes:
+// ld.global.nc.L1::no_allocate; q_R rows of the edge's two regions: ld.global.nc).
+// The loads of chunk j+1 (also across the row boundary) are issued before chunk
+// j is computed, so the DRAM latency overlaps the ~400-cycle fp64 body instead
+// of stalling its first use (ncu: 24 % of the samples before this change).
+// Elements beyond U are presented with zero q_R, i.e. zero pair weights.
+struct RowChunk {
+    double2 xa, xb, tm, a0, a1, b0, b1;
+};
+
+template <bool WITH_TM>
+__device__ __forceinline__ RowChunk load_chunk(const double* __restrict__ Ea, const double* __restrict__ Eb,
+                                               const double* __restrict__ Tm, int64_t row_off,
+                                               const double2* __restrict__ qn, const double2* __restrict__ qm,
+                                               int u, int U) {
+    RowChunk k;
+    const double2 z = make_double2(0.0, 0.0);
+    k.xa = k.xb = k.tm = k.a0 = k.a1 = k.b0 = k.b1 = z;
+    if (u < U) {
+        k.xa = ldg_stream2(Ea + row_off + u);
+        k.xb = ldg_stream2(Eb + row_off + u);
+        if (WITH_TM) k.tm = ldg_stream2(Tm + row_off + u);
+        k.a0 = __ldg(qn + u);
+        k.b0 = __ldg(qm + u);
+        if (u + 1 < U) {
+            k.a1 = __ldg(qn + u + 1);
+            k.b1 = __ldg(qm + u + 1);
+        }
+    }
+    return k;
+}
+
+// elem(ea, ebc, tm, qn, qm) is called for every (possibly zero-weight) element,
+// row_end(c) once per row after its last element.  Requires pitchU even and
+// 16-byte aligned planes.
+template <bool WITH_TM, class ElemFn, class RowFn>
+__device__ __forceinline__ void walk_rows(const double* __restrict__ Ea, const double* __restrict__ Eb,
+                                          const double* __restrict__ Tm, int64_t C, int U, int64_t pitchU,
+                                          const double* __restrict__ qR, int64_t c0,
+                                          ElemFn&& elem, RowFn&& row_end) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const double2* qR2 = reinterpret_cast<const double2*>(qR);
+    int64_t c = warp0;
+    if (c >= C) return;
+    int n, m;
+    c_to_nm(c0 + c, n, m);
+    const double2* qn = qR2 + (int64_t)n * U;
+    const double2* qm = qR2 + (int64_t)m * U;
+    RowChunk cur = load_chunk<WITH_TM>(Ea, Eb, Tm, c * pitchU, qn, qm, 2 * lane, U);
+    while (c < C) {
+        const int64_t cn = c + nwarps;
+        const double2 *qn2 = qn, *qm2 = qm;
+        if (cn < C) {
+            c_to_nm(c0 + cn, n, m);
+            qn2 = qR2 + (int64_t)n * U;
+            qm2 = qR2 + (int64_t)m * U;
+        }
+        for (int u0 = 0; u0 < U; u0 += 64) {
+            RowChunk nxt;
+            if (u0 + 64 < U) nxt = load_chunk<WITH_TM>(Ea, Eb, Tm, c * pitchU, qn, qm, u0 + 64 + 2 * lane, U);
+            else if (cn < C) nxt = load_chunk<WITH_TM>(Ea, Eb, Tm, cn * pitchU, qn2, qm2, 2 * lane, U);
+            else nxt = cur;
+            elem(cur.xa.x, cur.xb.x, cur.tm.x, cur.a0, cur.b0);
+            elem(cur.xa.y, cur.xb.y, cur.tm.y, cur.a1, cur.b1);
+            cur = nxt;
+        }
+        row_end(c);
+        c = cn;
+        qn = qn2;
+        qm = qm2;
+    }
+}
+
 // Deterministic grid reduction: every CTA reduces NV values, writes its partial
 // to ws[blockIdx.x*NV + i]; the CTA that arrives last sums the partials in a
 // fixed order and writes out[0..NV).  The ticket (ws[kWsPartials]) is restored

@@ -114,38 +114,33 @@ estep_qF_kernel(const double* __restrict__ S1, const double* __restrict__ S2,
     __shared__ double s_tab[FAST ? kLogTabSize : 1];
     load_log_table<FAST>(g_tab, s_tab);
     const int lane = threadIdx.x & 31;
-    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const double2* qR2 = reinterpret_cast<const double2*>(qR);
-    for (int64_t c = warp0; c < C; c += nwarps) {
-        int n, m;
-        c_to_nm(c0 + c, n, m);
-        const double* ra = Ea + c * pitchU;
-        const double* rb = Eb + c * pitchU;
-        const double2* qn = qR2 + (int64_t)n * U;
-        const double2* qm = qR2 + (int64_t)m * U;
-        double acc[3] = {0.0, 0.0, 0.0};
-        if (VEC2) {
-            for (int u = 2 * lane; u < U; u += 64) {
-                if (u + 1 < U) {
-                    const double2 xa = ldg_stream2(ra + u), xb = ldg_stream2(rb + u);
-                    const double2 a0 = __ldg(qn + u), a1 = __ldg(qn + u + 1);
-                    const double2 b0 = __ldg(qm + u), b1 = __ldg(qm + u + 1);
-                    k2_elem<FAST>(xa.x, xb.x, a0, b0, th, s_tab, acc);
-                    k2_elem<FAST>(xa.y, xb.y, a1, b1, th, s_tab, acc);
-                } else {
-                    k2_elem<FAST>(ldg_stream1(ra + u), ldg_stream1(rb + u), __ldg(qn + u), __ldg(qm + u),
-                                  th, s_tab, acc);
-                }
-            }
-        } else {
-            for (int u = lane; u < U; u += 32)
-                k2_elem<FAST>(ldg_stream1(ra + u), ldg_stream1(rb + u), __ldg(qn + u), __ldg(qm + u),
-                              th, s_tab, acc);
-        }
+    double acc[3] = {0.0, 0.0, 0.0};
+    auto row_end = [&](int64_t c) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) acc[k] = warp_sum(acc[k]);
         if (lane == 0) k2_finish(c, acc, S1[c], S2[c], th, lqF, qF);
+        acc[0] = acc[1] = acc[2] = 0.0;
+    };
+    if (VEC2) {
+        walk_rows<false>(Ea, Eb, nullptr, C, U, pitchU, qR, c0,
+                         [&](double ea, double ebc, double, double2 qn, double2 qm) {
+                             k2_elem<FAST>(ea, ebc, qn, qm, th, s_tab, acc);
+                         },
+                         row_end);
+    } else {
+        const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+        const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+        const double2* qR2 = reinterpret_cast<const double2*>(qR);
+        for (int64_t c = warp0; c < C; c += nwarps) {
+            int n, m;
+            c_to_nm(c0 + c, n, m);
+            const double2* qn = qR2 + (int64_t)n * U;
+            const double2* qm = qR2 + (int64_t)m * U;
+            for (int u = lane; u < U; u += 32)
+                k2_elem<FAST>(ldg_stream1(Ea + c * pitchU + u), ldg_stream1(Eb + c * pitchU + u),
+                              __ldg(qn + u), __ldg(qm + u), th, s_tab, acc);
+            row_end(c);
+        }
     }
 }
 

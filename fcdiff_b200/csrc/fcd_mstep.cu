@@ -74,7 +74,7 @@ __device__ __forceinline__ void k3_elem(double ea, double ebc, double2 qn, doubl
 }
 
 template <bool GRAD, bool CONST, bool VEC2, bool FAST>
-__global__ void __launch_bounds__(kRedThreads)
+__global__ void __launch_bounds__(kRedThreads, 2)
 elm_kernel(const double* __restrict__ Ea, const double* __restrict__ Eb, const double* __restrict__ Tm,
            int64_t C, int U, int64_t pitchU,
            const double* __restrict__ qF, const double* __restrict__ qR, int N, int64_t c0,
@@ -83,47 +83,17 @@ elm_kernel(const double* __restrict__ Ea, const double* __restrict__ Eb, const d
     __shared__ double s_tab[FAST ? kLogTabSize : 1];
     load_log_table<FAST>(g_tab, s_tab);
     const int lane = threadIdx.x & 31;
-    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const double2* qR2 = reinterpret_cast<const double2*>(qR);
     const double s2 = 2.0 * th.eta - 1.0;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int64_t c = warp0; c < C; c += nwarps) {
-        int n, m;
-        c_to_nm(c0 + c, n, m);
-        const double* ra = Ea + c * pitchU;
-        const double* rb = Eb + c * pitchU;
-        const double* rt = CONST ? Tm + c * pitchU : nullptr;
-        const double2* qn = qR2 + (int64_t)n * U;
-        const double2* qm = qR2 + (int64_t)m * U;
+    double A[3] = {0.0, 0.0, 0.0}, G[3] = {0.0, 0.0, 0.0}, Hh[3] = {0.0, 0.0, 0.0};
+    double cs = 0.0;
+    auto elem = [&](double ea, double ebc, double tm, double2 qn, double2 qm) {
+        double w[3];
+        k3_elem<GRAD, FAST>(ea, ebc, qn, qm, w, th, s2, s_tab, A, G, Hh);
+        if (CONST) cs = fma(w[0] + w[1] + w[2], tm - kHalfLog2Pi, cs);
+    };
+    auto row_end = [&](int64_t c) {
         const double qf[3] = {__ldg(qF + c * 3), __ldg(qF + c * 3 + 1), __ldg(qF + c * 3 + 2)};
-        double A[3] = {0.0, 0.0, 0.0}, G[3] = {0.0, 0.0, 0.0}, Hh[3] = {0.0, 0.0, 0.0};
-        double cs = 0.0, w[3];
-        if (VEC2) {
-            for (int u = 2 * lane; u < U; u += 64) {
-                if (u + 1 < U) {
-                    const double2 xa = ldg_stream2(ra + u), xb = ldg_stream2(rb + u);
-                    const double2 a0 = __ldg(qn + u), a1 = __ldg(qn + u + 1);
-                    const double2 b0 = __ldg(qm + u), b1 = __ldg(qm + u + 1);
-                    double2 tm;
-                    if (CONST) tm = ldg_stream2(rt + u);
-                    k3_elem<GRAD, FAST>(xa.x, xb.x, a0, b0, w, th, s2, s_tab, A, G, Hh);
-                    if (CONST) cs = fma(w[0] + w[1] + w[2], tm.x - kHalfLog2Pi, cs);
-                    k3_elem<GRAD, FAST>(xa.y, xb.y, a1, b1, w, th, s2, s_tab, A, G, Hh);
-                    if (CONST) cs = fma(w[0] + w[1] + w[2], tm.y - kHalfLog2Pi, cs);
-                } else {
-                    k3_elem<GRAD, FAST>(ldg_stream1(ra + u), ldg_stream1(rb + u), __ldg(qn + u), __ldg(qm + u),
-                                        w, th, s2, s_tab, A, G, Hh);
-                    if (CONST) cs = fma(w[0] + w[1] + w[2], ldg_stream1(rt + u) - kHalfLog2Pi, cs);
-                }
-            }
-        } else {
-            for (int u = lane; u < U; u += 32) {
-                k3_elem<GRAD, FAST>(ldg_stream1(ra + u), ldg_stream1(rb + u), __ldg(qn + u), __ldg(qm + u),
-                                    w, th, s2, s_tab, A, G, Hh);
-                if (CONST) cs = fma(w[0] + w[1] + w[2], ldg_stream1(rt + u) - kHalfLog2Pi, cs);
-            }
-        }
         if (Aout != nullptr) {                        // warp-uniform
 #pragma unroll
             for (int k = 0; k < 3; ++k) A[k] = warp_sum(A[k]);
@@ -140,6 +110,26 @@ elm_kernel(const double* __restrict__ Ea, const double* __restrict__ Eb, const d
             acc[2] -= fma(qf[0], G[0], fma(qf[1], G[1], qf[2] * G[2]));
         }
         if (CONST) acc[3] = fma(qf[0] + qf[1] + qf[2], cs, acc[3]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) A[k] = G[k] = Hh[k] = 0.0;
+        cs = 0.0;
+    };
+    if (VEC2) {
+        walk_rows<CONST>(Ea, Eb, Tm, C, U, pitchU, qR, c0, elem, row_end);
+    } else {
+        const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+        const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+        const double2* qR2 = reinterpret_cast<const double2*>(qR);
+        for (int64_t c = warp0; c < C; c += nwarps) {
+            int n, m;
+            c_to_nm(c0 + c, n, m);
+            const double2* qn = qR2 + (int64_t)n * U;
+            const double2* qm = qR2 + (int64_t)m * U;
+            for (int u = lane; u < U; u += 32)
+                elem(ldg_stream1(Ea + c * pitchU + u), ldg_stream1(Eb + c * pitchU + u),
+                     CONST ? ldg_stream1(Tm + c * pitchU + u) : 0.0, __ldg(qn + u), __ldg(qm + u));
+            row_end(c);
+        }
     }
     if (GRAD) acc[1] *= (2.0 * th.epsilon - 1.0);
     grid_reduce_store<4, kRedThreads>(acc, ws, out);
