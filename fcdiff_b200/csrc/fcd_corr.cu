@@ -13,11 +13,16 @@
 #include "fcd_common.cuh"
 #include "fcd_corr.cuh"
 
+#include <cstdlib>
+
 namespace fcd {
 
-// One warp per (subject, region) row.
+// One warp per (subject, region) row.  SPLIT: write the TF32 hi / lo parts
+// (both exactly representable in TF32) for the tensor-core path.
+template <bool SPLIT>
 __global__ void __launch_bounds__(256)
-standardise_kernel(const float* __restrict__ ts, int64_t rows, int T, int Tp, float* __restrict__ Z) {
+standardise_kernel(const float* __restrict__ ts, int64_t rows, int T, int Tp, float* __restrict__ Z,
+                   float* __restrict__ Zlo) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -33,8 +38,19 @@ standardise_kernel(const float* __restrict__ ts, int64_t rows, int T, int Tp, fl
         }
         ss = warp_sum(ss);
         const double inv = ss > 0.0 ? rsqrt(ss) : 0.0;
-        float* z = Z + r * Tp;
-        for (int t = lane; t < Tp; t += 32) z[t] = t < T ? (float)(((double)x[t] - mean) * inv) : 0.0f;
+        for (int t = lane; t < Tp; t += 32) {
+            const float z = t < T ? (float)(((double)x[t] - mean) * inv) : 0.0f;
+            if (SPLIT) {
+                uint32_t hb, lb;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(z));
+                const float zh = __uint_as_float(hb);
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(z - zh));
+                Z[r * Tp + t] = zh;
+                Zlo[r * Tp + t] = __uint_as_float(lb);
+            } else {
+                Z[r * Tp + t] = z;
+            }
+        }
     }
 }
 
@@ -93,28 +109,33 @@ extern "C" {
 
 int64_t fcd_corr_workspace_bytes(int32_t S, int32_t N, int32_t T) {
     if (S < 0 || N < 0 || T < 0) return -1;
-    return (int64_t)S * N * corr_padded_T(T) * (int64_t)sizeof(float) + 1024;
+    return 2 * ((int64_t)S * N * corr_padded_T(T) * (int64_t)sizeof(float) + 1024) + 1024;
 }
 
 int fcd_corr_fisherz(const float* ts, int32_t S, int32_t N, int32_t T,
                      double* out, int64_t pitch, int32_t s0, int32_t fisher,
                      void* zws, void* stream) {
     FCD_REQUIRE(ts != nullptr && out != nullptr && zws != nullptr, "fcd_corr_fisherz: NULL argument");
-    FCD_REQUIRE(S >= 0 && N >= 2 && T >= 2 && s0 >= 0 && pitch >= (int64_t)s0 + S && S <= 65535,
+    FCD_REQUIRE(S >= 0 && N >= 2 && T >= 2 && s0 >= 0 && pitch >= (int64_t)s0 + S && S <= 65535 * 4,
                 "fcd_corr_fisherz: bad shape S=%d N=%d T=%d s0=%d pitch=%lld", S, N, T, s0, (long long)pitch);
     if (S == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     const int Tp = corr_padded_T(T);
-    // 1024-byte aligned scratch (TMA / UMMA operand tiles need it in the tensor-core path)
+    // 1024-byte aligned scratch planes (TMA / UMMA operand tiles need it)
+    const int64_t plane = (((int64_t)S * N * Tp * (int64_t)sizeof(float)) + 1023) & ~(int64_t)1023;
     float* Z = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(zws) + 1023) & ~(uintptr_t)1023);
+    float* Zlo = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(Z) + plane);
     const int64_t rows = (int64_t)S * N;
     int64_t g = (rows + 7) / 8;
     const int64_t cap = (int64_t)sm_count() * 8;
-    standardise_kernel<<<(int)(g < cap ? g : cap), 256, 0, st>>>(ts, rows, T, Tp, Z);
+    const int grid1 = (int)(g < cap ? g : cap);
+    const bool tc = corr_tc_supported(N) && getenv("FCD_CORR_SIMT") == nullptr;
+    if (tc) standardise_kernel<true><<<grid1, 256, 0, st>>>(ts, rows, T, Tp, Z, Zlo);
+    else standardise_kernel<false><<<grid1, 256, 0, st>>>(ts, rows, T, Tp, Z, nullptr);
     int rc = check_launch("fcd_corr_fisherz(standardise)");
     if (rc) return rc;
-    rc = corr_gram_tc(Z, S, N, Tp, out, pitch, s0, fisher, st);
-    if (rc != 1) return rc;           // 0 = done on tensor cores, <0 = error, 1 = shape not supported there
+    if (tc) return corr_gram_tc(Z, Zlo, S, N, Tp, out, pitch, s0, fisher, st);
+    FCD_REQUIRE(S <= 65535, "fcd_corr_fisherz: S=%d too large for the SIMT Gram kernel", S);
     const int nt = (N + 31) / 32;
     dim3 grid((unsigned)(nt * (nt + 1) / 2), (unsigned)S);
     gram_simt_kernel<<<grid, 256, 0, st>>>(Z, N, Tp, nt, out, pitch, s0, fisher);

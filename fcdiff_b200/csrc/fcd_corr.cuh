@@ -16,10 +16,10 @@ __device__ __forceinline__ double corr_epilogue(double r, int fisher) {
 }
 #endif
 
-// Tensor-core Gram + epilogue (fcd_corr_tc.cu).  Returns 0 when done, 1 when the
-// shape is not supported by the tensor-core kernel (caller uses the SIMT
-// kernel), <0 on error.
-int corr_gram_tc(const float* Z, int S, int N, int Tp, double* out, int64_t pitch, int s0,
+// Tensor-core Gram + epilogue (fcd_corr_tc.cu): Zh / Zl are the TF32 hi / lo
+// parts of the standardised rows, [S*N][Tp] fp32 each, 1024-byte aligned.
+bool corr_tc_supported(int N);
+int corr_gram_tc(const float* Zh, const float* Zl, int S, int N, int Tp, double* out, int64_t pitch, int s0,
                  int fisher, cudaStream_t st);
 
 }  // namespace fcd

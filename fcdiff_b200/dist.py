@@ -57,14 +57,20 @@ class EdgeShards(object):
 
     # ------------------------------------------------------------------ collectives
     def allreduce_terms(self, out, idxs):
-        """Sums ``out[idxs]`` over ranks (partial sums of edge-local terms);
-        the other entries are complete on every rank already."""
-        idx = torch.as_tensor(list(idxs), device=out.device)
-        part = out.index_select(0, idx).contiguous()
-        dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group)
-        out = out.clone()
-        out.index_copy_(0, idx, part)
+        """Sums the device vector ``out`` over ranks in place (one collective, no
+        staging).  Entries in ``idxs`` are edge-local partial sums; the other
+        entries are already complete on every rank, so their sum is divided by
+        the world size by ``fix_replicated`` after the download."""
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
         return out
+
+    def fix_replicated(self, host_vec, idxs):
+        """Undo the summation of entries that were complete on every rank."""
+        keep = set(idxs)
+        for i in range(len(host_vec)):
+            if i not in keep:
+                host_vec[i] = host_vec[i] / self.world
+        return host_vec
 
     def _gather_rows(self, full, rows, width):
         """``full`` is a flat [rows * width] tensor whose rows [start, start+len)

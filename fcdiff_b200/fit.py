@@ -455,7 +455,10 @@ class UnsharedRegionFit(object):
         th = self._theta()
         out = _dev.empty((6,))
         ev = self._find_eval(need_F=True)
-        elm = None if ev is None else ctypes.byref(ctypes.c_double(ev['elm_local']))
+        elm = None
+        if ev is not None:      # global E_lM is known: rank 0 contributes it, the others zero
+            first = self.shards is None or self.shards.rank == 0
+            elm = ctypes.byref(ctypes.c_double(ev['elm'] if first else 0.0))
         with _dev.timed(self.profile, "K4_energy_terms" if ev is None else "K4_energy_small"):
             _lib.check(lib.fcd_energy_terms(
                 _dev.ptr(inp['S1']), _dev.ptr(inp['S2']), H, _dev.ptr(inp['Ea']), _dev.ptr(inp['Eb']),
@@ -465,6 +468,7 @@ class UnsharedRegionFit(object):
                 "fcd_energy_terms")
         if self.shards is not None:
             out = self.shards.allreduce_terms(out, (0, 1, 3, 4))
+            return self.shards.fix_replicated(_dev.download(out), (0, 1, 3, 4))
         return _dev.download(out)
 
     def _update_lq_F(self):
@@ -580,6 +584,7 @@ class UnsharedRegionFit(object):
                                            _dev.ptr(_dev.workspace()), _dev.stream()), "fcd_mstep_stats")
         if do_gamma and self.shards is not None and self._in is not None:
             out = self.shards.allreduce_terms(out, (0, 1, 2))
+            return self.shards.fix_replicated(_dev.download(out), (0, 1, 2)), C, NU
         return _dev.download(out), C, NU
 
     def _update_pi_gamma(self, do_pi, do_gamma):
@@ -631,16 +636,15 @@ class UnsharedRegionFit(object):
                 Cl, U, inp['pitchU'], _dev.ptr(qF[c0 * 3:]), _dev.ptr(qR), N, c0,
                 ctypes.byref(th), 1 if want_grad else 0, _dev.ptr(A), _dev.ptr(out),
                 _dev.ptr(_dev.workspace()), _dev.stream()), "fcd_elm_obj_grad")
-        o_local = _dev.download(out)
-        if need_const or not want_grad:
-            self._const = (ckey, float(o_local[3]))
-        elm_local = float(o_local[0]) + self._const[1]
-        self._evals.append(dict(x=(th.eta, th.epsilon), verF=self._mF.version, verR=self._mR.version,
-                                A=A, elm_local=elm_local))
-        o = np.array([elm_local, o_local[1], o_local[2]])
         if self.shards is not None:
-            o = _dev.download(self.shards.allreduce_terms(_dev.upload(o), (0, 1, 2)))
-        return -float(o[0]), np.array([o[1], o[2]])
+            out = self.shards.allreduce_terms(out, (0, 1, 2, 3))      # all four are edge-local partial sums
+        o = _dev.download(out)
+        if need_const or not want_grad:
+            self._const = (ckey, float(o[3]))
+        elm = float(o[0]) + self._const[1]
+        self._evals.append(dict(x=(th.eta, th.epsilon), verF=self._mF.version, verR=self._mR.version,
+                                A=A, elm=elm))
+        return -elm, np.array([o[1], o[2]])
 
     def _update_theta_sub(self):
         """

@@ -44,7 +44,7 @@ def _worker(rank, world, port, q):
         sh.allgather_patients(lqR.view(-1), qR.view(-1), N, U)
         ok = ok and bool(torch.equal(lqR, ref_R) and torch.equal(qR, ref_R))
         out = torch.tensor([1.0 + rank, 10.0, 100.0 * (rank + 1), 5.0], dtype=torch.float64)
-        red = sh.allreduce_terms(out, (0, 2))
+        red = sh.fix_replicated(sh.allreduce_terms(out, (0, 2)).numpy().copy(), (0, 2))
         ok = ok and red.tolist() == [3.0, 10.0, 300.0, 5.0]
         q.put((rank, ok))
     except Exception as e:      # surface the failure instead of a queue timeout
