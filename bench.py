@@ -269,6 +269,22 @@ def run_gpu_arm(args):
     value = C * (H + U) * args.steps / (ms * 1e-3)
     nfev = float(np.mean(fit.n_objective_evals)) if fit.n_objective_evals else 0.0
 
+    # ---- time to converge (north_star target): whole fit from device-resident inputs
+    barrier()
+    fitc = new_fit(b_dev, bt_dev)
+    fitc.max_iters = 100
+    tc0 = time.perf_counter()
+    fitc.run()
+    barrier()
+    t_conv = time.perf_counter() - tc0
+    tconv = torch.tensor([t_conv], dtype=torch.float64, device="cuda")
+    if shards is not None:
+        dist.all_reduce(tconv, op=dist.ReduceOp.MAX)
+    converge = {"seconds": float(tconv.item()), "iterations": len(fitc.energy) - 1,
+                "rel_tol": fitc.rel_tol, "objective_evals": int(sum(fitc.n_objective_evals)),
+                "what": "fit.run() to the reference's convergence rule (fit.py:138-140) incl. set-up "
+                        "(healthy stats, Gaussian cache, patient-major planes)"}
+
     # ---- end-to-end arm: host (pinned) arrays through the public API every step
     e2e = None
     b_host = torch.empty((Cl, H), dtype=torch.float64).pin_memory()
@@ -349,7 +365,7 @@ def run_gpu_arm(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": dict(workload_config(world), objective_evals_per_step=nfev),
         "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roofline,
-        "cpu_baseline": cpu, "kernels": kernels,
+        "cpu_baseline": cpu, "time_to_converge": converge, "kernels": kernels,
         "energy_trace": [float(e) for e in energies[:4]] + ["..."] + [float(energies[-1])],
     }
     print(json.dumps(line))

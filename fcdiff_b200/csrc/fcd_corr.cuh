@@ -14,6 +14,14 @@ __device__ __forceinline__ double corr_epilogue(double r, int fisher) {
     r = fmin(1.0, fmax(-1.0, r));
     return fisher ? atanh(r) : r;
 }
+// Same for an fp32 accumulator of the tensor-core path: the Gram entry carries
+// ~1e-6 of TF32 accumulation error, so fp32 transcendental precision (rel. 1e-7)
+// loses nothing; atanh(r) = (log1p(r) - log1p(-r)) / 2 is accurate for small |r|.
+__device__ __forceinline__ double corr_epilogue_f32(float r, int fisher) {
+    r = fminf(1.0f, fmaxf(-1.0f, r));
+    if (!fisher) return (double)r;
+    return (double)(0.5f * (log1pf(r) - log1pf(-r)));
+}
 #endif
 
 // Tensor-core Gram + epilogue (fcd_corr_tc.cu): Zh / Zl are the TF32 hi / lo

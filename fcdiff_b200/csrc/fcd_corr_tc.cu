@@ -208,16 +208,16 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
                     double* dst = out + (rowbase + m) * pitch + s0 + sg0;
                     if (vec_ok) {
                         double2 lo2, hi2;
-                        lo2.x = corr_epilogue((double)__uint_as_float(v[0][j]), fisher);
-                        lo2.y = corr_epilogue((double)__uint_as_float(v[1][j]), fisher);
-                        hi2.x = corr_epilogue((double)__uint_as_float(v[2][j]), fisher);
-                        hi2.y = corr_epilogue((double)__uint_as_float(v[3][j]), fisher);
+                        lo2.x = corr_epilogue_f32(__uint_as_float(v[0][j]), fisher);
+                        lo2.y = corr_epilogue_f32(__uint_as_float(v[1][j]), fisher);
+                        hi2.x = corr_epilogue_f32(__uint_as_float(v[2][j]), fisher);
+                        hi2.y = corr_epilogue_f32(__uint_as_float(v[3][j]), fisher);
                         reinterpret_cast<double2*>(dst)[0] = lo2;
                         reinterpret_cast<double2*>(dst)[1] = hi2;
                     } else {
 #pragma unroll
                         for (int sg = 0; sg < kSubj; ++sg)
-                            if (sg < nsub) dst[sg] = corr_epilogue((double)__uint_as_float(v[sg][j]), fisher);
+                            if (sg < nsub) dst[sg] = corr_epilogue_f32(__uint_as_float(v[sg][j]), fisher);
                     }
                 }
             }
