@@ -191,25 +191,44 @@ transpose_patients_kernel(const double* __restrict__ bt, int64_t C, int U, int64
 template <bool FAST>
 __global__ void __launch_bounds__(256)
 region_weights_kernel(const double* __restrict__ EaT, const double* __restrict__ EbT,
-                      int64_t C, int64_t pitchC,
+                      int Ul, int64_t C, int64_t pitchC,
                       const double* __restrict__ qF, const __grid_constant__ ThetaDev th,
                       const double* __restrict__ g_tab, double* __restrict__ WT) {
     __shared__ double s_tab[FAST ? kLogTabSize : 1];
     load_log_table<FAST>(g_tab, s_tab);
-    const int u = blockIdx.y;
-    const double* ra = EaT + (int64_t)u * pitchC;
-    const double* rb = EbT + (int64_t)u * pitchC;
-    double* out = WT + (int64_t)u * C * 3;
-    for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < C;
-         c += (int64_t)gridDim.x * blockDim.x) {
-        const ElemM r = elem_from_cache(ldg_stream1(ra + c), ldg_stream1(rb + c));
-        const double q0 = __ldg(qF + c * 3), q1 = __ldg(qF + c * 3 + 1), q2 = __ldg(qF + c * 3 + 2);
+    // persistent CTAs over (patient, 1024-edge tile) work items: no wave tail, one
+    // table load per CTA
+    const int64_t tiles_per_row = (C + 1023) / 1024;
+    const int64_t ntiles = tiles_per_row * Ul;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int u = (int)(t / tiles_per_row);
+        const int64_t cbase = (t - (int64_t)u * tiles_per_row) * 1024;
+        const double* ra = EaT + (int64_t)u * pitchC;
+        const double* rb = EbT + (int64_t)u * pitchC;
+        double* out = WT + (int64_t)u * C * 3;
+        double ea[4], eb[4];
 #pragma unroll
-        for (int l = 0; l < 3; ++l) {
-            double w = q0 * fast_log<FAST>(elem_Mp(r, th, 0, l), s_tab);
-            w = fma(q1, fast_log<FAST>(elem_Mp(r, th, 1, l), s_tab), w);
-            w = fma(q2, fast_log<FAST>(elem_Mp(r, th, 2, l), s_tab), w);
-            out[c * 3 + l] = w;
+        for (int j = 0; j < 4; ++j) {                 // issue the tile's loads first
+            const int64_t c = cbase + threadIdx.x + 256 * j;
+            ea[j] = eb[j] = 0.0;
+            if (c < C) {
+                ea[j] = ldg_stream1(ra + c);
+                eb[j] = ldg_stream1(rb + c);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t c = cbase + threadIdx.x + 256 * j;
+            if (c >= C) continue;
+            const ElemM r = elem_from_cache(ea[j], eb[j]);
+            const double q0 = __ldg(qF + c * 3), q1 = __ldg(qF + c * 3 + 1), q2 = __ldg(qF + c * 3 + 2);
+#pragma unroll
+            for (int l = 0; l < 3; ++l) {
+                double w = q0 * fast_log<FAST>(elem_Mp(r, th, 0, l), s_tab);
+                w = fma(q1, fast_log<FAST>(elem_Mp(r, th, 1, l), s_tab), w);
+                w = fma(q2, fast_log<FAST>(elem_Mp(r, th, 2, l), s_tab), w);
+                out[c * 3 + l] = w;
+            }
         }
     }
 }
@@ -283,12 +302,19 @@ sweep_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int u0,
                 a += s_red[n & 1][i][0];
                 b += s_red[n & 1][i][1];
             }
-            double l0 = lp0 + a, l1 = lp1 + b;
-            const double mx = fmax(l0, l1);
-            const double lse = mx + log(exp(l0 - mx) + exp(l1 - mx));       // fit.py:196
-            l0 -= lse;
-            l1 -= lse;
-            const double p0 = exp(l0), p1 = exp(l1);                        // fit.py:197
+            // lq = l - logsumexp(l), q = exp(lq) (fit.py:196-197) with one exponential:
+            // with d = -|l0 - l1| and t = exp(d):  lse = max + log1p(t),
+            // q_max = 1 / (1 + t), q_min = t / (1 + t).
+            const double l0r = lp0 + a, l1r = lp1 + b;
+            const bool first = l0r >= l1r;
+            const double d = first ? l1r - l0r : l0r - l1r;
+            const double t = exp_nonpos(d);
+            const double lg = log1p(t);
+            const double inv = 1.0 / (1.0 + t);
+            const double lmax = -lg, lmin = d - lg;
+            const double qmax = inv, qmin = t * inv;
+            const double l0 = first ? lmax : lmin, l1 = first ? lmin : lmax;
+            const double p0 = first ? qmax : qmin, p1 = first ? qmin : qmax;
             const int slot = n / T;
 #pragma unroll
             for (int j = 0; j < MPT; ++j)
@@ -400,19 +426,18 @@ int fcd_transpose_patients(const double* bt, int64_t C, int32_t U, int64_t pitch
 int fcd_region_weights(const double* EaT, const double* EbT, int32_t Ul, int64_t C, int64_t pitchC,
                        const double* qF, const fcd_theta* theta_host, double* WT, void* stream) {
     FCD_REQUIRE(theta_host != nullptr, "fcd_region_weights: theta is NULL");
-    FCD_REQUIRE(C >= 0 && Ul >= 0 && Ul <= 65535 && pitchC >= C, "fcd_region_weights: bad shape");
+    FCD_REQUIRE(C >= 0 && Ul >= 0 && pitchC >= C, "fcd_region_weights: bad shape");
     if (C == 0 || Ul == 0) return 0;
     const ThetaDev th = make_theta_dev(*theta_host, 0);
     const double* tab = log_table((cudaStream_t)stream);
     FCD_REQUIRE(tab != nullptr, "fcd_region_weights: log table initialisation failed");
-    int64_t bx = (C + 255) / 256;
-    const int64_t cap = ((int64_t)sm_count() * 4 + Ul - 1) / Ul;
-    if (bx > cap) bx = cap < 1 ? 1 : cap;
-    dim3 grid((unsigned)bx, (unsigned)Ul);
+    int64_t ntiles = ((C + 1023) / 1024) * (int64_t)Ul;
+    int64_t grid = (int64_t)sm_count() * 4;            // 4 CTAs / SM resident (43 KB table each, <= 64 regs)
+    if (grid > ntiles) grid = ntiles;
     if (log_table_covers(th.epsl, th.al))
-        region_weights_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(EaT, EbT, C, pitchC, qF, th, tab, WT);
+        region_weights_kernel<true><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(EaT, EbT, Ul, C, pitchC, qF, th, tab, WT);
     else
-        region_weights_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(EaT, EbT, C, pitchC, qF, th, tab, WT);
+        region_weights_kernel<false><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(EaT, EbT, Ul, C, pitchC, qF, th, tab, WT);
     return check_launch("fcd_region_weights");
 }
 
