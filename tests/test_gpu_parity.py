@@ -414,3 +414,104 @@ def test_config3_properties(N, H, U):
     fit.reuse_evaluations = False
     fit._update_lq_F()                       # full K2 pass
     nptest.assert_allclose(lq_reused, fit._lq_F, rtol=1e-12, atol=1e-12)
+
+
+# ------------------------------------------------------------------ kernel variants behind the C-ABI
+def test_safe_variant_outside_log_table_range():
+    """epsilon below 2^-19 leaves the log table's range: the host must pick the
+    SAFE kernels (log()/division) and still match the oracle."""
+    th = O.Theta()
+    th.epsilon = 1e-7
+    th.eta = 0.2
+    (N, H, U) = (9, 6, 10)
+    (_, _, _, _, b, bt) = O.sample(O.Theta(), N, H, U, np.random.RandomState(2))
+    (N, H, U, lq_F, lq_R) = _oracle_state(b, bt, th, 3)
+    (lpB, pBt, lM) = O.update_lps(b, bt, th)
+    model = fcdiff.UnsharedRegionModel()
+    (model.eta, model.epsilon) = (th.eta, th.epsilon)
+    fit = _fit_for(b, bt, model)
+    fit._init_lps(N, H, U)
+    fit._update_lps()
+    fit._lq_R, fit._lq_F = lq_R, lq_F
+    nptest.assert_allclose(fit._energy_terms(), O.eval_energy_terms(th, lq_F, lq_R, lpB, lM), rtol=1e-10)
+    fit._update_lq_F()
+    exp_F = O.update_lq_F(th.gamma, lpB, lM, lq_R)
+    nptest.assert_allclose(fit._lq_F, exp_F, rtol=1e-9, atol=1e-10)
+    fit._update_lq_R()
+    nptest.assert_allclose(fit._lq_R, O.update_lq_R(np.array([1 - th.pi, th.pi]), exp_F, lM, lq_R), rtol=1e-9, atol=1e-10)
+    (f, grad) = fit._objective([th.eta, th.epsilon])
+    (fo, go) = O.elm_objective_and_grad(pBt, np.exp(exp_F), np.exp(fit._lq_R), [th.eta, th.epsilon])
+    nptest.assert_allclose(f, fo, rtol=1e-10)
+    nptest.assert_allclose(grad, go, rtol=1e-7)
+
+
+def test_unaligned_odd_pitch_through_the_c_abi():
+    """Direct C-ABI calls with an odd row pitch and 8-byte-aligned planes take the
+    scalar-load kernels; results must equal the aligned 128-bit path bit for bit
+    up to the order of the per-lane sums."""
+    import ctypes
+    from fcdiff_b200 import _dev
+    lib = _lib.load()
+    (N, H, U) = (12, 7, 13)
+    C = N * (N - 1) // 2
+    th0 = O.Theta()
+    (_, _, _, _, b, bt) = O.sample(th0, N, H, U, np.random.RandomState(4))
+    fit = _fit_for(b, bt)
+    fit._init_lps(N, H, U)
+    fit._update_lps()
+    rng = np.random.RandomState(5)
+    fit._lq_R = np.log(rng.dirichlet([1, 1], size=(N, U)))
+    fit._lq_F = np.log(rng.dirichlet([1, 1, 1], size=(C, 1)))
+    ref_obj = fit._objective([0.3, 0.03])
+    fit._update_lq_F()
+    ref_lqF = fit._lq_F.copy()
+    inp = fit._in
+    # rebuild the planes with pitch U (odd) at an odd 8-byte offset
+    th = fit._theta()
+    btd = _dev.upload(bt)
+    buf = [_dev.empty((C * U + 1,)) for _ in range(3)]
+    (Ea, Eb, Tm) = [t[1:] for t in buf]
+    _lib.check(lib.fcd_gauss_cache(_dev.ptr(btd), C, U, U, ctypes.byref(th), _dev.ptr(Ea), _dev.ptr(Eb),
+                                   _dev.ptr(Tm), _dev.stream()))
+    (_, qR) = fit._mR.get_dev()
+    fit._lq_F = np.log(rng.dirichlet([1, 1, 1], size=(C, 1)))       # any q_F; K2 does not read it
+    lqF = _dev.empty((C * 3,))
+    _lib.check(lib.fcd_estep_qF(_dev.ptr(inp['S1']), _dev.ptr(inp['S2']), H, _dev.ptr(Ea), _dev.ptr(Eb), C, U, U,
+                                _dev.ptr(qR), N, 0, ctypes.byref(th), _dev.ptr(lqF), None, _dev.stream()))
+    nptest.assert_allclose(_dev.download(lqF).reshape(C, 1, 3), ref_lqF, rtol=1e-12, atol=1e-12)
+    fit2 = _fit_for(b, bt)
+    fit2._init_lps(N, H, U)
+    fit2._update_lps()
+    rng = np.random.RandomState(5)
+    fit2._lq_R = np.log(rng.dirichlet([1, 1], size=(N, U)))
+    fit2._lq_F = np.log(rng.dirichlet([1, 1, 1], size=(C, 1)))
+    (_, qF2) = fit2._mF.get_dev()
+    (_, qR2) = fit2._mR.get_dev()
+    th2 = fit2._theta()
+    out = _dev.empty((4,))
+    A = _dev.empty((C * 3,))
+    _lib.check(lib.fcd_elm_obj_grad(_dev.ptr(Ea), _dev.ptr(Eb), _dev.ptr(Tm), C, U, U, _dev.ptr(qF2), _dev.ptr(qR2),
+                                    N, 0, ctypes.byref(th2), 1, _dev.ptr(A), _dev.ptr(out),
+                                    _dev.ptr(_dev.workspace()), _dev.stream()))
+    o = _dev.download(out)
+    nptest.assert_allclose(-(o[0] + o[3]), ref_obj[0], rtol=1e-13)
+    nptest.assert_allclose(o[1:3], ref_obj[1], rtol=1e-11)
+
+
+def test_evaluation_reuse_is_invalidated_by_assignments():
+    th = O.Theta()
+    (_, _, _, _, b, bt) = O.sample(th, 8, 5, 6, np.random.RandomState(7))
+    fit = _fit_for(b, bt, eta_shift=0.1)
+    fit.max_iters = 2
+    fit.run()
+    assert fit._find_eval(need_F=True) is not None
+    fit._lq_R = fit._lq_R.copy()                 # any assignment bumps the version
+    assert fit._find_eval(need_F=False) is None
+    fit.run()
+    e1 = list(fit.energy)
+    fit2 = _fit_for(b, bt, eta_shift=0.1)
+    fit2.max_iters = 2
+    fit2.reuse_evaluations = False
+    fit2.run()
+    nptest.assert_allclose(e1, fit2.energy, rtol=1e-13)
+    nptest.assert_allclose(fit._lq_F, fit2._lq_F, rtol=1e-10, atol=1e-11)
