@@ -504,14 +504,14 @@ def test_evaluation_reuse_is_invalidated_by_assignments():
     fit = _fit_for(b, bt, eta_shift=0.1)
     fit.max_iters = 2
     fit.run()
+    e1 = list(fit.energy)
+    lqF1 = fit._lq_F.copy()
     assert fit._find_eval(need_F=True) is not None
     fit._lq_R = fit._lq_R.copy()                 # any assignment bumps the version
     assert fit._find_eval(need_F=False) is None
-    fit.run()
-    e1 = list(fit.energy)
     fit2 = _fit_for(b, bt, eta_shift=0.1)
     fit2.max_iters = 2
     fit2.reuse_evaluations = False
     fit2.run()
     nptest.assert_allclose(e1, fit2.energy, rtol=1e-13)
-    nptest.assert_allclose(fit._lq_F, fit2._lq_F, rtol=1e-10, atol=1e-11)
+    nptest.assert_allclose(lqF1, fit2._lq_F, rtol=1e-10, atol=1e-11)
