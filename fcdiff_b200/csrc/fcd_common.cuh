@@ -42,6 +42,7 @@ struct ThetaDev {
     double lc[3];        // -log(sigma_k)            (the -log sqrt(2 pi) is added where needed)
     double epsl[3];      // eps_l of fcdiff/fit.py:433-444
     double al[3];        // (1 - eps_l) / 2
+    double bl[3];        // eps_l - a_l
     double log_gamma[3];
     double hq_a[3];      // healthy quadratic: sum_h logN_k(b) = hq_a*S2 + hq_b*S1 + hq_c
     double hq_b[3];
@@ -103,7 +104,8 @@ __device__ __forceinline__ double ldg_stream1(const double* p) {
 //   mantissa bits, Tm = max_k t_k.
 struct ElemM {
     double e[3];
-    double o[3];
+    double aS[3];     // a_l * (e_0 + e_1 + e_2)
+    double mhS;       // -(e_0 + e_1 + e_2) / 2
 };
 
 struct GaussElem {
@@ -130,22 +132,29 @@ __device__ __forceinline__ GaussElem gauss_eval(double x, const ThetaDev& th) {
     return g;
 }
 
-__device__ __forceinline__ ElemM elem_from_cache(double ea, double ebc) {
+__device__ __forceinline__ ElemM elem_from_cache(double ea, double ebc, const ThetaDev& th) {
     const int code = __double2loint(ebc) & 3;
     const bool m0 = code == 0, m1 = code == 1;
     ElemM r;
     r.e[0] = m0 ? 1.0 : ea;
     r.e[1] = m1 ? 1.0 : (m0 ? ea : ebc);
     r.e[2] = (m0 || m1) ? ebc : 1.0;
-    r.o[0] = r.e[1] + r.e[2];
-    r.o[1] = r.e[0] + r.e[2];
-    r.o[2] = r.e[0] + r.e[1];
+    // Mp[k][l] = eps_l e_k + a_l (S - e_k) = b_l e_k + a_l S with b_l = eps_l - a_l: one FMA per
+    // (k, l).  Where b_l < 0 the cancellation costs at most 1e-16 a_l / eps_l relative
+    // (5e-12 at the optimiser's bound eps = 1e-5, 1e-15 at typical values).
+    const double S = (1.0 + ea) + ebc;
+#pragma unroll
+    for (int l = 0; l < 3; ++l) r.aS[l] = th.al[l] * S;
+    r.mhS = -0.5 * S;
     return r;
 }
 
 __device__ __forceinline__ double elem_Mp(const ElemM& r, const ThetaDev& th, int k, int l) {
-    return fma(th.epsl[l], r.e[k], th.al[l] * r.o[k]);
+    return fma(th.bl[l], r.e[k], r.aS[l]);
 }
+
+// e_k - o_k / 2 = 1.5 e_k - S / 2: numerator of d log M / d eps (fit.py:618-697)
+__device__ __forceinline__ double elem_num(const ElemM& r, int k) { return fma(1.5, r.e[k], r.mhS); }
 
 // q_R pair weights of fcdiff/fit.py:382-406.
 __device__ __forceinline__ void pair_weights(double2 qn, double2 qm, double (&w)[3]) {

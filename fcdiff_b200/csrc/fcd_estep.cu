@@ -74,7 +74,7 @@ __device__ __forceinline__ void k2_elem(double ea, double ebc, double2 qn, doubl
                                         const double* s_tab, double (&acc)[3]) {
     double w[3];
     pair_weights(qn, qm, w);
-    const ElemM r = elem_from_cache(ea, ebc);
+    const ElemM r = elem_from_cache(ea, ebc, th);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         double a = acc[k];
@@ -111,7 +111,7 @@ estep_qF_kernel(const double* __restrict__ S1, const double* __restrict__ S2,
                 const double* __restrict__ qR, int N, int64_t c0,
                 const __grid_constant__ ThetaDev th, const double* __restrict__ g_tab,
                 double* __restrict__ lqF, double* __restrict__ qF) {
-    __shared__ double s_tab[FAST ? kLogTabSize : 1];
+    extern __shared__ double s_tab[];               // kLogTabBytes when FAST, unused otherwise
     load_log_table<FAST>(g_tab, s_tab);
     const int lane = threadIdx.x & 31;
     double acc[3] = {0.0, 0.0, 0.0};
@@ -194,7 +194,7 @@ region_weights_kernel(const double* __restrict__ EaT, const double* __restrict__
                       int Ul, int64_t C, int64_t pitchC,
                       const double* __restrict__ qF, const __grid_constant__ ThetaDev th,
                       const double* __restrict__ g_tab, double* __restrict__ WT) {
-    __shared__ double s_tab[FAST ? kLogTabSize : 1];
+    extern __shared__ double s_tab[];               // kLogTabBytes when FAST, unused otherwise
     load_log_table<FAST>(g_tab, s_tab);
     // persistent CTAs over (patient, 1024-edge tile) work items: no wave tail, one
     // table load per CTA
@@ -220,7 +220,7 @@ region_weights_kernel(const double* __restrict__ EaT, const double* __restrict__
         for (int j = 0; j < 4; ++j) {
             const int64_t c = cbase + threadIdx.x + 256 * j;
             if (c >= C) continue;
-            const ElemM r = elem_from_cache(ea[j], eb[j]);
+            const ElemM r = elem_from_cache(ea[j], eb[j], th);
             const double q0 = __ldg(qF + c * 3), q1 = __ldg(qF + c * 3 + 1), q2 = __ldg(qF + c * 3 + 2);
 #pragma unroll
             for (int l = 0; l < 3; ++l) {
@@ -391,12 +391,16 @@ int fcd_estep_qF(const double* S1, const double* S2, int32_t H,
     const ThetaDev th = make_theta_dev(*theta_host, H);
     const double* tab = log_table((cudaStream_t)stream);
     FCD_REQUIRE(tab != nullptr, "fcd_estep_qF: log table initialisation failed");
-    const int grid = grid_for_rows(C, kEdgeThreads / 32, 4);
+    const int grid = grid_for_rows(C, kEdgeThreads / 32, 2);
     const bool vec2 = (pitchU % 2 == 0) && (((reinterpret_cast<uintptr_t>(Ea) | reinterpret_cast<uintptr_t>(Eb)) & 15) == 0);
     const bool fast = log_table_covers(th.epsl, th.al);
-#define FCD_K2(V, F)                                                              \
-    estep_qF_kernel<V, F><<<grid, kEdgeThreads, 0, (cudaStream_t)stream>>>(       \
-        S1, S2, Ea, Eb, C, U, pitchU, qR, N, c0, th, tab, lqF, qF)
+#define FCD_K2(V, F)                                                                              \
+    do {                                                                                          \
+        cudaFuncSetAttribute(estep_qF_kernel<V, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                             (int)kLogTabBytes);                                                  \
+        estep_qF_kernel<V, F><<<grid, kEdgeThreads, (F) ? kLogTabBytes : 0, (cudaStream_t)stream>>>( \
+            S1, S2, Ea, Eb, C, U, pitchU, qR, N, c0, th, tab, lqF, qF);                            \
+    } while (0)
     if (vec2) { if (fast) FCD_K2(true, true); else FCD_K2(true, false); }
     else      { if (fast) FCD_K2(false, true); else FCD_K2(false, false); }
 #undef FCD_K2
@@ -432,12 +436,17 @@ int fcd_region_weights(const double* EaT, const double* EbT, int32_t Ul, int64_t
     const double* tab = log_table((cudaStream_t)stream);
     FCD_REQUIRE(tab != nullptr, "fcd_region_weights: log table initialisation failed");
     int64_t ntiles = ((C + 1023) / 1024) * (int64_t)Ul;
-    int64_t grid = (int64_t)sm_count() * 4;            // 4 CTAs / SM resident (43 KB table each, <= 64 regs)
+    int64_t grid = (int64_t)sm_count() * 2;            // 2 CTAs / SM resident (86 KB table each)
     if (grid > ntiles) grid = ntiles;
-    if (log_table_covers(th.epsl, th.al))
-        region_weights_kernel<true><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(EaT, EbT, Ul, C, pitchC, qF, th, tab, WT);
-    else
-        region_weights_kernel<false><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(EaT, EbT, Ul, C, pitchC, qF, th, tab, WT);
+    if (log_table_covers(th.epsl, th.al)) {
+        cudaFuncSetAttribute(region_weights_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)kLogTabBytes);
+        region_weights_kernel<true><<<(unsigned)grid, 256, kLogTabBytes, (cudaStream_t)stream>>>(
+            EaT, EbT, Ul, C, pitchC, qF, th, tab, WT);
+    } else {
+        region_weights_kernel<false><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+            EaT, EbT, Ul, C, pitchC, qF, th, tab, WT);
+    }
     return check_launch("fcd_region_weights");
 }
 

@@ -7,21 +7,21 @@
 // what is known about the arguments:
 //
 //  * fast_log(y): y is a mixture weight in (0, 1].  MUFU.RCP64H gives r ~ 1/y;
-//    r is rounded to 8 mantissa bits (r8, exactly representable), so that
-//    u = y*r8 - 1 is one exact FMA with |u| <= 2^-9, and
+//    r is rounded to 9 mantissa bits (r8, exactly representable), so that
+//    u = y*r8 - 1 is one exact FMA with |u| <= 2^-10, and
 //        log y = -log r8 + log1p(u),
-//    -log r8 from a 5376-entry table in shared memory (indexed by the
-//    exponent/mantissa bits of r8), log1p(u) = u - u^2/2 + u^3/3 - u^4/4
-//    (truncation < 6e-15).  6 fp64 ops + 1 MUFU + 1 LDS instead of ~40.
-//  * fast_log_rcp additionally returns 1/y = r8 * (1 - u + u^2 - u^3), rel. error
-//    <= u^4 = 1.5e-11, for the analytic gradient (4 more fp64 ops, no second
+//    -log r8 from a 10752-entry table in shared memory (indexed by the
+//    exponent/mantissa bits of r8), log1p(u) = u - u^2/2 + u^3/3
+//    (truncation u^4/4 <= 2.3e-13).  5 fp64 ops + 1 MUFU + 1 LDS instead of ~40.
+//  * fast_log_rcp additionally returns 1/y = r8 * (1 - u + u^2), rel. error
+//    <= u^3 = 9.3e-10, for the analytic gradient (3 more fp64 ops, no second
 //    MUFU / Newton iteration).
 //  * exp_nonpos(d): d <= 0, argument reduction with the 1.5*2^52 trick (no
 //    F2I/I2F conversions), degree-11 polynomial, exponent patched in the ALU.
 //
-// Absolute error of fast_log < 1e-14, relative error of exp_nonpos < 1e-14:
-// five orders of magnitude inside the 1e-9 per-term budget that 1e-6 parity of
-// the posteriors needs (DESIGN.md "Numerics").
+// Absolute error of fast_log < 3e-13, relative error of exp_nonpos < 1e-14:
+// more than three orders of magnitude inside the 1e-9 per-term budget that 1e-6
+// parity of the posteriors needs (DESIGN.md "Numerics").
 #pragma once
 
 #include <cuda_runtime.h>
@@ -29,11 +29,12 @@
 
 namespace fcd {
 
-constexpr int kLogTabBits    = 8;                       // mantissa bits kept in r8
+constexpr int kLogTabBits    = 9;                       // mantissa bits kept in the rounded reciprocal
 constexpr int kLogTabMinExp  = -1;                      // r8 in [2^-1, 2^20)  <=>  y in (2^-20, 2]
 constexpr int kLogTabBinades = 21;
-constexpr int kLogTabSize    = kLogTabBinades << kLogTabBits;      // 5376 doubles = 43,008 bytes
+constexpr int kLogTabSize    = kLogTabBinades << kLogTabBits;      // 10752 doubles = 86,016 bytes
 constexpr int kLogTabBase    = (1023 + kLogTabMinExp) << kLogTabBits;
+constexpr size_t kLogTabBytes = (size_t)kLogTabSize * sizeof(double);      // dynamic shared memory of the FAST kernels
 
 // Host: device address of the table for the current device (built on first use).
 const double* log_table(cudaStream_t st);
@@ -74,9 +75,9 @@ __device__ __forceinline__ LogParts log_reduce(double y) {
     return p;
 }
 
+// |u| <= 2^-10: u - u^2/2 + u^3/3, truncation u^4/4 <= 2.3e-13
 __device__ __forceinline__ double log1p_small(double u) {
-    double q = fma(u, -0.25, 1.0 / 3.0);
-    q = fma(u, q, -0.5);
+    const double q = fma(u, 1.0 / 3.0, -0.5);
     return fma(u * u, q, u);
 }
 
@@ -94,9 +95,7 @@ __device__ __forceinline__ double fast_log_rcp(double y, const double* s_tab, do
         return log(y);
     }
     const LogParts p = log_reduce(y);
-    double g = 1.0 - p.u;
-    g = fma(-p.u, g, 1.0);                   // 1 - u + u^2
-    g = fma(-p.u, g, 1.0);                   // 1 - u + u^2 - u^3   (u^4 <= 1.5e-11 relative)
+    const double g = fma(p.u, p.u, 1.0 - p.u);       // 1 - u + u^2   (u^3 <= 9.3e-10 relative)
     rcp = p.r8 * g;
     return s_tab[p.idx] + log1p_small(p.u);
 }

@@ -43,7 +43,7 @@ __device__ __forceinline__ void k3_elem(double ea, double ebc, double2 qn, doubl
                                         const ThetaDev& th, double s2, const double* s_tab,
                                         double (&A)[3], double (&G)[3], double (&Hh)[3]) {
     pair_weights(qn, qm, w);
-    const ElemM r = elem_from_cache(ea, ebc);
+    const ElemM r = elem_from_cache(ea, ebc, th);
     const double sw2 = s2 * w[2];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -66,7 +66,7 @@ __device__ __forceinline__ void k3_elem(double ea, double ebc, double2 qn, doubl
         }
         A[k] = a;
         if (GRAD) {
-            const double num = fma(-0.5, r.o[k], r.e[k]);
+            const double num = elem_num(r, k);
             G[k] = fma(num, ds, G[k]);
             Hh[k] = fma(num, hs, Hh[k]);
         }
@@ -80,7 +80,7 @@ elm_kernel(const double* __restrict__ Ea, const double* __restrict__ Eb, const d
            const double* __restrict__ qF, const double* __restrict__ qR, int N, int64_t c0,
            const __grid_constant__ ThetaDev th, const double* __restrict__ g_tab,
            double* __restrict__ Aout, double* __restrict__ out, double* __restrict__ ws) {
-    __shared__ double s_tab[FAST ? kLogTabSize : 1];
+    extern __shared__ double s_tab[];               // kLogTabBytes when FAST, unused otherwise
     load_log_table<FAST>(g_tab, s_tab);
     const int lane = threadIdx.x & 31;
     const double s2 = 2.0 * th.eta - 1.0;
@@ -190,13 +190,17 @@ static int launch_elm(const double* Ea, const double* Eb, const double* Tm,
     FCD_REQUIRE(tab != nullptr, "fcd_elm_obj_grad: log table initialisation failed");
     FCD_REQUIRE(grad || Tm != nullptr, "fcd_elm_obj_grad: nothing to compute (no gradient, no Tm)");
     int grid = red_grid(C, kRedThreads / 32);
-    if (grid > sm_count() * 4) grid = sm_count() * 4;
+    if (grid > sm_count() * 2) grid = sm_count() * 2;      // 2 CTAs / SM resident (86 KB table, <= 128 regs)
     uintptr_t al = reinterpret_cast<uintptr_t>(Ea) | reinterpret_cast<uintptr_t>(Eb) | reinterpret_cast<uintptr_t>(Tm);
     const bool vec2 = (pitchU % 2 == 0) && ((al & 15) == 0);
     const bool fast = log_table_covers(th.epsl, th.al);
 #define FCD_ELM(G, K, V, F)                                                                        \
-    elm_kernel<G, K, V, F><<<grid, kRedThreads, 0, st>>>(Ea, Eb, Tm, C, U, pitchU, qF, qR, N, c0, th, tab, \
-                                                         Aout, out4, ws)
+    do {                                                                                           \
+        cudaFuncSetAttribute(elm_kernel<G, K, V, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                             (int)kLogTabBytes);                                                   \
+        elm_kernel<G, K, V, F><<<grid, kRedThreads, (F) ? kLogTabBytes : 0, st>>>(                 \
+            Ea, Eb, Tm, C, U, pitchU, qF, qR, N, c0, th, tab, Aout, out4, ws);                      \
+    } while (0)
 #define FCD_ELM_VF(G, K)                                                                           \
     do {                                                                                           \
         if (vec2) { if (fast) FCD_ELM(G, K, true, true); else FCD_ELM(G, K, true, false); }        \

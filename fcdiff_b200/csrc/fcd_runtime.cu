@@ -58,7 +58,7 @@ const double* log_table(cudaStream_t st) {
     if (addr[dev] == nullptr) {
         double* p = nullptr;
         if (cudaGetSymbolAddress((void**)&p, g_log_tab) != cudaSuccess) return nullptr;
-        build_log_table_kernel<<<21, 256, 0, st>>>();
+        build_log_table_kernel<<<42, 256, 0, st>>>();
         if (check_launch("build_log_table") != 0) return nullptr;
         if (cudaStreamSynchronize(st) != cudaSuccess) return nullptr;
         addr[dev] = p;
@@ -93,7 +93,10 @@ ThetaDev make_theta_dev(const fcd_theta& th, int H) {
     d.epsl[0] = 1.0 - th.epsilon;
     d.epsl[1] = th.epsilon;
     d.epsl[2] = th.eta * th.epsilon + (1.0 - th.eta) * (1.0 - th.epsilon);
-    for (int l = 0; l < 3; ++l) d.al[l] = (1.0 - d.epsl[l]) * 0.5;
+    for (int l = 0; l < 3; ++l) {
+        d.al[l] = (1.0 - d.epsl[l]) * 0.5;
+        d.bl[l] = d.epsl[l] - d.al[l];
+    }
     d.eta = th.eta;
     d.epsilon = th.epsilon;
     d.log_pi2[0] = log(1.0 - th.pi);

@@ -189,7 +189,9 @@ def test_cfg1_fused_iterations_without_optimiser(cfg1):
         nptest.assert_allclose(fit._eval_energy(), g["noopt_it%d_energy" % it], rtol=1e-10)
     for x, fg in zip(g["noopt_obj_pts"], g["noopt_obj_fg"]):
         (f, grad) = fit._objective(x)
-        nptest.assert_allclose([f, grad[0], grad[1]], fg, rtol=1e-10)
+        nptest.assert_allclose(f, fg[0], rtol=1e-10)
+        # the gradient uses 1/M' = r(1 - u + u^2): truncation <= 9.3e-10 relative (fcd_math.cuh)
+        nptest.assert_allclose(grad, fg[1:], rtol=5e-9)
         nptest.assert_allclose(fit._opt_fun(np.array(x)), fg[0], rtol=1e-10)
 
 
