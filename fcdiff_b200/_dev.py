@@ -13,8 +13,14 @@ from . import _lib
 _ws = {}
 
 
+_have_cuda = None
+
+
 def device():
-    if not torch.cuda.is_available():
+    global _have_cuda
+    if _have_cuda is None:
+        _have_cuda = bool(torch.cuda.is_available())
+    if not _have_cuda:
         raise _lib.FcdError(
             "fcdiff_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
     return torch.device("cuda", torch.cuda.current_device())
@@ -71,6 +77,21 @@ def upload_rows(a, pitch):
 
 def download(t):
     return t.detach().cpu().numpy()
+
+
+class SmallResult(object):
+    """A few doubles produced by a reduction kernel: one device vector reused for
+    every call and a pinned host mirror, so that reading a result costs one
+    asynchronous copy and one stream synchronisation (no allocation)."""
+
+    def __init__(self, n):
+        self.dev = torch.zeros(n, dtype=torch.float64, device=device())
+        self.host = torch.zeros(n, dtype=torch.float64).pin_memory()
+
+    def read(self):
+        self.host.copy_(self.dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.host.numpy().copy()
 
 
 def even(n):

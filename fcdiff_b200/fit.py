@@ -136,10 +136,12 @@ class UnsharedRegionFit(object):
         self._explicit = {}           # user-assigned _lp_B_g_F / _p_Bt_g_Ft / _lM
         self._mat = None              # materialised caches (host) for the getters
         self._theta_lps = None        # (mu, sigma, eta, epsilon) at the last _update_lps
+        self._cache_key = None        # (mu, sigma) as tuples: identity of the Gaussian cache
         self._in = None               # uploaded inputs
         self._evals = []              # recent K3b evaluations (per-edge sums reusable by K2 / K4)
         self._const = None            # theta-free part of E_lM for the current (q_F, q_R)
         self.reuse_evaluations = True
+        self._res = {}                # reusable device / pinned-host result vectors
 
     # ------------------------------------------------------------------ private arrays
     @property
@@ -254,8 +256,7 @@ class UnsharedRegionFit(object):
         (mu, sigma) of the last ``_update_lps`` (rebuilt only when they change;
         the reference never changes them, fit.py:232-237)."""
         inp = self._ensure_inputs()
-        (mu, sigma, _, _) = self._theta_lps
-        ckey = (tuple(float(v) for v in mu), tuple(float(v) for v in sigma))
+        ckey = self._cache_key
         if inp['cache_key'] == ckey:
             return inp
         lib = _lib.load()
@@ -305,6 +306,12 @@ class UnsharedRegionFit(object):
         if inp['WT'] is None:
             inp['WT'] = _dev.empty((Ul, C, 3))
         return inp
+
+    def _result(self, n):
+        key = (n, torch.cuda.current_device())
+        if key not in self._res:
+            self._res[key] = _dev.SmallResult(n)
+        return self._res[key]
 
     def _theta(self, use_snapshot=True):
         m = self.model
@@ -388,6 +395,7 @@ class UnsharedRegionFit(object):
         m = self.model
         self._theta_lps = (np.array(m.mu, dtype=np.float64), np.array(m.sigma, dtype=np.float64),
                            float(m.eta), float(m.epsilon))
+        self._cache_key = (tuple(float(v) for v in m.mu), tuple(float(v) for v in m.sigma))
         if self._dims is None:
             inp = self._in
             self._dims = (int(util.C_to_N(inp['C'])), inp['H'], inp['U'])
@@ -453,7 +461,8 @@ class UnsharedRegionFit(object):
         (lqR, qR) = self._mR.get_dev()
         (c0, Cl) = (inp['c0'], inp['Cl'])
         th = self._theta()
-        out = _dev.empty((6,))
+        res = self._result(6)
+        out = res.dev
         ev = self._find_eval(need_F=True)
         elm = None
         if ev is not None:      # global E_lM is known: rank 0 contributes it, the others zero
@@ -467,9 +476,9 @@ class UnsharedRegionFit(object):
                 ctypes.byref(th), elm, _dev.ptr(out), _dev.ptr(_dev.workspace()), _dev.stream()),
                 "fcd_energy_terms")
         if self.shards is not None:
-            out = self.shards.allreduce_terms(out, (0, 1, 3, 4))
-            return self.shards.fix_replicated(_dev.download(out), (0, 1, 3, 4))
-        return _dev.download(out)
+            self.shards.allreduce_terms(out, (0, 1, 3, 4))
+            return self.shards.fix_replicated(res.read(), (0, 1, 3, 4))
+        return res.read()
 
     def _update_lq_F(self):
         """
@@ -578,14 +587,15 @@ class UnsharedRegionFit(object):
         if do_pi:
             (lqR, _) = self._mR.get_dev()
             NU = lqR.numel() // 2
-        out = _dev.empty((4,))
+        res = self._result(5)
+        out = res.dev
         with _dev.timed(self.profile, "K3a_mstep_stats"):
             _lib.check(lib.fcd_mstep_stats(_dev.ptr(lqF), Cl, _dev.ptr(lqR), NU, _dev.ptr(out),
                                            _dev.ptr(_dev.workspace()), _dev.stream()), "fcd_mstep_stats")
         if do_gamma and self.shards is not None and self._in is not None:
-            out = self.shards.allreduce_terms(out, (0, 1, 2))
-            return self.shards.fix_replicated(_dev.download(out), (0, 1, 2)), C, NU
-        return _dev.download(out), C, NU
+            self.shards.allreduce_terms(out, (0, 1, 2))
+            return self.shards.fix_replicated(res.read(), (0, 1, 2)), C, NU
+        return res.read(), C, NU
 
     def _update_pi_gamma(self, do_pi, do_gamma):
         (s, C, NU) = self._mstep_sums(do_pi, do_gamma)
@@ -628,17 +638,17 @@ class UnsharedRegionFit(object):
             inp['A'][slot] = _dev.empty((max(Cl, 1) * 3,))
         A = inp['A'][slot]
         self._evals = [ev for ev in self._evals if ev['A'] is not A]
-        out = _dev.empty((4,))
+        res = self._result(4)
         with _dev.timed(self.profile, "K3b_elm_obj_grad"):
             _lib.check(lib.fcd_elm_obj_grad(
                 _dev.ptr(inp['Ea']), _dev.ptr(inp['Eb']),
                 _dev.ptr(inp['Tm']) if (need_const or not want_grad) else None,
                 Cl, U, inp['pitchU'], _dev.ptr(qF[c0 * 3:]), _dev.ptr(qR), N, c0,
-                ctypes.byref(th), 1 if want_grad else 0, _dev.ptr(A), _dev.ptr(out),
+                ctypes.byref(th), 1 if want_grad else 0, _dev.ptr(A), _dev.ptr(res.dev),
                 _dev.ptr(_dev.workspace()), _dev.stream()), "fcd_elm_obj_grad")
         if self.shards is not None:
-            out = self.shards.allreduce_terms(out, (0, 1, 2, 3))      # all four are edge-local partial sums
-        o = _dev.download(out)
+            self.shards.allreduce_terms(res.dev, (0, 1, 2, 3))        # all four are edge-local partial sums
+        o = res.read()
         if need_const or not want_grad:
             self._const = (ckey, float(o[3]))
         elm = float(o[0]) + self._const[1]
