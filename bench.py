@@ -290,6 +290,20 @@ def run_gpu_arm(args):
                 "rel_tol": fitc.rel_tol, "objective_evals": int(sum(fitc.n_objective_evals)),
                 "what": "fit.run() to the reference's convergence rule (fit.py:138-140) incl. set-up "
                         "(healthy stats, Gaussian cache, patient-major planes)"}
+    fitm = new_fit(b_dev, bt_dev)
+    fitm.max_iters = 100
+    fitm.convergence_rule = "magnitude"
+    barrier()
+    tm0 = time.perf_counter()
+    fitm.run()
+    barrier()
+    tmag = torch.tensor([time.perf_counter() - tm0], dtype=torch.float64, device="cuda")
+    if shards is not None:
+        dist.all_reduce(tmag, op=dist.ReduceOp.MAX)
+    converge["magnitude_rule"] = {"seconds": float(tmag.item()), "iterations": len(fitm.energy) - 1,
+                                  "objective_evals": int(sum(fitm.n_objective_evals)),
+                                  "what": "same with (e - e*)/|e| < rel_tol (the reference's rule stops at the first "
+                                          "decrease of a negative energy)"}
 
     # ---- end-to-end arm: host (pinned) arrays through the public API every step
     e2e = None

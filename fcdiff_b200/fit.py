@@ -113,6 +113,11 @@ class UnsharedRegionFit(object):
         Edge sharding over the ranks of a ``torch.distributed`` group (new).
     optimise_theta_sub : bool
         Run the (eta, epsilon) optimiser in ``_update_theta`` (default True).
+    convergence_rule : "reference" | "magnitude"
+        ``"reference"`` is fit.py:138-140 literally, ``(e - e*) / e < rel_tol``: with a
+        negative free energy (the usual case: densities > 1) any *decrease* makes the
+        ratio negative, so the loop stops at the first decrease after the sign change.
+        ``"magnitude"`` divides by ``|e|`` (new knob, not the default).
     """
 
     def __init__(self):
@@ -126,6 +131,7 @@ class UnsharedRegionFit(object):
         self.shards = None
         self.n_edges = None           # global edge count when b / bt are device edge shards
         self.optimise_theta_sub = True
+        self.convergence_rule = "reference"
         self.n_objective_evals = []
         self.profile = None           # _dev.KernelTimers for per-kernel CUDA-event timing
 
@@ -409,6 +415,8 @@ class UnsharedRegionFit(object):
         """
         e = self.energy[s - 1]
         e_star = self.energy[s]
+        if self.convergence_rule == "magnitude":
+            return ((e - e_star) / abs(e)) < self.rel_tol
         return ((e - e_star) / e) < self.rel_tol
 
     def _arrays_mode(self, *names):

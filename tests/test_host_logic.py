@@ -61,6 +61,16 @@ def test_is_converged(energy, expect):
     assert bool(fit._is_converged(1)) is expect
 
 
+def test_convergence_rule_with_negative_energy():
+    fit = fcdiff.fit.UnsharedRegionFit()
+    fit.energy = [-100.0, -110.0]                 # a 10 % decrease of a negative energy
+    assert bool(fit._is_converged(1)) is True     # the reference's rule stops here (ratio < 0)
+    fit.convergence_rule = "magnitude"
+    assert bool(fit._is_converged(1)) is False
+    fit.energy = [-100.0, -100.0000001]
+    assert bool(fit._is_converged(1)) is True
+
+
 def test_pack_unpack_theta_sub():
     fit = fcdiff.fit.UnsharedRegionFit()
     fit.model = fcdiff.UnsharedRegionModel()
