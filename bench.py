@@ -44,8 +44,13 @@ U_SUBJ = 500
 EDGES_PER_GPU = 79800           # Schaefer-400
 
 
+_REGIONS_OVERRIDE = 0
+
+
 def regions_for(n_gpus):
     """Smallest N whose edge count reaches n_gpus * 79,800 (400 at one GPU)."""
+    if _REGIONS_OVERRIDE > 0:
+        return _REGIONS_OVERRIDE
     N = 400
     while N * (N - 1) // 2 < n_gpus * EDGES_PER_GPU:
         N += 1
@@ -178,8 +183,8 @@ def run_reference_arm(args):
 def workload_config(n_gpus):
     N = regions_for(n_gpus)
     return {"workload": "Schaefer-400 x (500 controls + 500 patients), BASELINE.json configs[2]"
-                        if n_gpus == 1 else
-                        "%d-region atlas (~79,800 edges per GPU) x (500 controls + 500 patients)" % N,
+                        if (n_gpus == 1 and N == 400 and H_SUBJ == 500) else
+                        "%d-region atlas (%d edges over %d GPU) x (%d controls + %d patients)" % (N, N * (N - 1) // 2, n_gpus, H_SUBJ, U_SUBJ),
             "regions": N, "edges": N * (N - 1) // 2, "controls": H_SUBJ, "patients": U_SUBJ,
             "edge_lookup": "reference", "storage": "f64",
             "l2": "per-step working set (bt + btT + W = 1.6 GB per GPU) exceeds the 126 MB L2; no flush needed",
@@ -390,8 +395,11 @@ def run_gpu_arm(args):
         "cpu_baseline": cpu, "time_to_converge": converge, "kernels": kernels,
         "energy_trace": [float(e) for e in energies[:4]] + ["..."] + [float(energies[-1])],
     }
-    print(json.dumps(line))
+    _emit(json.dumps(line))
     return 0
+
+
+_emit = print
 
 
 def main():
@@ -401,9 +409,23 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--regions", type=int, default=0, help="override the atlas size (manual experiments)")
+    ap.add_argument("--subjects", type=int, default=0, help="override controls = patients (manual experiments)")
     args = ap.parse_args()
+    global H_SUBJ, U_SUBJ, _REGIONS_OVERRIDE
+    if args.subjects > 0:
+        H_SUBJ = U_SUBJ = args.subjects
+    _REGIONS_OVERRIDE = args.regions
     if args.impl == "reference":
         return run_reference_arm(args)
+    # Exactly one JSON line must reach stdout: libraries (NCCL's version banner, for one)
+    # print there too, so stdout is pointed at stderr for the duration of the run and the
+    # JSON line is written to the real stdout.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global _emit
+    _emit = lambda text: os.write(real_stdout, (text + "\n").encode())
     rc = run_gpu_arm(args)
     try:
         import torch.distributed as dist
