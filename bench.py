@@ -118,7 +118,7 @@ def algorithmic_bytes(kernel, C, N, H, U):
     return {
         "K2_estep_qF": 8 * C * U + 16 * C + 48 * C + 16 * N * U,        # bt, S1/S2, lqF+qF out, qR
         "K2b_region_weights": 8 * C * U + 24 * C + 24 * C * U,          # btT, qF, WT out
-        "K2b_sweep": 24 * 2 * C * U + 32 * N * U + 32 * N * U,          # WT window reads, qR/lqR in/out
+        "K2b_sweep": 24 * C * U + 16 * N * U + 32 * N * U,              # WT once (window overlaps hit L1/L2), qR in, qR/lqR out
         "K3b_elm_obj_grad": 8 * C * U + 24 * C + 16 * N * U,            # bt, qF, qR
         "K4_energy_terms": 8 * C * U + 64 * C + 48 * N * U,             # bt, S1/S2/lqF/qF, lqR/qR
         "K3a_mstep_stats": 24 * C + 16 * N * U,
@@ -279,6 +279,7 @@ def run_gpu_arm(args):
     ms = float(t.item())
     value = C * (H + U) * args.steps / (ms * 1e-3)
     nfev = float(np.mean(fit.n_objective_evals)) if fit.n_objective_evals else 0.0
+    del fit                                    # release its cache planes before the next fits allocate theirs
 
     # ---- time to converge (north_star target): whole fit from device-resident inputs
     barrier()
@@ -295,6 +296,7 @@ def run_gpu_arm(args):
                 "rel_tol": fitc.rel_tol, "objective_evals": int(sum(fitc.n_objective_evals)),
                 "what": "fit.run() to the reference's convergence rule (fit.py:138-140) incl. set-up "
                         "(healthy stats, Gaussian cache, patient-major planes)"}
+    del fitc
     fitm = new_fit(b_dev, bt_dev)
     fitm.max_iters = 100
     fitm.convergence_rule = "magnitude"
@@ -309,6 +311,7 @@ def run_gpu_arm(args):
                                   "objective_evals": int(sum(fitm.n_objective_evals)),
                                   "what": "same with (e - e*)/|e| < rel_tol (the reference's rule stops at the first "
                                           "decrease of a negative energy)"}
+    del fitm
 
     # ---- end-to-end arm: host (pinned) arrays through the public API every step
     e2e = None
