@@ -517,3 +517,30 @@ def test_evaluation_reuse_is_invalidated_by_assignments():
     fit2.run()
     nptest.assert_allclose(e1, fit2.energy, rtol=1e-13)
     nptest.assert_allclose(lqF1, fit2._lq_F, rtol=1e-10, atol=1e-11)
+
+
+# ------------------------------------------------------------------ recovery of planted structure
+@pytest.mark.parametrize("lookup", ["symmetric", "reference"])
+def test_fit_recovers_planted_template_and_regions(lookup):
+    """Data drawn from create_ideal_model() (test_fit.py:11-22) by the device
+    sampler in util edge order; the fit started at the truth must recover the
+    planted template f on nearly every edge and, with the mathematically
+    consistent edge lookup, the planted anomalous regions r."""
+    from fcdiff_b200 import _dev
+    true_model = ideal_model()
+    true_model.rng = np.random.RandomState(11)
+    (N, H, U) = (60, 40, 50)
+    (r, t, f, ft, b, bt) = true_model.sample(N, H, U)
+    fit = _fit_for(b, bt, ideal_model())
+    fit.edge_lookup = lookup
+    fit.convergence_rule = "magnitude"
+    fit.max_iters = 15
+    fit.run()
+    map_f = np.argmax(fit._lq_F[:, 0, :], axis=1)
+    assert np.mean(map_f == np.argmax(f, axis=1)) > 0.995
+    if lookup == "symmetric":
+        map_r = fit._lq_R[:, :, 1] > fit._lq_R[:, :, 0]
+        assert np.mean(map_r == r) > 0.97
+        nptest.assert_allclose(fit.model.pi, r.mean(), atol=0.03)
+        nptest.assert_allclose(fit.model.gamma, f.mean(axis=0), atol=0.02)
+    assert np.all(np.isfinite(fit.energy))
