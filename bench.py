@@ -120,6 +120,7 @@ def algorithmic_bytes(kernel, C, N, H, U):
         "K2b_region_weights": 8 * C * U + 24 * C + 24 * C * U,          # btT, qF, WT out
         "K2b_sweep": 24 * C * U + 16 * N * U + 32 * N * U,              # WT once (window overlaps hit L1/L2), qR in, qR/lqR out
         "K3b_elm_obj_grad": 8 * C * U + 24 * C + 16 * N * U,            # bt, qF, qR
+        "K3b_elm_const": 8 * C * U + 24 * C + 16 * N * U,
         "K4_energy_terms": 8 * C * U + 64 * C + 48 * N * U,             # bt, S1/S2/lqF/qF, lqR/qR
         "K3a_mstep_stats": 24 * C + 16 * N * U,
     }.get(kernel)

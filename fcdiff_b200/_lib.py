@@ -32,18 +32,23 @@ SIGNATURES = {
     "fcd_launch_count_reset": (None, []),
     "fcd_c_to_nm": (c_int, [c_int64, c_int64, _P, _P, _P]),
     "fcd_healthy_stats": (c_int, [_P, c_int64, c_int32, c_int64, _P, _P, _P]),
-    "fcd_gauss_cache": (c_int, [_P, c_int64, c_int32, c_int64, POINTER(FcdTheta), _P, _P, _P, _P]),
-    "fcd_estep_qF": (c_int, [_P, _P, c_int32, _P, _P, c_int64, c_int32, c_int64, _P, c_int32, c_int64,
+    "fcd_edge_table": (c_int, [c_int64, c_int64, _P, _P]),
+    "fcd_resp_cache": (c_int, [_P, c_int64, c_int32, c_int64, POINTER(FcdTheta), _P, c_int64, _P, _P]),
+    "fcd_peak_states_F": (c_int, [_P, c_int64, _P, _P]),
+    "fcd_peak_states_R": (c_int, [_P, c_int32, c_int32, c_int64, _P, _P]),
+    "fcd_estep_qF": (c_int, [_P, _P, c_int32, _P, c_int64, c_int64, c_int32, c_int64, _P, _P, c_int64, c_int32, _P,
                              POINTER(FcdTheta), _P, _P, _P]),
-    "fcd_estep_qF_finish": (c_int, [_P, _P, c_int32, _P, c_int64, POINTER(FcdTheta), _P, _P, _P]),
     "fcd_transpose_patients": (c_int, [_P, c_int64, c_int32, c_int64, c_int32, c_int32, _P, c_int64, _P]),
-    "fcd_region_weights": (c_int, [_P, _P, c_int32, c_int64, c_int64, _P, POINTER(FcdTheta), _P, _P]),
+    "fcd_region_weights": (c_int, [_P, c_int64, c_int32, c_int64, c_int64, _P, _P, POINTER(FcdTheta), _P, _P]),
     "fcd_estep_qR": (c_int, [_P, c_int64, c_int32, c_int32, c_int32, c_int32, _D3, c_int32, _P, _P, _P]),
     "fcd_mstep_stats": (c_int, [_P, c_int64, _P, c_int64, _P, _P, _P]),
-    "fcd_elm_obj_grad": (c_int, [_P, _P, _P, c_int64, c_int32, c_int64, _P, _P, c_int32, c_int64,
-                                 POINTER(FcdTheta), c_int32, _P, _P, _P, _P]),
-    "fcd_energy_terms": (c_int, [_P, _P, c_int32, _P, _P, _P, c_int64, c_int32, c_int64, _P, _P, _P, _P,
-                                 c_int32, c_int64, POINTER(FcdTheta), POINTER(c_double), _P, _P, _P]),
+    "fcd_elm_obj_grad": (c_int, [_P, c_int64, c_int64, c_int32, c_int64, _P, _P, _P, _P, c_int64, c_int32, _P,
+                                 POINTER(FcdTheta), c_int32, _P, _P, _P]),
+    "fcd_elm_const": (c_int, [_P, c_int64, c_int32, c_int64, _P, _P, _P, _P, c_int64, c_int32, _P, _P, _P, _P]),
+    "fcd_energy_terms": (c_int, [_P, _P, c_int32, _P, _P, c_int64, _P, _P, c_int32, c_int32,
+                                 POINTER(FcdTheta), c_double, _P, _P, _P]),
+    "fcd_state_moments": (c_int, [_P, _P, c_int32, _P, _P, c_int64, c_int64, c_int32, c_int64, _P, _P, c_int32, _P,
+                                  POINTER(FcdTheta), _P, _P, _P]),
     "fcd_materialize_lps": (c_int, [_P, _P, c_int64, c_int32, c_int32, POINTER(FcdTheta), _P, _P, _P, _P]),
     "fcd_eval_M": (c_int, [_P, c_int64, c_double, c_double, c_int32, c_int32, _P, _P]),
     "fcd_lqF_from_arrays": (c_int, [_P, _P, c_int64, c_int32, c_int32, _P, c_int32, _D3, _P, _P]),
@@ -84,7 +89,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the symbol is missing
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.fcd_version() < 100:
+    if lib.fcd_version() < 110:
         raise FcdError("fcdiff_b200: stale libfcdiff_b200.so (version %d)" % lib.fcd_version())
     _lib = lib
     return lib

@@ -30,7 +30,7 @@ constexpr double kHalfLog2Pi = 0.91893853320467274178032973640562;   // log(sqrt
 // Workspace layout (doubles): [0, kWsPartials) per-CTA partial sums,
 // then one 64-bit slot holding the arrival ticket, then 16 scratch doubles.
 constexpr int     kMaxReduceBlocks = 2048;
-constexpr int     kMaxReduceVals   = 8;
+constexpr int     kMaxReduceVals   = 9;
 constexpr int64_t kWsPartials      = (int64_t)kMaxReduceBlocks * kMaxReduceVals;
 constexpr int64_t kWsScratch       = kWsPartials + 2;      // 16 doubles of scratch for chained reductions
 constexpr int64_t kWsDoubles       = kWsScratch + 16;
@@ -86,75 +86,68 @@ __device__ __forceinline__ double ldg_stream1(const double* p) {
     return r;
 }
 
-// Per-element core shared by K2 / K2b / K3 / K4.
+// Per-element core shared by K2 / K2b / K3 / K4: the *responsibility planes*.
 //
-// For x = bt[c,u]:   t_k = -((x-mu_k)/sigma_k)^2/2 - log sigma_k,
-//                    e_k = exp(t_k - max_j t_j),  o_k = sum_{j != k} e_j,
-//                    Mp[k][l] = eps_l e_k + a_l o_k.
-// Then log M_kl(x) of fcdiff/fit.py:117-122 equals
-//                    log Mp[k][l] + tmax - log sqrt(2 pi)
-// exactly (M_kl = eps_l p_k + (1-eps_l)/2 * sum_{j != k} p_j, fit.py:427-430),
-// evaluated without the underflow of exp() in the far tails.
+// For x = bt[c,u]:   N_k = N(x; mu_k, sigma_k)                      (fit.py:115)
+//                    p_k = N_k / (N_0 + N_1 + N_2),   L = log(N_0 + N_1 + N_2).
+// Then, with a_l = (1 - eps_l)/2 and b_l = eps_l - a_l,
+//     M_kl = eps_l N_k + a_l sum_{j != k} N_j = (a_l + b_l p_k) exp(L)   (fit.py:427-430)
+//     log M_kl = L + log(a_l + b_l p_k)                                  (fit.py:117-122)
+// exactly, without the underflow of the reference's pdf in the far tails.
+// p_k and L depend on (x, mu, sigma) only and the reference never re-estimates
+// mu, sigma (fit.py:232-237): resp_cache_kernel takes the exponentials ONCE per
+// fit and stores the planes P0, P1, P2 and L ([C][pitchU] each); every later
+// pass reads planes.  All dependence on (eta, epsilon) is in (a_l, b_l), and the
+// theta-free term sum w L is summed separately (elm_const_kernel).
 //
-// e_k depends on (x, mu, sigma) only, and the reference never re-estimates mu,
-// sigma (fit.py:232-237): the E/M/energy kernels therefore read a per-element
-// *Gaussian cache* built once per fit by gauss_cache_kernel instead of x:
-//   Ea = e of the first non-maximal component, Eb = e of the second one with the
-//   index of the maximal component (whose e is exactly 1) in its two lowest
-//   mantissa bits, Tm = max_k t_k.
-struct ElemM {
-    double e[3];
-    double aS[3];     // a_l * (e_0 + e_1 + e_2)
-    double mhS;       // -(e_0 + e_1 + e_2) / 2
+// Tiers.  The posteriors of this model are sharply peaked: q_F[c,:] is one-hot to
+// rounding for (practically) every edge and q_R[n,u,:] for ~95 % of the
+// (region, patient) pairs.  A weight below kPeakTau = 2^-60 multiplies a log of
+// magnitude <= 14: dropping the term changes a sum of O(1) terms by less than
+// its own rounding error.  The peak-state bytes (peak_states_*_kernel)
+//   fstate[c]   = k* if q_F[c,k*] == 1.0 exactly and the others <= 2^-60, else 3
+//   rstate[n,u] = s  if q_R[n,u,s] == 1.0 exactly and the other  <= 2^-60, else 2
+//                 (4 in the padding column)
+// let the kernels take, per element,
+//   T1: edge and both regions peaked -> ONE plane (k*), ONE log (l* from 2 bytes);
+//   T2: edge peaked, a region not    -> k* plane, 3 logs, real pair weights;
+//   T3: edge not peaked              -> 3 planes, 9 logs (the reference's form).
+// T1 runs for all lanes of a warp; T2 elements are compacted into a per-warp
+// queue in shared memory and evaluated 32 at a time, so that the rare expensive
+// elements do not drag whole warps into the slow path.
+constexpr double kPeakTau = 8.673617379884035e-19;        // 2^-60
+constexpr int kStateMixedR = 2, kStateDead = 4, kStateMixedF = 3;
+
+struct Resp {
+    double p[3];
+    double L;
 };
 
-struct GaussElem {
-    double ea, ebc, tmax;
-};
-
-__device__ __forceinline__ GaussElem gauss_eval(double x, const ThetaDev& th) {
+__device__ __forceinline__ Resp resp_eval(double x, const ThetaDev& th) {
     double t[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         double z = (x - th.mu[k]) * th.isig[k];
         t[k] = fma(-0.5 * z, z, th.lc[k]);
     }
-    // the maximal component has e = exp(0) = 1 exactly: only two exponentials
-    const bool m0 = (t[0] >= t[1]) && (t[0] >= t[2]);
-    const bool m1 = !m0 && (t[1] >= t[2]);
-    const bool m01 = m0 || m1;
-    GaussElem g;
-    g.tmax = m0 ? t[0] : (m1 ? t[1] : t[2]);
-    g.ea = exp_nonpos((m0 ? t[1] : t[0]) - g.tmax);
-    const double eb = exp_nonpos((m01 ? t[2] : t[1]) - g.tmax);
-    const int code = m0 ? 0 : (m1 ? 1 : 2);
-    g.ebc = __hiloint2double(__double2hiint(eb), (__double2loint(eb) & ~3) | code);
-    return g;
-}
-
-__device__ __forceinline__ ElemM elem_from_cache(double ea, double ebc, const ThetaDev& th) {
-    const int code = __double2loint(ebc) & 3;
-    const bool m0 = code == 0, m1 = code == 1;
-    ElemM r;
-    r.e[0] = m0 ? 1.0 : ea;
-    r.e[1] = m1 ? 1.0 : (m0 ? ea : ebc);
-    r.e[2] = (m0 || m1) ? ebc : 1.0;
-    // Mp[k][l] = eps_l e_k + a_l (S - e_k) = b_l e_k + a_l S with b_l = eps_l - a_l: one FMA per
-    // (k, l).  Where b_l < 0 the cancellation costs at most 1e-16 a_l / eps_l relative
-    // (5e-12 at the optimiser's bound eps = 1e-5, 1e-15 at typical values).
-    const double S = (1.0 + ea) + ebc;
+    const double tmax = fmax(t[0], fmax(t[1], t[2]));
+    double e[3];
 #pragma unroll
-    for (int l = 0; l < 3; ++l) r.aS[l] = th.al[l] * S;
-    r.mhS = -0.5 * S;
+    for (int k = 0; k < 3; ++k) e[k] = (t[k] == tmax) ? 1.0 : exp_nonpos(t[k] - tmax);
+    const double S = e[0] + e[1] + e[2];
+    const double inv = 1.0 / S;
+    Resp r;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) r.p[k] = e[k] * inv;
+    r.L = (tmax - kHalfLog2Pi) + log(S);
     return r;
 }
 
-__device__ __forceinline__ double elem_Mp(const ElemM& r, const ThetaDev& th, int k, int l) {
-    return fma(th.bl[l], r.e[k], r.aS[l]);
-}
+// a_l + b_l p: the mixture weight relative to the total density
+__device__ __forceinline__ double mix_rel(const ThetaDev& th, int l, double p) { return fma(th.bl[l], p, th.al[l]); }
 
-// e_k - o_k / 2 = 1.5 e_k - S / 2: numerator of d log M / d eps (fit.py:618-697)
-__device__ __forceinline__ double elem_num(const ElemM& r, int k) { return fma(1.5, r.e[k], r.mhS); }
+// numerator of d log M_kl / d eps_l relative to the total density (fit.py:618-697)
+__device__ __forceinline__ double mix_num(double p) { return fma(1.5, p, -0.5); }
 
 // q_R pair weights of fcdiff/fit.py:382-406.
 __device__ __forceinline__ void pair_weights(double2 qn, double2 qm, double (&w)[3]) {
@@ -163,80 +156,254 @@ __device__ __forceinline__ void pair_weights(double2 qn, double2 qm, double (&w)
     w[2] = fma(qn.y, qm.x, qn.x * qm.y);
 }
 
-// Row walker shared by K2 / K3b / K4: every warp takes edge rows c = warp0,
-// warp0 + nwarps, ...; within a row each lane owns the patients u = 2*lane,
-// 2*lane + 1 (+64 per chunk), loaded with 128-bit requests (cache planes:
-// ld.global.nc.L1::no_allocate; q_R rows of the edge's two regions: ld.global.nc).
-// The loads of chunk j+1 (also across the row boundary) are issued before chunk
-// j is computed, so the DRAM latency overlaps the ~400-cycle fp64 body instead
-// of stalling its first use (ncu: 24 % of the samples before this change).
-// Elements beyond U are presented with zero q_R, i.e. zero pair weights.
-struct RowChunk {
-    double2 xa, xb, tm, a0, a1, b0, b1;
-};
+__device__ __forceinline__ double sel3(int l, const double (&v)[3]) { return l == 0 ? v[0] : (l == 1 ? v[1] : v[2]); }
 
-template <bool WITH_TM>
-__device__ __forceinline__ RowChunk load_chunk(const double* __restrict__ Ea, const double* __restrict__ Eb,
-                                               const double* __restrict__ Tm, int64_t row_off,
-                                               const double2* __restrict__ qn, const double2* __restrict__ qm,
-                                               int u, int U) {
-    RowChunk k;
-    const double2 z = make_double2(0.0, 0.0);
-    k.xa = k.xb = k.tm = k.a0 = k.a1 = k.b0 = k.b1 = z;
-    if (u < U) {
-        k.xa = ldg_stream2(Ea + row_off + u);
-        k.xb = ldg_stream2(Eb + row_off + u);
-        if (WITH_TM) k.tm = ldg_stream2(Tm + row_off + u);
-        k.a0 = __ldg(qn + u);
-        k.b0 = __ldg(qm + u);
-        if (u + 1 < U) {
-            k.a1 = __ldg(qn + u + 1);
-            k.b1 = __ldg(qm + u + 1);
-        }
-    }
-    return k;
+// ---------------------------------------------------------------- mbarrier / TMA helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// 1-D bulk copy global -> shared through the TMA unit (dst, src 16-byte aligned,
+// bytes a multiple of 16); completion is signalled on `bar` (complete_tx).
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// elem(ea, ebc, tm, qn, qm) is called for every (possibly zero-weight) element,
-// row_end(c) once per row after its last element.  Requires pitchU even and
-// 16-byte aligned planes.
-template <bool WITH_TM, class ElemFn, class RowFn>
-__device__ __forceinline__ void walk_rows(const double* __restrict__ Ea, const double* __restrict__ Eb,
-                                          const double* __restrict__ Tm, int64_t C, int U, int64_t pitchU,
-                                          const double* __restrict__ qR, int64_t c0,
-                                          ElemFn&& elem, RowFn&& row_end) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const double2* qR2 = reinterpret_cast<const double2*>(qR);
-    int64_t c = warp0;
-    if (c >= C) return;
-    int n, m;
-    c_to_nm(c0 + c, n, m);
-    const double2* qn = qR2 + (int64_t)n * U;
-    const double2* qm = qR2 + (int64_t)m * U;
-    RowChunk cur = load_chunk<WITH_TM>(Ea, Eb, Tm, c * pitchU, qn, qm, 2 * lane, U);
-    while (c < C) {
-        const int64_t cn = c + nwarps;
-        const double2 *qn2 = qn, *qm2 = qm;
-        if (cn < C) {
-            c_to_nm(c0 + cn, n, m);
-            qn2 = qR2 + (int64_t)n * U;
-            qm2 = qR2 + (int64_t)m * U;
+// ---------------------------------------------------------------- tiered streaming walker
+// The plane kernels are HBM-streaming with a few fp64 instructions per element,
+// so the bytes in flight must not be limited by registers: the rows are staged
+// through shared memory by the TMA unit.  One CTA per SM: NCW consumer warps
+// and one producer warp.  Consumer warp g (grid-wide index) owns the edge rows
+// c = g, g + G, ...; a row is cut into segments of SEG patients.  Producer lane
+// w feeds the private ring of consumer warp w (D stages; full / empty
+// mbarriers): per segment one 1-D bulk copy per plane (NPL planes starting at
+// plane fstate[c] when USE_K) and one for each of the two regions' peak-state
+// rows, plus a descriptor {k, n | m << 16}.  The producer never blocks: every
+// round each lane polls its ring's empty barrier once (mbarrier.test_wait).
+//   live(pv, l, on)              T1 body, called for both elements of a 64-patient chunk by
+//                                all lanes; `on` is false for deferred / padding slots;
+//   deferred(c, u, n, m, k, ok)  dense evaluation of 32 queued elements (T2), ONE call site;
+//   full(c, n, m, u0, u1)        rows with fstate == 3 (T3), patients [u0, u1), from global;
+//   row_end(c)                   after the last segment of a row (its deferred elements
+//                                have been evaluated when ROW_DRAIN).
+// Requirements: planes 16-byte aligned with even pitchU and planeStride, pitchS a
+// multiple of 16 with rstate == 4 in [U, pitchS), C < 2^29.
+template <int NPL, int SEG>
+struct StreamGeom {
+    static constexpr int kStageBytes = NPL * SEG * 8 + 2 * SEG;
+    static constexpr int kQueueSlots = 256;                  // >= 31 + SEG deferred elements per warp (int2 each)
+    static_assert(SEG % 64 == 0 && SEG + 31 <= kQueueSlots, "bad segment");
+    // bytes of dynamic shared memory after the log table, for NCW consumer warps and D stages
+    static constexpr size_t bytes(int ncw, int d) {
+        return (size_t)ncw * ((size_t)kQueueSlots * 8 + (size_t)d * (kStageBytes + 16 + 16));
+    }
+};
+
+constexpr int kStreamWarps = 15;                             // consumer warps per CTA (+1 producer warp)
+constexpr int kStreamThreads = (kStreamWarps + 1) * 32;
+constexpr size_t kSmemBudget = 224 * 1024;                   // dynamic shared memory of one CTA (1 CTA / SM)
+
+// Ring depth that fits next to `other` bytes (log table) in the CTA's shared memory; 0 if none does.
+template <int NPL, int SEG>
+inline int stream_depth(size_t other) {
+    using G = StreamGeom<NPL, SEG>;
+    for (int d = 8; d >= 2; --d)
+        if (other + G::bytes(kStreamWarps, d) <= kSmemBudget) return d;
+    return 0;
+}
+
+template <int NPL, int SEG, int NCW, bool ROW_DRAIN, bool USE_K, class LiveFn, class DeferredFn, class FullFn,
+          class RowEndFn>
+__device__ __forceinline__ void stream_tiered(const double* __restrict__ P, int64_t planeStride,
+                                              int64_t C, int U, int64_t pitchU,
+                                              const uint8_t* __restrict__ fstate,
+                                              const uint8_t* __restrict__ rstate, int64_t pitchS,
+                                              const int32_t* __restrict__ nm, unsigned char* smem, int D,
+                                              LiveFn&& live, DeferredFn&& deferred, FullFn&& full,
+                                              RowEndFn&& row_end) {
+    using G = StreamGeom<NPL, SEG>;
+    constexpr int QS = G::kQueueSlots;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int2* queues = reinterpret_cast<int2*>(smem);
+    unsigned char* rings = smem + (size_t)NCW * QS * 8;
+    int4* descs = reinterpret_cast<int4*>(rings + (size_t)NCW * D * G::kStageBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(descs + NCW * D);          // [w][d][full, empty]
+    // the rings start zeroed: lanes beyond the copied bytes of a short segment read
+    // stale but valid responsibilities (their contribution is masked)
+    for (int i = threadIdx.x; i < NCW * D * G::kStageBytes / 16; i += blockDim.x)
+        reinterpret_cast<int4*>(rings)[i] = make_int4(0, 0, 0, 0);
+    if (threadIdx.x < NCW * D) {
+        mbar_init(bars + 2 * threadIdx.x, 1);
+        mbar_init(bars + 2 * threadIdx.x + 1, 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    const int nseg = (U + SEG - 1) / SEG;
+    const int64_t nW = (int64_t)gridDim.x * NCW;
+
+    if (warp == NCW) {
+        // ------------------------------------------------------------ producer warp
+        const int w = lane;
+        int64_t c = (int64_t)blockIdx.x * NCW + w;
+        bool active = (w < NCW) && (c < C);
+        int s = 0, it = 0;
+        int cur_nm = 0, cur_k = 0, nxt_nm = 0, nxt_k = 0;
+        if (active) {
+            cur_nm = __ldg(nm + c);
+            cur_k = USE_K ? (int)__ldg(fstate + c) : 0;
+            if (c + nW < C) {
+                nxt_nm = __ldg(nm + c + nW);
+                nxt_k = USE_K ? (int)__ldg(fstate + c + nW) : 0;
+            }
         }
-        for (int u0 = 0; u0 < U; u0 += 64) {
-            RowChunk nxt;
-            if (u0 + 64 < U) nxt = load_chunk<WITH_TM>(Ea, Eb, Tm, c * pitchU, qn, qm, u0 + 64 + 2 * lane, U);
-            else if (cn < C) nxt = load_chunk<WITH_TM>(Ea, Eb, Tm, cn * pitchU, qn2, qm2, 2 * lane, U);
-            else nxt = cur;
-            elem(cur.xa.x, cur.xb.x, cur.tm.x, cur.a0, cur.b0);
-            elem(cur.xa.y, cur.xb.y, cur.tm.y, cur.a1, cur.b1);
-            cur = nxt;
+        while (__any_sync(0xffffffffu, active)) {
+            bool progress = false;
+            if (active) {
+                const int d = it % D;
+                uint64_t* fullb = bars + 2 * (w * D + d);
+                if (mbar_test(fullb + 1, ((it / D) & 1) ^ 1)) {
+                    descs[w * D + d] = make_int4(cur_k, cur_nm, 0, 0);
+                    const int u0 = s * SEG;
+                    const int np = (int)(pitchU - u0 < SEG ? pitchU - u0 : SEG);
+                    const int ns = (int)(pitchS - u0 < SEG ? pitchS - u0 : SEG);
+                    const bool planes = cur_k < 3;
+                    mbar_expect_tx(fullb, (uint32_t)(2 * ns + (planes ? NPL * np * 8 : 0)));
+                    unsigned char* st = rings + (size_t)(w * D + d) * G::kStageBytes;
+                    if (planes) {
+                        const double* src = P + (int64_t)cur_k * planeStride + c * pitchU + u0;
+#pragma unroll
+                        for (int i = 0; i < NPL; ++i)
+                            tma_load_1d(st + i * SEG * 8, src + i * planeStride, (uint32_t)(np * 8), fullb);
+                    }
+                    tma_load_1d(st + NPL * SEG * 8, rstate + (int64_t)(cur_nm & 0xffff) * pitchS + u0, (uint32_t)ns,
+                                fullb);
+                    tma_load_1d(st + NPL * SEG * 8 + SEG, rstate + (int64_t)((cur_nm >> 16) & 0xffff) * pitchS + u0,
+                                (uint32_t)ns, fullb);
+                    ++it;
+                    progress = true;
+                    if (++s == nseg) {
+                        s = 0;
+                        c += nW;
+                        active = c < C;
+                        cur_nm = nxt_nm;
+                        cur_k = nxt_k;
+                        if (c + nW < C) {
+                            nxt_nm = __ldg(nm + c + nW);
+                            nxt_k = USE_K ? (int)__ldg(fstate + c + nW) : 0;
+                        }
+                    }
+                }
+            }
+            if (!__any_sync(0xffffffffu, progress)) __nanosleep(64);      // every ring is full: yield the issue slots
         }
-        row_end(c);
-        c = cn;
-        qn = qn2;
-        qm = qm2;
+        return;
+    }
+
+    // ---------------------------------------------------------------- consumer warps
+    int2* queue = queues + warp * QS;
+    const unsigned lt = (1u << lane) - 1u;
+    int qhead = 0, qtail = 0, it = 0;
+    for (int64_t c = (int64_t)blockIdx.x * NCW + warp; c < C; c += nW) {
+        for (int s = 0; s < nseg; ++s, ++it) {
+            const int d = it % D;
+            uint64_t* fullb = bars + 2 * (warp * D + d);
+            mbar_wait(fullb, (it / D) & 1);
+            const int4 ds = descs[warp * D + d];
+            const int k = ds.x, n = ds.y & 0xffff, m = (ds.y >> 16) & 0xffff;
+            const unsigned char* st = rings + (size_t)(warp * D + d) * G::kStageBytes;
+            if (USE_K && k == 3) {
+                const int u1 = (s + 1) * SEG < U ? (s + 1) * SEG : U;
+                full(c, n, m, s * SEG, u1);
+            } else {
+#pragma unroll
+                for (int j = 0; j < SEG / 64; ++j) {
+                    const int u0 = s * SEG + 64 * j;
+                    if (u0 < U) {                                     // warp-uniform
+                        double2 p2[NPL];
+#pragma unroll
+                        for (int i = 0; i < NPL; ++i)
+                            p2[i] = *reinterpret_cast<const double2*>(st + i * SEG * 8 + (64 * j + 2 * lane) * 8);
+                        const uint32_t sn2 = *reinterpret_cast<const unsigned short*>(st + NPL * SEG * 8 + 64 * j + 2 * lane);
+                        const uint32_t sm2 =
+                            *reinterpret_cast<const unsigned short*>(st + NPL * SEG * 8 + SEG + 64 * j + 2 * lane);
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int sn = (sn2 >> (8 * e)) & 0xff;
+                            const int sm = (sm2 >> (8 * e)) & 0xff;
+                            const int o = (u0 + 2 * lane + e < U) ? (sn | sm) : kStateDead;   // stale bytes past the copy
+                            const bool on = o < 2;
+                            const bool mixed = (o & 6) == 2;          // a region is not peaked (and no padding)
+                            const int l = on ? (sn == sm ? sn : 2) : 0;
+                            double pv[NPL];
+#pragma unroll
+                            for (int i = 0; i < NPL; ++i) pv[i] = e ? p2[i].y : p2[i].x;
+                            if (__any_sync(0xffffffffu, on)) live(pv, l, on);
+                            const unsigned bal = __ballot_sync(0xffffffffu, mixed);
+                            if (bal) {
+                                if (mixed)
+                                    queue[(qtail + __popc(bal & lt)) & (QS - 1)] =
+                                        make_int2((int)c | (k << 29), u0 + 2 * lane + e);
+                                qtail += __popc(bal);
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(fullb + 1);                    // stage free for the producer
+            const bool row_done = s == nseg - 1;
+            const int at_least = (row_done && (ROW_DRAIN || c + nW >= C)) ? 1 : 32;
+            while (qtail - qhead >= at_least) {                       // the one deferred() call site
+                const int idx = qhead + lane;
+                const bool ok = idx < qtail;
+                int2 e = make_int2(0, 0);
+                if (ok) e = queue[idx & (QS - 1)];
+                const int64_t ce = e.x & 0x1fffffff;
+                int v = 0;
+                if (ok) v = __ldg(nm + ce);
+                deferred(ce, e.y, v & 0xffff, (v >> 16) & 0xffff, (e.x >> 29) & 3, ok);
+                qhead = (qtail - qhead > 32) ? qhead + 32 : qtail;
+                __syncwarp();
+            }
+            if (row_done) row_end(c);
+        }
     }
 }
 

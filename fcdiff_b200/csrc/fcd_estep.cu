@@ -1,5 +1,6 @@
-// E-step kernels: healthy sufficient statistics, K2 (template posterior q_F),
-// K2b (region-weight tensor W and the Gauss-Seidel sweep for q_R).
+// E-step kernels: healthy sufficient statistics, responsibility planes, peak
+// states, K2 (template posterior q_F), K2b (region-weight tensor W and the
+// Gauss-Seidel sweep for q_R).
 #include "fcd_common.cuh"
 
 namespace fcd {
@@ -14,6 +15,15 @@ __global__ void c_to_nm_kernel(int64_t c0, int64_t C, int32_t* n_out, int32_t* m
         c_to_nm(c0 + i, n, m);
         n_out[i] = n;
         m_out[i] = m;
+    }
+}
+
+__global__ void edge_table_kernel(int64_t c0, int64_t C, int32_t* __restrict__ nm) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < C;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int n, m;
+        c_to_nm(c0 + i, n, m);
+        nm[i] = n | (m << 16);
     }
 }
 
@@ -43,46 +53,68 @@ healthy_stats_kernel(const double* __restrict__ b, int64_t C, int H, int64_t pit
     }
 }
 
-// ------------------------------------------------------------ Gaussian cache
-// Ea / Eb / Tm planes (see fcd_common.cuh) from the patient correlations; the
+// ------------------------------------------------------ responsibility planes
+// P0 / P1 / P2 / L planes (see fcd_common.cuh) from the patient correlations; the
 // only place where exponentials of the data are taken.  Elementwise over the
 // padded [C][pitchU] rows (padding columns are written as zeros).
 __global__ void __launch_bounds__(256)
-gauss_cache_kernel(const double* __restrict__ bt, int64_t C, int U, int64_t pitchU,
-                   const __grid_constant__ ThetaDev th,
-                   double* __restrict__ Ea, double* __restrict__ Eb, double* __restrict__ Tm) {
+resp_cache_kernel(const double* __restrict__ bt, int64_t C, int U, int64_t pitchU,
+                  const __grid_constant__ ThetaDev th,
+                  double* __restrict__ P, int64_t planeStride, double* __restrict__ L) {
     const int64_t total = C * pitchU;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
         const int u = (int)(i % pitchU);
-        GaussElem g;
-        g.ea = g.ebc = g.tmax = 0.0;
-        if (u < U) g = gauss_eval(ldg_stream1(bt + i), th);
-        Ea[i] = g.ea;
-        Eb[i] = g.ebc;
-        if (Tm) Tm[i] = g.tmax;
+        Resp r;
+        r.p[0] = r.p[1] = r.p[2] = r.L = 0.0;
+        if (u < U) r = resp_eval(ldg_stream1(bt + i), th);
+        P[i] = r.p[0];
+        P[planeStride + i] = r.p[1];
+        P[2 * planeStride + i] = r.p[2];
+        if (L) L[i] = r.L;
+    }
+}
+
+// ------------------------------------------------------------- peak states
+// fstate[c] / rstate[n][u] of fcd_common.cuh from the probabilities.
+__global__ void __launch_bounds__(256)
+peak_states_F_kernel(const double* __restrict__ qF, int64_t C, uint8_t* __restrict__ fstate) {
+    for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < C;
+         c += (int64_t)gridDim.x * blockDim.x) {
+        const double q0 = qF[c * 3], q1 = qF[c * 3 + 1], q2 = qF[c * 3 + 2];
+        int s = kStateMixedF;
+        if (q0 == 1.0 && q1 <= kPeakTau && q2 <= kPeakTau) s = 0;
+        else if (q1 == 1.0 && q0 <= kPeakTau && q2 <= kPeakTau) s = 1;
+        else if (q2 == 1.0 && q0 <= kPeakTau && q1 <= kPeakTau) s = 2;
+        fstate[c] = (uint8_t)s;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+peak_states_R_kernel(const double* __restrict__ qR, int N, int U, int64_t pitchS, uint8_t* __restrict__ rstate) {
+    const int64_t total = (int64_t)N * pitchS;
+    const double2* q2 = reinterpret_cast<const double2*>(qR);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = i / pitchS;
+        const int u = (int)(i - n * pitchS);
+        int s = kStateDead;
+        if (u < U) {
+            const double2 q = q2[n * U + u];
+            s = kStateMixedR;
+            if (q.x == 1.0 && q.y <= kPeakTau) s = 0;
+            else if (q.y == 1.0 && q.x <= kPeakTau) s = 1;
+        }
+        rstate[i] = (uint8_t)s;
     }
 }
 
 // ------------------------------------------------------------------- K2
 // lqF[c,k] = log gamma_k + healthy_k(S1,S2) + sum_u sum_l w_l log M_kl(bt[c,u])
 //            - logsumexp_k                                 (fcdiff/fit.py:157-174)
-// The per-(c,u) term (tmax - log sqrt(2 pi)) * sum_l w_l is common to the three
-// states k and cancels in the normalisation, so it is never formed.
-template <bool FAST>
-__device__ __forceinline__ void k2_elem(double ea, double ebc, double2 qn, double2 qm, const ThetaDev& th,
-                                        const double* s_tab, double (&acc)[3]) {
-    double w[3];
-    pair_weights(qn, qm, w);
-    const ElemM r = elem_from_cache(ea, ebc, th);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        double a = acc[k];
-#pragma unroll
-        for (int l = 0; l < 3; ++l) a = fma(w[l], fast_log<FAST>(elem_Mp(r, th, k, l), s_tab), a);
-        acc[k] = a;
-    }
-}
+// The per-(c,u) term L * sum_l w_l is common to the three states k and cancels in
+// the normalisation, so it is never formed.  T1: both regions of the element
+// peaked -> the three logs of l*; deferred: all nine with the real pair weights.
 
 // lane 0 of the warp that owns edge c: log gamma + healthy quadratic + A, then
 // scipy.special.logsumexp: a_max + log(sum exp(a - a_max))           (fit.py:165-174)
@@ -103,59 +135,56 @@ __device__ __forceinline__ void k2_finish(int64_t c, const double (&A)[3], doubl
     }
 }
 
-template <bool VEC2, bool FAST>
-__global__ void __launch_bounds__(kEdgeThreads)
+constexpr int kK2Seg = 128;
+
+template <bool FAST>
+__global__ void __launch_bounds__(kStreamThreads, 1)
 estep_qF_kernel(const double* __restrict__ S1, const double* __restrict__ S2,
-                const double* __restrict__ Ea, const double* __restrict__ Eb,
+                const double* __restrict__ P, int64_t planeStride,
                 int64_t C, int U, int64_t pitchU,
-                const double* __restrict__ qR, int N, int64_t c0,
-                const __grid_constant__ ThetaDev th, const double* __restrict__ g_tab,
+                const double* __restrict__ qR, const uint8_t* __restrict__ rstate, int64_t pitchS,
+                const int32_t* __restrict__ nm,
+                const __grid_constant__ ThetaDev th, const __grid_constant__ LogTabWindow tab, int depth,
                 double* __restrict__ lqF, double* __restrict__ qF) {
-    extern __shared__ double s_tab[];               // kLogTabBytes when FAST, unused otherwise
-    load_log_table<FAST>(g_tab, s_tab);
+    extern __shared__ __align__(128) double s_dyn[];
+    const double* s_tab = load_log_table<FAST>(tab, s_dyn);
+    unsigned char* s_stream = reinterpret_cast<unsigned char*>(s_dyn + (FAST ? ((tab.n + 1) & ~1) : 0));
     const int lane = threadIdx.x & 31;
+    const double2* qR2 = reinterpret_cast<const double2*>(qR);
     double acc[3] = {0.0, 0.0, 0.0};
+    auto live = [&](const double (&pv)[3], int l, bool on) {
+        const double a = sel3(l, th.al), b = sel3(l, th.bl);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double lg = fast_log<FAST>(fma(b, pv[k], a), s_tab);
+            acc[k] += on ? lg : 0.0;
+        }
+    };
+    auto deferred = [&](int64_t c, int u, int n, int m, int, bool ok) {
+        double w[3] = {0.0, 0.0, 0.0};
+        double p[3] = {0.0, 0.0, 0.0};
+        if (ok) {
+            pair_weights(__ldg(qR2 + (int64_t)n * U + u), __ldg(qR2 + (int64_t)m * U + u), w);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) p[k] = ldg_stream1(P + k * planeStride + c * pitchU + u);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            double a = acc[k];
+#pragma unroll
+            for (int l = 0; l < 3; ++l) a = fma(w[l], fast_log<FAST>(mix_rel(th, l, p[k]), s_tab), a);
+            acc[k] = a;
+        }
+    };
     auto row_end = [&](int64_t c) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) acc[k] = warp_sum(acc[k]);
         if (lane == 0) k2_finish(c, acc, S1[c], S2[c], th, lqF, qF);
         acc[0] = acc[1] = acc[2] = 0.0;
     };
-    if (VEC2) {
-        walk_rows<false>(Ea, Eb, nullptr, C, U, pitchU, qR, c0,
-                         [&](double ea, double ebc, double, double2 qn, double2 qm) {
-                             k2_elem<FAST>(ea, ebc, qn, qm, th, s_tab, acc);
-                         },
-                         row_end);
-    } else {
-        const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-        const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-        const double2* qR2 = reinterpret_cast<const double2*>(qR);
-        for (int64_t c = warp0; c < C; c += nwarps) {
-            int n, m;
-            c_to_nm(c0 + c, n, m);
-            const double2* qn = qR2 + (int64_t)n * U;
-            const double2* qm = qR2 + (int64_t)m * U;
-            for (int u = lane; u < U; u += 32)
-                k2_elem<FAST>(ldg_stream1(Ea + c * pitchU + u), ldg_stream1(Eb + c * pitchU + u),
-                              __ldg(qn + u), __ldg(qm + u), th, s_tab, acc);
-            row_end(c);
-        }
-    }
-}
-
-// K2 from per-edge sums A[c][k] = sum_u sum_l w_l log Mp_kl that a K3b pass has
-// already produced with the same q_R and (eta, epsilon): no pass over the data.
-__global__ void __launch_bounds__(256)
-estep_qF_finish_kernel(const double* __restrict__ S1, const double* __restrict__ S2,
-                       const double* __restrict__ A, int64_t C,
-                       const __grid_constant__ ThetaDev th,
-                       double* __restrict__ lqF, double* __restrict__ qF) {
-    for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < C;
-         c += (int64_t)gridDim.x * blockDim.x) {
-        const double a[3] = {A[c * 3], A[c * 3 + 1], A[c * 3 + 2]};
-        k2_finish(c, a, S1[c], S2[c], th, lqF, qF);
-    }
+    stream_tiered<3, kK2Seg, kStreamWarps, true, false>(P, planeStride, C, U, pitchU, nullptr, rstate, pitchS, nm,
+                                                        s_stream, depth, live, deferred,
+                                                        [](int64_t, int, int, int, int) {}, row_end);
 }
 
 // ------------------------------------------------------ patient-major copy
@@ -184,18 +213,20 @@ transpose_patients_kernel(const double* __restrict__ bt, int64_t C, int U, int64
 }
 
 // ------------------------------------------------------------------- K2b/W
-// WT[u][c][l] = sum_k qF[c,k] log Mp_kl(u, c) from the patient-major cache planes.
-// The omitted per-(c,u) constant (tmax - log sqrt(2 pi)) sum_k qF[c,k] is the
-// same for l = 0, 1, 2 and enters both states of fcdiff/fit.py:190,194 multiplied
-// by (q_R[m,u,0] + q_R[m,u,1]), so it cancels at fit.py:196.
+// WT[u][c][l] = sum_k qF[c,k] log(a_l + b_l p_k(c,u)) from the patient-major
+// responsibility planes PT[k][u][c].  The omitted per-(c,u) constant L sum_k qF[c,k]
+// is the same for l = 0, 1, 2 and enters both states of fcdiff/fit.py:190,194
+// multiplied by (q_R[m,u,0] + q_R[m,u,1]), so it cancels at fit.py:196.
+// Edges whose q_F is peaked (fstate < 3) need the plane of k* only: 3 logs.
 template <bool FAST>
 __global__ void __launch_bounds__(256)
-region_weights_kernel(const double* __restrict__ EaT, const double* __restrict__ EbT,
+region_weights_kernel(const double* __restrict__ PT, int64_t planeStride,
                       int Ul, int64_t C, int64_t pitchC,
-                      const double* __restrict__ qF, const __grid_constant__ ThetaDev th,
-                      const double* __restrict__ g_tab, double* __restrict__ WT) {
-    extern __shared__ double s_tab[];               // kLogTabBytes when FAST, unused otherwise
-    load_log_table<FAST>(g_tab, s_tab);
+                      const double* __restrict__ qF, const uint8_t* __restrict__ fstate,
+                      const __grid_constant__ ThetaDev th, const __grid_constant__ LogTabWindow tab,
+                      double* __restrict__ WT) {
+    extern __shared__ __align__(16) double s_dyn[];
+    const double* s_tab = load_log_table<FAST>(tab, s_dyn);
     // persistent CTAs over (patient, 1024-edge tile) work items: no wave tail, one
     // table load per CTA
     const int64_t tiles_per_row = (C + 1023) / 1024;
@@ -203,32 +234,41 @@ region_weights_kernel(const double* __restrict__ EaT, const double* __restrict__
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int u = (int)(t / tiles_per_row);
         const int64_t cbase = (t - (int64_t)u * tiles_per_row) * 1024;
-        const double* ra = EaT + (int64_t)u * pitchC;
-        const double* rb = EbT + (int64_t)u * pitchC;
+        const double* row = PT + (int64_t)u * pitchC;
         double* out = WT + (int64_t)u * C * 3;
-        double ea[4], eb[4];
+        double pk[4];
+        int ks[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {                 // issue the tile's loads first
             const int64_t c = cbase + threadIdx.x + 256 * j;
-            ea[j] = eb[j] = 0.0;
+            pk[j] = 0.0;
+            ks[j] = -1;
             if (c < C) {
-                ea[j] = ldg_stream1(ra + c);
-                eb[j] = ldg_stream1(rb + c);
+                ks[j] = __ldg(fstate + c);
+                if (ks[j] < 3) pk[j] = ldg_stream1(row + ks[j] * planeStride + c);
             }
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int64_t c = cbase + threadIdx.x + 256 * j;
-            if (c >= C) continue;
-            const ElemM r = elem_from_cache(ea[j], eb[j], th);
-            const double q0 = __ldg(qF + c * 3), q1 = __ldg(qF + c * 3 + 1), q2 = __ldg(qF + c * 3 + 2);
+            if (ks[j] < 0) continue;
+            double w[3];
+            if (ks[j] < 3) {
 #pragma unroll
-            for (int l = 0; l < 3; ++l) {
-                double w = q0 * fast_log<FAST>(elem_Mp(r, th, 0, l), s_tab);
-                w = fma(q1, fast_log<FAST>(elem_Mp(r, th, 1, l), s_tab), w);
-                w = fma(q2, fast_log<FAST>(elem_Mp(r, th, 2, l), s_tab), w);
-                out[c * 3 + l] = w;
+                for (int l = 0; l < 3; ++l) w[l] = fast_log<FAST>(mix_rel(th, l, pk[j]), s_tab);
+            } else {
+                const double q[3] = {__ldg(qF + c * 3), __ldg(qF + c * 3 + 1), __ldg(qF + c * 3 + 2)};
+                w[0] = w[1] = w[2] = 0.0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const double p = ldg_stream1(row + k * planeStride + c);
+#pragma unroll
+                    for (int l = 0; l < 3; ++l) w[l] = fma(q[k], fast_log<FAST>(mix_rel(th, l, p), s_tab), w[l]);
+                }
             }
+            out[c * 3] = w[0];
+            out[c * 3 + 1] = w[1];
+            out[c * 3 + 2] = w[2];
         }
     }
 }
@@ -357,6 +397,14 @@ int fcd_c_to_nm(int64_t c0, int64_t C, int32_t* n_out, int32_t* m_out, void* str
     return check_launch("fcd_c_to_nm");
 }
 
+int fcd_edge_table(int64_t c0, int64_t C, int32_t* nm, void* stream) {
+    FCD_REQUIRE(C >= 0 && c0 >= 0 && (C == 0 || nm != nullptr), "fcd_edge_table: bad arguments");
+    FCD_REQUIRE(c0 + C <= (int64_t)65535 * 65534 / 2, "fcd_edge_table: more than 65535 regions");
+    if (C == 0) return 0;
+    edge_table_kernel<<<grid_for_rows(C, 256, 8), 256, 0, (cudaStream_t)stream>>>(c0, C, nm);
+    return check_launch("fcd_edge_table");
+}
+
 int fcd_healthy_stats(const double* b, int64_t C, int32_t H, int64_t pitchH,
                       double* S1, double* S2, void* stream) {
     FCD_REQUIRE(C >= 0 && H >= 1 && pitchH >= H, "fcd_healthy_stats: bad shape C=%lld H=%d pitch=%lld",
@@ -367,54 +415,64 @@ int fcd_healthy_stats(const double* b, int64_t C, int32_t H, int64_t pitchH,
     return check_launch("fcd_healthy_stats");
 }
 
-int fcd_gauss_cache(const double* bt, int64_t C, int32_t U, int64_t pitchU,
-                    const fcd_theta* theta_host, double* Ea, double* Eb, double* Tm, void* stream) {
-    FCD_REQUIRE(theta_host != nullptr && bt != nullptr && Ea != nullptr && Eb != nullptr,
-                "fcd_gauss_cache: NULL argument");
-    FCD_REQUIRE(C >= 0 && U >= 1 && pitchU >= U, "fcd_gauss_cache: bad shape");
+int fcd_resp_cache(const double* bt, int64_t C, int32_t U, int64_t pitchU,
+                   const fcd_theta* theta_host, double* P, int64_t planeStride, double* L, void* stream) {
+    FCD_REQUIRE(theta_host != nullptr && bt != nullptr && P != nullptr, "fcd_resp_cache: NULL argument");
+    FCD_REQUIRE(C >= 0 && U >= 1 && pitchU >= U && planeStride >= C * pitchU, "fcd_resp_cache: bad shape");
     if (C == 0) return 0;
     const ThetaDev th = make_theta_dev(*theta_host, 0);
-    gauss_cache_kernel<<<grid_for_rows(C * pitchU, 256, 16), 256, 0, (cudaStream_t)stream>>>(
-        bt, C, U, pitchU, th, Ea, Eb, Tm);
-    return check_launch("fcd_gauss_cache");
+    resp_cache_kernel<<<grid_for_rows(C * pitchU, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+        bt, C, U, pitchU, th, P, planeStride, L);
+    return check_launch("fcd_resp_cache");
+}
+
+int fcd_peak_states_F(const double* qF, int64_t C, uint8_t* fstate, void* stream) {
+    FCD_REQUIRE(C >= 0 && (C == 0 || (qF != nullptr && fstate != nullptr)), "fcd_peak_states_F: bad arguments");
+    if (C == 0) return 0;
+    peak_states_F_kernel<<<grid_for_rows(C, 256, 8), 256, 0, (cudaStream_t)stream>>>(qF, C, fstate);
+    return check_launch("fcd_peak_states_F");
+}
+
+int fcd_peak_states_R(const double* qR, int32_t N, int32_t U, int64_t pitchS, uint8_t* rstate, void* stream) {
+    FCD_REQUIRE(N >= 1 && U >= 1 && pitchS >= U && qR != nullptr && rstate != nullptr,
+                "fcd_peak_states_R: bad arguments");
+    peak_states_R_kernel<<<grid_for_rows((int64_t)N * pitchS, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        qR, N, U, pitchS, rstate);
+    return check_launch("fcd_peak_states_R");
 }
 
 int fcd_estep_qF(const double* S1, const double* S2, int32_t H,
-                 const double* Ea, const double* Eb, int64_t C, int32_t U, int64_t pitchU,
-                 const double* qR, int32_t N, int64_t c0,
+                 const double* P, int64_t planeStride, int64_t C, int32_t U, int64_t pitchU,
+                 const double* qR, const uint8_t* rstate, int64_t pitchS, int32_t N, const int32_t* nm,
                  const fcd_theta* theta_host, double* lqF, double* qF, void* stream) {
-    FCD_REQUIRE(theta_host != nullptr, "fcd_estep_qF: theta is NULL");
-    FCD_REQUIRE(C >= 0 && U >= 1 && pitchU >= U && N >= 2, "fcd_estep_qF: bad shape");
-    FCD_REQUIRE(c0 >= 0 && c0 + C <= (int64_t)N * (N - 1) / 2, "fcd_estep_qF: edge shard [%lld, %lld) outside N=%d",
-                (long long)c0, (long long)(c0 + C), N);
+    FCD_REQUIRE(theta_host != nullptr && P != nullptr && qR != nullptr && rstate != nullptr && nm != nullptr &&
+                lqF != nullptr, "fcd_estep_qF: NULL argument");
+    FCD_REQUIRE(C >= 0 && C < (1 << 29) && U >= 1 && pitchU >= U && pitchS >= U && N >= 2 && N < 65536,
+                "fcd_estep_qF: bad shape");
+    FCD_REQUIRE(((reinterpret_cast<uintptr_t>(P) & 15) == 0) && pitchU % 2 == 0 && planeStride % 2 == 0 &&
+                pitchS % 16 == 0, "fcd_estep_qF: planes must be 16-byte aligned with even pitches (pitchS % 16)");
     if (C == 0) return 0;
     const ThetaDev th = make_theta_dev(*theta_host, H);
-    const double* tab = log_table((cudaStream_t)stream);
-    FCD_REQUIRE(tab != nullptr, "fcd_estep_qF: log table initialisation failed");
-    const int grid = grid_for_rows(C, kEdgeThreads / 32, 2);
-    const bool vec2 = (pitchU % 2 == 0) && (((reinterpret_cast<uintptr_t>(Ea) | reinterpret_cast<uintptr_t>(Eb)) & 15) == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    LogTabWindow tab;
+    FCD_REQUIRE(log_table_window(th.epsl, th.al, st, tab), "fcd_estep_qF: log table initialisation failed");
     const bool fast = log_table_covers(th.epsl, th.al);
-#define FCD_K2(V, F)                                                                              \
+    const size_t tbytes = fast ? (size_t)((tab.n + 1) & ~1) * sizeof(double) : 0;
+    const int depth = stream_depth<3, kK2Seg>(tbytes);
+    FCD_REQUIRE(depth >= 2, "fcd_estep_qF: shared memory budget exceeded");
+    const size_t smem = tbytes + StreamGeom<3, kK2Seg>::bytes(kStreamWarps, depth);
+    int64_t grid = (C + kStreamWarps - 1) / kStreamWarps;
+    if (grid > sm_count()) grid = sm_count();                       // one persistent CTA per SM
+#define FCD_K2(F)                                                                                 \
     do {                                                                                          \
-        cudaFuncSetAttribute(estep_qF_kernel<V, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                             (int)kLogTabBytes);                                                  \
-        estep_qF_kernel<V, F><<<grid, kEdgeThreads, (F) ? kLogTabBytes : 0, (cudaStream_t)stream>>>( \
-            S1, S2, Ea, Eb, C, U, pitchU, qR, N, c0, th, tab, lqF, qF);                            \
+        cudaFuncSetAttribute(estep_qF_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                             (int)kSmemBudget);                                                   \
+        estep_qF_kernel<F><<<(unsigned)grid, kStreamThreads, smem, st>>>(                         \
+            S1, S2, P, planeStride, C, U, pitchU, qR, rstate, pitchS, nm, th, tab, depth, lqF, qF); \
     } while (0)
-    if (vec2) { if (fast) FCD_K2(true, true); else FCD_K2(true, false); }
-    else      { if (fast) FCD_K2(false, true); else FCD_K2(false, false); }
+    if (fast) FCD_K2(true); else FCD_K2(false);
 #undef FCD_K2
     return check_launch("fcd_estep_qF");
-}
-
-int fcd_estep_qF_finish(const double* S1, const double* S2, int32_t H, const double* A, int64_t C,
-                        const fcd_theta* theta_host, double* lqF, double* qF, void* stream) {
-    FCD_REQUIRE(theta_host != nullptr && A != nullptr && lqF != nullptr, "fcd_estep_qF_finish: NULL argument");
-    FCD_REQUIRE(C >= 0 && H >= 1, "fcd_estep_qF_finish: bad shape");
-    if (C == 0) return 0;
-    const ThetaDev th = make_theta_dev(*theta_host, H);
-    estep_qF_finish_kernel<<<grid_for_rows(C, 256, 8), 256, 0, (cudaStream_t)stream>>>(S1, S2, A, C, th, lqF, qF);
-    return check_launch("fcd_estep_qF_finish");
 }
 
 int fcd_transpose_patients(const double* bt, int64_t C, int32_t U, int64_t pitchU,
@@ -427,25 +485,32 @@ int fcd_transpose_patients(const double* bt, int64_t C, int32_t U, int64_t pitch
     return check_launch("fcd_transpose_patients");
 }
 
-int fcd_region_weights(const double* EaT, const double* EbT, int32_t Ul, int64_t C, int64_t pitchC,
-                       const double* qF, const fcd_theta* theta_host, double* WT, void* stream) {
-    FCD_REQUIRE(theta_host != nullptr, "fcd_region_weights: theta is NULL");
+int fcd_region_weights(const double* PT, int64_t planeStride, int32_t Ul, int64_t C, int64_t pitchC,
+                       const double* qF, const uint8_t* fstate, const fcd_theta* theta_host,
+                       double* WT, void* stream) {
+    FCD_REQUIRE(theta_host != nullptr && fstate != nullptr, "fcd_region_weights: NULL argument");
     FCD_REQUIRE(C >= 0 && Ul >= 0 && pitchC >= C, "fcd_region_weights: bad shape");
     if (C == 0 || Ul == 0) return 0;
     const ThetaDev th = make_theta_dev(*theta_host, 0);
-    const double* tab = log_table((cudaStream_t)stream);
-    FCD_REQUIRE(tab != nullptr, "fcd_region_weights: log table initialisation failed");
+    cudaStream_t st = (cudaStream_t)stream;
+    LogTabWindow tab;
+    FCD_REQUIRE(log_table_window(th.epsl, th.al, st, tab), "fcd_region_weights: log table initialisation failed");
     int64_t ntiles = ((C + 1023) / 1024) * (int64_t)Ul;
-    int64_t grid = (int64_t)sm_count() * 2;            // 2 CTAs / SM resident (86 KB table each)
-    if (grid > ntiles) grid = ntiles;
     if (log_table_covers(th.epsl, th.al)) {
+        int per_sm = (int)((200 * 1024) / (tab.bytes() + 1024));
+        if (per_sm > 8) per_sm = 8;
+        if (per_sm < 1) per_sm = 1;
+        int64_t grid = (int64_t)sm_count() * per_sm;
+        if (grid > ntiles) grid = ntiles;
         cudaFuncSetAttribute(region_weights_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)kLogTabBytes);
-        region_weights_kernel<true><<<(unsigned)grid, 256, kLogTabBytes, (cudaStream_t)stream>>>(
-            EaT, EbT, Ul, C, pitchC, qF, th, tab, WT);
+        region_weights_kernel<true><<<(unsigned)grid, 256, tab.bytes(), st>>>(
+            PT, planeStride, Ul, C, pitchC, qF, fstate, th, tab, WT);
     } else {
-        region_weights_kernel<false><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
-            EaT, EbT, Ul, C, pitchC, qF, th, tab, WT);
+        int64_t grid = (int64_t)sm_count() * 4;
+        if (grid > ntiles) grid = ntiles;
+        region_weights_kernel<false><<<(unsigned)grid, 256, 0, st>>>(
+            PT, planeStride, Ul, C, pitchC, qF, fstate, th, tab, WT);
     }
     return check_launch("fcd_region_weights");
 }

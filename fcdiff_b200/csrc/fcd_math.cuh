@@ -38,8 +38,19 @@ constexpr size_t kLogTabBytes = (size_t)kLogTabSize * sizeof(double);      // dy
 
 // Host: device address of the table for the current device (built on first use).
 const double* log_table(cudaStream_t st);
-// True when every mixture weight eps_l e_k + a_l o_k (max_k e_k = 1) lies inside the table's range.
+// True when every mixture weight a_l + b_l p (0 <= p <= 1) lies inside the table's range.
 bool log_table_covers(const double epsl[3], const double al[3]);
+
+// The slots [lo, lo + n) of the table that arguments in [min_l min(a_l, eps_l),
+// max_l max(a_l, eps_l)] can index: only this window is staged in shared memory
+// (typically 8 of the 21 binades, 32 KB instead of 86 KB -> more CTAs per SM).
+struct LogTabWindow {
+    const double* g;      // device table (all slots)
+    int lo;
+    int n;
+    size_t bytes() const { return (size_t)n * sizeof(double); }
+};
+bool log_table_window(const double epsl[3], const double al[3], cudaStream_t st, LogTabWindow& w);
 
 #ifdef __CUDACC__
 
@@ -48,11 +59,14 @@ __device__ __forceinline__ double log_table_r8(int i) {
     return __hiloint2double((i + kLogTabBase) << (20 - kLogTabBits), 0);
 }
 
+// Stages the window in shared memory; returns the pointer to index with the
+// FULL-table slot number (s_tab - lo: only slots inside the window are touched).
 template <bool FAST>
-__device__ __forceinline__ void load_log_table(const double* __restrict__ g_tab, double* s_tab) {
+__device__ __forceinline__ const double* load_log_table(const LogTabWindow& w, double* s_tab) {
     if (FAST)
-        for (int i = threadIdx.x; i < kLogTabSize; i += blockDim.x) s_tab[i] = g_tab[i];
+        for (int i = threadIdx.x; i < w.n; i += blockDim.x) s_tab[i] = w.g[w.lo + i];
     __syncthreads();
+    return s_tab - w.lo;
 }
 
 struct LogParts {
@@ -86,6 +100,16 @@ __device__ __forceinline__ double fast_log(double y, const double* s_tab) {
     if (!FAST) return log(y);
     const LogParts p = log_reduce(y);
     return s_tab[p.idx] + log1p_small(p.u);
+}
+
+// 1 / y alone (same reduction, no table access)
+template <bool FAST>
+__device__ __forceinline__ double fast_rcp(double y) {
+    if (!FAST) return 1.0 / y;
+    const LogParts p = log_reduce(y);
+    double g = fma(p.u, p.u, 1.0 - p.u);             // 1 - u + u^2
+    g = fma(-p.u * p.u, p.u, g);                     // - u^3          (u^4 <= 9.1e-13 relative)
+    return p.r8 * g;
 }
 
 template <bool FAST>

@@ -28,116 +28,214 @@ mstep_stats_kernel(const double* __restrict__ lqF, int64_t C,
 }
 
 // ------------------------------------------------------------------- K3b
-// One pass over the Gaussian-cache planes of the local edge rows.  With
-// A_k(c) = sum_u sum_l w_l log Mp_kl (fit.py:489-511 for the objective) and
-// num_k = e_k - o_k / 2 (fit.py:600-697 for the gradient; the common factor
-// exp(tmax)/sqrt(2 pi) of numerator and mixture cancels):
-//   out[0] = sum_c sum_k qF_k A_k                         (theta-dependent part of E_lM)
-//   out[1] = dE/d eta = -(2 eps - 1) sum_c sum_k qF_k sum_u w_2 num_k / Mp_k2
-//   out[2] = dE/d eps = -sum_c sum_k qF_k sum_u sum_l s_l w_l num_k / Mp_kl,  s = (-1, 1, 2 eta - 1)
-//   out[3] = sum_c (sum_k qF_k) sum_u (sum_l w_l)(tmax - log sqrt(2 pi))      (CONST; theta-free part)
-// E_lM = out[0] + out[3].  When Aout != NULL the per-edge sums A_k(c) are also
-// written: they are exactly what the next K2 and the energy need (no extra pass).
+// Objective and analytic gradient of the (eta, epsilon) sub-problem from the
+// responsibility planes of the local edge rows (fit.py:489-511 for the
+// objective, fit.py:600-697 for the gradient; the total density cancels in the
+// ratio num / M):
+//   out[0] = sum_c sum_k qF_k sum_u sum_l w_l log(a_l + b_l p_k)   (theta-dependent part of E_lM;
+//            E_lM = out[0] + the theta-free sum of elm_const_kernel)
+//   out[1] = dE/d eta = -(2 eps - 1) sum qF_k w_2 num_k / (a_2 + b_2 p_k)
+//   out[2] = dE/d eps = -sum qF_k s_l w_l num_k / (a_l + b_l p_k),  s = (-1, 1, 2 eta - 1)
+// with num_k = (3 p_k - 1)/2.  Tiers T1 / T2 / T3 as described in fcd_common.cuh.
+struct ElmAcc {
+    double obj, ge, gh;       // objective, sum s_l w_l d_l, sum w_2 d_2
+};
+
+constexpr int kElmSeg = 128;
+
 template <bool GRAD, bool FAST>
-__device__ __forceinline__ void k3_elem(double ea, double ebc, double2 qn, double2 qm, double (&w)[3],
-                                        const ThetaDev& th, double s2, const double* s_tab,
-                                        double (&A)[3], double (&G)[3], double (&Hh)[3]) {
-    pair_weights(qn, qm, w);
-    const ElemM r = elem_from_cache(ea, ebc, th);
-    const double sw2 = s2 * w[2];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        double a = A[k], ds = 0.0, hs = 0.0;
+__global__ void __launch_bounds__(kStreamThreads, 1)
+elm_kernel(const double* __restrict__ P, int64_t planeStride, int64_t C, int U, int64_t pitchU,
+           const double* __restrict__ qF, const uint8_t* __restrict__ fstate,
+           const double* __restrict__ qR, const uint8_t* __restrict__ rstate, int64_t pitchS,
+           const int32_t* __restrict__ nm, const __grid_constant__ ThetaDev th,
+           const __grid_constant__ LogTabWindow tab, int depth,
+           double* __restrict__ out, double* __restrict__ ws) {
+    extern __shared__ __align__(128) double s_dyn[];
+    const double* s_tab = load_log_table<FAST>(tab, s_dyn);
+    unsigned char* s_stream = reinterpret_cast<unsigned char*>(s_dyn + (FAST ? ((tab.n + 1) & ~1) : 0));
+    const double sl[3] = {-1.0, 1.0, 2.0 * th.eta - 1.0};
+    const double2* qR2 = reinterpret_cast<const double2*>(qR);
+    ElmAcc acc = {0.0, 0.0, 0.0};
+
+    auto live = [&](const double (&pv)[1], int l, bool on) {
+        const double M = fma(sel3(l, th.bl), pv[0], sel3(l, th.al));
+        if (GRAD) {
+            double rcp;
+            const double lg = fast_log_rcp<FAST>(M, s_tab, rcp);
+            const double d = mix_num(pv[0]) * rcp;
+            acc.obj += on ? lg : 0.0;
+            acc.ge = fma(on ? sel3(l, sl) : 0.0, d, acc.ge);
+            acc.gh += (on && l == 2) ? d : 0.0;
+        } else {
+            const double lg = fast_log<FAST>(M, s_tab);
+            acc.obj += on ? lg : 0.0;
+        }
+    };
+    auto deferred = [&](int64_t c, int u, int n, int m, int k, bool ok) {
+        double p = 0.0;
+        double w[3] = {0.0, 0.0, 0.0};
+        if (ok) {
+            p = ldg_stream1(P + k * planeStride + c * pitchU + u);
+            pair_weights(__ldg(qR2 + (int64_t)n * U + u), __ldg(qR2 + (int64_t)m * U + u), w);
+        }
+        const double num = mix_num(p);
 #pragma unroll
         for (int l = 0; l < 3; ++l) {
-            const double M = elem_Mp(r, th, k, l);
+            const double M = mix_rel(th, l, p);
             if (GRAD) {
                 double rcp;
-                a = fma(w[l], fast_log_rcp<FAST>(M, s_tab, rcp), a);
-                if (l == 0) ds = -w[0] * rcp;
-                else if (l == 1) ds = fma(w[1], rcp, ds);
-                else {
-                    ds = fma(sw2, rcp, ds);
-                    hs = w[2] * rcp;
-                }
+                acc.obj = fma(w[l], fast_log_rcp<FAST>(M, s_tab, rcp), acc.obj);
+                const double d = w[l] * (num * rcp);
+                acc.ge = fma(sl[l], d, acc.ge);
+                if (l == 2) acc.gh += d;
             } else {
-                a = fma(w[l], fast_log<FAST>(M, s_tab), a);
+                acc.obj = fma(w[l], fast_log<FAST>(M, s_tab), acc.obj);
             }
         }
-        A[k] = a;
-        if (GRAD) {
-            const double num = elem_num(r, k);
-            G[k] = fma(num, ds, G[k]);
-            Hh[k] = fma(num, hs, Hh[k]);
+    };
+    auto full = [&](int64_t c, int n, int m, int u0, int u1) {
+        const double qf[3] = {__ldg(qF + c * 3), __ldg(qF + c * 3 + 1), __ldg(qF + c * 3 + 2)};
+        for (int u = u0 + (threadIdx.x & 31); u < u1; u += 32) {
+            double w[3];
+            pair_weights(__ldg(qR2 + (int64_t)n * U + u), __ldg(qR2 + (int64_t)m * U + u), w);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double p = ldg_stream1(P + k * planeStride + c * pitchU + u);
+                const double num = mix_num(p);
+#pragma unroll
+                for (int l = 0; l < 3; ++l) {
+                    const double M = mix_rel(th, l, p);
+                    const double qw = qf[k] * w[l];
+                    if (GRAD) {
+                        double rcp;
+                        acc.obj = fma(qw, fast_log_rcp<FAST>(M, s_tab, rcp), acc.obj);
+                        const double d = qw * (num * rcp);
+                        acc.ge = fma(sl[l], d, acc.ge);
+                        if (l == 2) acc.gh += d;
+                    } else {
+                        acc.obj = fma(qw, fast_log<FAST>(M, s_tab), acc.obj);
+                    }
+                }
+            }
         }
-    }
+    };
+    stream_tiered<1, kElmSeg, kStreamWarps, false, true>(P, planeStride, C, U, pitchU, fstate, rstate, pitchS, nm,
+                                                         s_stream, depth, live, deferred, full, [](int64_t) {});
+    double v[3] = {acc.obj, -(2.0 * th.epsilon - 1.0) * acc.gh, -acc.ge};
+    grid_reduce_store<3, kStreamThreads>(v, ws, out);
 }
 
-template <bool GRAD, bool CONST, bool VEC2, bool FAST>
+// Theta-free part of E_lM: out[0] = sum_c (sum_k qF_k) sum_u (sum_l w_l) L[c,u]
+// (sum_l w_l = (q_n0 + q_n1)(q_m0 + q_m1), fit.py:382-406).  One read of the L plane.
+__global__ void __launch_bounds__(kStreamThreads, 1)
+elm_const_kernel(const double* __restrict__ L, int64_t C, int U, int64_t pitchU,
+                 const double* __restrict__ qF, const uint8_t* __restrict__ fstate,
+                 const double* __restrict__ qR, const uint8_t* __restrict__ rstate, int64_t pitchS,
+                 const int32_t* __restrict__ nm, int depth, double* __restrict__ out, double* __restrict__ ws) {
+    extern __shared__ __align__(128) double s_dyn[];
+    const double2* qR2 = reinterpret_cast<const double2*>(qR);
+    double acc = 0.0;
+    auto wsum = [&](int n, int m, int u) {
+        const double2 qn = __ldg(qR2 + (int64_t)n * U + u), qm = __ldg(qR2 + (int64_t)m * U + u);
+        return (qn.x + qn.y) * (qm.x + qm.y);
+    };
+    auto live = [&](const double (&pv)[1], int, bool on) { acc += on ? pv[0] : 0.0; };
+    auto deferred = [&](int64_t c, int u, int n, int m, int, bool ok) {
+        if (ok) acc = fma(wsum(n, m, u), ldg_stream1(L + c * pitchU + u), acc);
+    };
+    auto full = [&](int64_t c, int n, int m, int u0, int u1) {
+        const double qs = __ldg(qF + c * 3) + __ldg(qF + c * 3 + 1) + __ldg(qF + c * 3 + 2);
+        for (int u = u0 + (threadIdx.x & 31); u < u1; u += 32)
+            acc = fma(qs * wsum(n, m, u), ldg_stream1(L + c * pitchU + u), acc);
+    };
+    stream_tiered<1, kElmSeg, kStreamWarps, false, true>(L, 0, C, U, pitchU, fstate, rstate, pitchS, nm,
+                                                         reinterpret_cast<unsigned char*>(s_dyn), depth,
+                                                         live, deferred, full, [](int64_t) {});
+    double v[1] = {acc};
+    grid_reduce_store<1, kStreamThreads>(v, ws, out);
+}
+
+// ------------------------------------------------------------------- K3c
+// Per-state sufficient statistics of the correlations (north_star subsystem 3;
+// SURVEY 8f item 1 -- the reference ships only disabled pieces of a mu / sigma
+// update, fcdiff/fit.py:232-237, 542-597, 709-733).  For the patients, the
+// posterior weight that edge (c,u) is in state j, given q_F, q_R and theta, is
+//   R_j = p_j sum_k qF_k sum_l w_l kappa_jkl / (a_l + b_l p_k),   kappa_jkl = eps_l (j == k) or a_l (j != k)
+//       = p_j ( sum_l a_l Q_l + qF_j sum_l b_l T_jl ),  T_kl = w_l / (a_l + b_l p_k),  Q_l = sum_k qF_k T_kl
+// (sum_j R_j = sum_k qF_k sum_l w_l).  out[0..2] = sum R_j, out[3..5] = sum R_j x,
+// out[6..8] = sum R_j x^2: the weighted Gaussian statistics whose pooled maximiser
+// is the EM (lower-bound) update of mu_j, sigma_j.  Runs once per iteration at
+// most; all nine reciprocals for every element (no tiers).
+template <bool FAST>
 __global__ void __launch_bounds__(kRedThreads, 2)
-elm_kernel(const double* __restrict__ Ea, const double* __restrict__ Eb, const double* __restrict__ Tm,
-           int64_t C, int U, int64_t pitchU,
-           const double* __restrict__ qF, const double* __restrict__ qR, int N, int64_t c0,
-           const __grid_constant__ ThetaDev th, const double* __restrict__ g_tab,
-           double* __restrict__ Aout, double* __restrict__ out, double* __restrict__ ws) {
-    extern __shared__ double s_tab[];               // kLogTabBytes when FAST, unused otherwise
-    load_log_table<FAST>(g_tab, s_tab);
+patient_moments_kernel(const double* __restrict__ P, int64_t planeStride, const double* __restrict__ bt,
+                       int64_t C, int U, int64_t pitchU,
+                       const double* __restrict__ qF, const double* __restrict__ qR,
+                       const int32_t* __restrict__ nm, const __grid_constant__ ThetaDev th,
+                       double* __restrict__ out, double* __restrict__ ws) {
+    double acc[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     const int lane = threadIdx.x & 31;
-    const double s2 = 2.0 * th.eta - 1.0;
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    double A[3] = {0.0, 0.0, 0.0}, G[3] = {0.0, 0.0, 0.0}, Hh[3] = {0.0, 0.0, 0.0};
-    double cs = 0.0;
-    auto elem = [&](double ea, double ebc, double tm, double2 qn, double2 qm) {
-        double w[3];
-        k3_elem<GRAD, FAST>(ea, ebc, qn, qm, w, th, s2, s_tab, A, G, Hh);
-        if (CONST) cs = fma(w[0] + w[1] + w[2], tm - kHalfLog2Pi, cs);
-    };
-    auto row_end = [&](int64_t c) {
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const double2* qR2 = reinterpret_cast<const double2*>(qR);
+    for (int64_t c = warp0; c < C; c += nwarps) {
+        const int v = __ldg(nm + c);
+        const double2* qn = qR2 + (int64_t)(v & 0xffff) * U;
+        const double2* qm = qR2 + (int64_t)((v >> 16) & 0xffff) * U;
         const double qf[3] = {__ldg(qF + c * 3), __ldg(qF + c * 3 + 1), __ldg(qF + c * 3 + 2)};
-        if (Aout != nullptr) {                        // warp-uniform
+        for (int u = lane; u < U; u += 32) {
+            const int64_t i = c * pitchU + u;
+            const double x = ldg_stream1(bt + i);
+            const double p[3] = {ldg_stream1(P + i), ldg_stream1(P + planeStride + i),
+                                 ldg_stream1(P + 2 * planeStride + i)};
+            double w[3];
+            pair_weights(__ldg(qn + u), __ldg(qm + u), w);
+            double T[3][3], Q[3];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) A[k] = warp_sum(A[k]);
-            if (lane == 0) {
+            for (int l = 0; l < 3; ++l) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) Aout[c * 3 + k] = A[k];
-                acc[0] += fma(qf[0], A[0], fma(qf[1], A[1], qf[2] * A[2]));
+                for (int k = 0; k < 3; ++k) T[k][l] = w[l] * fast_rcp<FAST>(mix_rel(th, l, p[k]));
+                Q[l] = fma(qf[0], T[0][l], fma(qf[1], T[1][l], qf[2] * T[2][l]));
             }
-        } else {
-            acc[0] += fma(qf[0], A[0], fma(qf[1], A[1], qf[2] * A[2]));
-        }
-        if (GRAD) {
-            acc[1] -= fma(qf[0], Hh[0], fma(qf[1], Hh[1], qf[2] * Hh[2]));
-            acc[2] -= fma(qf[0], G[0], fma(qf[1], G[1], qf[2] * G[2]));
-        }
-        if (CONST) acc[3] = fma(qf[0] + qf[1] + qf[2], cs, acc[3]);
+            const double T0 = fma(th.al[0], Q[0], fma(th.al[1], Q[1], th.al[2] * Q[2]));
+            const double x2 = x * x;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) A[k] = G[k] = Hh[k] = 0.0;
-        cs = 0.0;
-    };
-    if (VEC2) {
-        walk_rows<CONST>(Ea, Eb, Tm, C, U, pitchU, qR, c0, elem, row_end);
-    } else {
-        const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-        const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-        const double2* qR2 = reinterpret_cast<const double2*>(qR);
-        for (int64_t c = warp0; c < C; c += nwarps) {
-            int n, m;
-            c_to_nm(c0 + c, n, m);
-            const double2* qn = qR2 + (int64_t)n * U;
-            const double2* qm = qR2 + (int64_t)m * U;
-            for (int u = lane; u < U; u += 32)
-                elem(ldg_stream1(Ea + c * pitchU + u), ldg_stream1(Eb + c * pitchU + u),
-                     CONST ? ldg_stream1(Tm + c * pitchU + u) : 0.0, __ldg(qn + u), __ldg(qm + u));
-            row_end(c);
+            for (int j = 0; j < 3; ++j) {
+                const double Tj = qf[j] * fma(th.bl[0], T[j][0], fma(th.bl[1], T[j][1], th.bl[2] * T[j][2]));
+                const double R = p[j] * (T0 + Tj);
+                acc[j] += R;
+                acc[3 + j] = fma(R, x, acc[3 + j]);
+                acc[6 + j] = fma(R, x2, acc[6 + j]);
+            }
         }
     }
-    if (GRAD) acc[1] *= (2.0 * th.epsilon - 1.0);
-    grid_reduce_store<4, kRedThreads>(acc, ws, out);
+    grid_reduce_store<9, kRedThreads>(acc, ws, out);
+}
+
+// Controls: out[0..2] = H sum_c qF[c,j], out[3..5] = sum_c qF[c,j] S1[c], out[6..8] = sum_c qF[c,j] S2[c].
+__global__ void __launch_bounds__(kRedThreads)
+control_moments_kernel(const double* __restrict__ S1, const double* __restrict__ S2, double H,
+                       const double* __restrict__ qF, int64_t C, double* __restrict__ out,
+                       double* __restrict__ ws) {
+    double acc[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < C;
+         c += (int64_t)gridDim.x * blockDim.x) {
+        const double s1 = S1[c], s2 = S2[c];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const double q = qF[c * 3 + j];
+            acc[j] = fma(H, q, acc[j]);
+            acc[3 + j] = fma(q, s1, acc[3 + j]);
+            acc[6 + j] = fma(q, s2, acc[6 + j]);
+        }
+    }
+    grid_reduce_store<9, kRedThreads>(acc, ws, out);
 }
 
 // ------------------------------------------------------------------- K4
-// The six terms of fcdiff/fit.py:142-155; E_lM (v[3]) is produced by elm_kernel
-// into the workspace scratch just before this kernel and folded in here.
+// The six terms of fcdiff/fit.py:142-155.  E_lM (v[3]) of the local shard comes
+// from the K3b passes (fcd_elm_obj_grad + fcd_elm_const) and is passed in.
 //  v[0] E_lp_F = sum qF log gamma (fit.py:458)   v[1] E_lp_B_g_F (fit.py:472, via S1,S2)
 //  v[2] E_lp_R = sum qR log[1-pi, pi] (fit.py:486)
 //  v[4] E_lq_F = sum qF lqF (fit.py:525)         v[5] E_lq_R = sum qR lqR (fit.py:539)
@@ -145,12 +243,12 @@ __global__ void __launch_bounds__(kRedThreads)
 energy_small_kernel(const double* __restrict__ S1, const double* __restrict__ S2,
                     const double* __restrict__ lqF, const double* __restrict__ qF, int64_t C,
                     const double* __restrict__ lqR, const double* __restrict__ qR, int64_t NU,
-                    const __grid_constant__ ThetaDev th, int elm_known, double elm_value,
+                    const __grid_constant__ ThetaDev th, double elm_value,
                     double* __restrict__ out6, double* __restrict__ ws) {
     double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t nth = (int64_t)gridDim.x * blockDim.x;
-    if (tid == 0) v[3] = elm_known ? elm_value : ws[kWsScratch] + ws[kWsScratch + 3];
+    if (tid == 0) v[3] = elm_value;
     for (int64_t c = tid; c < C; c += nth) {
         const double s1 = S1[c], s2 = S2[c];
 #pragma unroll
@@ -182,35 +280,15 @@ static inline int red_grid(int64_t work_items, int items_per_block) {
     return (int)(need < cap ? need : cap);
 }
 
-static int launch_elm(const double* Ea, const double* Eb, const double* Tm,
-                      int64_t C, int32_t U, int64_t pitchU,
-                      const double* qF, const double* qR, int32_t N, int64_t c0,
-                      const ThetaDev& th, bool grad, double* Aout, double* out4, double* ws, cudaStream_t st) {
-    const double* tab = log_table(st);
-    FCD_REQUIRE(tab != nullptr, "fcd_elm_obj_grad: log table initialisation failed");
-    FCD_REQUIRE(grad || Tm != nullptr, "fcd_elm_obj_grad: nothing to compute (no gradient, no Tm)");
-    int grid = red_grid(C, kRedThreads / 32);
-    if (grid > sm_count() * 2) grid = sm_count() * 2;      // 2 CTAs / SM resident (86 KB table, <= 128 regs)
-    uintptr_t al = reinterpret_cast<uintptr_t>(Ea) | reinterpret_cast<uintptr_t>(Eb) | reinterpret_cast<uintptr_t>(Tm);
-    const bool vec2 = (pitchU % 2 == 0) && ((al & 15) == 0);
-    const bool fast = log_table_covers(th.epsl, th.al);
-#define FCD_ELM(G, K, V, F)                                                                        \
-    do {                                                                                           \
-        cudaFuncSetAttribute(elm_kernel<G, K, V, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                             (int)kLogTabBytes);                                                   \
-        elm_kernel<G, K, V, F><<<grid, kRedThreads, (F) ? kLogTabBytes : 0, st>>>(                 \
-            Ea, Eb, Tm, C, U, pitchU, qF, qR, N, c0, th, tab, Aout, out4, ws);                      \
-    } while (0)
-#define FCD_ELM_VF(G, K)                                                                           \
-    do {                                                                                           \
-        if (vec2) { if (fast) FCD_ELM(G, K, true, true); else FCD_ELM(G, K, true, false); }        \
-        else      { if (fast) FCD_ELM(G, K, false, true); else FCD_ELM(G, K, false, false); }      \
-    } while (0)
-    if (grad) { if (Tm != nullptr) FCD_ELM_VF(true, true); else FCD_ELM_VF(true, false); }
-    else      FCD_ELM_VF(false, true);
-#undef FCD_ELM_VF
-#undef FCD_ELM
-    return check_launch("fcd_elm_obj_grad");
+static inline int stream_grid(int64_t C) {
+    int64_t need = (C + kStreamWarps - 1) / kStreamWarps;
+    if (need < 1) need = 1;
+    return (int)(need < sm_count() ? need : sm_count());          // one persistent CTA per SM
+}
+
+static inline bool planes_ok(const void* a, const void* b, int64_t pitchU, int64_t planeStride, int64_t pitchS) {
+    const uintptr_t al = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b);
+    return (al & 15) == 0 && pitchU % 2 == 0 && planeStride % 2 == 0 && pitchS % 16 == 0;
 }
 
 }  // namespace fcd
@@ -228,41 +306,94 @@ int fcd_mstep_stats(const double* lqF, int64_t C, const double* lqR, int64_t NU,
     return check_launch("fcd_mstep_stats");
 }
 
-int fcd_elm_obj_grad(const double* Ea, const double* Eb, const double* Tm,
-                     int64_t C, int32_t U, int64_t pitchU,
-                     const double* qF, const double* qR, int32_t N, int64_t c0,
+int fcd_elm_obj_grad(const double* P, int64_t planeStride, int64_t C, int32_t U, int64_t pitchU,
+                     const double* qF, const uint8_t* fstate, const double* qR, const uint8_t* rstate,
+                     int64_t pitchS, int32_t N, const int32_t* nm,
                      const fcd_theta* theta_host, int32_t want_grad,
-                     double* Aout, double* out4, double* ws, void* stream) {
-    FCD_REQUIRE(theta_host != nullptr && ws != nullptr && Ea != nullptr && Eb != nullptr,
+                     double* out3, double* ws, void* stream) {
+    FCD_REQUIRE(theta_host != nullptr && ws != nullptr && P != nullptr && qF != nullptr && fstate != nullptr &&
+                qR != nullptr && rstate != nullptr && nm != nullptr && out3 != nullptr,
                 "fcd_elm_obj_grad: NULL argument");
-    FCD_REQUIRE(C >= 0 && U >= 1 && pitchU >= U && N >= 2, "fcd_elm_obj_grad: bad shape");
-    FCD_REQUIRE(c0 >= 0 && c0 + C <= (int64_t)N * (N - 1) / 2, "fcd_elm_obj_grad: edge shard outside N=%d", N);
+    FCD_REQUIRE(C >= 0 && C < (1 << 29) && U >= 1 && pitchU >= U && pitchS >= U && N >= 2 && N < 65536,
+                "fcd_elm_obj_grad: bad shape");
+    FCD_REQUIRE(planes_ok(P, nullptr, pitchU, planeStride, pitchS),
+                "fcd_elm_obj_grad: planes must be 16-byte aligned with even pitches");
     const ThetaDev th = make_theta_dev(*theta_host, 0);
-    return launch_elm(Ea, Eb, Tm, C, U, pitchU, qF, qR, N, c0, th, want_grad != 0, Aout, out4, ws,
-                      (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    LogTabWindow tab;
+    FCD_REQUIRE(log_table_window(th.epsl, th.al, st, tab), "fcd_elm_obj_grad: log table initialisation failed");
+    const bool fast = log_table_covers(th.epsl, th.al);
+    const size_t tbytes = fast ? (size_t)((tab.n + 1) & ~1) * sizeof(double) : 0;
+    const int depth = stream_depth<1, kElmSeg>(tbytes);
+    FCD_REQUIRE(depth >= 2, "fcd_elm_obj_grad: shared memory budget exceeded");
+    const size_t smem = tbytes + StreamGeom<1, kElmSeg>::bytes(kStreamWarps, depth);
+    const int grid = stream_grid(C);
+#define FCD_ELM(G, F)                                                                                  \
+    do {                                                                                               \
+        cudaFuncSetAttribute(elm_kernel<G, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                             (int)kSmemBudget);                                                        \
+        elm_kernel<G, F><<<grid, kStreamThreads, smem, st>>>(P, planeStride, C, U, pitchU, qF, fstate, qR, \
+                                                             rstate, pitchS, nm, th, tab, depth, out3, ws); \
+    } while (0)
+    if (want_grad) { if (fast) FCD_ELM(true, true); else FCD_ELM(true, false); }
+    else           { if (fast) FCD_ELM(false, true); else FCD_ELM(false, false); }
+#undef FCD_ELM
+    return check_launch("fcd_elm_obj_grad");
+}
+
+int fcd_elm_const(const double* L, int64_t C, int32_t U, int64_t pitchU,
+                  const double* qF, const uint8_t* fstate, const double* qR, const uint8_t* rstate,
+                  int64_t pitchS, int32_t N, const int32_t* nm, double* out1, double* ws, void* stream) {
+    FCD_REQUIRE(ws != nullptr && L != nullptr && qF != nullptr && fstate != nullptr && qR != nullptr &&
+                rstate != nullptr && nm != nullptr && out1 != nullptr, "fcd_elm_const: NULL argument");
+    FCD_REQUIRE(C >= 0 && C < (1 << 29) && U >= 1 && pitchU >= U && pitchS >= U && N >= 2 && N < 65536,
+                "fcd_elm_const: bad shape");
+    FCD_REQUIRE(planes_ok(L, nullptr, pitchU, 0, pitchS), "fcd_elm_const: plane must be 16-byte aligned with even pitches");
+    const int depth = stream_depth<1, kElmSeg>(0);
+    const size_t smem = StreamGeom<1, kElmSeg>::bytes(kStreamWarps, depth);
+    cudaFuncSetAttribute(elm_const_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+    elm_const_kernel<<<stream_grid(C), kStreamThreads, smem, (cudaStream_t)stream>>>(
+        L, C, U, pitchU, qF, fstate, qR, rstate, pitchS, nm, depth, out1, ws);
+    return check_launch("fcd_elm_const");
 }
 
 int fcd_energy_terms(const double* S1, const double* S2, int32_t H,
-                     const double* Ea, const double* Eb, const double* Tm,
-                     int64_t C, int32_t U, int64_t pitchU,
-                     const double* lqF, const double* qF, const double* lqR, const double* qR,
-                     int32_t N, int64_t c0, const fcd_theta* theta_host, const double* elm_host,
+                     const double* lqF, const double* qF, int64_t C,
+                     const double* lqR, const double* qR, int32_t N, int32_t U,
+                     const fcd_theta* theta_host, double elm,
                      double* out6, double* ws, void* stream) {
-    FCD_REQUIRE(theta_host != nullptr && ws != nullptr, "fcd_energy_terms: NULL argument");
-    FCD_REQUIRE(C >= 0 && U >= 1 && pitchU >= U && N >= 2 && H >= 1, "fcd_energy_terms: bad shape");
-    FCD_REQUIRE(c0 >= 0 && c0 + C <= (int64_t)N * (N - 1) / 2, "fcd_energy_terms: edge shard outside N=%d", N);
+    FCD_REQUIRE(theta_host != nullptr && ws != nullptr && out6 != nullptr, "fcd_energy_terms: NULL argument");
+    FCD_REQUIRE(C >= 0 && U >= 1 && N >= 2 && H >= 1, "fcd_energy_terms: bad shape");
     const ThetaDev th = make_theta_dev(*theta_host, H);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (elm_host == nullptr) {      // otherwise E_lM of this shard is known from the last K3b evaluation
-        FCD_REQUIRE(Ea != nullptr && Eb != nullptr && Tm != nullptr, "fcd_energy_terms: cache planes are NULL");
-        int rc = launch_elm(Ea, Eb, Tm, C, U, pitchU, qF, qR, N, c0, th, false, nullptr, ws + kWsScratch, ws, st);
-        if (rc) return rc;
-    }
     const int64_t NU = (int64_t)N * U;
     const int64_t work = C > NU ? C : NU;
-    energy_small_kernel<<<red_grid(work, kRedThreads), kRedThreads, 0, st>>>(
-        S1, S2, lqF, qF, C, lqR, qR, NU, th, elm_host != nullptr, elm_host ? *elm_host : 0.0, out6, ws);
+    energy_small_kernel<<<red_grid(work, kRedThreads), kRedThreads, 0, (cudaStream_t)stream>>>(
+        S1, S2, lqF, qF, C, lqR, qR, NU, th, elm, out6, ws);
     return check_launch("fcd_energy_terms");
+}
+
+int fcd_state_moments(const double* S1, const double* S2, int32_t H,
+                      const double* bt, const double* P, int64_t planeStride,
+                      int64_t C, int32_t U, int64_t pitchU,
+                      const double* qF, const double* qR, int32_t N, const int32_t* nm,
+                      const fcd_theta* theta_host, double* out18, double* ws, void* stream) {
+    FCD_REQUIRE(theta_host != nullptr && ws != nullptr && out18 != nullptr && nm != nullptr,
+                "fcd_state_moments: NULL argument");
+    FCD_REQUIRE(C >= 0 && U >= 1 && pitchU >= U && N >= 2 && N < 65536 && H >= 1, "fcd_state_moments: bad shape");
+    const ThetaDev th = make_theta_dev(*theta_host, H);
+    cudaStream_t st = (cudaStream_t)stream;
+    control_moments_kernel<<<red_grid(C, kRedThreads), kRedThreads, 0, st>>>(S1, S2, (double)H, qF, C, out18, ws);
+    int rc = check_launch("fcd_state_moments(controls)");
+    if (rc) return rc;
+    int grid = red_grid(C, kRedThreads / 32);
+    if (grid > sm_count() * 2) grid = sm_count() * 2;
+    if (log_table_covers(th.epsl, th.al))
+        patient_moments_kernel<true><<<grid, kRedThreads, 0, st>>>(P, planeStride, bt, C, U, pitchU, qF, qR, nm, th,
+                                                                   out18 + 9, ws);
+    else
+        patient_moments_kernel<false><<<grid, kRedThreads, 0, st>>>(P, planeStride, bt, C, U, pitchU, qF, qR, nm, th,
+                                                                    out18 + 9, ws);
+    return check_launch("fcd_state_moments(patients)");
 }
 
 }  // extern "C"

@@ -74,6 +74,34 @@ bool log_table_covers(const double epsl[3], const double al[3]) {
     return true;
 }
 
+bool log_table_window(const double epsl[3], const double al[3], cudaStream_t st, LogTabWindow& w) {
+    w.g = log_table(st);
+    w.lo = 0;
+    w.n = kLogTabSize;
+    if (w.g == nullptr) return false;
+    if (!log_table_covers(epsl, al)) return true;          // SAFE kernels: table unused
+    double ymin = 1.0, ymax = 0.0;
+    for (int l = 0; l < 3; ++l) {
+        const double lo = epsl[l] < al[l] ? epsl[l] : al[l];
+        const double hi = epsl[l] < al[l] ? al[l] : epsl[l];
+        if (lo < ymin) ymin = lo;
+        if (hi > ymax) ymax = hi;
+    }
+    auto slot = [](double y) {                              // mirrors log_reduce (fcd_math.cuh)
+        const double r = 1.0 / y;
+        uint64_t bits;
+        memcpy(&bits, &r, sizeof(bits));
+        const int hi = ((int)(bits >> 32) + (1 << (19 - kLogTabBits))) & ~((1 << (20 - kLogTabBits)) - 1);
+        return (hi >> (20 - kLogTabBits)) - kLogTabBase;
+    };
+    int lo = slot(ymax) - 4, hi = slot(ymin) + 4;           // slack: MUFU.RCP64H error, FMA rounding
+    if (lo < 0) lo = 0;
+    if (hi > kLogTabSize - 1) hi = kLogTabSize - 1;
+    w.lo = lo;
+    w.n = hi - lo + 1;
+    return true;
+}
+
 ThetaDev make_theta_dev(const fcd_theta& th, int H) {
     ThetaDev d;
     memset(&d, 0, sizeof(d));

@@ -61,18 +61,40 @@ class _Mirror(object):
     def __init__(self):
         self.host = None
         self.dev = None      # (lq, q) device tensors, flat
+        self.state = None    # peak-state bytes of q (fstate / rstate, include/fcdiff_b200.h)
         self.version = 0
 
     def set_host(self, a):
         self.host = a
         self.dev = None
+        self.state = None
         self.version += 1
 
     def set_dev(self, lq, q, shape):
         self.dev = (lq, q)
         self.shape = shape
         self.host = None
+        self.state = None
         self.version += 1
+
+    def get_state(self):
+        """Peak states of the probabilities: (C,) bytes for a (C, 1, 3) array,
+        (N, U rounded up to 16) bytes for an (N, U, 2) array."""
+        if self.state is None:
+            lib = _lib.load()
+            (_, q) = self.get_dev()
+            if self.shape[-1] == 3:
+                C = int(np.prod(self.shape[:-1]))
+                st = _dev.empty((max(C, 1),), torch.uint8)
+                _lib.check(lib.fcd_peak_states_F(_dev.ptr(q), C, _dev.ptr(st), _dev.stream()), "fcd_peak_states_F")
+            else:
+                (N, U) = (int(self.shape[0]), int(self.shape[1]))
+                pitchS = (U + 15) // 16 * 16            # rows are moved by 16-byte-granular bulk copies
+                st = _dev.empty((N, pitchS), torch.uint8)
+                _lib.check(lib.fcd_peak_states_R(_dev.ptr(q), N, U, pitchS, _dev.ptr(st), _dev.stream()),
+                           "fcd_peak_states_R")
+            self.state = st
+        return self.state
 
     def get_host(self):
         if self.host is None and self.dev is not None:
@@ -113,6 +135,9 @@ class UnsharedRegionFit(object):
         Edge sharding over the ranks of a ``torch.distributed`` group (new).
     optimise_theta_sub : bool
         Run the (eta, epsilon) optimiser in ``_update_theta`` (default True).
+    update_mu_sigma : bool
+        Also re-estimate ``mu`` and ``sigma`` in ``_update_theta`` (new; the
+        reference ships this step disabled, fit.py:232-237; default False).
     convergence_rule : "reference" | "magnitude"
         ``"reference"`` is fit.py:138-140 literally, ``(e - e*) / e < rel_tol``: with a
         negative free energy (the usual case: densities > 1) any *decrease* makes the
@@ -131,6 +156,7 @@ class UnsharedRegionFit(object):
         self.shards = None
         self.n_edges = None           # global edge count when b / bt are device edge shards
         self.optimise_theta_sub = True
+        self.update_mu_sigma = False  # re-estimate mu, sigma (disabled in the reference, fit.py:232-237)
         self.convergence_rule = "reference"
         self.n_objective_evals = []
         self.profile = None           # _dev.KernelTimers for per-kernel CUDA-event timing
@@ -250,15 +276,16 @@ class UnsharedRegionFit(object):
             _lib.check(lib.fcd_healthy_stats(_dev.ptr(b_dev), Cl, H, H, _dev.ptr(S1), _dev.ptr(S2),
                                              _dev.stream()), "fcd_healthy_stats")
         del b_dev
+        nm = _dev.empty((max(Cl, 1),), torch.int32)
+        _lib.check(lib.fcd_edge_table(c0, Cl, _dev.ptr(nm), _dev.stream()), "fcd_edge_table")
         self._in = dict(key=key, C=C, H=H, U=U, c0=c0, Cl=Cl, u0=u0, Ul=Ul, pitchU=pitchU,
-                        bt=bt_dev, S1=S1, S2=S2, cache_key=None, Ea=None, Eb=None, Tm=None,
-                        EaT=None, EbT=None, WT=None, A=[None, None, None], A_next=0)
+                        bt=bt_dev, S1=S1, S2=S2, nm=nm, cache_key=None, P=None, L=None, PT=None, WT=None)
         self._evals = []
         self._const = None
         return self._in
 
     def _ensure_cache(self):
-        """Gaussian cache planes Ea / Eb / Tm of the local edge rows for the
+        """Responsibility planes P[3] / L of the local edge rows for the
         (mu, sigma) of the last ``_update_lps`` (rebuilt only when they change;
         the reference never changes them, fit.py:232-237)."""
         inp = self._ensure_inputs()
@@ -267,48 +294,49 @@ class UnsharedRegionFit(object):
             return inp
         lib = _lib.load()
         (Cl, U, pitchU) = (inp['Cl'], inp['U'], inp['pitchU'])
-        for name in ('Ea', 'Eb', 'Tm'):
-            if inp[name] is None:
-                inp[name] = _dev.empty((Cl, pitchU))
+        if inp['P'] is None:
+            inp['P'] = _dev.empty((3, max(Cl, 1), pitchU))
+            inp['L'] = _dev.empty((max(Cl, 1), pitchU))
         th = self._theta()
-        with _dev.timed(self.profile, "K0_gauss_cache"):
-            _lib.check(lib.fcd_gauss_cache(_dev.ptr(inp['bt']), Cl, U, pitchU, ctypes.byref(th),
-                                           _dev.ptr(inp['Ea']), _dev.ptr(inp['Eb']), _dev.ptr(inp['Tm']),
-                                           _dev.stream()), "fcd_gauss_cache")
+        with _dev.timed(self.profile, "K0_resp_cache"):
+            _lib.check(lib.fcd_resp_cache(_dev.ptr(inp['bt']), Cl, U, pitchU, ctypes.byref(th),
+                                          _dev.ptr(inp['P']), max(Cl, 1) * pitchU, _dev.ptr(inp['L']),
+                                          _dev.stream()), "fcd_resp_cache")
         inp['cache_key'] = ckey
-        inp['EaT'] = inp['EbT'] = None
+        inp['PT'] = None
         self._evals = []
         self._const = None
         return inp
 
     def _ensure_patient_major(self):
-        """Patient-major cache planes EaT / EbT [U_local][C] of ALL edges (K2b)."""
+        """Patient-major responsibility planes PT [3][U_local][C] of ALL edges (K2b)."""
         inp = self._ensure_cache()
-        if inp['EaT'] is not None:
+        if inp['PT'] is not None:
             return inp
         lib = _lib.load()
         (C, U, u0, Ul) = (inp['C'], inp['U'], inp['u0'], inp['Ul'])
         if self.shards is None:
-            (srcA, srcB, pitchU, uu0, Us) = (inp['Ea'], inp['Eb'], inp['pitchU'], u0, U)
+            (src, pitchU, uu0, Us) = (inp['P'], inp['pitchU'], u0, U)
         else:
             if torch.is_tensor(self.bt):
                 # edge-sharded device input: one all-to-all of (C_local x U_peer) blocks of bt
                 blk = self.shards.exchange_patient_blocks(inp['bt'], inp['Cl'], C, U)
             else:   # edge-sharded host input: this rank uploads every edge of its own patients
                 blk = _dev.upload(np.ascontiguousarray(np.asarray(self.bt)[:, u0:u0 + Ul]))
-            (srcA, srcB) = (_dev.empty((C, max(Ul, 1))), _dev.empty((C, max(Ul, 1))))
+            src = _dev.empty((3, C, max(Ul, 1)))
             if Ul > 0:
                 th = self._theta()
-                _lib.check(lib.fcd_gauss_cache(_dev.ptr(blk), C, Ul, Ul, ctypes.byref(th), _dev.ptr(srcA),
-                                               _dev.ptr(srcB), None, _dev.stream()), "fcd_gauss_cache")
+                _lib.check(lib.fcd_resp_cache(_dev.ptr(blk), C, Ul, Ul, ctypes.byref(th), _dev.ptr(src),
+                                              C * max(Ul, 1), None, _dev.stream()), "fcd_resp_cache")
             (pitchU, uu0, Us) = (Ul, 0, Ul)
-        (EaT, EbT) = (_dev.empty((Ul, C)), _dev.empty((Ul, C)))
+        PT = _dev.empty((3, max(Ul, 1), C))
         if Ul > 0:
             with _dev.timed(self.profile, "K0_transpose"):
-                for (src, dst) in ((srcA, EaT), (srcB, EbT)):
-                    _lib.check(lib.fcd_transpose_patients(_dev.ptr(src), C, Us, pitchU, uu0, Ul, _dev.ptr(dst), C,
-                                                          _dev.stream()), "fcd_transpose_patients")
-        inp['EaT'], inp['EbT'] = EaT, EbT
+                for k in range(3):
+                    _lib.check(lib.fcd_transpose_patients(_dev.ptr(src[k]), C, Us, pitchU, uu0, Ul,
+                                                          _dev.ptr(PT[k]), C, _dev.stream()),
+                               "fcd_transpose_patients")
+        inp['PT'] = PT
         if inp['WT'] is None:
             inp['WT'] = _dev.empty((Ul, C, 3))
         return inp
@@ -447,16 +475,14 @@ class UnsharedRegionFit(object):
         energy += t[5]
         return float(energy)
 
-    def _find_eval(self, need_F):
+    def _find_eval(self):
         """A recent K3b evaluation made at the current (eta, epsilon) snapshot with
-        the current q_R (and q_F when ``need_F``): its per-edge sums A[c][k] and
-        its E_lM are exactly what K2 / K4 would recompute."""
+        the current q_F and q_R: its E_lM is what the energy needs."""
         if not self.reuse_evaluations or self._theta_lps is None:
             return None
         (_, _, eta, epsilon) = self._theta_lps
         for ev in reversed(self._evals):
-            if ev['x'] == (eta, epsilon) and ev['verR'] == self._mR.version and \
-                    (not need_F or ev['verF'] == self._mF.version):
+            if ev['x'] == (eta, epsilon) and ev['verR'] == self._mR.version and ev['verF'] == self._mF.version:
                 return ev
         return None
 
@@ -465,24 +491,24 @@ class UnsharedRegionFit(object):
         lib = _lib.load()
         inp = self._ensure_cache()
         (N, H, U) = self._dims
+        (c0, Cl) = (inp['c0'], inp['Cl'])
+        ev = self._find_eval()
+        if ev is None:
+            (_, _, eta, epsilon) = self._theta_lps
+            self._objective(np.array([eta, epsilon]), want_grad=False, name="K4_elm")
+            ev = self._evals[-1]
         (lqF, qF) = self._mF.get_dev()
         (lqR, qR) = self._mR.get_dev()
-        (c0, Cl) = (inp['c0'], inp['Cl'])
         th = self._theta()
         res = self._result(6)
         out = res.dev
-        ev = self._find_eval(need_F=True)
-        elm = None
-        if ev is not None:      # global E_lM is known: rank 0 contributes it, the others zero
-            first = self.shards is None or self.shards.rank == 0
-            elm = ctypes.byref(ctypes.c_double(ev['elm'] if first else 0.0))
-        with _dev.timed(self.profile, "K4_energy_terms" if ev is None else "K4_energy_small"):
+        # the global E_lM is known: rank 0 contributes it, the others zero
+        first = self.shards is None or self.shards.rank == 0
+        with _dev.timed(self.profile, "K4_energy_small"):
             _lib.check(lib.fcd_energy_terms(
-                _dev.ptr(inp['S1']), _dev.ptr(inp['S2']), H, _dev.ptr(inp['Ea']), _dev.ptr(inp['Eb']),
-                _dev.ptr(inp['Tm']), Cl, U, inp['pitchU'],
-                _dev.ptr(lqF[c0 * 3:]), _dev.ptr(qF[c0 * 3:]), _dev.ptr(lqR), _dev.ptr(qR), N, c0,
-                ctypes.byref(th), elm, _dev.ptr(out), _dev.ptr(_dev.workspace()), _dev.stream()),
-                "fcd_energy_terms")
+                _dev.ptr(inp['S1']), _dev.ptr(inp['S2']), H, _dev.ptr(lqF[c0 * 3:]), _dev.ptr(qF[c0 * 3:]), Cl,
+                _dev.ptr(lqR), _dev.ptr(qR), N, U, ctypes.byref(th), ev['elm'] if first else 0.0,
+                _dev.ptr(out), _dev.ptr(_dev.workspace()), _dev.stream()), "fcd_energy_terms")
         if self.shards is not None:
             self.shards.allreduce_terms(out, (0, 1, 3, 4))
             return self.shards.fix_replicated(res.read(), (0, 1, 3, 4))
@@ -513,21 +539,15 @@ class UnsharedRegionFit(object):
         (N, H, U) = self._dims
         (C, c0, Cl) = (inp['C'], inp['c0'], inp['Cl'])
         (lqR, qR) = self._mR.get_dev()
+        rstate = self._mR.get_state()
         lqF = _dev.empty((C * 3,))
         qF = _dev.empty((C * 3,))
         th = self._theta()
-        ev = self._find_eval(need_F=False)
-        if ev is not None:
-            with _dev.timed(self.profile, "K2_estep_qF_finish"):
-                _lib.check(lib.fcd_estep_qF_finish(
-                    _dev.ptr(inp['S1']), _dev.ptr(inp['S2']), H, _dev.ptr(ev['A']), Cl, ctypes.byref(th),
-                    _dev.ptr(lqF[c0 * 3:]), _dev.ptr(qF[c0 * 3:]), _dev.stream()), "fcd_estep_qF_finish")
-        else:
-            with _dev.timed(self.profile, "K2_estep_qF"):
-                _lib.check(lib.fcd_estep_qF(
-                    _dev.ptr(inp['S1']), _dev.ptr(inp['S2']), H, _dev.ptr(inp['Ea']), _dev.ptr(inp['Eb']),
-                    Cl, U, inp['pitchU'], _dev.ptr(qR), N, c0, ctypes.byref(th),
-                    _dev.ptr(lqF[c0 * 3:]), _dev.ptr(qF[c0 * 3:]), _dev.stream()), "fcd_estep_qF")
+        with _dev.timed(self.profile, "K2_estep_qF"):
+            _lib.check(lib.fcd_estep_qF(
+                _dev.ptr(inp['S1']), _dev.ptr(inp['S2']), H, _dev.ptr(inp['P']), max(Cl, 1) * inp['pitchU'],
+                Cl, U, inp['pitchU'], _dev.ptr(qR), _dev.ptr(rstate), rstate.shape[1], N, _dev.ptr(inp['nm']),
+                ctypes.byref(th), _dev.ptr(lqF[c0 * 3:]), _dev.ptr(qF[c0 * 3:]), _dev.stream()), "fcd_estep_qF")
         if self.shards is not None:
             self.shards.allgather_edges(lqF, qF, C)
         self._mF.set_dev(lqF, qF, (C, 1, 3))
@@ -562,10 +582,11 @@ class UnsharedRegionFit(object):
         (lqF, qF) = self._mF.get_dev()
         (lqR, qR) = self._mR.get_dev()
         th = self._theta()
+        fstate = self._mF.get_state()
         with _dev.timed(self.profile, "K2b_region_weights"):
-            _lib.check(lib.fcd_region_weights(_dev.ptr(inp['EaT']), _dev.ptr(inp['EbT']), Ul, C, C,
-                                              _dev.ptr(qF), ctypes.byref(th), _dev.ptr(inp['WT']),
-                                              _dev.stream()), "fcd_region_weights")
+            _lib.check(lib.fcd_region_weights(_dev.ptr(inp['PT']), max(Ul, 1) * C, Ul, C, C,
+                                              _dev.ptr(qF), _dev.ptr(fstate), ctypes.byref(th),
+                                              _dev.ptr(inp['WT']), _dev.stream()), "fcd_region_weights")
         lqR_new, qR_new = lqR.clone(), qR.clone()
         with _dev.timed(self.profile, "K2b_sweep"):
             _lib.check(lib.fcd_estep_qR(_dev.ptr(inp['WT']), C, N, U, u0, Ul, log_pi2, lookup,
@@ -581,6 +602,8 @@ class UnsharedRegionFit(object):
         self._update_pi_gamma(True, True)
         if self.optimise_theta_sub:
             self._update_theta_sub()
+        if self.update_mu_sigma:
+            self._update_mu_sigma()
 
     def _mstep_sums(self, do_pi, do_gamma):
         lib = _lib.load()
@@ -612,6 +635,47 @@ class UnsharedRegionFit(object):
         if do_gamma:
             self.model.gamma = s[0:3] / C                          # fit.py:220
 
+    def _state_moments(self):
+        """(18,) per-state sufficient statistics of the correlations at the
+        current (q_F, q_R, theta): controls [n_j, sum x, sum x^2], then patients
+        (K3c, ``fcd_state_moments``)."""
+        lib = _lib.load()
+        if self._lps_state != 'derived':
+            self._update_lps()
+        inp = self._ensure_cache()
+        (N, H, U) = self._dims
+        (c0, Cl) = (inp['c0'], inp['Cl'])
+        (_, qF) = self._mF.get_dev()
+        (_, qR) = self._mR.get_dev()
+        th = self._theta(use_snapshot=False)
+        (th.mu[:], th.sigma[:]) = (list(self._theta_lps[0]), list(self._theta_lps[1]))   # the planes' (mu, sigma)
+        res = self._result(18)
+        with _dev.timed(self.profile, "K3c_state_moments"):
+            _lib.check(lib.fcd_state_moments(
+                _dev.ptr(inp['S1']), _dev.ptr(inp['S2']), H, _dev.ptr(inp['bt']), _dev.ptr(inp['P']),
+                max(Cl, 1) * inp['pitchU'], Cl, U, inp['pitchU'], _dev.ptr(qF[c0 * 3:]), _dev.ptr(qR), N,
+                _dev.ptr(inp['nm']), ctypes.byref(th), _dev.ptr(res.dev), _dev.ptr(_dev.workspace()),
+                _dev.stream()), "fcd_state_moments")
+        if self.shards is not None:
+            self.shards.allreduce_terms(res.dev, tuple(range(18)))
+        return res.read()
+
+    def _update_mu_sigma(self):
+        """
+        Updates mu and sigma (new: the reference holds them fixed,
+        fcdiff/fit.py:232-237, 250-251, 266-267): one generalised-EM step, the
+        pooled weighted Gaussian maximum likelihood over controls (weights q_F)
+        and patients (posterior state weights given q_F, q_R, theta).
+        """
+        mom = self._state_moments()
+        n = mom[0:3] + mom[9:12]
+        s1 = mom[3:6] + mom[12:15]
+        s2 = mom[6:9] + mom[15:18]
+        mu = s1 / n
+        var = np.maximum(s2 / n - mu * mu, 1e-12)
+        self.model.mu = mu
+        self.model.sigma = np.sqrt(var)
+
     def _update_pi(self):
         """
         Updates the value of the parameter pi (fcdiff/fit.py:208-213).
@@ -624,44 +688,56 @@ class UnsharedRegionFit(object):
         """
         self._update_pi_gamma(False, True)
 
-    def _objective(self, theta_sub, want_grad=True):
+    def _elm_const(self, inp):
+        """Part of E_lM that does not depend on (eta, epsilon): one pass over the
+        L plane per (q_F, q_R), cached."""
+        ckey = (self._mF.version, self._mR.version, inp['cache_key'])
+        if self._const is not None and self._const[0] == ckey:
+            return self._const[1]
+        lib = _lib.load()
+        (N, H, U) = self._dims
+        (c0, Cl) = (inp['c0'], inp['Cl'])
+        (_, qF) = self._mF.get_dev()
+        (_, qR) = self._mR.get_dev()
+        (fstate, rstate) = (self._mF.get_state(), self._mR.get_state())
+        res = self._result(1)
+        with _dev.timed(self.profile, "K3b_elm_const"):
+            _lib.check(lib.fcd_elm_const(
+                _dev.ptr(inp['L']), Cl, U, inp['pitchU'], _dev.ptr(qF[c0 * 3:]), _dev.ptr(fstate[c0:]),
+                _dev.ptr(qR), _dev.ptr(rstate), rstate.shape[1], N, _dev.ptr(inp['nm']),
+                _dev.ptr(res.dev), _dev.ptr(_dev.workspace()), _dev.stream()), "fcd_elm_const")
+        if self.shards is not None:
+            self.shards.allreduce_terms(res.dev, (0,))
+        self._const = (ckey, float(res.read()[0]))
+        return self._const[1]
+
+    def _objective(self, theta_sub, want_grad=True, name="K3b_elm_obj_grad"):
         """(-E_lM, gradient) at theta_sub = [eta, epsilon] from one fused pass
-        over the cache planes (K3b).  The pass also leaves the per-edge sums
-        A[c][k], which the next K2 and the energy reuse when (eta, epsilon) ends
-        up being the optimiser's answer."""
+        over the responsibility planes (K3b)."""
         lib = _lib.load()
         inp = self._ensure_cache()
         (N, H, U) = self._dims
         (c0, Cl) = (inp['c0'], inp['Cl'])
         (_, qF) = self._mF.get_dev()
         (_, qR) = self._mR.get_dev()
+        (fstate, rstate) = (self._mF.get_state(), self._mR.get_state())
         th = self._theta()
         th.eta = float(theta_sub[0])
         th.epsilon = float(theta_sub[1])
-        ckey = (self._mF.version, self._mR.version, inp['cache_key'])
-        need_const = self._const is None or self._const[0] != ckey
-        slot = inp['A_next']
-        inp['A_next'] = (slot + 1) % len(inp['A'])
-        if inp['A'][slot] is None:
-            inp['A'][slot] = _dev.empty((max(Cl, 1) * 3,))
-        A = inp['A'][slot]
-        self._evals = [ev for ev in self._evals if ev['A'] is not A]
-        res = self._result(4)
-        with _dev.timed(self.profile, "K3b_elm_obj_grad"):
+        const = self._elm_const(inp)
+        res = self._result(3)
+        with _dev.timed(self.profile, name):
             _lib.check(lib.fcd_elm_obj_grad(
-                _dev.ptr(inp['Ea']), _dev.ptr(inp['Eb']),
-                _dev.ptr(inp['Tm']) if (need_const or not want_grad) else None,
-                Cl, U, inp['pitchU'], _dev.ptr(qF[c0 * 3:]), _dev.ptr(qR), N, c0,
-                ctypes.byref(th), 1 if want_grad else 0, _dev.ptr(A), _dev.ptr(res.dev),
+                _dev.ptr(inp['P']), max(Cl, 1) * inp['pitchU'], Cl, U, inp['pitchU'],
+                _dev.ptr(qF[c0 * 3:]), _dev.ptr(fstate[c0:]), _dev.ptr(qR), _dev.ptr(rstate), rstate.shape[1],
+                N, _dev.ptr(inp['nm']), ctypes.byref(th), 1 if want_grad else 0, _dev.ptr(res.dev),
                 _dev.ptr(_dev.workspace()), _dev.stream()), "fcd_elm_obj_grad")
         if self.shards is not None:
-            self.shards.allreduce_terms(res.dev, (0, 1, 2, 3))        # all four are edge-local partial sums
+            self.shards.allreduce_terms(res.dev, (0, 1, 2))           # all three are edge-local partial sums
         o = res.read()
-        if need_const or not want_grad:
-            self._const = (ckey, float(o[3]))
-        elm = float(o[0]) + self._const[1]
-        self._evals.append(dict(x=(th.eta, th.epsilon), verF=self._mF.version, verR=self._mR.version,
-                                A=A, elm=elm))
+        elm = float(o[0]) + const
+        self._evals.append(dict(x=(th.eta, th.epsilon), verF=self._mF.version, verR=self._mR.version, elm=elm))
+        del self._evals[:-4]
         return -elm, np.array([o[1], o[2]])
 
     def _update_theta_sub(self):

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define FCD_VERSION 100
+#define FCD_VERSION 110
 
 #if defined(__GNUC__)
 #define FCD_API __attribute__((visibility("default")))
@@ -74,49 +74,54 @@ FCD_API int fcd_c_to_nm(int64_t c0, int64_t C, int32_t* n_out, int32_t* m_out, v
 FCD_API int fcd_healthy_stats(const double* b, int64_t C, int32_t H, int64_t pitchH,
                       double* S1, double* S2, void* stream);
 
-/* Gaussian cache, built once per fit (the reference never re-estimates mu,
- * sigma, fcdiff/fit.py:232-237): for every patient correlation x = bt[c,u], with
- * t_k = log N(x; mu_k, sigma_k) + log sqrt(2 pi) and e_k = exp(t_k - max_j t_j),
- *   Ea[c,u] = e of the first non-maximal state, Eb[c,u] = e of the second one
- *   (index of the maximal state, whose e is exactly 1, in its 2 lowest mantissa
- *   bits), Tm[c,u] = max_j t_j (may be NULL).
- * All three have the shape and pitch of bt.  This is the patient half of
- * `_update_lps` (fit.py:115) in a form that cannot underflow; the kernels below
- * read these planes instead of bt. */
-FCD_API int fcd_gauss_cache(const double* bt, int64_t C, int32_t U, int64_t pitchU,
-                    const fcd_theta* theta_host, double* Ea, double* Eb, double* Tm, void* stream);
+/* Edge table of the local shard: nm[i] = n | m << 16 for the edge c0 + i
+ * (fcdiff/util.py:62-84 c_to_nm; at most 65535 regions).  Built once per fit. */
+FCD_API int fcd_edge_table(int64_t c0, int64_t C, int32_t* nm, void* stream);
+
+/* Responsibility planes, built once per fit (the reference never re-estimates
+ * mu, sigma, fcdiff/fit.py:232-237): for every patient correlation x = bt[c,u]
+ * with N_k = N(x; mu_k, sigma_k) (fit.py:115),
+ *   P[k][c][u] = N_k / (N_0 + N_1 + N_2)   (three planes, `planeStride` elements apart)
+ *   L[c][u]    = log(N_0 + N_1 + N_2)      (may be NULL)
+ * each with the shape and pitch of bt.  Then (fit.py:117-122, 409-444)
+ *   log M_kl = L + log(a_l + b_l p_k),  a_l = (1 - eps_l)/2,  b_l = eps_l - a_l,
+ * exactly and without underflow; the kernels below read these planes, not bt. */
+FCD_API int fcd_resp_cache(const double* bt, int64_t C, int32_t U, int64_t pitchU,
+                   const fcd_theta* theta_host, double* P, int64_t planeStride, double* L, void* stream);
+
+/* Peak states of the posteriors (tier selection, DESIGN.md "Tiers"):
+ *   fstate[c]   = k if qF[c,k] == 1.0 and the other two <= 2^-60, else 3;
+ *   rstate[n][u] = s if qR[n,u,s] == 1.0 and the other <= 2^-60, else 2;
+ *                  4 in the padding columns u >= U (row pitch pitchS, a multiple of 16).
+ * A term whose weight is <= 2^-60 is below the rounding error of the sums it
+ * would enter and is skipped by the kernels below. */
+FCD_API int fcd_peak_states_F(const double* qF, int64_t C, uint8_t* fstate, void* stream);
+FCD_API int fcd_peak_states_R(const double* qR, int32_t N, int32_t U, int64_t pitchS, uint8_t* rstate, void* stream);
 
 /* K2 -- E-step for the template posterior; replaces `_update_lq_F`
  * (fcdiff/fit.py:157-174) + `_eval_q_R_w` (fit.py:382-406) + the patient half
  * of `_update_lps` (fit.py:115-122) + `_eval_M` (fit.py:409-444).
  *   lqF[c,k] = log gamma_k + sum_h logN_k(b[c,h])
  *            + sum_u sum_l w_l(n,m,u) log M_kl(bt[c,u]),  minus logsumexp_k.
- * qR is [N][U][2] probabilities.  Outputs lqF [C][3] and qF=exp(lqF) [C][3]. */
+ * P: planes of the local edge rows; qR [N][U][2] probabilities, rstate their peak
+ * states; nm the shard's edge table.  Outputs lqF [C][3] and qF=exp(lqF) [C][3]. */
 FCD_API int fcd_estep_qF(const double* S1, const double* S2, int32_t H,
-                 const double* Ea, const double* Eb, int64_t C, int32_t U, int64_t pitchU,
-                 const double* qR, int32_t N, int64_t c0,
-                 const fcd_theta* theta_host,
-                 double* lqF, double* qF, void* stream);
+                 const double* P, int64_t planeStride, int64_t C, int32_t U, int64_t pitchU,
+                 const double* qR, const uint8_t* rstate, int64_t pitchS, int32_t N, const int32_t* nm,
+                 const fcd_theta* theta_host, double* lqF, double* qF, void* stream);
 
-/* K2 without a pass over the data: A[c][k] = sum_u sum_l w_l log M'_kl is the
- * per-edge output of an fcd_elm_obj_grad call made with the same q_R and
- * (eta, epsilon); only log gamma, the healthy term and the normalisation of
- * fit.py:165-174 remain. */
-FCD_API int fcd_estep_qF_finish(const double* S1, const double* S2, int32_t H, const double* A, int64_t C,
-                        const fcd_theta* theta_host, double* lqF, double* qF, void* stream);
-
-/* Patient-major copy of the patient correlations: btT[u - u0][c] = bt[c][u]
+/* Patient-major copy of an edge-major plane: dst[u - u0][c] = src[c][u]
  * for u in [u0, u0+Ul), c in [0, C).  Built once per fit. */
 FCD_API int fcd_transpose_patients(const double* bt, int64_t C, int32_t U, int64_t pitchU,
                            int32_t u0, int32_t Ul, double* btT, int64_t pitchC, void* stream);
 
 /* K2b part 1 -- q_R-independent half of `_update_lq_R` (fcdiff/fit.py:187-194):
- *   WT[u][c][l] = sum_k qF[c,k] * log M_kl(bt[c][u])   (patient-major; EaT/EbT are the
- *   patient-major copies [Ul][pitchC] of the Ea/Eb cache planes)
+ *   WT[u][c][l] = sum_k qF[c,k] * log M_kl(bt[c][u])   (patient-major; PT[k][u][c] are the
+ *   patient-major copies [Ul][pitchC] of the responsibility planes)
  * up to an additive per-(c,u) constant common to all l, which cancels in the
- * normalisation of fit.py:196. qF is [C][3] for ALL edges. */
-FCD_API int fcd_region_weights(const double* EaT, const double* EbT, int32_t Ul, int64_t C, int64_t pitchC,
-                       const double* qF, const fcd_theta* theta_host,
+ * normalisation of fit.py:196. qF / fstate cover ALL edges. */
+FCD_API int fcd_region_weights(const double* PT, int64_t planeStride, int32_t Ul, int64_t C, int64_t pitchC,
+                       const double* qF, const uint8_t* fstate, const fcd_theta* theta_host,
                        double* WT, void* stream);
 
 /* K2b part 2 -- Gauss-Seidel sweep of `_update_lq_R` (fcdiff/fit.py:176-198)
@@ -139,31 +144,48 @@ FCD_API int fcd_mstep_stats(const double* lqF, int64_t C, const double* lqR, int
 /* K3b -- objective and analytic gradient of the (eta, epsilon) sub-problem;
  * replaces `_opt_fun` (fcdiff/fit.py:270-286) = `_update_lps` + `_eval_E_lM`
  * (fit.py:489-511) and `_eval_dE_dh` / `_eval_dE_de` / `_eval_dlM_dh` /
- * `_eval_dlM_de` (fit.py:600-697) in ONE pass over the cache planes.
- *   out[0] + out[3] = E_lM = sum_c sum_k qF[c,k] sum_u sum_l w_l log M_kl(bt[c,u])
- *       out[3] is the part that does not depend on (eta, epsilon); it is only
- *       computed when Tm != NULL (else 0)
- *   out[1] = dE/d eta, out[2] = dE/d epsilon   (of E = -E_lM; only if want_grad)
- * Aout (may be NULL): per-edge sums A[c][k] for fcd_estep_qF_finish. */
-FCD_API int fcd_elm_obj_grad(const double* Ea, const double* Eb, const double* Tm,
-                     int64_t C, int32_t U, int64_t pitchU,
-                     const double* qF, const double* qR, int32_t N, int64_t c0,
+ * `_eval_dlM_de` (fit.py:600-697) in ONE pass over the responsibility planes
+ * (one plane, 8 bytes per edge-patient, wherever the posteriors are peaked).
+ *   out[0] = sum_c sum_k qF[c,k] sum_u sum_l w_l log(a_l + b_l p_k)
+ *            E_lM = out[0] + fcd_elm_const (the part independent of eta, epsilon)
+ *   out[1] = dE/d eta, out[2] = dE/d epsilon   (of E = -E_lM; only if want_grad) */
+FCD_API int fcd_elm_obj_grad(const double* P, int64_t planeStride, int64_t C, int32_t U, int64_t pitchU,
+                     const double* qF, const uint8_t* fstate, const double* qR, const uint8_t* rstate,
+                     int64_t pitchS, int32_t N, const int32_t* nm,
                      const fcd_theta* theta_host, int32_t want_grad,
-                     double* Aout, double* out4, double* ws, void* stream);
+                     double* out3, double* ws, void* stream);
+
+/* out1[0] = sum_c (sum_k qF[c,k]) sum_u (sum_l w_l) L[c,u]: the part of E_lM
+ * (fit.py:489-511) that does not depend on (eta, epsilon). */
+FCD_API int fcd_elm_const(const double* L, int64_t C, int32_t U, int64_t pitchU,
+                  const double* qF, const uint8_t* fstate, const double* qR, const uint8_t* rstate,
+                  int64_t pitchS, int32_t N, const int32_t* nm, double* out1, double* ws, void* stream);
 
 /* K4 -- free-energy terms; replaces `_eval_energy` and `_eval_E_*`
  * (fcdiff/fit.py:142-155, 447-539).  out[0..5] = E_lp_F, E_lp_B_g_F, E_lp_R,
  * E_lM, E_lq_F, E_lq_R over the local edge shard (terms 2 and 5 involve q_R
  * only and are complete on every rank).  qF = exp(lqF), qR = exp(lqR) as left
- * by fcd_estep_qF / fcd_estep_qR (fit.py:146-147).  elm_host (may be NULL): the
- * shard's E_lM when the caller already has it from fcd_elm_obj_grad at the same
- * (q_F, q_R, theta); then no pass over the data is made. */
+ * by fcd_estep_qF / fcd_estep_qR (fit.py:146-147); lqF / qF / S1 / S2 are the
+ * shard's C rows.  `elm` = E_lM of the shard (fcd_elm_obj_grad + fcd_elm_const
+ * at the same q_F, q_R, theta). */
 FCD_API int fcd_energy_terms(const double* S1, const double* S2, int32_t H,
-                     const double* Ea, const double* Eb, const double* Tm,
-                     int64_t C, int32_t U, int64_t pitchU,
-                     const double* lqF, const double* qF, const double* lqR, const double* qR,
-                     int32_t N, int64_t c0, const fcd_theta* theta_host, const double* elm_host,
+                     const double* lqF, const double* qF, int64_t C,
+                     const double* lqR, const double* qR, int32_t N, int32_t U,
+                     const fcd_theta* theta_host, double elm,
                      double* out6, double* ws, void* stream);
+
+/* K3c -- per-state sufficient statistics of the correlations for the control
+ * and the patient group (north_star subsystem 3; the reference ships only
+ * disabled pieces of a mu / sigma update, fcdiff/fit.py:232-237, 542-597,
+ * 709-733; doc/methods.rst:715-944).  out[0..8] controls: n_j = H sum_c qF[c,j],
+ * sum qF[c,j] S1[c], sum qF[c,j] S2[c]; out[9..17] patients: sum R_j, sum R_j x,
+ * sum R_j x^2 with R_j(c,u) the posterior weight that patient edge (c,u) is in
+ * state j.  Pooled, they are the EM (lower-bound) update of mu_j, sigma_j. */
+FCD_API int fcd_state_moments(const double* S1, const double* S2, int32_t H,
+                      const double* bt, const double* P, int64_t planeStride,
+                      int64_t C, int32_t U, int64_t pitchU,
+                      const double* qF, const double* qR, int32_t N, const int32_t* nm,
+                      const fcd_theta* theta_host, double* out18, double* ws, void* stream);
 
 /* ------------------------------------------------------- materialised API   */
 /* The reference caches (C,H,3), (C,U,3) and (C,U,3,3) arrays and its tests

@@ -232,22 +232,39 @@ def test_cfg2_full_run_matches_reference(cfg2):
 
 
 # ------------------------------------------------------------------ fused path vs the oracle on seeded inputs
-def _oracle_state(b, bt, th, seed):
+def _oracle_state(b, bt, th, seed, peaked=False):
+    """Random posteriors; ``peaked``: most of them one-hot to rounding (q = 1.0
+    exactly, the rest ~1e-25 .. 1e-40), as they are after an EM iteration --
+    this is what sends the kernels down their T1 / T2 tiers."""
     (C, H) = b.shape
     U = bt.shape[1]
     N = int(O.C_to_N(C))
     rng = np.random.RandomState(seed)
-    lq_R = np.log(rng.dirichlet([1, 1], size=(N, U)))
-    lq_F = np.log(rng.dirichlet([1, 1, 1], size=(C, 1)))
-    return N, H, U, lq_F, lq_R
+    q_R = rng.dirichlet([1, 1], size=(N, U))
+    q_F = rng.dirichlet([1, 1, 1], size=(C, 1))
+    if peaked:
+        hot = rng.rand(N, U) < 0.9
+        one = (rng.rand(N, U) < 0.15).astype(int)
+        pk = np.full((N, U, 2), 1e-25)
+        pk[np.arange(N)[:, None], np.arange(U)[None, :], one] = 1.0
+        q_R[hot] = pk[hot]
+        hotF = rng.rand(C) < 0.9
+        kk = rng.randint(0, 3, size=C)
+        pkF = np.full((C, 1, 3), 1e-30)
+        pkF[np.arange(C), 0, kk] = 1.0
+        pkF[np.arange(C), 0, (kk + 1) % 3] = 1e-40
+        q_F[hotF] = pkF[hotF]
+    return N, H, U, np.log(q_F), np.log(q_R)
 
 
-@pytest.mark.parametrize("N,H,U", [(3, 1, 1), (4, 2, 3), (7, 5, 9), (10, 20, 20), (33, 17, 31), (40, 64, 128)])
+@pytest.mark.parametrize("N,H,U", [(3, 1, 1), (4, 2, 3), (7, 5, 9), (10, 20, 20), (33, 17, 31), (40, 64, 128),
+                                   (24, 8, 300)])
 @pytest.mark.parametrize("lookup", ["reference", "symmetric"])
-def test_fused_steps_vs_oracle(N, H, U, lookup):
+@pytest.mark.parametrize("peaked", [False, True])
+def test_fused_steps_vs_oracle(N, H, U, lookup, peaked):
     th = O.Theta() if (N % 2) else O.Theta.ideal()
     (_, _, _, _, b, bt) = O.sample(th, N, H, U, np.random.RandomState(N))
-    (N, H, U, lq_F, lq_R) = _oracle_state(b, bt, th, N + 1)
+    (N, H, U, lq_F, lq_R) = _oracle_state(b, bt, th, N + 1, peaked)
     (lpB, pBt, lM) = O.update_lps(b, bt, th)
     model = fcdiff.UnsharedRegionModel()
     (model.pi, model.eta, model.epsilon) = (th.pi, th.eta, th.epsilon)
@@ -281,6 +298,37 @@ def test_fused_steps_vs_oracle(N, H, U, lookup):
         (fo, go) = O.elm_objective_and_grad(pBt, np.exp(exp_F), np.exp(exp_R), x)
         nptest.assert_allclose(f, fo, rtol=1e-10)
         nptest.assert_allclose(grad, go, rtol=1e-8, atol=1e-8 * max(1.0, np.abs(go).max()))
+    # K3c sufficient statistics for mu / sigma
+    mom = fit._state_moments()
+    momo = O.state_moments(b, bt, th, np.exp(exp_F), np.exp(exp_R))
+    nptest.assert_allclose(mom, momo, rtol=1e-9, atol=1e-9 * np.abs(momo).max())
+
+
+def test_mu_sigma_update_vs_oracle_and_lowers_energy():
+    """mu / sigma re-estimation (disabled in the reference, fit.py:232-237): the
+    GPU fit with ``update_mu_sigma`` follows the oracle's trajectory, and the
+    generalised-EM step never raises the free energy."""
+    th_true = O.Theta()
+    (_, _, _, _, b, bt) = O.sample(th_true, 16, 30, 25, np.random.RandomState(11))
+    model = fcdiff.UnsharedRegionModel()
+    model.mu = np.array([-0.2, 0.02, 0.25])
+    model.sigma = np.array([0.04, 0.05, 0.07])
+    fit = _fit_for(b, bt, model)
+    fit.update_mu_sigma = True
+    fit.edge_lookup = "symmetric"    # a true coordinate descent (the reference's lookup quirk is not, SURVEY 0.3)
+    fit.max_iters = 4
+    fit.rel_tol = -1.0               # run all iterations
+    fit.run()
+    tho = O.Theta(mu=(-0.2, 0.02, 0.25), sigma=(0.04, 0.05, 0.07))
+    out = O.run(b, bt, tho, max_iters=4, rel_tol=-1.0, update_mu_sigma=True, edge_lookup="symmetric")
+    nptest.assert_allclose(fit.energy, out["energy"], rtol=1e-6)
+    nptest.assert_allclose(fit.model.mu, tho.mu, rtol=1e-6, atol=1e-9)
+    nptest.assert_allclose(fit.model.sigma, tho.sigma, rtol=1e-6)
+    nptest.assert_allclose([fit.model.pi, fit.model.eta, fit.model.epsilon], [tho.pi, tho.eta, tho.epsilon], rtol=1e-6)
+    assert np.all(np.diff(fit.energy) < 0)
+    # the re-estimated parameters moved towards the generating ones
+    assert np.abs(fit.model.mu - th_true.mu).max() < 0.02
+    assert np.abs(fit.model.sigma - th_true.sigma).max() < 0.01
 
 
 def test_full_run_symmetric_lookup_vs_oracle():
@@ -370,52 +418,65 @@ def test_config3_properties(N, H, U):
     nptest.assert_array_equal(fit2._lq_F, fit._lq_F)
     nptest.assert_array_equal(fit2._lq_R, fit._lq_R)
     assert fit2.energy == fit.energy
-    # -- shard additivity of K3b / K4: sum over 3 ragged edge shards == whole
+    # -- shard additivity of K3b (objective, gradient, theta-free part): sum over 3 ragged edge shards == whole
     inp = fit._ensure_cache()
     (lqF, qF) = fit._mF.get_dev()
     (lqR, qR) = fit._mR.get_dev()
+    (fstate, rstate) = (fit._mF.get_state(), fit._mR.get_state())
     th = fit._theta()
     ws = _dev.workspace()
-    P = inp['pitchU']
+    (P, pitch, pitchS) = (inp['P'], inp['pitchU'], rstate.shape[1])
 
-    def energy_terms(a, e):
-        out = _dev.empty((6,))
-        _lib.check(lib.fcd_energy_terms(
-            _dev.ptr(inp['S1'][a:]), _dev.ptr(inp['S2'][a:]), H, _dev.ptr(inp['Ea'][a:]), _dev.ptr(inp['Eb'][a:]),
-            _dev.ptr(inp['Tm'][a:]), e - a, U, P, _dev.ptr(lqF[a * 3:]), _dev.ptr(qF[a * 3:]), _dev.ptr(lqR),
-            _dev.ptr(qR), N, a, ctypes.byref(th), None, _dev.ptr(out), _dev.ptr(ws), _dev.stream()))
+    def elm(a, e, fst=None, rst=None, grad=1):
+        fst = fstate if fst is None else fst
+        rst = rstate if rst is None else rst
+        out = _dev.empty((4,))
+        _lib.check(lib.fcd_elm_obj_grad(
+            _dev.ptr(P[0, a:]), C * pitch, e - a, U, pitch, _dev.ptr(qF[a * 3:]), _dev.ptr(fst[a:]), _dev.ptr(qR),
+            _dev.ptr(rst), pitchS, N, _dev.ptr(inp['nm'][a:]), ctypes.byref(th), grad, _dev.ptr(out), _dev.ptr(ws),
+            _dev.stream()))
+        _lib.check(lib.fcd_elm_const(
+            _dev.ptr(inp['L'][a:]), e - a, U, pitch, _dev.ptr(qF[a * 3:]), _dev.ptr(fst[a:]), _dev.ptr(qR),
+            _dev.ptr(rst), pitchS, N, _dev.ptr(inp['nm'][a:]), _dev.ptr(out[3:]), _dev.ptr(ws), _dev.stream()))
         return _dev.download(out)
 
-    w = energy_terms(0, C)
+    w = elm(0, C)
     cuts = [0, 1234, 40001, C]
-    parts = sum(energy_terms(a, e) for (a, e) in zip(cuts[:-1], cuts[1:]))
-    nptest.assert_allclose(parts[[0, 1, 3, 4]], w[[0, 1, 3, 4]], rtol=1e-12)
-    nptest.assert_allclose(parts[[2, 5]] / 3, w[[2, 5]], rtol=1e-12)     # q_R-only terms are complete per shard
-    # -- the energy from a reused K3b evaluation equals the energy from a fresh K4 pass
-    nptest.assert_allclose(energy_terms(0, C)[3], fit._energy_terms()[3], rtol=1e-13)
+    parts = sum(elm(a, e) for (a, e) in zip(cuts[:-1], cuts[1:]))
+    gtol = 1e-13 * abs(w[0])              # the gradient is a cancelling sum of terms of the objective's size
+    nptest.assert_allclose(parts[[0, 3]], w[[0, 3]], rtol=1e-12)
+    nptest.assert_allclose(parts[1:3], w[1:3], rtol=0, atol=gtol)
+    # -- tiers: with every peak state forced to "not peaked" the kernels take the reference's
+    #    nine-log form for every element; the tiered result must agree to rounding
+    f_mixed = torch.full_like(fstate, 3)
+    r_mixed = rstate.clone()
+    r_mixed[r_mixed < 2] = 2
+    assert float((fstate < 3).float().mean()) > 0.99 and float((rstate < 2).float().mean()) > 0.5
+    for (fs_, rs_) in ((f_mixed, r_mixed), (fstate, r_mixed), (f_mixed, rstate)):
+        v = elm(0, C, fs_, rs_)
+        nptest.assert_allclose(v[[0, 3]], w[[0, 3]], rtol=1e-12)
+        nptest.assert_allclose(v[1:3], w[1:3], rtol=0, atol=gtol)
+    nptest.assert_allclose(elm(0, C, f_mixed, r_mixed, grad=0)[[0, 3]], w[[0, 3]], rtol=1e-12)
+    # -- the energy from a reused K3b evaluation equals the energy from a fresh pass
     fit.reuse_evaluations = False
     e_fresh = fit._eval_energy()
     fit.reuse_evaluations = True
     nptest.assert_allclose(fit._eval_energy(), e_fresh, rtol=1e-13)
     nptest.assert_allclose(fit.energy[-1], e_fresh, rtol=1e-13)
-    # -- K2 on a shard equals the slice of the whole; K2 from reused per-edge sums equals a fresh pass
+    nptest.assert_allclose(fit._energy_terms()[3], w[0] + w[3], rtol=1e-12)
+    # -- K2 on a shard equals the slice of the whole; tiered K2 equals the all-deferred form
     (a, e) = (40001, C)
-    qR_prev = _dev.upload(np.full((N, U, 2), 0.5).reshape(-1))
 
-    def estep(a, e):
+    def estep(a, e, rst):
         lq = _dev.empty(((e - a) * 3,))
-        _lib.check(lib.fcd_estep_qF(_dev.ptr(inp['S1'][a:]), _dev.ptr(inp['S2'][a:]), H, _dev.ptr(inp['Ea'][a:]),
-                                    _dev.ptr(inp['Eb'][a:]), e - a, U, P, _dev.ptr(qR_prev), N, a,
+        _lib.check(lib.fcd_estep_qF(_dev.ptr(inp['S1'][a:]), _dev.ptr(inp['S2'][a:]), H, _dev.ptr(P[0, a:]), C * pitch,
+                                    e - a, U, pitch, _dev.ptr(qR), _dev.ptr(rst), pitchS, N, _dev.ptr(inp['nm'][a:]),
                                     ctypes.byref(th), _dev.ptr(lq), None, _dev.stream()))
         return _dev.download(lq)
 
-    nptest.assert_array_equal(estep(a, e), estep(0, C)[a * 3:])
-    assert fit._find_eval(need_F=False) is not None
-    fit._update_lq_F()                       # finish kernel from the cached per-edge sums
-    lq_reused = fit._lq_F.copy()
-    fit.reuse_evaluations = False
-    fit._update_lq_F()                       # full K2 pass
-    nptest.assert_allclose(lq_reused, fit._lq_F, rtol=1e-12, atol=1e-12)
+    whole = estep(0, C, rstate)
+    nptest.assert_array_equal(estep(a, e, rstate), whole[a * 3:])
+    nptest.assert_allclose(estep(0, C, r_mixed), whole, rtol=1e-12, atol=1e-9)
 
 
 # ------------------------------------------------------------------ kernel variants behind the C-ABI
@@ -447,57 +508,37 @@ def test_safe_variant_outside_log_table_range():
     nptest.assert_allclose(grad, go, rtol=1e-7)
 
 
-def test_unaligned_odd_pitch_through_the_c_abi():
-    """Direct C-ABI calls with an odd row pitch and 8-byte-aligned planes take the
-    scalar-load kernels; results must equal the aligned 128-bit path bit for bit
-    up to the order of the per-lane sums."""
+def test_misaligned_planes_are_rejected_by_the_c_abi():
+    """The plane kernels use 128-bit loads: an odd pitch or an 8-byte-aligned
+    plane must fail loudly (error code + message), not read garbage."""
     import ctypes
     from fcdiff_b200 import _dev
     lib = _lib.load()
     (N, H, U) = (12, 7, 13)
     C = N * (N - 1) // 2
-    th0 = O.Theta()
-    (_, _, _, _, b, bt) = O.sample(th0, N, H, U, np.random.RandomState(4))
+    (_, _, _, _, b, bt) = O.sample(O.Theta(), N, H, U, np.random.RandomState(4))
     fit = _fit_for(b, bt)
     fit._init_lps(N, H, U)
     fit._update_lps()
-    rng = np.random.RandomState(5)
-    fit._lq_R = np.log(rng.dirichlet([1, 1], size=(N, U)))
-    fit._lq_F = np.log(rng.dirichlet([1, 1, 1], size=(C, 1)))
-    ref_obj = fit._objective([0.3, 0.03])
-    fit._update_lq_F()
-    ref_lqF = fit._lq_F.copy()
-    inp = fit._in
-    # rebuild the planes with pitch U (odd) at an odd 8-byte offset
-    th = fit._theta()
-    btd = _dev.upload(bt)
-    buf = [_dev.empty((C * U + 1,)) for _ in range(3)]
-    (Ea, Eb, Tm) = [t[1:] for t in buf]
-    _lib.check(lib.fcd_gauss_cache(_dev.ptr(btd), C, U, U, ctypes.byref(th), _dev.ptr(Ea), _dev.ptr(Eb),
-                                   _dev.ptr(Tm), _dev.stream()))
+    inp = fit._ensure_cache()
+    assert inp['pitchU'] == U + 1                      # odd U is padded to an even pitch
+    (_, qF) = fit._mF.get_dev()
     (_, qR) = fit._mR.get_dev()
-    fit._lq_F = np.log(rng.dirichlet([1, 1, 1], size=(C, 1)))       # any q_F; K2 does not read it
-    lqF = _dev.empty((C * 3,))
-    _lib.check(lib.fcd_estep_qF(_dev.ptr(inp['S1']), _dev.ptr(inp['S2']), H, _dev.ptr(Ea), _dev.ptr(Eb), C, U, U,
-                                _dev.ptr(qR), N, 0, ctypes.byref(th), _dev.ptr(lqF), None, _dev.stream()))
-    nptest.assert_allclose(_dev.download(lqF).reshape(C, 1, 3), ref_lqF, rtol=1e-12, atol=1e-12)
-    fit2 = _fit_for(b, bt)
-    fit2._init_lps(N, H, U)
-    fit2._update_lps()
-    rng = np.random.RandomState(5)
-    fit2._lq_R = np.log(rng.dirichlet([1, 1], size=(N, U)))
-    fit2._lq_F = np.log(rng.dirichlet([1, 1, 1], size=(C, 1)))
-    (_, qF2) = fit2._mF.get_dev()
-    (_, qR2) = fit2._mR.get_dev()
-    th2 = fit2._theta()
-    out = _dev.empty((4,))
-    A = _dev.empty((C * 3,))
-    _lib.check(lib.fcd_elm_obj_grad(_dev.ptr(Ea), _dev.ptr(Eb), _dev.ptr(Tm), C, U, U, _dev.ptr(qF2), _dev.ptr(qR2),
-                                    N, 0, ctypes.byref(th2), 1, _dev.ptr(A), _dev.ptr(out),
-                                    _dev.ptr(_dev.workspace()), _dev.stream()))
-    o = _dev.download(out)
-    nptest.assert_allclose(-(o[0] + o[3]), ref_obj[0], rtol=1e-13)
-    nptest.assert_allclose(o[1:3], ref_obj[1], rtol=1e-11)
+    (fstate, rstate) = (fit._mF.get_state(), fit._mR.get_state())
+    th = fit._theta()
+    out = _dev.empty((3,))
+
+    def call(P, pitch):
+        return lib.fcd_elm_obj_grad(_dev.ptr(P), C * pitch, C, U, pitch, _dev.ptr(qF), _dev.ptr(fstate), _dev.ptr(qR),
+                                    _dev.ptr(rstate), rstate.shape[1], N, _dev.ptr(inp['nm']), ctypes.byref(th), 1,
+                                    _dev.ptr(out), _dev.ptr(_dev.workspace()), _dev.stream())
+
+    assert call(inp['P'], inp['pitchU']) == 0
+    assert call(inp['P'], U) != 0                      # odd pitch
+    assert b"aligned" in lib.fcd_last_error()
+    assert call(inp['P'].view(-1)[1:], inp['pitchU']) != 0      # 8-byte aligned base
+    with pytest.raises(_lib.FcdError):
+        _lib.check(call(inp['P'], U), "fcd_elm_obj_grad")
 
 
 def test_evaluation_reuse_is_invalidated_by_assignments():
@@ -508,9 +549,9 @@ def test_evaluation_reuse_is_invalidated_by_assignments():
     fit.run()
     e1 = list(fit.energy)
     lqF1 = fit._lq_F.copy()
-    assert fit._find_eval(need_F=True) is not None
+    assert fit._find_eval() is not None
     fit._lq_R = fit._lq_R.copy()                 # any assignment bumps the version
-    assert fit._find_eval(need_F=False) is None
+    assert fit._find_eval() is None
     fit2 = _fit_for(b, bt, eta_shift=0.1)
     fit2.max_iters = 2
     fit2.reuse_evaluations = False
