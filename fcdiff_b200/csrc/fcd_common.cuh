@@ -207,36 +207,42 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 // ---------------------------------------------------------------- tiered streaming walker
 // The plane kernels are HBM-streaming with a few fp64 instructions per element,
 // so the bytes in flight must not be limited by registers: the rows are staged
-// through shared memory by the TMA unit.  One CTA per SM: NCW consumer warps
-// and one producer warp.  Consumer warp g (grid-wide index) owns the edge rows
-// c = g, g + G, ...; a row is cut into segments of SEG patients.  Producer lane
-// w feeds the private ring of consumer warp w (D stages; full / empty
-// mbarriers): per segment one 1-D bulk copy per plane (NPL planes starting at
+// through shared memory by the TMA unit.  One persistent CTA of NCW warps per
+// SM.  Warp g (grid-wide index) owns the edge rows c = g, g + G, ...; a row is cut
+// into segments of SEG patients.  Every warp runs its own ring of D stages: lane
+// 0 issues, per segment, one 1-D bulk copy per plane (NPL planes starting at
 // plane fstate[c] when USE_K) and one for each of the two regions' peak-state
-// rows, plus a descriptor {k, n | m << 16}.  The producer never blocks: every
-// round each lane polls its ring's empty barrier once (mbarrier.test_wait).
-//   live(pv, l, on)              T1 body, called for both elements of a 64-patient chunk by
-//                                all lanes; `on` is false for deferred / padding slots;
-//   deferred(c, u, n, m, k, ok)  dense evaluation of 32 queued elements (T2), ONE call site;
+// rows, all completing on the stage's mbarrier, and stores {k, n | m << 16} beside
+// them; after a stage has been consumed (by the same warp: no "empty" barrier is
+// needed) the segment D steps ahead is issued into it.
+//   live(pv, lp, e)              T1 body for element e (0 / 1) of a 64-patient chunk, all lanes,
+//                                branch-free: lp = l* in 0..2, or 3 for deferred / padding
+//                                slots (the kernels map 3 to constants that contribute 0);
+//                                e selects one of two independent accumulator sets (ILP);
+//   dload(c, u, n, m, k, ok)     loads the operands of one queued element (T2) and returns
+//   dcompute(ops)                them; evaluation of up to 4 x 32 queued elements at a time,
+//                                all loads issued before the first evaluation;
 //   full(c, n, m, u0, u1)        rows with fstate == 3 (T3), patients [u0, u1), from global;
 //   row_end(c)                   after the last segment of a row (its deferred elements
 //                                have been evaluated when ROW_DRAIN).
 // Requirements: planes 16-byte aligned with even pitchU and planeStride, pitchS a
-// multiple of 16 with rstate == 4 in [U, pitchS), C < 2^29.
+// multiple of 256 with rstate == 4 in [U, pitchS), U < 65536, fewer than 65536 rows
+// per warp.
 template <int NPL, int SEG>
 struct StreamGeom {
     static constexpr int kStageBytes = NPL * SEG * 8 + 2 * SEG;
-    static constexpr int kQueueSlots = 256;                  // >= 31 + SEG deferred elements per warp (int2 each)
-    static_assert(SEG % 64 == 0 && SEG + 31 <= kQueueSlots, "bad segment");
-    // bytes of dynamic shared memory after the log table, for NCW consumer warps and D stages
+    static constexpr int kDrainAt = 96;                      // queued elements that trigger an evaluation (<= 4 x 32)
+    static constexpr int kQueueSlots = SEG + kDrainAt <= 256 ? 256 : 512;    // >= kDrainAt - 1 + SEG entries (4 B each)
+    static_assert(SEG % 64 == 0 && SEG + kDrainAt - 1 <= kQueueSlots, "bad segment");
+    // bytes of dynamic shared memory after the log table, for ncw warps and d stages
     static constexpr size_t bytes(int ncw, int d) {
-        return (size_t)ncw * ((size_t)kQueueSlots * 8 + (size_t)d * (kStageBytes + 16 + 16));
+        return (size_t)ncw * ((size_t)kQueueSlots * 4 + (size_t)d * (kStageBytes + 16 + 16));
     }
 };
 
-constexpr int kStreamWarps = 15;                             // consumer warps per CTA (+1 producer warp)
-constexpr int kStreamThreads = (kStreamWarps + 1) * 32;
-constexpr size_t kSmemBudget = 224 * 1024;                   // dynamic shared memory of one CTA (1 CTA / SM)
+constexpr int kStreamWarps = 16;
+constexpr int kStreamThreads = kStreamWarps * 32;
+constexpr size_t kSmemBudget = 226 * 1024;                   // dynamic shared memory of one CTA (1 CTA / SM)
 
 // Ring depth that fits next to `other` bytes (log table) in the CTA's shared memory; 0 if none does.
 template <int NPL, int SEG>
@@ -247,107 +253,94 @@ inline int stream_depth(size_t other) {
     return 0;
 }
 
-template <int NPL, int SEG, int NCW, bool ROW_DRAIN, bool USE_K, class LiveFn, class DeferredFn, class FullFn,
-          class RowEndFn>
+template <int NPL, int SEG, int NCW, bool ROW_DRAIN, bool USE_K, class LiveFn, class DLoadFn, class DComputeFn,
+          class FullFn, class RowEndFn>
 __device__ __forceinline__ void stream_tiered(const double* __restrict__ P, int64_t planeStride,
                                               int64_t C, int U, int64_t pitchU,
                                               const uint8_t* __restrict__ fstate,
                                               const uint8_t* __restrict__ rstate, int64_t pitchS,
                                               const int32_t* __restrict__ nm, unsigned char* smem, int D,
-                                              LiveFn&& live, DeferredFn&& deferred, FullFn&& full,
-                                              RowEndFn&& row_end) {
+                                              LiveFn&& live, DLoadFn&& dload, DComputeFn&& dcompute,
+                                              FullFn&& full, RowEndFn&& row_end) {
     using G = StreamGeom<NPL, SEG>;
+    static_assert(256 % SEG == 0, "state rows are padded to a multiple of 256");
     constexpr int QS = G::kQueueSlots;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int2* queues = reinterpret_cast<int2*>(smem);
-    unsigned char* rings = smem + (size_t)NCW * QS * 8;
-    int4* descs = reinterpret_cast<int4*>(rings + (size_t)NCW * D * G::kStageBytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(descs + NCW * D);          // [w][d][full, empty]
+    uint32_t* queue = reinterpret_cast<uint32_t*>(smem) + warp * QS;
+    unsigned char* ring = smem + (size_t)NCW * QS * 4 + (size_t)warp * D * G::kStageBytes;
+    int4* descs = reinterpret_cast<int4*>(smem + (size_t)NCW * QS * 4 + (size_t)NCW * D * G::kStageBytes) + warp * D;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)NCW * QS * 4 +
+                                                 (size_t)NCW * D * (G::kStageBytes + 16)) + warp * D;
     // the rings start zeroed: lanes beyond the copied bytes of a short segment read
     // stale but valid responsibilities (their contribution is masked)
-    for (int i = threadIdx.x; i < NCW * D * G::kStageBytes / 16; i += blockDim.x)
-        reinterpret_cast<int4*>(rings)[i] = make_int4(0, 0, 0, 0);
-    if (threadIdx.x < NCW * D) {
-        mbar_init(bars + 2 * threadIdx.x, 1);
-        mbar_init(bars + 2 * threadIdx.x + 1, 1);
-    }
+    for (int i = lane; i < D * G::kStageBytes / 16; i += 32) reinterpret_cast<int4*>(ring)[i] = make_int4(0, 0, 0, 0);
+    if (lane < D) mbar_init(bars + lane, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
+    __syncwarp();
 
     const int nseg = (U + SEG - 1) / SEG;
     const int64_t nW = (int64_t)gridDim.x * NCW;
+    const int64_t c_first = (int64_t)blockIdx.x * NCW + warp;
 
-    if (warp == NCW) {
-        // ------------------------------------------------------------ producer warp
-        const int w = lane;
-        int64_t c = (int64_t)blockIdx.x * NCW + w;
-        bool active = (w < NCW) && (c < C);
-        int s = 0, it = 0;
-        int cur_nm = 0, cur_k = 0, nxt_nm = 0, nxt_k = 0;
-        if (active) {
-            cur_nm = __ldg(nm + c);
-            cur_k = USE_K ? (int)__ldg(fstate + c) : 0;
-            if (c + nW < C) {
-                nxt_nm = __ldg(nm + c + nW);
-                nxt_k = USE_K ? (int)__ldg(fstate + c + nW) : 0;
-            }
+    // ---- issue side (warp-uniform state; lane 0 talks to the TMA unit)
+    int64_t pc = c_first;
+    int ps = 0, pit = 0;
+    int cur_nm = 0, cur_k = 0, nxt_nm = 0, nxt_k = 0;
+    if (pc < C) {
+        cur_nm = __ldg(nm + pc);
+        cur_k = USE_K ? (int)__ldg(fstate + pc) : 0;
+        if (pc + nW < C) {
+            nxt_nm = __ldg(nm + pc + nW);
+            nxt_k = USE_K ? (int)__ldg(fstate + pc + nW) : 0;
         }
-        while (__any_sync(0xffffffffu, active)) {
-            bool progress = false;
-            if (active) {
-                const int d = it % D;
-                uint64_t* fullb = bars + 2 * (w * D + d);
-                if (mbar_test(fullb + 1, ((it / D) & 1) ^ 1)) {
-                    descs[w * D + d] = make_int4(cur_k, cur_nm, 0, 0);
-                    const int u0 = s * SEG;
-                    const int np = (int)(pitchU - u0 < SEG ? pitchU - u0 : SEG);
-                    const int ns = (int)(pitchS - u0 < SEG ? pitchS - u0 : SEG);
-                    const bool planes = cur_k < 3;
-                    mbar_expect_tx(fullb, (uint32_t)(2 * ns + (planes ? NPL * np * 8 : 0)));
-                    unsigned char* st = rings + (size_t)(w * D + d) * G::kStageBytes;
-                    if (planes) {
-                        const double* src = P + (int64_t)cur_k * planeStride + c * pitchU + u0;
-#pragma unroll
-                        for (int i = 0; i < NPL; ++i)
-                            tma_load_1d(st + i * SEG * 8, src + i * planeStride, (uint32_t)(np * 8), fullb);
-                    }
-                    tma_load_1d(st + NPL * SEG * 8, rstate + (int64_t)(cur_nm & 0xffff) * pitchS + u0, (uint32_t)ns,
-                                fullb);
-                    tma_load_1d(st + NPL * SEG * 8 + SEG, rstate + (int64_t)((cur_nm >> 16) & 0xffff) * pitchS + u0,
-                                (uint32_t)ns, fullb);
-                    ++it;
-                    progress = true;
-                    if (++s == nseg) {
-                        s = 0;
-                        c += nW;
-                        active = c < C;
-                        cur_nm = nxt_nm;
-                        cur_k = nxt_k;
-                        if (c + nW < C) {
-                            nxt_nm = __ldg(nm + c + nW);
-                            nxt_k = USE_K ? (int)__ldg(fstate + c + nW) : 0;
-                        }
-                    }
-                }
-            }
-            if (!__any_sync(0xffffffffu, progress)) __nanosleep(64);      // every ring is full: yield the issue slots
-        }
-        return;
     }
+    auto issue = [&]() {
+        if (pc >= C) return;
+        const int d = pit % D;
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the warp's reads of this slot are done
+            descs[d] = make_int4(cur_k, cur_nm, 0, 0);
+            const int u0 = ps * SEG;
+            const int np = (int)(pitchU - u0 < SEG ? pitchU - u0 : SEG);
+            constexpr int ns = SEG;                                   // pitchS is a multiple of SEG
+            const bool planes = cur_k < 3;
+            mbar_expect_tx(bars + d, (uint32_t)(2 * ns + (planes ? NPL * np * 8 : 0)));
+            unsigned char* st = ring + (size_t)d * G::kStageBytes;
+            if (planes) {
+                const double* src = P + (int64_t)cur_k * planeStride + pc * pitchU + u0;
+#pragma unroll
+                for (int i = 0; i < NPL; ++i)
+                    tma_load_1d(st + i * SEG * 8, src + i * planeStride, (uint32_t)(np * 8), bars + d);
+            }
+            tma_load_1d(st + NPL * SEG * 8, rstate + (int64_t)(cur_nm & 0xffff) * pitchS + u0, (uint32_t)ns, bars + d);
+            tma_load_1d(st + NPL * SEG * 8 + SEG, rstate + (int64_t)((cur_nm >> 16) & 0xffff) * pitchS + u0,
+                        (uint32_t)ns, bars + d);
+        }
+        ++pit;
+        if (++ps == nseg) {
+            ps = 0;
+            pc += nW;
+            cur_nm = nxt_nm;
+            cur_k = nxt_k;
+            if (pc + nW < C) {
+                nxt_nm = __ldg(nm + pc + nW);
+                nxt_k = USE_K ? (int)__ldg(fstate + pc + nW) : 0;
+            }
+        }
+    };
+    for (int i = 0; i < D; ++i) issue();
 
-    // ---------------------------------------------------------------- consumer warps
-    int2* queue = queues + warp * QS;
+    // ---- consume side
     const unsigned lt = (1u << lane) - 1u;
-    int qhead = 0, qtail = 0, it = 0;
-    for (int64_t c = (int64_t)blockIdx.x * NCW + warp; c < C; c += nW) {
+    int qhead = 0, qtail = 0, it = 0, row = 0;
+    for (int64_t c = c_first; c < C; c += nW, ++row) {
         for (int s = 0; s < nseg; ++s, ++it) {
             const int d = it % D;
-            uint64_t* fullb = bars + 2 * (warp * D + d);
-            mbar_wait(fullb, (it / D) & 1);
-            const int4 ds = descs[warp * D + d];
+            mbar_wait(bars + d, (it / D) & 1);
+            const int4 ds = descs[d];
             const int k = ds.x, n = ds.y & 0xffff, m = (ds.y >> 16) & 0xffff;
-            const unsigned char* st = rings + (size_t)(warp * D + d) * G::kStageBytes;
+            const unsigned char* st = ring + (size_t)d * G::kStageBytes;
             if (USE_K && k == 3) {
                 const int u1 = (s + 1) * SEG < U ? (s + 1) * SEG : U;
                 full(c, n, m, s * SEG, u1);
@@ -367,39 +360,49 @@ __device__ __forceinline__ void stream_tiered(const double* __restrict__ P, int6
                         for (int e = 0; e < 2; ++e) {
                             const int sn = (sn2 >> (8 * e)) & 0xff;
                             const int sm = (sm2 >> (8 * e)) & 0xff;
-                            const int o = (u0 + 2 * lane + e < U) ? (sn | sm) : kStateDead;   // stale bytes past the copy
-                            const bool on = o < 2;
-                            const bool mixed = (o & 6) == 2;          // a region is not peaked (and no padding)
-                            const int l = on ? (sn == sm ? sn : 2) : 0;
+                            const int o = sn | sm;                    // 0/1 peaked pair, 2/3 mixed, >= 4 padding
+                            const int lp = o < 2 ? (((sn ^ sm) << 1) + (sn & sm)) : 3;
+                            const bool mixed = (o & 6) == 2;
                             double pv[NPL];
 #pragma unroll
                             for (int i = 0; i < NPL; ++i) pv[i] = e ? p2[i].y : p2[i].x;
-                            if (__any_sync(0xffffffffu, on)) live(pv, l, on);
-                            const unsigned bal = __ballot_sync(0xffffffffu, mixed);
-                            if (bal) {
-                                if (mixed)
-                                    queue[(qtail + __popc(bal & lt)) & (QS - 1)] =
-                                        make_int2((int)c | (k << 29), u0 + 2 * lane + e);
-                                qtail += __popc(bal);
-                            }
+                            live(pv, lp, e);
+                            const unsigned bal = __ballot_sync(0xffffffffu, mixed);       // branch-free push
+                            if (mixed)
+                                queue[(qtail + __popc(bal & lt)) & (QS - 1)] =
+                                    ((uint32_t)row << 16) | (uint32_t)(u0 + 2 * lane + e);
+                            qtail += __popc(bal);
                         }
                     }
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(fullb + 1);                    // stage free for the producer
+            issue();                                                  // refill this stage D segments ahead
             const bool row_done = s == nseg - 1;
-            const int at_least = (row_done && (ROW_DRAIN || c + nW >= C)) ? 1 : 32;
-            while (qtail - qhead >= at_least) {                       // the one deferred() call site
-                const int idx = qhead + lane;
-                const bool ok = idx < qtail;
-                int2 e = make_int2(0, 0);
-                if (ok) e = queue[idx & (QS - 1)];
-                const int64_t ce = e.x & 0x1fffffff;
-                int v = 0;
-                if (ok) v = __ldg(nm + ce);
-                deferred(ce, e.y, v & 0xffff, (v >> 16) & 0xffff, (e.x >> 29) & 3, ok);
-                qhead = (qtail - qhead > 32) ? qhead + 32 : qtail;
+            const int at_least = (row_done && (ROW_DRAIN || c + nW >= C)) ? 1 : G::kDrainAt;
+            while (qtail - qhead >= at_least) {                       // the one deferred call site
+                const int cnt = qtail - qhead < 128 ? qtail - qhead : 128;
+                decltype(dload((int64_t)0, 0, 0, 0, 0, false)) ops[4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    if (b * 32 < cnt) {                               // warp-uniform
+                        const int idx = qhead + b * 32 + lane;
+                        const bool ok = idx < qtail;
+                        uint32_t e = 0;
+                        if (ok) e = queue[idx & (QS - 1)];
+                        const int64_t ce = c_first + (int64_t)(e >> 16) * nW;
+                        int v = 0, ke = 0;
+                        if (ok) {
+                            v = __ldg(nm + ce);
+                            if (USE_K) ke = __ldg(fstate + ce);
+                        }
+                        ops[b] = dload(ce, (int)(e & 0xffff), v & 0xffff, (v >> 16) & 0xffff, ke, ok);
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if (b * 32 < cnt) dcompute(ops[b]);
+                qhead += cnt;
                 __syncwarp();
             }
             if (row_done) row_end(c);

@@ -152,38 +152,53 @@ estep_qF_kernel(const double* __restrict__ S1, const double* __restrict__ S2,
     const int lane = threadIdx.x & 31;
     const double2* qR2 = reinterpret_cast<const double2*>(qR);
     double acc[3] = {0.0, 0.0, 0.0};
-    auto live = [&](const double (&pv)[3], int l, bool on) {
-        const double a = sel3(l, th.al), b = sel3(l, th.bl);
+    // per-l constants {a_l, b_l} of the T1 body; row 3 is neutral: log(1 + 0 p) = 0 exactly
+    __shared__ double2 s_lc[4];
+    if (threadIdx.x < 4) s_lc[threadIdx.x] = threadIdx.x < 3 ? make_double2(th.al[threadIdx.x], th.bl[threadIdx.x])
+                                                             : make_double2(1.0, 0.0);
+    __syncthreads();
+    double acc1[3] = {0.0, 0.0, 0.0};
+    auto live = [&](const double (&pv)[3], int lp, int e) {
+        const double2 k = s_lc[lp];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const double lg = fast_log<FAST>(fma(b, pv[k], a), s_tab);
-            acc[k] += on ? lg : 0.0;
-        }
+        for (int i = 0; i < 3; ++i) (e ? acc1 : acc)[i] += fast_log<FAST>(fma(k.y, pv[i], k.x), s_tab);
     };
-    auto deferred = [&](int64_t c, int u, int n, int m, int, bool ok) {
-        double w[3] = {0.0, 0.0, 0.0};
-        double p[3] = {0.0, 0.0, 0.0};
+    struct Ops {
+        double p[3];
+        double2 qn, qm;
+    };
+    auto dload = [&](int64_t c, int u, int n, int m, int, bool ok) {
+        Ops o;
+        o.p[0] = o.p[1] = o.p[2] = 0.0;
+        o.qn = o.qm = make_double2(0.0, 0.0);
         if (ok) {
-            pair_weights(__ldg(qR2 + (int64_t)n * U + u), __ldg(qR2 + (int64_t)m * U + u), w);
+            o.qn = __ldg(qR2 + (int64_t)n * U + u);
+            o.qm = __ldg(qR2 + (int64_t)m * U + u);
 #pragma unroll
-            for (int k = 0; k < 3; ++k) p[k] = ldg_stream1(P + k * planeStride + c * pitchU + u);
+            for (int k = 0; k < 3; ++k) o.p[k] = ldg_stream1(P + k * planeStride + c * pitchU + u);
         }
+        return o;
+    };
+    auto dcompute = [&](const Ops& o) {
+        double w[3];
+        pair_weights(o.qn, o.qm, w);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             double a = acc[k];
 #pragma unroll
-            for (int l = 0; l < 3; ++l) a = fma(w[l], fast_log<FAST>(mix_rel(th, l, p[k]), s_tab), a);
+            for (int l = 0; l < 3; ++l) a = fma(w[l], fast_log<FAST>(mix_rel(th, l, o.p[k]), s_tab), a);
             acc[k] = a;
         }
     };
     auto row_end = [&](int64_t c) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) acc[k] = warp_sum(acc[k]);
+        for (int k = 0; k < 3; ++k) acc[k] = warp_sum(acc[k] + acc1[k]);
         if (lane == 0) k2_finish(c, acc, S1[c], S2[c], th, lqF, qF);
         acc[0] = acc[1] = acc[2] = 0.0;
+        acc1[0] = acc1[1] = acc1[2] = 0.0;
     };
     stream_tiered<3, kK2Seg, kStreamWarps, true, false>(P, planeStride, C, U, pitchU, nullptr, rstate, pitchS, nm,
-                                                        s_stream, depth, live, deferred,
+                                                        s_stream, depth, live, dload, dcompute,
                                                         [](int64_t, int, int, int, int) {}, row_end);
 }
 
@@ -447,10 +462,10 @@ int fcd_estep_qF(const double* S1, const double* S2, int32_t H,
                  const fcd_theta* theta_host, double* lqF, double* qF, void* stream) {
     FCD_REQUIRE(theta_host != nullptr && P != nullptr && qR != nullptr && rstate != nullptr && nm != nullptr &&
                 lqF != nullptr, "fcd_estep_qF: NULL argument");
-    FCD_REQUIRE(C >= 0 && C < (1 << 29) && U >= 1 && pitchU >= U && pitchS >= U && N >= 2 && N < 65536,
+    FCD_REQUIRE(C >= 0 && U >= 1 && U < 65536 && pitchU >= U && pitchS >= U && N >= 2 && N < 65536,
                 "fcd_estep_qF: bad shape");
     FCD_REQUIRE(((reinterpret_cast<uintptr_t>(P) & 15) == 0) && pitchU % 2 == 0 && planeStride % 2 == 0 &&
-                pitchS % 16 == 0, "fcd_estep_qF: planes must be 16-byte aligned with even pitches (pitchS % 16)");
+                pitchS % 256 == 0, "fcd_estep_qF: planes must be 16-byte aligned with even pitches (pitchS % 256 == 0)");
     if (C == 0) return 0;
     const ThetaDev th = make_theta_dev(*theta_host, H);
     cudaStream_t st = (cudaStream_t)stream;

@@ -41,7 +41,7 @@ struct ElmAcc {
     double obj, ge, gh;       // objective, sum s_l w_l d_l, sum w_2 d_2
 };
 
-constexpr int kElmSeg = 128;
+constexpr int kElmSeg = 256;
 
 template <bool GRAD, bool FAST>
 __global__ void __launch_bounds__(kStreamThreads, 1)
@@ -56,33 +56,52 @@ elm_kernel(const double* __restrict__ P, int64_t planeStride, int64_t C, int U, 
     unsigned char* s_stream = reinterpret_cast<unsigned char*>(s_dyn + (FAST ? ((tab.n + 1) & ~1) : 0));
     const double sl[3] = {-1.0, 1.0, 2.0 * th.eta - 1.0};
     const double2* qR2 = reinterpret_cast<const double2*>(qR);
-    ElmAcc acc = {0.0, 0.0, 0.0};
+    ElmAcc acc = {0.0, 0.0, 0.0}, acc1 = {0.0, 0.0, 0.0};
+    // per-l constants of the T1 body {a_l, b_l, s_l, [l == 2]}; row 3 is the neutral
+    // element for deferred / padding slots: log(1 + 0 p) = 0 exactly, zero gradient weight
+    __shared__ double4 s_lc[4];
+    if (threadIdx.x < 4) {
+        const int l = threadIdx.x;
+        s_lc[l] = l < 3 ? make_double4(th.al[l], th.bl[l], sl[l], l == 2 ? 1.0 : 0.0) : make_double4(1.0, 0.0, 0.0, 0.0);
+    }
+    __syncthreads();
 
-    auto live = [&](const double (&pv)[1], int l, bool on) {
-        const double M = fma(sel3(l, th.bl), pv[0], sel3(l, th.al));
+    auto live = [&](const double (&pv)[1], int lp, int e) {
+        ElmAcc& a = e ? acc1 : acc;
+        const double4 k = s_lc[lp];
+        const double M = fma(k.y, pv[0], k.x);
         if (GRAD) {
             double rcp;
-            const double lg = fast_log_rcp<FAST>(M, s_tab, rcp);
+            a.obj += fast_log_rcp<FAST>(M, s_tab, rcp);
             const double d = mix_num(pv[0]) * rcp;
-            acc.obj += on ? lg : 0.0;
-            acc.ge = fma(on ? sel3(l, sl) : 0.0, d, acc.ge);
-            acc.gh += (on && l == 2) ? d : 0.0;
+            a.ge = fma(k.z, d, a.ge);
+            a.gh = fma(k.w, d, a.gh);
         } else {
-            const double lg = fast_log<FAST>(M, s_tab);
-            acc.obj += on ? lg : 0.0;
+            a.obj += fast_log<FAST>(M, s_tab);
         }
     };
-    auto deferred = [&](int64_t c, int u, int n, int m, int k, bool ok) {
-        double p = 0.0;
-        double w[3] = {0.0, 0.0, 0.0};
+    struct Ops {
+        double p;
+        double2 qn, qm;
+    };
+    auto dload = [&](int64_t c, int u, int n, int m, int k, bool ok) {
+        Ops o;
+        o.p = 0.0;
+        o.qn = o.qm = make_double2(0.0, 0.0);
         if (ok) {
-            p = ldg_stream1(P + k * planeStride + c * pitchU + u);
-            pair_weights(__ldg(qR2 + (int64_t)n * U + u), __ldg(qR2 + (int64_t)m * U + u), w);
+            o.p = ldg_stream1(P + k * planeStride + c * pitchU + u);
+            o.qn = __ldg(qR2 + (int64_t)n * U + u);
+            o.qm = __ldg(qR2 + (int64_t)m * U + u);
         }
-        const double num = mix_num(p);
+        return o;
+    };
+    auto dcompute = [&](const Ops& o) {
+        double w[3];
+        pair_weights(o.qn, o.qm, w);
+        const double num = mix_num(o.p);
 #pragma unroll
         for (int l = 0; l < 3; ++l) {
-            const double M = mix_rel(th, l, p);
+            const double M = mix_rel(th, l, o.p);
             if (GRAD) {
                 double rcp;
                 acc.obj = fma(w[l], fast_log_rcp<FAST>(M, s_tab, rcp), acc.obj);
@@ -121,8 +140,9 @@ elm_kernel(const double* __restrict__ P, int64_t planeStride, int64_t C, int U, 
         }
     };
     stream_tiered<1, kElmSeg, kStreamWarps, false, true>(P, planeStride, C, U, pitchU, fstate, rstate, pitchS, nm,
-                                                         s_stream, depth, live, deferred, full, [](int64_t) {});
-    double v[3] = {acc.obj, -(2.0 * th.epsilon - 1.0) * acc.gh, -acc.ge};
+                                                         s_stream, depth, live, dload, dcompute, full,
+                                                         [](int64_t) {});
+    double v[3] = {acc.obj + acc1.obj, -(2.0 * th.epsilon - 1.0) * (acc.gh + acc1.gh), -(acc.ge + acc1.ge)};
     grid_reduce_store<3, kStreamThreads>(v, ws, out);
 }
 
@@ -140,10 +160,21 @@ elm_const_kernel(const double* __restrict__ L, int64_t C, int U, int64_t pitchU,
         const double2 qn = __ldg(qR2 + (int64_t)n * U + u), qm = __ldg(qR2 + (int64_t)m * U + u);
         return (qn.x + qn.y) * (qm.x + qm.y);
     };
-    auto live = [&](const double (&pv)[1], int, bool on) { acc += on ? pv[0] : 0.0; };
-    auto deferred = [&](int64_t c, int u, int n, int m, int, bool ok) {
-        if (ok) acc = fma(wsum(n, m, u), ldg_stream1(L + c * pitchU + u), acc);
+    double acc1 = 0.0;
+    auto live = [&](const double (&pv)[1], int lp, int e) { (e ? acc1 : acc) += lp < 3 ? pv[0] : 0.0; };
+    struct Ops {
+        double w, L;
     };
+    auto dload = [&](int64_t c, int u, int n, int m, int, bool ok) {
+        Ops o;
+        o.w = o.L = 0.0;
+        if (ok) {
+            o.w = wsum(n, m, u);
+            o.L = ldg_stream1(L + c * pitchU + u);
+        }
+        return o;
+    };
+    auto dcompute = [&](const Ops& o) { acc = fma(o.w, o.L, acc); };
     auto full = [&](int64_t c, int n, int m, int u0, int u1) {
         const double qs = __ldg(qF + c * 3) + __ldg(qF + c * 3 + 1) + __ldg(qF + c * 3 + 2);
         for (int u = u0 + (threadIdx.x & 31); u < u1; u += 32)
@@ -151,8 +182,8 @@ elm_const_kernel(const double* __restrict__ L, int64_t C, int U, int64_t pitchU,
     };
     stream_tiered<1, kElmSeg, kStreamWarps, false, true>(L, 0, C, U, pitchU, fstate, rstate, pitchS, nm,
                                                          reinterpret_cast<unsigned char*>(s_dyn), depth,
-                                                         live, deferred, full, [](int64_t) {});
-    double v[1] = {acc};
+                                                         live, dload, dcompute, full, [](int64_t) {});
+    double v[1] = {acc + acc1};
     grid_reduce_store<1, kStreamThreads>(v, ws, out);
 }
 
@@ -281,14 +312,14 @@ static inline int red_grid(int64_t work_items, int items_per_block) {
 }
 
 static inline int stream_grid(int64_t C) {
-    int64_t need = (C + kStreamWarps - 1) / kStreamWarps;
+    int64_t need = (C + kStreamWarps - 1) / kStreamWarps;      // < 65536 rows per warp: C < 2^20 * grid
     if (need < 1) need = 1;
     return (int)(need < sm_count() ? need : sm_count());          // one persistent CTA per SM
 }
 
 static inline bool planes_ok(const void* a, const void* b, int64_t pitchU, int64_t planeStride, int64_t pitchS) {
     const uintptr_t al = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b);
-    return (al & 15) == 0 && pitchU % 2 == 0 && planeStride % 2 == 0 && pitchS % 16 == 0;
+    return (al & 15) == 0 && pitchU % 2 == 0 && planeStride % 2 == 0 && pitchS % 256 == 0;
 }
 
 }  // namespace fcd
@@ -314,10 +345,10 @@ int fcd_elm_obj_grad(const double* P, int64_t planeStride, int64_t C, int32_t U,
     FCD_REQUIRE(theta_host != nullptr && ws != nullptr && P != nullptr && qF != nullptr && fstate != nullptr &&
                 qR != nullptr && rstate != nullptr && nm != nullptr && out3 != nullptr,
                 "fcd_elm_obj_grad: NULL argument");
-    FCD_REQUIRE(C >= 0 && C < (1 << 29) && U >= 1 && pitchU >= U && pitchS >= U && N >= 2 && N < 65536,
+    FCD_REQUIRE(C >= 0 && U >= 1 && U < 65536 && pitchU >= U && pitchS >= U && N >= 2 && N < 65536,
                 "fcd_elm_obj_grad: bad shape");
     FCD_REQUIRE(planes_ok(P, nullptr, pitchU, planeStride, pitchS),
-                "fcd_elm_obj_grad: planes must be 16-byte aligned with even pitches");
+                "fcd_elm_obj_grad: planes must be 16-byte aligned with even pitches (pitchS % 256 == 0)");
     const ThetaDev th = make_theta_dev(*theta_host, 0);
     cudaStream_t st = (cudaStream_t)stream;
     LogTabWindow tab;
@@ -346,7 +377,7 @@ int fcd_elm_const(const double* L, int64_t C, int32_t U, int64_t pitchU,
                   int64_t pitchS, int32_t N, const int32_t* nm, double* out1, double* ws, void* stream) {
     FCD_REQUIRE(ws != nullptr && L != nullptr && qF != nullptr && fstate != nullptr && qR != nullptr &&
                 rstate != nullptr && nm != nullptr && out1 != nullptr, "fcd_elm_const: NULL argument");
-    FCD_REQUIRE(C >= 0 && C < (1 << 29) && U >= 1 && pitchU >= U && pitchS >= U && N >= 2 && N < 65536,
+    FCD_REQUIRE(C >= 0 && U >= 1 && U < 65536 && pitchU >= U && pitchS >= U && N >= 2 && N < 65536,
                 "fcd_elm_const: bad shape");
     FCD_REQUIRE(planes_ok(L, nullptr, pitchU, 0, pitchS), "fcd_elm_const: plane must be 16-byte aligned with even pitches");
     const int depth = stream_depth<1, kElmSeg>(0);

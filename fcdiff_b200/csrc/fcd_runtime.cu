@@ -80,12 +80,12 @@ bool log_table_window(const double epsl[3], const double al[3], cudaStream_t st,
     w.n = kLogTabSize;
     if (w.g == nullptr) return false;
     if (!log_table_covers(epsl, al)) return true;          // SAFE kernels: table unused
-    double ymin = 1.0, ymax = 0.0;
+    // up to y = 1: the neutral element of the branch-free T1 bodies is log(1 + 0 p) = 0
+    double ymin = 1.0;
+    const double ymax = 1.0;
     for (int l = 0; l < 3; ++l) {
         const double lo = epsl[l] < al[l] ? epsl[l] : al[l];
-        const double hi = epsl[l] < al[l] ? al[l] : epsl[l];
         if (lo < ymin) ymin = lo;
-        if (hi > ymax) ymax = hi;
     }
     auto slot = [](double y) {                              // mirrors log_reduce (fcd_math.cuh)
         const double r = 1.0 / y;

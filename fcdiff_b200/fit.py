@@ -79,7 +79,7 @@ class _Mirror(object):
 
     def get_state(self):
         """Peak states of the probabilities: (C,) bytes for a (C, 1, 3) array,
-        (N, U rounded up to 16) bytes for an (N, U, 2) array."""
+        (N, U rounded up to 256) bytes for an (N, U, 2) array."""
         if self.state is None:
             lib = _lib.load()
             (_, q) = self.get_dev()
@@ -89,7 +89,7 @@ class _Mirror(object):
                 _lib.check(lib.fcd_peak_states_F(_dev.ptr(q), C, _dev.ptr(st), _dev.stream()), "fcd_peak_states_F")
             else:
                 (N, U) = (int(self.shape[0]), int(self.shape[1]))
-                pitchS = (U + 15) // 16 * 16            # rows are moved by 16-byte-granular bulk copies
+                pitchS = (U + 255) // 256 * 256         # whole 256-byte segments are moved by TMA bulk copies
                 st = _dev.empty((N, pitchS), torch.uint8)
                 _lib.check(lib.fcd_peak_states_R(_dev.ptr(q), N, U, pitchS, _dev.ptr(st), _dev.stream()),
                            "fcd_peak_states_R")

@@ -92,7 +92,7 @@ FCD_API int fcd_resp_cache(const double* bt, int64_t C, int32_t U, int64_t pitch
 /* Peak states of the posteriors (tier selection, DESIGN.md "Tiers"):
  *   fstate[c]   = k if qF[c,k] == 1.0 and the other two <= 2^-60, else 3;
  *   rstate[n][u] = s if qR[n,u,s] == 1.0 and the other <= 2^-60, else 2;
- *                  4 in the padding columns u >= U (row pitch pitchS, a multiple of 16).
+ *                  4 in the padding columns u >= U (row pitch pitchS, a multiple of 256).
  * A term whose weight is <= 2^-60 is below the rounding error of the sums it
  * would enter and is skipped by the kernels below. */
 FCD_API int fcd_peak_states_F(const double* qF, int64_t C, uint8_t* fstate, void* stream);
