@@ -87,11 +87,17 @@ class SmallResult(object):
     def __init__(self, n):
         self.dev = torch.zeros(n, dtype=torch.float64, device=device())
         self.host = torch.zeros(n, dtype=torch.float64).pin_memory()
+        self.host_np = self.host.numpy()
+        self._args = (ctypes.c_void_p(self.host.data_ptr()), ctypes.c_void_p(self.dev.data_ptr()), 8 * n)
+        self._download = _lib.load().fcd_download
 
-    def read(self):
-        self.host.copy_(self.dev, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return self.host.numpy().copy()
+    def read(self, stream_handle=None):
+        """One asynchronous copy + one stream synchronisation, inside the library."""
+        rc = self._download(self._args[0], self._args[1], self._args[2],
+                            stream() if stream_handle is None else stream_handle)
+        if rc != 0:
+            _lib.check(rc, "fcd_download")
+        return self.host_np.copy()
 
 
 def even(n):

@@ -28,6 +28,7 @@ SIGNATURES = {
     "fcd_last_error": (c_char_p, []),
     "fcd_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "fcd_workspace_bytes": (c_int64, []),
+    "fcd_download": (c_int, [_P, _P, c_int64, _P]),
     "fcd_launch_count": (c_int64, []),
     "fcd_launch_count_reset": (None, []),
     "fcd_c_to_nm": (c_int, [c_int64, c_int64, _P, _P, _P]),

@@ -159,6 +159,17 @@ int fcd_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host) 
 
 int64_t fcd_workspace_bytes(void) { return fcd::kWsDoubles * (int64_t)sizeof(double); }
 
+int fcd_download(void* dst_host, const void* src, int64_t bytes, void* stream) {
+    if (bytes <= 0) return 0;
+    cudaError_t e = cudaMemcpyAsync(dst_host, src, (size_t)bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        fcd::set_error("fcd_download: %s", cudaGetErrorString(e));
+        return -2;
+    }
+    return 0;
+}
+
 int64_t fcd_launch_count(void) { return fcd::g_launches.load(); }
 
 void fcd_launch_count_reset(void) { fcd::g_launches.store(0); }

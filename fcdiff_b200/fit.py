@@ -36,10 +36,9 @@ the reference cannot execute:
 import ctypes
 
 import numpy as np
-import scipy.optimize
 import torch
 
-from . import _dev, _lib, util
+from . import _dev, _lib, _opt, util
 
 _LOOKUP = {"reference": 0, "symmetric": 1}
 
@@ -174,6 +173,7 @@ class UnsharedRegionFit(object):
         self._const = None            # theta-free part of E_lM for the current (q_F, q_R)
         self.reuse_evaluations = True
         self._res = {}                # reusable device / pinned-host result vectors
+        self._ctx = None              # cached argument list of the K3b evaluations
 
     # ------------------------------------------------------------------ private arrays
     @property
@@ -711,34 +711,51 @@ class UnsharedRegionFit(object):
         self._const = (ckey, float(res.read()[0]))
         return self._const[1]
 
-    def _objective(self, theta_sub, want_grad=True, name="K3b_elm_obj_grad"):
-        """(-E_lM, gradient) at theta_sub = [eta, epsilon] from one fused pass
-        over the responsibility planes (K3b)."""
-        lib = _lib.load()
+    def _objective_context(self):
+        """Everything of a K3b evaluation that does not depend on (eta, epsilon):
+        argument list, theta struct, result vector, stream, theta-free part of
+        E_lM.  Valid for one (q_F, q_R, planes) state."""
         inp = self._ensure_cache()
+        key = (self._mF.version, self._mR.version, inp['cache_key'], id(inp), id(self.profile))
+        ctx = self._ctx
+        if ctx is not None and ctx['key'] == key:
+            return ctx
         (N, H, U) = self._dims
         (c0, Cl) = (inp['c0'], inp['Cl'])
         (_, qF) = self._mF.get_dev()
         (_, qR) = self._mR.get_dev()
         (fstate, rstate) = (self._mF.get_state(), self._mR.get_state())
         th = self._theta()
+        res = self._result(3)
+        stream = _dev.stream()
+        head = (_dev.ptr(inp['P']), max(Cl, 1) * inp['pitchU'], Cl, U, inp['pitchU'],
+                _dev.ptr(qF[c0 * 3:]), _dev.ptr(fstate[c0:]), _dev.ptr(qR), _dev.ptr(rstate), rstate.shape[1],
+                N, _dev.ptr(inp['nm']), ctypes.byref(th))
+        tail = (_dev.ptr(res.dev), _dev.ptr(_dev.workspace()), stream)
+        self._ctx = dict(key=key, th=th, res=res, stream=stream, head=head, tail=tail, const=self._elm_const(inp),
+                         keep=(qF, qR, fstate, rstate), fn=_lib.load().fcd_elm_obj_grad,
+                         verF=self._mF.version, verR=self._mR.version)
+        return self._ctx
+
+    def _objective(self, theta_sub, want_grad=True, name="K3b_elm_obj_grad"):
+        """(-E_lM, gradient) at theta_sub = [eta, epsilon] from one fused pass
+        over the responsibility planes (K3b)."""
+        ctx = self._objective_context()
+        th = ctx['th']
         th.eta = float(theta_sub[0])
         th.epsilon = float(theta_sub[1])
-        const = self._elm_const(inp)
-        res = self._result(3)
         with _dev.timed(self.profile, name):
-            _lib.check(lib.fcd_elm_obj_grad(
-                _dev.ptr(inp['P']), max(Cl, 1) * inp['pitchU'], Cl, U, inp['pitchU'],
-                _dev.ptr(qF[c0 * 3:]), _dev.ptr(fstate[c0:]), _dev.ptr(qR), _dev.ptr(rstate), rstate.shape[1],
-                N, _dev.ptr(inp['nm']), ctypes.byref(th), 1 if want_grad else 0, _dev.ptr(res.dev),
-                _dev.ptr(_dev.workspace()), _dev.stream()), "fcd_elm_obj_grad")
+            rc = ctx['fn'](*ctx['head'], 1 if want_grad else 0, *ctx['tail'])
+        if rc != 0:
+            _lib.check(rc, "fcd_elm_obj_grad")
+        res = ctx['res']
         if self.shards is not None:
             self.shards.allreduce_terms(res.dev, (0, 1, 2))           # all three are edge-local partial sums
-        o = res.read()
-        elm = float(o[0]) + const
-        self._evals.append(dict(x=(th.eta, th.epsilon), verF=self._mF.version, verR=self._mR.version, elm=elm))
+        o = res.read(ctx['stream'])
+        elm = float(o[0]) + ctx['const']
+        self._evals.append(dict(x=(th.eta, th.epsilon), verF=ctx['verF'], verR=ctx['verR'], elm=elm))
         del self._evals[:-4]
-        return -elm, np.array([o[1], o[2]])
+        return -elm, o[1:3]
 
     def _update_theta_sub(self):
         """
@@ -748,20 +765,12 @@ class UnsharedRegionFit(object):
         """
         theta_sub = self._pack_theta_sub()
         eps = 1e-5
-        bnds = (
-            (eps, 1 - eps),
-            (eps, 1 - eps),
-        )
         if self._lps_state != 'derived':
             self._update_lps()
-        nfev = [0]
-
-        def fun(x):
-            nfev[0] += 1
-            return self._objective(x)
-
-        opt_result = scipy.optimize.minimize(fun, theta_sub, jac=True, method="L-BFGS-B", bounds=bnds)
-        self.n_objective_evals.append(nfev[0])
+        # scipy.optimize.minimize(..., method="L-BFGS-B", bounds=[(eps, 1 - eps)] * 2) of fit.py:228-241,
+        # driven without SciPy's Python front end (same compiled routine, same iterates: _opt.py)
+        opt_result = _opt.minimize_lbfgsb(self._objective, theta_sub, [eps, eps], [1 - eps, 1 - eps])
+        self.n_objective_evals.append(opt_result.nfev)
         self._unpack_theta_sub(opt_result.x)
 
     def _pack_theta_sub(self):

@@ -57,6 +57,10 @@ FCD_API const char* fcd_last_error(void);
 /* SM count and compute capability of the current device. */
 FCD_API int fcd_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host);
 FCD_API int64_t fcd_workspace_bytes(void);
+/* Copies `bytes` from device memory to (pinned) host memory on `stream` and
+ * waits for the stream: how the few doubles a reduction kernel leaves behind
+ * reach the host-side optimiser / convergence test. */
+FCD_API int fcd_download(void* dst_host, const void* src, int64_t bytes, void* stream);
 /* Number of kernels this library has launched in this process (bench.py's
  * `gpu_launches`), and reset. */
 FCD_API int64_t fcd_launch_count(void);

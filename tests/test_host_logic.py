@@ -142,3 +142,33 @@ def test_product_does_not_import_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(root, fn)).read()
             assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+def test_direct_lbfgsb_driver_is_bit_identical_to_scipy_minimize():
+    """fcdiff_b200/_opt.py drives scipy's compiled L-BFGS-B without the Python
+    front end; the oracle (and the reference, fit.py:239) call
+    scipy.optimize.minimize -- both must produce the same iterates."""
+    import scipy.optimize
+    from fcdiff_b200 import _opt
+    rng = np.random.RandomState(0)
+    for _ in range(25):
+        A = rng.rand(2, 2)
+        A = A @ A.T + 0.1 * np.eye(2)
+        c = rng.rand(2) * 2 - 0.5
+        sc = 10 ** rng.uniform(0, 8)
+
+        def fun(x):
+            d = x - c
+            return sc * (0.5 * d @ A @ d - 0.1 * np.sum(np.log(x))), sc * (A @ d - 0.1 / x)
+
+        x0 = rng.rand(2) * 0.8 + 0.1
+        r = _opt.minimize_lbfgsb(fun, x0, [1e-5, 1e-5], [1 - 1e-5, 1 - 1e-5])
+        n = [0]
+
+        def counted(x):
+            n[0] += 1
+            return fun(x)
+
+        r2 = scipy.optimize.minimize(counted, x0, jac=True, method="L-BFGS-B", bounds=[(1e-5, 1 - 1e-5)] * 2)
+        np.testing.assert_array_equal(r.x, r2.x)
+        assert r.nfev == n[0]
