@@ -84,9 +84,9 @@ class SmallResult(object):
     every call and a pinned host mirror, so that reading a result costs one
     asynchronous copy and one stream synchronisation (no allocation)."""
 
-    def __init__(self, n):
-        self.dev = torch.zeros(n, dtype=torch.float64, device=device())
-        self.host = torch.zeros(n, dtype=torch.float64).pin_memory()
+    def __init__(self, n, dtype=torch.float64):
+        self.dev = torch.zeros(n, dtype=dtype, device=device())
+        self.host = torch.zeros(n, dtype=dtype).pin_memory()
         self.host_np = self.host.numpy()
         self._args = (ctypes.c_void_p(self.host.data_ptr()), ctypes.c_void_p(self.dev.data_ptr()), 8 * n)
         self._download = _lib.load().fcd_download

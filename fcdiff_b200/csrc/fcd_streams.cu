@@ -1,0 +1,427 @@
+// K3b as dense streams.  Within one EM iteration the (eta, epsilon) optimiser
+// evaluates E_lM(eta, epsilon) 6-16 times with q_F, q_R and the responsibility
+// planes fixed (fcdiff/fit.py:228-241, 270-286).  Everything of an evaluation
+// that does not depend on (eta, epsilon) is therefore hoisted into ONE pass per
+// iteration, the *bucket pass*:
+//   * an element (c,u) whose edge and regions are peaked (fcd_common.cuh, "Tiers")
+//     contributes log(a_l + b_l p) for ONE (k*, l*) pair with weight 1: its p is
+//     appended to the stream G_l of its l* (three streams, 8 bytes per element);
+//   * every other element is expanded into records {p_k, w_0, w_1, w_2} with
+//     w_l = q_F[c,k] * pair weight_l (one record if the edge is peaked, three if not);
+//   * the theta-free part sum w L of E_lM is summed on the way.
+// An evaluation is then a flat reduction over the streams with warp-uniform
+// constants (a_l, b_l): no row structure, no weights, no peak-state decoding --
+// 8 bytes and ~25 instructions per edge-patient, which is what lets it run at
+// the HBM roofline.  Stream order is fixed by per-row counts and an exclusive
+// scan, so results are deterministic.
+#include "fcd_common.cuh"
+
+namespace fcd {
+
+constexpr int kBucketThreads = 256;
+
+// code of element (c,u): 0..2 = l* (both regions peaked), 3 = a region is mixed, 4 = padding
+__device__ __forceinline__ int pair_code(int sn, int sm) {
+    const int o = sn | sm;
+    return o < 2 ? (((sn ^ sm) << 1) + (sn & sm)) : ((o & 6) == 2 ? 3 : 4);
+}
+
+// Rows are handled in blocks of kRowBlock consecutive rows per CTA (one warp per
+// row, kRowBlock / 8 rows per warp), so that the position of a row in the streams
+// is (offset of its block) + (prefix inside the block): the block totals are
+// scanned by one small kernel, the in-block prefix is recomputed in shared memory
+// by the fill kernel -- no pass over per-row arrays by a single CTA.
+constexpr int kRowBlock = 64;
+
+// counts[c] = {n_0, n_1, n_2, n_records} of row c; blocktot[b] their sums over the rows of block b.
+__global__ void __launch_bounds__(kBucketThreads)
+bucket_count_kernel(const uint8_t* __restrict__ fstate, const uint8_t* __restrict__ rstate, int64_t pitchS,
+                    const int32_t* __restrict__ nm, int64_t C, int U, int4* __restrict__ counts,
+                    longlong4* __restrict__ blocktot) {
+    __shared__ int4 s_cnt[kRowBlock];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t cb = (int64_t)blockIdx.x * kRowBlock;
+    for (int r = warp; r < kRowBlock; r += kBucketThreads / 32) {
+        const int64_t c = cb + r;
+        int4 cnt = make_int4(0, 0, 0, 0);
+        if (c < C) {
+            const int k = fstate[c];
+            if (k == kStateMixedF) {
+                cnt.w = 3 * U;
+            } else {
+                const int v = __ldg(nm + c);
+                const uint8_t* rn = rstate + (int64_t)(v & 0xffff) * pitchS;
+                const uint8_t* rm = rstate + (int64_t)((v >> 16) & 0xffff) * pitchS;
+                // 4 patients per lane: one 32-bit load per state row (pitchS is a multiple of 256, padding = 4)
+                for (int u0 = 0; u0 < U; u0 += 128) {
+                    const int u = u0 + 4 * lane;
+                    uint32_t sn4 = 0x04040404u, sm4 = 0x04040404u;
+                    if (u < U) {
+                        sn4 = __ldg(reinterpret_cast<const uint32_t*>(rn + u));
+                        sm4 = __ldg(reinterpret_cast<const uint32_t*>(rm + u));
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int code = pair_code((sn4 >> (8 * e)) & 0xff, (sm4 >> (8 * e)) & 0xff);
+                        cnt.x += code == 0;
+                        cnt.y += code == 1;
+                        cnt.z += code == 2;
+                        cnt.w += code == 3;
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    cnt.x += __shfl_xor_sync(0xffffffffu, cnt.x, o);
+                    cnt.y += __shfl_xor_sync(0xffffffffu, cnt.y, o);
+                    cnt.z += __shfl_xor_sync(0xffffffffu, cnt.z, o);
+                    cnt.w += __shfl_xor_sync(0xffffffffu, cnt.w, o);
+                }
+            }
+            if (lane == 0) counts[c] = cnt;
+        }
+        if (lane == 0) s_cnt[r] = cnt;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        longlong4 t = make_longlong4(0, 0, 0, 0);
+        for (int r = 0; r < kRowBlock; ++r) {
+            t.x += s_cnt[r].x;
+            t.y += s_cnt[r].y;
+            t.z += s_cnt[r].z;
+            t.w += s_cnt[r].w;
+        }
+        blocktot[blockIdx.x] = t;
+    }
+}
+
+// blockoff[b] = exclusive prefix sums of blocktot, totals[0..3] the sums.  One CTA, coalesced.
+__global__ void __launch_bounds__(1024)
+bucket_scan_kernel(const longlong4* __restrict__ blocktot, int64_t nblocks, longlong4* __restrict__ blockoff,
+                   long long* __restrict__ totals) {
+    __shared__ long long s_part[4][1024];
+    const int t = threadIdx.x;
+    long long carry[4] = {0, 0, 0, 0};
+    for (int64_t b0 = 0; b0 < nblocks; b0 += 1024) {
+        const int64_t b = b0 + t;
+        longlong4 v = make_longlong4(0, 0, 0, 0);
+        if (b < nblocks) v = blocktot[b];
+        const long long mine[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s_part[i][t] = mine[i];
+        __syncthreads();
+        for (int d = 1; d < 1024; d <<= 1) {                 // Hillis-Steele inclusive scan
+            long long w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) w[i] = t >= d ? s_part[i][t - d] : 0;
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s_part[i][t] += w[i];
+            __syncthreads();
+        }
+        if (b < nblocks)
+            blockoff[b] = make_longlong4(carry[0] + s_part[0][t] - mine[0], carry[1] + s_part[1][t] - mine[1],
+                                         carry[2] + s_part[2][t] - mine[2], carry[3] + s_part[3][t] - mine[3]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) carry[i] += s_part[i][1023];
+        __syncthreads();
+    }
+    if (t == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) totals[i] = carry[i];
+    }
+}
+
+struct Record {
+    double p, w0, w1, w2;
+};
+
+// Fills the streams.  G_l starts at G + base[l]; records at D.  out[0] = theta-free part of E_lM.
+// Same row blocks as bucket_count_kernel.  Per 64-patient chunk a lane owns the
+// patients 2*lane, 2*lane+1 (128-bit loads); within a chunk the stream order is
+// "all first elements, then all second elements" -- any fixed order will do.
+__global__ void __launch_bounds__(kBucketThreads)
+bucket_fill_kernel(const double* __restrict__ P, int64_t planeStride, const double* __restrict__ L,
+                   int64_t C, int U, int64_t pitchU,
+                   const double* __restrict__ qF, const uint8_t* __restrict__ fstate,
+                   const double* __restrict__ qR, const uint8_t* __restrict__ rstate, int64_t pitchS,
+                   const int32_t* __restrict__ nm, const int4* __restrict__ counts,
+                   const longlong4* __restrict__ blockoff,
+                   long long base0, long long base1, long long base2,
+                   double* __restrict__ G, Record* __restrict__ D, double* __restrict__ out,
+                   double* __restrict__ ws) {
+    __shared__ longlong4 s_off[kRowBlock];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const double2* qR2 = reinterpret_cast<const double2*>(qR);
+    double cs = 0.0;
+    for (int64_t blk = blockIdx.x; blk * kRowBlock < C; blk += gridDim.x) {
+        const int64_t cb = blk * kRowBlock;
+        __syncthreads();
+        if (threadIdx.x == 0) {                              // in-block exclusive prefix of the row counts
+            longlong4 run = blockoff[blk];
+            for (int r = 0; r < kRowBlock; ++r) {
+                s_off[r] = run;
+                if (cb + r < C) {
+                    const int4 v = counts[cb + r];
+                    run.x += v.x;
+                    run.y += v.y;
+                    run.z += v.z;
+                    run.w += v.w;
+                }
+            }
+        }
+        __syncthreads();
+        for (int r = warp; r < kRowBlock; r += kBucketThreads / 32) {
+            const int64_t c = cb + r;
+            if (c >= C) break;
+            const int k = fstate[c];
+            const int v = __ldg(nm + c);
+            const int n = v & 0xffff, m = (v >> 16) & 0xffff;
+            const longlong4 o = s_off[r];
+            long long pos[4] = {base0 + o.x, base1 + o.y, base2 + o.z, o.w};
+            if (k == kStateMixedF) {
+                const double qf[3] = {__ldg(qF + c * 3), __ldg(qF + c * 3 + 1), __ldg(qF + c * 3 + 2)};
+                const double qs = qf[0] + qf[1] + qf[2];
+                for (int u = lane; u < U; u += 32) {
+                    double w[3];
+                    pair_weights(__ldg(qR2 + (int64_t)n * U + u), __ldg(qR2 + (int64_t)m * U + u), w);
+                    const int64_t i = c * pitchU + u;
+#pragma unroll
+                    for (int kk = 0; kk < 3; ++kk) {
+                        Record rec;
+                        rec.p = ldg_stream1(P + kk * planeStride + i);
+                        rec.w0 = qf[kk] * w[0];
+                        rec.w1 = qf[kk] * w[1];
+                        rec.w2 = qf[kk] * w[2];
+                        D[pos[3] + 3 * (int64_t)u + kk] = rec;
+                    }
+                    cs = fma(qs * (w[0] + w[1] + w[2]), ldg_stream1(L + i), cs);
+                }
+                continue;
+            }
+            const double* row = P + (int64_t)k * planeStride + c * pitchU;
+            const double* lrow = L + c * pitchU;
+            const uint8_t* rn = rstate + (int64_t)n * pitchS;
+            const uint8_t* rm = rstate + (int64_t)m * pitchS;
+            for (int u0 = 0; u0 < U; u0 += 64) {
+                const int u = u0 + 2 * lane;
+                uint32_t sn2 = 0x0404u, sm2 = 0x0404u;
+                double2 p2 = make_double2(0.0, 0.0), l2 = make_double2(0.0, 0.0);
+                if (u < U) {                                 // pitchU is even: u + 1 < pitchU
+                    sn2 = __ldg(reinterpret_cast<const unsigned short*>(rn + u));
+                    sm2 = __ldg(reinterpret_cast<const unsigned short*>(rm + u));
+                    p2 = ldg_stream2(row + u);
+                    l2 = ldg_stream2(lrow + u);
+                }
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int code = pair_code((sn2 >> (8 * e)) & 0xff, (sm2 >> (8 * e)) & 0xff);
+                    const double p = e ? p2.y : p2.x, lv = e ? l2.y : l2.x;
+#pragma unroll
+                    for (int l = 0; l < 3; ++l) {
+                        const unsigned bal = __ballot_sync(0xffffffffu, code == l);
+                        if (code == l) G[pos[l] + __popc(bal & lt)] = p;
+                        pos[l] += __popc(bal);
+                    }
+                    const unsigned bal = __ballot_sync(0xffffffffu, code == 3);
+                    double wsum = code < 3 ? 1.0 : 0.0;
+                    if (code == 3) {
+                        double w[3];
+                        pair_weights(__ldg(qR2 + (int64_t)n * U + u + e), __ldg(qR2 + (int64_t)m * U + u + e), w);
+                        Record rec;
+                        rec.p = p;
+                        rec.w0 = w[0];
+                        rec.w1 = w[1];
+                        rec.w2 = w[2];
+                        D[pos[3] + __popc(bal & lt)] = rec;
+                        wsum = w[0] + w[1] + w[2];
+                    }
+                    pos[3] += __popc(bal);
+                    cs = fma(wsum, lv, cs);
+                }
+            }
+        }
+    }
+    double vv[1] = {cs};
+    grid_reduce_store<1, kBucketThreads>(vv, ws, out);
+}
+
+// One evaluation: out[0] = sum_l sum_{p in G_l} log(a_l + b_l p) + sum_records sum_l w_l log(a_l + b_l p),
+// out[1] = dE/d eta, out[2] = dE/d eps as in elm_kernel (fcd_mstep.cu).
+struct StreamAcc {
+    double obj, g;
+};
+
+template <bool GRAD, bool FAST>
+__device__ __forceinline__ void stream_elem(double p, double a, double b, const double* s_tab, StreamAcc& acc) {
+    const double M = fma(b, p, a);
+    if (GRAD) {
+        double rcp;
+        acc.obj += fast_log_rcp<FAST>(M, s_tab, rcp);
+        acc.g = fma(mix_num(p), rcp, acc.g);
+    } else {
+        acc.obj += fast_log<FAST>(M, s_tab);
+    }
+}
+
+constexpr int kStreamEvalThreads = 256;
+
+template <bool GRAD, bool FAST>
+__global__ void __launch_bounds__(kStreamEvalThreads)
+elm_streams_kernel(const double* __restrict__ G, long long base0, long long base1, long long base2,
+                   long long n0, long long n1, long long n2,
+                   const Record* __restrict__ D, long long nd,
+                   const __grid_constant__ ThetaDev th, const __grid_constant__ LogTabWindow tab,
+                   double* __restrict__ out, double* __restrict__ ws) {
+    extern __shared__ __align__(16) double s_dyn[];
+    const double* s_tab = load_log_table<FAST>(tab, s_dyn);
+    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long nth = (long long)gridDim.x * blockDim.x;
+    const long long base[3] = {base0, base1, base2};
+    const long long cnt[3] = {n0, n1, n2};
+    double obj = 0.0, gl[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+        const double a = th.al[l], b = th.bl[l];
+        const double* g = G + base[l];                       // 16-byte aligned (even base)
+        const long long npair = cnt[l] >> 1;
+        StreamAcc a0 = {0.0, 0.0}, a1 = {0.0, 0.0};
+        long long i = tid;
+        // four independent 128-bit loads in flight per thread
+        for (; i + 3 * nth < npair; i += 4 * nth) {
+            const double2 v0 = ldg_stream2(g + 2 * i), v1 = ldg_stream2(g + 2 * (i + nth));
+            const double2 v2 = ldg_stream2(g + 2 * (i + 2 * nth)), v3 = ldg_stream2(g + 2 * (i + 3 * nth));
+            stream_elem<GRAD, FAST>(v0.x, a, b, s_tab, a0);
+            stream_elem<GRAD, FAST>(v0.y, a, b, s_tab, a1);
+            stream_elem<GRAD, FAST>(v1.x, a, b, s_tab, a0);
+            stream_elem<GRAD, FAST>(v1.y, a, b, s_tab, a1);
+            stream_elem<GRAD, FAST>(v2.x, a, b, s_tab, a0);
+            stream_elem<GRAD, FAST>(v2.y, a, b, s_tab, a1);
+            stream_elem<GRAD, FAST>(v3.x, a, b, s_tab, a0);
+            stream_elem<GRAD, FAST>(v3.y, a, b, s_tab, a1);
+        }
+        for (; i < npair; i += nth) {
+            const double2 v0 = ldg_stream2(g + 2 * i);
+            stream_elem<GRAD, FAST>(v0.x, a, b, s_tab, a0);
+            stream_elem<GRAD, FAST>(v0.y, a, b, s_tab, a1);
+        }
+        if ((cnt[l] & 1) && tid == 0) stream_elem<GRAD, FAST>(g[cnt[l] - 1], a, b, s_tab, a0);
+        obj += a0.obj + a1.obj;
+        gl[l] = a0.g + a1.g;
+    }
+    for (long long i = tid; i < nd; i += nth) {
+        const double4 r = *reinterpret_cast<const double4*>(D + i);
+        const double w[3] = {r.y, r.z, r.w};
+        const double num = mix_num(r.x);
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            const double M = mix_rel(th, l, r.x);
+            if (GRAD) {
+                double rcp;
+                obj = fma(w[l], fast_log_rcp<FAST>(M, s_tab, rcp), obj);
+                gl[l] = fma(w[l], num * rcp, gl[l]);
+            } else {
+                obj = fma(w[l], fast_log<FAST>(M, s_tab), obj);
+            }
+        }
+    }
+    // dE/d eta = -(2 eps - 1) g_2;  dE/d eps = -(-g_0 + g_1 + (2 eta - 1) g_2)      (fit.py:600-697)
+    double v[3] = {obj, -(2.0 * th.epsilon - 1.0) * gl[2], -(-gl[0] + gl[1] + (2.0 * th.eta - 1.0) * gl[2])};
+    grid_reduce_store<3, kStreamEvalThreads>(v, ws, out);
+}
+
+static inline int rows_grid(int64_t rows, int rows_per_block, int waves) {
+    int64_t need = (rows + rows_per_block - 1) / rows_per_block;
+    int64_t cap = (int64_t)sm_count() * waves;
+    if (cap > kMaxReduceBlocks) cap = kMaxReduceBlocks;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+}  // namespace fcd
+
+using namespace fcd;
+
+extern "C" {
+
+int fcd_bucket_count(const uint8_t* fstate, const uint8_t* rstate, int64_t pitchS, const int32_t* nm,
+                     int64_t C, int32_t U, int32_t* counts, int64_t* blockoff, int64_t* totals, void* stream) {
+    FCD_REQUIRE(fstate != nullptr && rstate != nullptr && nm != nullptr && counts != nullptr && blockoff != nullptr &&
+                totals != nullptr, "fcd_bucket_count: NULL argument");
+    FCD_REQUIRE(C >= 1 && U >= 1 && pitchS >= U && pitchS % 4 == 0, "fcd_bucket_count: bad shape");
+    FCD_REQUIRE((reinterpret_cast<uintptr_t>(counts) & 15) == 0 && (reinterpret_cast<uintptr_t>(blockoff) & 31) == 0 &&
+                (reinterpret_cast<uintptr_t>(rstate) & 3) == 0,
+                "fcd_bucket_count: counts / blockoff must be 16 / 32-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nblocks = (C + kRowBlock - 1) / kRowBlock;
+    // blockoff doubles as the block totals' storage: [nblocks] totals followed by [nblocks] offsets
+    longlong4* bt = reinterpret_cast<longlong4*>(blockoff);
+    bucket_count_kernel<<<(unsigned)nblocks, kBucketThreads, 0, st>>>(fstate, rstate, pitchS, nm, C, U,
+                                                                      reinterpret_cast<int4*>(counts), bt);
+    int rc = check_launch("fcd_bucket_count");
+    if (rc) return rc;
+    bucket_scan_kernel<<<1, 1024, 0, st>>>(bt, nblocks, bt + nblocks, reinterpret_cast<long long*>(totals));
+    return check_launch("fcd_bucket_count(scan)");
+}
+
+int64_t fcd_bucket_blocks(int64_t C) { return (C + kRowBlock - 1) / kRowBlock; }
+
+int fcd_bucket_fill(const double* P, int64_t planeStride, const double* L, int64_t C, int32_t U, int64_t pitchU,
+                    const double* qF, const uint8_t* fstate, const double* qR, const uint8_t* rstate,
+                    int64_t pitchS, int32_t N, const int32_t* nm, const int32_t* counts, const int64_t* blockoff,
+                    const int64_t* base3_host, double* G, double* D, double* out1, double* ws, void* stream) {
+    FCD_REQUIRE(P != nullptr && L != nullptr && qF != nullptr && fstate != nullptr && qR != nullptr &&
+                rstate != nullptr && nm != nullptr && counts != nullptr && blockoff != nullptr &&
+                base3_host != nullptr && G != nullptr && D != nullptr && out1 != nullptr && ws != nullptr,
+                "fcd_bucket_fill: NULL argument");
+    FCD_REQUIRE(C >= 1 && U >= 1 && pitchU >= U && pitchS >= U && N >= 2 && N < 65536, "fcd_bucket_fill: bad shape");
+    FCD_REQUIRE((reinterpret_cast<uintptr_t>(D) & 31) == 0 && ((reinterpret_cast<uintptr_t>(P) | reinterpret_cast<uintptr_t>(L)) & 15) == 0 &&
+                pitchU % 2 == 0 && planeStride % 2 == 0 && pitchS % 2 == 0,
+                "fcd_bucket_fill: planes must be 16-byte aligned with even pitches, records 32-byte aligned");
+    const int64_t nblocks = (C + kRowBlock - 1) / kRowBlock;
+    int64_t grid = nblocks;
+    if (grid > (int64_t)sm_count() * 8) grid = (int64_t)sm_count() * 8;
+    if (grid > kMaxReduceBlocks) grid = kMaxReduceBlocks;
+    bucket_fill_kernel<<<(unsigned)grid, kBucketThreads, 0, (cudaStream_t)stream>>>(
+        P, planeStride, L, C, U, pitchU, qF, fstate, qR, rstate, pitchS, nm, reinterpret_cast<const int4*>(counts),
+        reinterpret_cast<const longlong4*>(blockoff) + nblocks, base3_host[0], base3_host[1], base3_host[2], G,
+        reinterpret_cast<Record*>(D), out1, ws);
+    return check_launch("fcd_bucket_fill");
+}
+
+int fcd_elm_streams(const double* G, const int64_t* base3_host, const int64_t* count3_host,
+                    const double* D, int64_t nd, const fcd_theta* theta_host, int32_t want_grad,
+                    double* out3, double* ws, void* stream) {
+    FCD_REQUIRE(G != nullptr && base3_host != nullptr && count3_host != nullptr && theta_host != nullptr &&
+                out3 != nullptr && ws != nullptr && (nd == 0 || D != nullptr), "fcd_elm_streams: NULL argument");
+    FCD_REQUIRE((reinterpret_cast<uintptr_t>(G) & 15) == 0 && base3_host[0] % 2 == 0 && base3_host[1] % 2 == 0 &&
+                base3_host[2] % 2 == 0 && (reinterpret_cast<uintptr_t>(D) & 31) == 0,
+                "fcd_elm_streams: streams must start 16-byte aligned (even bases), records 32-byte aligned");
+    const ThetaDev th = make_theta_dev(*theta_host, 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    LogTabWindow tab;
+    FCD_REQUIRE(log_table_window(th.epsl, th.al, st, tab), "fcd_elm_streams: log table initialisation failed");
+    const bool fast = log_table_covers(th.epsl, th.al);
+    const size_t smem = fast ? tab.bytes() : 0;
+    int per_sm = fast ? (int)((200 * 1024) / (smem + 1024)) : 4;
+    if (per_sm > 4) per_sm = 4;                              // 64 registers x 256 threads: 4 CTAs / SM resident
+    if (per_sm < 1) per_sm = 1;
+    const long long work = (count3_host[0] + count3_host[1] + count3_host[2]) / 2 + nd;
+    long long grid = (work + kStreamEvalThreads - 1) / kStreamEvalThreads;
+    if (grid > (long long)sm_count() * per_sm) grid = (long long)sm_count() * per_sm;
+    if (grid < 1) grid = 1;
+#define FCD_ES(G_, F_)                                                                               \
+    do {                                                                                             \
+        cudaFuncSetAttribute(elm_streams_kernel<G_, F_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             (int)kLogTabBytes);                                                     \
+        elm_streams_kernel<G_, F_><<<(unsigned)grid, kStreamEvalThreads, smem, st>>>(                \
+            G, base3_host[0], base3_host[1], base3_host[2], count3_host[0], count3_host[1], count3_host[2], \
+            reinterpret_cast<const Record*>(D), nd, th, tab, out3, ws);                               \
+    } while (0)
+    if (want_grad) { if (fast) FCD_ES(true, true); else FCD_ES(true, false); }
+    else           { if (fast) FCD_ES(false, true); else FCD_ES(false, false); }
+#undef FCD_ES
+    return check_launch("fcd_elm_streams");
+}
+
+}  // extern "C"

@@ -134,6 +134,12 @@ class UnsharedRegionFit(object):
         Edge sharding over the ranks of a ``torch.distributed`` group (new).
     optimise_theta_sub : bool
         Run the (eta, epsilon) optimiser in ``_update_theta`` (default True).
+    elm_path : "auto" | "streams" | "tiered"
+        Form of the (eta, epsilon) objective kernel (new).  ``"streams"``: one
+        bucket pass per (q_F, q_R) state, then every evaluation reduces flat
+        streams (8 bytes per edge-patient); ``"tiered"``: every evaluation walks
+        the responsibility planes; ``"auto"``: streams unless more than a quarter
+        of the elements would need weighted records (e.g. the uniform start).
     update_mu_sigma : bool
         Also re-estimate ``mu`` and ``sigma`` in ``_update_theta`` (new; the
         reference ships this step disabled, fit.py:232-237; default False).
@@ -156,6 +162,7 @@ class UnsharedRegionFit(object):
         self.n_edges = None           # global edge count when b / bt are device edge shards
         self.optimise_theta_sub = True
         self.update_mu_sigma = False  # re-estimate mu, sigma (disabled in the reference, fit.py:232-237)
+        self.elm_path = "auto"        # K3b form: "streams" | "tiered" | "auto" (streams unless most elements are unpeaked)
         self.convergence_rule = "reference"
         self.n_objective_evals = []
         self.profile = None           # _dev.KernelTimers for per-kernel CUDA-event timing
@@ -341,11 +348,56 @@ class UnsharedRegionFit(object):
             inp['WT'] = _dev.empty((Ul, C, 3))
         return inp
 
-    def _result(self, n):
-        key = (n, torch.cuda.current_device())
+    def _result(self, n, dtype=torch.float64, tag=""):
+        key = (n, dtype, tag, torch.cuda.current_device())
         if key not in self._res:
-            self._res[key] = _dev.SmallResult(n)
+            self._res[key] = _dev.SmallResult(n, dtype)
         return self._res[key]
+
+    def _build_streams(self, inp, res4):
+        """Bucket pass (csrc/fcd_streams.cu): the planes of the local edge rows
+        become three streams of responsibilities plus weighted records for the
+        current (q_F, q_R); the theta-free part of E_lM lands in res4.dev[3].
+        Returns the argument head for ``fcd_elm_streams`` or None when the
+        tiered kernel should be used instead."""
+        if self.elm_path == "tiered":
+            return None
+        lib = _lib.load()
+        (N, H, U) = self._dims
+        (c0, Cl) = (inp['c0'], inp['Cl'])
+        if Cl == 0:
+            return None
+        (_, qF) = self._mF.get_dev()
+        (_, qR) = self._mR.get_dev()
+        (fstate, rstate) = (self._mF.get_state(), self._mR.get_state())
+        stream = _dev.stream()
+        if inp.get('bk_counts') is None:
+            inp['bk_counts'] = _dev.empty((Cl, 4), torch.int32)
+            inp['bk_offs'] = _dev.empty((2 * int(lib.fcd_bucket_blocks(Cl)), 4), torch.int64)
+        tot = self._result(4, torch.int64, "totals")
+        with _dev.timed(self.profile, "K3b_bucket_count"):
+            _lib.check(lib.fcd_bucket_count(_dev.ptr(fstate[c0:]), _dev.ptr(rstate), rstate.shape[1],
+                                            _dev.ptr(inp['nm']), Cl, U, _dev.ptr(inp['bk_counts']),
+                                            _dev.ptr(inp['bk_offs']), _dev.ptr(tot.dev), stream), "fcd_bucket_count")
+        (n0, n1, n2, nd) = (int(v) for v in tot.read(stream))
+        if self.elm_path == "auto" and nd * 4 > Cl * U:
+            return None
+        base = [0, n0 + (n0 & 1), 0]
+        base[2] = base[1] + n1 + (n1 & 1)
+        if inp.get('bk_G') is None:
+            inp['bk_G'] = _dev.empty((Cl * U + 4,))
+        if inp.get('bk_D') is None or inp['bk_D'].numel() < 4 * nd:
+            inp['bk_D'] = _dev.empty((4 * max(nd, Cl * U // 4, 1),))
+        base3 = (ctypes.c_int64 * 3)(*base)
+        count3 = (ctypes.c_int64 * 3)(n0, n1, n2)
+        with _dev.timed(self.profile, "K3b_bucket_fill"):
+            _lib.check(lib.fcd_bucket_fill(
+                _dev.ptr(inp['P']), max(Cl, 1) * inp['pitchU'], _dev.ptr(inp['L']), Cl, U, inp['pitchU'],
+                _dev.ptr(qF[c0 * 3:]), _dev.ptr(fstate[c0:]), _dev.ptr(qR), _dev.ptr(rstate), rstate.shape[1], N,
+                _dev.ptr(inp['nm']), _dev.ptr(inp['bk_counts']), _dev.ptr(inp['bk_offs']), base3,
+                _dev.ptr(inp['bk_G']), _dev.ptr(inp['bk_D']),
+                _dev.ptr(res4.dev[3:]), _dev.ptr(_dev.workspace()), stream), "fcd_bucket_fill")
+        return (_dev.ptr(inp['bk_G']), base3, count3, _dev.ptr(inp['bk_D']), nd)
 
     def _theta(self, use_snapshot=True):
         m = self.model
@@ -713,10 +765,11 @@ class UnsharedRegionFit(object):
 
     def _objective_context(self):
         """Everything of a K3b evaluation that does not depend on (eta, epsilon):
-        argument list, theta struct, result vector, stream, theta-free part of
-        E_lM.  Valid for one (q_F, q_R, planes) state."""
+        the streams of the bucket pass (or, for the tiered form, the plane
+        pointers and the theta-free part of E_lM), theta struct, result vector,
+        stream.  Valid for one (q_F, q_R, planes) state."""
         inp = self._ensure_cache()
-        key = (self._mF.version, self._mR.version, inp['cache_key'], id(inp), id(self.profile))
+        key = (self._mF.version, self._mR.version, inp['cache_key'], id(inp), id(self.profile), self.elm_path)
         ctx = self._ctx
         if ctx is not None and ctx['key'] == key:
             return ctx
@@ -726,33 +779,46 @@ class UnsharedRegionFit(object):
         (_, qR) = self._mR.get_dev()
         (fstate, rstate) = (self._mF.get_state(), self._mR.get_state())
         th = self._theta()
-        res = self._result(3)
+        res = self._result(4, tag="elm")          # [obj, dE/d eta, dE/d eps, theta-free part]
         stream = _dev.stream()
-        head = (_dev.ptr(inp['P']), max(Cl, 1) * inp['pitchU'], Cl, U, inp['pitchU'],
-                _dev.ptr(qF[c0 * 3:]), _dev.ptr(fstate[c0:]), _dev.ptr(qR), _dev.ptr(rstate), rstate.shape[1],
-                N, _dev.ptr(inp['nm']), ctypes.byref(th))
+        lib = _lib.load()
         tail = (_dev.ptr(res.dev), _dev.ptr(_dev.workspace()), stream)
-        self._ctx = dict(key=key, th=th, res=res, stream=stream, head=head, tail=tail, const=self._elm_const(inp),
-                         keep=(qF, qR, fstate, rstate), fn=_lib.load().fcd_elm_obj_grad,
+        head = self._build_streams(inp, res)
+        if head is not None:
+            (fn, name, const) = (lib.fcd_elm_streams, "K3b_elm_streams", None)
+            head = head + (ctypes.byref(th),)
+        else:
+            (fn, name, const) = (lib.fcd_elm_obj_grad, "K3b_elm_obj_grad", self._elm_const(inp))
+            head = (_dev.ptr(inp['P']), max(Cl, 1) * inp['pitchU'], Cl, U, inp['pitchU'],
+                    _dev.ptr(qF[c0 * 3:]), _dev.ptr(fstate[c0:]), _dev.ptr(qR), _dev.ptr(rstate), rstate.shape[1],
+                    N, _dev.ptr(inp['nm']), ctypes.byref(th))
+        self._ctx = dict(key=key, th=th, res=res, stream=stream, head=head, tail=tail, const=const,
+                         keep=(qF, qR, fstate, rstate), fn=fn, name=name,
                          verF=self._mF.version, verR=self._mR.version)
         return self._ctx
 
-    def _objective(self, theta_sub, want_grad=True, name="K3b_elm_obj_grad"):
+    def _objective(self, theta_sub, want_grad=True, name=None):
         """(-E_lM, gradient) at theta_sub = [eta, epsilon] from one fused pass
-        over the responsibility planes (K3b)."""
+        (K3b) over the bucketed streams or the responsibility planes."""
         ctx = self._objective_context()
         th = ctx['th']
         th.eta = float(theta_sub[0])
         th.epsilon = float(theta_sub[1])
-        with _dev.timed(self.profile, name):
+        with _dev.timed(self.profile, name or ctx['name']):
             rc = ctx['fn'](*ctx['head'], 1 if want_grad else 0, *ctx['tail'])
         if rc != 0:
-            _lib.check(rc, "fcd_elm_obj_grad")
+            _lib.check(rc, ctx['name'])
         res = ctx['res']
         if self.shards is not None:
-            self.shards.allreduce_terms(res.dev, (0, 1, 2))           # all three are edge-local partial sums
+            self.shards.allreduce_terms(res.dev, (0, 1, 2, 3))        # all four are edge-local partial sums
         o = res.read(ctx['stream'])
-        elm = float(o[0]) + ctx['const']
+        if ctx['const'] is None and self.shards is not None:
+            # the theta-free part sits in slot 3 and was summed over ranks together with the rest:
+            # keep the global value and zero the slot so that later all-reduces do not add it again
+            ctx['const'] = float(o[3])
+            res.dev[3:].zero_()
+        const = float(o[3]) if ctx['const'] is None else ctx['const']
+        elm = float(o[0]) + const
         self._evals.append(dict(x=(th.eta, th.epsilon), verF=ctx['verF'], verR=ctx['verR'], elm=elm))
         del self._evals[:-4]
         return -elm, o[1:3]

@@ -293,11 +293,15 @@ def test_fused_steps_vs_oracle(N, H, U, lookup, peaked):
     nptest.assert_allclose(fit.model.pi, O.update_pi(exp_R), rtol=1e-10)
     nptest.assert_allclose(fit.model.gamma, O.update_gamma(exp_F), rtol=1e-10)
     # K3b objective + analytic gradient at interior and near-bound points
-    for x in ([0.3, 0.03], [0.7, 0.4], [1e-5, 1 - 1e-5], [1 - 1e-5, 1e-5]):
-        (f, grad) = fit._objective(x)
-        (fo, go) = O.elm_objective_and_grad(pBt, np.exp(exp_F), np.exp(exp_R), x)
-        nptest.assert_allclose(f, fo, rtol=1e-10)
-        nptest.assert_allclose(grad, go, rtol=1e-8, atol=1e-8 * max(1.0, np.abs(go).max()))
+    # (both forms of the kernel: bucketed streams and tiered walk over the planes)
+    for path in ("tiered", "streams", "auto"):
+        fit.elm_path = path
+        for x in ([0.3, 0.03], [0.7, 0.4], [1e-5, 1 - 1e-5], [1 - 1e-5, 1e-5]):
+            (f, grad) = fit._objective(x)
+            (fo, go) = O.elm_objective_and_grad(pBt, np.exp(exp_F), np.exp(exp_R), x)
+            nptest.assert_allclose(f, fo, rtol=1e-10)
+            nptest.assert_allclose(grad, go, rtol=1e-8, atol=1e-8 * max(1.0, np.abs(go).max()))
+        assert fit._ctx['name'] == {"tiered": "K3b_elm_obj_grad", "streams": "K3b_elm_streams"}.get(path, fit._ctx['name'])
     # K3c sufficient statistics for mu / sigma
     mom = fit._state_moments()
     momo = O.state_moments(b, bt, th, np.exp(exp_F), np.exp(exp_R))
@@ -464,6 +468,16 @@ def test_config3_properties(N, H, U):
     nptest.assert_allclose(fit._eval_energy(), e_fresh, rtol=1e-13)
     nptest.assert_allclose(fit.energy[-1], e_fresh, rtol=1e-13)
     nptest.assert_allclose(fit._energy_terms()[3], w[0] + w[3], rtol=1e-12)
+    # -- the bucketed-streams form of K3b equals the tiered walk over the planes
+    res = {}
+    for path in ("tiered", "streams"):
+        fit.elm_path = path
+        res[path] = fit._objective([th.eta, th.epsilon])
+        assert fit._ctx['name'] == ("K3b_elm_streams" if path == "streams" else "K3b_elm_obj_grad")
+    nptest.assert_allclose(res["streams"][0], res["tiered"][0], rtol=1e-13)
+    nptest.assert_allclose(res["streams"][1], res["tiered"][1], rtol=0, atol=gtol)
+    nptest.assert_allclose(-res["streams"][0], w[0] + w[3], rtol=1e-12)
+    fit.elm_path = "auto"
     # -- K2 on a shard equals the slice of the whole; tiered K2 equals the all-deferred form
     (a, e) = (40001, C)
 
