@@ -31,7 +31,7 @@ __device__ __forceinline__ int pair_code(int sn, int sm) {
 // is (offset of its block) + (prefix inside the block): the block totals are
 // scanned by one small kernel, the in-block prefix is recomputed in shared memory
 // by the fill kernel -- no pass over per-row arrays by a single CTA.
-constexpr int kRowBlock = 64;
+constexpr int kRowBlock = 16;
 
 // counts[c] = {n_0, n_1, n_2, n_records} of row c; blocktot[b] their sums over the rows of block b.
 __global__ void __launch_bounds__(kBucketThreads)
@@ -139,7 +139,7 @@ struct Record {
 // Same row blocks as bucket_count_kernel.  Per 64-patient chunk a lane owns the
 // patients 2*lane, 2*lane+1 (128-bit loads); within a chunk the stream order is
 // "all first elements, then all second elements" -- any fixed order will do.
-__global__ void __launch_bounds__(kBucketThreads)
+__global__ void __launch_bounds__(kBucketThreads, 2)
 bucket_fill_kernel(const double* __restrict__ P, int64_t planeStride, const double* __restrict__ L,
                    int64_t C, int U, int64_t pitchU,
                    const double* __restrict__ qF, const uint8_t* __restrict__ fstate,
@@ -179,23 +179,19 @@ bucket_fill_kernel(const double* __restrict__ P, int64_t planeStride, const doub
             const int n = v & 0xffff, m = (v >> 16) & 0xffff;
             const longlong4 o = s_off[r];
             long long pos[4] = {base0 + o.x, base1 + o.y, base2 + o.z, o.w};
-            if (k == kStateMixedF) {
-                const double qf[3] = {__ldg(qF + c * 3), __ldg(qF + c * 3 + 1), __ldg(qF + c * 3 + 2)};
-                const double qs = qf[0] + qf[1] + qf[2];
+            if (k == kStateMixedF) {                         // three records per element, tagged with their state
                 for (int u = lane; u < U; u += 32) {
-                    double w[3];
-                    pair_weights(__ldg(qR2 + (int64_t)n * U + u), __ldg(qR2 + (int64_t)m * U + u), w);
                     const int64_t i = c * pitchU + u;
+                    const double lv = ldg_stream1(L + i);
 #pragma unroll
                     for (int kk = 0; kk < 3; ++kk) {
                         Record rec;
                         rec.p = ldg_stream1(P + kk * planeStride + i);
-                        rec.w0 = qf[kk] * w[0];
-                        rec.w1 = qf[kk] * w[1];
-                        rec.w2 = qf[kk] * w[2];
+                        rec.w0 = lv;
+                        rec.w1 = __hiloint2double((int)c, u);
+                        rec.w2 = 1.0 + kk;
                         D[pos[3] + 3 * (int64_t)u + kk] = rec;
                     }
-                    cs = fma(qs * (w[0] + w[1] + w[2]), ldg_stream1(L + i), cs);
                 }
                 continue;
             }
@@ -203,46 +199,104 @@ bucket_fill_kernel(const double* __restrict__ P, int64_t planeStride, const doub
             const double* lrow = L + c * pitchU;
             const uint8_t* rn = rstate + (int64_t)n * pitchS;
             const uint8_t* rm = rstate + (int64_t)m * pitchS;
-            for (int u0 = 0; u0 < U; u0 += 64) {
+            struct Chunk {
+                uint32_t sn2, sm2;
+                double2 p2, l2;
+            };
+            auto load = [&](int u0) {
+                Chunk ch;
+                ch.sn2 = ch.sm2 = 0x0404u;
+                ch.p2 = ch.l2 = make_double2(0.0, 0.0);
                 const int u = u0 + 2 * lane;
-                uint32_t sn2 = 0x0404u, sm2 = 0x0404u;
-                double2 p2 = make_double2(0.0, 0.0), l2 = make_double2(0.0, 0.0);
                 if (u < U) {                                 // pitchU is even: u + 1 < pitchU
-                    sn2 = __ldg(reinterpret_cast<const unsigned short*>(rn + u));
-                    sm2 = __ldg(reinterpret_cast<const unsigned short*>(rm + u));
-                    p2 = ldg_stream2(row + u);
-                    l2 = ldg_stream2(lrow + u);
+                    ch.sn2 = __ldg(reinterpret_cast<const unsigned short*>(rn + u));
+                    ch.sm2 = __ldg(reinterpret_cast<const unsigned short*>(rm + u));
+                    ch.p2 = ldg_stream2(row + u);
+                    ch.l2 = ldg_stream2(lrow + u);
                 }
+                return ch;
+            };
+            auto process = [&](const Chunk& cur, int u0) {
+                if (u0 >= U) return;                         // warp-uniform
+                const int u = u0 + 2 * lane;
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const int code = pair_code((sn2 >> (8 * e)) & 0xff, (sm2 >> (8 * e)) & 0xff);
-                    const double p = e ? p2.y : p2.x, lv = e ? l2.y : l2.x;
-#pragma unroll
-                    for (int l = 0; l < 3; ++l) {
-                        const unsigned bal = __ballot_sync(0xffffffffu, code == l);
-                        if (code == l) G[pos[l] + __popc(bal & lt)] = p;
-                        pos[l] += __popc(bal);
-                    }
-                    const unsigned bal = __ballot_sync(0xffffffffu, code == 3);
-                    double wsum = code < 3 ? 1.0 : 0.0;
-                    if (code == 3) {
-                        double w[3];
-                        pair_weights(__ldg(qR2 + (int64_t)n * U + u + e), __ldg(qR2 + (int64_t)m * U + u + e), w);
+                    const int code = pair_code((cur.sn2 >> (8 * e)) & 0xff, (cur.sm2 >> (8 * e)) & 0xff);
+                    const double p = e ? cur.p2.y : cur.p2.x, lv = e ? cur.l2.y : cur.l2.x;
+                    // every element has exactly one destination: one store per lane
+                    const unsigned b0 = __ballot_sync(0xffffffffu, code == 0);
+                    const unsigned b1 = __ballot_sync(0xffffffffu, code == 1);
+                    const unsigned b2 = __ballot_sync(0xffffffffu, code == 2);
+                    const unsigned b3 = __ballot_sync(0xffffffffu, code == 3);
+                    const unsigned mine = code == 0 ? b0 : (code == 1 ? b1 : (code == 2 ? b2 : b3));
+                    const long long at = (code == 0 ? pos[0] : (code == 1 ? pos[1] : (code == 2 ? pos[2] : pos[3]))) +
+                                         __popc(mine & lt);
+                    if (code < 3) G[at] = p;
+                    if (code == 3) {                         // weights are filled in by bucket_records_kernel
                         Record rec;
                         rec.p = p;
-                        rec.w0 = w[0];
-                        rec.w1 = w[1];
-                        rec.w2 = w[2];
-                        D[pos[3] + __popc(bal & lt)] = rec;
-                        wsum = w[0] + w[1] + w[2];
+                        rec.w0 = lv;
+                        rec.w1 = __hiloint2double((int)c, u + e);
+                        rec.w2 = 0.0;
+                        D[at] = rec;
                     }
-                    pos[3] += __popc(bal);
-                    cs = fma(wsum, lv, cs);
+                    pos[0] += __popc(b0);
+                    pos[1] += __popc(b1);
+                    pos[2] += __popc(b2);
+                    pos[3] += __popc(b3);
+                    cs += code < 3 ? lv : 0.0;
                 }
+            };
+            // two register sets of two chunks each, loaded in turn (no register rotation:
+            // a move of a loaded value would wait for the load and defeat the prefetch)
+            Chunk a0 = load(0), a1 = load(64);
+            for (int u0 = 0; u0 < U; u0 += 256) {
+                const Chunk b0 = load(u0 + 128), b1 = load(u0 + 192);
+                process(a0, u0);
+                process(a1, u0 + 64);
+                a0 = load(u0 + 256);
+                a1 = load(u0 + 320);
+                process(b0, u0 + 128);
+                process(b1, u0 + 192);
             }
         }
     }
     double vv[1] = {cs};
+    grid_reduce_store<1, kBucketThreads>(vv, ws, out);
+}
+
+// Second half of the bucket pass: the records of unpeaked elements of peaked rows
+// were left as {p, L, (c, u)}; one thread per record gathers the two regions'
+// posteriors (massively parallel, nothing on a row walker's critical path),
+// writes {p, w_0, w_1, w_2} and adds its share sum_l w_l L to out[0].
+__global__ void __launch_bounds__(kBucketThreads)
+bucket_records_kernel(Record* __restrict__ D, long long nd, const double* __restrict__ qF,
+                      const double* __restrict__ qR, int U, const int32_t* __restrict__ nm,
+                      double* __restrict__ out, double* __restrict__ ws) {
+    const double2* qR2 = reinterpret_cast<const double2*>(qR);
+    double cs = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nd;
+         i += (long long)gridDim.x * blockDim.x) {
+        Record rec = D[i];                                   // {p, L, (c, u), tag}: tag 0 = peaked edge, 1 + k otherwise
+        const int c = __double2hiint(rec.w1), u = __double2loint(rec.w1);
+        const int tag = (int)rec.w2;
+        const int v = __ldg(nm + c);
+        double w[3];
+        pair_weights(__ldg(qR2 + (int64_t)(v & 0xffff) * U + u), __ldg(qR2 + (int64_t)((v >> 16) & 0xffff) * U + u), w);
+        double scale = 1.0, cscale = 1.0;
+        if (tag > 0) {
+            const double qf[3] = {__ldg(qF + (int64_t)c * 3), __ldg(qF + (int64_t)c * 3 + 1), __ldg(qF + (int64_t)c * 3 + 2)};
+            scale = qf[tag - 1];
+            cscale = tag == 1 ? qf[0] + qf[1] + qf[2] : 0.0;  // the element's theta-free term is counted once
+        }
+        cs = fma(cscale * (w[0] + w[1] + w[2]), rec.w0, cs);
+        rec.w0 = scale * w[0];
+        rec.w1 = scale * w[1];
+        rec.w2 = scale * w[2];
+        D[i] = rec;
+    }
+    // out[0] (left by bucket_fill_kernel) enters the sum once
+    double vv[1] = {cs + ((blockIdx.x == 0 && threadIdx.x == 0) ? out[0] : 0.0)};
     grid_reduce_store<1, kBucketThreads>(vv, ws, out);
 }
 
@@ -267,7 +321,7 @@ __device__ __forceinline__ void stream_elem(double p, double a, double b, const 
 constexpr int kStreamEvalThreads = 256;
 
 template <bool GRAD, bool FAST>
-__global__ void __launch_bounds__(kStreamEvalThreads)
+__global__ void __launch_bounds__(kStreamEvalThreads, 3)
 elm_streams_kernel(const double* __restrict__ G, long long base0, long long base1, long long base2,
                    long long n0, long long n1, long long n2,
                    const Record* __restrict__ D, long long nd,
@@ -287,18 +341,16 @@ elm_streams_kernel(const double* __restrict__ G, long long base0, long long base
         const long long npair = cnt[l] >> 1;
         StreamAcc a0 = {0.0, 0.0}, a1 = {0.0, 0.0};
         long long i = tid;
-        // four independent 128-bit loads in flight per thread
-        for (; i + 3 * nth < npair; i += 4 * nth) {
-            const double2 v0 = ldg_stream2(g + 2 * i), v1 = ldg_stream2(g + 2 * (i + nth));
-            const double2 v2 = ldg_stream2(g + 2 * (i + 2 * nth)), v3 = ldg_stream2(g + 2 * (i + 3 * nth));
-            stream_elem<GRAD, FAST>(v0.x, a, b, s_tab, a0);
-            stream_elem<GRAD, FAST>(v0.y, a, b, s_tab, a1);
-            stream_elem<GRAD, FAST>(v1.x, a, b, s_tab, a0);
-            stream_elem<GRAD, FAST>(v1.y, a, b, s_tab, a1);
-            stream_elem<GRAD, FAST>(v2.x, a, b, s_tab, a0);
-            stream_elem<GRAD, FAST>(v2.y, a, b, s_tab, a1);
-            stream_elem<GRAD, FAST>(v3.x, a, b, s_tab, a0);
-            stream_elem<GRAD, FAST>(v3.y, a, b, s_tab, a1);
+        // eight independent 128-bit loads in flight per thread
+        for (; i + 7 * nth < npair; i += 8 * nth) {
+            double2 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = ldg_stream2(g + 2 * (i + j * nth));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                stream_elem<GRAD, FAST>(v[j].x, a, b, s_tab, a0);
+                stream_elem<GRAD, FAST>(v[j].y, a, b, s_tab, a1);
+            }
         }
         for (; i < npair; i += nth) {
             const double2 v0 = ldg_stream2(g + 2 * i);
@@ -369,7 +421,8 @@ int64_t fcd_bucket_blocks(int64_t C) { return (C + kRowBlock - 1) / kRowBlock; }
 int fcd_bucket_fill(const double* P, int64_t planeStride, const double* L, int64_t C, int32_t U, int64_t pitchU,
                     const double* qF, const uint8_t* fstate, const double* qR, const uint8_t* rstate,
                     int64_t pitchS, int32_t N, const int32_t* nm, const int32_t* counts, const int64_t* blockoff,
-                    const int64_t* base3_host, double* G, double* D, double* out1, double* ws, void* stream) {
+                    const int64_t* base3_host, double* G, double* D, int64_t nd, double* out1, double* ws,
+                    void* stream) {
     FCD_REQUIRE(P != nullptr && L != nullptr && qF != nullptr && fstate != nullptr && qR != nullptr &&
                 rstate != nullptr && nm != nullptr && counts != nullptr && blockoff != nullptr &&
                 base3_host != nullptr && G != nullptr && D != nullptr && out1 != nullptr && ws != nullptr,
@@ -379,14 +432,19 @@ int fcd_bucket_fill(const double* P, int64_t planeStride, const double* L, int64
                 pitchU % 2 == 0 && planeStride % 2 == 0 && pitchS % 2 == 0,
                 "fcd_bucket_fill: planes must be 16-byte aligned with even pitches, records 32-byte aligned");
     const int64_t nblocks = (C + kRowBlock - 1) / kRowBlock;
-    int64_t grid = nblocks;
-    if (grid > (int64_t)sm_count() * 8) grid = (int64_t)sm_count() * 8;
-    if (grid > kMaxReduceBlocks) grid = kMaxReduceBlocks;
+    int64_t grid = nblocks;                                  // persistent: the resident CTAs share the row blocks
+    if (grid > (int64_t)sm_count() * 2) grid = (int64_t)sm_count() * 2;
     bucket_fill_kernel<<<(unsigned)grid, kBucketThreads, 0, (cudaStream_t)stream>>>(
         P, planeStride, L, C, U, pitchU, qF, fstate, qR, rstate, pitchS, nm, reinterpret_cast<const int4*>(counts),
         reinterpret_cast<const longlong4*>(blockoff) + nblocks, base3_host[0], base3_host[1], base3_host[2], G,
         reinterpret_cast<Record*>(D), out1, ws);
-    return check_launch("fcd_bucket_fill");
+    int rc = check_launch("fcd_bucket_fill");
+    if (rc || nd == 0) return rc;
+    int64_t rgrid = (nd + kBucketThreads - 1) / kBucketThreads;
+    if (rgrid > (int64_t)sm_count() * 8) rgrid = (int64_t)sm_count() * 8;
+    bucket_records_kernel<<<(unsigned)rgrid, kBucketThreads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<Record*>(D), nd, qF, qR, U, nm, out1, ws);
+    return check_launch("fcd_bucket_fill(records)");
 }
 
 int fcd_elm_streams(const double* G, const int64_t* base3_host, const int64_t* count3_host,
@@ -404,7 +462,7 @@ int fcd_elm_streams(const double* G, const int64_t* base3_host, const int64_t* c
     const bool fast = log_table_covers(th.epsl, th.al);
     const size_t smem = fast ? tab.bytes() : 0;
     int per_sm = fast ? (int)((200 * 1024) / (smem + 1024)) : 4;
-    if (per_sm > 4) per_sm = 4;                              // 64 registers x 256 threads: 4 CTAs / SM resident
+    if (per_sm > 3) per_sm = 3;                              // __launch_bounds__(256, 3)
     if (per_sm < 1) per_sm = 1;
     const long long work = (count3_host[0] + count3_host[1] + count3_host[2]) / 2 + nd;
     long long grid = (work + kStreamEvalThreads - 1) / kStreamEvalThreads;

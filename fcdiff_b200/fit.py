@@ -395,7 +395,7 @@ class UnsharedRegionFit(object):
                 _dev.ptr(inp['P']), max(Cl, 1) * inp['pitchU'], _dev.ptr(inp['L']), Cl, U, inp['pitchU'],
                 _dev.ptr(qF[c0 * 3:]), _dev.ptr(fstate[c0:]), _dev.ptr(qR), _dev.ptr(rstate), rstate.shape[1], N,
                 _dev.ptr(inp['nm']), _dev.ptr(inp['bk_counts']), _dev.ptr(inp['bk_offs']), base3,
-                _dev.ptr(inp['bk_G']), _dev.ptr(inp['bk_D']),
+                _dev.ptr(inp['bk_G']), _dev.ptr(inp['bk_D']), nd,
                 _dev.ptr(res4.dev[3:]), _dev.ptr(_dev.workspace()), stream), "fcd_bucket_fill")
         return (_dev.ptr(inp['bk_G']), base3, count3, _dev.ptr(inp['bk_D']), nd)
 
