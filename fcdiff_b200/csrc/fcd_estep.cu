@@ -392,6 +392,196 @@ sweep_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int u0,
     }
 }
 
+// --------------------------------------------------------------- K2b fused
+// Gauss-Seidel sweep of fcdiff/fit.py:184-197 with the region weights computed
+// on the fly (no WT tensor, no region_weights pass).  With edge_lookup =
+// "reference" the edges read at step n are the contiguous window
+// [n(n-1)/2, n(n-1)/2 + N) (fit.py:185-186), and the windows of successive steps
+// slide monotonically over the patient's row of the patient-major planes: the
+// row is streamed through a shared-memory ring by TMA bulk copies (chunks of
+// kSwChunk edges: planes 0 and 1 and the edges' peak states; p_2 = 1 - p_0 - p_1,
+// an absolute error of 1e-16 on an argument >= min(a_l, eps_l)), far enough ahead
+// that no step waits for DRAM.  T threads per patient (thread t owns the regions
+// m = t, t + T, ...; their q_R stay in registers), PPC patients per CTA sharing
+// the log table; each patient group synchronises on its own named barrier.
+// Step n: partial sums from the weights W_n held in registers, warp reduction,
+// then -- while the other warps arrive -- the logs of W_{n+1} from the ring, ONE
+// barrier, and only the owner of region n normalises (fit.py:196-197).
+constexpr int kSwChunk = 256;
+constexpr int kSwSlots = 8;
+constexpr int kSwRing = kSwChunk * kSwSlots;
+
+template <int T>
+struct SweepSmem {
+    static constexpr int NW = T / 32;
+    static constexpr size_t bytes = (size_t)2 * kSwRing * 8 + kSwRing + kSwSlots * 8 + 2 * NW * 2 * 8;
+    static constexpr size_t padded = (bytes + 127) / 128 * 128;
+};
+
+template <int T, int MPT, int PPC, bool FAST>
+__global__ void __launch_bounds__(T * PPC)
+sweep_fused_kernel(const double* __restrict__ PT, int64_t planeStride, int64_t pitchC,
+                   const double* __restrict__ qF, const uint8_t* __restrict__ fstate, int64_t pitchF,
+                   int64_t C, int N, int U, int u0, int Ul, double lp0, double lp1,
+                   const __grid_constant__ ThetaDev th, const __grid_constant__ LogTabWindow tab,
+                   double* __restrict__ qR, double* __restrict__ lqR) {
+    constexpr int NW = T / 32;
+    extern __shared__ __align__(128) double s_dyn[];
+    const double* s_tab = load_log_table<FAST>(tab, s_dyn);
+    const int pp = threadIdx.x / T, tid = threadIdx.x % T, lane = tid & 31, warp = tid >> 5;
+    const int ul = blockIdx.x * PPC + pp;
+    if (ul >= Ul) return;                                    // whole patient group leaves (own barrier id)
+    unsigned char* mine = reinterpret_cast<unsigned char*>(s_dyn + (FAST ? ((tab.n + 15) & ~15) : 0)) +
+                          (size_t)pp * SweepSmem<T>::padded;
+    double* ring0 = reinterpret_cast<double*>(mine);
+    double* ring1 = ring0 + kSwRing;
+    uint8_t* fring = reinterpret_cast<uint8_t*>(ring1 + kSwRing);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(fring + kSwRing);
+    double* s_red = reinterpret_cast<double*>(bars + kSwSlots);          // [2][NW][2]
+    auto group_sync = [&]() {                                // immediate barrier ids: a register id reserves all 16
+        if (PPC == 1 || pp == 0) asm volatile("bar.sync 1, %0;" ::"n"(T) : "memory");
+        else asm volatile("bar.sync 2, %0;" ::"n"(T) : "memory");
+    };
+
+    const int u = u0 + ul;
+    const double* row0 = PT + (int64_t)ul * pitchC;
+    const double* row1 = row0 + planeStride;
+    const int nchunks = (int)((pitchC + kSwChunk - 1) / kSwChunk);
+    int next_issue = 0;                                      // meaningful in tid 0 only
+    auto issue = [&](int g) {
+        uint64_t* bar = bars + (g % kSwSlots);
+        const int64_t e0 = (int64_t)g * kSwChunk;
+        const uint32_t ne = (uint32_t)(pitchC - e0 < kSwChunk ? pitchC - e0 : kSwChunk);
+        const uint32_t nf = (uint32_t)(pitchF - e0 < kSwChunk ? pitchF - e0 : kSwChunk);
+        const int so = (g % kSwSlots) * kSwChunk;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, 2 * ne * 8 + nf);
+        tma_load_1d(ring0 + so, row0 + e0, ne * 8, bar);
+        tma_load_1d(ring1 + so, row1 + e0, ne * 8, bar);
+        tma_load_1d(fring + so, fstate + e0, nf, bar);
+    };
+    if (tid < kSwSlots) mbar_init(bars + tid, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    group_sync();
+    if (tid == 0)
+        for (; next_issue < kSwSlots && next_issue < nchunks; ++next_issue) issue(next_issue);
+
+    double q0[MPT], q1[MPT], w[MPT][3], wn[MPT][3];
+#pragma unroll
+    for (int j = 0; j < MPT; ++j) {
+        const int m = tid + j * T;
+        q0[j] = q1[j] = 0.0;
+        if (m < N) {
+            q0[j] = qR[((int64_t)m * U + u) * 2];
+            q1[j] = qR[((int64_t)m * U + u) * 2 + 1];
+        }
+    }
+    int waited = -1;                                         // chunks 0..waited have arrived (per thread)
+    const double al[3] = {th.al[0], th.al[1], th.al[2]}, bl[3] = {th.bl[0], th.bl[1], th.bl[2]};
+    auto window = [&](int n, double (&dst)[MPT][3]) {
+        const int64_t base = (int64_t)n * (n - 1) / 2;
+        int64_t last = base + N - 1;
+        if (last > C - 1) last = C - 1;
+        const int ghi = (int)(last / kSwChunk);
+        for (; waited < ghi; ++waited) mbar_wait(bars + ((waited + 1) % kSwSlots), ((waited + 1) / kSwSlots) & 1);
+        const uint32_t base_lo = (uint32_t)base;
+        bool slow = false;
+#pragma unroll
+        for (int j = 0; j < MPT; ++j) {                       // branch-free: invalid slots read a valid index, weight 0
+            const int m = tid + j * T;
+            const bool valid = m < N && m != n;
+            const uint32_t idx = (base_lo + (uint32_t)(valid ? m : 0)) & (kSwRing - 1);
+            const int k = fring[idx];
+            const double p0 = ring0[idx], p1 = ring1[idx];
+            const double p = k == 0 ? p0 : (k == 1 ? p1 : (1.0 - p0) - p1);
+            slow |= valid && k == 3;
+#pragma unroll
+            for (int l = 0; l < 3; ++l) {
+                const double lg = fast_log<FAST>(fma(bl[l], p, al[l]), s_tab);
+                dst[j][l] = valid ? lg : 0.0;
+            }
+        }
+        if (__any_sync(0xffffffffu, slow)) {                  // edges whose q_F is not peaked (rare)
+#pragma unroll
+            for (int j = 0; j < MPT; ++j) {
+                const int m = tid + j * T;
+                if (m < N && m != n) {
+                    const int64_t c = base + m;
+                    const int idx = (int)(c & (kSwRing - 1));
+                    if (fring[idx] == 3) {
+                        const double p0 = ring0[idx], p1 = ring1[idx];
+                        const double pk[3] = {p0, p1, (1.0 - p0) - p1};
+                        const double qf[3] = {__ldg(qF + c * 3), __ldg(qF + c * 3 + 1), __ldg(qF + c * 3 + 2)};
+                        dst[j][0] = dst[j][1] = dst[j][2] = 0.0;
+#pragma unroll
+                        for (int kk = 0; kk < 3; ++kk)
+#pragma unroll
+                            for (int l = 0; l < 3; ++l)
+                                dst[j][l] = fma(qf[kk], fast_log<FAST>(fma(bl[l], pk[kk], al[l]), s_tab), dst[j][l]);
+                    }
+                }
+            }
+        }
+    };
+    // one Gauss-Seidel step with the weights `cur`; leaves the next step's weights in `nxt`
+    auto step = [&](int n, const double (&cur)[MPT][3], double (&nxt)[MPT][3]) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < MPT; ++j) {                       // zero weights for m == n / m >= N
+            s0 += fma(q0[j], cur[j][0], q1[j] * cur[j][2]);   // fit.py:188-190
+            s1 += fma(q1[j], cur[j][1], q0[j] * cur[j][2]);   // fit.py:192-194
+        }
+        s0 = warp_sum(s0);
+        s1 = warp_sum(s1);
+        if (lane == 0) {
+            s_red[((n & 1) * NW + warp) * 2] = s0;
+            s_red[((n & 1) * NW + warp) * 2 + 1] = s1;
+        }
+        if (n + 1 < N) window(n + 1, nxt);                    // the logs of the next step overlap the barrier
+        group_sync();
+        if (tid == (n & (T - 1))) {                           // owner of region n
+            double a = 0.0, b = 0.0;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+                a += s_red[((n & 1) * NW + i) * 2];
+                b += s_red[((n & 1) * NW + i) * 2 + 1];
+            }
+            // lq = l - logsumexp(l), q = exp(lq) (fit.py:196-197) with one exponential
+            const double l0r = lp0 + a, l1r = lp1 + b;
+            const bool first = l0r >= l1r;
+            const double d = first ? l1r - l0r : l0r - l1r;
+            const double t = exp_nonpos(d);
+            const double lg = log1p(t);
+            const double inv = 1.0 / (1.0 + t);
+            const double lmax = -lg, lmin = d - lg;
+            const double qmax = inv, qmin = t * inv;
+            const double l0 = first ? lmax : lmin, l1 = first ? lmin : lmax;
+            const double p0 = first ? qmax : qmin, p1 = first ? qmin : qmax;
+            const int slot = n / T;
+#pragma unroll
+            for (int j = 0; j < MPT; ++j)
+                if (j == slot) {
+                    q0[j] = p0;
+                    q1[j] = p1;
+                }
+            const int64_t o = ((int64_t)n * U + u) * 2;
+            lqR[o] = l0;
+            lqR[o + 1] = l1;
+            qR[o] = p0;
+            qR[o + 1] = p1;
+        }
+        if (tid == 0 && n + 2 < N) {                          // chunks below window n+2 are dead: refill their slots
+            const int glo = (int)(((int64_t)(n + 2) * (n + 1) / 2) / kSwChunk);
+            for (; next_issue < nchunks && next_issue - kSwSlots < glo; ++next_issue) issue(next_issue);
+        }
+    };
+    window(0, w);
+    for (int n = 0; n < N; n += 2) {                          // two steps per trip: the weight sets swap roles, no moves
+        step(n, w, wn);
+        if (n + 1 < N) step(n + 1, wn, w);
+    }
+}
+
 static inline int grid_for_rows(int64_t rows, int rows_per_block, int waves) {
     int64_t need = (rows + rows_per_block - 1) / rows_per_block;
     int64_t cap = (int64_t)sm_count() * waves;
@@ -558,6 +748,48 @@ int fcd_estep_qR(const double* WT, int64_t C, int32_t N, int32_t U, int32_t u0, 
     else FCD_SWEEP(1024, 8);
 #undef FCD_SWEEP
     return check_launch("fcd_estep_qR");
+}
+
+int fcd_estep_qR_fused(const double* PT, int64_t planeStride, int64_t pitchC,
+                       const double* qF, const uint8_t* fstate, int64_t pitchF,
+                       int64_t C, int32_t N, int32_t U, int32_t u0, int32_t Ul,
+                       const double* log_pi2_host, const fcd_theta* theta_host,
+                       double* qR, double* lqR, void* stream) {
+    FCD_REQUIRE(PT != nullptr && qF != nullptr && fstate != nullptr && log_pi2_host != nullptr &&
+                theta_host != nullptr && qR != nullptr && lqR != nullptr, "fcd_estep_qR_fused: NULL argument");
+    FCD_REQUIRE(N >= 3 && N <= 1024 && C == (int64_t)N * (N - 1) / 2,
+                "fcd_estep_qR_fused: needs 3 <= N <= 1024 and C = N(N-1)/2 (got N=%d, C=%lld)", N, (long long)C);
+    FCD_REQUIRE(u0 >= 0 && Ul >= 0 && u0 + Ul <= U, "fcd_estep_qR_fused: bad patient range");
+    FCD_REQUIRE(pitchC >= C && pitchC % 2 == 0 && planeStride % 2 == 0 && pitchF >= pitchC && pitchF % 16 == 0 &&
+                ((reinterpret_cast<uintptr_t>(PT) | reinterpret_cast<uintptr_t>(fstate)) & 15) == 0,
+                "fcd_estep_qR_fused: planes / states must be 16-byte aligned, pitchC even, pitchF % 16 == 0");
+    if (Ul == 0) return 0;
+    const ThetaDev th = make_theta_dev(*theta_host, 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    LogTabWindow tab;
+    FCD_REQUIRE(log_table_window(th.epsl, th.al, st, tab), "fcd_estep_qR_fused: log table initialisation failed");
+    const bool fast = log_table_covers(th.epsl, th.al);
+    const size_t tbytes = fast ? (size_t)((tab.n + 15) & ~15) * sizeof(double) : 0;
+    const double lp0 = log_pi2_host[0], lp1 = log_pi2_host[1];
+#define FCD_SWF(T, PPC, F)                                                                              \
+    do {                                                                                                \
+        const size_t smem = tbytes + (size_t)(PPC) * SweepSmem<T>::padded;                              \
+        cudaFuncSetAttribute(sweep_fused_kernel<T, 4, PPC, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             (int)(kLogTabBytes + 128 + (PPC) * SweepSmem<T>::padded));                  \
+        sweep_fused_kernel<T, 4, PPC, F><<<(Ul + (PPC) - 1) / (PPC), (T) * (PPC), smem, st>>>(           \
+            PT, planeStride, pitchC, qF, fstate, pitchF, C, N, U, u0, Ul, lp0, lp1, th, tab, qR, lqR);   \
+    } while (0)
+#define FCD_SWF_N(F)                                                                                    \
+    do {                                                                                                \
+        if (N <= 128) FCD_SWF(32, 2, F);                                                                \
+        else if (N <= 256) FCD_SWF(64, 2, F);                                                           \
+        else if (N <= 512) FCD_SWF(128, 2, F);                                                          \
+        else FCD_SWF(256, 1, F);                                                                        \
+    } while (0)
+    if (fast) FCD_SWF_N(true); else FCD_SWF_N(false);
+#undef FCD_SWF_N
+#undef FCD_SWF
+    return check_launch("fcd_estep_qR_fused");
 }
 
 }  // extern "C"

@@ -84,7 +84,7 @@ class _Mirror(object):
             (_, q) = self.get_dev()
             if self.shape[-1] == 3:
                 C = int(np.prod(self.shape[:-1]))
-                st = _dev.empty((max(C, 1),), torch.uint8)
+                st = _dev.zeros(((max(C, 1) + 255) // 256 * 256,), torch.uint8)   # padded: moved in 256-byte chunks
                 _lib.check(lib.fcd_peak_states_F(_dev.ptr(q), C, _dev.ptr(st), _dev.stream()), "fcd_peak_states_F")
             else:
                 (N, U) = (int(self.shape[0]), int(self.shape[1]))
@@ -162,6 +162,7 @@ class UnsharedRegionFit(object):
         self.n_edges = None           # global edge count when b / bt are device edge shards
         self.optimise_theta_sub = True
         self.update_mu_sigma = False  # re-estimate mu, sigma (disabled in the reference, fit.py:232-237)
+        self.fused_sweep = False      # K2b: weights computed inside the sweep (no WT tensor; reference lookup, N <= 1024)
         self.elm_path = "auto"        # K3b form: "streams" | "tiered" | "auto" (streams unless most elements are unpeaked)
         self.convergence_rule = "reference"
         self.n_objective_evals = []
@@ -336,16 +337,15 @@ class UnsharedRegionFit(object):
                 _lib.check(lib.fcd_resp_cache(_dev.ptr(blk), C, Ul, Ul, ctypes.byref(th), _dev.ptr(src),
                                               C * max(Ul, 1), None, _dev.stream()), "fcd_resp_cache")
             (pitchU, uu0, Us) = (Ul, 0, Ul)
-        PT = _dev.empty((3, max(Ul, 1), C))
+        pitchC = _dev.even(C)                      # rows are moved by 16-byte-granular bulk copies
+        PT = _dev.zeros((3, max(Ul, 1), pitchC))
         if Ul > 0:
             with _dev.timed(self.profile, "K0_transpose"):
                 for k in range(3):
                     _lib.check(lib.fcd_transpose_patients(_dev.ptr(src[k]), C, Us, pitchU, uu0, Ul,
-                                                          _dev.ptr(PT[k]), C, _dev.stream()),
+                                                          _dev.ptr(PT[k]), pitchC, _dev.stream()),
                                "fcd_transpose_patients")
         inp['PT'] = PT
-        if inp['WT'] is None:
-            inp['WT'] = _dev.empty((Ul, C, 3))
         return inp
 
     def _result(self, n, dtype=torch.float64, tag=""):
@@ -635,14 +635,25 @@ class UnsharedRegionFit(object):
         (lqR, qR) = self._mR.get_dev()
         th = self._theta()
         fstate = self._mF.get_state()
-        with _dev.timed(self.profile, "K2b_region_weights"):
-            _lib.check(lib.fcd_region_weights(_dev.ptr(inp['PT']), max(Ul, 1) * C, Ul, C, C,
-                                              _dev.ptr(qF), _dev.ptr(fstate), ctypes.byref(th),
-                                              _dev.ptr(inp['WT']), _dev.stream()), "fcd_region_weights")
+        (PT, pitchC) = (inp['PT'], inp['PT'].shape[2])
         lqR_new, qR_new = lqR.clone(), qR.clone()
-        with _dev.timed(self.profile, "K2b_sweep"):
-            _lib.check(lib.fcd_estep_qR(_dev.ptr(inp['WT']), C, N, U, u0, Ul, log_pi2, lookup,
-                                        _dev.ptr(qR_new), _dev.ptr(lqR_new), _dev.stream()), "fcd_estep_qR")
+        if lookup == 0 and 3 <= N <= 1024 and self.fused_sweep:
+            # weights computed inside the sweep from the TMA-streamed planes: no WT tensor
+            with _dev.timed(self.profile, "K2b_sweep_fused"):
+                _lib.check(lib.fcd_estep_qR_fused(
+                    _dev.ptr(PT), max(Ul, 1) * pitchC, pitchC, _dev.ptr(qF), _dev.ptr(fstate), fstate.numel(),
+                    C, N, U, u0, Ul, log_pi2, ctypes.byref(th), _dev.ptr(qR_new), _dev.ptr(lqR_new),
+                    _dev.stream()), "fcd_estep_qR_fused")
+        else:
+            if inp['WT'] is None:
+                inp['WT'] = _dev.empty((Ul, C, 3))
+            with _dev.timed(self.profile, "K2b_region_weights"):
+                _lib.check(lib.fcd_region_weights(_dev.ptr(PT), max(Ul, 1) * pitchC, Ul, C, pitchC,
+                                                  _dev.ptr(qF), _dev.ptr(fstate), ctypes.byref(th),
+                                                  _dev.ptr(inp['WT']), _dev.stream()), "fcd_region_weights")
+            with _dev.timed(self.profile, "K2b_sweep"):
+                _lib.check(lib.fcd_estep_qR(_dev.ptr(inp['WT']), C, N, U, u0, Ul, log_pi2, lookup,
+                                            _dev.ptr(qR_new), _dev.ptr(lqR_new), _dev.stream()), "fcd_estep_qR")
         if self.shards is not None:
             self.shards.allgather_patients(lqR_new, qR_new, N, U)
         self._mR.set_dev(lqR_new, qR_new, (N, U, 2))

@@ -138,6 +138,19 @@ FCD_API int fcd_estep_qR(const double* WT, int64_t C, int32_t N, int32_t U, int3
                  const double* log_pi2_host, int32_t edge_lookup,
                  double* qR, double* lqR, void* stream);
 
+/* K2b fused -- the whole of `_update_lq_R` (fcdiff/fit.py:176-198) for the
+ * patients [u0, u0+Ul) with edge_lookup = FCD_LOOKUP_REFERENCE, without the WT
+ * tensor: the weights W[c][l] = sum_k qF[c,k] log M_kl are computed inside the
+ * sweep from the patient-major responsibility planes 0 and 1 (PT, row pitch
+ * pitchC even; p_2 = 1 - p_0 - p_1), streamed through shared memory by TMA.
+ * fstate: peak states of ALL edges, padded to pitchF >= pitchC bytes (pitchF %
+ * 16 == 0).  3 <= N <= 1024.  Other arguments as fcd_estep_qR. */
+FCD_API int fcd_estep_qR_fused(const double* PT, int64_t planeStride, int64_t pitchC,
+                       const double* qF, const uint8_t* fstate, int64_t pitchF,
+                       int64_t C, int32_t N, int32_t U, int32_t u0, int32_t Ul,
+                       const double* log_pi2_host, const fcd_theta* theta_host,
+                       double* qR, double* lqR, void* stream);
+
 /* K3a -- M-step sums; replaces `_update_pi` / `_update_gamma`
  * (fcdiff/fit.py:208-220).  out[0..2] = sum_c exp(lqF[c,k]),
  * out[3] = sum_{n,u} exp(lqR[n,u,1]).  The caller divides by counts (after an

@@ -283,9 +283,15 @@ def test_fused_steps_vs_oracle(N, H, U, lookup, peaked):
     exp_F = O.update_lq_F(th.gamma, lpB, lM, lq_R)
     nptest.assert_allclose(fit._lq_F, exp_F, rtol=1e-9, atol=1e-10)
     nptest.assert_allclose(np.exp(fit._lq_F).sum(axis=2), 1.0, rtol=1e-12)
-    # K2b
-    fit._update_lq_R()
+    # K2b (both forms: region weights + sweep over WT, and the fused sweep)
     exp_R = O.update_lq_R(np.array([1 - th.pi, th.pi]), exp_F, lM, lq_R, lookup)
+    if lookup == "reference" and N >= 3:
+        fit.fused_sweep = True
+        fit._update_lq_R()
+        nptest.assert_allclose(fit._lq_R, exp_R, rtol=1e-9, atol=1e-10)
+        fit._lq_R = lq_R
+        fit.fused_sweep = False
+    fit._update_lq_R()
     nptest.assert_allclose(fit._lq_R, exp_R, rtol=1e-9, atol=1e-10)
     # K3a
     fit._update_pi()
@@ -491,6 +497,15 @@ def test_config3_properties(N, H, U):
     whole = estep(0, C, rstate)
     nptest.assert_array_equal(estep(a, e, rstate), whole[a * 3:])
     nptest.assert_allclose(estep(0, C, r_mixed), whole, rtol=1e-12, atol=1e-9)
+    # -- K2b: the fused sweep (weights from TMA-streamed planes) equals region weights + sweep over WT
+    lqR0 = fit._lq_R.copy()
+    fit.fused_sweep = True
+    fit._update_lq_R()
+    fused = fit._lq_R.copy()
+    fit._lq_R = lqR0
+    fit.fused_sweep = False
+    fit._update_lq_R()
+    nptest.assert_allclose(fused, fit._lq_R, rtol=1e-9, atol=1e-9)
 
 
 # ------------------------------------------------------------------ kernel variants behind the C-ABI
