@@ -15,8 +15,8 @@ all-gathered -- fcdiff_b200/dist.py).
 
 A *step* is one pass of the reference's loop body (fcdiff/fit.py:76-80):
 E-step q_F (K2), region weights + Gauss-Seidel sweep for q_R (K2b), pi/gamma
-(K3a), the L-BFGS-B solve for (eta, epsilon) with J fused objective+gradient
-passes (K3b), free energy (K4).  Steps are consecutive iterations of one fit.
+(K3a), the L-BFGS-B solve for (eta, epsilon): one bucket pass, then J
+objective+gradient evaluations over the bucketed streams (K3b), free energy (K4).  Steps are consecutive iterations of one fit.
 
 value  = C*(H+U)*K / t with inputs resident in HBM (CUDA events, max over ranks)
 e2e    = the same metric through the public API from HOST (pinned) arrays: every
@@ -114,14 +114,19 @@ class ClockSampler(object):
 
 # --------------------------------------------------------------------------- algorithmic bytes
 def algorithmic_bytes(kernel, C, N, H, U):
-    """Per-launch algorithmic bytes (DESIGN.md 'Kernels')."""
+    """Per-launch algorithmic bytes (DESIGN.md 'Kernels'): 8 bytes per
+    edge-patient for every pass over the patient correlations, whatever form the
+    kernel actually reads them in."""
     return {
         "K2_estep_qF": 8 * C * U + 16 * C + 48 * C + 16 * N * U,        # bt, S1/S2, lqF+qF out, qR
         "K2b_region_weights": 8 * C * U + 24 * C + 24 * C * U,          # btT, qF, WT out
         "K2b_sweep": 24 * C * U + 16 * N * U + 32 * N * U,              # WT once (window overlaps hit L1/L2), qR in, qR/lqR out
+        "K2b_sweep_fused": 8 * C * U + 24 * C + 48 * N * U,             # btT once, qF, qR in / out
         "K3b_elm_obj_grad": 8 * C * U + 24 * C + 16 * N * U,            # bt, qF, qR
+        "K3b_elm_streams": 8 * C * U + 24 * C + 16 * N * U,             # the same evaluation from the bucketed streams
         "K3b_elm_const": 8 * C * U + 24 * C + 16 * N * U,
-        "K4_energy_terms": 8 * C * U + 64 * C + 48 * N * U,             # bt, S1/S2/lqF/qF, lqR/qR
+        "K3b_bucket_fill": 16 * C * U + 8 * C * U + 24 * C + 16 * N * U,   # p and log-density planes in, streams out
+        "K4_elm": 8 * C * U + 24 * C + 16 * N * U,
         "K3a_mstep_stats": 24 * C + 16 * N * U,
     }.get(kernel)
 
@@ -188,7 +193,8 @@ def workload_config(n_gpus):
                         "%d-region atlas (%d edges over %d GPU) x (%d controls + %d patients)" % (N, N * (N - 1) // 2, n_gpus, H_SUBJ, U_SUBJ),
             "regions": N, "edges": N * (N - 1) // 2, "controls": H_SUBJ, "patients": U_SUBJ,
             "edge_lookup": "reference", "storage": "f64",
-            "l2": "per-step working set (bt + btT + W = 1.6 GB per GPU) exceeds the 126 MB L2; no flush needed",
+            "l2": "per-step working set (responsibility planes, patient-major planes, WT, streams: > 2 GB per GPU) "
+                  "exceeds the 126 MB L2; no flush needed",
             "parallelism": "edge shards x%d, patient-sharded region sweep" % n_gpus}
 
 
@@ -377,7 +383,8 @@ def run_gpu_arm(args):
     roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
                 "unit": "GB/s", "frac": kernels[dom]["frac_of_hbm_peak"], "traffic": traffic,
                 "peak_source": peak_src,
-                "note": "fp64 transcendental-bound (9 log + 3 exp per edge-patient); see DESIGN.md"}
+                "note": "achieved = algorithmic bytes (8 B per edge-patient, SURVEY 8d) / mean launch time; "
+                        "see DESIGN.md 'Kernels' for what each kernel actually reads"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
     cpu = None

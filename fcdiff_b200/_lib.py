@@ -35,6 +35,7 @@ SIGNATURES = {
     "fcd_healthy_stats": (c_int, [_P, c_int64, c_int32, c_int64, _P, _P, _P]),
     "fcd_edge_table": (c_int, [c_int64, c_int64, _P, _P]),
     "fcd_resp_cache": (c_int, [_P, c_int64, c_int32, c_int64, POINTER(FcdTheta), _P, c_int64, _P, _P]),
+    "fcd_map_labels": (c_int, [_P, c_int64, c_int32, _P, _P]),
     "fcd_peak_states_F": (c_int, [_P, c_int64, _P, _P]),
     "fcd_peak_states_R": (c_int, [_P, c_int32, c_int32, c_int64, _P, _P]),
     "fcd_estep_qF": (c_int, [_P, _P, c_int32, _P, c_int64, c_int64, c_int32, c_int64, _P, _P, c_int64, c_int32, _P,

@@ -109,6 +109,26 @@ peak_states_R_kernel(const double* __restrict__ qR, int N, int U, int64_t pitchS
     }
 }
 
+// ---------------------------------------------------------------- MAP labels
+// labels[i] = argmax_k lq[i][k] (first maximum on ties, like numpy.argmax): the MAP
+// template state of an edge (width 3) or the MAP anomaly flag of a (region,
+// patient) pair (width 2) -- what the cited evaluation reads off the posteriors
+// (doc/methods.rst:241-246).
+__global__ void __launch_bounds__(256)
+map_labels_kernel(const double* __restrict__ lq, int64_t n, int width, uint8_t* __restrict__ labels) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double* v = lq + i * width;
+        int best = 0;
+        double bv = v[0];
+        for (int k = 1; k < width; ++k)
+            if (v[k] > bv) {
+                bv = v[k];
+                best = k;
+            }
+        labels[i] = (uint8_t)best;
+    }
+}
+
 // ------------------------------------------------------------------- K2
 // lqF[c,k] = log gamma_k + healthy_k(S1,S2) + sum_u sum_l w_l log M_kl(bt[c,u])
 //            - logsumexp_k                                 (fcdiff/fit.py:157-174)
@@ -629,6 +649,13 @@ int fcd_resp_cache(const double* bt, int64_t C, int32_t U, int64_t pitchU,
     resp_cache_kernel<<<grid_for_rows(C * pitchU, 256, 16), 256, 0, (cudaStream_t)stream>>>(
         bt, C, U, pitchU, th, P, planeStride, L);
     return check_launch("fcd_resp_cache");
+}
+
+int fcd_map_labels(const double* lq, int64_t n, int32_t width, uint8_t* labels, void* stream) {
+    FCD_REQUIRE(n >= 0 && width >= 1 && (n == 0 || (lq != nullptr && labels != nullptr)), "fcd_map_labels: bad arguments");
+    if (n == 0) return 0;
+    map_labels_kernel<<<grid_for_rows(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(lq, n, width, labels);
+    return check_launch("fcd_map_labels");
 }
 
 int fcd_peak_states_F(const double* qF, int64_t C, uint8_t* fstate, void* stream) {

@@ -658,6 +658,32 @@ class UnsharedRegionFit(object):
             self.shards.allgather_patients(lqR_new, qR_new, N, U)
         self._mR.set_dev(lqR_new, qR_new, (N, U, 2))
 
+    # ------------------------------------------------------------------ posterior summaries (new)
+    def _map_labels(self, mirror, width):
+        lib = _lib.load()
+        (lq, _) = mirror.get_dev()
+        n = lq.numel() // width
+        out = _dev.empty((max(n, 1),), torch.uint8)
+        _lib.check(lib.fcd_map_labels(_dev.ptr(lq), n, width, _dev.ptr(out), _dev.stream()), "fcd_map_labels")
+        return out[:n].cpu().numpy()
+
+    def map_template(self):
+        """(C,) MAP template state of every edge, argmax_k q_F[c, k]: 0 negative,
+        1 none, 2 positive (doc/methods.rst:107-129, 241-246)."""
+        return self._map_labels(self._mF, 3)
+
+    def map_anomalous_regions(self):
+        """(N, U) bool: region n of patient u is anomalous under the MAP of q_R."""
+        (N, H, U) = self._dims
+        return self._map_labels(self._mR, 2).reshape(N, U).astype(bool)
+
+    def anomalous_region_ranking(self):
+        """(U, N) region indices of every patient ordered by decreasing posterior
+        probability of being anomalous (the per-patient ranking the cited
+        evaluation uses)."""
+        q1 = np.exp(self._lq_R[:, :, 1])
+        return np.argsort(-q1, axis=0, kind="stable").T
+
     def _update_theta(self):
         """
         Update the parameters of the model (fcdiff/fit.py:200-206).

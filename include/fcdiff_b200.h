@@ -102,6 +102,12 @@ FCD_API int fcd_resp_cache(const double* bt, int64_t C, int32_t U, int64_t pitch
 FCD_API int fcd_peak_states_F(const double* qF, int64_t C, uint8_t* fstate, void* stream);
 FCD_API int fcd_peak_states_R(const double* qR, int32_t N, int32_t U, int64_t pitchS, uint8_t* rstate, void* stream);
 
+/* MAP labels of a log-posterior array lq [n][width]: labels[i] = argmax_k lq[i][k]
+ * (first maximum on ties).  width 3: template state of an edge (q_F of
+ * fit.py:157-174); width 2: anomaly flag of a (region, patient) pair (q_R of
+ * fit.py:176-198). */
+FCD_API int fcd_map_labels(const double* lq, int64_t n, int32_t width, uint8_t* labels, void* stream);
+
 /* K2 -- E-step for the template posterior; replaces `_update_lq_F`
  * (fcdiff/fit.py:157-174) + `_eval_q_R_w` (fit.py:382-406) + the patient half
  * of `_update_lps` (fit.py:115-122) + `_eval_M` (fit.py:409-444).

@@ -1,0 +1,68 @@
+"""Replica sweeps (BASELINE.json configs[4]) and posterior summaries on the GPU."""
+import numpy as np
+import numpy.testing as nptest
+import pytest
+import torch
+
+from oracle import iar_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+import fcdiff_b200 as fcdiff          # noqa: E402
+from fcdiff_b200 import sweep         # noqa: E402
+
+
+def _problem(N=12, H=14, U=10, seed=3):
+    (_, _, _, _, b, bt) = O.sample(O.Theta(), N, H, U, np.random.RandomState(seed))
+    corr = np.concatenate([b, bt], axis=1)
+    labels = np.r_[np.zeros(H, bool), np.ones(U, bool)]
+    return b, bt, corr, labels
+
+
+def test_permutation_sweep_matches_individual_fits_and_the_oracle():
+    (b, bt, corr, labels) = _problem()
+    opts = dict(max_iters=3, rel_tol=-1.0)
+    res = sweep.permutation_sweep(corr, labels, 4, seed=7, fit_options=opts)
+    assert sorted(res) == [0, 1, 2, 3, 4]
+    lab = sweep.permuted_labels(labels, 4, seed=7)
+    assert np.all(lab.sum(axis=1) == labels.sum())
+    for i in (0, 3):
+        th = O.Theta()
+        out = O.run(np.ascontiguousarray(corr[:, ~lab[i]]), np.ascontiguousarray(corr[:, lab[i]]), th,
+                    max_iters=3, rel_tol=-1.0)
+        nptest.assert_allclose(res[i]["energy"], out["energy"], rtol=1e-6)
+        nptest.assert_allclose([res[i]["pi"], res[i]["eta"], res[i]["epsilon"]], [th.pi, th.eta, th.epsilon], rtol=1e-6)
+    # replicas can be split over ranks without changing any of them
+    parts = {}
+    for r in range(2):
+        parts.update(sweep.permutation_sweep(corr, labels, 4, seed=7, fit_options=opts, rank=r, world=2, gather=False))
+    assert sorted(parts) == sorted(res)
+    for i in res:
+        assert parts[i]["energy"] == res[i]["energy"]
+    assert 0.0 < sweep.permutation_p_value(res) <= 1.0
+
+
+def test_restart_sweep_returns_the_lowest_energy():
+    (b, bt, _, _) = _problem()
+    (res, best) = sweep.restart_sweep(b, bt, 3, seed=1, fit_options=dict(max_iters=4))
+    assert sorted(res) == [0, 1, 2, 3]
+    assert res[best]["energy"][-1] == min(r["energy"][-1] for r in res.values())
+
+
+def test_map_labels_and_ranking():
+    (b, bt, _, _) = _problem(N=9, H=8, U=7, seed=5)
+    fit = fcdiff.fit.UnsharedRegionFit()
+    fit.model = fcdiff.UnsharedRegionModel()
+    (fit.b, fit.bt) = (b, bt)
+    fit.max_iters = 2
+    fit.run()
+    nptest.assert_array_equal(fit.map_template(), np.argmax(fit._lq_F[:, 0, :], axis=1))
+    nptest.assert_array_equal(fit.map_anomalous_regions(), np.argmax(fit._lq_R, axis=2).astype(bool))
+    rank = fit.anomalous_region_ranking()
+    assert rank.shape == (7, 9)
+    q1 = np.exp(fit._lq_R[:, :, 1])
+    for u in range(7):
+        assert np.all(np.diff(q1[rank[u], u]) <= 0)
+    # ties resolve to the first maximum, like numpy.argmax
+    fit._lq_F = np.log(np.full((36, 1, 3), 1.0 / 3))
+    nptest.assert_array_equal(fit.map_template(), np.zeros(36, dtype=np.uint8))

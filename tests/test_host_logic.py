@@ -172,3 +172,27 @@ def test_direct_lbfgsb_driver_is_bit_identical_to_scipy_minimize():
         r2 = scipy.optimize.minimize(counted, x0, jac=True, method="L-BFGS-B", bounds=[(1e-5, 1 - 1e-5)] * 2)
         np.testing.assert_array_equal(r.x, r2.x)
         assert r.nfev == n[0]
+
+
+def test_replica_split_and_label_permutations():
+    """Host logic of the replica sweeps (fcdiff_b200/sweep.py): every replica is
+    handled by exactly one rank; permutations preserve the group sizes and are
+    reproducible from the seed."""
+    import ast
+    import os
+    src = open(os.path.join(os.path.dirname(__file__), "..", "fcdiff_b200", "sweep.py")).read()
+    tree = ast.parse(src)
+    ns = {"np": np}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("replica_indices", "permuted_labels"):
+            exec(compile(ast.Module([node], []), "sweep.py", "exec"), ns)
+    for (n, world) in ((1001, 8), (5, 8), (16, 4)):
+        seen = sorted(i for r in range(world) for i in ns["replica_indices"](n, r, world))
+        assert seen == list(range(n))
+        sizes = [len(ns["replica_indices"](n, r, world)) for r in range(world)]
+        assert max(sizes) - min(sizes) <= 1
+    labels = np.r_[np.zeros(7, bool), np.ones(5, bool)]
+    a = ns["permuted_labels"](labels, 6, seed=3)
+    assert a.shape == (7, 12) and np.array_equal(a[0], labels) and np.all(a.sum(axis=1) == 5)
+    assert np.array_equal(a, ns["permuted_labels"](labels, 6, seed=3))
+    assert not np.array_equal(a[1], a[2])
