@@ -64,6 +64,14 @@ class EdgeShards(object):
         dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
         return out
 
+    def any_rank(self, flag):
+        """True on every rank if ``flag`` is true on any rank (one tiny all-reduce):
+        used where the ranks must agree on a code path whose collectives differ."""
+        dev = "cuda" if (torch.cuda.is_available() and dist.get_backend(self.group) == "nccl") else "cpu"
+        t = torch.tensor([1.0 if flag else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return bool(t.item() > 0)
+
     def fix_replicated(self, host_vec, idxs):
         """Undo the summation of entries that were complete on every rank."""
         keep = set(idxs)

@@ -366,6 +366,8 @@ class UnsharedRegionFit(object):
         (N, H, U) = self._dims
         (c0, Cl) = (inp['c0'], inp['Cl'])
         if Cl == 0:
+            if self.shards is not None and self.elm_path != "tiered":
+                self.shards.any_rank(True)     # keep the collective sequence of _build_streams aligned
             return None
         (_, qF) = self._mF.get_dev()
         (_, qR) = self._mR.get_dev()
@@ -380,7 +382,10 @@ class UnsharedRegionFit(object):
                                             _dev.ptr(inp['nm']), Cl, U, _dev.ptr(inp['bk_counts']),
                                             _dev.ptr(inp['bk_offs']), _dev.ptr(tot.dev), stream), "fcd_bucket_count")
         (n0, n1, n2, nd) = (int(v) for v in tot.read(stream))
-        if self.elm_path == "auto" and nd * 4 > Cl * U:
+        use_tiered = self.elm_path == "auto" and nd * 4 > Cl * U
+        if self.shards is not None:            # the ranks must take the same form: its collectives differ
+            use_tiered = self.shards.any_rank(use_tiered)
+        if use_tiered:
             return None
         base = [0, n0 + (n0 & 1), 0]
         base[2] = base[1] + n1 + (n1 & 1)

@@ -16,8 +16,9 @@ from fcdiff_b200 import dist as fdist       # noqa: E402
 from oracle import iar_oracle as O          # noqa: E402
 
 
-def run(b, bt, shards, device_shards=False, n_edges=None):
+def run(b, bt, shards, device_shards=False, n_edges=None, fused=False):
     fit = fcdiff.fit.UnsharedRegionFit()
+    fit.fused_sweep = fused
     fit.model = fcdiff.UnsharedRegionModel()
     fit.model.eta += 0.1
     fit.b, fit.bt = b, bt
@@ -40,7 +41,8 @@ def main():
         (c0, Cl) = shards.span(C)
         dev = run(torch.from_numpy(b[c0:c0 + Cl]).cuda(), torch.from_numpy(bt[c0:c0 + Cl]).cuda(), shards,
                   device_shards=True, n_edges=C)             # device edge shards + all-to-all re-layout
-        for name, f in (("host-sharded", sharded), ("device-sharded", dev)):
+        fus = run(b, bt, shards, fused=True)                 # fused sweep on the patient shards
+        for name, f in (("host-sharded", sharded), ("device-sharded", dev), ("host-sharded, fused sweep", fus)):
             e = np.max(np.abs(np.array(f.energy) / np.array(single.energy) - 1))
             dF = np.max(np.abs(f._lq_F - single._lq_F))
             dR = np.max(np.abs(f._lq_R - single._lq_R))
@@ -50,7 +52,19 @@ def main():
             ok = ok and good
             if rank == 0:
                 print("N=%d %s: iters %d energy rel %.2e  lqF %.2e  lqR %.2e  theta %.2e  %s"
-                      % (N, name, len(f.energy) - 1, e, dF, dR, dth, "OK" if good else "MISMATCH"))
+                      % (N, name, len(f.energy) - 1, e, dF, dR, dth, "OK" if good else "MISMATCH"), flush=True)
+    # replica sweep: 5 labellings split over the ranks, gathered at the end, equal to rank-local runs
+    from fcdiff_b200 import sweep
+    (_, _, _, _, b, bt) = O.sample(O.Theta(), 12, 14, 10, np.random.RandomState(3))
+    corr = np.concatenate([b, bt], axis=1)
+    labels = np.r_[np.zeros(14, bool), np.ones(10, bool)]
+    opts = dict(max_iters=3, rel_tol=-1.0)
+    res = sweep.permutation_sweep(corr, labels, 4, seed=7, fit_options=opts, rank=rank, world=dist.get_world_size())
+    ref = sweep.permutation_sweep(corr, labels, 4, seed=7, fit_options=opts, gather=False)
+    good = sorted(res) == sorted(ref) and all(res[i]["energy"] == ref[i]["energy"] for i in ref)
+    ok = ok and good
+    if rank == 0:
+        print("replica sweep over %d ranks: %s" % (dist.get_world_size(), "OK" if good else "MISMATCH"))
     t = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
