@@ -285,7 +285,7 @@ __device__ __forceinline__ void stream_tiered(const double* __restrict__ P, int6
 
     // ---- issue side (warp-uniform state; lane 0 talks to the TMA unit)
     int64_t pc = c_first;
-    int ps = 0, pit = 0;
+    int ps = 0, pd = 0;                                      // next segment / ring slot to issue
     int cur_nm = 0, cur_k = 0, nxt_nm = 0, nxt_k = 0;
     if (pc < C) {
         cur_nm = __ldg(nm + pc);
@@ -297,7 +297,7 @@ __device__ __forceinline__ void stream_tiered(const double* __restrict__ P, int6
     }
     auto issue = [&]() {
         if (pc >= C) return;
-        const int d = pit % D;
+        const int d = pd;
         if (lane == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the warp's reads of this slot are done
             descs[d] = make_int4(cur_k, cur_nm, 0, 0);
@@ -317,7 +317,7 @@ __device__ __forceinline__ void stream_tiered(const double* __restrict__ P, int6
             tma_load_1d(st + NPL * SEG * 8 + SEG, rstate + (int64_t)((cur_nm >> 16) & 0xffff) * pitchS + u0,
                         (uint32_t)ns, bars + d);
         }
-        ++pit;
+        if (++pd == D) pd = 0;
         if (++ps == nseg) {
             ps = 0;
             pc += nW;
@@ -333,11 +333,11 @@ __device__ __forceinline__ void stream_tiered(const double* __restrict__ P, int6
 
     // ---- consume side
     const unsigned lt = (1u << lane) - 1u;
-    int qhead = 0, qtail = 0, it = 0, row = 0;
+    int qhead = 0, qtail = 0, row = 0, d = 0;
+    uint32_t phase = 0;
     for (int64_t c = c_first; c < C; c += nW, ++row) {
-        for (int s = 0; s < nseg; ++s, ++it) {
-            const int d = it % D;
-            mbar_wait(bars + d, (it / D) & 1);
+        for (int s = 0; s < nseg; ++s) {
+            mbar_wait(bars + d, phase);
             const int4 ds = descs[d];
             const int k = ds.x, n = ds.y & 0xffff, m = (ds.y >> 16) & 0xffff;
             const unsigned char* st = ring + (size_t)d * G::kStageBytes;
@@ -406,6 +406,10 @@ __device__ __forceinline__ void stream_tiered(const double* __restrict__ P, int6
                 __syncwarp();
             }
             if (row_done) row_end(c);
+            if (++d == D) {
+                d = 0;
+                phase ^= 1;
+            }
         }
     }
 }

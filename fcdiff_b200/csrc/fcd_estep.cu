@@ -328,7 +328,7 @@ sweep_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int u0,
     const int u = u0 + ul;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double* Wu = WT + (int64_t)ul * C * 3;
-    double q0[MPT], q1[MPT], w[MPT][3], wn[MPT][3];
+    double q0[MPT], q1[MPT];
 #pragma unroll
     for (int j = 0; j < MPT; ++j) {
         const int m = tid + j * T;
@@ -354,9 +354,12 @@ sweep_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int u0,
             }
         }
     };
-    load_w(0, w);
-    for (int n = 0; n < N; ++n) {
-        load_w(n + 1, wn);                            // prefetch the next window
+    // One Gauss-Seidel step with the window `w`; the window of step n + 2 is requested
+    // into `far` first (the loads do not depend on q_R), so that every window has two
+    // steps to arrive.  The three register sets take turns (steps are unrolled by
+    // three): no set is ever copied, a copy would wait for its loads.
+    auto step = [&](int n, const double (&w)[MPT][3], double (&far)[MPT][3]) {
+        load_w(n + 2, far);
         double s0 = 0.0, s1 = 0.0;
 #pragma unroll
         for (int j = 0; j < MPT; ++j) {               // zero weights for m == n / m >= N
@@ -384,8 +387,13 @@ sweep_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int u0,
             const bool first = l0r >= l1r;
             const double d = first ? l1r - l0r : l0r - l1r;
             const double t = exp_nonpos(d);
-            const double lg = log1p(t);
-            const double inv = 1.0 / (1.0 + t);
+            // most regions are decided: below 2^-54, log1p(t) = t and 1/(1+t) = 1 to rounding
+            // (skips the two long dependent chains of the step's critical path)
+            double lg = t, inv = 1.0;
+            if (t >= 5.551115123125783e-17) {
+                lg = log1p(t);
+                inv = 1.0 / (1.0 + t);
+            }
             const double lmax = -lg, lmin = d - lg;
             const double qmax = inv, qmin = t * inv;
             const double l0 = first ? lmax : lmin, l1 = first ? lmin : lmax;
@@ -403,12 +411,14 @@ sweep_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int u0,
             qR[o] = p0;
             qR[o + 1] = p1;
         }
-#pragma unroll
-        for (int j = 0; j < MPT; ++j) {
-            w[j][0] = wn[j][0];
-            w[j][1] = wn[j][1];
-            w[j][2] = wn[j][2];
-        }
+    };
+    double wa[MPT][3], wb[MPT][3], wc[MPT][3];
+    load_w(0, wa);
+    load_w(1, wb);
+    for (int n = 0; n < N; n += 3) {
+        step(n, wa, wc);
+        if (n + 1 < N) step(n + 1, wb, wa);
+        if (n + 2 < N) step(n + 2, wc, wb);
     }
 }
 
@@ -571,8 +581,13 @@ sweep_fused_kernel(const double* __restrict__ PT, int64_t planeStride, int64_t p
             const bool first = l0r >= l1r;
             const double d = first ? l1r - l0r : l0r - l1r;
             const double t = exp_nonpos(d);
-            const double lg = log1p(t);
-            const double inv = 1.0 / (1.0 + t);
+            // most regions are decided: below 2^-54, log1p(t) = t and 1/(1+t) = 1 to rounding
+            // (skips the two long dependent chains of the step's critical path)
+            double lg = t, inv = 1.0;
+            if (t >= 5.551115123125783e-17) {
+                lg = log1p(t);
+                inv = 1.0 / (1.0 + t);
+            }
             const double lmax = -lg, lmin = d - lg;
             const double qmax = inv, qmin = t * inv;
             const double l0 = first ? lmax : lmin, l1 = first ? lmin : lmax;
