@@ -317,10 +317,10 @@ region_weights_kernel(const double* __restrict__ PT, int64_t planeStride,
 // finishes the reduction, normalises (fit.py:196) and updates its register
 // copy of q_R[n] (fit.py:197) while the other threads already run step n+1.
 // The two-slot s_red buffer makes the single barrier per step sufficient.
-template <int T, int MPT>
+template <int T, int MPT, int LOOKUP>
 __global__ void __launch_bounds__(T)
 sweep_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int u0,
-             int lookup, double lp0, double lp1,
+             double lp0, double lp1,
              double* __restrict__ qR, double* __restrict__ lqR) {
     constexpr int NW = T / 32;
     __shared__ double s_red[2][NW][2];
@@ -338,19 +338,37 @@ sweep_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int u0,
             q1[j] = qR[((int64_t)m * U + u) * 2 + 1];
         }
     }
+    // reference lookup: the window of step n starts at Wu + 3 n(n-1)/2 and moves by 3n doubles per
+    // step (fit.py:185-186): one running pointer, no index arithmetic per edge
+    const double* win = Wu + 3 * tid;                 // window of the next load_w call (n_next), thread's first edge
+    int n_next = 0;
     auto load_w = [&](int n, double (&dst)[MPT][3]) {
-        const int64_t base = (int64_t)n * (n - 1) / 2;
+        if (LOOKUP == FCD_LOOKUP_REFERENCE) {         // load_w is called with n = 0, 1, 2, ... in order
 #pragma unroll
-        for (int j = 0; j < MPT; ++j) {
-            const int m = tid + j * T;
-            dst[j][0] = dst[j][1] = dst[j][2] = 0.0;
-            if (m < N && m != n && n < N) {
-                const int64_t c = (lookup == FCD_LOOKUP_REFERENCE || m < n)
-                                      ? base + m
-                                      : (int64_t)m * (m - 1) / 2 + n;
-                dst[j][0] = __ldg(Wu + c * 3);
-                dst[j][1] = __ldg(Wu + c * 3 + 1);
-                dst[j][2] = __ldg(Wu + c * 3 + 2);
+            for (int j = 0; j < MPT; ++j) {
+                const int m = tid + j * T;
+                dst[j][0] = dst[j][1] = dst[j][2] = 0.0;
+                if (m < N && m != n && n < N) {
+                    const double* p = win + 3 * j * T;
+                    dst[j][0] = __ldg(p);
+                    dst[j][1] = __ldg(p + 1);
+                    dst[j][2] = __ldg(p + 2);
+                }
+            }
+            win += 3 * n_next;                        // base(n + 1) - base(n) = n
+            ++n_next;
+        } else {
+            const int64_t base = (int64_t)n * (n - 1) / 2;
+#pragma unroll
+            for (int j = 0; j < MPT; ++j) {
+                const int m = tid + j * T;
+                dst[j][0] = dst[j][1] = dst[j][2] = 0.0;
+                if (m < N && m != n && n < N) {
+                    const int64_t c = m < n ? base + m : (int64_t)m * (m - 1) / 2 + n;
+                    dst[j][0] = __ldg(Wu + c * 3);
+                    dst[j][1] = __ldg(Wu + c * 3 + 1);
+                    dst[j][2] = __ldg(Wu + c * 3 + 2);
+                }
             }
         }
     };
@@ -778,7 +796,12 @@ int fcd_estep_qR(const double* WT, int64_t C, int32_t N, int32_t U, int32_t u0, 
     cudaStream_t st = (cudaStream_t)stream;
     const double lp0 = log_pi2_host[0], lp1 = log_pi2_host[1];
 #define FCD_SWEEP(T, M)                                                                            \
-    sweep_kernel<T, M><<<Ul, T, 0, st>>>(WT, C, N, U, u0, edge_lookup, lp0, lp1, qR, lqR)
+    do {                                                                                           \
+        if (edge_lookup == FCD_LOOKUP_REFERENCE)                                                   \
+            sweep_kernel<T, M, FCD_LOOKUP_REFERENCE><<<Ul, T, 0, st>>>(WT, C, N, U, u0, lp0, lp1, qR, lqR); \
+        else                                                                                       \
+            sweep_kernel<T, M, FCD_LOOKUP_SYMMETRIC><<<Ul, T, 0, st>>>(WT, C, N, U, u0, lp0, lp1, qR, lqR); \
+    } while (0)
     if (N <= 32) FCD_SWEEP(32, 1);
     else if (N <= 64) FCD_SWEEP(32, 2);
     else if (N <= 128) FCD_SWEEP(64, 2);
