@@ -382,6 +382,130 @@ elm_streams_kernel(const double* __restrict__ G, long long base0, long long base
     grid_reduce_store<3, kStreamEvalThreads>(v, ws, out);
 }
 
+// The same evaluation with the streams staged through shared memory by the TMA unit:
+// the bytes in flight no longer depend on registers (the register version above
+// stalls on its loads at ~55 % of the HBM peak).  One persistent CTA of 16 warps per
+// SM; the three streams are cut into chunks of kEvChunk doubles, numbered across the
+// streams, and warp g takes the chunks g, g + G, ...; every warp runs a private ring
+// of kEvDepth stages (one 1-D bulk copy and one mbarrier per stage) and refills a
+// stage as soon as it has consumed it.
+constexpr int kEvChunk = 256;
+constexpr int kEvDepth = 4;
+constexpr int kEvWarps = 16;
+constexpr int kEvThreads = kEvWarps * 32;
+
+template <bool GRAD, bool FAST>
+__global__ void __launch_bounds__(kEvThreads, 1)
+elm_streams_tma_kernel(const double* __restrict__ G, long long base0, long long base1, long long base2,
+                       long long n0, long long n1, long long n2,
+                       const Record* __restrict__ D, long long nd,
+                       const __grid_constant__ ThetaDev th, const __grid_constant__ LogTabWindow tab,
+                       double* __restrict__ out, double* __restrict__ ws) {
+    extern __shared__ __align__(128) double s_dyn[];
+    const double* s_tab = load_log_table<FAST>(tab, s_dyn);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* ring = s_dyn + (FAST ? ((tab.n + 15) & ~15) : 0) + (size_t)warp * kEvDepth * kEvChunk;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_dyn + (FAST ? ((tab.n + 15) & ~15) : 0) +
+                                                 (size_t)kEvWarps * kEvDepth * kEvChunk) + warp * kEvDepth;
+    if (lane < kEvDepth) mbar_init(bars + lane, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+
+    // chunks are numbered across the streams; a warp's position is (stream l, chunk i of that stream)
+    const long long nq[3] = {(n0 + kEvChunk - 1) / kEvChunk, (n1 + kEvChunk - 1) / kEvChunk,
+                             (n2 + kEvChunk - 1) / kEvChunk};
+    const long long nn[3] = {n0, n1, n2}, bb[3] = {base0, base1, base2};
+    const long long W = (long long)gridDim.x * kEvWarps;
+    struct Pos {
+        int l;
+        long long i;
+    };
+    auto normalise = [&](Pos& p) {                           // carry into the next stream(s)
+        while (p.l < 3 && p.i >= (p.l == 0 ? nq[0] : (p.l == 1 ? nq[1] : nq[2]))) {
+            p.i -= (p.l == 0 ? nq[0] : (p.l == 1 ? nq[1] : nq[2]));
+            ++p.l;
+        }
+    };
+    Pos ip = {0, (long long)blockIdx.x * kEvWarps + warp};   // next chunk to issue
+    normalise(ip);
+    int pd = 0;
+    auto issue = [&]() {
+        if (ip.l >= 3) return;
+        if (lane == 0) {
+            const long long n = ip.l == 0 ? nn[0] : (ip.l == 1 ? nn[1] : nn[2]);
+            const long long b = ip.l == 0 ? bb[0] : (ip.l == 1 ? bb[1] : bb[2]);
+            const long long left = n - ip.i * kEvChunk;
+            const uint32_t cnt = (uint32_t)(left < kEvChunk ? left : kEvChunk);
+            const uint32_t bytes = ((cnt + 1) & ~1u) * 8;    // even element count: 16-byte granules
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bars + pd, bytes);
+            tma_load_1d(ring + pd * kEvChunk, G + b + ip.i * kEvChunk, bytes, bars + pd);
+        }
+        ip.i += W;
+        normalise(ip);
+        if (++pd == kEvDepth) pd = 0;
+    };
+#pragma unroll 1
+    for (int i = 0; i < kEvDepth; ++i) issue();
+
+    double obj = 0.0, gl[3] = {0.0, 0.0, 0.0};
+    const double al[3] = {th.al[0], th.al[1], th.al[2]}, bl[3] = {th.bl[0], th.bl[1], th.bl[2]};
+    int d = 0;
+    uint32_t phase = 0;
+    Pos cp = {0, (long long)blockIdx.x * kEvWarps + warp};
+    normalise(cp);
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {                            // the warp's chunks of stream l: constants in registers
+        const double a = al[l], b = bl[l];
+        StreamAcc a0 = {0.0, 0.0}, a1 = {0.0, 0.0};
+        while (cp.l == l) {
+            const long long left = nn[l] - cp.i * kEvChunk;
+            mbar_wait(bars + d, phase);
+            const double* st = ring + d * kEvChunk;
+            if (left >= kEvChunk) {
+#pragma unroll
+                for (int j = 0; j < kEvChunk / 64; ++j) {
+                    const double2 v = *reinterpret_cast<const double2*>(st + 64 * j + 2 * lane);
+                    stream_elem<GRAD, FAST>(v.x, a, b, s_tab, a0);
+                    stream_elem<GRAD, FAST>(v.y, a, b, s_tab, a1);
+                }
+            } else {
+                for (int e = lane; e < (int)left; e += 32) stream_elem<GRAD, FAST>(st[e], a, b, s_tab, a0);
+            }
+            __syncwarp();
+            issue();
+            if (++d == kEvDepth) {
+                d = 0;
+                phase ^= 1;
+            }
+            cp.i += W;
+            normalise(cp);
+        }
+        obj += a0.obj + a1.obj;
+        gl[l] = a0.g + a1.g;
+    }
+    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long nth = (long long)gridDim.x * blockDim.x;
+    for (long long i = tid; i < nd; i += nth) {
+        const double4 r = *reinterpret_cast<const double4*>(D + i);
+        const double w[3] = {r.y, r.z, r.w};
+        const double num = mix_num(r.x);
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            const double M = mix_rel(th, l, r.x);
+            if (GRAD) {
+                double rcp;
+                obj = fma(w[l], fast_log_rcp<FAST>(M, s_tab, rcp), obj);
+                gl[l] = fma(w[l], num * rcp, gl[l]);
+            } else {
+                obj = fma(w[l], fast_log<FAST>(M, s_tab), obj);
+            }
+        }
+    }
+    double v[3] = {obj, -(2.0 * th.epsilon - 1.0) * gl[2], -(-gl[0] + gl[1] + (2.0 * th.eta - 1.0) * gl[2])};
+    grid_reduce_store<3, kEvThreads>(v, ws, out);
+}
+
 static inline int rows_grid(int64_t rows, int rows_per_block, int waves) {
     int64_t need = (rows + rows_per_block - 1) / rows_per_block;
     int64_t cap = (int64_t)sm_count() * waves;
@@ -460,21 +584,22 @@ int fcd_elm_streams(const double* G, const int64_t* base3_host, const int64_t* c
     LogTabWindow tab;
     FCD_REQUIRE(log_table_window(th.epsl, th.al, st, tab), "fcd_elm_streams: log table initialisation failed");
     const bool fast = log_table_covers(th.epsl, th.al);
-    const size_t smem = fast ? tab.bytes() : 0;
-    int per_sm = fast ? (int)((200 * 1024) / (smem + 1024)) : 4;
-    if (per_sm > 3) per_sm = 3;                              // __launch_bounds__(256, 3)
-    if (per_sm < 1) per_sm = 1;
-    const long long work = (count3_host[0] + count3_host[1] + count3_host[2]) / 2 + nd;
-    long long grid = (work + kStreamEvalThreads - 1) / kStreamEvalThreads;
-    if (grid > (long long)sm_count() * per_sm) grid = (long long)sm_count() * per_sm;
+    const size_t tbytes = fast ? (size_t)((tab.n + 15) & ~15) * sizeof(double) : 0;
+    const size_t smem = tbytes + (size_t)kEvWarps * kEvDepth * (kEvChunk * 8 + 8);
+    const long long chunks = (count3_host[0] + kEvChunk - 1) / kEvChunk + (count3_host[1] + kEvChunk - 1) / kEvChunk +
+                             (count3_host[2] + kEvChunk - 1) / kEvChunk;
+    long long grid = (chunks + kEvWarps - 1) / kEvWarps;
+    const long long dgrid = (nd + kEvThreads - 1) / kEvThreads;
+    if (grid < dgrid) grid = dgrid;
+    if (grid > sm_count()) grid = sm_count();                // one persistent CTA per SM
     if (grid < 1) grid = 1;
-#define FCD_ES(G_, F_)                                                                               \
-    do {                                                                                             \
-        cudaFuncSetAttribute(elm_streams_kernel<G_, F_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                             (int)kLogTabBytes);                                                     \
-        elm_streams_kernel<G_, F_><<<(unsigned)grid, kStreamEvalThreads, smem, st>>>(                \
+#define FCD_ES(G_, F_)                                                                                   \
+    do {                                                                                                 \
+        cudaFuncSetAttribute(elm_streams_tma_kernel<G_, F_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             (int)(kLogTabBytes + 128 + (size_t)kEvWarps * kEvDepth * (kEvChunk * 8 + 8))); \
+        elm_streams_tma_kernel<G_, F_><<<(unsigned)grid, kEvThreads, smem, st>>>(                        \
             G, base3_host[0], base3_host[1], base3_host[2], count3_host[0], count3_host[1], count3_host[2], \
-            reinterpret_cast<const Record*>(D), nd, th, tab, out3, ws);                               \
+            reinterpret_cast<const Record*>(D), nd, th, tab, out3, ws);                                   \
     } while (0)
     if (want_grad) { if (fast) FCD_ES(true, true); else FCD_ES(true, false); }
     else           { if (fast) FCD_ES(false, true); else FCD_ES(false, false); }
