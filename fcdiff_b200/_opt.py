@@ -56,10 +56,10 @@ def _minimize_direct(fun, x0, lower, upper, m=10, ftol=2.2204460492503131e-09, g
         _lbfgsb.setulb(m, x, low_bnd, upper_bnd, nbd, f, g, factr, gtol, wa, iwa, task, lsave, isave, dsave,
                        maxls, ln_task)
         if task[0] == 3:
-            (fv, gv) = fun(np.array(x))
+            (fv, gv) = fun(x)
             nfev += 1
-            f = np.array(fv, dtype=np.float64)
-            g = np.asarray(gv, dtype=np.float64)
+            f[...] = fv
+            g[...] = gv
         elif task[0] == 1:
             nit += 1
             if nit >= maxiter:

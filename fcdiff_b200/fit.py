@@ -877,7 +877,33 @@ class UnsharedRegionFit(object):
             self._update_lps()
         # scipy.optimize.minimize(..., method="L-BFGS-B", bounds=[(eps, 1 - eps)] * 2) of fit.py:228-241,
         # driven without SciPy's Python front end (same compiled routine, same iterates: _opt.py)
-        opt_result = _opt.minimize_lbfgsb(self._objective, theta_sub, [eps, eps], [1 - eps, 1 - eps])
+        fun = self._objective
+        if self.shards is None:
+            # the optimiser's inner loop: everything pre-bound, one launch + one download per evaluation
+            ctx = self._objective_context()
+            (th, fn, head, tail, res) = (ctx['th'], ctx['fn'], ctx['head'], ctx['tail'], ctx['res'])
+            (read, stream, const, evals) = (res.read, ctx['stream'], ctx['const'], self._evals)
+            (verF, verR, name) = (ctx['verF'], ctx['verR'], ctx['name'])
+
+            timed = self.profile
+
+            def fun(x):
+                th.eta = float(x[0])
+                th.epsilon = float(x[1])
+                if timed is None:
+                    rc = fn(*head, 1, *tail)
+                else:
+                    with timed(name):
+                        rc = fn(*head, 1, *tail)
+                if rc != 0:
+                    _lib.check(rc, name)
+                o = read(stream)
+                elm = float(o[0]) + (float(o[3]) if const is None else const)
+                evals.append(dict(x=(th.eta, th.epsilon), verF=verF, verR=verR, elm=elm))
+                return -elm, o[1:3]
+
+        opt_result = _opt.minimize_lbfgsb(fun, theta_sub, [eps, eps], [1 - eps, 1 - eps])
+        del self._evals[:-4]
         self.n_objective_evals.append(opt_result.nfev)
         self._unpack_theta_sub(opt_result.x)
 
