@@ -179,6 +179,12 @@ bucket_fill_kernel(const double* __restrict__ P, int64_t planeStride, const doub
             const int n = v & 0xffff, m = (v >> 16) & 0xffff;
             const longlong4 o = s_off[r];
             long long pos[4] = {base0 + o.x, base1 + o.y, base2 + o.z, o.w};
+            // 32-bit running offsets from the row's four stream positions
+            double* const g0 = G + pos[0];
+            double* const g1 = G + pos[1];
+            double* const g2 = G + pos[2];
+            Record* const d3 = D + pos[3];
+            uint32_t off0 = 0, off1 = 0, off2 = 0, off3 = 0;
             if (k == kStateMixedF) {                         // three records per element, tagged with their state
                 for (int u = lane; u < U; u += 32) {
                     const int64_t i = c * pitchU + u;
@@ -229,21 +235,21 @@ bucket_fill_kernel(const double* __restrict__ P, int64_t planeStride, const doub
                     const unsigned b2 = __ballot_sync(0xffffffffu, code == 2);
                     const unsigned b3 = __ballot_sync(0xffffffffu, code == 3);
                     const unsigned mine = code == 0 ? b0 : (code == 1 ? b1 : (code == 2 ? b2 : b3));
-                    const long long at = (code == 0 ? pos[0] : (code == 1 ? pos[1] : (code == 2 ? pos[2] : pos[3]))) +
-                                         __popc(mine & lt);
-                    if (code < 3) G[at] = p;
+                    const uint32_t at = (code == 0 ? off0 : (code == 1 ? off1 : (code == 2 ? off2 : off3))) +
+                                        __popc(mine & lt);
+                    if (code < 3) (code == 0 ? g0 : (code == 1 ? g1 : g2))[at] = p;
                     if (code == 3) {                         // weights are filled in by bucket_records_kernel
                         Record rec;
                         rec.p = p;
                         rec.w0 = lv;
                         rec.w1 = __hiloint2double((int)c, u + e);
                         rec.w2 = 0.0;
-                        D[at] = rec;
+                        d3[at] = rec;
                     }
-                    pos[0] += __popc(b0);
-                    pos[1] += __popc(b1);
-                    pos[2] += __popc(b2);
-                    pos[3] += __popc(b3);
+                    off0 += __popc(b0);
+                    off1 += __popc(b1);
+                    off2 += __popc(b2);
+                    off3 += __popc(b3);
                     cs += code < 3 ? lv : 0.0;
                 }
             };

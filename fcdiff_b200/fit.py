@@ -693,13 +693,16 @@ class UnsharedRegionFit(object):
         """
         Update the parameters of the model (fcdiff/fit.py:200-206).
         """
-        self._update_pi_gamma(True, True)
+        # the bucket pass of the (eta, epsilon) solve does not depend on pi / gamma: it is enqueued
+        # behind the K3a launch, so that one wait on the stream serves both results
+        early = self._objective_context if (self.optimise_theta_sub and self._lps_state == 'derived') else None
+        self._update_pi_gamma(True, True, early)
         if self.optimise_theta_sub:
             self._update_theta_sub()
         if self.update_mu_sigma:
             self._update_mu_sigma()
 
-    def _mstep_sums(self, do_pi, do_gamma):
+    def _mstep_sums(self, do_pi, do_gamma, between=None):
         lib = _lib.load()
         (lqF, lqR, C, NU, c0, Cl) = (None, None, 0, 0, 0, 0)
         if do_gamma:
@@ -719,11 +722,15 @@ class UnsharedRegionFit(object):
                                            _dev.ptr(_dev.workspace()), _dev.stream()), "fcd_mstep_stats")
         if do_gamma and self.shards is not None and self._in is not None:
             self.shards.allreduce_terms(out, (0, 1, 2))
+            if between is not None:
+                between()
             return self.shards.fix_replicated(res.read(), (0, 1, 2)), C, NU
+        if between is not None:
+            between()
         return res.read(), C, NU
 
-    def _update_pi_gamma(self, do_pi, do_gamma):
-        (s, C, NU) = self._mstep_sums(do_pi, do_gamma)
+    def _update_pi_gamma(self, do_pi, do_gamma, between=None):
+        (s, C, NU) = self._mstep_sums(do_pi, do_gamma, between)
         if do_pi:
             self.model.pi = float(s[3] / NU)                       # fit.py:213
         if do_gamma:
