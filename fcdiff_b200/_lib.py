@@ -41,7 +41,7 @@ SIGNATURES = {
     "fcd_estep_qF": (c_int, [_P, _P, c_int32, _P, c_int64, c_int64, c_int32, c_int64, _P, _P, c_int64, c_int32, _P,
                              POINTER(FcdTheta), _P, _P, _P]),
     "fcd_transpose_patients": (c_int, [_P, c_int64, c_int32, c_int64, c_int32, c_int32, _P, c_int64, _P]),
-    "fcd_region_weights": (c_int, [_P, c_int64, c_int32, c_int64, c_int64, _P, _P, POINTER(FcdTheta), _P, _P]),
+    "fcd_region_weights": (c_int, [_P, c_int64, c_int32, c_int64, c_int64, _P, _P, _P, _P, POINTER(FcdTheta), _P, _P]),
     "fcd_estep_qR": (c_int, [_P, c_int64, c_int32, c_int32, c_int32, c_int32, _D3, c_int32, _P, _P, _P]),
     "fcd_estep_qR_fused": (c_int, [_P, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32,
                                    _D3, POINTER(FcdTheta), _P, _P, _P]),

@@ -247,6 +247,31 @@ transpose_patients_kernel(const double* __restrict__ bt, int64_t C, int U, int64
     }
 }
 
+// ------------------------------------------------------------------- K2b/P*
+// PsT[u][c] = PT[k*(c)][u][c]: the patient-major plane of each edge's dominant
+// state.  q_F settles after the first iteration, so the plane is gathered once and
+// afterwards only the columns of edges whose state changed are refreshed
+// (kcache[c] = the state PsT[.][c] was gathered for; 255 = never).
+__global__ void __launch_bounds__(256)
+pstar_refresh_kernel(const double* __restrict__ PT, int64_t planeStride, int Ul, int64_t C, int64_t pitchC,
+                     const uint8_t* __restrict__ fstate, const uint8_t* __restrict__ kcache,
+                     double* __restrict__ PsT) {
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const int k = fstate[c];
+    if (k >= 3 || k == kcache[c]) return;
+    const int per = (Ul + gridDim.y - 1) / gridDim.y;
+    const int u1 = min(Ul, (int)(blockIdx.y + 1) * per);
+    const double* src = PT + (int64_t)k * planeStride + c;
+    for (int u = blockIdx.y * per; u < u1; ++u) PsT[(int64_t)u * pitchC + c] = ldg_stream1(src + (int64_t)u * pitchC);
+}
+
+__global__ void __launch_bounds__(256)
+pstar_commit_kernel(const uint8_t* __restrict__ fstate, int64_t C, uint8_t* __restrict__ kcache) {
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c < C && fstate[c] < 3) kcache[c] = fstate[c];
+}
+
 // ------------------------------------------------------------------- K2b/W
 // WT[u][c][l] = sum_k qF[c,k] log(a_l + b_l p_k(c,u)) from the patient-major
 // responsibility planes PT[k][u][c].  The omitted per-(c,u) constant L sum_k qF[c,k]
@@ -258,6 +283,7 @@ __global__ void __launch_bounds__(256)
 region_weights_kernel(const double* __restrict__ PT, int64_t planeStride,
                       int Ul, int64_t C, int64_t pitchC,
                       const double* __restrict__ qF, const uint8_t* __restrict__ fstate,
+                      const double* __restrict__ PsT,
                       const __grid_constant__ ThetaDev th, const __grid_constant__ LogTabWindow tab,
                       double* __restrict__ WT) {
     extern __shared__ __align__(16) double s_dyn[];
@@ -280,7 +306,8 @@ region_weights_kernel(const double* __restrict__ PT, int64_t planeStride,
             ks[j] = -1;
             if (c < C) {
                 ks[j] = __ldg(fstate + c);
-                if (ks[j] < 3) pk[j] = ldg_stream1(row + ks[j] * planeStride + c);
+                if (ks[j] < 3)                                // coalesced from the dominant-state plane when it is kept
+                    pk[j] = PsT ? ldg_stream1(PsT + (int64_t)u * pitchC + c) : ldg_stream1(row + ks[j] * planeStride + c);
             }
         }
 #pragma unroll
@@ -751,13 +778,23 @@ int fcd_transpose_patients(const double* bt, int64_t C, int32_t U, int64_t pitch
 }
 
 int fcd_region_weights(const double* PT, int64_t planeStride, int32_t Ul, int64_t C, int64_t pitchC,
-                       const double* qF, const uint8_t* fstate, const fcd_theta* theta_host,
-                       double* WT, void* stream) {
+                       const double* qF, const uint8_t* fstate, double* PsT, uint8_t* kcache,
+                       const fcd_theta* theta_host, double* WT, void* stream) {
     FCD_REQUIRE(theta_host != nullptr && fstate != nullptr, "fcd_region_weights: NULL argument");
     FCD_REQUIRE(C >= 0 && Ul >= 0 && pitchC >= C, "fcd_region_weights: bad shape");
+    FCD_REQUIRE((PsT == nullptr) == (kcache == nullptr), "fcd_region_weights: PsT and kcache go together");
     if (C == 0 || Ul == 0) return 0;
     const ThetaDev th = make_theta_dev(*theta_host, 0);
     cudaStream_t st = (cudaStream_t)stream;
+    if (PsT != nullptr) {                                     // refresh the columns of edges whose state changed
+        dim3 rgrid((unsigned)((C + 255) / 256), (unsigned)(Ul < 16 ? Ul : 16));
+        pstar_refresh_kernel<<<rgrid, 256, 0, st>>>(PT, planeStride, Ul, C, pitchC, fstate, kcache, PsT);
+        int rc = check_launch("fcd_region_weights(refresh)");
+        if (rc) return rc;
+        pstar_commit_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(fstate, C, kcache);
+        rc = check_launch("fcd_region_weights(commit)");
+        if (rc) return rc;
+    }
     LogTabWindow tab;
     FCD_REQUIRE(log_table_window(th.epsl, th.al, st, tab), "fcd_region_weights: log table initialisation failed");
     int64_t ntiles = ((C + 1023) / 1024) * (int64_t)Ul;
@@ -770,12 +807,12 @@ int fcd_region_weights(const double* PT, int64_t planeStride, int32_t Ul, int64_
         cudaFuncSetAttribute(region_weights_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)kLogTabBytes);
         region_weights_kernel<true><<<(unsigned)grid, 256, tab.bytes(), st>>>(
-            PT, planeStride, Ul, C, pitchC, qF, fstate, th, tab, WT);
+            PT, planeStride, Ul, C, pitchC, qF, fstate, PsT, th, tab, WT);
     } else {
         int64_t grid = (int64_t)sm_count() * 4;
         if (grid > ntiles) grid = ntiles;
         region_weights_kernel<false><<<(unsigned)grid, 256, 0, st>>>(
-            PT, planeStride, Ul, C, pitchC, qF, fstate, th, tab, WT);
+            PT, planeStride, Ul, C, pitchC, qF, fstate, PsT, th, tab, WT);
     }
     return check_launch("fcd_region_weights");
 }

@@ -346,6 +346,7 @@ class UnsharedRegionFit(object):
                                                           _dev.ptr(PT[k]), pitchC, _dev.stream()),
                                "fcd_transpose_patients")
         inp['PT'] = PT
+        inp['PsT'] = inp['kcache'] = None
         return inp
 
     def _result(self, n, dtype=torch.float64, tag=""):
@@ -652,9 +653,13 @@ class UnsharedRegionFit(object):
         else:
             if inp['WT'] is None:
                 inp['WT'] = _dev.empty((Ul, C, 3))
+            if inp.get('PsT') is None:             # dominant-state plane, gathered on first use (q_F settles early)
+                inp['PsT'] = _dev.empty((max(Ul, 1), pitchC))
+                inp['kcache'] = torch.full((max(C, 1),), 255, dtype=torch.uint8, device=_dev.device())
             with _dev.timed(self.profile, "K2b_region_weights"):
                 _lib.check(lib.fcd_region_weights(_dev.ptr(PT), max(Ul, 1) * pitchC, Ul, C, pitchC,
-                                                  _dev.ptr(qF), _dev.ptr(fstate), ctypes.byref(th),
+                                                  _dev.ptr(qF), _dev.ptr(fstate), _dev.ptr(inp['PsT']),
+                                                  _dev.ptr(inp['kcache']), ctypes.byref(th),
                                                   _dev.ptr(inp['WT']), _dev.stream()), "fcd_region_weights")
             with _dev.timed(self.profile, "K2b_sweep"):
                 _lib.check(lib.fcd_estep_qR(_dev.ptr(inp['WT']), C, N, U, u0, Ul, log_pi2, lookup,

@@ -129,10 +129,14 @@ FCD_API int fcd_transpose_patients(const double* bt, int64_t C, int32_t U, int64
  *   WT[u][c][l] = sum_k qF[c,k] * log M_kl(bt[c][u])   (patient-major; PT[k][u][c] are the
  *   patient-major copies [Ul][pitchC] of the responsibility planes)
  * up to an additive per-(c,u) constant common to all l, which cancels in the
- * normalisation of fit.py:196. qF / fstate cover ALL edges. */
+ * normalisation of fit.py:196. qF / fstate cover ALL edges.
+ * PsT / kcache (both or neither): caller-kept [Ul][pitchC] plane of each edge's
+ * dominant-state responsibility and the [C] states it was gathered for (255 =
+ * never; set by the caller once); the call refreshes the columns of edges whose
+ * state changed and then reads one coalesced plane instead of three. */
 FCD_API int fcd_region_weights(const double* PT, int64_t planeStride, int32_t Ul, int64_t C, int64_t pitchC,
-                       const double* qF, const uint8_t* fstate, const fcd_theta* theta_host,
-                       double* WT, void* stream);
+                       const double* qF, const uint8_t* fstate, double* PsT, uint8_t* kcache,
+                       const fcd_theta* theta_host, double* WT, void* stream);
 
 /* K2b part 2 -- Gauss-Seidel sweep of `_update_lq_R` (fcdiff/fit.py:176-198)
  * for the patients [u0, u0+Ul).  qR/lqR are the full [N][U][2] arrays; only
