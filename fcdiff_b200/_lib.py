@@ -43,8 +43,9 @@ SIGNATURES = {
     "fcd_transpose_patients": (c_int, [_P, c_int64, c_int32, c_int64, c_int32, c_int32, _P, c_int64, _P]),
     "fcd_region_weights": (c_int, [_P, c_int64, c_int32, c_int64, c_int64, _P, _P, _P, _P, POINTER(FcdTheta), _P, _P]),
     "fcd_estep_qR": (c_int, [_P, c_int64, c_int32, c_int32, c_int32, c_int32, _D3, c_int32, _P, _P, _P]),
-    "fcd_estep_qR_fused": (c_int, [_P, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32,
+    "fcd_estep_qR_fused": (c_int, [_P, _P, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32,
                                    _D3, POINTER(FcdTheta), _P, _P, _P]),
+    "fcd_pstar_refresh": (c_int, [_P, c_int64, c_int32, c_int64, c_int64, _P, _P, _P, _P]),
     "fcd_mstep_stats": (c_int, [_P, c_int64, _P, c_int64, _P, _P, _P]),
     "fcd_elm_obj_grad": (c_int, [_P, c_int64, c_int64, c_int32, c_int64, _P, _P, _P, _P, c_int64, c_int32, _P,
                                  POINTER(FcdTheta), c_int32, _P, _P, _P]),

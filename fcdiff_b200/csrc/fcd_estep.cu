@@ -469,79 +469,81 @@ sweep_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int u0,
 
 // --------------------------------------------------------------- K2b fused
 // Gauss-Seidel sweep of fcdiff/fit.py:184-197 with the region weights computed
-// on the fly (no WT tensor, no region_weights pass).  With edge_lookup =
-// "reference" the edges read at step n are the contiguous window
-// [n(n-1)/2, n(n-1)/2 + N) (fit.py:185-186), and the windows of successive steps
-// slide monotonically over the patient's row of the patient-major planes: the
-// row is streamed through a shared-memory ring by TMA bulk copies (chunks of
-// kSwChunk edges: planes 0 and 1 and the edges' peak states; p_2 = 1 - p_0 - p_1,
-// an absolute error of 1e-16 on an argument >= min(a_l, eps_l)), far enough ahead
-// that no step waits for DRAM.  T threads per patient (thread t owns the regions
-// m = t, t + T, ...; their q_R stay in registers), PPC patients per CTA sharing
-// the log table; each patient group synchronises on its own named barrier.
-// Step n: partial sums from the weights W_n held in registers, warp reduction,
-// then -- while the other warps arrive -- the logs of W_{n+1} from the ring, ONE
-// barrier, and only the owner of region n normalises (fit.py:196-197).
-constexpr int kSwChunk = 256;
-constexpr int kSwSlots = 8;
-constexpr int kSwRing = kSwChunk * kSwSlots;
+// inside the kernel: no WT tensor (24 bytes per edge-patient written and read
+// back) and no region_weights pass.  With edge_lookup = "reference" the edges
+// read at step n are the contiguous window [n(n-1)/2, n(n-1)/2 + N)
+// (fit.py:185-186), and the windows of successive steps slide monotonically over
+// the patient's row of the dominant-state plane PsT (fcd_region_weights): the
+// row is streamed by TMA bulk copies (64-edge chunks, p and the edges' peak
+// states) into a staging ring, every edge is converted ONCE into its three
+// weights W_l = log(a_l + b_l p) -- by all threads of the patient's group, ahead
+// of the window that needs it -- and kept in a shared-memory ring until the
+// window has passed.  A step then reads its window from shared memory, reduces
+// (warp shuffle + ONE barrier) and only the owner of region n normalises
+// (fit.py:196-197).  T threads per patient (thread t owns the regions m = t,
+// t + T, ...; their q_R stay in registers), PPC patients per CTA sharing the log
+// table; each patient group synchronises on its own named barrier.
+// Ring capacity: window n (still being read) and window n + 1 (being prepared)
+// must fit: n + N <= R for every step n, i.e. 2N - 1 <= R.
+constexpr int kSwChunk = 64;
 
-template <int T>
+template <int T, int R>
 struct SweepSmem {
     static constexpr int NW = T / 32;
-    static constexpr size_t bytes = (size_t)2 * kSwRing * 8 + kSwRing + kSwSlots * 8 + 2 * NW * 2 * 8;
+    static constexpr int kSlots = R / kSwChunk;
+    static constexpr size_t bytes = (size_t)3 * R * 8 + (size_t)R * 8 + R + kSlots * 8 + 2 * NW * 2 * 8;
     static constexpr size_t padded = (bytes + 127) / 128 * 128;
 };
 
-template <int T, int MPT, int PPC, bool FAST>
+template <int T, int MPT, int PPC, int R, bool FAST>
 __global__ void __launch_bounds__(T * PPC)
-sweep_fused_kernel(const double* __restrict__ PT, int64_t planeStride, int64_t pitchC,
-                   const double* __restrict__ qF, const uint8_t* __restrict__ fstate, int64_t pitchF,
-                   int64_t C, int N, int U, int u0, int Ul, double lp0, double lp1,
+sweep_fused_kernel(const double* __restrict__ PsT, const double* __restrict__ PT, int64_t planeStride,
+                   int64_t pitchC, const double* __restrict__ qF, const uint8_t* __restrict__ fstate,
+                   int64_t pitchF, int64_t C, int N, int U, int u0, int Ul, double lp0, double lp1,
                    const __grid_constant__ ThetaDev th, const __grid_constant__ LogTabWindow tab,
                    double* __restrict__ qR, double* __restrict__ lqR) {
-    constexpr int NW = T / 32;
+    constexpr int NW = T / 32, kSlots = R / kSwChunk, kAhead = 128;
     extern __shared__ __align__(128) double s_dyn[];
     const double* s_tab = load_log_table<FAST>(tab, s_dyn);
     const int pp = threadIdx.x / T, tid = threadIdx.x % T, lane = tid & 31, warp = tid >> 5;
     const int ul = blockIdx.x * PPC + pp;
     if (ul >= Ul) return;                                    // whole patient group leaves (own barrier id)
     unsigned char* mine = reinterpret_cast<unsigned char*>(s_dyn + (FAST ? ((tab.n + 15) & ~15) : 0)) +
-                          (size_t)pp * SweepSmem<T>::padded;
-    double* ring0 = reinterpret_cast<double*>(mine);
-    double* ring1 = ring0 + kSwRing;
-    uint8_t* fring = reinterpret_cast<uint8_t*>(ring1 + kSwRing);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(fring + kSwRing);
-    double* s_red = reinterpret_cast<double*>(bars + kSwSlots);          // [2][NW][2]
+                          (size_t)pp * SweepSmem<T, R>::padded;
+    double* wring = reinterpret_cast<double*>(mine);         // [3][R]
+    double* pring = wring + 3 * R;                           // [R] staged responsibilities
+    uint8_t* fring = reinterpret_cast<uint8_t*>(pring + R);  // [R] staged peak states
+    uint64_t* bars = reinterpret_cast<uint64_t*>(fring + R);
+    double* s_red = reinterpret_cast<double*>(bars + kSlots);            // [2][NW][2]
     auto group_sync = [&]() {                                // immediate barrier ids: a register id reserves all 16
         if (PPC == 1 || pp == 0) asm volatile("bar.sync 1, %0;" ::"n"(T) : "memory");
-        else asm volatile("bar.sync 2, %0;" ::"n"(T) : "memory");
+        else if (pp == 1) asm volatile("bar.sync 2, %0;" ::"n"(T) : "memory");
+        else if (pp == 2) asm volatile("bar.sync 3, %0;" ::"n"(T) : "memory");
+        else asm volatile("bar.sync 4, %0;" ::"n"(T) : "memory");
     };
 
     const int u = u0 + ul;
-    const double* row0 = PT + (int64_t)ul * pitchC;
-    const double* row1 = row0 + planeStride;
+    const double* row = PsT + (int64_t)ul * pitchC;
     const int nchunks = (int)((pitchC + kSwChunk - 1) / kSwChunk);
     int next_issue = 0;                                      // meaningful in tid 0 only
     auto issue = [&](int g) {
-        uint64_t* bar = bars + (g % kSwSlots);
+        uint64_t* bar = bars + (g % kSlots);
         const int64_t e0 = (int64_t)g * kSwChunk;
         const uint32_t ne = (uint32_t)(pitchC - e0 < kSwChunk ? pitchC - e0 : kSwChunk);
         const uint32_t nf = (uint32_t)(pitchF - e0 < kSwChunk ? pitchF - e0 : kSwChunk);
-        const int so = (g % kSwSlots) * kSwChunk;
+        const int so = (g % kSlots) * kSwChunk;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(bar, 2 * ne * 8 + nf);
-        tma_load_1d(ring0 + so, row0 + e0, ne * 8, bar);
-        tma_load_1d(ring1 + so, row1 + e0, ne * 8, bar);
+        mbar_expect_tx(bar, ne * 8 + nf);
+        tma_load_1d(pring + so, row + e0, ne * 8, bar);
         tma_load_1d(fring + so, fstate + e0, nf, bar);
     };
-    if (tid < kSwSlots) mbar_init(bars + tid, 1);
+    if (tid < kSlots) mbar_init(bars + tid, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     group_sync();
     if (tid == 0)
-        for (; next_issue < kSwSlots && next_issue < nchunks; ++next_issue) issue(next_issue);
+        for (; next_issue < kSlots && next_issue < nchunks; ++next_issue) issue(next_issue);
 
-    double q0[MPT], q1[MPT], w[MPT][3], wn[MPT][3];
+    double q0[MPT], q1[MPT];
 #pragma unroll
     for (int j = 0; j < MPT; ++j) {
         const int m = tid + j * T;
@@ -551,60 +553,54 @@ sweep_fused_kernel(const double* __restrict__ PT, int64_t planeStride, int64_t p
             q1[j] = qR[((int64_t)m * U + u) * 2 + 1];
         }
     }
-    int waited = -1;                                         // chunks 0..waited have arrived (per thread)
     const double al[3] = {th.al[0], th.al[1], th.al[2]}, bl[3] = {th.bl[0], th.bl[1], th.bl[2]};
-    auto window = [&](int n, double (&dst)[MPT][3]) {
-        const int64_t base = (int64_t)n * (n - 1) / 2;
-        int64_t last = base + N - 1;
-        if (last > C - 1) last = C - 1;
-        const int ghi = (int)(last / kSwChunk);
-        for (; waited < ghi; ++waited) mbar_wait(bars + ((waited + 1) % kSwSlots), ((waited + 1) / kSwSlots) & 1);
-        const uint32_t base_lo = (uint32_t)base;
-        bool slow = false;
-#pragma unroll
-        for (int j = 0; j < MPT; ++j) {                       // branch-free: invalid slots read a valid index, weight 0
-            const int m = tid + j * T;
-            const bool valid = m < N && m != n;
-            const uint32_t idx = (base_lo + (uint32_t)(valid ? m : 0)) & (kSwRing - 1);
+    int waited = -1;                                         // chunks 0..waited have arrived (per thread)
+    int64_t cv = 0;                                          // edges [0, cv) have been converted (same in all threads)
+    // converts the edges [cv, target) of the patient's row into the weight ring
+    auto convert = [&](int64_t target) {
+        if (target <= cv) return;
+        const int ghi = (int)((target - 1) / kSwChunk);
+        for (; waited < ghi; ++waited) mbar_wait(bars + ((waited + 1) % kSlots), ((waited + 1) / kSlots) & 1);
+        for (int64_t e = cv + tid; e < target; e += T) {
+            const int idx = (int)(e & (R - 1));
             const int k = fring[idx];
-            const double p0 = ring0[idx], p1 = ring1[idx];
-            const double p = k == 0 ? p0 : (k == 1 ? p1 : (1.0 - p0) - p1);
-            slow |= valid && k == 3;
+            double w[3];
+            if (k < 3) {
+                const double p = pring[idx];
 #pragma unroll
-            for (int l = 0; l < 3; ++l) {
-                const double lg = fast_log<FAST>(fma(bl[l], p, al[l]), s_tab);
-                dst[j][l] = valid ? lg : 0.0;
-            }
-        }
-        if (__any_sync(0xffffffffu, slow)) {                  // edges whose q_F is not peaked (rare)
+                for (int l = 0; l < 3; ++l) w[l] = fast_log<FAST>(fma(bl[l], p, al[l]), s_tab);
+            } else {                                         // edge whose q_F is not peaked (rare): all three planes
+                const double qf[3] = {__ldg(qF + e * 3), __ldg(qF + e * 3 + 1), __ldg(qF + e * 3 + 2)};
+                w[0] = w[1] = w[2] = 0.0;
 #pragma unroll
-            for (int j = 0; j < MPT; ++j) {
-                const int m = tid + j * T;
-                if (m < N && m != n) {
-                    const int64_t c = base + m;
-                    const int idx = (int)(c & (kSwRing - 1));
-                    if (fring[idx] == 3) {
-                        const double p0 = ring0[idx], p1 = ring1[idx];
-                        const double pk[3] = {p0, p1, (1.0 - p0) - p1};
-                        const double qf[3] = {__ldg(qF + c * 3), __ldg(qF + c * 3 + 1), __ldg(qF + c * 3 + 2)};
-                        dst[j][0] = dst[j][1] = dst[j][2] = 0.0;
+                for (int kk = 0; kk < 3; ++kk) {
+                    const double p = ldg_stream1(PT + kk * planeStride + (int64_t)ul * pitchC + e);
 #pragma unroll
-                        for (int kk = 0; kk < 3; ++kk)
-#pragma unroll
-                            for (int l = 0; l < 3; ++l)
-                                dst[j][l] = fma(qf[kk], fast_log<FAST>(fma(bl[l], pk[kk], al[l]), s_tab), dst[j][l]);
-                    }
+                    for (int l = 0; l < 3; ++l) w[l] = fma(qf[kk], fast_log<FAST>(fma(bl[l], p, al[l]), s_tab), w[l]);
                 }
             }
+            wring[idx] = w[0];
+            wring[R + idx] = w[1];
+            wring[2 * R + idx] = w[2];
         }
+        cv = target;
     };
-    // one Gauss-Seidel step with the weights `cur`; leaves the next step's weights in `nxt`
-    auto step = [&](int n, const double (&cur)[MPT][3], double (&nxt)[MPT][3]) {
+    auto clampC = [&](int64_t e) { return e < C ? e : C; };
+    convert(clampC((int64_t)N + kAhead < R ? (int64_t)N + kAhead : R));       // window 0 = [0, N)
+    group_sync();
+    for (int n = 0; n < N; ++n) {
+        const int64_t base = (int64_t)n * (n - 1) / 2;
+        const uint32_t base_lo = (uint32_t)base;
         double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-        for (int j = 0; j < MPT; ++j) {                       // zero weights for m == n / m >= N
-            s0 += fma(q0[j], cur[j][0], q1[j] * cur[j][2]);   // fit.py:188-190
-            s1 += fma(q1[j], cur[j][1], q0[j] * cur[j][2]);   // fit.py:192-194
+        for (int j = 0; j < MPT; ++j) {
+            const int m = tid + j * T;
+            const bool valid = m < N && m != n;
+            const uint32_t idx = (base_lo + (uint32_t)(valid ? m : 0)) & (R - 1);
+            const double w0 = valid ? wring[idx] : 0.0, w1 = valid ? wring[R + idx] : 0.0,
+                         w2 = valid ? wring[2 * R + idx] : 0.0;
+            s0 += fma(q0[j], w0, q1[j] * w2);                 // fit.py:188-190
+            s1 += fma(q1[j], w1, q0[j] * w2);                 // fit.py:192-194
         }
         s0 = warp_sum(s0);
         s1 = warp_sum(s1);
@@ -612,7 +608,11 @@ sweep_fused_kernel(const double* __restrict__ PT, int64_t planeStride, int64_t p
             s_red[((n & 1) * NW + warp) * 2] = s0;
             s_red[((n & 1) * NW + warp) * 2 + 1] = s1;
         }
-        if (n + 1 < N) window(n + 1, nxt);                    // the logs of the next step overlap the barrier
+        if (n + 1 < N) {                                      // prepare window n + 1 while the others arrive
+            int64_t target = base + n + N + kAhead;           // end of window n + 1, and a little ahead
+            if (target > base + R) target = base + R;         // window n is still being read: its slots stay
+            convert(clampC(target));
+        }
         group_sync();
         if (tid == (n & (T - 1))) {                           // owner of region n
             double a = 0.0, b = 0.0;
@@ -627,7 +627,6 @@ sweep_fused_kernel(const double* __restrict__ PT, int64_t planeStride, int64_t p
             const double d = first ? l1r - l0r : l0r - l1r;
             const double t = exp_nonpos(d);
             // most regions are decided: below 2^-54, log1p(t) = t and 1/(1+t) = 1 to rounding
-            // (skips the two long dependent chains of the step's critical path)
             double lg = t, inv = 1.0;
             if (t >= 5.551115123125783e-17) {
                 lg = log1p(t);
@@ -650,15 +649,10 @@ sweep_fused_kernel(const double* __restrict__ PT, int64_t planeStride, int64_t p
             qR[o] = p0;
             qR[o + 1] = p1;
         }
-        if (tid == 0 && n + 2 < N) {                          // chunks below window n+2 are dead: refill their slots
-            const int glo = (int)(((int64_t)(n + 2) * (n + 1) / 2) / kSwChunk);
-            for (; next_issue < nchunks && next_issue - kSwSlots < glo; ++next_issue) issue(next_issue);
+        if (tid == 0) {                                       // staged chunks that are converted are dead: refill
+            const int done = (int)(cv / kSwChunk);            // chunks [0, done) fully converted
+            for (; next_issue < nchunks && next_issue - kSlots < done; ++next_issue) issue(next_issue);
         }
-    };
-    window(0, w);
-    for (int n = 0; n < N; n += 2) {                          // two steps per trip: the weight sets swap roles, no moves
-        step(n, w, wn);
-        if (n + 1 < N) step(n + 1, wn, w);
     }
 }
 
@@ -777,6 +771,21 @@ int fcd_transpose_patients(const double* bt, int64_t C, int32_t U, int64_t pitch
     return check_launch("fcd_transpose_patients");
 }
 
+int fcd_pstar_refresh(const double* PT, int64_t planeStride, int32_t Ul, int64_t C, int64_t pitchC,
+                      const uint8_t* fstate, double* PsT, uint8_t* kcache, void* stream) {
+    FCD_REQUIRE(PT != nullptr && fstate != nullptr && PsT != nullptr && kcache != nullptr,
+                "fcd_pstar_refresh: NULL argument");
+    FCD_REQUIRE(C >= 0 && Ul >= 0 && pitchC >= C, "fcd_pstar_refresh: bad shape");
+    if (C == 0 || Ul == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 rgrid((unsigned)((C + 255) / 256), (unsigned)(Ul < 16 ? Ul : 16));
+    pstar_refresh_kernel<<<rgrid, 256, 0, st>>>(PT, planeStride, Ul, C, pitchC, fstate, kcache, PsT);
+    int rc = check_launch("fcd_pstar_refresh");
+    if (rc) return rc;
+    pstar_commit_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(fstate, C, kcache);
+    return check_launch("fcd_pstar_refresh(commit)");
+}
+
 int fcd_region_weights(const double* PT, int64_t planeStride, int32_t Ul, int64_t C, int64_t pitchC,
                        const double* qF, const uint8_t* fstate, double* PsT, uint8_t* kcache,
                        const fcd_theta* theta_host, double* WT, void* stream) {
@@ -787,12 +796,7 @@ int fcd_region_weights(const double* PT, int64_t planeStride, int32_t Ul, int64_
     const ThetaDev th = make_theta_dev(*theta_host, 0);
     cudaStream_t st = (cudaStream_t)stream;
     if (PsT != nullptr) {                                     // refresh the columns of edges whose state changed
-        dim3 rgrid((unsigned)((C + 255) / 256), (unsigned)(Ul < 16 ? Ul : 16));
-        pstar_refresh_kernel<<<rgrid, 256, 0, st>>>(PT, planeStride, Ul, C, pitchC, fstate, kcache, PsT);
-        int rc = check_launch("fcd_region_weights(refresh)");
-        if (rc) return rc;
-        pstar_commit_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(fstate, C, kcache);
-        rc = check_launch("fcd_region_weights(commit)");
+        int rc = fcd_pstar_refresh(PT, planeStride, Ul, C, pitchC, fstate, PsT, kcache, stream);
         if (rc) return rc;
     }
     LogTabWindow tab;
@@ -852,19 +856,19 @@ int fcd_estep_qR(const double* WT, int64_t C, int32_t N, int32_t U, int32_t u0, 
     return check_launch("fcd_estep_qR");
 }
 
-int fcd_estep_qR_fused(const double* PT, int64_t planeStride, int64_t pitchC,
+int fcd_estep_qR_fused(const double* PsT, const double* PT, int64_t planeStride, int64_t pitchC,
                        const double* qF, const uint8_t* fstate, int64_t pitchF,
                        int64_t C, int32_t N, int32_t U, int32_t u0, int32_t Ul,
                        const double* log_pi2_host, const fcd_theta* theta_host,
                        double* qR, double* lqR, void* stream) {
-    FCD_REQUIRE(PT != nullptr && qF != nullptr && fstate != nullptr && log_pi2_host != nullptr &&
+    FCD_REQUIRE(PsT != nullptr && PT != nullptr && qF != nullptr && fstate != nullptr && log_pi2_host != nullptr &&
                 theta_host != nullptr && qR != nullptr && lqR != nullptr, "fcd_estep_qR_fused: NULL argument");
     FCD_REQUIRE(N >= 3 && N <= 1024 && C == (int64_t)N * (N - 1) / 2,
                 "fcd_estep_qR_fused: needs 3 <= N <= 1024 and C = N(N-1)/2 (got N=%d, C=%lld)", N, (long long)C);
     FCD_REQUIRE(u0 >= 0 && Ul >= 0 && u0 + Ul <= U, "fcd_estep_qR_fused: bad patient range");
-    FCD_REQUIRE(pitchC >= C && pitchC % 2 == 0 && planeStride % 2 == 0 && pitchF >= pitchC && pitchF % 16 == 0 &&
-                ((reinterpret_cast<uintptr_t>(PT) | reinterpret_cast<uintptr_t>(fstate)) & 15) == 0,
-                "fcd_estep_qR_fused: planes / states must be 16-byte aligned, pitchC even, pitchF % 16 == 0");
+    FCD_REQUIRE(pitchC >= C && pitchC % 2 == 0 && pitchF >= pitchC && pitchF % 16 == 0 &&
+                ((reinterpret_cast<uintptr_t>(PsT) | reinterpret_cast<uintptr_t>(fstate)) & 15) == 0,
+                "fcd_estep_qR_fused: plane / states must be 16-byte aligned, pitchC even, pitchF % 16 == 0");
     if (Ul == 0) return 0;
     const ThetaDev th = make_theta_dev(*theta_host, 0);
     cudaStream_t st = (cudaStream_t)stream;
@@ -873,20 +877,20 @@ int fcd_estep_qR_fused(const double* PT, int64_t planeStride, int64_t pitchC,
     const bool fast = log_table_covers(th.epsl, th.al);
     const size_t tbytes = fast ? (size_t)((tab.n + 15) & ~15) * sizeof(double) : 0;
     const double lp0 = log_pi2_host[0], lp1 = log_pi2_host[1];
-#define FCD_SWF(T, PPC, F)                                                                              \
+#define FCD_SWF(T, PPC, RR, F)                                                                          \
     do {                                                                                                \
-        const size_t smem = tbytes + (size_t)(PPC) * SweepSmem<T>::padded;                              \
-        cudaFuncSetAttribute(sweep_fused_kernel<T, 4, PPC, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                             (int)(kLogTabBytes + 128 + (PPC) * SweepSmem<T>::padded));                  \
-        sweep_fused_kernel<T, 4, PPC, F><<<(Ul + (PPC) - 1) / (PPC), (T) * (PPC), smem, st>>>(           \
-            PT, planeStride, pitchC, qF, fstate, pitchF, C, N, U, u0, Ul, lp0, lp1, th, tab, qR, lqR);   \
+        const size_t smem = tbytes + (size_t)(PPC) * SweepSmem<T, RR>::padded;                          \
+        cudaFuncSetAttribute(sweep_fused_kernel<T, 4, PPC, RR, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             (int)(kLogTabBytes + 128 + (PPC) * SweepSmem<T, RR>::padded));              \
+        sweep_fused_kernel<T, 4, PPC, RR, F><<<(Ul + (PPC) - 1) / (PPC), (T) * (PPC), smem, st>>>(       \
+            PsT, PT, planeStride, pitchC, qF, fstate, pitchF, C, N, U, u0, Ul, lp0, lp1, th, tab, qR, lqR); \
     } while (0)
 #define FCD_SWF_N(F)                                                                                    \
     do {                                                                                                \
-        if (N <= 128) FCD_SWF(32, 2, F);                                                                \
-        else if (N <= 256) FCD_SWF(64, 2, F);                                                           \
-        else if (N <= 512) FCD_SWF(128, 2, F);                                                          \
-        else FCD_SWF(256, 1, F);                                                                        \
+        if (N <= 128) FCD_SWF(32, 4, 1024, F);                                                          \
+        else if (N <= 256) FCD_SWF(64, 4, 1024, F);                                                     \
+        else if (N <= 512) FCD_SWF(128, 4, 1024, F);                                                    \
+        else FCD_SWF(256, 2, 2048, F);                                                                  \
     } while (0)
     if (fast) FCD_SWF_N(true); else FCD_SWF_N(false);
 #undef FCD_SWF_N

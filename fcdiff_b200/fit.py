@@ -643,19 +643,22 @@ class UnsharedRegionFit(object):
         fstate = self._mF.get_state()
         (PT, pitchC) = (inp['PT'], inp['PT'].shape[2])
         lqR_new, qR_new = lqR.clone(), qR.clone()
+        if inp.get('PsT') is None:                 # dominant-state plane, gathered on first use (q_F settles early)
+            inp['PsT'] = _dev.empty((max(Ul, 1), pitchC))
+            inp['kcache'] = torch.full((max(C, 1),), 255, dtype=torch.uint8, device=_dev.device())
         if lookup == 0 and 3 <= N <= 1024 and self.fused_sweep:
-            # weights computed inside the sweep from the TMA-streamed planes: no WT tensor
+            # every edge's weights are computed once inside the sweep and kept in a shared-memory ring: no WT tensor
             with _dev.timed(self.profile, "K2b_sweep_fused"):
+                _lib.check(lib.fcd_pstar_refresh(_dev.ptr(PT), max(Ul, 1) * pitchC, Ul, C, pitchC, _dev.ptr(fstate),
+                                                 _dev.ptr(inp['PsT']), _dev.ptr(inp['kcache']), _dev.stream()),
+                           "fcd_pstar_refresh")
                 _lib.check(lib.fcd_estep_qR_fused(
-                    _dev.ptr(PT), max(Ul, 1) * pitchC, pitchC, _dev.ptr(qF), _dev.ptr(fstate), fstate.numel(),
-                    C, N, U, u0, Ul, log_pi2, ctypes.byref(th), _dev.ptr(qR_new), _dev.ptr(lqR_new),
+                    _dev.ptr(inp['PsT']), _dev.ptr(PT), max(Ul, 1) * pitchC, pitchC, _dev.ptr(qF), _dev.ptr(fstate),
+                    fstate.numel(), C, N, U, u0, Ul, log_pi2, ctypes.byref(th), _dev.ptr(qR_new), _dev.ptr(lqR_new),
                     _dev.stream()), "fcd_estep_qR_fused")
         else:
             if inp['WT'] is None:
                 inp['WT'] = _dev.empty((Ul, C, 3))
-            if inp.get('PsT') is None:             # dominant-state plane, gathered on first use (q_F settles early)
-                inp['PsT'] = _dev.empty((max(Ul, 1), pitchC))
-                inp['kcache'] = torch.full((max(C, 1),), 255, dtype=torch.uint8, device=_dev.device())
             with _dev.timed(self.profile, "K2b_region_weights"):
                 _lib.check(lib.fcd_region_weights(_dev.ptr(PT), max(Ul, 1) * pitchC, Ul, C, pitchC,
                                                   _dev.ptr(qF), _dev.ptr(fstate), _dev.ptr(inp['PsT']),

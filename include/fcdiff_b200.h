@@ -150,16 +150,23 @@ FCD_API int fcd_estep_qR(const double* WT, int64_t C, int32_t N, int32_t U, int3
 
 /* K2b fused -- the whole of `_update_lq_R` (fcdiff/fit.py:176-198) for the
  * patients [u0, u0+Ul) with edge_lookup = FCD_LOOKUP_REFERENCE, without the WT
- * tensor: the weights W[c][l] = sum_k qF[c,k] log M_kl are computed inside the
- * sweep from the patient-major responsibility planes 0 and 1 (PT, row pitch
- * pitchC even; p_2 = 1 - p_0 - p_1), streamed through shared memory by TMA.
+ * tensor: every edge's weights W[c][l] = sum_k qF[c,k] log M_kl are computed once
+ * inside the sweep from the dominant-state plane PsT (kept by
+ * fcd_region_weights' refresh; row pitch pitchC even), streamed through shared
+ * memory by TMA, and held in a shared-memory ring while the sweep's window
+ * passes.  PT (3 planes) is read only for edges whose q_F is not peaked.
  * fstate: peak states of ALL edges, padded to pitchF >= pitchC bytes (pitchF %
  * 16 == 0).  3 <= N <= 1024.  Other arguments as fcd_estep_qR. */
-FCD_API int fcd_estep_qR_fused(const double* PT, int64_t planeStride, int64_t pitchC,
+FCD_API int fcd_estep_qR_fused(const double* PsT, const double* PT, int64_t planeStride, int64_t pitchC,
                        const double* qF, const uint8_t* fstate, int64_t pitchF,
                        int64_t C, int32_t N, int32_t U, int32_t u0, int32_t Ul,
                        const double* log_pi2_host, const fcd_theta* theta_host,
                        double* qR, double* lqR, void* stream);
+
+/* Refreshes the dominant-state plane PsT / kcache (see fcd_region_weights) for the
+ * current peak states without computing region weights. */
+FCD_API int fcd_pstar_refresh(const double* PT, int64_t planeStride, int32_t Ul, int64_t C, int64_t pitchC,
+                      const uint8_t* fstate, double* PsT, uint8_t* kcache, void* stream);
 
 /* K3a -- M-step sums; replaces `_update_pi` / `_update_gamma`
  * (fcdiff/fit.py:208-220).  out[0..2] = sum_c exp(lqF[c,k]),
