@@ -80,35 +80,31 @@ class EdgeShards(object):
                 host_vec[i] = host_vec[i] / self.world
         return host_vec
 
-    def _gather_rows(self, full, rows, width):
-        """``full`` is a flat [rows * width] tensor whose rows [start, start+len)
-        are valid on this rank; after the call all rows are valid everywhere."""
-        ch = self.chunk(rows, self.world)
-        (start, length) = self.span(rows)
-        local = full.new_zeros((ch * width,))
-        local[:length * width].copy_(full[start * width:(start + length) * width])
-        gathered = full.new_empty((self.world * ch * width,))
-        dist.all_gather_into_tensor(gathered, local, group=self.group)
-        full.copy_(gathered[:rows * width])
-
     def allgather_edges(self, lqF, qF, C):
-        """lqF, qF: flat [C*3]."""
-        self._gather_rows(lqF, C, 3)
-        self._gather_rows(qF, C, 3)
+        """lqF, qF: flat [C*3]; this rank's edge rows are valid on entry, all rows on
+        exit.  One collective for both arrays."""
+        ch = self.chunk(C, self.world)
+        (start, length) = self.span(C)
+        local = lqF.new_zeros((2, ch * 3))
+        local[0, :length * 3].copy_(lqF[start * 3:(start + length) * 3])
+        local[1, :length * 3].copy_(qF[start * 3:(start + length) * 3])
+        gathered = lqF.new_empty((self.world, 2, ch * 3))
+        dist.all_gather_into_tensor(gathered.view(-1), local.view(-1), group=self.group)
+        lqF.copy_(gathered[:, 0].reshape(-1)[:C * 3])
+        qF.copy_(gathered[:, 1].reshape(-1)[:C * 3])
 
     def allgather_patients(self, lqR, qR, N, U):
-        """lqR, qR: flat [N*U*2]; this rank's patient columns are valid."""
+        """lqR, qR: flat [N*U*2]; this rank's patient columns are valid on entry, all
+        columns on exit.  One collective for both arrays."""
         ch = self.chunk(U, self.world)
         (u0, Ul) = self.span(U)
-        for t in (lqR, qR):
-            v = t.view(N, U, 2)
-            local = t.new_zeros((N, ch, 2))
-            local[:, :Ul].copy_(v[:, u0:u0 + Ul])
-            gathered = t.new_empty((self.world * N * ch * 2,))
-            dist.all_gather_into_tensor(gathered, local.view(-1), group=self.group)
-            g = gathered.view(self.world, N, ch, 2)
-            v.copy_(g.permute(1, 0, 2, 3).reshape(N, self.world * ch, 2)[:, :U])
-
+        local = lqR.new_zeros((2, N, ch, 2))
+        local[0, :, :Ul].copy_(lqR.view(N, U, 2)[:, u0:u0 + Ul])
+        local[1, :, :Ul].copy_(qR.view(N, U, 2)[:, u0:u0 + Ul])
+        gathered = lqR.new_empty((self.world, 2, N, ch, 2))
+        dist.all_gather_into_tensor(gathered.view(-1), local.view(-1), group=self.group)
+        for (i, t) in enumerate((lqR, qR)):
+            t.view(N, U, 2).copy_(gathered[:, i].permute(1, 0, 2, 3).reshape(N, self.world * ch, 2)[:, :U])
 
     def exchange_patient_blocks(self, bt_local, Cl, C, U):
         """Edge-sharded -> patient-sharded re-layout of the patient correlations

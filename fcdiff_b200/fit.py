@@ -892,30 +892,42 @@ class UnsharedRegionFit(object):
             self._update_lps()
         # scipy.optimize.minimize(..., method="L-BFGS-B", bounds=[(eps, 1 - eps)] * 2) of fit.py:228-241,
         # driven without SciPy's Python front end (same compiled routine, same iterates: _opt.py)
-        fun = self._objective
-        if self.shards is None:
-            # the optimiser's inner loop: everything pre-bound, one launch + one download per evaluation
-            ctx = self._objective_context()
-            (th, fn, head, tail, res) = (ctx['th'], ctx['fn'], ctx['head'], ctx['tail'], ctx['res'])
-            (read, stream, const, evals) = (res.read, ctx['stream'], ctx['const'], self._evals)
-            (verF, verR, name) = (ctx['verF'], ctx['verR'], ctx['name'])
+        # the optimiser's inner loop: everything pre-bound, one launch (+ one all-reduce of the
+        # four partial sums when edges are sharded) + one download per evaluation
+        ctx = self._objective_context()
+        (th, fn, head, tail, res) = (ctx['th'], ctx['fn'], ctx['head'], ctx['tail'], ctx['res'])
+        (read, stream, evals) = (res.read, ctx['stream'], self._evals)
+        (verF, verR, name) = (ctx['verF'], ctx['verR'], ctx['name'])
+        timed = self.profile
+        shards = self.shards
+        if shards is not None:
+            import torch.distributed as dist
+            (all_reduce, group, dev_vec) = (dist.all_reduce, shards.group, res.dev)
 
-            timed = self.profile
-
-            def fun(x):
-                th.eta = float(x[0])
-                th.epsilon = float(x[1])
-                if timed is None:
+        def fun(x):
+            th.eta = float(x[0])
+            th.epsilon = float(x[1])
+            if timed is None:
+                rc = fn(*head, 1, *tail)
+            else:
+                with timed(name):
                     rc = fn(*head, 1, *tail)
-                else:
-                    with timed(name):
-                        rc = fn(*head, 1, *tail)
-                if rc != 0:
-                    _lib.check(rc, name)
-                o = read(stream)
-                elm = float(o[0]) + (float(o[3]) if const is None else const)
-                evals.append(dict(x=(th.eta, th.epsilon), verF=verF, verR=verR, elm=elm))
-                return -elm, o[1:3]
+            if rc != 0:
+                _lib.check(rc, name)
+            if shards is not None:
+                all_reduce(dev_vec, group=group)              # all four slots are edge-local partial sums
+            o = read(stream)
+            const = ctx['const']
+            if const is None:
+                const = float(o[3])
+                if shards is not None:
+                    # slot 3 (theta-free part, written once by the bucket pass) is now global: keep it
+                    # and zero the slot so that the next all-reduces do not add it again
+                    ctx['const'] = const
+                    dev_vec[3:].zero_()
+            elm = float(o[0]) + const
+            evals.append(dict(x=(th.eta, th.epsilon), verF=verF, verR=verR, elm=elm))
+            return -elm, o[1:3]
 
         opt_result = _opt.minimize_lbfgsb(fun, theta_sub, [eps, eps], [1 - eps, 1 - eps])
         del self._evals[:-4]
