@@ -66,3 +66,26 @@ def test_map_labels_and_ranking():
     # ties resolve to the first maximum, like numpy.argmax
     fit._lq_F = np.log(np.full((36, 1, 3), 1.0 / 3))
     nptest.assert_array_equal(fit.map_template(), np.zeros(36, dtype=np.uint8))
+
+
+def test_time_series_files_to_fit(tmp_path):
+    """Input adapter end to end: per-subject CSV time series -> K1 (tensor-core or
+    SIMT Gram + Fisher z) -> (b, bt) equal to numpy.corrcoef + arctanh, usable by the fit."""
+    from fcdiff_b200 import io as fio
+    rng = np.random.RandomState(1)
+    (N, T, H, U) = (9, 50, 6, 5)
+    paths = []
+    for s in range(H + U):
+        p = tmp_path / ("sub%02d.csv" % s)
+        np.savetxt(p, rng.randn(N, T), delimiter=",")
+        paths.append(str(p))
+    (b, bt) = fio.correlations_from_files(paths[:H], paths[H:])
+    assert b.shape == (36, H) and bt.shape == (36, U)
+    ts = fio.load_timeseries(paths)
+    nptest.assert_allclose(np.concatenate([b, bt], axis=1), O.corr_fisherz(ts.astype(np.float64)), rtol=1e-5, atol=2e-6)
+    fit = fcdiff.fit.UnsharedRegionFit()
+    fit.model = fcdiff.UnsharedRegionModel()
+    (fit.b, fit.bt) = (b, bt)
+    fit.max_iters = 2
+    fit.run()
+    assert len(fit.energy) >= 2 and np.all(np.isfinite(fit.energy))

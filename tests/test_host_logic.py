@@ -196,3 +196,34 @@ def test_replica_split_and_label_permutations():
     assert a.shape == (7, 12) and np.array_equal(a[0], labels) and np.all(a.sum(axis=1) == 5)
     assert np.array_equal(a, ns["permuted_labels"](labels, 6, seed=3))
     assert not np.array_equal(a[1], a[2])
+
+
+def test_time_series_file_loaders(tmp_path):
+    """Host half of the input adapters (fcdiff_b200/io.py): .npy / .csv / .tsv
+    parsing, header detection, time-major transposition, shape checks.  The
+    module is loaded without its package (the package needs CUDA at call time
+    only, but importing torch is enough of a dependency for this test)."""
+    import ast
+    import os
+    src = open(os.path.join(os.path.dirname(__file__), "..", "fcdiff_b200", "io.py")).read()
+    tree = ast.parse(src)
+    ns = {"np": np, "os": os}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("load_subject", "load_timeseries"):
+            exec(compile(ast.Module([node], []), "io.py", "exec"), ns)
+    rng = np.random.RandomState(0)
+    a = rng.randn(5, 12).astype(np.float32)
+    np.save(tmp_path / "s0.npy", a)
+    np.savetxt(tmp_path / "s1.csv", a, delimiter=",", header="t0,t1", comments="")     # header line
+    np.savetxt(tmp_path / "s2.tsv", a.T, delimiter="\t")                                # time-major
+    got0 = ns["load_subject"](str(tmp_path / "s0.npy"))
+    got1 = ns["load_subject"](str(tmp_path / "s1.csv"))
+    got2 = ns["load_subject"](str(tmp_path / "s2.tsv"), time_major=True)
+    for g in (got0, got1, got2):
+        assert g.dtype == np.float32 and g.shape == (5, 12)
+        np.testing.assert_allclose(g, a, rtol=1e-6)
+    ts = ns["load_timeseries"]([str(tmp_path / "s0.npy"), str(tmp_path / "s1.csv")])
+    assert ts.shape == (2, 5, 12)
+    np.save(tmp_path / "bad.npy", a[:, :7])
+    with pytest.raises(ValueError):
+        ns["load_timeseries"]([str(tmp_path / "s0.npy"), str(tmp_path / "bad.npy")])
