@@ -178,10 +178,13 @@ estep_qF_kernel(const double* __restrict__ S1, const double* __restrict__ S2,
                                                              : make_double2(1.0, 0.0);
     __syncthreads();
     double acc1[3] = {0.0, 0.0, 0.0};
-    auto live = [&](const double (&pv)[3], int lp, int e) {
+    // planes 0 and 1 are streamed; p_2 = 1 - p_0 - p_1 (absolute error 1e-16 on an argument
+    // a_l + b_l p >= min(a_l, eps_l): below the rounding of the log)
+    auto live = [&](const double (&pv)[2], int lp, int e) {
         const double2 k = s_lc[lp];
+        const double p3[3] = {pv[0], pv[1], (1.0 - pv[0]) - pv[1]};
 #pragma unroll
-        for (int i = 0; i < 3; ++i) (e ? acc1 : acc)[i] += fast_log<FAST>(fma(k.y, pv[i], k.x), s_tab);
+        for (int i = 0; i < 3; ++i) (e ? acc1 : acc)[i] += fast_log<FAST>(fma(k.y, p3[i], k.x), s_tab);
     };
     struct Ops {
         double p[3];
@@ -194,8 +197,9 @@ estep_qF_kernel(const double* __restrict__ S1, const double* __restrict__ S2,
         if (ok) {
             o.qn = __ldg(qR2 + (int64_t)n * U + u);
             o.qm = __ldg(qR2 + (int64_t)m * U + u);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) o.p[k] = ldg_stream1(P + k * planeStride + c * pitchU + u);
+            o.p[0] = ldg_stream1(P + c * pitchU + u);
+            o.p[1] = ldg_stream1(P + planeStride + c * pitchU + u);
+            o.p[2] = (1.0 - o.p[0]) - o.p[1];
         }
         return o;
     };
@@ -217,7 +221,7 @@ estep_qF_kernel(const double* __restrict__ S1, const double* __restrict__ S2,
         acc[0] = acc[1] = acc[2] = 0.0;
         acc1[0] = acc1[1] = acc1[2] = 0.0;
     };
-    stream_tiered<3, kK2Seg, kStreamWarps, true, false>(P, planeStride, C, U, pitchU, nullptr, rstate, pitchS, nm,
+    stream_tiered<2, kK2Seg, kStreamWarps, true, false>(P, planeStride, C, U, pitchU, nullptr, rstate, pitchS, nm,
                                                         s_stream, depth, live, dload, dcompute,
                                                         [](int64_t, int, int, int, int) {}, row_end);
 }
@@ -744,9 +748,9 @@ int fcd_estep_qF(const double* S1, const double* S2, int32_t H,
     FCD_REQUIRE(log_table_window(th.epsl, th.al, st, tab), "fcd_estep_qF: log table initialisation failed");
     const bool fast = log_table_covers(th.epsl, th.al);
     const size_t tbytes = fast ? (size_t)((tab.n + 1) & ~1) * sizeof(double) : 0;
-    const int depth = stream_depth<3, kK2Seg>(tbytes);
+    const int depth = stream_depth<2, kK2Seg>(tbytes);
     FCD_REQUIRE(depth >= 2, "fcd_estep_qF: shared memory budget exceeded");
-    const size_t smem = tbytes + StreamGeom<3, kK2Seg>::bytes(kStreamWarps, depth);
+    const size_t smem = tbytes + StreamGeom<2, kK2Seg>::bytes(kStreamWarps, depth);
     int64_t grid = (C + kStreamWarps - 1) / kStreamWarps;
     if (grid > sm_count()) grid = sm_count();                       // one persistent CTA per SM
 #define FCD_K2(F)                                                                                 \
