@@ -246,6 +246,8 @@ def run_gpu_arm(args):
         if shards is not None:
             fit.shards = shards
             fit.n_edges = C
+        if os.environ.get("FCD_FUSED_SWEEP"):                 # manual experiments
+            fit.fused_sweep = os.environ["FCD_FUSED_SWEEP"] == "1"
         return fit
 
     def barrier():

@@ -477,76 +477,152 @@ sweep_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int u0,
 // back) and no region_weights pass.  With edge_lookup = "reference" the edges
 // read at step n are the contiguous window [n(n-1)/2, n(n-1)/2 + N)
 // (fit.py:185-186), and the windows of successive steps slide monotonically over
-// the patient's row of the dominant-state plane PsT (fcd_region_weights): the
-// row is streamed by TMA bulk copies (64-edge chunks, p and the edges' peak
-// states) into a staging ring, every edge is converted ONCE into its three
-// weights W_l = log(a_l + b_l p) -- by all threads of the patient's group, ahead
-// of the window that needs it -- and kept in a shared-memory ring until the
-// window has passed.  A step then reads its window from shared memory, reduces
-// (warp shuffle + ONE barrier) and only the owner of region n normalises
-// (fit.py:196-197).  T threads per patient (thread t owns the regions m = t,
-// t + T, ...; their q_R stay in registers), PPC patients per CTA sharing the log
-// table; each patient group synchronises on its own named barrier.
-// Ring capacity: window n (still being read) and window n + 1 (being prepared)
-// must fit: n + N <= R for every step n, i.e. 2N - 1 <= R.
+// the patient's row of the dominant-state plane PsT (fcd_region_weights).
+// Warp-specialised, per patient a group of T sweep threads and TC converter
+// threads:
+//   * converter lane 0 streams the row by TMA bulk copies (64-edge chunks: p and
+//     the edges' peak states) into a staging ring;
+//   * the converter warps turn every edge ONCE into its three weights
+//     W_l = log(a_l + b_l p) and store them in a shared-memory ring of R edges,
+//     one window ahead of the sweep (iteration j prepares window j while the
+//     sweep works on step j - 1; handshake over two mbarriers: READY_j / START_j);
+//   * the sweep threads (thread t owns the regions m = t, t + T, ...; their q_R
+//     stay in registers) read their window from shared memory, reduce (warp
+//     shuffle + ONE named barrier) and only the owner of region n normalises
+//     (fit.py:196-197): no logarithm is left on the sweep's critical path.
+// PPC patient groups per CTA share the log table.  Ring capacity: window n (being
+// read) and window n + 1 (being prepared) must fit: 2N - 1 <= R.
 constexpr int kSwChunk = 64;
 
 template <int T, int R>
 struct SweepSmem {
     static constexpr int NW = T / 32;
     static constexpr int kSlots = R / kSwChunk;
-    static constexpr size_t bytes = (size_t)3 * R * 8 + (size_t)R * 8 + R + kSlots * 8 + 2 * NW * 2 * 8;
+    static constexpr size_t bytes = (size_t)3 * R * 8 + (size_t)R * 8 + R + (kSlots + 2) * 8 + 2 * NW * 2 * 8;
     static constexpr size_t padded = (bytes + 127) / 128 * 128;
 };
 
-template <int T, int MPT, int PPC, int R, bool FAST>
-__global__ void __launch_bounds__(T * PPC)
+template <int T, int TC, int MPT, int PPC, int R, bool FAST>
+__global__ void __launch_bounds__((T + TC) * PPC)
 sweep_fused_kernel(const double* __restrict__ PsT, const double* __restrict__ PT, int64_t planeStride,
                    int64_t pitchC, const double* __restrict__ qF, const uint8_t* __restrict__ fstate,
                    int64_t pitchF, int64_t C, int N, int U, int u0, int Ul, double lp0, double lp1,
                    const __grid_constant__ ThetaDev th, const __grid_constant__ LogTabWindow tab,
                    double* __restrict__ qR, double* __restrict__ lqR) {
-    constexpr int NW = T / 32, kSlots = R / kSwChunk, kAhead = 128;
+    constexpr int NW = T / 32, NCV = TC / 32, kSlots = R / kSwChunk, kAhead = 64;
     extern __shared__ __align__(128) double s_dyn[];
     const double* s_tab = load_log_table<FAST>(tab, s_dyn);
-    const int pp = threadIdx.x / T, tid = threadIdx.x % T, lane = tid & 31, warp = tid >> 5;
+    const int pp = threadIdx.x / (T + TC), gt = threadIdx.x % (T + TC);      // patient group, thread in group
     const int ul = blockIdx.x * PPC + pp;
-    if (ul >= Ul) return;                                    // whole patient group leaves (own barrier id)
+    if (ul >= Ul) return;                                    // whole patient group leaves (its barriers are its own)
     unsigned char* mine = reinterpret_cast<unsigned char*>(s_dyn + (FAST ? ((tab.n + 15) & ~15) : 0)) +
                           (size_t)pp * SweepSmem<T, R>::padded;
-    double* wring = reinterpret_cast<double*>(mine);         // [3][R]
+    double* wring = reinterpret_cast<double*>(mine);         // [3][R] weights
     double* pring = wring + 3 * R;                           // [R] staged responsibilities
     uint8_t* fring = reinterpret_cast<uint8_t*>(pring + R);  // [R] staged peak states
-    uint64_t* bars = reinterpret_cast<uint64_t*>(fring + R);
-    double* s_red = reinterpret_cast<double*>(bars + kSlots);            // [2][NW][2]
-    auto group_sync = [&]() {                                // immediate barrier ids: a register id reserves all 16
-        if (PPC == 1 || pp == 0) asm volatile("bar.sync 1, %0;" ::"n"(T) : "memory");
-        else if (pp == 1) asm volatile("bar.sync 2, %0;" ::"n"(T) : "memory");
-        else if (pp == 2) asm volatile("bar.sync 3, %0;" ::"n"(T) : "memory");
-        else asm volatile("bar.sync 4, %0;" ::"n"(T) : "memory");
-    };
+    uint64_t* bars = reinterpret_cast<uint64_t*>(fring + R); // [kSlots] chunk arrival, then READY, START
+    uint64_t* ready = bars + kSlots;                         // completed by the NCV converter warps per window
+    uint64_t* start = ready + 1;                             // completed by the NW sweep warps per step
+    double* s_red = reinterpret_cast<double*>(start + 1);    // [2][NW][2]
+    // init by the group's first thread, published to the group by a named barrier over ALL its threads
+    if (gt == 0) {
+        for (int i = 0; i < kSlots; ++i) mbar_init(bars + i, 1);
+        mbar_init(ready, NCV);
+        mbar_init(start, NW);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (PPC == 1 || pp == 0) asm volatile("bar.sync 1, %0;" ::"n"(T + TC) : "memory");
+    else if (pp == 1) asm volatile("bar.sync 2, %0;" ::"n"(T + TC) : "memory");
+    else if (pp == 2) asm volatile("bar.sync 3, %0;" ::"n"(T + TC) : "memory");
+    else asm volatile("bar.sync 4, %0;" ::"n"(T + TC) : "memory");
 
     const int u = u0 + ul;
-    const double* row = PsT + (int64_t)ul * pitchC;
-    const int nchunks = (int)((pitchC + kSwChunk - 1) / kSwChunk);
-    int next_issue = 0;                                      // meaningful in tid 0 only
-    auto issue = [&](int g) {
-        uint64_t* bar = bars + (g % kSlots);
-        const int64_t e0 = (int64_t)g * kSwChunk;
-        const uint32_t ne = (uint32_t)(pitchC - e0 < kSwChunk ? pitchC - e0 : kSwChunk);
-        const uint32_t nf = (uint32_t)(pitchF - e0 < kSwChunk ? pitchF - e0 : kSwChunk);
-        const int so = (g % kSlots) * kSwChunk;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(bar, ne * 8 + nf);
-        tma_load_1d(pring + so, row + e0, ne * 8, bar);
-        tma_load_1d(fring + so, fstate + e0, nf, bar);
+    auto clampC = [&](int64_t e) { return e < C ? e : C; };
+    // edges [0, target(j)) must be converted before the sweep reads window j
+    auto target = [&](int j) {
+        const int64_t base = (int64_t)j * (j - 1) / 2;
+        int64_t t = base + N + kAhead;                       // end of window j and a little ahead
+        if (j > 0) {                                         // window j - 1 is still being read: its slots stay
+            const int64_t cap = (int64_t)(j - 1) * (j - 2) / 2 + R;
+            if (t > cap) t = cap;
+        } else if (t > R) {
+            t = R;
+        }
+        return clampC(t);
     };
-    if (tid < kSlots) mbar_init(bars + tid, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    group_sync();
-    if (tid == 0)
-        for (; next_issue < kSlots && next_issue < nchunks; ++next_issue) issue(next_issue);
 
+    if (gt >= T) {
+        // ------------------------------------------------------------ converter warps
+        const int ct = gt - T, lane = ct & 31;
+        const double* row = PsT + (int64_t)ul * pitchC;
+        const int nchunks = (int)((pitchC + kSwChunk - 1) / kSwChunk);
+        const double al[3] = {th.al[0], th.al[1], th.al[2]}, bl[3] = {th.bl[0], th.bl[1], th.bl[2]};
+        int next_issue = 0;                                  // meaningful in ct == 0 only
+        auto issue = [&](int g) {
+            uint64_t* bar = bars + (g % kSlots);
+            const int64_t e0 = (int64_t)g * kSwChunk;
+            const uint32_t ne = (uint32_t)(pitchC - e0 < kSwChunk ? pitchC - e0 : kSwChunk);
+            const uint32_t nf = (uint32_t)(pitchF - e0 < kSwChunk ? pitchF - e0 : kSwChunk);
+            const int so = (g % kSlots) * kSwChunk;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bar, ne * 8 + nf);
+            tma_load_1d(pring + so, row + e0, ne * 8, bar);
+            tma_load_1d(fring + so, fstate + e0, nf, bar);
+        };
+        if (ct == 0)
+            for (; next_issue < kSlots && next_issue < nchunks; ++next_issue) issue(next_issue);
+        int waited = -1;                                     // chunks 0..waited have arrived (per thread)
+        int64_t cv = 0;                                      // edges [0, cv) are converted (same in all converter threads)
+        for (int j = 0; j < N; ++j) {
+            if (j >= 1) mbar_wait(start, (uint32_t)((j - 1) & 1));       // sweep has begun step j-1: windows < j-1 are dead
+            const int64_t tg = target(j);
+            if (tg > cv) {
+                const int ghi = (int)((tg - 1) / kSwChunk);
+                for (; waited < ghi; ++waited) mbar_wait(bars + ((waited + 1) % kSlots), ((waited + 1) / kSlots) & 1);
+                for (int64_t e = cv + ct; e < tg; e += TC) {
+                    const int idx = (int)(e & (R - 1));
+                    const int k = fring[idx];
+                    double w[3];
+                    if (k < 3) {
+                        const double p = pring[idx];
+#pragma unroll
+                        for (int l = 0; l < 3; ++l) w[l] = fast_log<FAST>(fma(bl[l], p, al[l]), s_tab);
+                    } else {                                 // edge whose q_F is not peaked (rare): all three planes
+                        const double qf[3] = {__ldg(qF + e * 3), __ldg(qF + e * 3 + 1), __ldg(qF + e * 3 + 2)};
+                        w[0] = w[1] = w[2] = 0.0;
+#pragma unroll
+                        for (int kk = 0; kk < 3; ++kk) {
+                            const double p = ldg_stream1(PT + kk * planeStride + (int64_t)ul * pitchC + e);
+#pragma unroll
+                            for (int l = 0; l < 3; ++l)
+                                w[l] = fma(qf[kk], fast_log<FAST>(fma(bl[l], p, al[l]), s_tab), w[l]);
+                        }
+                    }
+                    wring[idx] = w[0];
+                    wring[R + idx] = w[1];
+                    wring[2 * R + idx] = w[2];
+                }
+                cv = tg;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ready);               // window j is in the ring (release)
+            if (ct == 0) {                                   // staged chunks every converter is done with: refill
+                mbar_wait(ready, (uint32_t)(j & 1));
+                const int done = (int)(cv / kSwChunk);
+                for (; next_issue < nchunks && next_issue - kSlots < done; ++next_issue) issue(next_issue);
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------- sweep warps
+    const int tid = gt, lane = tid & 31, warp = tid >> 5;
+    auto sweep_sync = [&]() {                                // immediate barrier ids: a register id reserves all 16
+        if (PPC == 1 || pp == 0) asm volatile("bar.sync 5, %0;" ::"n"(T) : "memory");
+        else if (pp == 1) asm volatile("bar.sync 6, %0;" ::"n"(T) : "memory");
+        else if (pp == 2) asm volatile("bar.sync 7, %0;" ::"n"(T) : "memory");
+        else asm volatile("bar.sync 8, %0;" ::"n"(T) : "memory");
+    };
     double q0[MPT], q1[MPT];
 #pragma unroll
     for (int j = 0; j < MPT; ++j) {
@@ -557,44 +633,11 @@ sweep_fused_kernel(const double* __restrict__ PsT, const double* __restrict__ PT
             q1[j] = qR[((int64_t)m * U + u) * 2 + 1];
         }
     }
-    const double al[3] = {th.al[0], th.al[1], th.al[2]}, bl[3] = {th.bl[0], th.bl[1], th.bl[2]};
-    int waited = -1;                                         // chunks 0..waited have arrived (per thread)
-    int64_t cv = 0;                                          // edges [0, cv) have been converted (same in all threads)
-    // converts the edges [cv, target) of the patient's row into the weight ring
-    auto convert = [&](int64_t target) {
-        if (target <= cv) return;
-        const int ghi = (int)((target - 1) / kSwChunk);
-        for (; waited < ghi; ++waited) mbar_wait(bars + ((waited + 1) % kSlots), ((waited + 1) / kSlots) & 1);
-        for (int64_t e = cv + tid; e < target; e += T) {
-            const int idx = (int)(e & (R - 1));
-            const int k = fring[idx];
-            double w[3];
-            if (k < 3) {
-                const double p = pring[idx];
-#pragma unroll
-                for (int l = 0; l < 3; ++l) w[l] = fast_log<FAST>(fma(bl[l], p, al[l]), s_tab);
-            } else {                                         // edge whose q_F is not peaked (rare): all three planes
-                const double qf[3] = {__ldg(qF + e * 3), __ldg(qF + e * 3 + 1), __ldg(qF + e * 3 + 2)};
-                w[0] = w[1] = w[2] = 0.0;
-#pragma unroll
-                for (int kk = 0; kk < 3; ++kk) {
-                    const double p = ldg_stream1(PT + kk * planeStride + (int64_t)ul * pitchC + e);
-#pragma unroll
-                    for (int l = 0; l < 3; ++l) w[l] = fma(qf[kk], fast_log<FAST>(fma(bl[l], p, al[l]), s_tab), w[l]);
-                }
-            }
-            wring[idx] = w[0];
-            wring[R + idx] = w[1];
-            wring[2 * R + idx] = w[2];
-        }
-        cv = target;
-    };
-    auto clampC = [&](int64_t e) { return e < C ? e : C; };
-    convert(clampC((int64_t)N + kAhead < R ? (int64_t)N + kAhead : R));       // window 0 = [0, N)
-    group_sync();
     for (int n = 0; n < N; ++n) {
-        const int64_t base = (int64_t)n * (n - 1) / 2;
-        const uint32_t base_lo = (uint32_t)base;
+        mbar_wait(ready, (uint32_t)(n & 1));                 // window n converted (acquire)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(start);                   // step n has begun: the converters may prepare window n+1
+        const uint32_t base_lo = (uint32_t)((int64_t)n * (n - 1) / 2);
         double s0 = 0.0, s1 = 0.0;
 #pragma unroll
         for (int j = 0; j < MPT; ++j) {
@@ -612,12 +655,7 @@ sweep_fused_kernel(const double* __restrict__ PsT, const double* __restrict__ PT
             s_red[((n & 1) * NW + warp) * 2] = s0;
             s_red[((n & 1) * NW + warp) * 2 + 1] = s1;
         }
-        if (n + 1 < N) {                                      // prepare window n + 1 while the others arrive
-            int64_t target = base + n + N + kAhead;           // end of window n + 1, and a little ahead
-            if (target > base + R) target = base + R;         // window n is still being read: its slots stay
-            convert(clampC(target));
-        }
-        group_sync();
+        sweep_sync();
         if (tid == (n & (T - 1))) {                           // owner of region n
             double a = 0.0, b = 0.0;
 #pragma unroll
@@ -652,10 +690,6 @@ sweep_fused_kernel(const double* __restrict__ PsT, const double* __restrict__ PT
             lqR[o + 1] = l1;
             qR[o] = p0;
             qR[o + 1] = p1;
-        }
-        if (tid == 0) {                                       // staged chunks that are converted are dead: refill
-            const int done = (int)(cv / kSwChunk);            // chunks [0, done) fully converted
-            for (; next_issue < nchunks && next_issue - kSlots < done; ++next_issue) issue(next_issue);
         }
     }
 }
@@ -881,20 +915,21 @@ int fcd_estep_qR_fused(const double* PsT, const double* PT, int64_t planeStride,
     const bool fast = log_table_covers(th.epsl, th.al);
     const size_t tbytes = fast ? (size_t)((tab.n + 15) & ~15) * sizeof(double) : 0;
     const double lp0 = log_pi2_host[0], lp1 = log_pi2_host[1];
-#define FCD_SWF(T, PPC, RR, F)                                                                          \
+#define FCD_SWF(T, TC, PPC, RR, F)                                                                      \
     do {                                                                                                \
         const size_t smem = tbytes + (size_t)(PPC) * SweepSmem<T, RR>::padded;                          \
-        cudaFuncSetAttribute(sweep_fused_kernel<T, 4, PPC, RR, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+        cudaFuncSetAttribute(sweep_fused_kernel<T, TC, 4, PPC, RR, F>,                                  \
+                             cudaFuncAttributeMaxDynamicSharedMemorySize,                               \
                              (int)(kLogTabBytes + 128 + (PPC) * SweepSmem<T, RR>::padded));              \
-        sweep_fused_kernel<T, 4, PPC, RR, F><<<(Ul + (PPC) - 1) / (PPC), (T) * (PPC), smem, st>>>(       \
+        sweep_fused_kernel<T, TC, 4, PPC, RR, F><<<(Ul + (PPC) - 1) / (PPC), ((T) + (TC)) * (PPC), smem, st>>>( \
             PsT, PT, planeStride, pitchC, qF, fstate, pitchF, C, N, U, u0, Ul, lp0, lp1, th, tab, qR, lqR); \
     } while (0)
 #define FCD_SWF_N(F)                                                                                    \
     do {                                                                                                \
-        if (N <= 128) FCD_SWF(32, 4, 1024, F);                                                          \
-        else if (N <= 256) FCD_SWF(64, 4, 1024, F);                                                     \
-        else if (N <= 512) FCD_SWF(128, 4, 1024, F);                                                    \
-        else FCD_SWF(256, 2, 2048, F);                                                                  \
+        if (N <= 128) FCD_SWF(32, 32, 4, 1024, F);                                                      \
+        else if (N <= 256) FCD_SWF(64, 64, 4, 1024, F);                                                 \
+        else if (N <= 512) FCD_SWF(128, 128, 4, 1024, F);                                               \
+        else FCD_SWF(256, 128, 2, 2048, F);                                                             \
     } while (0)
     if (fast) FCD_SWF_N(true); else FCD_SWF_N(false);
 #undef FCD_SWF_N
