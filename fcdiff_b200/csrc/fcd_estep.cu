@@ -178,13 +178,32 @@ estep_qF_kernel(const double* __restrict__ S1, const double* __restrict__ S2,
                                                              : make_double2(1.0, 0.0);
     __syncthreads();
     double acc1[3] = {0.0, 0.0, 0.0};
+    // FAST: the T1 logs have weight exactly 1, so each lane keeps running PRODUCTS of the mixture
+    // weights (two sets of three, fcd_math.cuh "Sum of logs as the log of a product") and takes
+    // three logarithms per row (or per kProdMax chunks of a long row) instead of three per element.
+    double pr[2][3] = {{1.0, 1.0, 1.0}, {1.0, 1.0, 1.0}};
+    int nf = 0;
+    auto flush = [&]() {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            acc[i] += log_pos<FAST>(pr[0][i] * pr[1][i], s_tab);
+            pr[0][i] = pr[1][i] = 1.0;
+        }
+        nf = 0;
+    };
     // planes 0 and 1 are streamed; p_2 = 1 - p_0 - p_1 (absolute error 1e-16 on an argument
     // a_l + b_l p >= min(a_l, eps_l): below the rounding of the log)
     auto live = [&](const double (&pv)[2], int lp, int e) {
         const double2 k = s_lc[lp];
         const double p3[3] = {pv[0], pv[1], (1.0 - pv[0]) - pv[1]};
+        if (FAST) {
 #pragma unroll
-        for (int i = 0; i < 3; ++i) (e ? acc1 : acc)[i] += fast_log<FAST>(fma(k.y, p3[i], k.x), s_tab);
+            for (int i = 0; i < 3; ++i) pr[e][i] *= fma(k.y, p3[i], k.x);
+            if (e == 1 && ++nf == kProdMax) flush();              // warp-uniform
+        } else {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) (e ? acc1 : acc)[i] += fast_log<FAST>(fma(k.y, p3[i], k.x), s_tab);
+        }
     };
     struct Ops {
         double p[3];
@@ -215,6 +234,7 @@ estep_qF_kernel(const double* __restrict__ S1, const double* __restrict__ S2,
         }
     };
     auto row_end = [&](int64_t c) {
+        if (FAST && nf > 0) flush();
 #pragma unroll
         for (int k = 0; k < 3; ++k) acc[k] = warp_sum(acc[k] + acc1[k]);
         if (lane == 0) k2_finish(c, acc, S1[c], S2[c], th, lqF, qF);
@@ -779,7 +799,7 @@ int fcd_estep_qF(const double* S1, const double* S2, int32_t H,
     const ThetaDev th = make_theta_dev(*theta_host, H);
     cudaStream_t st = (cudaStream_t)stream;
     LogTabWindow tab;
-    FCD_REQUIRE(log_table_window(th.epsl, th.al, st, tab), "fcd_estep_qF: log table initialisation failed");
+    FCD_REQUIRE(log_table_window(th.epsl, th.al, st, tab, true), "fcd_estep_qF: log table initialisation failed");
     const bool fast = log_table_covers(th.epsl, th.al);
     const size_t tbytes = fast ? (size_t)((tab.n + 1) & ~1) * sizeof(double) : 0;
     const int depth = stream_depth<2, kK2Seg>(tbytes);

@@ -13,8 +13,8 @@
 //    -log r8 from a 10752-entry table in shared memory (indexed by the
 //    exponent/mantissa bits of r8), log1p(u) = u - u^2/2 + u^3/3
 //    (truncation u^4/4 <= 2.3e-13).  5 fp64 ops + 1 MUFU + 1 LDS instead of ~40.
-//  * fast_log_rcp additionally returns 1/y = r8 * (1 - u + u^2), rel. error
-//    <= u^3 = 9.3e-10, for the analytic gradient (3 more fp64 ops, no second
+//  * fast_log_rcp additionally returns 1/y = r8 * (1 - u + u^2 - u^3 + u^4), rel.
+//    error <= u^5 = 2^-50, for the analytic gradient (4 more fp64 ops, no second
 //    MUFU / Newton iteration).
 //  * exp_nonpos(d): d <= 0, argument reduction with the 1.5*2^52 trick (no
 //    F2I/I2F conversions), degree-11 polynomial, exponent patched in the ALU.
@@ -50,7 +50,10 @@ struct LogTabWindow {
     int n;
     size_t bytes() const { return (size_t)n * sizeof(double); }
 };
-bool log_table_window(const double epsl[3], const double al[3], cudaStream_t st, LogTabWindow& w);
+// with_mantissa: the window also starts at slot 0, i.e. includes the binade of arguments in [1, 2]
+// that log_pos (below) needs for the mantissa of an arbitrary positive double (+ 4 KB).
+bool log_table_window(const double epsl[3], const double al[3], cudaStream_t st, LogTabWindow& w,
+                      bool with_mantissa = false);
 
 #ifdef __CUDACC__
 
@@ -119,9 +122,41 @@ __device__ __forceinline__ double fast_log_rcp(double y, const double* s_tab, do
         return log(y);
     }
     const LogParts p = log_reduce(y);
-    const double g = fma(p.u, p.u, 1.0 - p.u);       // 1 - u + u^2   (u^3 <= 9.3e-10 relative)
+    // 1 / (1 + u) = 1 - u + u^2 - u^3 + u^4 (- u^5 <= 2^-50): the gradient sums ~10^7 such terms with
+    // cancellation, so a one-sided truncation error of 1e-9 per term would show at 1e-3 of the net gradient
+    const double om = 1.0 - p.u, uu = p.u * p.u;
+    const double g = fma(uu, fma(p.u, p.u, om), om);
     rcp = p.r8 * g;
-    return s_tab[p.idx] + log1p_small(p.u);
+    return s_tab[p.idx] + fma(uu, fma(p.u, 1.0 / 3.0, -0.5), p.u);
+}
+
+// Sum of logs as the log of a product.  Where a kernel adds log(y_i) with weight exactly 1 (tier T1),
+// it multiplies the y_i into a running product instead and takes ONE logarithm per kProdMax factors:
+// y_i > 2^-20 (log_table_covers) bounds a product of 2 x kProdMax factors below by 2^-960 (no underflow),
+// and the relative rounding error of n multiplications, n 2^-53, is an ABSOLUTE error of the sum of logs
+// -- smaller than the table logarithm's 3e-13 per term.  One multiplication instead of ~12 instructions.
+constexpr int kProdMax = 24;      // factors per running product; two products are merged before the log
+
+// log(x) for any positive normal double: x = m 2^e, m in [1, 2); needs the window's mantissa binade
+// (log_table_window(..., with_mantissa = true)).
+template <bool FAST>
+__device__ __forceinline__ double log_pos(double x, const double* s_tab) {
+    if (!FAST) return log(x);
+    const int hi = __double2hiint(x);
+    const int e = (hi >> 20) - 1023;
+    const double m = __hiloint2double((hi & 0x000fffff) | (1023 << 20), __double2loint(x));
+    const LogParts p = log_reduce(m);
+    return fma((double)e, 6.93147180559945286227e-01, s_tab[p.idx] + log1p_small(p.u));
+}
+
+// 1 / y to rounding: MUFU.RCP64H (relative error e ~ 2^-18) and r0 (1 + e + e^2), e = 1 - y r0 exact
+// to one rounding; the truncation e^3 ~ 2^-54 leaves no systematic bias in sums of 10^7 terms
+// (a plain Newton step's -e^2 does).  No table, no integer work.
+__device__ __forceinline__ double rcp_newton(double y) {
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(y));
+    const double e = fma(-y, r0, 1.0);
+    return fma(r0, fma(e, e, e), r0);
 }
 
 // e^d for d <= 0 (d is clamped at -700: e^-700 ~ 1e-304 is far below any

@@ -74,7 +74,8 @@ bool log_table_covers(const double epsl[3], const double al[3]) {
     return true;
 }
 
-bool log_table_window(const double epsl[3], const double al[3], cudaStream_t st, LogTabWindow& w) {
+bool log_table_window(const double epsl[3], const double al[3], cudaStream_t st, LogTabWindow& w,
+                      bool with_mantissa) {
     w.g = log_table(st);
     w.lo = 0;
     w.n = kLogTabSize;
@@ -95,7 +96,7 @@ bool log_table_window(const double epsl[3], const double al[3], cudaStream_t st,
         return (hi >> (20 - kLogTabBits)) - kLogTabBase;
     };
     int lo = slot(ymax) - 4, hi = slot(ymin) + 4;           // slack: MUFU.RCP64H error, FMA rounding
-    if (lo < 0) lo = 0;
+    if (lo < 0 || with_mantissa) lo = 0;
     if (hi > kLogTabSize - 1) hi = kLogTabSize - 1;
     w.lo = lo;
     w.n = hi - lo + 1;

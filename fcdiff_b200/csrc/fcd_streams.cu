@@ -308,14 +308,20 @@ bucket_records_kernel(Record* __restrict__ D, long long nd, const double* __rest
 
 // One evaluation: out[0] = sum_l sum_{p in G_l} log(a_l + b_l p) + sum_records sum_l w_l log(a_l + b_l p),
 // out[1] = dE/d eta, out[2] = dE/d eps as in elm_kernel (fcd_mstep.cu).
+// FAST: the stream elements have weight exactly 1, so the objective is the log of a running product
+// (fcd_math.cuh "Sum of logs as the log of a product"; flushed by the caller every kProdMax factors)
+// and the gradient needs 1 / M only: MUFU.RCP64H + one Newton step.  7 fp64 instructions per element.
 struct StreamAcc {
-    double obj, g;
+    double obj, g, prod;
 };
 
 template <bool GRAD, bool FAST>
 __device__ __forceinline__ void stream_elem(double p, double a, double b, const double* s_tab, StreamAcc& acc) {
     const double M = fma(b, p, a);
-    if (GRAD) {
+    if (FAST) {
+        acc.prod *= M;
+        if (GRAD) acc.g = fma(mix_num(p), rcp_newton(M), acc.g);
+    } else if (GRAD) {
         double rcp;
         acc.obj += fast_log_rcp<FAST>(M, s_tab, rcp);
         acc.g = fma(mix_num(p), rcp, acc.g);
@@ -324,73 +330,16 @@ __device__ __forceinline__ void stream_elem(double p, double a, double b, const 
     }
 }
 
-constexpr int kStreamEvalThreads = 256;
-
-template <bool GRAD, bool FAST>
-__global__ void __launch_bounds__(kStreamEvalThreads, 3)
-elm_streams_kernel(const double* __restrict__ G, long long base0, long long base1, long long base2,
-                   long long n0, long long n1, long long n2,
-                   const Record* __restrict__ D, long long nd,
-                   const __grid_constant__ ThetaDev th, const __grid_constant__ LogTabWindow tab,
-                   double* __restrict__ out, double* __restrict__ ws) {
-    extern __shared__ __align__(16) double s_dyn[];
-    const double* s_tab = load_log_table<FAST>(tab, s_dyn);
-    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const long long nth = (long long)gridDim.x * blockDim.x;
-    const long long base[3] = {base0, base1, base2};
-    const long long cnt[3] = {n0, n1, n2};
-    double obj = 0.0, gl[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-    for (int l = 0; l < 3; ++l) {
-        const double a = th.al[l], b = th.bl[l];
-        const double* g = G + base[l];                       // 16-byte aligned (even base)
-        const long long npair = cnt[l] >> 1;
-        StreamAcc a0 = {0.0, 0.0}, a1 = {0.0, 0.0};
-        long long i = tid;
-        // eight independent 128-bit loads in flight per thread
-        for (; i + 7 * nth < npair; i += 8 * nth) {
-            double2 v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = ldg_stream2(g + 2 * (i + j * nth));
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                stream_elem<GRAD, FAST>(v[j].x, a, b, s_tab, a0);
-                stream_elem<GRAD, FAST>(v[j].y, a, b, s_tab, a1);
-            }
-        }
-        for (; i < npair; i += nth) {
-            const double2 v0 = ldg_stream2(g + 2 * i);
-            stream_elem<GRAD, FAST>(v0.x, a, b, s_tab, a0);
-            stream_elem<GRAD, FAST>(v0.y, a, b, s_tab, a1);
-        }
-        if ((cnt[l] & 1) && tid == 0) stream_elem<GRAD, FAST>(g[cnt[l] - 1], a, b, s_tab, a0);
-        obj += a0.obj + a1.obj;
-        gl[l] = a0.g + a1.g;
+template <bool FAST>
+__device__ __forceinline__ void stream_flush(StreamAcc& a0, StreamAcc& a1, const double* s_tab) {
+    if (FAST) {
+        a0.obj += log_pos<FAST>(a0.prod * a1.prod, s_tab);
+        a0.prod = a1.prod = 1.0;
     }
-    for (long long i = tid; i < nd; i += nth) {
-        const double4 r = *reinterpret_cast<const double4*>(D + i);
-        const double w[3] = {r.y, r.z, r.w};
-        const double num = mix_num(r.x);
-#pragma unroll
-        for (int l = 0; l < 3; ++l) {
-            const double M = mix_rel(th, l, r.x);
-            if (GRAD) {
-                double rcp;
-                obj = fma(w[l], fast_log_rcp<FAST>(M, s_tab, rcp), obj);
-                gl[l] = fma(w[l], num * rcp, gl[l]);
-            } else {
-                obj = fma(w[l], fast_log<FAST>(M, s_tab), obj);
-            }
-        }
-    }
-    // dE/d eta = -(2 eps - 1) g_2;  dE/d eps = -(-g_0 + g_1 + (2 eta - 1) g_2)      (fit.py:600-697)
-    double v[3] = {obj, -(2.0 * th.epsilon - 1.0) * gl[2], -(-gl[0] + gl[1] + (2.0 * th.eta - 1.0) * gl[2])};
-    grid_reduce_store<3, kStreamEvalThreads>(v, ws, out);
 }
 
-// The same evaluation with the streams staged through shared memory by the TMA unit:
-// the bytes in flight no longer depend on registers (the register version above
-// stalls on its loads at ~55 % of the HBM peak).  One persistent CTA of 16 warps per
+// The streams are staged through shared memory by the TMA unit: the bytes in flight do not
+// depend on registers (a register-prefetching version stalled on its loads at ~55 % of the HBM peak).  One persistent CTA of 16 warps per
 // SM; the three streams are cut into chunks of kEvChunk doubles, numbered across the
 // streams, and warp g takes the chunks g, g + G, ...; every warp runs a private ring
 // of kEvDepth stages (one 1-D bulk copy and one mbarrier per stage) and refills a
@@ -408,7 +357,6 @@ elm_streams_tma_kernel(const double* __restrict__ G, long long base0, long long 
                        const __grid_constant__ ThetaDev th, const __grid_constant__ LogTabWindow tab,
                        double* __restrict__ out, double* __restrict__ ws) {
     extern __shared__ __align__(128) double s_dyn[];
-    const double* s_tab = load_log_table<FAST>(tab, s_dyn);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* ring = s_dyn + (FAST ? ((tab.n + 15) & ~15) : 0) + (size_t)warp * kEvDepth * kEvChunk;
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_dyn + (FAST ? ((tab.n + 15) & ~15) : 0) +
@@ -417,18 +365,21 @@ elm_streams_tma_kernel(const double* __restrict__ G, long long base0, long long 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
 
-    // chunks are numbered across the streams; a warp's position is (stream l, chunk i of that stream)
-    const long long nq[3] = {(n0 + kEvChunk - 1) / kEvChunk, (n1 + kEvChunk - 1) / kEvChunk,
-                             (n2 + kEvChunk - 1) / kEvChunk};
-    const long long nn[3] = {n0, n1, n2}, bb[3] = {base0, base1, base2};
+    // chunks are numbered across the FOUR streams (G_0, G_1, G_2, then the records as a stream of
+    // 4-double elements); a warp's position is (stream l, chunk i of that stream)
+    const long long n3 = nd * 4;
+    const long long nq0 = (n0 + kEvChunk - 1) / kEvChunk, nq1 = (n1 + kEvChunk - 1) / kEvChunk,
+                    nq2 = (n2 + kEvChunk - 1) / kEvChunk, nq3 = (n3 + kEvChunk - 1) / kEvChunk;
+    const double* const Dd = reinterpret_cast<const double*>(D);
     const long long W = (long long)gridDim.x * kEvWarps;
     struct Pos {
         int l;
         long long i;
     };
+    auto chunks_of = [&](int l) { return l == 0 ? nq0 : (l == 1 ? nq1 : (l == 2 ? nq2 : nq3)); };
     auto normalise = [&](Pos& p) {                           // carry into the next stream(s)
-        while (p.l < 3 && p.i >= (p.l == 0 ? nq[0] : (p.l == 1 ? nq[1] : nq[2]))) {
-            p.i -= (p.l == 0 ? nq[0] : (p.l == 1 ? nq[1] : nq[2]));
+        while (p.l < 4 && p.i >= chunks_of(p.l)) {
+            p.i -= chunks_of(p.l);
             ++p.l;
         }
     };
@@ -436,16 +387,16 @@ elm_streams_tma_kernel(const double* __restrict__ G, long long base0, long long 
     normalise(ip);
     int pd = 0;
     auto issue = [&]() {
-        if (ip.l >= 3) return;
+        if (ip.l >= 4) return;
         if (lane == 0) {
-            const long long n = ip.l == 0 ? nn[0] : (ip.l == 1 ? nn[1] : nn[2]);
-            const long long b = ip.l == 0 ? bb[0] : (ip.l == 1 ? bb[1] : bb[2]);
+            const long long n = ip.l == 0 ? n0 : (ip.l == 1 ? n1 : (ip.l == 2 ? n2 : n3));
+            const double* src = ip.l == 0 ? G + base0 : (ip.l == 1 ? G + base1 : (ip.l == 2 ? G + base2 : Dd));
             const long long left = n - ip.i * kEvChunk;
             const uint32_t cnt = (uint32_t)(left < kEvChunk ? left : kEvChunk);
             const uint32_t bytes = ((cnt + 1) & ~1u) * 8;    // even element count: 16-byte granules
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(bars + pd, bytes);
-            tma_load_1d(ring + pd * kEvChunk, G + b + ip.i * kEvChunk, bytes, bars + pd);
+            tma_load_1d(ring + pd * kEvChunk, src + ip.i * kEvChunk, bytes, bars + pd);
         }
         ip.i += W;
         normalise(ip);
@@ -453,17 +404,32 @@ elm_streams_tma_kernel(const double* __restrict__ G, long long base0, long long 
     };
 #pragma unroll 1
     for (int i = 0; i < kEvDepth; ++i) issue();
+    // the table is staged while the first chunks are in flight (the stream bodies need it only for
+    // the rare product flush)
+    const double* s_tab = load_log_table<FAST>(tab, s_dyn);
 
     double obj = 0.0, gl[3] = {0.0, 0.0, 0.0};
     const double al[3] = {th.al[0], th.al[1], th.al[2]}, bl[3] = {th.bl[0], th.bl[1], th.bl[2]};
+    const long long nn[3] = {n0, n1, n2};
     int d = 0;
     uint32_t phase = 0;
     Pos cp = {0, (long long)blockIdx.x * kEvWarps + warp};
     normalise(cp);
+    auto advance = [&]() {
+        __syncwarp();
+        issue();
+        if (++d == kEvDepth) {
+            d = 0;
+            phase ^= 1;
+        }
+        cp.i += W;
+        normalise(cp);
+    };
 #pragma unroll
     for (int l = 0; l < 3; ++l) {                            // the warp's chunks of stream l: constants in registers
         const double a = al[l], b = bl[l];
-        StreamAcc a0 = {0.0, 0.0}, a1 = {0.0, 0.0};
+        StreamAcc a0 = {0.0, 0.0, 1.0}, a1 = {0.0, 0.0, 1.0};
+        int nf = 0;                                          // factors in each running product
         while (cp.l == l) {
             const long long left = nn[l] - cp.i * kEvChunk;
             mbar_wait(bars + d, phase);
@@ -478,36 +444,45 @@ elm_streams_tma_kernel(const double* __restrict__ G, long long base0, long long 
             } else {
                 for (int e = lane; e < (int)left; e += 32) stream_elem<GRAD, FAST>(st[e], a, b, s_tab, a0);
             }
-            __syncwarp();
-            issue();
-            if (++d == kEvDepth) {
-                d = 0;
-                phase ^= 1;
+            advance();
+            nf += left >= kEvChunk ? kEvChunk / 64 : kEvChunk / 32;      // a tail chunk goes to a0 only
+            if (nf + kEvChunk / 32 > kProdMax) {
+                stream_flush<FAST>(a0, a1, s_tab);
+                nf = 0;
             }
-            cp.i += W;
-            normalise(cp);
         }
+        stream_flush<FAST>(a0, a1, s_tab);
         obj += a0.obj + a1.obj;
         gl[l] = a0.g + a1.g;
     }
-    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const long long nth = (long long)gridDim.x * blockDim.x;
-    for (long long i = tid; i < nd; i += nth) {
-        const double4 r = *reinterpret_cast<const double4*>(D + i);
-        const double w[3] = {r.y, r.z, r.w};
-        const double num = mix_num(r.x);
+    while (cp.l == 3) {                                      // records {p, w_0, w_1, w_2}: real weights, three logs each
+        const long long left = (n3 - cp.i * kEvChunk) >> 2;
+        const int cnt = (int)(left < kEvChunk / 4 ? left : kEvChunk / 4);
+        mbar_wait(bars + d, phase);
+        const double4* st = reinterpret_cast<const double4*>(ring + d * kEvChunk);
 #pragma unroll
-        for (int l = 0; l < 3; ++l) {
-            const double M = mix_rel(th, l, r.x);
-            if (GRAD) {
-                double rcp;
-                obj = fma(w[l], fast_log_rcp<FAST>(M, s_tab, rcp), obj);
-                gl[l] = fma(w[l], num * rcp, gl[l]);
-            } else {
-                obj = fma(w[l], fast_log<FAST>(M, s_tab), obj);
+        for (int j = 0; j < kEvChunk / 128; ++j) {
+            const int e = 32 * j + lane;
+            if (e < cnt) {
+                const double4 r = st[e];
+                const double w[3] = {r.y, r.z, r.w};
+                const double num = mix_num(r.x);
+#pragma unroll
+                for (int l = 0; l < 3; ++l) {
+                    const double M = fma(bl[l], r.x, al[l]);
+                    if (GRAD) {
+                        double rcp;
+                        obj = fma(w[l], fast_log_rcp<FAST>(M, s_tab, rcp), obj);
+                        gl[l] = fma(w[l], num * rcp, gl[l]);
+                    } else {
+                        obj = fma(w[l], fast_log<FAST>(M, s_tab), obj);
+                    }
+                }
             }
         }
+        advance();
     }
+    // dE/d eta = -(2 eps - 1) g_2;  dE/d eps = -(-g_0 + g_1 + (2 eta - 1) g_2)      (fit.py:600-697)
     double v[3] = {obj, -(2.0 * th.epsilon - 1.0) * gl[2], -(-gl[0] + gl[1] + (2.0 * th.eta - 1.0) * gl[2])};
     grid_reduce_store<3, kEvThreads>(v, ws, out);
 }
@@ -588,15 +563,13 @@ int fcd_elm_streams(const double* G, const int64_t* base3_host, const int64_t* c
     const ThetaDev th = make_theta_dev(*theta_host, 0);
     cudaStream_t st = (cudaStream_t)stream;
     LogTabWindow tab;
-    FCD_REQUIRE(log_table_window(th.epsl, th.al, st, tab), "fcd_elm_streams: log table initialisation failed");
+    FCD_REQUIRE(log_table_window(th.epsl, th.al, st, tab, true), "fcd_elm_streams: log table initialisation failed");
     const bool fast = log_table_covers(th.epsl, th.al);
     const size_t tbytes = fast ? (size_t)((tab.n + 15) & ~15) * sizeof(double) : 0;
     const size_t smem = tbytes + (size_t)kEvWarps * kEvDepth * (kEvChunk * 8 + 8);
     const long long chunks = (count3_host[0] + kEvChunk - 1) / kEvChunk + (count3_host[1] + kEvChunk - 1) / kEvChunk +
-                             (count3_host[2] + kEvChunk - 1) / kEvChunk;
+                             (count3_host[2] + kEvChunk - 1) / kEvChunk + (nd * 4 + kEvChunk - 1) / kEvChunk;
     long long grid = (chunks + kEvWarps - 1) / kEvWarps;
-    const long long dgrid = (nd + kEvThreads - 1) / kEvThreads;
-    if (grid < dgrid) grid = dgrid;
     if (grid > sm_count()) grid = sm_count();                // one persistent CTA per SM
     if (grid < 1) grid = 1;
 #define FCD_ES(G_, F_)                                                                                   \
