@@ -52,7 +52,8 @@ SIGNATURES = {
     "fcd_elm_const": (c_int, [_P, c_int64, c_int32, c_int64, _P, _P, _P, _P, c_int64, c_int32, _P, _P, _P, _P]),
     "fcd_bucket_count": (c_int, [_P, _P, c_int64, _P, c_int64, c_int32, _P, _P, _P, _P]),
     "fcd_bucket_blocks": (c_int64, [c_int64]),
-    "fcd_bucket_fill": (c_int, [_P, c_int64, _P, c_int64, c_int32, c_int64, _P, _P, _P, _P, c_int64, c_int32, _P, _P, _P,
+    "fcd_plane_sum": (c_int, [_P, c_int64, c_int32, c_int64, _P, _P, _P]),
+    "fcd_bucket_fill": (c_int, [_P, c_int64, _P, _P, c_int64, c_int32, c_int64, _P, _P, _P, _P, c_int64, c_int32, _P, _P, _P,
                                 POINTER(c_int64), _P, _P, c_int64, _P, _P, _P]),
     "fcd_elm_streams": (c_int, [_P, POINTER(c_int64), POINTER(c_int64), _P, c_int64, POINTER(FcdTheta), c_int32,
                                 _P, _P, _P]),

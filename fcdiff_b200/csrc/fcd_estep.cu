@@ -233,17 +233,34 @@ estep_qF_kernel(const double* __restrict__ S1, const double* __restrict__ S2,
             acc[k] = a;
         }
     };
+    // Row ends: the warp sums are parked in the registers of lane (row mod 32); every 32 rows (and
+    // after the last one) all lanes finish their own row at once -- the normalisation's exp / log
+    // would otherwise occupy the warp's issue slots for ONE active lane per row.
+    double keep[3] = {0.0, 0.0, 0.0};
+    int64_t keep_c = -1;
+    int rows_done = 0;
+    auto finish_rows = [&]() {
+        if (keep_c >= 0) k2_finish(keep_c, keep, __ldg(S1 + keep_c), __ldg(S2 + keep_c), th, lqF, qF);
+        keep_c = -1;
+    };
     auto row_end = [&](int64_t c) {
         if (FAST && nf > 0) flush();
 #pragma unroll
         for (int k = 0; k < 3; ++k) acc[k] = warp_sum(acc[k] + acc1[k]);
-        if (lane == 0) k2_finish(c, acc, S1[c], S2[c], th, lqF, qF);
+        if (lane == (rows_done & 31)) {
+            keep[0] = acc[0];
+            keep[1] = acc[1];
+            keep[2] = acc[2];
+            keep_c = c;
+        }
+        if ((++rows_done & 31) == 0) finish_rows();
         acc[0] = acc[1] = acc[2] = 0.0;
         acc1[0] = acc1[1] = acc1[2] = 0.0;
     };
     stream_tiered<2, kK2Seg, kStreamWarps, true, false>(P, planeStride, C, U, pitchU, nullptr, rstate, pitchS, nm,
                                                         s_stream, depth, live, dload, dcompute,
                                                         [](int64_t, int, int, int, int) {}, row_end);
+    finish_rows();
 }
 
 // ------------------------------------------------------ patient-major copy

@@ -135,25 +135,43 @@ struct Record {
     double p, w0, w1, w2;
 };
 
-// Fills the streams.  G_l starts at G + base[l]; records at D.  out[0] = theta-free part of E_lM.
+// out[0] = sum of the [C][U] plane (pitch pitchU): the L plane's total, once per cache.
+__global__ void __launch_bounds__(kBucketThreads)
+plane_sum_kernel(const double* __restrict__ X, int64_t C, int U, int64_t pitchU, double* __restrict__ out,
+                 double* __restrict__ ws) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nw = (int64_t)gridDim.x * (kBucketThreads / 32);
+    double s0 = 0.0, s1 = 0.0;
+    for (int64_t c = (int64_t)blockIdx.x * (kBucketThreads / 32) + (threadIdx.x >> 5); c < C; c += nw) {
+        const double* row = X + c * pitchU;
+        for (int u = 2 * lane; u < U; u += 64) {             // pitchU even: u + 1 < pitchU
+            const double2 v = ldg_stream2(row + u);
+            s0 += v.x;
+            s1 += u + 1 < U ? v.y : 0.0;
+        }
+    }
+    double vv[1] = {s0 + s1};
+    grid_reduce_store<1, kBucketThreads>(vv, ws, out);
+}
+
+// Fills the streams.  G_l starts at G + base[l]; records at D.  The L plane is not read here: the
+// theta-free part of E_lM over the stream elements is (sum of L over all local elements, once per
+// cache) - (L of the record elements), finished by bucket_records_kernel.
 // Same row blocks as bucket_count_kernel.  Per 64-patient chunk a lane owns the
 // patients 2*lane, 2*lane+1 (128-bit loads); within a chunk the stream order is
 // "all first elements, then all second elements" -- any fixed order will do.
 __global__ void __launch_bounds__(kBucketThreads, 2)
-bucket_fill_kernel(const double* __restrict__ P, int64_t planeStride, const double* __restrict__ L,
+bucket_fill_kernel(const double* __restrict__ P, int64_t planeStride,
                    int64_t C, int U, int64_t pitchU,
                    const double* __restrict__ qF, const uint8_t* __restrict__ fstate,
                    const double* __restrict__ qR, const uint8_t* __restrict__ rstate, int64_t pitchS,
                    const int32_t* __restrict__ nm, const int4* __restrict__ counts,
                    const longlong4* __restrict__ blockoff,
                    long long base0, long long base1, long long base2,
-                   double* __restrict__ G, Record* __restrict__ D, double* __restrict__ out,
-                   double* __restrict__ ws) {
+                   double* __restrict__ G, Record* __restrict__ D) {
     __shared__ longlong4 s_off[kRowBlock];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
-    const double2* qR2 = reinterpret_cast<const double2*>(qR);
-    double cs = 0.0;
     for (int64_t blk = blockIdx.x; blk * kRowBlock < C; blk += gridDim.x) {
         const int64_t cb = blk * kRowBlock;
         __syncthreads();
@@ -188,12 +206,11 @@ bucket_fill_kernel(const double* __restrict__ P, int64_t planeStride, const doub
             if (k == kStateMixedF) {                         // three records per element, tagged with their state
                 for (int u = lane; u < U; u += 32) {
                     const int64_t i = c * pitchU + u;
-                    const double lv = ldg_stream1(L + i);
 #pragma unroll
                     for (int kk = 0; kk < 3; ++kk) {
                         Record rec;
                         rec.p = ldg_stream1(P + kk * planeStride + i);
-                        rec.w0 = lv;
+                        rec.w0 = 0.0;
                         rec.w1 = __hiloint2double((int)c, u);
                         rec.w2 = 1.0 + kk;
                         D[pos[3] + 3 * (int64_t)u + kk] = rec;
@@ -202,23 +219,21 @@ bucket_fill_kernel(const double* __restrict__ P, int64_t planeStride, const doub
                 continue;
             }
             const double* row = P + (int64_t)k * planeStride + c * pitchU;
-            const double* lrow = L + c * pitchU;
             const uint8_t* rn = rstate + (int64_t)n * pitchS;
             const uint8_t* rm = rstate + (int64_t)m * pitchS;
             struct Chunk {
                 uint32_t sn2, sm2;
-                double2 p2, l2;
+                double2 p2;
             };
             auto load = [&](int u0) {
                 Chunk ch;
                 ch.sn2 = ch.sm2 = 0x0404u;
-                ch.p2 = ch.l2 = make_double2(0.0, 0.0);
+                ch.p2 = make_double2(0.0, 0.0);
                 const int u = u0 + 2 * lane;
                 if (u < U) {                                 // pitchU is even: u + 1 < pitchU
                     ch.sn2 = __ldg(reinterpret_cast<const unsigned short*>(rn + u));
                     ch.sm2 = __ldg(reinterpret_cast<const unsigned short*>(rm + u));
                     ch.p2 = ldg_stream2(row + u);
-                    ch.l2 = ldg_stream2(lrow + u);
                 }
                 return ch;
             };
@@ -228,7 +243,7 @@ bucket_fill_kernel(const double* __restrict__ P, int64_t planeStride, const doub
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int code = pair_code((cur.sn2 >> (8 * e)) & 0xff, (cur.sm2 >> (8 * e)) & 0xff);
-                    const double p = e ? cur.p2.y : cur.p2.x, lv = e ? cur.l2.y : cur.l2.x;
+                    const double p = e ? cur.p2.y : cur.p2.x;
                     // every element has exactly one destination: one store per lane
                     const unsigned b0 = __ballot_sync(0xffffffffu, code == 0);
                     const unsigned b1 = __ballot_sync(0xffffffffu, code == 1);
@@ -241,7 +256,7 @@ bucket_fill_kernel(const double* __restrict__ P, int64_t planeStride, const doub
                     if (code == 3) {                         // weights are filled in by bucket_records_kernel
                         Record rec;
                         rec.p = p;
-                        rec.w0 = lv;
+                        rec.w0 = 0.0;
                         rec.w1 = __hiloint2double((int)c, u + e);
                         rec.w2 = 0.0;
                         d3[at] = rec;
@@ -250,7 +265,6 @@ bucket_fill_kernel(const double* __restrict__ P, int64_t planeStride, const doub
                     off1 += __popc(b1);
                     off2 += __popc(b2);
                     off3 += __popc(b3);
-                    cs += code < 3 ? lv : 0.0;
                 }
             };
             // two register sets of two chunks each, loaded in turn (no register rotation:
@@ -267,25 +281,26 @@ bucket_fill_kernel(const double* __restrict__ P, int64_t planeStride, const doub
             }
         }
     }
-    double vv[1] = {cs};
-    grid_reduce_store<1, kBucketThreads>(vv, ws, out);
 }
 
-// Second half of the bucket pass: the records of unpeaked elements of peaked rows
-// were left as {p, L, (c, u)}; one thread per record gathers the two regions'
-// posteriors (massively parallel, nothing on a row walker's critical path),
-// writes {p, w_0, w_1, w_2} and adds its share sum_l w_l L to out[0].
+// Second half of the bucket pass: the records of unpeaked elements were left as {p, -, (c, u), tag};
+// one thread per record gathers the two regions' posteriors and the element's L (massively parallel,
+// nothing on a row walker's critical path), writes {p, w_0, w_1, w_2} and accumulates
+//   out[0] = Lsum - sum_{record elements} L + sum_records (sum_l w_l) L
+// (Lsum = sum of L over all local elements, fcd_plane_sum: the stream elements have weight exactly 1).
 __global__ void __launch_bounds__(kBucketThreads)
-bucket_records_kernel(Record* __restrict__ D, long long nd, const double* __restrict__ qF,
+bucket_records_kernel(Record* __restrict__ D, long long nd, const double* __restrict__ L, int64_t pitchU,
+                      const double* __restrict__ Lsum, const double* __restrict__ qF,
                       const double* __restrict__ qR, int U, const int32_t* __restrict__ nm,
                       double* __restrict__ out, double* __restrict__ ws) {
     const double2* qR2 = reinterpret_cast<const double2*>(qR);
     double cs = 0.0;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nd;
          i += (long long)gridDim.x * blockDim.x) {
-        Record rec = D[i];                                   // {p, L, (c, u), tag}: tag 0 = peaked edge, 1 + k otherwise
+        Record rec = D[i];                                   // {p, -, (c, u), tag}: tag 0 = peaked edge, 1 + k otherwise
         const int c = __double2hiint(rec.w1), u = __double2loint(rec.w1);
         const int tag = (int)rec.w2;
+        const double lv = __ldg(L + (int64_t)c * pitchU + u);
         const int v = __ldg(nm + c);
         double w[3];
         pair_weights(__ldg(qR2 + (int64_t)(v & 0xffff) * U + u), __ldg(qR2 + (int64_t)((v >> 16) & 0xffff) * U + u), w);
@@ -295,14 +310,14 @@ bucket_records_kernel(Record* __restrict__ D, long long nd, const double* __rest
             scale = qf[tag - 1];
             cscale = tag == 1 ? qf[0] + qf[1] + qf[2] : 0.0;  // the element's theta-free term is counted once
         }
-        cs = fma(cscale * (w[0] + w[1] + w[2]), rec.w0, cs);
+        // the element's theta-free term is counted once (tag <= 1), and it leaves the weight-1 sum
+        cs = fma(cscale * (w[0] + w[1] + w[2]) - (tag <= 1 ? 1.0 : 0.0), lv, cs);
         rec.w0 = scale * w[0];
         rec.w1 = scale * w[1];
         rec.w2 = scale * w[2];
         D[i] = rec;
     }
-    // out[0] (left by bucket_fill_kernel) enters the sum once
-    double vv[1] = {cs + ((blockIdx.x == 0 && threadIdx.x == 0) ? out[0] : 0.0)};
+    double vv[1] = {cs + ((blockIdx.x == 0 && threadIdx.x == 0) ? Lsum[0] : 0.0)};
     grid_reduce_store<1, kBucketThreads>(vv, ws, out);
 }
 
@@ -523,12 +538,21 @@ int fcd_bucket_count(const uint8_t* fstate, const uint8_t* rstate, int64_t pitch
 
 int64_t fcd_bucket_blocks(int64_t C) { return (C + kRowBlock - 1) / kRowBlock; }
 
-int fcd_bucket_fill(const double* P, int64_t planeStride, const double* L, int64_t C, int32_t U, int64_t pitchU,
-                    const double* qF, const uint8_t* fstate, const double* qR, const uint8_t* rstate,
+int fcd_plane_sum(const double* X, int64_t C, int32_t U, int64_t pitchU, double* out1, double* ws, void* stream) {
+    FCD_REQUIRE(X != nullptr && out1 != nullptr && ws != nullptr, "fcd_plane_sum: NULL argument");
+    FCD_REQUIRE(C >= 1 && U >= 1 && pitchU >= U && pitchU % 2 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0,
+                "fcd_plane_sum: bad shape (even pitch, 16-byte aligned)");
+    plane_sum_kernel<<<rows_grid(C, kBucketThreads / 32, 8), kBucketThreads, 0, (cudaStream_t)stream>>>(
+        X, C, U, pitchU, out1, ws);
+    return check_launch("fcd_plane_sum");
+}
+
+int fcd_bucket_fill(const double* P, int64_t planeStride, const double* L, const double* Lsum,
+                    int64_t C, int32_t U, int64_t pitchU, const double* qF, const uint8_t* fstate, const double* qR, const uint8_t* rstate,
                     int64_t pitchS, int32_t N, const int32_t* nm, const int32_t* counts, const int64_t* blockoff,
                     const int64_t* base3_host, double* G, double* D, int64_t nd, double* out1, double* ws,
                     void* stream) {
-    FCD_REQUIRE(P != nullptr && L != nullptr && qF != nullptr && fstate != nullptr && qR != nullptr &&
+    FCD_REQUIRE(P != nullptr && L != nullptr && Lsum != nullptr && qF != nullptr && fstate != nullptr && qR != nullptr &&
                 rstate != nullptr && nm != nullptr && counts != nullptr && blockoff != nullptr &&
                 base3_host != nullptr && G != nullptr && D != nullptr && out1 != nullptr && ws != nullptr,
                 "fcd_bucket_fill: NULL argument");
@@ -540,15 +564,16 @@ int fcd_bucket_fill(const double* P, int64_t planeStride, const double* L, int64
     int64_t grid = nblocks;                                  // persistent: the resident CTAs share the row blocks
     if (grid > (int64_t)sm_count() * 2) grid = (int64_t)sm_count() * 2;
     bucket_fill_kernel<<<(unsigned)grid, kBucketThreads, 0, (cudaStream_t)stream>>>(
-        P, planeStride, L, C, U, pitchU, qF, fstate, qR, rstate, pitchS, nm, reinterpret_cast<const int4*>(counts),
+        P, planeStride, C, U, pitchU, qF, fstate, qR, rstate, pitchS, nm, reinterpret_cast<const int4*>(counts),
         reinterpret_cast<const longlong4*>(blockoff) + nblocks, base3_host[0], base3_host[1], base3_host[2], G,
-        reinterpret_cast<Record*>(D), out1, ws);
+        reinterpret_cast<Record*>(D));
     int rc = check_launch("fcd_bucket_fill");
-    if (rc || nd == 0) return rc;
-    int64_t rgrid = (nd + kBucketThreads - 1) / kBucketThreads;
+    if (rc) return rc;
+    int64_t rgrid = (nd + kBucketThreads - 1) / kBucketThreads;       // nd == 0: one CTA writes out1[0] = Lsum
     if (rgrid > (int64_t)sm_count() * 8) rgrid = (int64_t)sm_count() * 8;
+    if (rgrid < 1) rgrid = 1;
     bucket_records_kernel<<<(unsigned)rgrid, kBucketThreads, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<Record*>(D), nd, qF, qR, U, nm, out1, ws);
+        reinterpret_cast<Record*>(D), nd, L, pitchU, Lsum, qF, qR, U, nm, out1, ws);
     return check_launch("fcd_bucket_fill(records)");
 }
 

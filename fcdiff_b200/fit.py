@@ -310,6 +310,7 @@ class UnsharedRegionFit(object):
             _lib.check(lib.fcd_resp_cache(_dev.ptr(inp['bt']), Cl, U, pitchU, ctypes.byref(th),
                                           _dev.ptr(inp['P']), max(Cl, 1) * pitchU, _dev.ptr(inp['L']),
                                           _dev.stream()), "fcd_resp_cache")
+        inp['Lsum'] = None                          # total of the L plane, formed on first use (bucket pass)
         inp['cache_key'] = ckey
         inp['PT'] = None
         self._evals = []
@@ -396,9 +397,14 @@ class UnsharedRegionFit(object):
             inp['bk_D'] = _dev.empty((4 * max(nd, Cl * U // 4, 1),))
         base3 = (ctypes.c_int64 * 3)(*base)
         count3 = (ctypes.c_int64 * 3)(n0, n1, n2)
+        if inp.get('Lsum') is None:
+            inp['Lsum'] = _dev.empty((1,))
+            _lib.check(lib.fcd_plane_sum(_dev.ptr(inp['L']), Cl, U, inp['pitchU'], _dev.ptr(inp['Lsum']),
+                                         _dev.ptr(_dev.workspace()), stream), "fcd_plane_sum")
         with _dev.timed(self.profile, "K3b_bucket_fill"):
             _lib.check(lib.fcd_bucket_fill(
-                _dev.ptr(inp['P']), max(Cl, 1) * inp['pitchU'], _dev.ptr(inp['L']), Cl, U, inp['pitchU'],
+                _dev.ptr(inp['P']), max(Cl, 1) * inp['pitchU'], _dev.ptr(inp['L']), _dev.ptr(inp['Lsum']),
+                Cl, U, inp['pitchU'],
                 _dev.ptr(qF[c0 * 3:]), _dev.ptr(fstate[c0:]), _dev.ptr(qR), _dev.ptr(rstate), rstate.shape[1], N,
                 _dev.ptr(inp['nm']), _dev.ptr(inp['bk_counts']), _dev.ptr(inp['bk_offs']), base3,
                 _dev.ptr(inp['bk_G']), _dev.ptr(inp['bk_D']), nd,

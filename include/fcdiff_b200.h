@@ -205,15 +205,19 @@ FCD_API int fcd_elm_const(const double* L, int64_t C, int32_t U, int64_t pitchU,
  *   fcd_bucket_count: counts[c] = {n_0, n_1, n_2, n_records} (int32 x 4) per row,
  *     blockoff: scratch of 2 * fcd_bucket_blocks(C) x 4 int64 (totals and exclusive
  *     prefix sums of blocks of 16 rows), totals[4] (int64);
+ *   fcd_plane_sum: out1[0] = sum of a [C][U] plane -- the total of the L plane, once per cache;
  *   fcd_bucket_fill: G_l occupies G[base3[l] .. base3[l] + totals[l]) (bases even),
  *     D holds nd = totals[3] records (32 bytes each);  out1[0] = the theta-free part of
- *     E_lM (same value as fcd_elm_const);
+ *     E_lM (same value as fcd_elm_const), formed as Lsum[0] (device, from fcd_plane_sum)
+ *     corrected by the record elements only: the fill never reads the L plane;
  *   fcd_elm_streams: out3 as fcd_elm_obj_grad. */
 FCD_API int64_t fcd_bucket_blocks(int64_t C);
 FCD_API int fcd_bucket_count(const uint8_t* fstate, const uint8_t* rstate, int64_t pitchS, const int32_t* nm,
                      int64_t C, int32_t U, int32_t* counts, int64_t* blockoff, int64_t* totals, void* stream);
-FCD_API int fcd_bucket_fill(const double* P, int64_t planeStride, const double* L, int64_t C, int32_t U, int64_t pitchU,
-                    const double* qF, const uint8_t* fstate, const double* qR, const uint8_t* rstate,
+FCD_API int fcd_plane_sum(const double* X, int64_t C, int32_t U, int64_t pitchU, double* out1, double* ws,
+                  void* stream);
+FCD_API int fcd_bucket_fill(const double* P, int64_t planeStride, const double* L, const double* Lsum,
+                    int64_t C, int32_t U, int64_t pitchU, const double* qF, const uint8_t* fstate, const double* qR, const uint8_t* rstate,
                     int64_t pitchS, int32_t N, const int32_t* nm, const int32_t* counts, const int64_t* blockoff,
                     const int64_t* base3_host, double* G, double* D, int64_t nd, double* out1, double* ws,
                     void* stream);
