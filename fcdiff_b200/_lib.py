@@ -31,6 +31,19 @@ SIGNATURES = {
     "fcd_download": (c_int, [_P, _P, c_int64, _P]),
     "fcd_launch_count": (c_int64, []),
     "fcd_launch_count_reset": (None, []),
+    "fcd_comm_window_bytes": (c_int64, []),
+    "fcd_comm_handle_bytes": (c_int32, []),
+    "fcd_comm_max_world": (c_int32, []),
+    "fcd_comm_max_vals": (c_int32, []),
+    "fcd_comm_window_create": (c_int, [POINTER(c_void_p)]),
+    "fcd_comm_window_destroy": (c_int, [_P]),
+    "fcd_comm_window_export": (c_int, [_P, _P]),
+    "fcd_comm_window_open": (c_int, [_P, POINTER(c_void_p)]),
+    "fcd_comm_window_close": (c_int, [_P]),
+    "fcd_host_result_alloc": (c_int, [POINTER(c_void_p)]),
+    "fcd_host_result_free": (c_int, [_P]),
+    "fcd_allreduce_small": (c_int, [_P, c_int32, POINTER(c_void_p), c_int32, c_int32, c_uint64, _P, _P]),
+    "fcd_wait_result": (c_int, [_P, c_int32, c_uint64, _P, c_int32]),
     "fcd_c_to_nm": (c_int, [c_int64, c_int64, _P, _P, _P]),
     "fcd_healthy_stats": (c_int, [_P, c_int64, c_int32, c_int64, _P, _P, _P]),
     "fcd_edge_table": (c_int, [c_int64, c_int64, _P, _P]),

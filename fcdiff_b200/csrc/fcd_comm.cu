@@ -1,0 +1,227 @@
+// One-shot all-reduce of a few doubles over NVLink peer memory.
+//
+// The sharded fit exchanges, per M-step / objective evaluation / energy, <= 8
+// doubles of edge-local partial sums (fcdiff/fit.py:208-220, 270-286, 142-155
+// become sums over edge shards).  Such an exchange is pure latency: through NCCL
+// plus a device-to-host copy it costs ~0.1-0.25 ms at 8 GPUs, more than the
+// evaluation kernel it follows.  Here every rank owns a small *window* in its
+// device memory, exported to the other ranks of the box by CUDA IPC; ONE kernel
+// (one CTA) per exchange
+//   1. stores the rank's partial sums into its slot of EVERY rank's window
+//      (peer stores over NVLink / NVSwitch), fences, and raises its flag there;
+//   2. waits until the flags of all ranks have arrived in its own window;
+//   3. adds the slots in rank order (every rank forms bit-identical sums, so the
+//      host-side optimisers of all ranks take identical steps), writes the result
+//      back to the device vector and to MAPPED pinned host memory, and raises a host
+//      flag the CPU spins on -- no cudaMemcpy, no stream synchronisation.
+// Two slot sets (sequence parity) make back-to-back exchanges safe: a rank can be
+// at most one exchange ahead of the slowest one.  With world == 1 the kernel is
+// just the device -> mapped-host publication of a reduction result.
+#include <chrono>
+#include <cstring>
+
+#include "fcd_common.cuh"
+
+namespace fcd {
+
+constexpr int kCommMaxWorld = 16;
+constexpr int kCommMaxVals = 8;
+
+struct CommWindow {
+    double slot[2][kCommMaxWorld][kCommMaxVals];
+    unsigned long long flag[2][kCommMaxWorld];
+};
+
+struct CommPeers {
+    CommWindow* w[kCommMaxWorld];
+};
+
+constexpr unsigned long long kCommTimeoutBit = 1ull << 63;
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(double* p, double v) {
+    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// result_host: [kCommMaxVals] doubles followed by one 64-bit flag (= seq, or seq | timeout bit)
+__global__ void __launch_bounds__(kCommMaxWorld* kCommMaxVals)
+allreduce_small_kernel(double* __restrict__ vec, int n, const __grid_constant__ CommPeers peers, int rank, int world,
+                       unsigned long long seq, double* __restrict__ result_host, long long spin_cycles) {
+    __shared__ int s_timeout;
+    const int t = threadIdx.x;
+    const int par = (int)(seq & 1ull);
+    if (t == 0) s_timeout = 0;
+    __syncthreads();
+    if (world > 1) {
+        if (t < world * n) {                                  // 1. my partial sums into every rank's window
+            const int p = t / n, i = t - p * n;
+            st_relaxed_sys(&peers.w[p]->slot[par][rank][i], vec[i]);
+            __threadfence_system();
+        }
+        __syncthreads();
+        if (t < world) {
+            st_release_sys(&peers.w[t]->flag[par][rank], seq);
+            const unsigned long long* f = &peers.w[rank]->flag[par][t];       // 2. everybody's flag in my window
+            const long long t0 = clock64();
+            while (ld_acquire_sys(f) != seq) {
+                if (clock64() - t0 > spin_cycles) {
+                    s_timeout = 1;
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (t < n) {                                              // 3. sum in rank order, publish
+        double s = 0.0;
+        if (world > 1) {
+            for (int r = 0; r < world; ++r) s += ld_relaxed_sys(&peers.w[rank]->slot[par][r][t]);
+            vec[t] = s;
+        } else {
+            s = vec[t];
+        }
+        st_relaxed_sys(result_host + t, s);
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (t == 0)
+        st_release_sys(reinterpret_cast<unsigned long long*>(result_host + kCommMaxVals),
+                       s_timeout ? (seq | kCommTimeoutBit) : seq);
+}
+
+}  // namespace fcd
+
+using namespace fcd;
+
+extern "C" {
+
+int64_t fcd_comm_window_bytes(void) { return (int64_t)sizeof(CommWindow); }
+int32_t fcd_comm_handle_bytes(void) { return (int32_t)sizeof(cudaIpcMemHandle_t); }
+int32_t fcd_comm_max_world(void) { return kCommMaxWorld; }
+int32_t fcd_comm_max_vals(void) { return kCommMaxVals; }
+
+#define FCD_CUDA(call, what)                                                   \
+    do {                                                                       \
+        cudaError_t e_ = (call);                                               \
+        if (e_ != cudaSuccess) {                                               \
+            ::fcd::set_error("%s: %s", what, cudaGetErrorString(e_));          \
+            return -2;                                                         \
+        }                                                                      \
+    } while (0)
+
+int fcd_comm_window_create(void** window_out_host) {
+    FCD_REQUIRE(window_out_host != nullptr, "fcd_comm_window_create: NULL argument");
+    void* p = nullptr;
+    FCD_CUDA(cudaMalloc(&p, sizeof(CommWindow)), "fcd_comm_window_create(cudaMalloc)");
+    FCD_CUDA(cudaMemset(p, 0, sizeof(CommWindow)), "fcd_comm_window_create(cudaMemset)");
+    FCD_CUDA(cudaDeviceSynchronize(), "fcd_comm_window_create(sync)");
+    *window_out_host = p;
+    return 0;
+}
+
+int fcd_comm_window_destroy(void* window) {
+    if (window != nullptr) FCD_CUDA(cudaFree(window), "fcd_comm_window_destroy");
+    return 0;
+}
+
+int fcd_comm_window_export(void* window, void* handle_host) {
+    FCD_REQUIRE(window != nullptr && handle_host != nullptr, "fcd_comm_window_export: NULL argument");
+    cudaIpcMemHandle_t h;
+    FCD_CUDA(cudaIpcGetMemHandle(&h, window), "fcd_comm_window_export(cudaIpcGetMemHandle)");
+    memcpy(handle_host, &h, sizeof(h));
+    return 0;
+}
+
+int fcd_comm_window_open(const void* handle_host, void** peer_window_out_host) {
+    FCD_REQUIRE(handle_host != nullptr && peer_window_out_host != nullptr, "fcd_comm_window_open: NULL argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle_host, sizeof(h));
+    void* p = nullptr;
+    FCD_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "fcd_comm_window_open(cudaIpcOpenMemHandle)");
+    *peer_window_out_host = p;
+    return 0;
+}
+
+int fcd_comm_window_close(void* peer_window) {
+    if (peer_window != nullptr) FCD_CUDA(cudaIpcCloseMemHandle(peer_window), "fcd_comm_window_close");
+    return 0;
+}
+
+/* Mapped pinned host memory for results ([fcd_comm_max_vals()] doubles + one 64-bit flag), zero-filled. */
+int fcd_host_result_alloc(void** result_out_host) {
+    FCD_REQUIRE(result_out_host != nullptr, "fcd_host_result_alloc: NULL argument");
+    void* p = nullptr;
+    const size_t bytes = (kCommMaxVals + 1) * sizeof(double);
+    FCD_CUDA(cudaHostAlloc(&p, bytes, cudaHostAllocMapped | cudaHostAllocPortable), "fcd_host_result_alloc");
+    memset(p, 0, bytes);
+    *result_out_host = p;
+    return 0;
+}
+
+int fcd_host_result_free(void* result_host) {
+    if (result_host != nullptr) FCD_CUDA(cudaFreeHost(result_host), "fcd_host_result_free");
+    return 0;
+}
+
+int fcd_allreduce_small(double* vec, int32_t n, void* const* windows_host, int32_t rank, int32_t world,
+                        uint64_t seq, double* result_host, void* stream) {
+    FCD_REQUIRE(vec != nullptr && result_host != nullptr, "fcd_allreduce_small: NULL argument");
+    FCD_REQUIRE(n >= 1 && n <= kCommMaxVals && world >= 1 && world <= kCommMaxWorld && rank >= 0 && rank < world &&
+                seq >= 1 && (seq & kCommTimeoutBit) == 0, "fcd_allreduce_small: bad shape");
+    CommPeers peers;
+    memset(&peers, 0, sizeof(peers));
+    if (world > 1) {
+        FCD_REQUIRE(windows_host != nullptr, "fcd_allreduce_small: NULL windows");
+        for (int r = 0; r < world; ++r) {
+            FCD_REQUIRE(windows_host[r] != nullptr, "fcd_allreduce_small: NULL window");
+            peers.w[r] = static_cast<CommWindow*>(windows_host[r]);
+        }
+    }
+    double* result_dev = nullptr;
+    FCD_CUDA(cudaHostGetDevicePointer((void**)&result_dev, result_host, 0), "fcd_allreduce_small(cudaHostGetDevicePointer)");
+    const long long spin_cycles = 20000000000ll;              // ~10 s at 2 GHz: a lost peer must not hang the GPU
+    allreduce_small_kernel<<<1, kCommMaxWorld * kCommMaxVals, 0, (cudaStream_t)stream>>>(
+        vec, n, peers, rank, world, (unsigned long long)seq, result_dev, spin_cycles);
+    return check_launch("fcd_allreduce_small");
+}
+
+/* Spins until the kernel of exchange `seq` has published its result; copies n doubles to out_host. */
+int fcd_wait_result(const double* result_host, int32_t n, uint64_t seq, double* out_host, int32_t timeout_ms) {
+    FCD_REQUIRE(result_host != nullptr && out_host != nullptr && n >= 1 && n <= kCommMaxVals,
+                "fcd_wait_result: bad argument");
+    const volatile unsigned long long* flag =
+        reinterpret_cast<const volatile unsigned long long*>(result_host + kCommMaxVals);
+    const auto t0 = std::chrono::steady_clock::now();
+    unsigned long long f;
+    long long spins = 0;
+    while (((f = *flag) & ~kCommTimeoutBit) != seq) {
+        if ((++spins & 0xfff) == 0) {
+            const auto dt = std::chrono::steady_clock::now() - t0;
+            if (std::chrono::duration_cast<std::chrono::milliseconds>(dt).count() > timeout_ms) {
+                cudaError_t e = cudaGetLastError();
+                set_error("fcd_wait_result: no result for exchange %llu after %d ms (%s)", (unsigned long long)seq,
+                          timeout_ms, cudaGetErrorString(e));
+                return -3;
+            }
+        }
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    FCD_REQUIRE((f & kCommTimeoutBit) == 0, "fcd_wait_result: a peer rank did not arrive (device-side timeout)");
+    const volatile double* r = result_host;
+    for (int i = 0; i < n; ++i) out_host[i] = r[i];
+    return 0;
+}
+
+}  // extern "C"

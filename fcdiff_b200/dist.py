@@ -11,7 +11,11 @@ iteration:
 
 * all-gather of ``lq_F`` / ``q_F`` (24*C bytes each) after K2,
 * all-gather of ``lq_R`` / ``q_R`` (16*N*U bytes each) after K2b,
-* all-reduce (sum) of <= 6 doubles after K3a, per K3b evaluation and after K4.
+* all-reduce (sum) of <= 6 doubles after K3a, per K3b evaluation and after K4:
+  on GPUs a one-shot exchange over NVLink peer memory whose result lands in
+  mapped host memory (:class:`PeerWindow`, csrc/fcd_comm.cu) -- these exchanges
+  are pure latency, and NCCL + a download per call cost more than the kernels
+  they follow; NCCL / gloo otherwise.
 
 The reference has no distributed code; the sharded fit must equal the
 single-device fit up to the order of the fp64 partial sums.
@@ -22,6 +26,78 @@ import torch.distributed as dist
 
 def _ceil_div(a, b):
     return (a + b - 1) // b
+
+
+class PeerWindow(object):
+    """All-reduce of <= 8 doubles over NVLink peer memory, delivered to the host
+    (``fcd_allreduce_small`` / ``fcd_wait_result``).  Every rank creates a window
+    in its device memory; the CUDA IPC handles travel once through the process
+    group; afterwards an exchange is one kernel launch and a host-side spin on
+    mapped pinned memory.  ``world == 1`` (no group) publishes reduction results
+    to the host the same way."""
+
+    TIMEOUT_MS = 30000
+
+    def __init__(self, group=None, rank=0, world=1):
+        import ctypes
+        import numpy as np
+        from . import _lib
+        self._ct = ctypes
+        self.lib = _lib.load()
+        self._check = _lib.check
+        (self.rank, self.world) = (int(rank), int(world))
+        self.max_vals = int(self.lib.fcd_comm_max_vals())
+        if self.world > int(self.lib.fcd_comm_max_world()):
+            raise ValueError("PeerWindow: world size %d exceeds %d" % (self.world, self.lib.fcd_comm_max_world()))
+        self.seq = 0
+        self._opened = []
+        self._own = ctypes.c_void_p(0)
+        self.windows = (ctypes.c_void_p * max(self.world, 1))()
+        if self.world > 1:
+            self._check(self.lib.fcd_comm_window_create(ctypes.byref(self._own)), "fcd_comm_window_create")
+            hb = int(self.lib.fcd_comm_handle_bytes())
+            handle = ctypes.create_string_buffer(hb)
+            self._check(self.lib.fcd_comm_window_export(self._own, handle), "fcd_comm_window_export")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            for r in range(self.world):
+                if r == self.rank:
+                    self.windows[r] = self._own
+                    continue
+                peer = ctypes.c_void_p(0)
+                buf = ctypes.create_string_buffer(handles[r], hb)
+                self._check(self.lib.fcd_comm_window_open(buf, ctypes.byref(peer)), "fcd_comm_window_open")
+                self._opened.append(peer)
+                self.windows[r] = peer
+            dist.barrier(group=group)              # every window is open everywhere before the first exchange
+        self._result = ctypes.c_void_p(0)
+        self._check(self.lib.fcd_host_result_alloc(ctypes.byref(self._result)), "fcd_host_result_alloc")
+        self._out = np.zeros(self.max_vals, dtype=np.float64)
+        self._out_p = ctypes.c_void_p(self._out.ctypes.data)
+
+    def allreduce(self, vec_dev, n, stream):
+        """Sums ``vec_dev[:n]`` (device, float64) over the ranks in place and returns
+        the sums as a fresh host array."""
+        self.seq += 1
+        rc = self.lib.fcd_allreduce_small(self._ct.c_void_p(vec_dev.data_ptr()), n, self.windows, self.rank,
+                                          self.world, self.seq, self._result, stream)
+        if rc != 0:
+            self._check(rc, "fcd_allreduce_small")
+        rc = self.lib.fcd_wait_result(self._result, n, self.seq, self._out_p, self.TIMEOUT_MS)
+        if rc != 0:
+            self._check(rc, "fcd_wait_result")
+        return self._out[:n].copy()
+
+    def close(self):
+        for p in self._opened:
+            self.lib.fcd_comm_window_close(p)
+        self._opened = []
+        if self._own:
+            self.lib.fcd_comm_window_destroy(self._own)
+            self._own = self._ct.c_void_p(0)
+        if self._result:
+            self.lib.fcd_host_result_free(self._result)
+            self._result = self._ct.c_void_p(0)
 
 
 class EdgeShards(object):
@@ -35,6 +111,28 @@ class EdgeShards(object):
             world = dist.get_world_size(group)
         self.rank = int(rank)
         self.world = int(world)
+        self._peer = None             # PeerWindow, created on first use (NCCL groups on CUDA only)
+        self._peer_tried = False
+
+    def peer_window(self):
+        """The NVLink peer window of this group, or None (gloo / CPU groups)."""
+        if not self._peer_tried:
+            self._peer_tried = True
+            if torch.cuda.is_available() and dist.is_initialized() and dist.get_backend(self.group) == "nccl":
+                self._peer = PeerWindow(self.group, self.rank, self.world)
+        return self._peer
+
+    def reduce_read(self, res, n=None, stream=None):
+        """Sums the device vector ``res.dev`` (a ``_dev.SmallResult``) over the ranks in
+        place and returns the sums on the host: one peer-memory exchange, or an
+        all-reduce + download where no peer window exists."""
+        n = res.dev.numel() if n is None else n
+        pw = self.peer_window()
+        if pw is not None and n <= pw.max_vals:
+            from . import _dev
+            return pw.allreduce(res.dev, n, _dev.stream() if stream is None else stream)
+        dist.all_reduce(res.dev, op=dist.ReduceOp.SUM, group=self.group)
+        return res.read(stream)
 
     def key(self):
         return (self.rank, self.world)
@@ -67,6 +165,13 @@ class EdgeShards(object):
     def any_rank(self, flag):
         """True on every rank if ``flag`` is true on any rank (one tiny all-reduce):
         used where the ranks must agree on a code path whose collectives differ."""
+        pw = self.peer_window()
+        if pw is not None:
+            from . import _dev
+            if getattr(self, "_flag_vec", None) is None:
+                self._flag_vec = _dev.zeros((1,))
+            self._flag_vec.fill_(1.0 if flag else 0.0)
+            return bool(pw.allreduce(self._flag_vec, 1, _dev.stream())[0] > 0)
         dev = "cuda" if (torch.cuda.is_available() and dist.get_backend(self.group) == "nccl") else "cpu"
         t = torch.tensor([1.0 if flag else 0.0], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)

@@ -574,8 +574,7 @@ class UnsharedRegionFit(object):
                 _dev.ptr(lqR), _dev.ptr(qR), N, U, ctypes.byref(th), ev['elm'] if first else 0.0,
                 _dev.ptr(out), _dev.ptr(_dev.workspace()), _dev.stream()), "fcd_energy_terms")
         if self.shards is not None:
-            self.shards.allreduce_terms(out, (0, 1, 3, 4))
-            return self.shards.fix_replicated(res.read(), (0, 1, 3, 4))
+            return self.shards.fix_replicated(self.shards.reduce_read(res), (0, 1, 3, 4))
         return res.read()
 
     def _update_lq_F(self):
@@ -735,10 +734,10 @@ class UnsharedRegionFit(object):
             _lib.check(lib.fcd_mstep_stats(_dev.ptr(lqF), Cl, _dev.ptr(lqR), NU, _dev.ptr(out),
                                            _dev.ptr(_dev.workspace()), _dev.stream()), "fcd_mstep_stats")
         if do_gamma and self.shards is not None and self._in is not None:
-            self.shards.allreduce_terms(out, (0, 1, 2))
+            red = self.shards.reduce_read(res)
             if between is not None:
                 between()
-            return self.shards.fix_replicated(res.read(), (0, 1, 2)), C, NU
+            return self.shards.fix_replicated(red, (0, 1, 2)), C, NU
         if between is not None:
             between()
         return res.read(), C, NU
@@ -821,9 +820,8 @@ class UnsharedRegionFit(object):
                 _dev.ptr(inp['L']), Cl, U, inp['pitchU'], _dev.ptr(qF[c0 * 3:]), _dev.ptr(fstate[c0:]),
                 _dev.ptr(qR), _dev.ptr(rstate), rstate.shape[1], N, _dev.ptr(inp['nm']),
                 _dev.ptr(res.dev), _dev.ptr(_dev.workspace()), _dev.stream()), "fcd_elm_const")
-        if self.shards is not None:
-            self.shards.allreduce_terms(res.dev, (0,))
-        self._const = (ckey, float(res.read()[0]))
+        val = res.read() if self.shards is None else self.shards.reduce_read(res)
+        self._const = (ckey, float(val[0]))
         return self._const[1]
 
     def _objective_context(self):
@@ -873,8 +871,9 @@ class UnsharedRegionFit(object):
             _lib.check(rc, ctx['name'])
         res = ctx['res']
         if self.shards is not None:
-            self.shards.allreduce_terms(res.dev, (0, 1, 2, 3))        # all four are edge-local partial sums
-        o = res.read(ctx['stream'])
+            o = self.shards.reduce_read(res, 4, ctx['stream'])        # all four are edge-local partial sums
+        else:
+            o = res.read(ctx['stream'])
         if ctx['const'] is None and self.shards is not None:
             # the theta-free part sits in slot 3 and was summed over ranks together with the rest:
             # keep the global value and zero the slot so that later all-reduces do not add it again
@@ -907,8 +906,7 @@ class UnsharedRegionFit(object):
         timed = self.profile
         shards = self.shards
         if shards is not None:
-            import torch.distributed as dist
-            (all_reduce, group, dev_vec) = (dist.all_reduce, shards.group, res.dev)
+            (reduce_read, dev_vec) = (shards.reduce_read, res.dev)
 
         def fun(x):
             th.eta = float(x[0])
@@ -921,8 +919,9 @@ class UnsharedRegionFit(object):
             if rc != 0:
                 _lib.check(rc, name)
             if shards is not None:
-                all_reduce(dev_vec, group=group)              # all four slots are edge-local partial sums
-            o = read(stream)
+                o = reduce_read(res, 4, stream)               # all four slots are edge-local partial sums
+            else:
+                o = read(stream)
             const = ctx['const']
             if const is None:
                 const = float(o[3])

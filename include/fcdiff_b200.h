@@ -66,6 +66,38 @@ FCD_API int fcd_download(void* dst_host, const void* src, int64_t bytes, void* s
 FCD_API int64_t fcd_launch_count(void);
 FCD_API void fcd_launch_count_reset(void);
 
+/* ------------------------------------------------------- small exchanges    */
+/* One-shot all-reduce (sum) of n <= fcd_comm_max_vals() doubles over NVLink peer
+ * memory, result delivered to the host without a copy or a stream synchronisation
+ * (csrc/fcd_comm.cu).  Replaces, for the edge-sharded fit, the NCCL all-reduce +
+ * download after every reduction kernel: the M-step sums (fcdiff/fit.py:208-220),
+ * the objective / gradient partial sums of every (eta, epsilon) evaluation
+ * (fit.py:270-286) and the energy terms (fit.py:142-155).
+ *   window: fcd_comm_window_bytes() of device memory per rank, created here (the one
+ *     explicit allocation of this library), exported / opened as a CUDA IPC handle of
+ *     fcd_comm_handle_bytes() bytes; windows_host[world] lists every rank's window in
+ *     THIS process' address space (own window at [rank]);
+ *   result_host: mapped pinned memory from fcd_host_result_alloc;
+ *   seq: 1, 2, 3, ... -- the same on every rank for the same exchange;
+ *   fcd_allreduce_small launches one kernel on `stream`: vec (device, in place) and
+ *     result_host receive the sums, formed in rank order (bit-identical on all ranks);
+ *     world == 1 publishes vec to the host only;
+ *   fcd_wait_result spins until exchange seq has been published, copies n doubles. */
+FCD_API int64_t fcd_comm_window_bytes(void);
+FCD_API int32_t fcd_comm_handle_bytes(void);
+FCD_API int32_t fcd_comm_max_world(void);
+FCD_API int32_t fcd_comm_max_vals(void);
+FCD_API int fcd_comm_window_create(void** window_out_host);
+FCD_API int fcd_comm_window_destroy(void* window);
+FCD_API int fcd_comm_window_export(void* window, void* handle_host);
+FCD_API int fcd_comm_window_open(const void* handle_host, void** peer_window_out_host);
+FCD_API int fcd_comm_window_close(void* peer_window);
+FCD_API int fcd_host_result_alloc(void** result_out_host);
+FCD_API int fcd_host_result_free(void* result_host);
+FCD_API int fcd_allreduce_small(double* vec, int32_t n, void* const* windows_host, int32_t rank, int32_t world,
+                        uint64_t seq, double* result_host, void* stream);
+FCD_API int fcd_wait_result(const double* result_host, int32_t n, uint64_t seq, double* out_host, int32_t timeout_ms);
+
 /* ------------------------------------------------------- index arithmetic   */
 /* fcdiff/util.py:62-84 c_to_nm for c in [c0, c0+C): n_out[i], m_out[i] int32. */
 FCD_API int fcd_c_to_nm(int64_t c0, int64_t C, int32_t* n_out, int32_t* m_out, void* stream);
