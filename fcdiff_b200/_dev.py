@@ -31,6 +31,17 @@ def stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_side = {}
+
+
+def side_stream():
+    """Per-device side stream for host -> device uploads that overlap the main stream's kernels."""
+    key = device().index
+    if key not in _side:
+        _side[key] = torch.cuda.Stream(device=device())
+    return _side[key]
+
+
 def ptr(t):
     """Device address of a torch tensor (None -> NULL)."""
     if t is None:

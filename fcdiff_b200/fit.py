@@ -59,20 +59,30 @@ class _Mirror(object):
 
     def __init__(self):
         self.host = None
+        self.fill = None     # (shape, value) of a constant array not yet materialised
         self.dev = None      # (lq, q) device tensors, flat
         self.state = None    # peak-state bytes of q (fstate / rstate, include/fcdiff_b200.h)
         self.version = 0
 
     def set_host(self, a):
         self.host = a
+        self.fill = None
         self.dev = None
         self.state = None
         self.version += 1
+
+    def set_fill(self, shape, value):
+        """A constant array (the uniform start of fit.py:84-102): formed on the device by a fill,
+        on the host only if somebody reads it -- no host-to-device copy queues behind the inputs."""
+        self.set_host(None)
+        self.fill = (tuple(shape), float(value))
+        self.shape = tuple(shape)
 
     def set_dev(self, lq, q, shape):
         self.dev = (lq, q)
         self.shape = shape
         self.host = None
+        self.fill = None
         self.state = None
         self.version += 1
 
@@ -96,11 +106,18 @@ class _Mirror(object):
         return self.state
 
     def get_host(self):
+        if self.host is None and self.fill is not None:
+            self.host = np.full(self.fill[0], self.fill[1])
         if self.host is None and self.dev is not None:
             self.host = _dev.download(self.dev[0]).reshape(self.shape)
         return self.host
 
     def get_dev(self):
+        if self.dev is None and self.host is None and self.fill is not None:
+            (shape, value) = self.fill
+            n = int(np.prod(shape))
+            self.dev = (torch.full((n,), value, dtype=torch.float64, device=_dev.device()),
+                        torch.full((n,), float(np.exp(np.float64(value))), dtype=torch.float64, device=_dev.device()))
         if self.dev is None:
             if self.host is None:
                 raise ValueError("log-probabilities have not been initialized (call _init_lps)")
@@ -182,6 +199,7 @@ class UnsharedRegionFit(object):
         self.reuse_evaluations = True
         self._res = {}                # reusable device / pinned-host result vectors
         self._ctx = None              # cached argument list of the K3b evaluations
+        self._keep_host = None        # host arrays an asynchronous upload is still reading
 
     # ------------------------------------------------------------------ private arrays
     @property
@@ -275,22 +293,58 @@ class UnsharedRegionFit(object):
                 bt_dev = _dev.zeros((Cl, pitchU))
                 bt_dev[:, :U].copy_(bt_src)
             assert b_dev.shape[0] == Cl and bt_dev.shape[0] == Cl, "edge shard has the wrong number of rows"
+            ev_S = None
         else:
-            b_dev = _dev.upload(np.asarray(self.b)[c0:c0 + Cl])
-            bt_dev = _dev.upload_rows(np.asarray(self.bt)[c0:c0 + Cl], pitchU)
-        S1 = _dev.empty((Cl,))
-        S2 = _dev.empty((Cl,))
-        with _dev.timed(self.profile, "K0_healthy_stats"):
-            _lib.check(lib.fcd_healthy_stats(_dev.ptr(b_dev), Cl, H, H, _dev.ptr(S1), _dev.ptr(S2),
-                                             _dev.stream()), "fcd_healthy_stats")
-        del b_dev
+            # Host arrays: the patient correlations go first, on a side stream; the controls and their
+            # sufficient statistics follow there, while the main stream already builds the planes
+            # and evaluates the initial E_lM from bt alone.  The first consumer of S1 / S2 waits for
+            # them (_wait_healthy).  Buffers are allocated on the main stream: freeing stays simple.
+            (b_h, bt_h) = (np.ascontiguousarray(np.asarray(self.b)[c0:c0 + Cl], dtype=np.float64),
+                           np.ascontiguousarray(np.asarray(self.bt)[c0:c0 + Cl], dtype=np.float64))
+            (b_t, bt_t) = (torch.from_numpy(b_h), torch.from_numpy(bt_h))
+            b_dev = _dev.empty((Cl, H))
+            bt_dev = _dev.empty((Cl, pitchU)) if pitchU == U else _dev.zeros((Cl, pitchU))
+            S1 = _dev.empty((Cl,))
+            S2 = _dev.empty((Cl,))
+            (cur, side) = (torch.cuda.current_stream(), _dev.side_stream())
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                (bt_dev if pitchU == U else bt_dev[:, :U]).copy_(bt_t, non_blocking=bt_t.is_pinned())
+                ev_bt = torch.cuda.Event()
+                ev_bt.record(side)
+                b_dev.copy_(b_t, non_blocking=b_t.is_pinned())
+                if Cl > 0:
+                    _lib.check(lib.fcd_healthy_stats(_dev.ptr(b_dev), Cl, H, H, _dev.ptr(S1), _dev.ptr(S2),
+                                                     _dev.stream()), "fcd_healthy_stats")
+                ev_S = torch.cuda.Event()
+                ev_S.record(side)
+            cur.wait_event(ev_bt)
+            self._keep_host = (b_t, bt_t)      # the asynchronous copies read these until ev_S
+        if ev_S is None:
+            S1 = _dev.empty((Cl,))
+            S2 = _dev.empty((Cl,))
+            with _dev.timed(self.profile, "K0_healthy_stats"):
+                _lib.check(lib.fcd_healthy_stats(_dev.ptr(b_dev), Cl, H, H, _dev.ptr(S1), _dev.ptr(S2),
+                                                 _dev.stream()), "fcd_healthy_stats")
+            del b_dev
         nm = _dev.empty((max(Cl, 1),), torch.int32)
         _lib.check(lib.fcd_edge_table(c0, Cl, _dev.ptr(nm), _dev.stream()), "fcd_edge_table")
         self._in = dict(key=key, C=C, H=H, U=U, c0=c0, Cl=Cl, u0=u0, Ul=Ul, pitchU=pitchU,
-                        bt=bt_dev, S1=S1, S2=S2, nm=nm, cache_key=None, P=None, L=None, PT=None, WT=None)
+                        bt=bt_dev, S1=S1, S2=S2, nm=nm, cache_key=None, P=None, L=None, PT=None, WT=None,
+                        ev_S=ev_S, b_dev=(b_dev if ev_S is not None else None))
         self._evals = []
         self._const = None
         return self._in
+
+    def _wait_healthy(self, inp):
+        """Before the first kernel that reads S1 / S2: the main stream joins the side stream that
+        uploaded the controls and reduced them (host-array inputs)."""
+        ev = inp.get('ev_S')
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+            inp['ev_S'] = None
+            inp['b_dev'] = None
+            self._keep_host = None
 
     def _ensure_cache(self):
         """Responsibility planes P[3] / L of the local edge rows for the
@@ -459,6 +513,10 @@ class UnsharedRegionFit(object):
 
         self._init_lps(N, H, U)
         self._update_lps()
+        if self._in is not None and self._in.get('ev_S') is not None:
+            # host inputs still uploading: everything that needs the patient correlations only
+            # (planes, patient-major planes of the region sweep) is enqueued under the upload
+            self._ensure_patient_major()
 
         self.energy = [self._eval_energy()]
         self.n_objective_evals = []
@@ -477,8 +535,8 @@ class UnsharedRegionFit(object):
         """
         C = util.N_to_C(N)
         self._dims = (N, H, U)
-        self._mR.set_host(np.full((N, U, 2), -np.log(2)))
-        self._mF.set_host(np.full((C, 1, 3), -np.log(3)))
+        self._mR.set_fill((N, U, 2), -np.log(2))
+        self._mF.set_fill((C, 1, 3), -np.log(3))
         self._lps_state = 'ones'
         self._explicit = {}
         self._mat = None
@@ -566,6 +624,7 @@ class UnsharedRegionFit(object):
         th = self._theta()
         res = self._result(6)
         out = res.dev
+        self._wait_healthy(inp)
         # the global E_lM is known: rank 0 contributes it, the others zero
         first = self.shards is None or self.shards.rank == 0
         with _dev.timed(self.profile, "K4_energy_small"):
@@ -606,6 +665,7 @@ class UnsharedRegionFit(object):
         lqF = _dev.empty((C * 3,))
         qF = _dev.empty((C * 3,))
         th = self._theta()
+        self._wait_healthy(inp)
         with _dev.timed(self.profile, "K2_estep_qF"):
             _lib.check(lib.fcd_estep_qF(
                 _dev.ptr(inp['S1']), _dev.ptr(inp['S2']), H, _dev.ptr(inp['P']), max(Cl, 1) * inp['pitchU'],
@@ -764,6 +824,7 @@ class UnsharedRegionFit(object):
         th = self._theta(use_snapshot=False)
         (th.mu[:], th.sigma[:]) = (list(self._theta_lps[0]), list(self._theta_lps[1]))   # the planes' (mu, sigma)
         res = self._result(18)
+        self._wait_healthy(inp)
         with _dev.timed(self.profile, "K3c_state_moments"):
             _lib.check(lib.fcd_state_moments(
                 _dev.ptr(inp['S1']), _dev.ptr(inp['S2']), H, _dev.ptr(inp['bt']), _dev.ptr(inp['P']),
