@@ -44,6 +44,8 @@ SIGNATURES = {
     "fcd_host_result_free": (c_int, [_P]),
     "fcd_allreduce_small": (c_int, [_P, c_int32, POINTER(c_void_p), c_int32, c_int32, c_uint64, _P, _P]),
     "fcd_wait_result": (c_int, [_P, c_int32, c_uint64, _P, c_int32]),
+    "fcd_pack_patients": (c_int, [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P]),
+    "fcd_unpack_patients": (c_int, [_P, c_int32, c_int32, c_int32, c_int32, _P, _P, _P]),
     "fcd_c_to_nm": (c_int, [c_int64, c_int64, _P, _P, _P]),
     "fcd_healthy_stats": (c_int, [_P, c_int64, c_int32, c_int64, _P, _P, _P]),
     "fcd_edge_table": (c_int, [c_int64, c_int64, _P, _P]),

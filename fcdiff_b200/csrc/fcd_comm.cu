@@ -101,6 +101,38 @@ allreduce_small_kernel(double* __restrict__ vec, int n, const __grid_constant__ 
                        s_timeout ? (seq | kCommTimeoutBit) : seq);
 }
 
+// Staging of the patient all-gather: the region posteriors are (N, U, 2) arrays and a
+// rank owns the patient columns [u0, u0 + Ul): not contiguous.  pack: both arrays' own columns into
+// one contiguous block [2][N][ch][2] (ch = columns per rank, zero padded); unpack: the gathered
+// [world][2][N][ch][2] back into the two (N, U, 2) arrays.  One launch each instead of a chain of
+// strided tensor copies.
+__global__ void __launch_bounds__(256)
+pack_patients_kernel(const double2* __restrict__ a, const double2* __restrict__ b, int N, int U, int u0, int Ul, int ch,
+                     double2* __restrict__ out) {
+    const int64_t total = 2ll * N * ch;
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int j = (int)(i % ch);
+        const int64_t r = i / ch;
+        const int n = (int)(r % N), w = (int)(r / N);
+        double2 v = make_double2(0.0, 0.0);
+        if (j < Ul) v = (w ? b : a)[(int64_t)n * U + u0 + j];
+        out[i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+unpack_patients_kernel(const double2* __restrict__ g, int world, int N, int U, int ch, double2* __restrict__ a,
+                       double2* __restrict__ b) {
+    const int64_t total = 2ll * N * U;
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int u = (int)(i % U);
+        const int64_t r = i / U;
+        const int n = (int)(r % N), w = (int)(r / N);
+        const int rk = u / ch, j = u - rk * ch;
+        (w ? b : a)[(int64_t)n * U + u] = g[(((int64_t)rk * 2 + w) * N + n) * ch + j];
+    }
+}
+
 }  // namespace fcd
 
 using namespace fcd;
@@ -195,6 +227,31 @@ int fcd_allreduce_small(double* vec, int32_t n, void* const* windows_host, int32
     allreduce_small_kernel<<<1, kCommMaxWorld * kCommMaxVals, 0, (cudaStream_t)stream>>>(
         vec, n, peers, rank, world, (unsigned long long)seq, result_dev, spin_cycles);
     return check_launch("fcd_allreduce_small");
+}
+
+int fcd_pack_patients(const double* lqR, const double* qR, int32_t N, int32_t U, int32_t u0, int32_t Ul, int32_t ch,
+                      double* out, void* stream) {
+    FCD_REQUIRE(lqR != nullptr && qR != nullptr && out != nullptr, "fcd_pack_patients: NULL argument");
+    FCD_REQUIRE(N >= 1 && U >= 1 && ch >= 1 && u0 >= 0 && Ul >= 0 && Ul <= ch && u0 + Ul <= U,
+                "fcd_pack_patients: bad shape");
+    int64_t grid = (2ll * N * ch + 255) / 256;
+    if (grid > 4ll * sm_count()) grid = 4ll * sm_count();
+    pack_patients_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const double2*>(lqR), reinterpret_cast<const double2*>(qR), N, U, u0, Ul, ch,
+        reinterpret_cast<double2*>(out));
+    return check_launch("fcd_pack_patients");
+}
+
+int fcd_unpack_patients(const double* gathered, int32_t world, int32_t N, int32_t U, int32_t ch, double* lqR,
+                        double* qR, void* stream) {
+    FCD_REQUIRE(gathered != nullptr && lqR != nullptr && qR != nullptr, "fcd_unpack_patients: NULL argument");
+    FCD_REQUIRE(world >= 1 && N >= 1 && U >= 1 && ch >= 1 && (int64_t)world * ch >= U, "fcd_unpack_patients: bad shape");
+    int64_t grid = (2ll * N * U + 255) / 256;
+    if (grid > 4ll * sm_count()) grid = 4ll * sm_count();
+    unpack_patients_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const double2*>(gathered), world, N, U, ch, reinterpret_cast<double2*>(lqR),
+        reinterpret_cast<double2*>(qR));
+    return check_launch("fcd_unpack_patients");
 }
 
 /* Spins until the kernel of exchange `seq` has published its result; copies n doubles to out_host. */

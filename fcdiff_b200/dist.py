@@ -185,24 +185,49 @@ class EdgeShards(object):
                 host_vec[i] = host_vec[i] / self.world
         return host_vec
 
+    def edge_buffer_len(self, C):
+        """Length of a flat [C*3] edge array padded so that every rank's rows are an equal-sized
+        chunk: the all-gather then runs in place on the array itself."""
+        return self.world * self.chunk(C, self.world) * 3
+
     def allgather_edges(self, lqF, qF, C):
-        """lqF, qF: flat [C*3]; this rank's edge rows are valid on entry, all rows on
-        exit.  One collective for both arrays."""
+        """lqF, qF: flat [C*3] (or padded to ``edge_buffer_len(C)``: gathered in place, no
+        staging copies); this rank's edge rows are valid on entry, all rows on exit."""
         ch = self.chunk(C, self.world)
         (start, length) = self.span(C)
+        if lqF.numel() >= self.world * ch * 3 and qF.numel() >= self.world * ch * 3 and lqF.is_cuda:
+            for t in (lqF, qF):
+                full = t[:self.world * ch * 3]
+                dist.all_gather_into_tensor(full, full[self.rank * ch * 3:(self.rank + 1) * ch * 3], group=self.group)
+            return
         local = lqF.new_zeros((2, ch * 3))
         local[0, :length * 3].copy_(lqF[start * 3:(start + length) * 3])
         local[1, :length * 3].copy_(qF[start * 3:(start + length) * 3])
         gathered = lqF.new_empty((self.world, 2, ch * 3))
         dist.all_gather_into_tensor(gathered.view(-1), local.view(-1), group=self.group)
-        lqF.copy_(gathered[:, 0].reshape(-1)[:C * 3])
-        qF.copy_(gathered[:, 1].reshape(-1)[:C * 3])
+        lqF[:C * 3].copy_(gathered[:, 0].reshape(-1)[:C * 3])
+        qF[:C * 3].copy_(gathered[:, 1].reshape(-1)[:C * 3])
 
     def allgather_patients(self, lqR, qR, N, U):
         """lqR, qR: flat [N*U*2]; this rank's patient columns are valid on entry, all
-        columns on exit.  One collective for both arrays."""
+        columns on exit.  One collective for both arrays; on the GPU the staging is one
+        pack and one unpack kernel over reused buffers."""
         ch = self.chunk(U, self.world)
         (u0, Ul) = self.span(U)
+        if lqR.is_cuda:
+            from . import _dev, _lib
+            lib = _lib.load()
+            key = (N, ch, lqR.device)
+            if getattr(self, "_stage_key", None) != key:
+                self._stage = (lqR.new_empty((2 * N * ch * 2,)), lqR.new_empty((self.world * 2 * N * ch * 2,)))
+                self._stage_key = key
+            (local, gathered) = self._stage
+            _lib.check(lib.fcd_pack_patients(_dev.ptr(lqR), _dev.ptr(qR), N, U, u0, Ul, ch, _dev.ptr(local),
+                                             _dev.stream()), "fcd_pack_patients")
+            dist.all_gather_into_tensor(gathered, local, group=self.group)
+            _lib.check(lib.fcd_unpack_patients(_dev.ptr(gathered), self.world, N, U, ch, _dev.ptr(lqR), _dev.ptr(qR),
+                                               _dev.stream()), "fcd_unpack_patients")
+            return
         local = lqR.new_zeros((2, N, ch, 2))
         local[0, :, :Ul].copy_(lqR.view(N, U, 2)[:, u0:u0 + Ul])
         local[1, :, :Ul].copy_(qR.view(N, U, 2)[:, u0:u0 + Ul])

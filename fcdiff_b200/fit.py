@@ -662,8 +662,9 @@ class UnsharedRegionFit(object):
         (C, c0, Cl) = (inp['C'], inp['c0'], inp['Cl'])
         (lqR, qR) = self._mR.get_dev()
         rstate = self._mR.get_state()
-        lqF = _dev.empty((C * 3,))
-        qF = _dev.empty((C * 3,))
+        nbuf = C * 3 if self.shards is None else self.shards.edge_buffer_len(C)   # padded: gathered in place
+        (lqF_buf, qF_buf) = (_dev.empty((nbuf,)), _dev.empty((nbuf,)))
+        (lqF, qF) = (lqF_buf[:C * 3], qF_buf[:C * 3])
         th = self._theta()
         self._wait_healthy(inp)
         with _dev.timed(self.profile, "K2_estep_qF"):
@@ -672,7 +673,7 @@ class UnsharedRegionFit(object):
                 Cl, U, inp['pitchU'], _dev.ptr(qR), _dev.ptr(rstate), rstate.shape[1], N, _dev.ptr(inp['nm']),
                 ctypes.byref(th), _dev.ptr(lqF[c0 * 3:]), _dev.ptr(qF[c0 * 3:]), _dev.stream()), "fcd_estep_qF")
         if self.shards is not None:
-            self.shards.allgather_edges(lqF, qF, C)
+            self.shards.allgather_edges(lqF_buf, qF_buf, C)
         self._mF.set_dev(lqF, qF, (C, 1, 3))
 
     def _update_lq_R(self):

@@ -97,6 +97,14 @@ FCD_API int fcd_host_result_free(void* result_host);
 FCD_API int fcd_allreduce_small(double* vec, int32_t n, void* const* windows_host, int32_t rank, int32_t world,
                         uint64_t seq, double* result_host, void* stream);
 FCD_API int fcd_wait_result(const double* result_host, int32_t n, uint64_t seq, double* out_host, int32_t timeout_ms);
+/* Staging of the all-gather of the region posteriors `_lq_R` / exp(_lq_R) ((N, U, 2), fcdiff/fit.py:176-198)
+ * when patients are sharded: pack this rank's columns [u0, u0+Ul) of both arrays into one
+ * contiguous block [2][N][ch][2] (ch columns per rank, zero padded); unpack the gathered
+ * [world][2][N][ch][2] into the two full arrays. */
+FCD_API int fcd_pack_patients(const double* lqR, const double* qR, int32_t N, int32_t U, int32_t u0, int32_t Ul,
+                      int32_t ch, double* out, void* stream);
+FCD_API int fcd_unpack_patients(const double* gathered, int32_t world, int32_t N, int32_t U, int32_t ch, double* lqR,
+                        double* qR, void* stream);
 
 /* ------------------------------------------------------- index arithmetic   */
 /* fcdiff/util.py:62-84 c_to_nm for c in [c0, c0+C): n_out[i], m_out[i] int32. */
