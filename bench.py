@@ -119,8 +119,8 @@ def algorithmic_bytes(kernel, C, N, H, U):
     kernel actually reads them in."""
     return {
         "K2_estep_qF": 8 * C * U + 16 * C + 48 * C + 16 * N * U,        # bt, S1/S2, lqF+qF out, qR
-        "K2b_region_weights": 8 * C * U + 24 * C + 24 * C * U,          # btT, qF, WT out
-        "K2b_sweep": 24 * C * U + 16 * N * U + 32 * N * U,              # WT once (window overlaps hit L1/L2), qR in, qR/lqR out
+        "K2b_region_weights": 8 * C * U + 24 * C + 16 * C * U,          # btT, qF, WT out (two weight differences)
+        "K2b_sweep": 16 * C * U + 16 * N * U + 32 * N * U,              # WT once (window overlaps hit L1/L2), qR in, qR/lqR out
         "K2b_sweep_fused": 8 * C * U + 24 * C + 48 * N * U,             # btT once, qF, qR in / out
         "K3b_elm_obj_grad": 8 * C * U + 24 * C + 16 * N * U,            # bt, qF, qR
         "K3b_elm_streams": 8 * C * U + 24 * C + 16 * N * U,             # the same evaluation from the bucketed streams

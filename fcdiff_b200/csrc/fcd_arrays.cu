@@ -121,7 +121,8 @@ lqF_from_arrays_kernel(const double* __restrict__ lpB, const double* __restrict_
     }
 }
 
-// WT[u][c][l] = sum_k qF[c,k] lM[c,u,k,l]  (fcdiff/fit.py:187-194, q_R-independent part)
+// W_l = sum_k qF[c,k] lM[c,u,k,l]  (fcdiff/fit.py:187-194, q_R-independent part);
+// WT[u][c] = {W_0 - W_2, W_2 - W_1}: what survives the normalisation of fit.py:196 (fcd_estep.cu, K2b/W)
 __global__ void __launch_bounds__(kArrThreads)
 region_weights_from_lM_kernel(const double* __restrict__ lM, int64_t C, int U,
                               const double* __restrict__ qF, double* __restrict__ WT) {
@@ -132,9 +133,10 @@ region_weights_from_lM_kernel(const double* __restrict__ lM, int64_t C, int U,
         const int u = (int)(i - c * U);
         const double* lm = lM + i * 9;
         const double q0 = qF[c * 3], q1 = qF[c * 3 + 1], q2 = qF[c * 3 + 2];
-        double* out = WT + ((int64_t)u * C + c) * 3;
+        double w[3];
 #pragma unroll
-        for (int l = 0; l < 3; ++l) out[l] = fma(q2, lm[6 + l], fma(q1, lm[3 + l], q0 * lm[l]));
+        for (int l = 0; l < 3; ++l) w[l] = fma(q2, lm[6 + l], fma(q1, lm[3 + l], q0 * lm[l]));
+        reinterpret_cast<double2*>(WT)[(int64_t)u * C + c] = make_double2(w[0] - w[2], w[2] - w[1]);
     }
 }
 

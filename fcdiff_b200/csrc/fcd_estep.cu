@@ -314,10 +314,15 @@ pstar_commit_kernel(const uint8_t* __restrict__ fstate, int64_t C, uint8_t* __re
 }
 
 // ------------------------------------------------------------------- K2b/W
-// WT[u][c][l] = sum_k qF[c,k] log(a_l + b_l p_k(c,u)) from the patient-major
+// W_l[c,u] = sum_k qF[c,k] log(a_l + b_l p_k(c,u)) from the patient-major
 // responsibility planes PT[k][u][c].  The omitted per-(c,u) constant L sum_k qF[c,k]
 // is the same for l = 0, 1, 2 and enters both states of fcdiff/fit.py:190,194
 // multiplied by (q_R[m,u,0] + q_R[m,u,1]), so it cancels at fit.py:196.
+// Only the DIFFERENCE of the two region states' sums survives the normalisation of
+// fit.py:196-197 (lq = l - logsumexp(l) is a function of l_0 - l_1), and
+//   l_0 - l_1 = log(pi_0 / pi_1) + sum_m q_R[m,0] (W_0 - W_2) + q_R[m,1] (W_2 - W_1),
+// so the tensor holds two numbers per edge-patient: WT[u][c] = {W_0 - W_2, W_2 - W_1}
+// (16 bytes written here and read by the sweep instead of 24).
 // Edges whose q_F is peaked (fstate < 3) need the plane of k* only: 3 logs.
 template <bool FAST>
 __global__ void __launch_bounds__(256)
@@ -337,7 +342,7 @@ region_weights_kernel(const double* __restrict__ PT, int64_t planeStride,
         const int u = (int)(t / tiles_per_row);
         const int64_t cbase = (t - (int64_t)u * tiles_per_row) * 1024;
         const double* row = PT + (int64_t)u * pitchC;
-        double* out = WT + (int64_t)u * C * 3;
+        double2* out = reinterpret_cast<double2*>(WT) + (int64_t)u * C;
         double pk[4];
         int ks[4];
 #pragma unroll
@@ -369,9 +374,7 @@ region_weights_kernel(const double* __restrict__ PT, int64_t planeStride,
                     for (int l = 0; l < 3; ++l) w[l] = fma(q[k], fast_log<FAST>(mix_rel(th, l, p), s_tab), w[l]);
                 }
             }
-            out[c * 3] = w[0];
-            out[c * 3 + 1] = w[1];
-            out[c * 3 + 2] = w[2];
+            out[c] = make_double2(w[0] - w[2], w[2] - w[1]);
         }
     }
 }
@@ -391,11 +394,11 @@ sweep_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int u0,
              double lp0, double lp1,
              double* __restrict__ qR, double* __restrict__ lqR) {
     constexpr int NW = T / 32;
-    __shared__ double s_red[2][NW][2];
+    __shared__ double s_red[2][NW];
     const int ul = blockIdx.x;
     const int u = u0 + ul;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const double* Wu = WT + (int64_t)ul * C * 3;
+    const double2* Wu = reinterpret_cast<const double2*>(WT) + (int64_t)ul * C;     // {W_0 - W_2, W_2 - W_1}
     double q0[MPT], q1[MPT];
 #pragma unroll
     for (int j = 0; j < MPT; ++j) {
@@ -406,72 +409,57 @@ sweep_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int u0,
             q1[j] = qR[((int64_t)m * U + u) * 2 + 1];
         }
     }
-    // reference lookup: the window of step n starts at Wu + 3 n(n-1)/2 and moves by 3n doubles per
+    // reference lookup: the window of step n starts at edge n(n-1)/2 and moves by n edges per
     // step (fit.py:185-186): one running pointer, no index arithmetic per edge
-    const double* win = Wu + 3 * tid;                 // window of the next load_w call (n_next), thread's first edge
+    const double2* win = Wu + tid;                    // window of the next load_w call (n_next), thread's first edge
     int n_next = 0;
-    auto load_w = [&](int n, double (&dst)[MPT][3]) {
+    auto load_w = [&](int n, double2 (&dst)[MPT]) {
         if (LOOKUP == FCD_LOOKUP_REFERENCE) {         // load_w is called with n = 0, 1, 2, ... in order
 #pragma unroll
             for (int j = 0; j < MPT; ++j) {
                 const int m = tid + j * T;
-                dst[j][0] = dst[j][1] = dst[j][2] = 0.0;
-                if (m < N && m != n && n < N) {
-                    const double* p = win + 3 * j * T;
-                    dst[j][0] = __ldg(p);
-                    dst[j][1] = __ldg(p + 1);
-                    dst[j][2] = __ldg(p + 2);
-                }
+                dst[j] = make_double2(0.0, 0.0);
+                if (m < N && m != n && n < N) dst[j] = __ldg(win + j * T);
             }
-            win += 3 * n_next;                        // base(n + 1) - base(n) = n
+            win += n_next;                            // base(n + 1) - base(n) = n
             ++n_next;
         } else {
             const int64_t base = (int64_t)n * (n - 1) / 2;
 #pragma unroll
             for (int j = 0; j < MPT; ++j) {
                 const int m = tid + j * T;
-                dst[j][0] = dst[j][1] = dst[j][2] = 0.0;
+                dst[j] = make_double2(0.0, 0.0);
                 if (m < N && m != n && n < N) {
                     const int64_t c = m < n ? base + m : (int64_t)m * (m - 1) / 2 + n;
-                    dst[j][0] = __ldg(Wu + c * 3);
-                    dst[j][1] = __ldg(Wu + c * 3 + 1);
-                    dst[j][2] = __ldg(Wu + c * 3 + 2);
+                    dst[j] = __ldg(Wu + c);
                 }
             }
         }
     };
+    const double dlp = lp0 - lp1;
     // One Gauss-Seidel step with the window `w`; the window of step n + 2 is requested
     // into `far` first (the loads do not depend on q_R), so that every window has two
     // steps to arrive.  The three register sets take turns (steps are unrolled by
     // three): no set is ever copied, a copy would wait for its loads.
-    auto step = [&](int n, const double (&w)[MPT][3], double (&far)[MPT][3]) {
+    auto step = [&](int n, const double2 (&w)[MPT], double2 (&far)[MPT]) {
         load_w(n + 2, far);
-        double s0 = 0.0, s1 = 0.0;
+        double sd = 0.0;
 #pragma unroll
-        for (int j = 0; j < MPT; ++j) {               // zero weights for m == n / m >= N
-            s0 += fma(q0[j], w[j][0], q1[j] * w[j][2]);       // fit.py:188-190
-            s1 += fma(q1[j], w[j][1], q0[j] * w[j][2]);       // fit.py:192-194
-        }
-        s0 = warp_sum(s0);
-        s1 = warp_sum(s1);
-        if (lane == 0) {
-            s_red[n & 1][warp][0] = s0;
-            s_red[n & 1][warp][1] = s1;
-        }
+        for (int j = 0; j < MPT; ++j)                 // zero weights for m == n / m >= N
+            sd += fma(q0[j], w[j].x, q1[j] * w[j].y);          // (fit.py:188-190) - (fit.py:192-194)
+        sd = warp_sum(sd);
+        if (lane == 0) s_red[n & 1][warp] = sd;
         __syncthreads();
         if (tid == n % T) {                           // owner of region n
-            double a = 0.0, b = 0.0;
+            double a = 0.0;
 #pragma unroll
-            for (int i = 0; i < NW; ++i) {
-                a += s_red[n & 1][i][0];
-                b += s_red[n & 1][i][1];
-            }
+            for (int i = 0; i < NW; ++i) a += s_red[n & 1][i];
             // lq = l - logsumexp(l), q = exp(lq) (fit.py:196-197) with one exponential:
-            // with d = -|l0 - l1| and t = exp(d):  lse = max + log1p(t),
+            // with D = l_0 - l_1, d = -|D| and t = exp(d):  lse = max + log1p(t),
             // q_max = 1 / (1 + t), q_min = t / (1 + t).
-            const double l0r = lp0 + a, l1r = lp1 + b;
-            const bool first = l0r >= l1r;
-            const double d = first ? l1r - l0r : l0r - l1r;
+            const double D = dlp + a;
+            const bool first = D >= 0.0;
+            const double d = first ? -D : D;
             const double t = exp_nonpos(d);
             // most regions are decided: below 2^-54, log1p(t) = t and 1/(1+t) = 1 to rounding
             // (skips the two long dependent chains of the step's critical path)
@@ -492,13 +480,11 @@ sweep_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int u0,
                     q1[j] = p1;
                 }
             const int64_t o = ((int64_t)n * U + u) * 2;
-            lqR[o] = l0;
-            lqR[o + 1] = l1;
-            qR[o] = p0;
-            qR[o + 1] = p1;
+            *reinterpret_cast<double2*>(lqR + o) = make_double2(l0, l1);
+            *reinterpret_cast<double2*>(qR + o) = make_double2(p0, p1);
         }
     };
-    double wa[MPT][3], wb[MPT][3], wc[MPT][3];
+    double2 wa[MPT], wb[MPT], wc[MPT];
     load_w(0, wa);
     load_w(1, wb);
     for (int n = 0; n < N; n += 3) {

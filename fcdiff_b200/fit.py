@@ -690,7 +690,7 @@ class UnsharedRegionFit(object):
             (lqF, qF) = self._mF.get_dev()
             (lqR, qR) = self._mR.get_dev()
             N = self._mR.shape[0]
-            WT = _dev.empty((U, C, 3))
+            WT = _dev.empty((U, C, 2))
             _lib.check(lib.fcd_region_weights_from_lM(keep.up(lM), C, U, _dev.ptr(qF),
                                                       _dev.ptr(WT), _dev.stream()),
                        "fcd_region_weights_from_lM")
@@ -724,7 +724,7 @@ class UnsharedRegionFit(object):
                     _dev.stream()), "fcd_estep_qR_fused")
         else:
             if inp['WT'] is None:
-                inp['WT'] = _dev.empty((Ul, C, 3))
+                inp['WT'] = _dev.empty((Ul, C, 2))
             with _dev.timed(self.profile, "K2b_region_weights"):
                 _lib.check(lib.fcd_region_weights(_dev.ptr(PT), max(Ul, 1) * pitchC, Ul, C, pitchC,
                                                   _dev.ptr(qF), _dev.ptr(fstate), _dev.ptr(inp['PsT']),

@@ -166,10 +166,13 @@ FCD_API int fcd_transpose_patients(const double* bt, int64_t C, int32_t U, int64
                            int32_t u0, int32_t Ul, double* btT, int64_t pitchC, void* stream);
 
 /* K2b part 1 -- q_R-independent half of `_update_lq_R` (fcdiff/fit.py:187-194):
- *   WT[u][c][l] = sum_k qF[c,k] * log M_kl(bt[c][u])   (patient-major; PT[k][u][c] are the
- *   patient-major copies [Ul][pitchC] of the responsibility planes)
+ *   W_l[c,u] = sum_k qF[c,k] * log M_kl(bt[c][u])   (PT[k][u][c] are the patient-major
+ *   copies [Ul][pitchC] of the responsibility planes)
  * up to an additive per-(c,u) constant common to all l, which cancels in the
- * normalisation of fit.py:196. qF / fstate cover ALL edges.
+ * normalisation of fit.py:196.  Only l_0 - l_1 survives that
+ * normalisation, so the tensor holds two numbers per edge-patient (16 bytes):
+ *   WT[u][c] = { W_0 - W_2, W_2 - W_1 }     ([Ul][C][2], patient-major)
+ * qF / fstate cover ALL edges.
  * PsT / kcache (both or neither): caller-kept [Ul][pitchC] plane of each edge's
  * dominant-state responsibility and the [C] states it was gathered for (255 =
  * never; set by the caller once); the call refreshes the columns of edges whose
@@ -179,7 +182,7 @@ FCD_API int fcd_region_weights(const double* PT, int64_t planeStride, int32_t Ul
                        const fcd_theta* theta_host, double* WT, void* stream);
 
 /* K2b part 2 -- Gauss-Seidel sweep of `_update_lq_R` (fcdiff/fit.py:176-198)
- * for the patients [u0, u0+Ul).  qR/lqR are the full [N][U][2] arrays; only
+ * for the patients [u0, u0+Ul) from WT [Ul][C][2] (fcd_region_weights).  qR/lqR are the full [N][U][2] arrays; only
  * the [u0, u0+Ul) columns are read and written.  log_pi2_host = {log(1-pi),
  * log(pi)} (the 2-vector convention of test_fcdiff/test_fit.py:477-487).
  * edge_lookup: FCD_LOOKUP_REFERENCE reproduces nm_to_c(n, m) for all m != n
@@ -312,7 +315,8 @@ FCD_API int fcd_lqF_from_arrays(const double* lpB, const double* lM, int64_t C, 
                         const double* qR, int32_t N, const double* log_gamma_host,
                         double* lqF, void* stream);
 
-/* W for `_update_lq_R` from a materialised lM: WT[u][c][l] = sum_k qF[c,k] lM[c,u,k,l]. */
+/* W for `_update_lq_R` from a materialised lM: W_l = sum_k qF[c,k] lM[c,u,k,l], stored as
+ * WT[u][c] = { W_0 - W_2, W_2 - W_1 } ([U][C][2], the layout fcd_estep_qR reads). */
 FCD_API int fcd_region_weights_from_lM(const double* lM, int64_t C, int32_t U, const double* qF,
                                double* WT, void* stream);
 
