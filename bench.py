@@ -123,9 +123,9 @@ def algorithmic_bytes(kernel, C, N, H, U):
         "K2b_sweep": 16 * C * U + 16 * N * U + 32 * N * U,              # WT once (window overlaps hit L1/L2), qR in, qR/lqR out
         "K2b_sweep_fused": 8 * C * U + 24 * C + 48 * N * U,             # btT once, qF, qR in / out
         "K3b_elm_obj_grad": 8 * C * U + 24 * C + 16 * N * U,            # bt, qF, qR
-        "K3b_elm_streams": 8 * C * U + 24 * C + 16 * N * U,             # the same evaluation from the bucketed streams
+        "K3b_elm_streams": 8 * C * U + 24 * C + 16 * N * U,             # the same evaluation from the coded plane
         "K3b_elm_const": 8 * C * U + 24 * C + 16 * N * U,
-        "K3b_bucket_fill": 16 * C * U + 8 * C * U + 24 * C + 16 * N * U,   # p and log-density planes in, streams out
+        "K3b_code_plane": C * U + 16 * N * U,                           # one code byte per edge-patient out, q_R states in
         "K4_elm": 8 * C * U + 24 * C + 16 * N * U,
         "K3a_mstep_stats": 24 * C + 16 * N * U,
     }.get(kernel)

@@ -65,13 +65,12 @@ SIGNATURES = {
     "fcd_elm_obj_grad": (c_int, [_P, c_int64, c_int64, c_int32, c_int64, _P, _P, _P, _P, c_int64, c_int32, _P,
                                  POINTER(FcdTheta), c_int32, _P, _P, _P]),
     "fcd_elm_const": (c_int, [_P, c_int64, c_int32, c_int64, _P, _P, _P, _P, c_int64, c_int32, _P, _P, _P, _P]),
-    "fcd_bucket_count": (c_int, [_P, _P, c_int64, _P, c_int64, c_int32, _P, _P, _P, _P]),
     "fcd_bucket_blocks": (c_int64, [c_int64]),
     "fcd_plane_sum": (c_int, [_P, c_int64, c_int32, c_int64, _P, _P, _P]),
-    "fcd_bucket_fill": (c_int, [_P, c_int64, _P, _P, c_int64, c_int32, c_int64, _P, _P, _P, _P, c_int64, c_int32, _P, _P, _P,
-                                POINTER(c_int64), _P, _P, c_int64, _P, _P, _P]),
-    "fcd_elm_streams": (c_int, [_P, POINTER(c_int64), POINTER(c_int64), _P, c_int64, POINTER(FcdTheta), c_int32,
-                                _P, _P, _P]),
+    "fcd_code_plane": (c_int, [_P, c_int64, c_int64, c_int32, c_int64, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "fcd_code_records": (c_int, [_P, c_int64, _P, _P, _P, _P, c_int64, c_int32, c_int64, _P, _P, _P, c_int32, _P,
+                                 _P, _P, _P, c_int64, _P, _P, _P]),
+    "fcd_elm_coded": (c_int, [_P, _P, c_int64, _P, c_int64, POINTER(FcdTheta), c_int32, _P, _P, _P]),
     "fcd_energy_terms": (c_int, [_P, _P, c_int32, _P, _P, c_int64, _P, _P, c_int32, c_int32,
                                  POINTER(FcdTheta), c_double, _P, _P, _P]),
     "fcd_state_moments": (c_int, [_P, _P, c_int32, _P, _P, c_int64, c_int64, c_int32, c_int64, _P, _P, c_int32, _P,

@@ -364,7 +364,8 @@ class UnsharedRegionFit(object):
             _lib.check(lib.fcd_resp_cache(_dev.ptr(inp['bt']), Cl, U, pitchU, ctypes.byref(th),
                                           _dev.ptr(inp['P']), max(Cl, 1) * pitchU, _dev.ptr(inp['L']),
                                           _dev.stream()), "fcd_resp_cache")
-        inp['Lsum'] = None                          # total of the L plane, formed on first use (bucket pass)
+        inp['Lsum'] = None                          # total of the L plane, formed on first use (code pass)
+        inp['PsE'] = None                           # dominant-state plane of the code pass: rebuilt with the planes
         inp['cache_key'] = ckey
         inp['PT'] = None
         self._evals = []
@@ -411,16 +412,15 @@ class UnsharedRegionFit(object):
         return self._res[key]
 
     def _build_streams(self, inp, res4):
-        """Bucket pass (csrc/fcd_streams.cu): the planes of the local edge rows
-        become three streams of responsibilities plus weighted records for the
-        current (q_F, q_R); the theta-free part of E_lM lands in res4.dev[3].
-        Returns the argument head for ``fcd_elm_streams`` or None when the
-        tiered kernel should be used instead."""
+        """Code pass (csrc/fcd_streams.cu): dominant-state plane + one code byte per
+        element + weighted records for the current (q_F, q_R); the theta-free part
+        of E_lM lands in res4.dev[3].  Returns the argument head for
+        ``fcd_elm_coded`` or None when the tiered kernel should be used instead."""
         if self.elm_path == "tiered":
             return None
         lib = _lib.load()
         (N, H, U) = self._dims
-        (c0, Cl) = (inp['c0'], inp['Cl'])
+        (c0, Cl, pitchU) = (inp['c0'], inp['Cl'], inp['pitchU'])
         if Cl == 0:
             if self.shards is not None and self.elm_path != "tiered":
                 self.shards.any_rank(True)     # keep the collective sequence of _build_streams aligned
@@ -429,41 +429,39 @@ class UnsharedRegionFit(object):
         (_, qR) = self._mR.get_dev()
         (fstate, rstate) = (self._mF.get_state(), self._mR.get_state())
         stream = _dev.stream()
-        if inp.get('bk_counts') is None:
-            inp['bk_counts'] = _dev.empty((Cl, 4), torch.int32)
-            inp['bk_offs'] = _dev.empty((2 * int(lib.fcd_bucket_blocks(Cl)), 4), torch.int64)
-        tot = self._result(4, torch.int64, "totals")
-        with _dev.timed(self.profile, "K3b_bucket_count"):
-            _lib.check(lib.fcd_bucket_count(_dev.ptr(fstate[c0:]), _dev.ptr(rstate), rstate.shape[1],
-                                            _dev.ptr(inp['nm']), Cl, U, _dev.ptr(inp['bk_counts']),
-                                            _dev.ptr(inp['bk_offs']), _dev.ptr(tot.dev), stream), "fcd_bucket_count")
-        (n0, n1, n2, nd) = (int(v) for v in tot.read(stream))
+        if inp.get('PsE') is None:
+            inp['PsE'] = _dev.zeros((Cl, pitchU))
+            inp['kcE'] = torch.full((Cl,), 255, dtype=torch.uint8, device=_dev.device())
+            inp['code'] = _dev.empty((Cl * pitchU + 256,), torch.uint8)
+            inp['bk_counts'] = _dev.empty((Cl,), torch.int32)
+            inp['bk_offs'] = _dev.empty((2 * int(lib.fcd_bucket_blocks(Cl)),), torch.int64)
+        tot = self._result(1, tag="records")
+        planeStride = max(Cl, 1) * pitchU
+        with _dev.timed(self.profile, "K3b_code_plane"):
+            _lib.check(lib.fcd_code_plane(
+                _dev.ptr(inp['P']), planeStride, Cl, U, pitchU, _dev.ptr(fstate[c0:]), _dev.ptr(rstate),
+                rstate.shape[1], _dev.ptr(inp['nm']), _dev.ptr(inp['PsE']), _dev.ptr(inp['kcE']),
+                _dev.ptr(inp['code']), _dev.ptr(inp['bk_counts']), _dev.ptr(inp['bk_offs']), _dev.ptr(tot.dev),
+                stream), "fcd_code_plane")
+        nd = int(tot.read(stream)[0])
         use_tiered = self.elm_path == "auto" and nd * 4 > Cl * U
         if self.shards is not None:            # the ranks must take the same form: its collectives differ
             use_tiered = self.shards.any_rank(use_tiered)
         if use_tiered:
             return None
-        base = [0, n0 + (n0 & 1), 0]
-        base[2] = base[1] + n1 + (n1 & 1)
-        if inp.get('bk_G') is None:
-            inp['bk_G'] = _dev.empty((Cl * U + 4,))
         if inp.get('bk_D') is None or inp['bk_D'].numel() < 4 * nd:
             inp['bk_D'] = _dev.empty((4 * max(nd, Cl * U // 4, 1),))
-        base3 = (ctypes.c_int64 * 3)(*base)
-        count3 = (ctypes.c_int64 * 3)(n0, n1, n2)
         if inp.get('Lsum') is None:
             inp['Lsum'] = _dev.empty((1,))
-            _lib.check(lib.fcd_plane_sum(_dev.ptr(inp['L']), Cl, U, inp['pitchU'], _dev.ptr(inp['Lsum']),
+            _lib.check(lib.fcd_plane_sum(_dev.ptr(inp['L']), Cl, U, pitchU, _dev.ptr(inp['Lsum']),
                                          _dev.ptr(_dev.workspace()), stream), "fcd_plane_sum")
-        with _dev.timed(self.profile, "K3b_bucket_fill"):
-            _lib.check(lib.fcd_bucket_fill(
-                _dev.ptr(inp['P']), max(Cl, 1) * inp['pitchU'], _dev.ptr(inp['L']), _dev.ptr(inp['Lsum']),
-                Cl, U, inp['pitchU'],
-                _dev.ptr(qF[c0 * 3:]), _dev.ptr(fstate[c0:]), _dev.ptr(qR), _dev.ptr(rstate), rstate.shape[1], N,
-                _dev.ptr(inp['nm']), _dev.ptr(inp['bk_counts']), _dev.ptr(inp['bk_offs']), base3,
-                _dev.ptr(inp['bk_G']), _dev.ptr(inp['bk_D']), nd,
-                _dev.ptr(res4.dev[3:]), _dev.ptr(_dev.workspace()), stream), "fcd_bucket_fill")
-        return (_dev.ptr(inp['bk_G']), base3, count3, _dev.ptr(inp['bk_D']), nd)
+        with _dev.timed(self.profile, "K3b_records"):
+            _lib.check(lib.fcd_code_records(
+                _dev.ptr(inp['P']), planeStride, _dev.ptr(inp['PsE']), _dev.ptr(inp['code']), _dev.ptr(inp['L']),
+                _dev.ptr(inp['Lsum']), Cl, U, pitchU, _dev.ptr(qF[c0 * 3:]), _dev.ptr(fstate[c0:]), _dev.ptr(qR), N,
+                _dev.ptr(inp['nm']), _dev.ptr(inp['bk_counts']), _dev.ptr(inp['bk_offs']), _dev.ptr(inp['bk_D']), nd,
+                _dev.ptr(res4.dev[3:]), _dev.ptr(_dev.workspace()), stream), "fcd_code_records")
+        return (_dev.ptr(inp['PsE']), _dev.ptr(inp['code']), Cl * pitchU, _dev.ptr(inp['bk_D']), nd)
 
     def _theta(self, use_snapshot=True):
         m = self.model
@@ -908,7 +906,7 @@ class UnsharedRegionFit(object):
         tail = (_dev.ptr(res.dev), _dev.ptr(_dev.workspace()), stream)
         head = self._build_streams(inp, res)
         if head is not None:
-            (fn, name, const) = (lib.fcd_elm_streams, "K3b_elm_streams", None)
+            (fn, name, const) = (lib.fcd_elm_coded, "K3b_elm_streams", None)
             head = head + (ctypes.byref(th),)
         else:
             (fn, name, const) = (lib.fcd_elm_obj_grad, "K3b_elm_obj_grad", self._elm_const(inp))

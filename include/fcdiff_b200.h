@@ -238,35 +238,39 @@ FCD_API int fcd_elm_const(const double* L, int64_t C, int32_t U, int64_t pitchU,
                   const double* qF, const uint8_t* fstate, const double* qR, const uint8_t* rstate,
                   int64_t pitchS, int32_t N, const int32_t* nm, double* out1, double* ws, void* stream);
 
-/* K3b as dense streams (DESIGN.md "Streams").  Between two E-steps the optimiser
- * evaluates E_lM(eta, epsilon) many times with q_F, q_R fixed (fit.py:228-241):
- * the bucket pass turns the planes into what an evaluation needs and nothing
- * else -- three streams G_l of responsibilities p (elements whose edge and
- * regions are peaked, grouped by their pair state l: weight 1, one log each)
- * and records {p, w_0, w_1, w_2} for all other elements -- and fcd_elm_streams
- * reduces them: 8 bytes per edge-patient per evaluation, no row structure.
- *   fcd_bucket_count: counts[c] = {n_0, n_1, n_2, n_records} (int32 x 4) per row,
- *     blockoff: scratch of 2 * fcd_bucket_blocks(C) x 4 int64 (totals and exclusive
- *     prefix sums of blocks of 16 rows), totals[4] (int64);
+/* K3b over the coded dominant-state plane (DESIGN.md "Coded plane").  Between two
+ * E-steps the optimiser evaluates E_lM(eta, epsilon) many times with q_F, q_R fixed
+ * (fit.py:228-241): the code pass turns the planes into what an evaluation needs
+ * and nothing else --
+ *   PsE  [C][pitchU] f64: responsibility of each edge's dominant state (rows re-gathered
+ *        from P only when kcache[c] != fstate[c]; kcache starts at 255, PsE zero-filled);
+ *   code [C][pitchU] u8 (+ 16 bytes of slack): l* in 0..2 for elements whose edge and
+ *        regions are peaked (weight exactly 1, one log), 3 for all others;
+ *   records {p, w_0, w_1, w_2} (32 bytes) for all other elements, nd of them
+ * -- and fcd_elm_coded reduces them: 9 bytes per edge-patient per evaluation, no row
+ * structure, no partition of the elements.
  *   fcd_plane_sum: out1[0] = sum of a [C][U] plane -- the total of the L plane, once per cache;
- *   fcd_bucket_fill: G_l occupies G[base3[l] .. base3[l] + totals[l]) (bases even),
- *     D holds nd = totals[3] records (32 bytes each);  out1[0] = the theta-free part of
- *     E_lM (same value as fcd_elm_const), formed as Lsum[0] (device, from fcd_plane_sum)
- *     corrected by the record elements only: the fill never reads the L plane;
- *   fcd_elm_streams: out3 as fcd_elm_obj_grad. */
+ *   fcd_code_plane: refreshes PsE, writes code, counts[c] = records of row c (int32),
+ *     blockoff: scratch of 2 * fcd_bucket_blocks(C) int64 (totals and exclusive prefix
+ *     sums of blocks of 16 rows), total1[0] = nd (as a double);
+ *   fcd_code_records: D receives the nd records; out1[0] = the theta-free part of E_lM
+ *     (same value as fcd_elm_const), formed as Lsum[0] (device, from fcd_plane_sum)
+ *     corrected by the record elements only;
+ *   fcd_elm_coded: nE = C * pitchU elements of PsE / code; out3 as fcd_elm_obj_grad. */
 FCD_API int64_t fcd_bucket_blocks(int64_t C);
-FCD_API int fcd_bucket_count(const uint8_t* fstate, const uint8_t* rstate, int64_t pitchS, const int32_t* nm,
-                     int64_t C, int32_t U, int32_t* counts, int64_t* blockoff, int64_t* totals, void* stream);
 FCD_API int fcd_plane_sum(const double* X, int64_t C, int32_t U, int64_t pitchU, double* out1, double* ws,
                   void* stream);
-FCD_API int fcd_bucket_fill(const double* P, int64_t planeStride, const double* L, const double* Lsum,
-                    int64_t C, int32_t U, int64_t pitchU, const double* qF, const uint8_t* fstate, const double* qR, const uint8_t* rstate,
-                    int64_t pitchS, int32_t N, const int32_t* nm, const int32_t* counts, const int64_t* blockoff,
-                    const int64_t* base3_host, double* G, double* D, int64_t nd, double* out1, double* ws,
-                    void* stream);
-FCD_API int fcd_elm_streams(const double* G, const int64_t* base3_host, const int64_t* count3_host,
-                    const double* D, int64_t nd, const fcd_theta* theta_host, int32_t want_grad,
-                    double* out3, double* ws, void* stream);
+FCD_API int fcd_code_plane(const double* P, int64_t planeStride, int64_t C, int32_t U, int64_t pitchU,
+                   const uint8_t* fstate, const uint8_t* rstate, int64_t pitchS, const int32_t* nm,
+                   double* PsE, uint8_t* kcache, uint8_t* code, int32_t* counts, int64_t* blockoff,
+                   double* total1, void* stream);
+FCD_API int fcd_code_records(const double* P, int64_t planeStride, const double* PsE, const uint8_t* code,
+                     const double* L, const double* Lsum, int64_t C, int32_t U, int64_t pitchU,
+                     const double* qF, const uint8_t* fstate, const double* qR, int32_t N, const int32_t* nm,
+                     const int32_t* counts, const int64_t* blockoff, double* D, int64_t nd, double* out1, double* ws,
+                     void* stream);
+FCD_API int fcd_elm_coded(const double* PsE, const uint8_t* code, int64_t nE, const double* D, int64_t nd,
+                  const fcd_theta* theta_host, int32_t want_grad, double* out3, double* ws, void* stream);
 
 /* K4 -- free-energy terms; replaces `_eval_energy` and `_eval_E_*`
  * (fcdiff/fit.py:142-155, 447-539).  out[0..5] = E_lp_F, E_lp_B_g_F, E_lp_R,

@@ -29,6 +29,13 @@ def main():
             out.append((int(r[S]), int(r[E]), fpath, int(r[0]), r[1].strip()))
         except ValueError:
             pass
+    agg = {}
+    for o in out:                                   # several launches of the kernel: one entry per source line
+        k = (o[2], o[3], o[4])
+        a = agg.setdefault(k, [0, 0])
+        a[0] += o[0]
+        a[1] += o[1]
+    out = [(v[0], v[1], k[0], k[1], k[2]) for (k, v) in agg.items()]
     ts = sum(o[0] for o in out)
     te = sum(o[1] for o in out)
     print("samples %d  executed warp-instructions %d" % (ts, te))
