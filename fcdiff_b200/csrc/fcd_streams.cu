@@ -38,28 +38,13 @@ __device__ __forceinline__ int pair_code(int sn, int sm) {
 // kernel -- no pass over per-row arrays by a single CTA.
 constexpr int kRowBlock = 16;
 
-// PsE[c][:] = P[k*(c)][c][:] for the rows whose dominant state changed since the last call.
-__global__ void __launch_bounds__(kBucketThreads)
-pstar_edge_kernel(const double* __restrict__ P, int64_t planeStride, int64_t C, int64_t pitchU,
-                  const uint8_t* __restrict__ fstate, double* __restrict__ PsE, uint8_t* __restrict__ kcache) {
-    const int lane = threadIdx.x & 31;
-    const int64_t nw = (int64_t)gridDim.x * (kBucketThreads / 32);
-    for (int64_t c = (int64_t)blockIdx.x * (kBucketThreads / 32) + (threadIdx.x >> 5); c < C; c += nw) {
-        const int k = fstate[c];
-        if (k >= 3 || k == kcache[c]) continue;               // warp-uniform
-        const double* src = P + (int64_t)k * planeStride + c * pitchU;
-        double* dst = PsE + c * pitchU;
-        for (int64_t u = 2 * lane; u < pitchU; u += 64)
-            *reinterpret_cast<double2*>(dst + u) = ldg_stream2(src + u);
-        __syncwarp();
-        if (lane == 0) kcache[c] = (uint8_t)k;
-    }
-}
-
 // code[c][u] for u in [0, pitchU) and counts[c] = number of records of row c; blocktot[b] = their
-// sum over the rows of block b.
+// sum over the rows of block b.  On the way: PsE[c][:] = P[k*(c)][c][:] for the rows whose dominant
+// state changed since the last call (kcache).
 __global__ void __launch_bounds__(kBucketThreads)
-code_plane_kernel(const uint8_t* __restrict__ fstate, const uint8_t* __restrict__ rstate, int64_t pitchS,
+code_plane_kernel(const double* __restrict__ P, int64_t planeStride, double* __restrict__ PsE,
+                  uint8_t* __restrict__ kcache,
+                  const uint8_t* __restrict__ fstate, const uint8_t* __restrict__ rstate, int64_t pitchS,
                   const int32_t* __restrict__ nm, int64_t C, int U, int64_t pitchU, uint8_t* __restrict__ code,
                   int32_t* __restrict__ counts, long long* __restrict__ blocktot) {
     __shared__ int s_cnt[kRowBlock];
@@ -76,6 +61,14 @@ code_plane_kernel(const uint8_t* __restrict__ fstate, const uint8_t* __restrict_
                 cnt = 3 * U;
             } else {
                 const int v = __ldg(nm + c);
+                if (k != kcache[c]) {                        // warp-uniform; rare once q_F has settled
+                    const double* src = P + (int64_t)k * planeStride + c * pitchU;
+                    double* dst = PsE + c * pitchU;
+                    for (int64_t u = 2 * lane; u < pitchU; u += 64)
+                        *reinterpret_cast<double2*>(dst + u) = ldg_stream2(src + u);
+                    __syncwarp();
+                    if (lane == 0) kcache[c] = (uint8_t)k;
+                }
                 const uint8_t* rn = rstate + (int64_t)(v & 0xffff) * pitchS;
                 const uint8_t* rm = rstate + (int64_t)((v >> 16) & 0xffff) * pitchS;
                 // two patients per lane; the state rows are padded with 4 up to pitchS >= pitchU
@@ -149,14 +142,14 @@ plane_sum_kernel(const double* __restrict__ X, int64_t C, int U, int64_t pitchU,
     grid_reduce_store<1, kBucketThreads>(vv, ws, out);
 }
 
-// Records of the elements the code plane leaves out, as {p, -, (c, u), tag}: tag 0 = element of a
-// peaked edge with a mixed region (one record), tag 1 + k = state k of an unpeaked edge (three
-// records per element).  Same row blocks as code_plane_kernel; weights by bucket_records_kernel.
-__global__ void __launch_bounds__(kBucketThreads, 3)
-record_fill_kernel(const double* __restrict__ P, int64_t planeStride, const double* __restrict__ PsE,
-                   const uint8_t* __restrict__ code, const uint8_t* __restrict__ fstate,
+// Keys of the elements the code plane leaves out: (tag << 48) | (c << 16) | u with tag 0 = element of
+// a peaked edge with a mixed region (one record), tag 1 + k = state k of an unpeaked edge (three
+// records per element).  Same row blocks as code_plane_kernel.  Only the code plane is read: the
+// operands of a record are gathered by record_weights_kernel, one thread per record.
+__global__ void __launch_bounds__(kBucketThreads, 4)
+record_keys_kernel(const uint8_t* __restrict__ code, const uint8_t* __restrict__ fstate,
                    int64_t C, int U, int64_t pitchU, const int32_t* __restrict__ counts,
-                   const long long* __restrict__ blockoff, Record* __restrict__ D) {
+                   const long long* __restrict__ blockoff, unsigned long long* __restrict__ keys) {
     __shared__ long long s_off[kRowBlock];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
@@ -178,29 +171,21 @@ record_fill_kernel(const double* __restrict__ P, int64_t planeStride, const doub
         for (int r = warp; r < kRowBlock; r += kBucketThreads / 32) {
             const int64_t c = cb + r;
             if (c >= C) break;
-            if (counts[c] == 0) continue;                    // warp-uniform: most rows of a settled fit
+            if (counts[c] == 0) continue;                    // warp-uniform
             const int k = fstate[c];
-            Record* const d3 = D + s_off[r];
+            unsigned long long* const d3 = keys + s_off[r];
+            const unsigned long long ckey = (unsigned long long)c << 16;
             if (k == kStateMixedF) {                         // three records per element, tagged with their state
                 for (int u = lane; u < U; u += 32) {
-                    const int64_t i = c * pitchU + u;
 #pragma unroll
-                    for (int kk = 0; kk < 3; ++kk) {
-                        Record rec;
-                        rec.p = ldg_stream1(P + kk * planeStride + i);
-                        rec.w0 = 0.0;
-                        rec.w1 = __hiloint2double((int)c, u);
-                        rec.w2 = 1.0 + kk;
-                        d3[3 * (int64_t)u + kk] = rec;
-                    }
+                    for (int kk = 0; kk < 3; ++kk)
+                        d3[3 * (int64_t)u + kk] = ((unsigned long long)(1 + kk) << 48) | ckey | (unsigned long long)u;
                 }
                 continue;
             }
             const unsigned short* crow = reinterpret_cast<const unsigned short*>(code + c * pitchU);
-            const double* prow = PsE + c * pitchU;
             uint32_t off = 0;
-            // batches of 8 x 64 patients: all code loads first, then positions (ballots only), then all
-            // gathers of p, then the stores -- the row is latency-bound, not bandwidth-bound
+            // batches of 8 x 64 patients: all code loads first, then positions (ballots) and stores
             for (int ub = 0; ub < U; ub += 512) {
                 uint32_t c2[8];
 #pragma unroll
@@ -208,7 +193,6 @@ record_fill_kernel(const double* __restrict__ P, int64_t planeStride, const doub
                     const int u = ub + 64 * i + 2 * lane;
                     c2[i] = u < U ? (uint32_t)__ldg(crow + (u >> 1)) : 0u;
                 }
-                int at[16];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int u = ub + 64 * i + 2 * lane;
@@ -216,25 +200,8 @@ record_fill_kernel(const double* __restrict__ P, int64_t planeStride, const doub
                     for (int e = 0; e < 2; ++e) {
                         const bool mixed = u + e < U && ((c2[i] >> (8 * e)) & 0xff) == 3;
                         const unsigned bal = __ballot_sync(0xffffffffu, mixed);
-                        at[2 * i + e] = mixed ? (int)(off + __popc(bal & lt)) : -1;
+                        if (mixed) d3[off + __popc(bal & lt)] = ckey | (unsigned long long)(u + e);
                         off += __popc(bal);
-                    }
-                }
-                double pv[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    pv[j] = 0.0;
-                    if (at[j] >= 0) pv[j] = __ldg(prow + ub + 64 * (j >> 1) + 2 * lane + (j & 1));
-                }
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    if (at[j] >= 0) {
-                        Record rec;
-                        rec.p = pv[j];
-                        rec.w0 = 0.0;
-                        rec.w1 = __hiloint2double((int)c, ub + 64 * (j >> 1) + 2 * lane + (j & 1));
-                        rec.w2 = 0.0;
-                        d3[at[j]] = rec;
                     }
                 }
             }
@@ -242,30 +209,34 @@ record_fill_kernel(const double* __restrict__ P, int64_t planeStride, const doub
     }
 }
 
-// Second half of the bucket pass: the records of unpeaked elements were left as {p, -, (c, u), tag};
-// one thread per record gathers the two regions' posteriors and the element's L (massively parallel,
-// nothing on a row walker's critical path), writes {p, w_0, w_1, w_2} and accumulates
+// Second half of the record pass, one thread per record: gathers the responsibility (dominant-state
+// plane, or plane k of an unpeaked edge), the two regions' posteriors and the element's L, writes
+// {p, w_0, w_1, w_2} and accumulates
 //   out[0] = Lsum - sum_{record elements} L + sum_records (sum_l w_l) L
-// (Lsum = sum of L over all local elements, fcd_plane_sum: the stream elements have weight exactly 1).
+// (Lsum = sum of L over all local elements, fcd_plane_sum: the coded elements have weight exactly 1).
 __global__ void __launch_bounds__(kBucketThreads)
-bucket_records_kernel(Record* __restrict__ D, long long nd, const double* __restrict__ L, int64_t pitchU,
-                      const double* __restrict__ Lsum, const double* __restrict__ qF,
+record_weights_kernel(const unsigned long long* __restrict__ keys, long long nd, const double* __restrict__ P,
+                      int64_t planeStride, const double* __restrict__ PsE, const double* __restrict__ L,
+                      int64_t pitchU, const double* __restrict__ Lsum, const double* __restrict__ qF,
                       const double* __restrict__ qR, int U, const int32_t* __restrict__ nm,
-                      double* __restrict__ out, double* __restrict__ ws) {
+                      Record* __restrict__ D, double* __restrict__ out, double* __restrict__ ws) {
     const double2* qR2 = reinterpret_cast<const double2*>(qR);
     double cs = 0.0;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nd;
          i += (long long)gridDim.x * blockDim.x) {
-        Record rec = D[i];                                   // {p, -, (c, u), tag}: tag 0 = peaked edge, 1 + k otherwise
-        const int c = __double2hiint(rec.w1), u = __double2loint(rec.w1);
-        const int tag = (int)rec.w2;
-        const double lv = __ldg(L + (int64_t)c * pitchU + u);
+        const unsigned long long key = keys[i];
+        const int u = (int)(key & 0xffffull), tag = (int)(key >> 48);
+        const int64_t c = (int64_t)((key >> 16) & 0xffffffffull);
+        const int64_t e = c * pitchU + u;
+        const double lv = __ldg(L + e);
         const int v = __ldg(nm + c);
+        Record rec;
+        rec.p = tag == 0 ? __ldg(PsE + e) : ldg_stream1(P + (int64_t)(tag - 1) * planeStride + e);
         double w[3];
         pair_weights(__ldg(qR2 + (int64_t)(v & 0xffff) * U + u), __ldg(qR2 + (int64_t)((v >> 16) & 0xffff) * U + u), w);
         double scale = 1.0, cscale = 1.0;
         if (tag > 0) {
-            const double qf[3] = {__ldg(qF + (int64_t)c * 3), __ldg(qF + (int64_t)c * 3 + 1), __ldg(qF + (int64_t)c * 3 + 2)};
+            const double qf[3] = {__ldg(qF + c * 3), __ldg(qF + c * 3 + 1), __ldg(qF + c * 3 + 2)};
             scale = qf[tag - 1];
             cscale = tag == 1 ? qf[0] + qf[1] + qf[2] : 0.0;  // the element's theta-free term is counted once
         }
@@ -509,16 +480,12 @@ int fcd_code_plane(const double* P, int64_t planeStride, int64_t C, int32_t U, i
                 (reinterpret_cast<uintptr_t>(rstate) & 1) == 0 && (reinterpret_cast<uintptr_t>(blockoff) & 7) == 0,
                 "fcd_code_plane: planes / code must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    pstar_edge_kernel<<<rows_grid(C, kBucketThreads / 32, 8), kBucketThreads, 0, st>>>(P, planeStride, C, pitchU,
-                                                                                      fstate, PsE, kcache);
-    int rc = check_launch("fcd_code_plane(pstar)");
-    if (rc) return rc;
     const int64_t nblocks = (C + kRowBlock - 1) / kRowBlock;
     // blockoff doubles as the block totals' storage: [nblocks] totals followed by [nblocks] offsets
     long long* bt = reinterpret_cast<long long*>(blockoff);
-    code_plane_kernel<<<(unsigned)nblocks, kBucketThreads, 0, st>>>(fstate, rstate, pitchS, nm, C, U, pitchU, code,
-                                                                    counts, bt);
-    rc = check_launch("fcd_code_plane");
+    code_plane_kernel<<<(unsigned)nblocks, kBucketThreads, 0, st>>>(P, planeStride, PsE, kcache, fstate, rstate, pitchS,
+                                                                    nm, C, U, pitchU, code, counts, bt);
+    int rc = check_launch("fcd_code_plane");
     if (rc) return rc;
     record_scan_kernel<<<1, 1024, 0, st>>>(bt, nblocks, bt + nblocks, total1);
     return check_launch("fcd_code_plane(scan)");
@@ -527,31 +494,33 @@ int fcd_code_plane(const double* P, int64_t planeStride, int64_t C, int32_t U, i
 int fcd_code_records(const double* P, int64_t planeStride, const double* PsE, const uint8_t* code,
                      const double* L, const double* Lsum, int64_t C, int32_t U, int64_t pitchU,
                      const double* qF, const uint8_t* fstate, const double* qR, int32_t N, const int32_t* nm,
-                     const int32_t* counts, const int64_t* blockoff, double* D, int64_t nd, double* out1, double* ws,
-                     void* stream) {
+                     const int32_t* counts, const int64_t* blockoff, uint64_t* keys, double* D, int64_t nd,
+                     double* out1, double* ws, void* stream) {
     FCD_REQUIRE(P != nullptr && PsE != nullptr && code != nullptr && L != nullptr && Lsum != nullptr && qF != nullptr &&
                 fstate != nullptr && qR != nullptr && nm != nullptr && counts != nullptr && blockoff != nullptr &&
-                D != nullptr && out1 != nullptr && ws != nullptr, "fcd_code_records: NULL argument");
-    FCD_REQUIRE(C >= 1 && U >= 1 && pitchU >= U && pitchU % 2 == 0 && N >= 2 && N < 65536 && nd >= 0,
-                "fcd_code_records: bad shape");
-    FCD_REQUIRE((reinterpret_cast<uintptr_t>(D) & 31) == 0, "fcd_code_records: records must be 32-byte aligned");
+                keys != nullptr && D != nullptr && out1 != nullptr && ws != nullptr, "fcd_code_records: NULL argument");
+    FCD_REQUIRE(C >= 1 && C < (1ll << 32) && U >= 1 && U < 65536 && pitchU >= U && pitchU % 2 == 0 && N >= 2 &&
+                N < 65536 && nd >= 0, "fcd_code_records: bad shape");
+    FCD_REQUIRE((reinterpret_cast<uintptr_t>(D) & 31) == 0 && (reinterpret_cast<uintptr_t>(keys) & 7) == 0,
+                "fcd_code_records: records must be 32-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t nblocks = (C + kRowBlock - 1) / kRowBlock;
     int rc = 0;
     if (nd > 0) {
         int64_t grid = nblocks;                              // persistent: the resident CTAs share the row blocks
-        if (grid > (int64_t)sm_count() * 3) grid = (int64_t)sm_count() * 3;
-        record_fill_kernel<<<(unsigned)grid, kBucketThreads, 0, st>>>(
-            P, planeStride, PsE, code, fstate, C, U, pitchU, counts,
-            reinterpret_cast<const long long*>(blockoff) + nblocks, reinterpret_cast<Record*>(D));
-        rc = check_launch("fcd_code_records(fill)");
+        if (grid > (int64_t)sm_count() * 4) grid = (int64_t)sm_count() * 4;
+        record_keys_kernel<<<(unsigned)grid, kBucketThreads, 0, st>>>(
+            code, fstate, C, U, pitchU, counts, reinterpret_cast<const long long*>(blockoff) + nblocks,
+            reinterpret_cast<unsigned long long*>(keys));
+        rc = check_launch("fcd_code_records(keys)");
         if (rc) return rc;
     }
     int64_t rgrid = (nd + kBucketThreads - 1) / kBucketThreads;       // nd == 0: one CTA writes out1[0] = Lsum
     if (rgrid > (int64_t)sm_count() * 8) rgrid = (int64_t)sm_count() * 8;
     if (rgrid < 1) rgrid = 1;
-    bucket_records_kernel<<<(unsigned)rgrid, kBucketThreads, 0, st>>>(reinterpret_cast<Record*>(D), nd, L, pitchU,
-                                                                      Lsum, qF, qR, U, nm, out1, ws);
+    record_weights_kernel<<<(unsigned)rgrid, kBucketThreads, 0, st>>>(
+        reinterpret_cast<const unsigned long long*>(keys), nd, P, planeStride, PsE, L, pitchU, Lsum, qF, qR, U, nm,
+        reinterpret_cast<Record*>(D), out1, ws);
     return check_launch("fcd_code_records");
 }
 

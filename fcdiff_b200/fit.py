@@ -451,6 +451,7 @@ class UnsharedRegionFit(object):
             return None
         if inp.get('bk_D') is None or inp['bk_D'].numel() < 4 * nd:
             inp['bk_D'] = _dev.empty((4 * max(nd, Cl * U // 4, 1),))
+            inp['bk_K'] = _dev.empty((max(nd, Cl * U // 4, 1),), torch.int64)
         if inp.get('Lsum') is None:
             inp['Lsum'] = _dev.empty((1,))
             _lib.check(lib.fcd_plane_sum(_dev.ptr(inp['L']), Cl, U, pitchU, _dev.ptr(inp['Lsum']),
@@ -459,8 +460,9 @@ class UnsharedRegionFit(object):
             _lib.check(lib.fcd_code_records(
                 _dev.ptr(inp['P']), planeStride, _dev.ptr(inp['PsE']), _dev.ptr(inp['code']), _dev.ptr(inp['L']),
                 _dev.ptr(inp['Lsum']), Cl, U, pitchU, _dev.ptr(qF[c0 * 3:]), _dev.ptr(fstate[c0:]), _dev.ptr(qR), N,
-                _dev.ptr(inp['nm']), _dev.ptr(inp['bk_counts']), _dev.ptr(inp['bk_offs']), _dev.ptr(inp['bk_D']), nd,
-                _dev.ptr(res4.dev[3:]), _dev.ptr(_dev.workspace()), stream), "fcd_code_records")
+                _dev.ptr(inp['nm']), _dev.ptr(inp['bk_counts']), _dev.ptr(inp['bk_offs']), _dev.ptr(inp['bk_K']),
+                _dev.ptr(inp['bk_D']), nd, _dev.ptr(res4.dev[3:]), _dev.ptr(_dev.workspace()), stream),
+                "fcd_code_records")
         return (_dev.ptr(inp['PsE']), _dev.ptr(inp['code']), Cl * pitchU, _dev.ptr(inp['bk_D']), nd)
 
     def _theta(self, use_snapshot=True):

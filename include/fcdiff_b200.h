@@ -253,7 +253,7 @@ FCD_API int fcd_elm_const(const double* L, int64_t C, int32_t U, int64_t pitchU,
  *   fcd_code_plane: refreshes PsE, writes code, counts[c] = records of row c (int32),
  *     blockoff: scratch of 2 * fcd_bucket_blocks(C) int64 (totals and exclusive prefix
  *     sums of blocks of 16 rows), total1[0] = nd (as a double);
- *   fcd_code_records: D receives the nd records; out1[0] = the theta-free part of E_lM
+ *   fcd_code_records: D receives the nd records (keys: scratch of nd uint64); out1[0] = the theta-free part of E_lM
  *     (same value as fcd_elm_const), formed as Lsum[0] (device, from fcd_plane_sum)
  *     corrected by the record elements only;
  *   fcd_elm_coded: nE = C * pitchU elements of PsE / code; out3 as fcd_elm_obj_grad. */
@@ -267,8 +267,8 @@ FCD_API int fcd_code_plane(const double* P, int64_t planeStride, int64_t C, int3
 FCD_API int fcd_code_records(const double* P, int64_t planeStride, const double* PsE, const uint8_t* code,
                      const double* L, const double* Lsum, int64_t C, int32_t U, int64_t pitchU,
                      const double* qF, const uint8_t* fstate, const double* qR, int32_t N, const int32_t* nm,
-                     const int32_t* counts, const int64_t* blockoff, double* D, int64_t nd, double* out1, double* ws,
-                     void* stream);
+                     const int32_t* counts, const int64_t* blockoff, uint64_t* keys, double* D, int64_t nd,
+                     double* out1, double* ws, void* stream);
 FCD_API int fcd_elm_coded(const double* PsE, const uint8_t* code, int64_t nE, const double* D, int64_t nd,
                   const fcd_theta* theta_host, int32_t want_grad, double* out3, double* ws, void* stream);
 

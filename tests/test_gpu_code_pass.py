@@ -1,0 +1,157 @@
+"""GPU: the K3b code pass (dominant-state plane, code bytes, records), the evaluator over it, the
+small-vector exchange and the patient gather staging -- each through the C-ABI against NumPy."""
+import ctypes
+
+import numpy as np
+import numpy.testing as nptest
+import pytest
+import torch
+
+from oracle import iar_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+import fcdiff_b200 as fcdiff            # noqa: E402
+from fcdiff_b200 import _dev, _lib      # noqa: E402
+from fcdiff_b200 import util            # noqa: E402
+
+
+def _pair_code(sn, sm):
+    """code of an element from the two regions' peak states (csrc/fcd_streams.cu:pair_code)."""
+    o = sn | sm
+    if o < 2:
+        return ((sn ^ sm) << 1) + (sn & sm)
+    return 3
+
+
+@pytest.mark.parametrize("N,U", [(9, 7), (23, 130), (40, 300)])
+def test_code_plane_and_evaluator_match_numpy(N, U):
+    lib = _lib.load()
+    rng = np.random.RandomState(N * 1000 + U)
+    C = N * (N - 1) // 2
+    pitchU = U + (U & 1)
+    pitchS = (U + 255) // 256 * 256
+    P = rng.dirichlet([1.0, 1.0, 1.0], size=(C, pitchU)).transpose(2, 0, 1).copy()      # [3][C][pitchU]
+    L = rng.randn(C, pitchU)
+    fstate = rng.choice([0, 1, 2, 3], size=C, p=[0.3, 0.3, 0.3, 0.1]).astype(np.uint8)
+    rstate = np.full((N, pitchS), 4, np.uint8)
+    rstate[:, :U] = rng.choice([0, 1, 2], size=(N, U), p=[0.6, 0.3, 0.1])
+    # posteriors consistent with the states (peaked rows are exactly one-hot)
+    qF = np.zeros((C, 3))
+    for c in range(C):
+        qF[c] = rng.dirichlet([2.0, 2.0, 2.0]) if fstate[c] == 3 else np.eye(3)[fstate[c]]
+    qR = np.zeros((N, U, 2))
+    for n in range(N):
+        for u in range(U):
+            s = rstate[n, u]
+            qR[n, u] = rng.dirichlet([2.0, 2.0]) if s == 2 else np.eye(2)[s]
+    nm = np.array([(util.c_to_nm(c)[0] | (util.c_to_nm(c)[1] << 16)) for c in range(C)], dtype=np.int32)
+
+    d = {k: _dev.upload(v) for (k, v) in dict(P=P, L=L, qF=qF.reshape(-1), qR=qR.reshape(-1)).items()}
+    fs = torch.from_numpy(fstate).cuda()
+    rs = torch.from_numpy(rstate).cuda()
+    nmd = torch.from_numpy(nm).cuda()
+    PsE = _dev.zeros((C, pitchU))
+    kc = torch.full((C,), 255, dtype=torch.uint8, device="cuda")
+    code = _dev.empty((C * pitchU + 256,), torch.uint8)
+    counts = _dev.empty((C,), torch.int32)
+    offs = _dev.empty((2 * int(lib.fcd_bucket_blocks(C)),), torch.int64)
+    tot = _dev.zeros((1,))
+    st = _dev.stream()
+    _lib.check(lib.fcd_code_plane(_dev.ptr(d['P']), C * pitchU, C, U, pitchU, _dev.ptr(fs), _dev.ptr(rs), pitchS,
+                                  _dev.ptr(nmd), _dev.ptr(PsE), _dev.ptr(kc), _dev.ptr(code), _dev.ptr(counts),
+                                  _dev.ptr(offs), _dev.ptr(tot), st), "fcd_code_plane")
+    # ---- NumPy restatement of the code pass
+    want_code = np.full((C, pitchU), 3, np.uint8)
+    want_cnt = np.zeros(C, np.int64)
+    for c in range(C):
+        (n, m) = util.c_to_nm(c)
+        if fstate[c] == 3:
+            want_cnt[c] = 3 * U
+            continue
+        for u in range(U):
+            want_code[c, u] = _pair_code(int(rstate[n, u]), int(rstate[m, u]))
+        want_cnt[c] = int((want_code[c, :U] == 3).sum())
+    got_code = code[:C * pitchU].cpu().numpy().reshape(C, pitchU)
+    nptest.assert_array_equal(got_code, want_code)
+    nptest.assert_array_equal(counts.cpu().numpy(), want_cnt)
+    nd = int(tot.cpu().numpy()[0])
+    assert nd == want_cnt.sum()
+    got_PsE = PsE.cpu().numpy()
+    for c in range(C):
+        if fstate[c] < 3:
+            nptest.assert_array_equal(got_PsE[c], P[fstate[c], c])
+    nptest.assert_array_equal(kc.cpu().numpy()[fstate < 3], fstate[fstate < 3])
+
+    # ---- records + evaluation against the plain triple sum (fit.py:489-511, 600-697)
+    Lsum = _dev.zeros((1,))
+    ws = _dev.workspace()
+    _lib.check(lib.fcd_plane_sum(_dev.ptr(d['L']), C, U, pitchU, _dev.ptr(Lsum), _dev.ptr(ws), st), "fcd_plane_sum")
+    nptest.assert_allclose(Lsum.cpu().numpy()[0], L[:, :U].sum(), rtol=1e-12, atol=1e-9)
+    D = _dev.empty((4 * max(nd, 1),))
+    K = _dev.empty((max(nd, 1),), torch.int64)
+    out = _dev.zeros((4,))
+    _lib.check(lib.fcd_code_records(_dev.ptr(d['P']), C * pitchU, _dev.ptr(PsE), _dev.ptr(code), _dev.ptr(d['L']),
+                                    _dev.ptr(Lsum), C, U, pitchU, _dev.ptr(d['qF']), _dev.ptr(fs), _dev.ptr(d['qR']), N,
+                                    _dev.ptr(nmd), _dev.ptr(counts), _dev.ptr(offs), _dev.ptr(K), _dev.ptr(D), nd,
+                                    _dev.ptr(out[3:]), _dev.ptr(ws), st), "fcd_code_records")
+    (eta, eps) = (0.37, 0.12)
+    th = _lib.make_theta(0.1, eta, eps, [0.2, 0.5, 0.3], [-0.1, 0.0, 0.1], [0.1, 0.1, 0.1])
+    _lib.check(lib.fcd_elm_coded(_dev.ptr(PsE), _dev.ptr(code), C * pitchU, _dev.ptr(D), nd, ctypes.byref(th), 1,
+                                 _dev.ptr(out), _dev.ptr(ws), st), "fcd_elm_coded")
+    got = out.cpu().numpy()
+    epsl = np.array([1 - eps, eps, eta * eps + (1 - eta) * (1 - eps)])
+    (al, bl) = ((1 - epsl) / 2, epsl - (1 - epsl) / 2)
+    sl = np.array([-1.0, 1.0, 2 * eta - 1])
+    (obj, const, ge, gh) = (0.0, 0.0, 0.0, 0.0)
+    for c in range(C):
+        (n, m) = util.c_to_nm(c)
+        for u in range(U):
+            (qn, qm) = (qR[n, u], qR[m, u])
+            w = np.array([qn[0] * qm[0], qn[1] * qm[1], qn[0] * qm[1] + qn[1] * qm[0]])
+            const += qF[c].sum() * w.sum() * L[c, u]
+            for k in range(3):
+                p = P[k, c, u]
+                M = al + bl * p
+                obj += qF[c, k] * (w * np.log(M)).sum()
+                dd = qF[c, k] * w * (1.5 * p - 0.5) / M
+                ge += (sl * dd).sum()
+                gh += dd[2]
+    scale = max(1.0, abs(obj))
+    nptest.assert_allclose(got[0], obj, rtol=1e-11, atol=1e-11 * scale)
+    nptest.assert_allclose(got[3], const, rtol=1e-11, atol=1e-10)
+    nptest.assert_allclose(got[1], -(2 * eps - 1) * gh, rtol=0, atol=1e-10 * scale)
+    nptest.assert_allclose(got[2], -ge, rtol=0, atol=1e-10 * scale)
+
+
+def test_small_exchange_world1_publishes_to_the_host():
+    from fcdiff_b200.dist import PeerWindow
+    pw = PeerWindow()
+    st = _dev.stream()
+    for n in (1, 4, 8):
+        x = np.random.RandomState(n).randn(n)
+        v = _dev.upload(x)
+        for _ in range(3):                      # consecutive exchanges reuse the window and the result slot
+            nptest.assert_array_equal(pw.allreduce(v, n, st), x)
+    pw.close()
+
+
+@pytest.mark.parametrize("N,U,world", [(5, 7, 2), (12, 500, 8), (3, 3, 4)])
+def test_patient_gather_staging_roundtrip(N, U, world):
+    lib = _lib.load()
+    rng = np.random.RandomState(U)
+    (a, b) = (rng.randn(N, U, 2), rng.randn(N, U, 2))
+    ch = (U + world - 1) // world
+    st = _dev.stream()
+    gathered = _dev.empty((world, 2 * N * ch * 2))
+    (ad, bd) = (_dev.upload(a.reshape(-1)), _dev.upload(b.reshape(-1)))
+    for r in range(world):
+        u0 = min(r * ch, U)
+        Ul = min(ch, U - u0)
+        _lib.check(lib.fcd_pack_patients(_dev.ptr(ad), _dev.ptr(bd), N, U, u0, Ul, ch, _dev.ptr(gathered[r]), st),
+                   "fcd_pack_patients")
+    (oa, ob) = (_dev.zeros((N * U * 2,)), _dev.zeros((N * U * 2,)))
+    _lib.check(lib.fcd_unpack_patients(_dev.ptr(gathered), world, N, U, ch, _dev.ptr(oa), _dev.ptr(ob), st),
+               "fcd_unpack_patients")
+    nptest.assert_array_equal(oa.cpu().numpy().reshape(N, U, 2), a)
+    nptest.assert_array_equal(ob.cpu().numpy().reshape(N, U, 2), b)
