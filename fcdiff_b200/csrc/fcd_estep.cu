@@ -263,6 +263,174 @@ estep_qF_kernel(const double* __restrict__ S1, const double* __restrict__ S2,
     finish_rows();
 }
 
+// ------------------------------------------------------------------- K2 (coded)
+// The same E-step from the code plane the previous M-step left behind (fcd_streams.cu): between
+// that code pass and this E-step q_R has not changed, so code[c][u] still says which pair state l*
+// a peaked element has (one byte -> the constants of a running product, no peak-state decoding, no
+// queue) and the row's key list names the elements with a mixed region (evaluated densely after
+// the row, nine logs each with the real pair weights).  One persistent CTA of 16 warps per SM, warp
+// per row; per 128-patient segment three bulk copies (p_0, p_1, codes) into the warp's private ring.
+constexpr int kK2cSeg = 128;
+constexpr int kK2cStage = 2 * kK2cSeg * 8 + kK2cSeg;          // bytes: p_0, p_1, codes
+constexpr int kK2cMaxDepth = 5;
+constexpr size_t k2c_ring_bytes(int depth) { return (size_t)kStreamWarps * depth * (kK2cStage + 8); }
+
+template <bool FAST>
+__global__ void __launch_bounds__(kStreamThreads, 1)
+estep_qF_coded_kernel(const double* __restrict__ S1, const double* __restrict__ S2,
+                      const double* __restrict__ P, int64_t planeStride, int64_t C, int U, int64_t pitchU,
+                      const double* __restrict__ qR, const int32_t* __restrict__ nm,
+                      const uint8_t* __restrict__ code, int64_t pitchQ, const int32_t* __restrict__ counts,
+                      const unsigned long long* __restrict__ keys, const long long* __restrict__ rowoff,
+                      const __grid_constant__ ThetaDev th, const __grid_constant__ LogTabWindow tab, int depth,
+                      double* __restrict__ lqF, double* __restrict__ qF) {
+    extern __shared__ __align__(128) double s_dyn[];
+    __shared__ double2 s_lc[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* ring0 = reinterpret_cast<unsigned char*>(s_dyn + (FAST ? ((tab.n + 15) & ~15) : 0));
+    unsigned char* ring = ring0 + (size_t)warp * depth * kK2cStage;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring0 + (size_t)kStreamWarps * depth * kK2cStage) + warp * depth;
+    // the ring starts zeroed: lanes beyond the copied bytes of a short segment read stale but finite
+    // responsibilities (their code is forced to 3)
+    for (int i = lane; i < depth * kK2cStage / 16; i += 32) reinterpret_cast<int4*>(ring)[i] = make_int4(0, 0, 0, 0);
+    if (lane < depth) mbar_init(bars + lane, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // per-code constants {a_l, b_l}; code 3 is neutral: the factor 1 + 0 p = 1 exactly
+    if (threadIdx.x < 4) s_lc[threadIdx.x] = threadIdx.x < 3 ? make_double2(th.al[threadIdx.x], th.bl[threadIdx.x])
+                                                             : make_double2(1.0, 0.0);
+    __syncwarp();
+
+    const int nseg = (int)((pitchU + kK2cSeg - 1) / kK2cSeg);
+    const int64_t W = (int64_t)gridDim.x * kStreamWarps;
+    const int64_t c_first = (int64_t)blockIdx.x * kStreamWarps + warp;
+    const uint32_t ring_s = smem_u32(ring), bars_s = smem_u32(bars);
+    int64_t pc = c_first;                                    // next (row, segment) to issue
+    int ps = 0, pd = 0;
+    auto issue = [&]() {
+        if (pc >= C) return;
+        if (lane == 0) {
+            const int u0 = ps * kK2cSeg;
+            const uint32_t np = (uint32_t)(pitchU - u0 < kK2cSeg ? pitchU - u0 : kK2cSeg);      // even
+            const uint32_t cb = (np + 15) & ~15u;                                               // pitchQ % 16 == 0
+            const uint32_t st = ring_s + pd * kK2cStage, bar = bars_s + pd * 8;
+            const double* src = P + pc * pitchU + u0;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * np * 8 + cb) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(st), "l"(src), "r"(np * 8), "r"(bar) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(st + kK2cSeg * 8), "l"(src + planeStride), "r"(np * 8), "r"(bar) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(st + 2 * kK2cSeg * 8), "l"(code + pc * pitchQ + u0), "r"(cb), "r"(bar) : "memory");
+        }
+        if (++pd == depth) pd = 0;
+        if (++ps == nseg) {
+            ps = 0;
+            pc += W;
+        }
+    };
+#pragma unroll 1
+    for (int i = 0; i < depth; ++i) issue();
+    const double* s_tab = load_log_table<FAST>(tab, s_dyn);  // staged while the first segments are in flight
+
+    const double2* qR2 = reinterpret_cast<const double2*>(qR);
+    double acc[3] = {0.0, 0.0, 0.0};
+    double pr[2][3] = {{1.0, 1.0, 1.0}, {1.0, 1.0, 1.0}};
+    int nf = 0;
+    auto flush = [&]() {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (FAST) acc[i] += log_pos<FAST>(pr[0][i] * pr[1][i], s_tab);
+            pr[0][i] = pr[1][i] = 1.0;
+        }
+        nf = 0;
+    };
+    // an element with real pair weights: nine logs (fit.py:165-171 with fit.py:382-406)
+    auto weighted = [&](int64_t c, int u, int n, int m) {
+        const double2 qn = __ldg(qR2 + (int64_t)n * U + u), qm = __ldg(qR2 + (int64_t)m * U + u);
+        const double p0 = __ldg(P + c * pitchU + u), p1 = __ldg(P + planeStride + c * pitchU + u);
+        const double p3[3] = {p0, p1, (1.0 - p0) - p1};
+        double w[3];
+        pair_weights(qn, qm, w);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            double a = acc[k];
+#pragma unroll
+            for (int l = 0; l < 3; ++l) a = fma(w[l], fast_log<FAST>(mix_rel(th, l, p3[k]), s_tab), a);
+            acc[k] = a;
+        }
+    };
+    double keep[3] = {0.0, 0.0, 0.0};                        // row ends: see estep_qF_kernel
+    int64_t keep_c = -1;
+    int rows_done = 0;
+    auto finish_rows = [&]() {
+        if (keep_c >= 0) k2_finish(keep_c, keep, __ldg(S1 + keep_c), __ldg(S2 + keep_c), th, lqF, qF);
+        keep_c = -1;
+    };
+    int d = 0;
+    uint32_t phase = 0;
+    for (int64_t c = c_first; c < C; c += W) {
+        for (int s = 0; s < nseg; ++s) {
+            mbar_wait(bars + d, phase);
+            const unsigned char* st = ring + d * kK2cStage;
+#pragma unroll
+            for (int j = 0; j < kK2cSeg / 64; ++j) {
+                if (s * kK2cSeg + 64 * j < pitchU) {         // warp-uniform
+                    const double2 a0 = *reinterpret_cast<const double2*>(st + (64 * j + 2 * lane) * 8);
+                    const double2 a1 = *reinterpret_cast<const double2*>(st + kK2cSeg * 8 + (64 * j + 2 * lane) * 8);
+                    // beyond pitchU the stage holds stale (finite) responsibilities: force their code to 3
+                    const bool in = s * kK2cSeg + 64 * j + 2 * lane < pitchU;
+                    const uint32_t c2 = in ? *reinterpret_cast<const unsigned short*>(st + 2 * kK2cSeg * 8 + 64 * j + 2 * lane)
+                                           : 0x0303u;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const double2 k = s_lc[(c2 >> (8 * e)) & 0xff];
+                        const double p0 = e ? a0.y : a0.x, p1 = e ? a1.y : a1.x;
+                        const double p3[3] = {p0, p1, (1.0 - p0) - p1};
+                        if (FAST) {
+#pragma unroll
+                            for (int i = 0; i < 3; ++i) pr[e][i] *= fma(k.y, p3[i], k.x);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 3; ++i) acc[i] += log(fma(k.y, p3[i], k.x));
+                        }
+                    }
+                    if (++nf == kProdMax) flush();
+                }
+            }
+            __syncwarp();
+            issue();
+            if (++d == depth) {
+                d = 0;
+                phase ^= 1;
+            }
+        }
+        flush();
+        // the row's elements with real weights
+        const int v = __ldg(nm + c);
+        const int n = v & 0xffff, m = (v >> 16) & 0xffff;
+        const int cnt = __ldg(counts + c);
+        if (cnt == 3 * U) {                                  // the edge was unpeaked at the code pass: every element
+            for (int u = lane; u < U; u += 32) weighted(c, u, n, m);
+        } else if (cnt > 0) {
+            const unsigned long long* kr = keys + __ldg(rowoff + c);
+            for (int i = lane; i < cnt; i += 32) weighted(c, (int)(__ldg(kr + i) & 0xffffull), n, m);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) acc[k] = warp_sum(acc[k]);
+        if (lane == (rows_done & 31)) {
+            keep[0] = acc[0];
+            keep[1] = acc[1];
+            keep[2] = acc[2];
+            keep_c = c;
+        }
+        if ((++rows_done & 31) == 0) finish_rows();
+        acc[0] = acc[1] = acc[2] = 0.0;
+    }
+    finish_rows();
+}
+
 // ------------------------------------------------------ patient-major copy
 // btT[u - u0][c] = bt[c][u]; 32x32 tiles through padded shared memory so both
 // sides are coalesced.
@@ -820,6 +988,49 @@ int fcd_estep_qF(const double* S1, const double* S2, int32_t H,
     if (fast) FCD_K2(true); else FCD_K2(false);
 #undef FCD_K2
     return check_launch("fcd_estep_qF");
+}
+
+int fcd_estep_qF_coded(const double* S1, const double* S2, int32_t H,
+                       const double* P, int64_t planeStride, int64_t C, int32_t U, int64_t pitchU,
+                       const double* qR, int32_t N, const int32_t* nm,
+                       const uint8_t* code, int64_t pitchQ, const int32_t* counts, const uint64_t* keys,
+                       const int64_t* rowoff, const fcd_theta* theta_host, double* lqF, double* qF, void* stream) {
+    FCD_REQUIRE(theta_host != nullptr && S1 != nullptr && S2 != nullptr && P != nullptr && qR != nullptr &&
+                nm != nullptr && code != nullptr && counts != nullptr && keys != nullptr && rowoff != nullptr &&
+                lqF != nullptr, "fcd_estep_qF_coded: NULL argument");
+    FCD_REQUIRE(C >= 0 && U >= 1 && U < 65536 && pitchU >= U && N >= 2 && N < 65536, "fcd_estep_qF_coded: bad shape");
+    FCD_REQUIRE(((reinterpret_cast<uintptr_t>(P) | reinterpret_cast<uintptr_t>(code)) & 15) == 0 && pitchU % 2 == 0 &&
+                planeStride % 2 == 0 && pitchQ >= pitchU && pitchQ % 16 == 0,
+                "fcd_estep_qF_coded: planes / code must be 16-byte aligned (even pitchU, pitchQ % 16 == 0)");
+    if (C == 0) return 0;
+    const ThetaDev th = make_theta_dev(*theta_host, H);
+    cudaStream_t st = (cudaStream_t)stream;
+    LogTabWindow tab;
+    FCD_REQUIRE(log_table_window(th.epsl, th.al, st, tab, true), "fcd_estep_qF_coded: log table initialisation failed");
+    const bool fast = log_table_covers(th.epsl, th.al);
+    const size_t tbytes = fast ? (size_t)((tab.n + 15) & ~15) * sizeof(double) : 0;
+    int depth = kK2cMaxDepth;
+    while (depth > 2 && tbytes + k2c_ring_bytes(depth) > kSmemBudget) --depth;
+    FCD_REQUIRE(tbytes + k2c_ring_bytes(depth) <= kSmemBudget, "fcd_estep_qF_coded: shared memory budget exceeded");
+    const size_t smem = tbytes + k2c_ring_bytes(depth);
+    int64_t grid = (C + kStreamWarps - 1) / kStreamWarps;
+    if (grid > sm_count()) grid = sm_count();                       // one persistent CTA per SM
+#define FCD_K2C(F)                                                                                    \
+    do {                                                                                              \
+        static bool attr_set = false;                                                                 \
+        if (!attr_set) {                                                                              \
+            cudaFuncSetAttribute(estep_qF_coded_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 (int)kSmemBudget);                                                   \
+            attr_set = true;                                                                          \
+        }                                                                                             \
+        estep_qF_coded_kernel<F><<<(unsigned)grid, kStreamThreads, smem, st>>>(                       \
+            S1, S2, P, planeStride, C, U, pitchU, qR, nm, code, pitchQ, counts,                       \
+            reinterpret_cast<const unsigned long long*>(keys), reinterpret_cast<const long long*>(rowoff), th, tab, \
+            depth, lqF, qF);                                                                          \
+    } while (0)
+    if (fast) FCD_K2C(true); else FCD_K2C(false);
+#undef FCD_K2C
+    return check_launch("fcd_estep_qF_coded");
 }
 
 int fcd_transpose_patients(const double* bt, int64_t C, int32_t U, int64_t pitchU,

@@ -45,8 +45,8 @@ __global__ void __launch_bounds__(kBucketThreads)
 code_plane_kernel(const double* __restrict__ P, int64_t planeStride, double* __restrict__ PsE,
                   uint8_t* __restrict__ kcache,
                   const uint8_t* __restrict__ fstate, const uint8_t* __restrict__ rstate, int64_t pitchS,
-                  const int32_t* __restrict__ nm, int64_t C, int U, int64_t pitchU, uint8_t* __restrict__ code,
-                  int32_t* __restrict__ counts, long long* __restrict__ blocktot) {
+                  const int32_t* __restrict__ nm, int64_t C, int U, int64_t pitchU, int64_t pitchQ,
+                  uint8_t* __restrict__ code, int32_t* __restrict__ counts, long long* __restrict__ blocktot) {
     __shared__ int s_cnt[kRowBlock];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t cb = (int64_t)blockIdx.x * kRowBlock;
@@ -55,15 +55,15 @@ code_plane_kernel(const double* __restrict__ P, int64_t planeStride, double* __r
         int cnt = 0;
         if (c < C) {
             const int k = fstate[c];
-            unsigned short* crow = reinterpret_cast<unsigned short*>(code + c * pitchU);      // pitchU is even
+            unsigned short* crow = reinterpret_cast<unsigned short*>(code + c * pitchQ);      // pitchQ % 16 == 0
             if (k == kStateMixedF) {
-                for (int u = 2 * lane; u < pitchU; u += 64) crow[u >> 1] = 0x0303;
+                for (int u = 2 * lane; u < pitchQ; u += 64) crow[u >> 1] = 0x0303;
                 cnt = 3 * U;
             } else {
                 const int v = __ldg(nm + c);
                 if (k != kcache[c]) {                        // warp-uniform; rare once q_F has settled
                     const double* src = P + (int64_t)k * planeStride + c * pitchU;
-                    double* dst = PsE + c * pitchU;
+                    double* dst = PsE + c * pitchQ;
                     for (int64_t u = 2 * lane; u < pitchU; u += 64)
                         *reinterpret_cast<double2*>(dst + u) = ldg_stream2(src + u);
                     __syncwarp();
@@ -71,8 +71,8 @@ code_plane_kernel(const double* __restrict__ P, int64_t planeStride, double* __r
                 }
                 const uint8_t* rn = rstate + (int64_t)(v & 0xffff) * pitchS;
                 const uint8_t* rm = rstate + (int64_t)((v >> 16) & 0xffff) * pitchS;
-                // two patients per lane; the state rows are padded with 4 up to pitchS >= pitchU
-                for (int u = 2 * lane; u < pitchU; u += 64) {
+                // two patients per lane; the state rows are padded with 4 up to pitchS >= pitchQ
+                for (int u = 2 * lane; u < pitchQ; u += 64) {
                     const uint32_t sn2 = __ldg(reinterpret_cast<const unsigned short*>(rn + u));
                     const uint32_t sm2 = __ldg(reinterpret_cast<const unsigned short*>(rm + u));
                     const int c0 = pair_code(sn2 & 0xff, sm2 & 0xff), c1 = pair_code(sn2 >> 8, sm2 >> 8);
@@ -148,8 +148,9 @@ plane_sum_kernel(const double* __restrict__ X, int64_t C, int U, int64_t pitchU,
 // operands of a record are gathered by record_weights_kernel, one thread per record.
 __global__ void __launch_bounds__(kBucketThreads, 4)
 record_keys_kernel(const uint8_t* __restrict__ code, const uint8_t* __restrict__ fstate,
-                   int64_t C, int U, int64_t pitchU, const int32_t* __restrict__ counts,
-                   const long long* __restrict__ blockoff, unsigned long long* __restrict__ keys) {
+                   int64_t C, int U, int64_t pitchQ, const int32_t* __restrict__ counts,
+                   const long long* __restrict__ blockoff, unsigned long long* __restrict__ keys,
+                   long long* __restrict__ rowoff) {
     __shared__ long long s_off[kRowBlock];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
@@ -165,7 +166,10 @@ record_keys_kernel(const uint8_t* __restrict__ code, const uint8_t* __restrict__
                 const long long w = __shfl_up_sync(0xffffffffu, v, o);
                 if (r >= o) v += w;
             }
-            if (r < kRowBlock) s_off[r] = blockoff[blk] + v - mine;
+            if (r < kRowBlock) {
+                s_off[r] = blockoff[blk] + v - mine;
+                if (cb + r < C) rowoff[cb + r] = s_off[r];   // kept for the next E-step (fcd_estep_qF_coded)
+            }
         }
         __syncthreads();
         for (int r = warp; r < kRowBlock; r += kBucketThreads / 32) {
@@ -183,7 +187,7 @@ record_keys_kernel(const uint8_t* __restrict__ code, const uint8_t* __restrict__
                 }
                 continue;
             }
-            const unsigned short* crow = reinterpret_cast<const unsigned short*>(code + c * pitchU);
+            const unsigned short* crow = reinterpret_cast<const unsigned short*>(code + c * pitchQ);
             uint32_t off = 0;
             // batches of 8 x 64 patients: all code loads first, then positions (ballots) and stores
             for (int ub = 0; ub < U; ub += 512) {
@@ -216,8 +220,9 @@ record_keys_kernel(const uint8_t* __restrict__ code, const uint8_t* __restrict__
 // (Lsum = sum of L over all local elements, fcd_plane_sum: the coded elements have weight exactly 1).
 __global__ void __launch_bounds__(kBucketThreads)
 record_weights_kernel(const unsigned long long* __restrict__ keys, long long nd, const double* __restrict__ P,
-                      int64_t planeStride, const double* __restrict__ PsE, const double* __restrict__ L,
-                      int64_t pitchU, const double* __restrict__ Lsum, const double* __restrict__ qF,
+                      int64_t planeStride, const double* __restrict__ PsE, int64_t pitchQ,
+                      const double* __restrict__ L, int64_t pitchU, const double* __restrict__ Lsum,
+                      const double* __restrict__ qF,
                       const double* __restrict__ qR, int U, const int32_t* __restrict__ nm,
                       Record* __restrict__ D, double* __restrict__ out, double* __restrict__ ws) {
     const double2* qR2 = reinterpret_cast<const double2*>(qR);
@@ -228,10 +233,9 @@ record_weights_kernel(const unsigned long long* __restrict__ keys, long long nd,
         const int u = (int)(key & 0xffffull), tag = (int)(key >> 48);
         const int64_t c = (int64_t)((key >> 16) & 0xffffffffull);
         const int64_t e = c * pitchU + u;
-        const double lv = __ldg(L + e);
         const int v = __ldg(nm + c);
         Record rec;
-        rec.p = tag == 0 ? __ldg(PsE + e) : ldg_stream1(P + (int64_t)(tag - 1) * planeStride + e);
+        rec.p = tag == 0 ? __ldg(PsE + c * pitchQ + u) : ldg_stream1(P + (int64_t)(tag - 1) * planeStride + e);
         double w[3];
         pair_weights(__ldg(qR2 + (int64_t)(v & 0xffff) * U + u), __ldg(qR2 + (int64_t)((v >> 16) & 0xffff) * U + u), w);
         double scale = 1.0, cscale = 1.0;
@@ -240,8 +244,11 @@ record_weights_kernel(const unsigned long long* __restrict__ keys, long long nd,
             scale = qf[tag - 1];
             cscale = tag == 1 ? qf[0] + qf[1] + qf[2] : 0.0;  // the element's theta-free term is counted once
         }
-        // the element's theta-free term is counted once (tag <= 1), and it leaves the weight-1 sum
-        cs = fma(cscale * (w[0] + w[1] + w[2]) - (tag <= 1 ? 1.0 : 0.0), lv, cs);
+        // the element's theta-free term is counted once (tag <= 1), and it leaves the weight-1 sum.  For
+        // normalised posteriors the coefficient is a rounding residue: below 2^-50 the product with
+        // L is below the rounding of the sum and L is not fetched (a 64-byte DRAM access per record)
+        const double coef = cscale * (w[0] + w[1] + w[2]) - (tag <= 1 ? 1.0 : 0.0);
+        if (fabs(coef) > 8.881784197001252e-16) cs = fma(coef, __ldg(L + e), cs);
         rec.w0 = scale * w[0];
         rec.w1 = scale * w[1];
         rec.w2 = scale * w[2];
@@ -467,15 +474,18 @@ int fcd_plane_sum(const double* X, int64_t C, int32_t U, int64_t pitchU, double*
     return check_launch("fcd_plane_sum");
 }
 
+int64_t fcd_code_pitch(int32_t U) { return ((int64_t)U + 15) & ~(int64_t)15; }
+
 int fcd_code_plane(const double* P, int64_t planeStride, int64_t C, int32_t U, int64_t pitchU,
                    const uint8_t* fstate, const uint8_t* rstate, int64_t pitchS, const int32_t* nm,
-                   double* PsE, uint8_t* kcache, uint8_t* code, int32_t* counts, int64_t* blockoff,
+                   double* PsE, uint8_t* kcache, uint8_t* code, int64_t pitchQ, int32_t* counts, int64_t* blockoff,
                    double* total1, void* stream) {
     FCD_REQUIRE(P != nullptr && fstate != nullptr && rstate != nullptr && nm != nullptr && PsE != nullptr &&
                 kcache != nullptr && code != nullptr && counts != nullptr && blockoff != nullptr && total1 != nullptr,
                 "fcd_code_plane: NULL argument");
-    FCD_REQUIRE(C >= 1 && U >= 1 && pitchU >= U && pitchU % 2 == 0 && planeStride % 2 == 0 && pitchS >= pitchU &&
-                pitchS % 2 == 0, "fcd_code_plane: bad shape (even pitches, pitchS >= pitchU)");
+    FCD_REQUIRE(C >= 1 && U >= 1 && pitchU >= U && pitchU % 2 == 0 && planeStride % 2 == 0 && pitchQ >= pitchU &&
+                pitchQ % 16 == 0 && pitchS >= pitchQ && pitchS % 2 == 0,
+                "fcd_code_plane: bad shape (even pitches, pitchQ % 16 == 0, pitchS >= pitchQ >= pitchU)");
     FCD_REQUIRE(((reinterpret_cast<uintptr_t>(P) | reinterpret_cast<uintptr_t>(PsE) | reinterpret_cast<uintptr_t>(code)) & 15) == 0 &&
                 (reinterpret_cast<uintptr_t>(rstate) & 1) == 0 && (reinterpret_cast<uintptr_t>(blockoff) & 7) == 0,
                 "fcd_code_plane: planes / code must be 16-byte aligned");
@@ -484,23 +494,24 @@ int fcd_code_plane(const double* P, int64_t planeStride, int64_t C, int32_t U, i
     // blockoff doubles as the block totals' storage: [nblocks] totals followed by [nblocks] offsets
     long long* bt = reinterpret_cast<long long*>(blockoff);
     code_plane_kernel<<<(unsigned)nblocks, kBucketThreads, 0, st>>>(P, planeStride, PsE, kcache, fstate, rstate, pitchS,
-                                                                    nm, C, U, pitchU, code, counts, bt);
+                                                                    nm, C, U, pitchU, pitchQ, code, counts, bt);
     int rc = check_launch("fcd_code_plane");
     if (rc) return rc;
     record_scan_kernel<<<1, 1024, 0, st>>>(bt, nblocks, bt + nblocks, total1);
     return check_launch("fcd_code_plane(scan)");
 }
 
-int fcd_code_records(const double* P, int64_t planeStride, const double* PsE, const uint8_t* code,
+int fcd_code_records(const double* P, int64_t planeStride, const double* PsE, const uint8_t* code, int64_t pitchQ,
                      const double* L, const double* Lsum, int64_t C, int32_t U, int64_t pitchU,
                      const double* qF, const uint8_t* fstate, const double* qR, int32_t N, const int32_t* nm,
-                     const int32_t* counts, const int64_t* blockoff, uint64_t* keys, double* D, int64_t nd,
-                     double* out1, double* ws, void* stream) {
+                     const int32_t* counts, const int64_t* blockoff, uint64_t* keys, int64_t* rowoff, double* D,
+                     int64_t nd, double* out1, double* ws, void* stream) {
     FCD_REQUIRE(P != nullptr && PsE != nullptr && code != nullptr && L != nullptr && Lsum != nullptr && qF != nullptr &&
                 fstate != nullptr && qR != nullptr && nm != nullptr && counts != nullptr && blockoff != nullptr &&
-                keys != nullptr && D != nullptr && out1 != nullptr && ws != nullptr, "fcd_code_records: NULL argument");
-    FCD_REQUIRE(C >= 1 && C < (1ll << 32) && U >= 1 && U < 65536 && pitchU >= U && pitchU % 2 == 0 && N >= 2 &&
-                N < 65536 && nd >= 0, "fcd_code_records: bad shape");
+                keys != nullptr && rowoff != nullptr && D != nullptr && out1 != nullptr && ws != nullptr,
+                "fcd_code_records: NULL argument");
+    FCD_REQUIRE(C >= 1 && C < (1ll << 32) && U >= 1 && U < 65536 && pitchU >= U && pitchU % 2 == 0 &&
+                pitchQ >= pitchU && pitchQ % 16 == 0 && N >= 2 && N < 65536 && nd >= 0, "fcd_code_records: bad shape");
     FCD_REQUIRE((reinterpret_cast<uintptr_t>(D) & 31) == 0 && (reinterpret_cast<uintptr_t>(keys) & 7) == 0,
                 "fcd_code_records: records must be 32-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
@@ -510,8 +521,8 @@ int fcd_code_records(const double* P, int64_t planeStride, const double* PsE, co
         int64_t grid = nblocks;                              // persistent: the resident CTAs share the row blocks
         if (grid > (int64_t)sm_count() * 4) grid = (int64_t)sm_count() * 4;
         record_keys_kernel<<<(unsigned)grid, kBucketThreads, 0, st>>>(
-            code, fstate, C, U, pitchU, counts, reinterpret_cast<const long long*>(blockoff) + nblocks,
-            reinterpret_cast<unsigned long long*>(keys));
+            code, fstate, C, U, pitchQ, counts, reinterpret_cast<const long long*>(blockoff) + nblocks,
+            reinterpret_cast<unsigned long long*>(keys), reinterpret_cast<long long*>(rowoff));
         rc = check_launch("fcd_code_records(keys)");
         if (rc) return rc;
     }
@@ -519,7 +530,7 @@ int fcd_code_records(const double* P, int64_t planeStride, const double* PsE, co
     if (rgrid > (int64_t)sm_count() * 8) rgrid = (int64_t)sm_count() * 8;
     if (rgrid < 1) rgrid = 1;
     record_weights_kernel<<<(unsigned)rgrid, kBucketThreads, 0, st>>>(
-        reinterpret_cast<const unsigned long long*>(keys), nd, P, planeStride, PsE, L, pitchU, Lsum, qF, qR, U, nm,
+        reinterpret_cast<const unsigned long long*>(keys), nd, P, planeStride, PsE, pitchQ, L, pitchU, Lsum, qF, qR, U, nm,
         reinterpret_cast<Record*>(D), out1, ws);
     return check_launch("fcd_code_records");
 }

@@ -179,6 +179,7 @@ class UnsharedRegionFit(object):
         self.n_edges = None           # global edge count when b / bt are device edge shards
         self.optimise_theta_sub = True
         self.update_mu_sigma = False  # re-estimate mu, sigma (disabled in the reference, fit.py:232-237)
+        self.coded_estep = True       # K2 from the previous M-step's code plane when it still describes q_R
         self.fused_sweep = False      # K2b: weights computed inside the sweep (no WT tensor; reference lookup, N <= 1024)
         self.elm_path = "auto"        # K3b form: "streams" | "tiered" | "auto" (streams unless most elements are unpeaked)
         self.convergence_rule = "reference"
@@ -421,6 +422,7 @@ class UnsharedRegionFit(object):
         lib = _lib.load()
         (N, H, U) = self._dims
         (c0, Cl, pitchU) = (inp['c0'], inp['Cl'], inp['pitchU'])
+        inp['code_verR'] = None                     # the key lists are rebuilt below (or not at all)
         if Cl == 0:
             if self.shards is not None and self.elm_path != "tiered":
                 self.shards.any_rank(True)     # keep the collective sequence of _build_streams aligned
@@ -429,11 +431,13 @@ class UnsharedRegionFit(object):
         (_, qR) = self._mR.get_dev()
         (fstate, rstate) = (self._mF.get_state(), self._mR.get_state())
         stream = _dev.stream()
+        pitchQ = int(lib.fcd_code_pitch(U))        # code rows 16-byte aligned; PsE shares the pitch
         if inp.get('PsE') is None:
-            inp['PsE'] = _dev.zeros((Cl, pitchU))
+            inp['PsE'] = _dev.zeros((Cl, pitchQ))
             inp['kcE'] = torch.full((Cl,), 255, dtype=torch.uint8, device=_dev.device())
-            inp['code'] = _dev.empty((Cl * pitchU + 256,), torch.uint8)
+            inp['code'] = _dev.empty((Cl * pitchQ + 256,), torch.uint8)
             inp['bk_counts'] = _dev.empty((Cl,), torch.int32)
+            inp['bk_rowoff'] = _dev.empty((Cl,), torch.int64)
             inp['bk_offs'] = _dev.empty((2 * int(lib.fcd_bucket_blocks(Cl)),), torch.int64)
         tot = self._result(1, tag="records")
         planeStride = max(Cl, 1) * pitchU
@@ -441,8 +445,8 @@ class UnsharedRegionFit(object):
             _lib.check(lib.fcd_code_plane(
                 _dev.ptr(inp['P']), planeStride, Cl, U, pitchU, _dev.ptr(fstate[c0:]), _dev.ptr(rstate),
                 rstate.shape[1], _dev.ptr(inp['nm']), _dev.ptr(inp['PsE']), _dev.ptr(inp['kcE']),
-                _dev.ptr(inp['code']), _dev.ptr(inp['bk_counts']), _dev.ptr(inp['bk_offs']), _dev.ptr(tot.dev),
-                stream), "fcd_code_plane")
+                _dev.ptr(inp['code']), pitchQ, _dev.ptr(inp['bk_counts']), _dev.ptr(inp['bk_offs']),
+                _dev.ptr(tot.dev), stream), "fcd_code_plane")
         nd = int(tot.read(stream)[0])
         use_tiered = self.elm_path == "auto" and nd * 4 > Cl * U
         if self.shards is not None:            # the ranks must take the same form: its collectives differ
@@ -458,12 +462,14 @@ class UnsharedRegionFit(object):
                                          _dev.ptr(_dev.workspace()), stream), "fcd_plane_sum")
         with _dev.timed(self.profile, "K3b_records"):
             _lib.check(lib.fcd_code_records(
-                _dev.ptr(inp['P']), planeStride, _dev.ptr(inp['PsE']), _dev.ptr(inp['code']), _dev.ptr(inp['L']),
-                _dev.ptr(inp['Lsum']), Cl, U, pitchU, _dev.ptr(qF[c0 * 3:]), _dev.ptr(fstate[c0:]), _dev.ptr(qR), N,
+                _dev.ptr(inp['P']), planeStride, _dev.ptr(inp['PsE']), _dev.ptr(inp['code']), pitchQ,
+                _dev.ptr(inp['L']), _dev.ptr(inp['Lsum']), Cl, U, pitchU, _dev.ptr(qF[c0 * 3:]), _dev.ptr(fstate[c0:]), _dev.ptr(qR), N,
                 _dev.ptr(inp['nm']), _dev.ptr(inp['bk_counts']), _dev.ptr(inp['bk_offs']), _dev.ptr(inp['bk_K']),
-                _dev.ptr(inp['bk_D']), nd, _dev.ptr(res4.dev[3:]), _dev.ptr(_dev.workspace()), stream),
-                "fcd_code_records")
-        return (_dev.ptr(inp['PsE']), _dev.ptr(inp['code']), Cl * pitchU, _dev.ptr(inp['bk_D']), nd)
+                _dev.ptr(inp['bk_rowoff']), _dev.ptr(inp['bk_D']), nd, _dev.ptr(res4.dev[3:]),
+                _dev.ptr(_dev.workspace()), stream), "fcd_code_records")
+        inp['code_verR'] = self._mR.version         # codes and key lists describe this q_R: the next E-step may use them
+        inp['pitchQ'] = pitchQ
+        return (_dev.ptr(inp['PsE']), _dev.ptr(inp['code']), Cl * pitchQ, _dev.ptr(inp['bk_D']), nd)
 
     def _theta(self, use_snapshot=True):
         m = self.model
@@ -667,6 +673,19 @@ class UnsharedRegionFit(object):
         (lqF, qF) = (lqF_buf[:C * 3], qF_buf[:C * 3])
         th = self._theta()
         self._wait_healthy(inp)
+        if self.coded_estep and Cl > 0 and inp.get('code_verR') == self._mR.version and inp.get('PsE') is not None:
+            # the code plane and key lists of the last M-step still describe q_R (fcd_estep_qF_coded)
+            with _dev.timed(self.profile, "K2_estep_qF"):
+                _lib.check(lib.fcd_estep_qF_coded(
+                    _dev.ptr(inp['S1']), _dev.ptr(inp['S2']), H, _dev.ptr(inp['P']), max(Cl, 1) * inp['pitchU'],
+                    Cl, U, inp['pitchU'], _dev.ptr(qR), N, _dev.ptr(inp['nm']), _dev.ptr(inp['code']), inp['pitchQ'],
+                    _dev.ptr(inp['bk_counts']), _dev.ptr(inp['bk_K']), _dev.ptr(inp['bk_rowoff']),
+                    ctypes.byref(th), _dev.ptr(lqF[c0 * 3:]), _dev.ptr(qF[c0 * 3:]), _dev.stream()),
+                    "fcd_estep_qF_coded")
+            if self.shards is not None:
+                self.shards.allgather_edges(lqF_buf, qF_buf, C)
+            self._mF.set_dev(lqF, qF, (C, 1, 3))
+            return
         with _dev.timed(self.profile, "K2_estep_qF"):
             _lib.check(lib.fcd_estep_qF(
                 _dev.ptr(inp['S1']), _dev.ptr(inp['S2']), H, _dev.ptr(inp['P']), max(Cl, 1) * inp['pitchU'],

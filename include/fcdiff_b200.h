@@ -160,6 +160,18 @@ FCD_API int fcd_estep_qF(const double* S1, const double* S2, int32_t H,
                  const double* qR, const uint8_t* rstate, int64_t pitchS, int32_t N, const int32_t* nm,
                  const fcd_theta* theta_host, double* lqF, double* qF, void* stream);
 
+/* The same E-step driven by the code pass of the previous M-step (fcd_code_plane / fcd_code_records:
+ * valid while q_R has not changed since): the coded elements need no peak-state decoding and no
+ * queue -- one code byte selects the constants of a running product -- and the elements with a
+ * mixed region are taken from the row's key list.  code / counts / keys / rowoff as written by the
+ * code pass for the same local rows; rows whose edge was unpeaked then (counts[c] == 3 U) are
+ * evaluated in full. */
+FCD_API int fcd_estep_qF_coded(const double* S1, const double* S2, int32_t H,
+                       const double* P, int64_t planeStride, int64_t C, int32_t U, int64_t pitchU,
+                       const double* qR, int32_t N, const int32_t* nm,
+                       const uint8_t* code, int64_t pitchQ, const int32_t* counts, const uint64_t* keys,
+                       const int64_t* rowoff, const fcd_theta* theta_host, double* lqF, double* qF, void* stream);
+
 /* Patient-major copy of an edge-major plane: dst[u - u0][c] = src[c][u]
  * for u in [u0, u0+Ul), c in [0, C).  Built once per fit. */
 FCD_API int fcd_transpose_patients(const double* bt, int64_t C, int32_t U, int64_t pitchU,
@@ -242,9 +254,10 @@ FCD_API int fcd_elm_const(const double* L, int64_t C, int32_t U, int64_t pitchU,
  * E-steps the optimiser evaluates E_lM(eta, epsilon) many times with q_F, q_R fixed
  * (fit.py:228-241): the code pass turns the planes into what an evaluation needs
  * and nothing else --
- *   PsE  [C][pitchU] f64: responsibility of each edge's dominant state (rows re-gathered
+ *   PsE  [C][pitchQ] f64: responsibility of each edge's dominant state (rows re-gathered
  *        from P only when kcache[c] != fstate[c]; kcache starts at 255, PsE zero-filled);
- *   code [C][pitchU] u8 (+ 16 bytes of slack): l* in 0..2 for elements whose edge and
+ *        pitchQ = fcd_code_pitch(U): U rounded up to 16, so that code rows are 16-byte aligned;
+ *   code [C][pitchQ] u8 (+ 16 bytes of slack): l* in 0..2 for elements whose edge and
  *        regions are peaked (weight exactly 1, one log), 3 for all others;
  *   records {p, w_0, w_1, w_2} (32 bytes) for all other elements, nd of them
  * -- and fcd_elm_coded reduces them: 9 bytes per edge-patient per evaluation, no row
@@ -253,22 +266,25 @@ FCD_API int fcd_elm_const(const double* L, int64_t C, int32_t U, int64_t pitchU,
  *   fcd_code_plane: refreshes PsE, writes code, counts[c] = records of row c (int32),
  *     blockoff: scratch of 2 * fcd_bucket_blocks(C) int64 (totals and exclusive prefix
  *     sums of blocks of 16 rows), total1[0] = nd (as a double);
- *   fcd_code_records: D receives the nd records (keys: scratch of nd uint64); out1[0] = the theta-free part of E_lM
+ *   fcd_code_records: D receives the nd records; keys [nd] uint64 = (tag << 48 | c << 16 | u) of every
+ *     record and rowoff [C] int64 = first key of each row are kept for fcd_estep_qF_coded (not written
+ *     when nd == 0); out1[0] = the theta-free part of E_lM
  *     (same value as fcd_elm_const), formed as Lsum[0] (device, from fcd_plane_sum)
  *     corrected by the record elements only;
- *   fcd_elm_coded: nE = C * pitchU elements of PsE / code; out3 as fcd_elm_obj_grad. */
+ *   fcd_elm_coded: nE = C * pitchQ elements of PsE / code; out3 as fcd_elm_obj_grad. */
 FCD_API int64_t fcd_bucket_blocks(int64_t C);
+FCD_API int64_t fcd_code_pitch(int32_t U);
 FCD_API int fcd_plane_sum(const double* X, int64_t C, int32_t U, int64_t pitchU, double* out1, double* ws,
                   void* stream);
 FCD_API int fcd_code_plane(const double* P, int64_t planeStride, int64_t C, int32_t U, int64_t pitchU,
                    const uint8_t* fstate, const uint8_t* rstate, int64_t pitchS, const int32_t* nm,
-                   double* PsE, uint8_t* kcache, uint8_t* code, int32_t* counts, int64_t* blockoff,
+                   double* PsE, uint8_t* kcache, uint8_t* code, int64_t pitchQ, int32_t* counts, int64_t* blockoff,
                    double* total1, void* stream);
 FCD_API int fcd_code_records(const double* P, int64_t planeStride, const double* PsE, const uint8_t* code,
-                     const double* L, const double* Lsum, int64_t C, int32_t U, int64_t pitchU,
+                     int64_t pitchQ, const double* L, const double* Lsum, int64_t C, int32_t U, int64_t pitchU,
                      const double* qF, const uint8_t* fstate, const double* qR, int32_t N, const int32_t* nm,
-                     const int32_t* counts, const int64_t* blockoff, uint64_t* keys, double* D, int64_t nd,
-                     double* out1, double* ws, void* stream);
+                     const int32_t* counts, const int64_t* blockoff, uint64_t* keys, int64_t* rowoff, double* D,
+                     int64_t nd, double* out1, double* ws, void* stream);
 FCD_API int fcd_elm_coded(const double* PsE, const uint8_t* code, int64_t nE, const double* D, int64_t nd,
                   const fcd_theta* theta_host, int32_t want_grad, double* out3, double* ws, void* stream);
 

@@ -3,11 +3,12 @@
 # and one --set full capture of the hot kernels of the same command.  Outputs land in gpurun_out/.
 set -o pipefail
 mkdir -p gpurun_out
+TAG=${1:-r01n}
 CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline"
 $CMD > gpurun_out/plain_bench.json 2> gpurun_out/plain_bench.err || { echo "plain run failed"; tail -5 gpurun_out/plain_bench.err; exit 1; }
-ncu --metrics gpu__time_duration.sum --clock-control none -s 0 -c 400 --csv --log-file gpurun_out/launches_r01.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -s 0 -c 600 --csv --log-file gpurun_out/launches_$TAG.csv \
     $CMD > gpurun_out/ncu_launches.log 2>&1
 ncu --set full --clock-control none --import-source on \
-    -k regex:"elm_streams|estep_qF|sweep_kernel|region_weights|bucket_fill|bucket_count|bucket_records|resp_cache" -s 40 -c 12 \
-    -o gpurun_out/prof_r01_final -f $CMD > gpurun_out/ncu_full.log 2>&1
+    -k regex:"elm_coded|estep_qF|sweep_kernel|region_weights|code_plane|record_keys|record_weights" -s 44 -c 14 \
+    -o gpurun_out/prof_$TAG -f $CMD > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log

@@ -30,15 +30,15 @@ def sync():
 def code_plane():
     _lib.check(lib.fcd_code_plane(_dev.ptr(inp['P']), planeStride, Cl, U, pitchU, _dev.ptr(fstate[c0:]), _dev.ptr(rstate),
                                   rstate.shape[1], _dev.ptr(inp['nm']), _dev.ptr(inp['PsE']), _dev.ptr(inp['kcE']),
-                                  _dev.ptr(inp['code']), _dev.ptr(inp['bk_counts']), _dev.ptr(inp['bk_offs']),
+                                  _dev.ptr(inp['code']), inp['pitchQ'], _dev.ptr(inp['bk_counts']), _dev.ptr(inp['bk_offs']),
                                   _dev.ptr(tot.dev), stream))
 
 
 def records(nd):
-    _lib.check(lib.fcd_code_records(_dev.ptr(inp['P']), planeStride, _dev.ptr(inp['PsE']), _dev.ptr(inp['code']),
+    _lib.check(lib.fcd_code_records(_dev.ptr(inp['P']), planeStride, _dev.ptr(inp['PsE']), _dev.ptr(inp['code']), inp['pitchQ'],
                                     _dev.ptr(inp['L']), _dev.ptr(inp['Lsum']), Cl, U, pitchU, _dev.ptr(qF[c0 * 3:]),
                                     _dev.ptr(fstate[c0:]), _dev.ptr(qR), N, _dev.ptr(inp['nm']), _dev.ptr(inp['bk_counts']),
-                                    _dev.ptr(inp['bk_offs']), _dev.ptr(inp['bk_K']), _dev.ptr(inp['bk_D']), nd, _dev.ptr(res4.dev[3:]),
+                                    _dev.ptr(inp['bk_offs']), _dev.ptr(inp['bk_K']), _dev.ptr(inp['bk_rowoff']), _dev.ptr(inp['bk_D']), nd, _dev.ptr(res4.dev[3:]),
                                     _dev.ptr(_dev.workspace()), stream))
 
 

@@ -31,6 +31,8 @@ def test_code_plane_and_evaluator_match_numpy(N, U):
     C = N * (N - 1) // 2
     pitchU = U + (U & 1)
     pitchS = (U + 255) // 256 * 256
+    pitchQ = int(lib.fcd_code_pitch(U))
+    assert pitchQ % 16 == 0 and pitchU <= pitchQ <= pitchS
     P = rng.dirichlet([1.0, 1.0, 1.0], size=(C, pitchU)).transpose(2, 0, 1).copy()      # [3][C][pitchU]
     L = rng.randn(C, pitchU)
     fstate = rng.choice([0, 1, 2, 3], size=C, p=[0.3, 0.3, 0.3, 0.1]).astype(np.uint8)
@@ -51,18 +53,18 @@ def test_code_plane_and_evaluator_match_numpy(N, U):
     fs = torch.from_numpy(fstate).cuda()
     rs = torch.from_numpy(rstate).cuda()
     nmd = torch.from_numpy(nm).cuda()
-    PsE = _dev.zeros((C, pitchU))
+    PsE = _dev.zeros((C, pitchQ))
     kc = torch.full((C,), 255, dtype=torch.uint8, device="cuda")
-    code = _dev.empty((C * pitchU + 256,), torch.uint8)
+    code = _dev.empty((C * pitchQ + 256,), torch.uint8)
     counts = _dev.empty((C,), torch.int32)
     offs = _dev.empty((2 * int(lib.fcd_bucket_blocks(C)),), torch.int64)
     tot = _dev.zeros((1,))
     st = _dev.stream()
     _lib.check(lib.fcd_code_plane(_dev.ptr(d['P']), C * pitchU, C, U, pitchU, _dev.ptr(fs), _dev.ptr(rs), pitchS,
-                                  _dev.ptr(nmd), _dev.ptr(PsE), _dev.ptr(kc), _dev.ptr(code), _dev.ptr(counts),
+                                  _dev.ptr(nmd), _dev.ptr(PsE), _dev.ptr(kc), _dev.ptr(code), pitchQ, _dev.ptr(counts),
                                   _dev.ptr(offs), _dev.ptr(tot), st), "fcd_code_plane")
     # ---- NumPy restatement of the code pass
-    want_code = np.full((C, pitchU), 3, np.uint8)
+    want_code = np.full((C, pitchQ), 3, np.uint8)
     want_cnt = np.zeros(C, np.int64)
     for c in range(C):
         (n, m) = util.c_to_nm(c)
@@ -72,7 +74,7 @@ def test_code_plane_and_evaluator_match_numpy(N, U):
         for u in range(U):
             want_code[c, u] = _pair_code(int(rstate[n, u]), int(rstate[m, u]))
         want_cnt[c] = int((want_code[c, :U] == 3).sum())
-    got_code = code[:C * pitchU].cpu().numpy().reshape(C, pitchU)
+    got_code = code[:C * pitchQ].cpu().numpy().reshape(C, pitchQ)
     nptest.assert_array_equal(got_code, want_code)
     nptest.assert_array_equal(counts.cpu().numpy(), want_cnt)
     nd = int(tot.cpu().numpy()[0])
@@ -80,7 +82,8 @@ def test_code_plane_and_evaluator_match_numpy(N, U):
     got_PsE = PsE.cpu().numpy()
     for c in range(C):
         if fstate[c] < 3:
-            nptest.assert_array_equal(got_PsE[c], P[fstate[c], c])
+            nptest.assert_array_equal(got_PsE[c, :pitchU], P[fstate[c], c])
+            assert not got_PsE[c, pitchU:].any()
     nptest.assert_array_equal(kc.cpu().numpy()[fstate < 3], fstate[fstate < 3])
 
     # ---- records + evaluation against the plain triple sum (fit.py:489-511, 600-697)
@@ -90,14 +93,15 @@ def test_code_plane_and_evaluator_match_numpy(N, U):
     nptest.assert_allclose(Lsum.cpu().numpy()[0], L[:, :U].sum(), rtol=1e-12, atol=1e-9)
     D = _dev.empty((4 * max(nd, 1),))
     K = _dev.empty((max(nd, 1),), torch.int64)
+    RO = _dev.empty((C,), torch.int64)
     out = _dev.zeros((4,))
-    _lib.check(lib.fcd_code_records(_dev.ptr(d['P']), C * pitchU, _dev.ptr(PsE), _dev.ptr(code), _dev.ptr(d['L']),
+    _lib.check(lib.fcd_code_records(_dev.ptr(d['P']), C * pitchU, _dev.ptr(PsE), _dev.ptr(code), pitchQ, _dev.ptr(d['L']),
                                     _dev.ptr(Lsum), C, U, pitchU, _dev.ptr(d['qF']), _dev.ptr(fs), _dev.ptr(d['qR']), N,
-                                    _dev.ptr(nmd), _dev.ptr(counts), _dev.ptr(offs), _dev.ptr(K), _dev.ptr(D), nd,
+                                    _dev.ptr(nmd), _dev.ptr(counts), _dev.ptr(offs), _dev.ptr(K), _dev.ptr(RO), _dev.ptr(D), nd,
                                     _dev.ptr(out[3:]), _dev.ptr(ws), st), "fcd_code_records")
     (eta, eps) = (0.37, 0.12)
     th = _lib.make_theta(0.1, eta, eps, [0.2, 0.5, 0.3], [-0.1, 0.0, 0.1], [0.1, 0.1, 0.1])
-    _lib.check(lib.fcd_elm_coded(_dev.ptr(PsE), _dev.ptr(code), C * pitchU, _dev.ptr(D), nd, ctypes.byref(th), 1,
+    _lib.check(lib.fcd_elm_coded(_dev.ptr(PsE), _dev.ptr(code), C * pitchQ, _dev.ptr(D), nd, ctypes.byref(th), 1,
                                  _dev.ptr(out), _dev.ptr(ws), st), "fcd_elm_coded")
     got = out.cpu().numpy()
     epsl = np.array([1 - eps, eps, eta * eps + (1 - eta) * (1 - eps)])
@@ -122,6 +126,36 @@ def test_code_plane_and_evaluator_match_numpy(N, U):
     nptest.assert_allclose(got[3], const, rtol=1e-11, atol=1e-10)
     nptest.assert_allclose(got[1], -(2 * eps - 1) * gh, rtol=0, atol=1e-10 * scale)
     nptest.assert_allclose(got[2], -ge, rtol=0, atol=1e-10 * scale)
+
+    # ---- the E-step driven by the same code plane / key lists (fit.py:157-174)
+    H = 6
+    (S1, S2) = (rng.randn(C), np.abs(rng.randn(C)) + 1.0)
+    (lqF_c, qF_c) = (_dev.zeros((C * 3,)), _dev.zeros((C * 3,)))
+    (S1d, S2d) = (_dev.upload(S1), _dev.upload(S2))
+    _lib.check(lib.fcd_estep_qF_coded(_dev.ptr(S1d), _dev.ptr(S2d), H, _dev.ptr(d['P']), C * pitchU, C, U, pitchU,
+                                      _dev.ptr(d['qR']), N, _dev.ptr(nmd), _dev.ptr(code), pitchQ, _dev.ptr(counts),
+                                      _dev.ptr(K), _dev.ptr(RO), ctypes.byref(th), _dev.ptr(lqF_c), _dev.ptr(qF_c), st),
+               "fcd_estep_qF_coded")
+    (lqF_p, qF_p) = (_dev.zeros((C * 3,)), _dev.zeros((C * 3,)))
+    _lib.check(lib.fcd_estep_qF(_dev.ptr(S1d), _dev.ptr(S2d), H, _dev.ptr(d['P']), C * pitchU, C, U, pitchU,
+                                _dev.ptr(d['qR']), _dev.ptr(rs), pitchS, N, _dev.ptr(nmd), ctypes.byref(th),
+                                _dev.ptr(lqF_p), _dev.ptr(qF_p), st), "fcd_estep_qF")
+    # NumPy: lqF[c,k] = log gamma_k + healthy_k + sum_u sum_l w_l log(a_l + b_l p_k) - logsumexp_k  (L cancels)
+    mu = np.array([-0.1, 0.0, 0.1]); sg = np.array([0.1, 0.1, 0.1]); gam = np.array([0.2, 0.5, 0.3])
+    want = np.zeros((C, 3))
+    for c in range(C):
+        (n, m) = util.c_to_nm(c)
+        l = np.log(gam) - (S2[c] - 2 * mu * S1[c] + H * mu ** 2) / (2 * sg ** 2) - H * (np.log(sg) + 0.5 * np.log(2 * np.pi))
+        for u in range(U):
+            (qn, qm) = (qR[n, u], qR[m, u])
+            w = np.array([qn[0] * qm[0], qn[1] * qm[1], qn[0] * qm[1] + qn[1] * qm[0]])
+            p3 = np.array([P[0, c, u], P[1, c, u], 1.0 - P[0, c, u] - P[1, c, u]])
+            for k in range(3):
+                l[k] += (w * np.log(al + bl * p3[k])).sum()
+        want[c] = l - (l.max() + np.log(np.exp(l - l.max()).sum()))
+    nptest.assert_allclose(lqF_c.cpu().numpy().reshape(C, 3), want, rtol=1e-10, atol=1e-9)
+    nptest.assert_allclose(lqF_p.cpu().numpy().reshape(C, 3), want, rtol=1e-10, atol=1e-9)
+    nptest.assert_allclose(qF_c.cpu().numpy(), np.exp(lqF_c.cpu().numpy()), rtol=1e-12, atol=1e-300)
 
 
 def test_small_exchange_world1_publishes_to_the_host():
