@@ -166,7 +166,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    n_regions = 40
+    n_regions = 100
     threads = max(1, min(os.cpu_count() or 1, 32))
     r = oracle_step_rate(n_regions, args.steps, args.warmup, threads)
     sample = ("oracle port (NumPy restatement of fcdiff/fit.py step functions; the (eta, epsilon) objective, "
@@ -392,10 +392,10 @@ def run_gpu_arm(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = max(1, min(os.cpu_count() or 1, 32))
-        r = oracle_step_rate(40, 1, 1, threads)
+        r = oracle_step_rate(100, 2, 1, threads)
         cpu = {"value": r["rate"], "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "oracle port (objective split over %d threads), sub-network of 40 regions (%d edges) x "
-                         "500+500 subjects, one EM iteration after one warm-up iteration, %.0f objective evals"
+               "sample": "oracle port (objective split over %d threads), sub-network of 100 regions (%d edges) x "
+                         "500+500 subjects, two EM iterations after one warm-up iteration, %.1f objective evals each"
                          % (threads, r["C"], r["nfev"]),
                "host_cores": os.cpu_count()}
 

@@ -472,7 +472,16 @@ pstar_refresh_kernel(const double* __restrict__ PT, int64_t planeStride, int Ul,
     const int per = (Ul + gridDim.y - 1) / gridDim.y;
     const int u1 = min(Ul, (int)(blockIdx.y + 1) * per);
     const double* src = PT + (int64_t)k * planeStride + c;
-    for (int u = blockIdx.y * per; u < u1; ++u) PsT[(int64_t)u * pitchC + c] = ldg_stream1(src + (int64_t)u * pitchC);
+    // a thread that has to copy keeps eight loads in flight (the launch lasts as long as its slowest column)
+    int u = blockIdx.y * per;
+    for (; u + 8 <= u1; u += 8) {
+        double v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = ldg_stream1(src + (int64_t)(u + i) * pitchC);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) PsT[(int64_t)(u + i) * pitchC + c] = v[i];
+    }
+    for (; u < u1; ++u) PsT[(int64_t)u * pitchC + c] = ldg_stream1(src + (int64_t)u * pitchC);
 }
 
 __global__ void __launch_bounds__(256)
@@ -1050,7 +1059,7 @@ int fcd_pstar_refresh(const double* PT, int64_t planeStride, int32_t Ul, int64_t
     FCD_REQUIRE(C >= 0 && Ul >= 0 && pitchC >= C, "fcd_pstar_refresh: bad shape");
     if (C == 0 || Ul == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 rgrid((unsigned)((C + 255) / 256), (unsigned)(Ul < 16 ? Ul : 16));
+    dim3 rgrid((unsigned)((C + 255) / 256), (unsigned)(Ul < 64 ? Ul : 64));
     pstar_refresh_kernel<<<rgrid, 256, 0, st>>>(PT, planeStride, Ul, C, pitchC, fstate, kcache, PsT);
     int rc = check_launch("fcd_pstar_refresh");
     if (rc) return rc;
@@ -1120,9 +1129,16 @@ int fcd_estep_qR(const double* WT, int64_t C, int32_t N, int32_t U, int32_t u0, 
     else if (N <= 128) FCD_SWEEP(64, 2);
     else if (N <= 256) FCD_SWEEP(128, 2);
     else if (N <= 512) FCD_SWEEP(128, 4);
-    else if (N <= 1024) FCD_SWEEP(256, 4);
-    else if (N <= 2048) FCD_SWEEP(256, 8);
-    else if (N <= 4096) FCD_SWEEP(512, 8);
+    // larger atlases (few patients per GPU when sharded): more warps, fewer regions per thread -- the
+    // step's latency is what one warp has to issue, occupancy is not the limit
+    else if (N <= 640) FCD_SWEEP(320, 2);
+    else if (N <= 768) FCD_SWEEP(384, 2);
+    else if (N <= 896) FCD_SWEEP(448, 2);
+    else if (N <= 1024) FCD_SWEEP(512, 2);
+    else if (N <= 1280) FCD_SWEEP(640, 2);
+    else if (N <= 1536) FCD_SWEEP(512, 3);
+    else if (N <= 2048) FCD_SWEEP(512, 4);
+    else if (N <= 4096) FCD_SWEEP(1024, 4);
     else FCD_SWEEP(1024, 8);
 #undef FCD_SWEEP
     return check_launch("fcd_estep_qR");

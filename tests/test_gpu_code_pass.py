@@ -189,3 +189,37 @@ def test_patient_gather_staging_roundtrip(N, U, world):
                "fcd_unpack_patients")
     nptest.assert_array_equal(oa.cpu().numpy().reshape(N, U, 2), a)
     nptest.assert_array_equal(ob.cpu().numpy().reshape(N, U, 2), b)
+
+
+@pytest.mark.parametrize("N,U,lookup", [(37, 5, 0), (600, 3, 0), (600, 2, 1), (1100, 2, 0), (1400, 2, 1), (2100, 1, 0)])
+def test_sweep_launch_shapes_match_numpy(N, U, lookup):
+    """Gauss-Seidel sweep of fit.py:184-197 over the two weight differences, for every launch shape of
+    fcd_estep_qR (regions per thread / warps per patient depend on N), both edge lookups."""
+    lib = _lib.load()
+    rng = np.random.RandomState(N + U)
+    C = N * (N - 1) // 2
+    WT = 0.05 * rng.randn(U, C + 1, 2)                       # {W_0 - W_2, W_2 - W_1}; one edge of slack (fit.py:186 quirk)
+    q = rng.dirichlet([1.0, 1.0], size=(N, U))
+    lp = np.log(np.array([0.7, 0.3]))
+    WTd = _dev.upload(WT[:, :C].copy().reshape(-1))
+    (qd, lqd) = (_dev.upload(q.reshape(-1)), _dev.zeros((N * U * 2,)))
+    _lib.check(lib.fcd_estep_qR(_dev.ptr(WTd), C, N, U, 0, U, _lib.d3(lp), lookup, _dev.ptr(qd), _dev.ptr(lqd),
+                                _dev.stream()), "fcd_estep_qR")
+    want_q = q.copy()
+    want_lq = np.zeros((N, U, 2))
+    for u in range(U):
+        for n in range(N):
+            base = n * (n - 1) // 2
+            m = np.arange(N)
+            if lookup == 0:
+                c = base + m                                  # nm_to_c(n, m) for every m != n (SURVEY 0.3)
+            else:
+                c = np.where(m < n, base + m, m * (m - 1) // 2 + n)
+            keep = (m != n) & (c < C)
+            D = (lp[0] - lp[1]) + (want_q[keep, u, 0] * WT[u, c[keep], 0] + want_q[keep, u, 1] * WT[u, c[keep], 1]).sum()
+            l = np.array([0.0, -D])
+            l -= l.max() + np.log(np.exp(l - l.max()).sum())
+            want_lq[n, u] = l
+            want_q[n, u] = np.exp(l)
+    nptest.assert_allclose(lqd.cpu().numpy().reshape(N, U, 2), want_lq, rtol=1e-9, atol=1e-11)
+    nptest.assert_allclose(qd.cpu().numpy().reshape(N, U, 2), want_q, rtol=1e-9, atol=1e-13)
