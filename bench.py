@@ -15,8 +15,9 @@ all-gathered -- fcdiff_b200/dist.py).
 
 A *step* is one pass of the reference's loop body (fcdiff/fit.py:76-80):
 E-step q_F (K2), region weights + Gauss-Seidel sweep for q_R (K2b), pi/gamma
-(K3a), the L-BFGS-B solve for (eta, epsilon): one bucket pass, then J
-objective+gradient evaluations over the bucketed streams (K3b), free energy (K4).  Steps are consecutive iterations of one fit.
+(K3a), the L-BFGS-B solve for (eta, epsilon): one code pass, then J
+objective+gradient evaluations over the coded dominant-state plane (K3b), free energy (K4).  Steps are consecutive
+iterations of one fit.
 
 value  = C*(H+U)*K / t with inputs resident in HBM (CUDA events, max over ranks)
 e2e    = the same metric through the public API from HOST (pinned) arrays: every
@@ -193,7 +194,7 @@ def workload_config(n_gpus):
                         "%d-region atlas (%d edges over %d GPU) x (%d controls + %d patients)" % (N, N * (N - 1) // 2, n_gpus, H_SUBJ, U_SUBJ),
             "regions": N, "edges": N * (N - 1) // 2, "controls": H_SUBJ, "patients": U_SUBJ,
             "edge_lookup": "reference", "storage": "f64",
-            "l2": "per-step working set (responsibility planes, patient-major planes, WT, streams: > 2 GB per GPU) "
+            "l2": "per-step working set (responsibility planes, patient-major planes, WT, coded plane and records: > 2 GB per GPU) "
                   "exceeds the 126 MB L2; no flush needed",
             "parallelism": "edge shards x%d, patient-sharded region sweep" % n_gpus}
 
