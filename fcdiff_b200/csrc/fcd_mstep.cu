@@ -66,19 +66,34 @@ elm_kernel(const double* __restrict__ P, int64_t planeStride, int64_t C, int U, 
     }
     __syncthreads();
 
+    // FAST: the T1 logs have weight exactly 1 -- running products, one logarithm per 2 x kProdMax factors
+    // (fcd_math.cuh "Sum of logs as the log of a product"); the gradient takes 1 / M from rcp_newton
+    double pr0 = 1.0, pr1 = 1.0;
+    int nf = 0;
+    auto flush = [&]() {
+        if (FAST) acc.obj += log_pos<FAST>(pr0 * pr1, s_tab);
+        pr0 = pr1 = 1.0;
+        nf = 0;
+    };
     auto live = [&](const double (&pv)[1], int lp, int e) {
         ElmAcc& a = e ? acc1 : acc;
         const double4 k = s_lc[lp];
         const double M = fma(k.y, pv[0], k.x);
-        if (GRAD) {
-            double rcp;
+        double rcp = 0.0;
+        if (FAST) {
+            (e ? pr1 : pr0) *= M;
+            if (GRAD) rcp = rcp_newton(M);
+        } else if (GRAD) {
             a.obj += fast_log_rcp<FAST>(M, s_tab, rcp);
-            const double d = mix_num(pv[0]) * rcp;
-            a.ge = fma(k.z, d, a.ge);
-            a.gh = fma(k.w, d, a.gh);
         } else {
             a.obj += fast_log<FAST>(M, s_tab);
         }
+        if (GRAD) {
+            const double d = mix_num(pv[0]) * rcp;
+            a.ge = fma(k.z, d, a.ge);
+            a.gh = fma(k.w, d, a.gh);
+        }
+        if (e == 1 && ++nf == kProdMax) flush();              // warp-uniform
     };
     struct Ops {
         double p;
@@ -142,6 +157,7 @@ elm_kernel(const double* __restrict__ P, int64_t planeStride, int64_t C, int U, 
     stream_tiered<1, kElmSeg, kStreamWarps, false, true>(P, planeStride, C, U, pitchU, fstate, rstate, pitchS, nm,
                                                          s_stream, depth, live, dload, dcompute, full,
                                                          [](int64_t) {});
+    flush();
     double v[3] = {acc.obj + acc1.obj, -(2.0 * th.epsilon - 1.0) * (acc.gh + acc1.gh), -(acc.ge + acc1.ge)};
     grid_reduce_store<3, kStreamThreads>(v, ws, out);
 }
@@ -352,7 +368,7 @@ int fcd_elm_obj_grad(const double* P, int64_t planeStride, int64_t C, int32_t U,
     const ThetaDev th = make_theta_dev(*theta_host, 0);
     cudaStream_t st = (cudaStream_t)stream;
     LogTabWindow tab;
-    FCD_REQUIRE(log_table_window(th.epsl, th.al, st, tab), "fcd_elm_obj_grad: log table initialisation failed");
+    FCD_REQUIRE(log_table_window(th.epsl, th.al, st, tab, true), "fcd_elm_obj_grad: log table initialisation failed");
     const bool fast = log_table_covers(th.epsl, th.al);
     const size_t tbytes = fast ? (size_t)((tab.n + 1) & ~1) * sizeof(double) : 0;
     const int depth = stream_depth<1, kElmSeg>(tbytes);
