@@ -153,10 +153,15 @@ class UnsharedRegionFit(object):
         Run the (eta, epsilon) optimiser in ``_update_theta`` (default True).
     elm_path : "auto" | "streams" | "tiered"
         Form of the (eta, epsilon) objective kernel (new).  ``"streams"``: one
-        bucket pass per (q_F, q_R) state, then every evaluation reduces flat
-        streams (8 bytes per edge-patient); ``"tiered"``: every evaluation walks
-        the responsibility planes; ``"auto"``: streams unless more than a quarter
-        of the elements would need weighted records (e.g. the uniform start).
+        code pass per (q_F, q_R) state (dominant-state plane, one code byte per
+        element, weighted records for the undecided elements), then every
+        evaluation reduces the flat planes (9 bytes per edge-patient);
+        ``"tiered"``: every evaluation walks the responsibility planes;
+        ``"auto"``: the coded form unless more than a quarter of the elements
+        would need weighted records (e.g. the uniform start).
+    coded_estep : bool
+        Let ``_update_lq_F`` reuse the code plane and key lists of the last code
+        pass while q_R has not changed since (default True; same result).
     update_mu_sigma : bool
         Also re-estimate ``mu`` and ``sigma`` in ``_update_theta`` (new; the
         reference ships this step disabled, fit.py:232-237; default False).
@@ -181,7 +186,7 @@ class UnsharedRegionFit(object):
         self.update_mu_sigma = False  # re-estimate mu, sigma (disabled in the reference, fit.py:232-237)
         self.coded_estep = True       # K2 from the previous M-step's code plane when it still describes q_R
         self.fused_sweep = False      # K2b: weights computed inside the sweep (no WT tensor; reference lookup, N <= 1024)
-        self.elm_path = "auto"        # K3b form: "streams" | "tiered" | "auto" (streams unless most elements are unpeaked)
+        self.elm_path = "auto"        # K3b form: "streams" (coded plane) | "tiered" | "auto" (coded unless most elements are undecided)
         self.convergence_rule = "reference"
         self.n_objective_evals = []
         self.profile = None           # _dev.KernelTimers for per-kernel CUDA-event timing
@@ -786,7 +791,7 @@ class UnsharedRegionFit(object):
         """
         Update the parameters of the model (fcdiff/fit.py:200-206).
         """
-        # the bucket pass of the (eta, epsilon) solve does not depend on pi / gamma: it is enqueued
+        # the code pass of the (eta, epsilon) solve does not depend on pi / gamma: it is enqueued
         # behind the K3a launch, so that one wait on the stream serves both results
         early = self._objective_context if (self.optimise_theta_sub and self._lps_state == 'derived') else None
         self._update_pi_gamma(True, True, early)
@@ -907,7 +912,7 @@ class UnsharedRegionFit(object):
 
     def _objective_context(self):
         """Everything of a K3b evaluation that does not depend on (eta, epsilon):
-        the streams of the bucket pass (or, for the tiered form, the plane
+        the coded plane and records of the code pass (or, for the tiered form, the plane
         pointers and the theta-free part of E_lM), theta struct, result vector,
         stream.  Valid for one (q_F, q_R, planes) state."""
         inp = self._ensure_cache()
@@ -941,7 +946,7 @@ class UnsharedRegionFit(object):
 
     def _objective(self, theta_sub, want_grad=True, name=None):
         """(-E_lM, gradient) at theta_sub = [eta, epsilon] from one fused pass
-        (K3b) over the bucketed streams or the responsibility planes."""
+        (K3b) over the coded dominant-state plane or the responsibility planes."""
         ctx = self._objective_context()
         th = ctx['th']
         th.eta = float(theta_sub[0])
@@ -1007,7 +1012,7 @@ class UnsharedRegionFit(object):
             if const is None:
                 const = float(o[3])
                 if shards is not None:
-                    # slot 3 (theta-free part, written once by the bucket pass) is now global: keep it
+                    # slot 3 (theta-free part, written once by the code pass) is now global: keep it
                     # and zero the slot so that the next all-reduces do not add it again
                     ctx['const'] = const
                     dev_vec[3:].zero_()
