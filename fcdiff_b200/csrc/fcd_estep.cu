@@ -511,36 +511,50 @@ region_weights_kernel(const double* __restrict__ PT, int64_t planeStride,
                       double* __restrict__ WT) {
     extern __shared__ __align__(16) double s_dyn[];
     const double* s_tab = load_log_table<FAST>(tab, s_dyn);
-    // persistent CTAs over (patient, 1024-edge tile) work items: no wave tail, one
-    // table load per CTA
+    // persistent CTAs over (patient, 1024-edge tile) work items: no wave tail, one table load per
+    // CTA.  The kernel is bound by load latency, so (a) with the dominant-state plane the
+    // responsibility is requested together with the edge's state, not after it (the address does
+    // not depend on the state; an unpeaked edge's value is simply not used), and (b) the loads of the
+    // CTA's next tile are in flight while the logs of the current one are taken.
     const int64_t tiles_per_row = (C + 1023) / 1024;
     const int64_t ntiles = tiles_per_row * Ul;
+    struct Tile {
+        double pk[4];
+        int ks[4];
+    };
+    auto load = [&](int64_t t) {
+        Tile tl;
+        const int u = (int)(t / tiles_per_row);
+        const int64_t cbase = (t - (int64_t)u * tiles_per_row) * 1024;
+        const double* row = PT + (int64_t)u * pitchC;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t c = cbase + threadIdx.x + 256 * j;
+            tl.pk[j] = 0.0;
+            tl.ks[j] = -1;
+            if (t < ntiles && c < C) {
+                tl.ks[j] = __ldg(fstate + c);
+                if (PsT) tl.pk[j] = ldg_stream1(PsT + (int64_t)u * pitchC + c);
+                else if (tl.ks[j] < 3) tl.pk[j] = ldg_stream1(row + tl.ks[j] * planeStride + c);
+            }
+        }
+        return tl;
+    };
+    Tile cur = load(blockIdx.x);
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const Tile nxt = load(t + gridDim.x);
         const int u = (int)(t / tiles_per_row);
         const int64_t cbase = (t - (int64_t)u * tiles_per_row) * 1024;
         const double* row = PT + (int64_t)u * pitchC;
         double2* out = reinterpret_cast<double2*>(WT) + (int64_t)u * C;
-        double pk[4];
-        int ks[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {                 // issue the tile's loads first
-            const int64_t c = cbase + threadIdx.x + 256 * j;
-            pk[j] = 0.0;
-            ks[j] = -1;
-            if (c < C) {
-                ks[j] = __ldg(fstate + c);
-                if (ks[j] < 3)                                // coalesced from the dominant-state plane when it is kept
-                    pk[j] = PsT ? ldg_stream1(PsT + (int64_t)u * pitchC + c) : ldg_stream1(row + ks[j] * planeStride + c);
-            }
-        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int64_t c = cbase + threadIdx.x + 256 * j;
-            if (ks[j] < 0) continue;
+            if (cur.ks[j] < 0) continue;
             double w[3];
-            if (ks[j] < 3) {
+            if (cur.ks[j] < 3) {
 #pragma unroll
-                for (int l = 0; l < 3; ++l) w[l] = fast_log<FAST>(mix_rel(th, l, pk[j]), s_tab);
+                for (int l = 0; l < 3; ++l) w[l] = fast_log<FAST>(mix_rel(th, l, cur.pk[j]), s_tab);
             } else {
                 const double q[3] = {__ldg(qF + c * 3), __ldg(qF + c * 3 + 1), __ldg(qF + c * 3 + 2)};
                 w[0] = w[1] = w[2] = 0.0;
@@ -553,6 +567,7 @@ region_weights_kernel(const double* __restrict__ PT, int64_t planeStride,
             }
             out[c] = make_double2(w[0] - w[2], w[2] - w[1]);
         }
+        cur = nxt;
     }
 }
 
