@@ -70,11 +70,11 @@ SIGNATURES = {
     "fcd_code_pitch": (c_int64, [c_int32]),
     "fcd_code_plane": (c_int, [_P, c_int64, c_int64, c_int32, c_int64, _P, _P, c_int64, _P, _P, _P, _P, c_int64, _P, _P,
                                _P, _P]),
-    "fcd_code_records": (c_int, [_P, c_int64, _P, _P, c_int64, _P, _P, c_int64, c_int32, c_int64, _P, _P, _P, c_int32,
-                                 _P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P]),
+    "fcd_code_records": (c_int, [_P, c_int64, _P, _P, c_int64, _P, _P, c_int64, c_int32, c_int64, _P, _P, _P, _P, c_int64,
+                                 c_int32, _P, _P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, _P, _P, _P]),
     "fcd_estep_qF_coded": (c_int, [_P, _P, c_int32, _P, c_int64, c_int64, c_int32, c_int64, _P, c_int32, _P,
-                                   _P, c_int64, _P, _P, _P, POINTER(FcdTheta), _P, _P, _P]),
-    "fcd_elm_coded": (c_int, [_P, _P, c_int64, _P, c_int64, POINTER(FcdTheta), c_int32, _P, _P, _P]),
+                                   _P, c_int64, _P, _P, _P, _P, _P, POINTER(FcdTheta), _P, _P, _P]),
+    "fcd_elm_coded": (c_int, [_P, _P, c_int64, _P, c_int64, _P, c_int64, POINTER(FcdTheta), c_int32, _P, _P, _P]),
     "fcd_energy_terms": (c_int, [_P, _P, c_int32, _P, _P, c_int64, _P, _P, c_int32, c_int32,
                                  POINTER(FcdTheta), c_double, _P, _P, _P]),
     "fcd_state_moments": (c_int, [_P, _P, c_int32, _P, _P, c_int64, c_int64, c_int32, c_int64, _P, _P, c_int32, _P,

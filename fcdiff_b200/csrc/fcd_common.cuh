@@ -106,8 +106,8 @@ __device__ __forceinline__ double ldg_stream1(const double* p) {
 // magnitude <= 14: dropping the term changes a sum of O(1) terms by less than
 // its own rounding error.  The peak-state bytes (peak_states_*_kernel)
 //   fstate[c]   = k* if q_F[c,k*] == 1.0 exactly and the others <= 2^-60, else 3
-//   rstate[n,u] = s  if q_R[n,u,s] == 1.0 exactly and the other  <= 2^-60, else 2
-//                 (4 in the padding column)
+//   rstate[n,u] = s  if q_R[n,u,s] == 1.0 exactly and the other  <= 2^-60, else 2 (3 if the pair
+//                 does not sum to 1 within 2^-50: user-assigned, unnormalised), 4 in the padding column
 // let the kernels take, per element,
 //   T1: edge and both regions peaked -> ONE plane (k*), ONE log (l* from 2 bytes);
 //   T2: edge peaked, a region not    -> k* plane, 3 logs, real pair weights;
@@ -116,7 +116,7 @@ __device__ __forceinline__ double ldg_stream1(const double* p) {
 // queue in shared memory and evaluated 32 at a time, so that the rare expensive
 // elements do not drag whole warps into the slow path.
 constexpr double kPeakTau = 8.673617379884035e-19;        // 2^-60
-constexpr int kStateMixedR = 2, kStateDead = 4, kStateMixedF = 3;
+constexpr int kStateMixedR = 2, kStateLooseR = 3, kStateDead = 4, kStateMixedF = 3;
 
 struct Resp {
     double p[3];

@@ -101,7 +101,8 @@ peak_states_R_kernel(const double* __restrict__ qR, int N, int U, int64_t pitchS
         int s = kStateDead;
         if (u < U) {
             const double2 q = q2[n * U + u];
-            s = kStateMixedR;
+            // mixed; "loose" if the pair is not normalised (the one-weight form of a half record needs q_0 + q_1 = 1)
+            s = fabs((q.x + q.y) - 1.0) <= 8.881784197001252e-16 ? kStateMixedR : kStateLooseR;
             if (q.x == 1.0 && q.y <= kPeakTau) s = 0;
             else if (q.y == 1.0 && q.x <= kPeakTau) s = 1;
         }
@@ -280,12 +281,13 @@ __global__ void __launch_bounds__(kStreamThreads, 1)
 estep_qF_coded_kernel(const double* __restrict__ S1, const double* __restrict__ S2,
                       const double* __restrict__ P, int64_t planeStride, int64_t C, int U, int64_t pitchU,
                       const double* __restrict__ qR, const int32_t* __restrict__ nm,
-                      const uint8_t* __restrict__ code, int64_t pitchQ, const int32_t* __restrict__ counts,
-                      const unsigned long long* __restrict__ keys, const long long* __restrict__ rowoff,
+                      const uint8_t* __restrict__ code, int64_t pitchQ, const int2* __restrict__ counts,
+                      const unsigned long long* __restrict__ keysF, const unsigned long long* __restrict__ keysH,
+                      const longlong2* __restrict__ rowoff, const double2* __restrict__ Hh,
                       const __grid_constant__ ThetaDev th, const __grid_constant__ LogTabWindow tab, int depth,
                       double* __restrict__ lqF, double* __restrict__ qF) {
     extern __shared__ __align__(128) double s_dyn[];
-    __shared__ double2 s_lc[4];
+    __shared__ double2 s_lc[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* ring0 = reinterpret_cast<unsigned char*>(s_dyn + (FAST ? ((tab.n + 15) & ~15) : 0));
     unsigned char* ring = ring0 + (size_t)warp * depth * kK2cStage;
@@ -296,9 +298,12 @@ estep_qF_coded_kernel(const double* __restrict__ S1, const double* __restrict__ 
     if (lane < depth) mbar_init(bars + lane, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    // per-code constants {a_l, b_l}; code 3 is neutral: the factor 1 + 0 p = 1 exactly
-    if (threadIdx.x < 4) s_lc[threadIdx.x] = threadIdx.x < 3 ? make_double2(th.al[threadIdx.x], th.bl[threadIdx.x])
-                                                             : make_double2(1.0, 0.0);
+    // per-code constants {a_l, b_l}; code 3 is neutral: the factor 1 + 0 p = 1 exactly; the codes 4, 5
+    // (one undecided region) count as l = 2 here, their correction comes from the half records
+    if (threadIdx.x < 8) {
+        const int l = threadIdx.x >= 4 ? 2 : threadIdx.x;
+        s_lc[threadIdx.x] = l < 3 ? make_double2(th.al[l], th.bl[l]) : make_double2(1.0, 0.0);
+    }
     __syncwarp();
 
     const int nseg = (int)((pitchU + kK2cSeg - 1) / kK2cSeg);
@@ -361,6 +366,15 @@ estep_qF_coded_kernel(const double* __restrict__ S1, const double* __restrict__ 
             acc[k] = a;
         }
     };
+    // an element with one undecided region: q (log M_s - log M_2) per template state (half record {p*, +-q})
+    auto half = [&](int64_t c, int u, bool sx, double q) {
+        const double p0 = __ldg(P + c * pitchU + u), p1 = __ldg(P + planeStride + c * pitchU + u);
+        const double p3[3] = {p0, p1, (1.0 - p0) - p1};
+        const double ax = sx ? th.al[1] : th.al[0], bx = sx ? th.bl[1] : th.bl[0];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            acc[k] = fma(q, fast_log<FAST>(fma(bx, p3[k], ax), s_tab) - fast_log<FAST>(mix_rel(th, 2, p3[k]), s_tab), acc[k]);
+    };
     double keep[3] = {0.0, 0.0, 0.0};                        // row ends: see estep_qF_kernel
     int64_t keep_c = -1;
     int rows_done = 0;
@@ -410,12 +424,19 @@ estep_qF_coded_kernel(const double* __restrict__ S1, const double* __restrict__ 
         // the row's elements with real weights
         const int v = __ldg(nm + c);
         const int n = v & 0xffff, m = (v >> 16) & 0xffff;
-        const int cnt = __ldg(counts + c);
-        if (cnt == 3 * U) {                                  // the edge was unpeaked at the code pass: every element
+        const int2 cnt = __ldg(counts + c);
+        if (cnt.x == 3 * U) {                                // the edge was unpeaked at the code pass: every element
             for (int u = lane; u < U; u += 32) weighted(c, u, n, m);
-        } else if (cnt > 0) {
-            const unsigned long long* kr = keys + __ldg(rowoff + c);
-            for (int i = lane; i < cnt; i += 32) weighted(c, (int)(__ldg(kr + i) & 0xffffull), n, m);
+        } else if (cnt.x > 0 || cnt.y > 0) {
+            const longlong2 ro = __ldg(rowoff + c);
+            const unsigned long long* kf = keysF + ro.x;
+            for (int i = lane; i < cnt.x; i += 32) weighted(c, (int)(__ldg(kf + i) & 0xffffull), n, m);
+            const unsigned long long* kh = keysH + ro.y;
+            const double2* hr = Hh + ro.y;
+            for (int i = lane; i < cnt.y; i += 32) {
+                const double qs = __ldg(hr + i).y;
+                half(c, (int)(__ldg(kh + i) & 0xffffull), __double2hiint(qs) < 0, fabs(qs));
+            }
         }
 #pragma unroll
         for (int k = 0; k < 3; ++k) acc[k] = warp_sum(acc[k]);
@@ -1017,15 +1038,17 @@ int fcd_estep_qF(const double* S1, const double* S2, int32_t H,
 int fcd_estep_qF_coded(const double* S1, const double* S2, int32_t H,
                        const double* P, int64_t planeStride, int64_t C, int32_t U, int64_t pitchU,
                        const double* qR, int32_t N, const int32_t* nm,
-                       const uint8_t* code, int64_t pitchQ, const int32_t* counts, const uint64_t* keys,
-                       const int64_t* rowoff, const fcd_theta* theta_host, double* lqF, double* qF, void* stream) {
+                       const uint8_t* code, int64_t pitchQ, const int32_t* counts, const uint64_t* keysF,
+                       const uint64_t* keysH, const int64_t* rowoff, const double* Hh,
+                       const fcd_theta* theta_host, double* lqF, double* qF, void* stream) {
     FCD_REQUIRE(theta_host != nullptr && S1 != nullptr && S2 != nullptr && P != nullptr && qR != nullptr &&
-                nm != nullptr && code != nullptr && counts != nullptr && keys != nullptr && rowoff != nullptr &&
-                lqF != nullptr, "fcd_estep_qF_coded: NULL argument");
+                nm != nullptr && code != nullptr && counts != nullptr && keysF != nullptr && keysH != nullptr &&
+                rowoff != nullptr && Hh != nullptr && lqF != nullptr, "fcd_estep_qF_coded: NULL argument");
     FCD_REQUIRE(C >= 0 && U >= 1 && U < 65536 && pitchU >= U && N >= 2 && N < 65536, "fcd_estep_qF_coded: bad shape");
-    FCD_REQUIRE(((reinterpret_cast<uintptr_t>(P) | reinterpret_cast<uintptr_t>(code)) & 15) == 0 && pitchU % 2 == 0 &&
-                planeStride % 2 == 0 && pitchQ >= pitchU && pitchQ % 16 == 0,
-                "fcd_estep_qF_coded: planes / code must be 16-byte aligned (even pitchU, pitchQ % 16 == 0)");
+    FCD_REQUIRE(((reinterpret_cast<uintptr_t>(P) | reinterpret_cast<uintptr_t>(code) | reinterpret_cast<uintptr_t>(rowoff) |
+                  reinterpret_cast<uintptr_t>(Hh)) & 15) == 0 && (reinterpret_cast<uintptr_t>(counts) & 7) == 0 &&
+                pitchU % 2 == 0 && planeStride % 2 == 0 && pitchQ >= pitchU && pitchQ % 16 == 0,
+                "fcd_estep_qF_coded: planes / code / rowoff / half records must be 16-byte aligned (even pitchU, pitchQ % 16 == 0)");
     if (C == 0) return 0;
     const ThetaDev th = make_theta_dev(*theta_host, H);
     cudaStream_t st = (cudaStream_t)stream;
@@ -1048,9 +1071,9 @@ int fcd_estep_qF_coded(const double* S1, const double* S2, int32_t H,
             attr_set = true;                                                                          \
         }                                                                                             \
         estep_qF_coded_kernel<F><<<(unsigned)grid, kStreamThreads, smem, st>>>(                       \
-            S1, S2, P, planeStride, C, U, pitchU, qR, nm, code, pitchQ, counts,                       \
-            reinterpret_cast<const unsigned long long*>(keys), reinterpret_cast<const long long*>(rowoff), th, tab, \
-            depth, lqF, qF);                                                                          \
+            S1, S2, P, planeStride, C, U, pitchU, qR, nm, code, pitchQ, reinterpret_cast<const int2*>(counts), \
+            reinterpret_cast<const unsigned long long*>(keysF), reinterpret_cast<const unsigned long long*>(keysH), \
+            reinterpret_cast<const longlong2*>(rowoff), reinterpret_cast<const double2*>(Hh), th, tab, depth, lqF, qF); \
     } while (0)
     if (fast) FCD_K2C(true); else FCD_K2C(false);
 #undef FCD_K2C

@@ -9,6 +9,10 @@
 //   * code[c][u] (one byte): l* in 0..2 when the edge and both regions are peaked
 //     (fcd_common.cuh, "Tiers": the element contributes log(a_l + b_l p) for ONE
 //     (k*, l*) pair with weight exactly 1), 3 otherwise (nothing to add here);
+//   * an element with ONE undecided region (normalised posterior (q_0, q_1), the other region in
+//     state s) has the weights (q_s at l = s, 1 - q_s at l = 2): it stays in the plane with code
+//     4 + s, where it counts as l = 2 with weight 1, and adds a 16-byte *half record* {p, +-q_s}
+//     for the correction q_s (log M_s - log M_2) (sign bit = s);
 //   * every other element is expanded into records {p_k, w_0, w_1, w_2} with
 //     w_l = q_F[c,k] * pair weight_l (one record if the edge is peaked, three if not);
 //   * the theta-free part sum w L of E_lM: (total of the L plane, once per cache)
@@ -25,10 +29,16 @@ namespace fcd {
 
 constexpr int kBucketThreads = 256;
 
-// code of element (c,u): 0..2 = l* (both regions peaked), 3 = a region is mixed, 4 = padding
+// code of element (c,u) from the two regions' peak states: 0..2 = l* (both regions peaked),
+// 4 + s = one region mixed and normalised, the other in state s (half record), 3 = any other mixed
+// pair (full record), 6 = padding (written as 3, not counted)
 __device__ __forceinline__ int pair_code(int sn, int sm) {
     const int o = sn | sm;
-    return o < 2 ? (((sn ^ sm) << 1) + (sn & sm)) : ((o & 6) == 2 ? 3 : 4);
+    if (o < 2) return ((sn ^ sm) << 1) + (sn & sm);
+    if (o & 4) return 6;
+    if (sn == kStateMixedR && sm < 2) return 4 + sm;
+    if (sm == kStateMixedR && sn < 2) return 4 + sn;
+    return 3;
 }
 
 // Rows are handled in blocks of kRowBlock consecutive rows per CTA (one warp per
@@ -38,21 +48,27 @@ __device__ __forceinline__ int pair_code(int sn, int sm) {
 // kernel -- no pass over per-row arrays by a single CTA.
 constexpr int kRowBlock = 16;
 
-// code[c][u] for u in [0, pitchU) and counts[c] = number of records of row c; blocktot[b] = their
-// sum over the rows of block b.  On the way: PsE[c][:] = P[k*(c)][c][:] for the rows whose dominant
+// code[c][u] for u in [0, pitchQ) and counts[c] = {full records, half records} of row c; blocktot[b]
+// = their sums over the rows of block b.  On the way: PsE[c][:] = P[k*(c)][c][:] for the rows whose dominant
 // state changed since the last call (kcache).
 __global__ void __launch_bounds__(kBucketThreads)
 code_plane_kernel(const double* __restrict__ P, int64_t planeStride, double* __restrict__ PsE,
                   uint8_t* __restrict__ kcache,
                   const uint8_t* __restrict__ fstate, const uint8_t* __restrict__ rstate, int64_t pitchS,
                   const int32_t* __restrict__ nm, int64_t C, int U, int64_t pitchU, int64_t pitchQ,
-                  uint8_t* __restrict__ code, int32_t* __restrict__ counts, long long* __restrict__ blocktot) {
-    __shared__ int s_cnt[kRowBlock];
+                  uint8_t* __restrict__ code, int2* __restrict__ counts, longlong2* __restrict__ blocktot) {
+    __shared__ int2 s_cnt[kRowBlock];
+    __shared__ uint8_t s_lut[64];                            // pair_code by (sn << 3 | sm): one LDS per element
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 64) {
+        const int sn = threadIdx.x >> 3, sm = threadIdx.x & 7;
+        s_lut[threadIdx.x] = (uint8_t)((sn > 4 || sm > 4) ? 6 : pair_code(sn, sm));
+    }
+    __syncthreads();
     const int64_t cb = (int64_t)blockIdx.x * kRowBlock;
     for (int r = warp; r < kRowBlock; r += kBucketThreads / 32) {
         const int64_t c = cb + r;
-        int cnt = 0;
+        int cnt = 0, cnh = 0;
         if (c < C) {
             const int k = fstate[c];
             unsigned short* crow = reinterpret_cast<unsigned short*>(code + c * pitchQ);      // pitchQ % 16 == 0
@@ -75,48 +91,63 @@ code_plane_kernel(const double* __restrict__ P, int64_t planeStride, double* __r
                 for (int u = 2 * lane; u < pitchQ; u += 64) {
                     const uint32_t sn2 = __ldg(reinterpret_cast<const unsigned short*>(rn + u));
                     const uint32_t sm2 = __ldg(reinterpret_cast<const unsigned short*>(rm + u));
-                    const int c0 = pair_code(sn2 & 0xff, sm2 & 0xff), c1 = pair_code(sn2 >> 8, sm2 >> 8);
+                    const int c0 = s_lut[((sn2 & 7) << 3) | (sm2 & 7)], c1 = s_lut[((sn2 >> 5) & 0x38) | ((sm2 >> 8) & 7)];
                     cnt += (c0 == 3) + (c1 == 3);
-                    crow[u >> 1] = (unsigned short)(min(c0, 3) | (min(c1, 3) << 8));
+                    cnh += ((c0 & 6) == 4) + ((c1 & 6) == 4);
+                    crow[u >> 1] = (unsigned short)((c0 == 6 ? 3 : c0) | ((c1 == 6 ? 3 : c1) << 8));
                 }
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+                for (int o = 16; o > 0; o >>= 1) {
+                    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+                    cnh += __shfl_xor_sync(0xffffffffu, cnh, o);
+                }
             }
-            if (lane == 0) counts[c] = cnt;
+            if (lane == 0) counts[c] = make_int2(cnt, cnh);
         }
-        if (lane == 0) s_cnt[r] = cnt;
+        if (lane == 0) s_cnt[r] = make_int2(cnt, cnh);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        long long t = 0;
-        for (int r = 0; r < kRowBlock; ++r) t += s_cnt[r];
+        longlong2 t = make_longlong2(0, 0);
+        for (int r = 0; r < kRowBlock; ++r) {
+            t.x += s_cnt[r].x;
+            t.y += s_cnt[r].y;
+        }
         blocktot[blockIdx.x] = t;
     }
 }
 
-// blockoff[b] = exclusive prefix sums of blocktot, total[0] the sum (as a double: < 2^53).  One CTA.
+// blockoff[b] = exclusive prefix sums of blocktot, total[0..1] the sums (as doubles: < 2^53).  One CTA.
 __global__ void __launch_bounds__(1024)
-record_scan_kernel(const long long* __restrict__ blocktot, int64_t nblocks, long long* __restrict__ blockoff,
+record_scan_kernel(const longlong2* __restrict__ blocktot, int64_t nblocks, longlong2* __restrict__ blockoff,
                    double* __restrict__ total) {
-    __shared__ long long s_part[1024];
+    __shared__ long long s_part[2][1024];
     const int t = threadIdx.x;
-    long long carry = 0;
+    long long carry[2] = {0, 0};
     for (int64_t b0 = 0; b0 < nblocks; b0 += 1024) {
         const int64_t b = b0 + t;
-        const long long mine = b < nblocks ? blocktot[b] : 0;
-        s_part[t] = mine;
+        const longlong2 v = b < nblocks ? blocktot[b] : make_longlong2(0, 0);
+        const long long mine[2] = {v.x, v.y};
+        s_part[0][t] = mine[0];
+        s_part[1][t] = mine[1];
         __syncthreads();
         for (int d = 1; d < 1024; d <<= 1) {                 // Hillis-Steele inclusive scan
-            const long long w = t >= d ? s_part[t - d] : 0;
+            const long long w0 = t >= d ? s_part[0][t - d] : 0, w1 = t >= d ? s_part[1][t - d] : 0;
             __syncthreads();
-            s_part[t] += w;
+            s_part[0][t] += w0;
+            s_part[1][t] += w1;
             __syncthreads();
         }
-        if (b < nblocks) blockoff[b] = carry + s_part[t] - mine;
-        carry += s_part[1023];
+        if (b < nblocks)
+            blockoff[b] = make_longlong2(carry[0] + s_part[0][t] - mine[0], carry[1] + s_part[1][t] - mine[1]);
+        carry[0] += s_part[0][1023];
+        carry[1] += s_part[1][1023];
         __syncthreads();
     }
-    if (t == 0) total[0] = (double)carry;
+    if (t == 0) {
+        total[0] = (double)carry[0];
+        total[1] = (double)carry[1];
+    }
 }
 
 struct Record {
@@ -142,16 +173,18 @@ plane_sum_kernel(const double* __restrict__ X, int64_t C, int U, int64_t pitchU,
     grid_reduce_store<1, kBucketThreads>(vv, ws, out);
 }
 
-// Keys of the elements the code plane leaves out: (tag << 48) | (c << 16) | u with tag 0 = element of
-// a peaked edge with a mixed region (one record), tag 1 + k = state k of an unpeaked edge (three
-// records per element).  Same row blocks as code_plane_kernel.  Only the code plane is read: the
-// operands of a record are gathered by record_weights_kernel, one thread per record.
+// Keys of the elements that need a record: (tag << 48) | (c << 16) | u.  Full records (keysF): tag 0 =
+// element of a peaked edge whose regions are both undecided or not normalised, tag 1 + k = state k
+// of an unpeaked edge (three records per element).  Half records (keysH): tag = s, the state of the
+// decided region (code 4 + s).  Same row blocks as code_plane_kernel; rowoff[c] = first key of row c
+// in either list (kept for the next E-step).  Only the code plane is read: the operands of a record
+// are gathered by the record kernels, one thread per record.
 __global__ void __launch_bounds__(kBucketThreads, 4)
 record_keys_kernel(const uint8_t* __restrict__ code, const uint8_t* __restrict__ fstate,
-                   int64_t C, int U, int64_t pitchQ, const int32_t* __restrict__ counts,
-                   const long long* __restrict__ blockoff, unsigned long long* __restrict__ keys,
-                   long long* __restrict__ rowoff) {
-    __shared__ long long s_off[kRowBlock];
+                   int64_t C, int U, int64_t pitchQ, const int2* __restrict__ counts,
+                   const longlong2* __restrict__ blockoff, unsigned long long* __restrict__ keysF,
+                   unsigned long long* __restrict__ keysH, longlong2* __restrict__ rowoff) {
+    __shared__ longlong2 s_off[kRowBlock];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
     for (int64_t blk = blockIdx.x; blk * kRowBlock < C; blk += gridDim.x) {
@@ -159,36 +192,42 @@ record_keys_kernel(const uint8_t* __restrict__ code, const uint8_t* __restrict__
         __syncthreads();
         if (threadIdx.x < 32) {                              // in-block exclusive prefix of the row counts (one warp scan)
             const int r = threadIdx.x;
-            long long v = (r < kRowBlock && cb + r < C) ? (long long)counts[cb + r] : 0;
-            const long long mine = v;
+            const int2 cv = (r < kRowBlock && cb + r < C) ? counts[cb + r] : make_int2(0, 0);
+            long long v0 = cv.x, v1 = cv.y;
 #pragma unroll
             for (int o = 1; o < kRowBlock; o <<= 1) {
-                const long long w = __shfl_up_sync(0xffffffffu, v, o);
-                if (r >= o) v += w;
+                const long long w0 = __shfl_up_sync(0xffffffffu, v0, o), w1 = __shfl_up_sync(0xffffffffu, v1, o);
+                if (r >= o) {
+                    v0 += w0;
+                    v1 += w1;
+                }
             }
             if (r < kRowBlock) {
-                s_off[r] = blockoff[blk] + v - mine;
-                if (cb + r < C) rowoff[cb + r] = s_off[r];   // kept for the next E-step (fcd_estep_qF_coded)
+                const longlong2 bo = blockoff[blk];
+                s_off[r] = make_longlong2(bo.x + v0 - cv.x, bo.y + v1 - cv.y);
+                if (cb + r < C) rowoff[cb + r] = s_off[r];
             }
         }
         __syncthreads();
         for (int r = warp; r < kRowBlock; r += kBucketThreads / 32) {
             const int64_t c = cb + r;
             if (c >= C) break;
-            if (counts[c] == 0) continue;                    // warp-uniform
+            const int2 cv = counts[c];
+            if (cv.x == 0 && cv.y == 0) continue;            // warp-uniform
             const int k = fstate[c];
-            unsigned long long* const d3 = keys + s_off[r];
+            unsigned long long* const dF = keysF + s_off[r].x;
+            unsigned long long* const dH = keysH + s_off[r].y;
             const unsigned long long ckey = (unsigned long long)c << 16;
             if (k == kStateMixedF) {                         // three records per element, tagged with their state
                 for (int u = lane; u < U; u += 32) {
 #pragma unroll
                     for (int kk = 0; kk < 3; ++kk)
-                        d3[3 * (int64_t)u + kk] = ((unsigned long long)(1 + kk) << 48) | ckey | (unsigned long long)u;
+                        dF[3 * (int64_t)u + kk] = ((unsigned long long)(1 + kk) << 48) | ckey | (unsigned long long)u;
                 }
                 continue;
             }
             const unsigned short* crow = reinterpret_cast<const unsigned short*>(code + c * pitchQ);
-            uint32_t off = 0;
+            uint32_t offF = 0, offH = 0;
             // batches of 8 x 64 patients: all code loads first, then positions (ballots) and stores
             for (int ub = 0; ub < U; ub += 512) {
                 uint32_t c2[8];
@@ -202,14 +241,38 @@ record_keys_kernel(const uint8_t* __restrict__ code, const uint8_t* __restrict__
                     const int u = ub + 64 * i + 2 * lane;
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        const bool mixed = u + e < U && ((c2[i] >> (8 * e)) & 0xff) == 3;
-                        const unsigned bal = __ballot_sync(0xffffffffu, mixed);
-                        if (mixed) d3[off + __popc(bal & lt)] = ckey | (unsigned long long)(u + e);
-                        off += __popc(bal);
+                        const int cd = u + e < U ? (int)((c2[i] >> (8 * e)) & 0xff) : 0;
+                        const unsigned balF = __ballot_sync(0xffffffffu, cd == 3);
+                        const unsigned balH = __ballot_sync(0xffffffffu, cd >= 4);
+                        if (cd == 3) dF[offF + __popc(balF & lt)] = ckey | (unsigned long long)(u + e);
+                        if (cd >= 4)
+                            dH[offH + __popc(balH & lt)] = ((unsigned long long)(cd - 4) << 48) | ckey | (unsigned long long)(u + e);
+                        offF += __popc(balF);
+                        offH += __popc(balH);
                     }
                 }
             }
         }
+    }
+}
+
+// Half records, one thread per key: {p, +-q_s} with p the dominant-state responsibility, q_s the
+// undecided region's posterior of state s (the other region's state) and the sign bit = s.
+__global__ void __launch_bounds__(kBucketThreads)
+record_half_kernel(const unsigned long long* __restrict__ keys, long long nh, const double* __restrict__ PsE,
+                   int64_t pitchQ, const double* __restrict__ qR, int U, const uint8_t* __restrict__ rstate,
+                   int64_t pitchS, const int32_t* __restrict__ nm, double2* __restrict__ Hh) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nh;
+         i += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long key = keys[i];
+        const int u = (int)(key & 0xffffull), sx = (int)(key >> 48);
+        const int64_t c = (int64_t)((key >> 16) & 0xffffffffull);
+        const int v = __ldg(nm + c);
+        const int n = v & 0xffff, m = (v >> 16) & 0xffff;
+        const int who = __ldg(rstate + (int64_t)n * pitchS + u) == kStateMixedR ? n : m;     // the undecided region
+        const double q = __ldg(qR + ((int64_t)who * U + u) * 2 + sx);
+        const double p = __ldg(PsE + c * pitchQ + u);
+        Hh[i] = make_double2(p, sx ? -q : q);
     }
 }
 
@@ -259,13 +322,15 @@ record_weights_kernel(const unsigned long long* __restrict__ keys, long long nd,
 }
 
 // One evaluation:
-//   out[0] = sum_{code < 3} log(a_l + b_l p) + sum_records sum_l w_l log(a_l + b_l p),   l = code
+//   out[0] = sum_{code != 3} log(a_l + b_l p) + sum_records sum_l w_l log(a_l + b_l p)
+//            + sum_half q (log(a_s + b_s p) - log(a_2 + b_2 p)),          l = code (2 for the codes 4, 5)
 //   out[1] = dE/d eta, out[2] = dE/d eps as in elm_kernel (fcd_mstep.cu).
 // FAST: the coded elements have weight exactly 1, so the objective is the log of a running product
 // (fcd_math.cuh "Sum of logs as the log of a product") and the gradient needs 1 / M only
 // (MUFU.RCP64H + Newton): ~11 fp64 instructions and two table reads per element.
 // One persistent CTA of 16 warps per SM; the plane is cut into chunks of kEvChunk elements (2 KB of
-// p + 256 code bytes, two bulk copies on one mbarrier), followed by the records as chunks of 64;
+// p + 256 code bytes, two bulk copies on one mbarrier), followed by the records as chunks of 64 and
+// the half records as chunks of 128;
 // warp g takes the chunks g, g + G, ...; every warp runs a private ring of kEvDepth stages and
 // refills a stage as soon as it has consumed it: the bytes in flight do not depend on registers.
 constexpr int kEvChunk = 256;
@@ -304,35 +369,38 @@ __device__ __forceinline__ void coded_elem(double p, int code, const double2* s_
 template <bool GRAD, bool FAST>
 __global__ void __launch_bounds__(kEvThreads, 1)
 elm_coded_kernel(const double* __restrict__ PsE, const uint8_t* __restrict__ code, long long nE,
-                 const Record* __restrict__ D, long long nd,
+                 const Record* __restrict__ D, long long nd, const double2* __restrict__ Hh, long long nh,
                  const __grid_constant__ ThetaDev th, const __grid_constant__ LogTabWindow tab, int depth,
                  double* __restrict__ out, double* __restrict__ ws) {
     extern __shared__ __align__(128) double s_dyn[];
-    __shared__ double2 s_ab[4], s_sh[4];
+    __shared__ double2 s_ab[8], s_sh[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* ring0 = reinterpret_cast<unsigned char*>(s_dyn + (FAST ? ((tab.n + 15) & ~15) : 0));
     unsigned char* ring = ring0 + (size_t)warp * depth * kEvStage;
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring0 + (size_t)kEvWarps * depth * kEvStage) + warp * depth;
     if (lane < depth) mbar_init(bars + lane, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (threadIdx.x < 4) {
+    if (threadIdx.x < 8) {
         // per-code constants {a_l, b_l} and {s_l, [l == 2]}, s = (-1, 1, 2 eta - 1) (fit.py:600-697);
-        // code 3 is neutral: log(1 + 0 p) = 0 exactly, zero gradient weight
-        const int l = threadIdx.x;
+        // code 3 is neutral: log(1 + 0 p) = 0 exactly, zero gradient weight; codes 4, 5 count as l = 2
+        const int code = threadIdx.x;
+        const int l = code >= 4 ? 2 : code;
         const double sl = l == 0 ? -1.0 : (l == 1 ? 1.0 : 2.0 * th.eta - 1.0);
-        s_ab[l] = l < 3 ? make_double2(th.al[l], th.bl[l]) : make_double2(1.0, 0.0);
-        s_sh[l] = l < 3 ? make_double2(sl, l == 2 ? 1.0 : 0.0) : make_double2(0.0, 0.0);
+        s_ab[code] = l < 3 ? make_double2(th.al[l], th.bl[l]) : make_double2(1.0, 0.0);
+        s_sh[code] = l < 3 ? make_double2(sl, l == 2 ? 1.0 : 0.0) : make_double2(0.0, 0.0);
     }
     __syncwarp();
 
     // Chunks are numbered across the two streams: the coded plane (nqf full chunks, then one partial
     // chunk if nE is not a multiple of the chunk), then the records (4 doubles each).  Full plane
     // chunks -- all but a handful -- take the short path: constant sizes, 32-bit shared addresses.
-    const long long n3 = nd * 4;
+    const long long n3 = nd * 4, n4 = nh * 2;
     const long long nqf = nE / kEvChunk;
     const long long nq0 = (nE + kEvChunk - 1) / kEvChunk, nq1 = (n3 + kEvChunk - 1) / kEvChunk;
-    const long long nq = nq0 + nq1;
+    const long long nq01 = nq0 + nq1;
+    const long long nq = nq01 + (n4 + kEvChunk - 1) / kEvChunk;
     const double* const Dd = reinterpret_cast<const double*>(D);
+    const double* const Hd = reinterpret_cast<const double*>(Hh);
     const long long W = (long long)gridDim.x * kEvWarps;
     const uint32_t ring_s = smem_u32(ring), bars_s = smem_u32(bars);
     long long ip = (long long)blockIdx.x * kEvWarps + warp;  // next chunk to issue
@@ -355,11 +423,12 @@ elm_coded_kernel(const double* __restrict__ PsE, const uint8_t* __restrict__ cod
                 tma_load_1d(ring + pd * kEvStage, PsE + ip * kEvChunk, pbytes, bars + pd);
                 tma_load_1d(ring + pd * kEvStage + kEvChunk * 8, code + ip * kEvChunk, cbytes, bars + pd);
             } else {
-                const long long i = ip - nq0;
-                const long long left = n3 - i * kEvChunk;
+                const bool half = ip >= nq01;
+                const long long i = ip - (half ? nq01 : nq0);
+                const long long left = (half ? n4 : n3) - i * kEvChunk;
                 const uint32_t bytes = (uint32_t)(left < kEvChunk ? left : kEvChunk) * 8;
                 mbar_expect_tx(bars + pd, bytes);
-                tma_load_1d(ring + pd * kEvStage, Dd + i * kEvChunk, bytes, bars + pd);
+                tma_load_1d(ring + pd * kEvStage, (half ? Hd : Dd) + i * kEvChunk, bytes, bars + pd);
             }
         }
         ip += W;
@@ -416,7 +485,7 @@ elm_coded_kernel(const double* __restrict__ PsE, const uint8_t* __restrict__ cod
     double obj = a0.obj + a1.obj, ge = a0.ge + a1.ge, gh = a0.gh + a1.gh;
     const double al[3] = {th.al[0], th.al[1], th.al[2]}, bl[3] = {th.bl[0], th.bl[1], th.bl[2]};
     const double sl[3] = {-1.0, 1.0, 2.0 * th.eta - 1.0};
-    for (; cp < nq; advance()) {                             // records {p, w_0, w_1, w_2}: real weights, three logs each
+    for (; cp < nq01; advance()) {                           // records {p, w_0, w_1, w_2}: real weights, three logs each
         const long long left = (n3 - (cp - nq0) * kEvChunk) >> 2;
         const int cnt = (int)(left < kEvChunk / 4 ? left : kEvChunk / 4);
         mbar_wait(bars + d, phase);
@@ -440,6 +509,33 @@ elm_coded_kernel(const double* __restrict__ PsE, const uint8_t* __restrict__ cod
                     } else {
                         obj = fma(w[l], fast_log<FAST>(M, s_tab), obj);
                     }
+                }
+            }
+        }
+    }
+    for (; cp < nq; advance()) {                             // half records {p, +-q}: q (log M_s - log M_2), sign bit = s
+        const long long left = (n4 - (cp - nq01) * kEvChunk) >> 1;
+        const int cnt = (int)(left < kEvChunk / 2 ? left : kEvChunk / 2);
+        mbar_wait(bars + d, phase);
+        const double2* st = reinterpret_cast<const double2*>(ring + d * kEvStage);
+#pragma unroll
+        for (int j = 0; j < kEvChunk / 64; ++j) {
+            const int e = 32 * j + lane;
+            if (e < cnt) {
+                const double2 r = st[e];
+                const bool sx = __double2hiint(r.y) < 0;
+                const double q = fabs(r.y);
+                const double Mx = fma(sx ? bl[1] : bl[0], r.x, sx ? al[1] : al[0]), M2 = fma(bl[2], r.x, al[2]);
+                if (GRAD) {
+                    double rx, r2;
+                    const double lx = fast_log_rcp<FAST>(Mx, s_tab, rx), l2 = fast_log_rcp<FAST>(M2, s_tab, r2);
+                    obj = fma(q, lx - l2, obj);
+                    const double qn = q * mix_num(r.x);
+                    const double dx = qn * rx, d2 = qn * r2;
+                    ge += fma(sx ? 1.0 : -1.0, dx, -sl[2] * d2);
+                    gh -= d2;
+                } else {
+                    obj = fma(q, fast_log<FAST>(Mx, s_tab) - fast_log<FAST>(M2, s_tab), obj);
                 }
             }
         }
@@ -479,69 +575,87 @@ int64_t fcd_code_pitch(int32_t U) { return ((int64_t)U + 15) & ~(int64_t)15; }
 int fcd_code_plane(const double* P, int64_t planeStride, int64_t C, int32_t U, int64_t pitchU,
                    const uint8_t* fstate, const uint8_t* rstate, int64_t pitchS, const int32_t* nm,
                    double* PsE, uint8_t* kcache, uint8_t* code, int64_t pitchQ, int32_t* counts, int64_t* blockoff,
-                   double* total1, void* stream) {
+                   double* total2, void* stream) {
     FCD_REQUIRE(P != nullptr && fstate != nullptr && rstate != nullptr && nm != nullptr && PsE != nullptr &&
-                kcache != nullptr && code != nullptr && counts != nullptr && blockoff != nullptr && total1 != nullptr,
+                kcache != nullptr && code != nullptr && counts != nullptr && blockoff != nullptr && total2 != nullptr,
                 "fcd_code_plane: NULL argument");
     FCD_REQUIRE(C >= 1 && U >= 1 && pitchU >= U && pitchU % 2 == 0 && planeStride % 2 == 0 && pitchQ >= pitchU &&
                 pitchQ % 16 == 0 && pitchS >= pitchQ && pitchS % 2 == 0,
                 "fcd_code_plane: bad shape (even pitches, pitchQ % 16 == 0, pitchS >= pitchQ >= pitchU)");
-    FCD_REQUIRE(((reinterpret_cast<uintptr_t>(P) | reinterpret_cast<uintptr_t>(PsE) | reinterpret_cast<uintptr_t>(code)) & 15) == 0 &&
-                (reinterpret_cast<uintptr_t>(rstate) & 1) == 0 && (reinterpret_cast<uintptr_t>(blockoff) & 7) == 0,
-                "fcd_code_plane: planes / code must be 16-byte aligned");
+    FCD_REQUIRE(((reinterpret_cast<uintptr_t>(P) | reinterpret_cast<uintptr_t>(PsE) | reinterpret_cast<uintptr_t>(code) |
+                  reinterpret_cast<uintptr_t>(blockoff)) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(rstate) & 1) == 0 && (reinterpret_cast<uintptr_t>(counts) & 7) == 0,
+                "fcd_code_plane: planes / code / blockoff must be 16-byte aligned, counts 8-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t nblocks = (C + kRowBlock - 1) / kRowBlock;
-    // blockoff doubles as the block totals' storage: [nblocks] totals followed by [nblocks] offsets
-    long long* bt = reinterpret_cast<long long*>(blockoff);
+    // blockoff doubles as the block totals' storage: [nblocks] totals followed by [nblocks] offsets (pairs)
+    longlong2* bt = reinterpret_cast<longlong2*>(blockoff);
     code_plane_kernel<<<(unsigned)nblocks, kBucketThreads, 0, st>>>(P, planeStride, PsE, kcache, fstate, rstate, pitchS,
-                                                                    nm, C, U, pitchU, pitchQ, code, counts, bt);
+                                                                    nm, C, U, pitchU, pitchQ, code,
+                                                                    reinterpret_cast<int2*>(counts), bt);
     int rc = check_launch("fcd_code_plane");
     if (rc) return rc;
-    record_scan_kernel<<<1, 1024, 0, st>>>(bt, nblocks, bt + nblocks, total1);
+    record_scan_kernel<<<1, 1024, 0, st>>>(bt, nblocks, bt + nblocks, total2);
     return check_launch("fcd_code_plane(scan)");
 }
 
 int fcd_code_records(const double* P, int64_t planeStride, const double* PsE, const uint8_t* code, int64_t pitchQ,
                      const double* L, const double* Lsum, int64_t C, int32_t U, int64_t pitchU,
-                     const double* qF, const uint8_t* fstate, const double* qR, int32_t N, const int32_t* nm,
-                     const int32_t* counts, const int64_t* blockoff, uint64_t* keys, int64_t* rowoff, double* D,
-                     int64_t nd, double* out1, double* ws, void* stream) {
+                     const double* qF, const uint8_t* fstate, const double* qR, const uint8_t* rstate, int64_t pitchS,
+                     int32_t N, const int32_t* nm, const int32_t* counts, const int64_t* blockoff,
+                     uint64_t* keysF, uint64_t* keysH, int64_t* rowoff, double* D, int64_t nd, double* Hh, int64_t nh,
+                     double* out1, double* ws, void* stream) {
     FCD_REQUIRE(P != nullptr && PsE != nullptr && code != nullptr && L != nullptr && Lsum != nullptr && qF != nullptr &&
-                fstate != nullptr && qR != nullptr && nm != nullptr && counts != nullptr && blockoff != nullptr &&
-                keys != nullptr && rowoff != nullptr && D != nullptr && out1 != nullptr && ws != nullptr,
-                "fcd_code_records: NULL argument");
+                fstate != nullptr && qR != nullptr && rstate != nullptr && nm != nullptr && counts != nullptr &&
+                blockoff != nullptr && keysF != nullptr && keysH != nullptr && rowoff != nullptr && D != nullptr &&
+                Hh != nullptr && out1 != nullptr && ws != nullptr, "fcd_code_records: NULL argument");
     FCD_REQUIRE(C >= 1 && C < (1ll << 32) && U >= 1 && U < 65536 && pitchU >= U && pitchU % 2 == 0 &&
-                pitchQ >= pitchU && pitchQ % 16 == 0 && N >= 2 && N < 65536 && nd >= 0, "fcd_code_records: bad shape");
-    FCD_REQUIRE((reinterpret_cast<uintptr_t>(D) & 31) == 0 && (reinterpret_cast<uintptr_t>(keys) & 7) == 0,
-                "fcd_code_records: records must be 32-byte aligned");
+                pitchQ >= pitchU && pitchQ % 16 == 0 && pitchS >= U && N >= 2 && N < 65536 && nd >= 0 && nh >= 0,
+                "fcd_code_records: bad shape");
+    FCD_REQUIRE((reinterpret_cast<uintptr_t>(D) & 31) == 0 &&
+                ((reinterpret_cast<uintptr_t>(Hh) | reinterpret_cast<uintptr_t>(rowoff) | reinterpret_cast<uintptr_t>(blockoff)) & 15) == 0 &&
+                ((reinterpret_cast<uintptr_t>(keysF) | reinterpret_cast<uintptr_t>(keysH) | reinterpret_cast<uintptr_t>(counts)) & 7) == 0,
+                "fcd_code_records: records must be 32-byte, half records / rowoff 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t nblocks = (C + kRowBlock - 1) / kRowBlock;
     int rc = 0;
-    if (nd > 0) {
+    if (nd + nh > 0) {
         int64_t grid = nblocks;                              // persistent: the resident CTAs share the row blocks
         if (grid > (int64_t)sm_count() * 4) grid = (int64_t)sm_count() * 4;
         record_keys_kernel<<<(unsigned)grid, kBucketThreads, 0, st>>>(
-            code, fstate, C, U, pitchQ, counts, reinterpret_cast<const long long*>(blockoff) + nblocks,
-            reinterpret_cast<unsigned long long*>(keys), reinterpret_cast<long long*>(rowoff));
+            code, fstate, C, U, pitchQ, reinterpret_cast<const int2*>(counts),
+            reinterpret_cast<const longlong2*>(blockoff) + nblocks, reinterpret_cast<unsigned long long*>(keysF),
+            reinterpret_cast<unsigned long long*>(keysH), reinterpret_cast<longlong2*>(rowoff));
         rc = check_launch("fcd_code_records(keys)");
+        if (rc) return rc;
+    }
+    if (nh > 0) {
+        int64_t hgrid = (nh + kBucketThreads - 1) / kBucketThreads;
+        if (hgrid > (int64_t)sm_count() * 8) hgrid = (int64_t)sm_count() * 8;
+        record_half_kernel<<<(unsigned)hgrid, kBucketThreads, 0, st>>>(
+            reinterpret_cast<const unsigned long long*>(keysH), nh, PsE, pitchQ, qR, U, rstate, pitchS, nm,
+            reinterpret_cast<double2*>(Hh));
+        rc = check_launch("fcd_code_records(half)");
         if (rc) return rc;
     }
     int64_t rgrid = (nd + kBucketThreads - 1) / kBucketThreads;       // nd == 0: one CTA writes out1[0] = Lsum
     if (rgrid > (int64_t)sm_count() * 8) rgrid = (int64_t)sm_count() * 8;
     if (rgrid < 1) rgrid = 1;
     record_weights_kernel<<<(unsigned)rgrid, kBucketThreads, 0, st>>>(
-        reinterpret_cast<const unsigned long long*>(keys), nd, P, planeStride, PsE, pitchQ, L, pitchU, Lsum, qF, qR, U, nm,
+        reinterpret_cast<const unsigned long long*>(keysF), nd, P, planeStride, PsE, pitchQ, L, pitchU, Lsum, qF, qR, U, nm,
         reinterpret_cast<Record*>(D), out1, ws);
     return check_launch("fcd_code_records");
 }
 
 int fcd_elm_coded(const double* PsE, const uint8_t* code, int64_t nE, const double* D, int64_t nd,
-                  const fcd_theta* theta_host, int32_t want_grad, double* out3, double* ws, void* stream) {
+                  const double* Hh, int64_t nh, const fcd_theta* theta_host, int32_t want_grad, double* out3, double* ws,
+                  void* stream) {
     FCD_REQUIRE(PsE != nullptr && code != nullptr && theta_host != nullptr && out3 != nullptr && ws != nullptr &&
-                (nd == 0 || D != nullptr) && nE >= 1 && nd >= 0, "fcd_elm_coded: bad argument");
-    FCD_REQUIRE(((reinterpret_cast<uintptr_t>(PsE) | reinterpret_cast<uintptr_t>(code)) & 15) == 0 &&
+                (nd == 0 || D != nullptr) && (nh == 0 || Hh != nullptr) && nE >= 1 && nd >= 0 && nh >= 0,
+                "fcd_elm_coded: bad argument");
+    FCD_REQUIRE(((reinterpret_cast<uintptr_t>(PsE) | reinterpret_cast<uintptr_t>(code) | reinterpret_cast<uintptr_t>(Hh)) & 15) == 0 &&
                 (reinterpret_cast<uintptr_t>(D) & 31) == 0,
-                "fcd_elm_coded: plane / code must be 16-byte aligned, records 32-byte aligned");
+                "fcd_elm_coded: plane / code / half records must be 16-byte aligned, records 32-byte aligned");
     const ThetaDev th = make_theta_dev(*theta_host, 0);
     cudaStream_t st = (cudaStream_t)stream;
     LogTabWindow tab;
@@ -552,7 +666,8 @@ int fcd_elm_coded(const double* PsE, const uint8_t* code, int64_t nE, const doub
     while (depth > 2 && tbytes + ev_ring_bytes(depth) > kSmemBudget) --depth;
     FCD_REQUIRE(tbytes + ev_ring_bytes(depth) <= kSmemBudget, "fcd_elm_coded: shared memory budget exceeded");
     const size_t smem = tbytes + ev_ring_bytes(depth);
-    const long long chunks = (nE + kEvChunk - 1) / kEvChunk + (nd * 4 + kEvChunk - 1) / kEvChunk;
+    const long long chunks = (nE + kEvChunk - 1) / kEvChunk + (nd * 4 + kEvChunk - 1) / kEvChunk +
+                             (nh * 2 + kEvChunk - 1) / kEvChunk;
     long long grid = (chunks + kEvWarps - 1) / kEvWarps;
     if (grid > sm_count()) grid = sm_count();                // one persistent CTA per SM
     if (grid < 1) grid = 1;
@@ -565,7 +680,8 @@ int fcd_elm_coded(const double* PsE, const uint8_t* code, int64_t nE, const doub
             attr_set = true;                                                                             \
         }                                                                                                \
         elm_coded_kernel<G_, F_><<<(unsigned)grid, kEvThreads, smem, st>>>(                              \
-            PsE, code, nE, reinterpret_cast<const Record*>(D), nd, th, tab, depth, out3, ws);            \
+            PsE, code, nE, reinterpret_cast<const Record*>(D), nd, reinterpret_cast<const double2*>(Hh), nh, th, \
+            tab, depth, out3, ws);                                                                       \
     } while (0)
     if (want_grad) { if (fast) FCD_EC(true, true); else FCD_EC(true, false); }
     else           { if (fast) FCD_EC(false, true); else FCD_EC(false, false); }

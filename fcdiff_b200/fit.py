@@ -441,10 +441,10 @@ class UnsharedRegionFit(object):
             inp['PsE'] = _dev.zeros((Cl, pitchQ))
             inp['kcE'] = torch.full((Cl,), 255, dtype=torch.uint8, device=_dev.device())
             inp['code'] = _dev.empty((Cl * pitchQ + 256,), torch.uint8)
-            inp['bk_counts'] = _dev.empty((Cl,), torch.int32)
-            inp['bk_rowoff'] = _dev.empty((Cl,), torch.int64)
-            inp['bk_offs'] = _dev.empty((2 * int(lib.fcd_bucket_blocks(Cl)),), torch.int64)
-        tot = self._result(1, tag="records")
+            inp['bk_counts'] = _dev.empty((Cl, 2), torch.int32)      # {records, half records} per row
+            inp['bk_rowoff'] = _dev.empty((Cl, 2), torch.int64)
+            inp['bk_offs'] = _dev.empty((4 * int(lib.fcd_bucket_blocks(Cl)),), torch.int64)
+        tot = self._result(2, tag="records")
         planeStride = max(Cl, 1) * pitchU
         with _dev.timed(self.profile, "K3b_code_plane"):
             _lib.check(lib.fcd_code_plane(
@@ -452,15 +452,18 @@ class UnsharedRegionFit(object):
                 rstate.shape[1], _dev.ptr(inp['nm']), _dev.ptr(inp['PsE']), _dev.ptr(inp['kcE']),
                 _dev.ptr(inp['code']), pitchQ, _dev.ptr(inp['bk_counts']), _dev.ptr(inp['bk_offs']),
                 _dev.ptr(tot.dev), stream), "fcd_code_plane")
-        nd = int(tot.read(stream)[0])
-        use_tiered = self.elm_path == "auto" and nd * 4 > Cl * U
+        (nd, nh) = (int(v) for v in tot.read(stream))
+        use_tiered = self.elm_path == "auto" and nd * 4 + nh * 2 > Cl * U
         if self.shards is not None:            # the ranks must take the same form: its collectives differ
             use_tiered = self.shards.any_rank(use_tiered)
         if use_tiered:
             return None
         if inp.get('bk_D') is None or inp['bk_D'].numel() < 4 * nd:
-            inp['bk_D'] = _dev.empty((4 * max(nd, Cl * U // 4, 1),))
-            inp['bk_K'] = _dev.empty((max(nd, Cl * U // 4, 1),), torch.int64)
+            inp['bk_D'] = _dev.empty((4 * max(nd, Cl * U // 8, 1),))
+            inp['bk_K'] = _dev.empty((max(nd, Cl * U // 8, 1),), torch.int64)
+        if inp.get('bk_H') is None or inp['bk_H'].numel() < 2 * nh:
+            inp['bk_H'] = _dev.empty((2 * max(nh, Cl * U // 4, 1),))
+            inp['bk_KH'] = _dev.empty((max(nh, Cl * U // 4, 1),), torch.int64)
         if inp.get('Lsum') is None:
             inp['Lsum'] = _dev.empty((1,))
             _lib.check(lib.fcd_plane_sum(_dev.ptr(inp['L']), Cl, U, pitchU, _dev.ptr(inp['Lsum']),
@@ -468,13 +471,15 @@ class UnsharedRegionFit(object):
         with _dev.timed(self.profile, "K3b_records"):
             _lib.check(lib.fcd_code_records(
                 _dev.ptr(inp['P']), planeStride, _dev.ptr(inp['PsE']), _dev.ptr(inp['code']), pitchQ,
-                _dev.ptr(inp['L']), _dev.ptr(inp['Lsum']), Cl, U, pitchU, _dev.ptr(qF[c0 * 3:]), _dev.ptr(fstate[c0:]), _dev.ptr(qR), N,
+                _dev.ptr(inp['L']), _dev.ptr(inp['Lsum']), Cl, U, pitchU, _dev.ptr(qF[c0 * 3:]), _dev.ptr(fstate[c0:]),
+                _dev.ptr(qR), _dev.ptr(rstate), rstate.shape[1], N,
                 _dev.ptr(inp['nm']), _dev.ptr(inp['bk_counts']), _dev.ptr(inp['bk_offs']), _dev.ptr(inp['bk_K']),
-                _dev.ptr(inp['bk_rowoff']), _dev.ptr(inp['bk_D']), nd, _dev.ptr(res4.dev[3:]),
-                _dev.ptr(_dev.workspace()), stream), "fcd_code_records")
+                _dev.ptr(inp['bk_KH']), _dev.ptr(inp['bk_rowoff']), _dev.ptr(inp['bk_D']), nd, _dev.ptr(inp['bk_H']), nh,
+                _dev.ptr(res4.dev[3:]), _dev.ptr(_dev.workspace()), stream), "fcd_code_records")
         inp['code_verR'] = self._mR.version         # codes and key lists describe this q_R: the next E-step may use them
         inp['pitchQ'] = pitchQ
-        return (_dev.ptr(inp['PsE']), _dev.ptr(inp['code']), Cl * pitchQ, _dev.ptr(inp['bk_D']), nd)
+        return (_dev.ptr(inp['PsE']), _dev.ptr(inp['code']), Cl * pitchQ, _dev.ptr(inp['bk_D']), nd,
+                _dev.ptr(inp['bk_H']), nh)
 
     def _theta(self, use_snapshot=True):
         m = self.model
@@ -684,8 +689,8 @@ class UnsharedRegionFit(object):
                 _lib.check(lib.fcd_estep_qF_coded(
                     _dev.ptr(inp['S1']), _dev.ptr(inp['S2']), H, _dev.ptr(inp['P']), max(Cl, 1) * inp['pitchU'],
                     Cl, U, inp['pitchU'], _dev.ptr(qR), N, _dev.ptr(inp['nm']), _dev.ptr(inp['code']), inp['pitchQ'],
-                    _dev.ptr(inp['bk_counts']), _dev.ptr(inp['bk_K']), _dev.ptr(inp['bk_rowoff']),
-                    ctypes.byref(th), _dev.ptr(lqF[c0 * 3:]), _dev.ptr(qF[c0 * 3:]), _dev.stream()),
+                    _dev.ptr(inp['bk_counts']), _dev.ptr(inp['bk_K']), _dev.ptr(inp['bk_KH']), _dev.ptr(inp['bk_rowoff']),
+                    _dev.ptr(inp['bk_H']), ctypes.byref(th), _dev.ptr(lqF[c0 * 3:]), _dev.ptr(qF[c0 * 3:]), _dev.stream()),
                     "fcd_estep_qF_coded")
             if self.shards is not None:
                 self.shards.allgather_edges(lqF_buf, qF_buf, C)

@@ -163,14 +163,16 @@ FCD_API int fcd_estep_qF(const double* S1, const double* S2, int32_t H,
 /* The same E-step driven by the code pass of the previous M-step (fcd_code_plane / fcd_code_records:
  * valid while q_R has not changed since): the coded elements need no peak-state decoding and no
  * queue -- one code byte selects the constants of a running product -- and the elements with a
- * mixed region are taken from the row's key list.  code / counts / keys / rowoff as written by the
- * code pass for the same local rows; rows whose edge was unpeaked then (counts[c] == 3 U) are
- * evaluated in full. */
+ * mixed region are taken from the row's key lists (half records: three differences of logs with
+ * one weight; full records: nine logs).  code / counts / keysF / keysH / rowoff / Hh as written by
+ * the code pass for the same local rows; rows whose edge was unpeaked then (counts[c][0] == 3 U)
+ * are evaluated in full. */
 FCD_API int fcd_estep_qF_coded(const double* S1, const double* S2, int32_t H,
                        const double* P, int64_t planeStride, int64_t C, int32_t U, int64_t pitchU,
                        const double* qR, int32_t N, const int32_t* nm,
-                       const uint8_t* code, int64_t pitchQ, const int32_t* counts, const uint64_t* keys,
-                       const int64_t* rowoff, const fcd_theta* theta_host, double* lqF, double* qF, void* stream);
+                       const uint8_t* code, int64_t pitchQ, const int32_t* counts, const uint64_t* keysF,
+                       const uint64_t* keysH, const int64_t* rowoff, const double* Hh,
+                       const fcd_theta* theta_host, double* lqF, double* qF, void* stream);
 
 /* Patient-major copy of an edge-major plane: dst[u - u0][c] = src[c][u]
  * for u in [u0, u0+Ul), c in [0, C).  Built once per fit. */
@@ -258,17 +260,22 @@ FCD_API int fcd_elm_const(const double* L, int64_t C, int32_t U, int64_t pitchU,
  *        from P only when kcache[c] != fstate[c]; kcache starts at 255, PsE zero-filled);
  *        pitchQ = fcd_code_pitch(U): U rounded up to 16, so that code rows are 16-byte aligned;
  *   code [C][pitchQ] u8 (+ 16 bytes of slack): l* in 0..2 for elements whose edge and
- *        regions are peaked (weight exactly 1, one log), 3 for all others;
+ *        regions are peaked (weight exactly 1, one log); 4 + s for an element with ONE undecided,
+ *        normalised region and the other in state s -- it counts as l = 2 with weight 1 and
+ *        adds a half record; 3 for all others;
+ *   half records {p, +-q_s} (16 bytes, sign bit = s), nh of them: the correction
+ *        q_s (log M_s - log M_2) of the elements coded 4 + s (fit.py:382-406 with q_0 + q_1 = 1);
  *   records {p, w_0, w_1, w_2} (32 bytes) for all other elements, nd of them
  * -- and fcd_elm_coded reduces them: 9 bytes per edge-patient per evaluation, no row
  * structure, no partition of the elements.
  *   fcd_plane_sum: out1[0] = sum of a [C][U] plane -- the total of the L plane, once per cache;
- *   fcd_code_plane: refreshes PsE, writes code, counts[c] = records of row c (int32),
- *     blockoff: scratch of 2 * fcd_bucket_blocks(C) int64 (totals and exclusive prefix
- *     sums of blocks of 16 rows), total1[0] = nd (as a double);
- *   fcd_code_records: D receives the nd records; keys [nd] uint64 = (tag << 48 | c << 16 | u) of every
- *     record and rowoff [C] int64 = first key of each row are kept for fcd_estep_qF_coded (not written
- *     when nd == 0); out1[0] = the theta-free part of E_lM
+ *   fcd_code_plane: refreshes PsE, writes code, counts[c] = {records, half records} of row c
+ *     (int32 x 2), blockoff: scratch of 4 * fcd_bucket_blocks(C) int64 (totals and exclusive
+ *     prefix sums of blocks of 16 rows), total2 = {nd, nh} (as doubles);
+ *   fcd_code_records: D receives the nd records, Hh the nh half records; keysF [nd] / keysH [nh]
+ *     uint64 = (tag << 48 | c << 16 | u) of every record / half record and rowoff [C][2] int64 =
+ *     first key of each row in either list are kept for fcd_estep_qF_coded (not written when
+ *     nd + nh == 0); out1[0] = the theta-free part of E_lM
  *     (same value as fcd_elm_const), formed as Lsum[0] (device, from fcd_plane_sum)
  *     corrected by the record elements only;
  *   fcd_elm_coded: nE = C * pitchQ elements of PsE / code; out3 as fcd_elm_obj_grad. */
@@ -279,14 +286,16 @@ FCD_API int fcd_plane_sum(const double* X, int64_t C, int32_t U, int64_t pitchU,
 FCD_API int fcd_code_plane(const double* P, int64_t planeStride, int64_t C, int32_t U, int64_t pitchU,
                    const uint8_t* fstate, const uint8_t* rstate, int64_t pitchS, const int32_t* nm,
                    double* PsE, uint8_t* kcache, uint8_t* code, int64_t pitchQ, int32_t* counts, int64_t* blockoff,
-                   double* total1, void* stream);
+                   double* total2, void* stream);
 FCD_API int fcd_code_records(const double* P, int64_t planeStride, const double* PsE, const uint8_t* code,
                      int64_t pitchQ, const double* L, const double* Lsum, int64_t C, int32_t U, int64_t pitchU,
-                     const double* qF, const uint8_t* fstate, const double* qR, int32_t N, const int32_t* nm,
-                     const int32_t* counts, const int64_t* blockoff, uint64_t* keys, int64_t* rowoff, double* D,
-                     int64_t nd, double* out1, double* ws, void* stream);
+                     const double* qF, const uint8_t* fstate, const double* qR, const uint8_t* rstate, int64_t pitchS,
+                     int32_t N, const int32_t* nm, const int32_t* counts, const int64_t* blockoff,
+                     uint64_t* keysF, uint64_t* keysH, int64_t* rowoff, double* D, int64_t nd, double* Hh, int64_t nh,
+                     double* out1, double* ws, void* stream);
 FCD_API int fcd_elm_coded(const double* PsE, const uint8_t* code, int64_t nE, const double* D, int64_t nd,
-                  const fcd_theta* theta_host, int32_t want_grad, double* out3, double* ws, void* stream);
+                  const double* Hh, int64_t nh, const fcd_theta* theta_host, int32_t want_grad, double* out3,
+                  double* ws, void* stream);
 
 /* K4 -- free-energy terms; replaces `_eval_energy` and `_eval_E_*`
  * (fcdiff/fit.py:142-155, 447-539).  out[0..5] = E_lp_F, E_lp_B_g_F, E_lp_R,

@@ -17,10 +17,16 @@ from fcdiff_b200 import util            # noqa: E402
 
 
 def _pair_code(sn, sm):
-    """code of an element from the two regions' peak states (csrc/fcd_streams.cu:pair_code)."""
+    """code of an element from the two regions' peak states (csrc/fcd_streams.cu:pair_code):
+    0..2 pair state of two decided regions, 4 + s one undecided normalised region (state 2) beside a
+    region in state s, 3 anything else."""
     o = sn | sm
     if o < 2:
         return ((sn ^ sm) << 1) + (sn & sm)
+    if sn == 2 and sm < 2:
+        return 4 + sm
+    if sm == 2 and sn < 2:
+        return 4 + sn
     return 3
 
 
@@ -37,7 +43,7 @@ def test_code_plane_and_evaluator_match_numpy(N, U):
     L = rng.randn(C, pitchU)
     fstate = rng.choice([0, 1, 2, 3], size=C, p=[0.3, 0.3, 0.3, 0.1]).astype(np.uint8)
     rstate = np.full((N, pitchS), 4, np.uint8)
-    rstate[:, :U] = rng.choice([0, 1, 2], size=(N, U), p=[0.6, 0.3, 0.1])
+    rstate[:, :U] = rng.choice([0, 1, 2, 3], size=(N, U), p=[0.55, 0.25, 0.15, 0.05])
     # posteriors consistent with the states (peaked rows are exactly one-hot)
     qF = np.zeros((C, 3))
     for c in range(C):
@@ -46,7 +52,12 @@ def test_code_plane_and_evaluator_match_numpy(N, U):
     for n in range(N):
         for u in range(U):
             s = rstate[n, u]
-            qR[n, u] = rng.dirichlet([2.0, 2.0]) if s == 2 else np.eye(2)[s]
+            if s == 2:
+                qR[n, u] = rng.dirichlet([2.0, 2.0])                    # undecided, normalised
+            elif s == 3:
+                qR[n, u] = rng.dirichlet([2.0, 2.0]) * 1.25             # undecided, not normalised ("loose")
+            else:
+                qR[n, u] = np.eye(2)[s]
     nm = np.array([(util.c_to_nm(c)[0] | (util.c_to_nm(c)[1] << 16)) for c in range(C)], dtype=np.int32)
 
     d = {k: _dev.upload(v) for (k, v) in dict(P=P, L=L, qF=qF.reshape(-1), qR=qR.reshape(-1)).items()}
@@ -56,29 +67,33 @@ def test_code_plane_and_evaluator_match_numpy(N, U):
     PsE = _dev.zeros((C, pitchQ))
     kc = torch.full((C,), 255, dtype=torch.uint8, device="cuda")
     code = _dev.empty((C * pitchQ + 256,), torch.uint8)
-    counts = _dev.empty((C,), torch.int32)
-    offs = _dev.empty((2 * int(lib.fcd_bucket_blocks(C)),), torch.int64)
-    tot = _dev.zeros((1,))
+    counts = _dev.empty((C, 2), torch.int32)
+    offs = _dev.empty((4 * int(lib.fcd_bucket_blocks(C)),), torch.int64)
+    tot = _dev.zeros((2,))
+    # the peak states the library derives from these posteriors are the ones drawn above
+    rs_lib = _dev.empty((N, pitchS), torch.uint8)
+    _lib.check(lib.fcd_peak_states_R(_dev.ptr(d['qR']), N, U, pitchS, _dev.ptr(rs_lib), _dev.stream()), "fcd_peak_states_R")
+    nptest.assert_array_equal(rs_lib.cpu().numpy(), rstate)
     st = _dev.stream()
     _lib.check(lib.fcd_code_plane(_dev.ptr(d['P']), C * pitchU, C, U, pitchU, _dev.ptr(fs), _dev.ptr(rs), pitchS,
                                   _dev.ptr(nmd), _dev.ptr(PsE), _dev.ptr(kc), _dev.ptr(code), pitchQ, _dev.ptr(counts),
                                   _dev.ptr(offs), _dev.ptr(tot), st), "fcd_code_plane")
     # ---- NumPy restatement of the code pass
     want_code = np.full((C, pitchQ), 3, np.uint8)
-    want_cnt = np.zeros(C, np.int64)
+    want_cnt = np.zeros((C, 2), np.int64)
     for c in range(C):
         (n, m) = util.c_to_nm(c)
         if fstate[c] == 3:
-            want_cnt[c] = 3 * U
+            want_cnt[c, 0] = 3 * U
             continue
         for u in range(U):
             want_code[c, u] = _pair_code(int(rstate[n, u]), int(rstate[m, u]))
-        want_cnt[c] = int((want_code[c, :U] == 3).sum())
+        want_cnt[c] = (int((want_code[c, :U] == 3).sum()), int((want_code[c, :U] >= 4).sum()))
     got_code = code[:C * pitchQ].cpu().numpy().reshape(C, pitchQ)
     nptest.assert_array_equal(got_code, want_code)
     nptest.assert_array_equal(counts.cpu().numpy(), want_cnt)
-    nd = int(tot.cpu().numpy()[0])
-    assert nd == want_cnt.sum()
+    (nd, nh) = (int(v) for v in tot.cpu().numpy())
+    assert (nd, nh) == tuple(want_cnt.sum(axis=0)) and nh > 0
     got_PsE = PsE.cpu().numpy()
     for c in range(C):
         if fstate[c] < 3:
@@ -93,15 +108,27 @@ def test_code_plane_and_evaluator_match_numpy(N, U):
     nptest.assert_allclose(Lsum.cpu().numpy()[0], L[:, :U].sum(), rtol=1e-12, atol=1e-9)
     D = _dev.empty((4 * max(nd, 1),))
     K = _dev.empty((max(nd, 1),), torch.int64)
-    RO = _dev.empty((C,), torch.int64)
+    KH = _dev.empty((max(nh, 1),), torch.int64)
+    Hh = _dev.empty((2 * max(nh, 1),))
+    RO = _dev.empty((C, 2), torch.int64)
     out = _dev.zeros((4,))
     _lib.check(lib.fcd_code_records(_dev.ptr(d['P']), C * pitchU, _dev.ptr(PsE), _dev.ptr(code), pitchQ, _dev.ptr(d['L']),
-                                    _dev.ptr(Lsum), C, U, pitchU, _dev.ptr(d['qF']), _dev.ptr(fs), _dev.ptr(d['qR']), N,
-                                    _dev.ptr(nmd), _dev.ptr(counts), _dev.ptr(offs), _dev.ptr(K), _dev.ptr(RO), _dev.ptr(D), nd,
+                                    _dev.ptr(Lsum), C, U, pitchU, _dev.ptr(d['qF']), _dev.ptr(fs), _dev.ptr(d['qR']),
+                                    _dev.ptr(rs), pitchS, N, _dev.ptr(nmd), _dev.ptr(counts), _dev.ptr(offs), _dev.ptr(K),
+                                    _dev.ptr(KH), _dev.ptr(RO), _dev.ptr(D), nd, _dev.ptr(Hh), nh,
                                     _dev.ptr(out[3:]), _dev.ptr(ws), st), "fcd_code_records")
+    # half records: {p of the dominant state, +-q_s of the undecided region}, in row order
+    keysH = KH.cpu().numpy()[:nh].astype(np.uint64)
+    half = Hh.cpu().numpy()[:2 * nh].reshape(nh, 2)
+    for i in range(0, nh, max(1, nh // 50)):
+        (u, c, sx) = (int(keysH[i] & np.uint64(0xffff)), int((keysH[i] >> np.uint64(16)) & np.uint64(0xffffffff)), int(keysH[i] >> np.uint64(48)))
+        (n, m) = util.c_to_nm(c)
+        who = n if rstate[n, u] == 2 else m
+        assert want_code[c, u] == 4 + sx and half[i, 0] == P[fstate[c], c, u]
+        assert abs(half[i, 1]) == qR[who, u, sx] and bool(np.signbit(half[i, 1])) == bool(sx)
     (eta, eps) = (0.37, 0.12)
     th = _lib.make_theta(0.1, eta, eps, [0.2, 0.5, 0.3], [-0.1, 0.0, 0.1], [0.1, 0.1, 0.1])
-    _lib.check(lib.fcd_elm_coded(_dev.ptr(PsE), _dev.ptr(code), C * pitchQ, _dev.ptr(D), nd, ctypes.byref(th), 1,
+    _lib.check(lib.fcd_elm_coded(_dev.ptr(PsE), _dev.ptr(code), C * pitchQ, _dev.ptr(D), nd, _dev.ptr(Hh), nh, ctypes.byref(th), 1,
                                  _dev.ptr(out), _dev.ptr(ws), st), "fcd_elm_coded")
     got = out.cpu().numpy()
     epsl = np.array([1 - eps, eps, eta * eps + (1 - eta) * (1 - eps)])
@@ -134,7 +161,8 @@ def test_code_plane_and_evaluator_match_numpy(N, U):
     (S1d, S2d) = (_dev.upload(S1), _dev.upload(S2))
     _lib.check(lib.fcd_estep_qF_coded(_dev.ptr(S1d), _dev.ptr(S2d), H, _dev.ptr(d['P']), C * pitchU, C, U, pitchU,
                                       _dev.ptr(d['qR']), N, _dev.ptr(nmd), _dev.ptr(code), pitchQ, _dev.ptr(counts),
-                                      _dev.ptr(K), _dev.ptr(RO), ctypes.byref(th), _dev.ptr(lqF_c), _dev.ptr(qF_c), st),
+                                      _dev.ptr(K), _dev.ptr(KH), _dev.ptr(RO), _dev.ptr(Hh), ctypes.byref(th), _dev.ptr(lqF_c),
+                                      _dev.ptr(qF_c), st),
                "fcd_estep_qF_coded")
     (lqF_p, qF_p) = (_dev.zeros((C * 3,)), _dev.zeros((C * 3,)))
     _lib.check(lib.fcd_estep_qF(_dev.ptr(S1d), _dev.ptr(S2d), H, _dev.ptr(d['P']), C * pitchU, C, U, pitchU,
