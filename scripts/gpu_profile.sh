@@ -9,6 +9,6 @@ $CMD > gpurun_out/plain_bench.json 2> gpurun_out/plain_bench.err || { echo "plai
 ncu --metrics gpu__time_duration.sum --clock-control none -s 0 -c 600 --csv --log-file gpurun_out/launches_$TAG.csv \
     $CMD > gpurun_out/ncu_launches.log 2>&1
 ncu --set full --clock-control none --import-source on \
-    -k regex:"elm_coded|estep_qF_coded|sweep_kernel|region_weights|code_plane|record_keys|record_weights" -s 40 -c 14 \
+    -k regex:"elm_coded|estep_qF_coded|sweep_kernel|region_weights|code_plane|record_keys|record_weights|record_half" -s 42 -c 15 \
     -o gpurun_out/prof_$TAG -f $CMD > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log
