@@ -1167,16 +1167,23 @@ int fcd_estep_qR(const double* WT, int64_t C, int32_t N, int32_t U, int32_t u0, 
     else if (N <= 128) FCD_SWEEP(64, 2);
     else if (N <= 256) FCD_SWEEP(128, 2);
     else if (N <= 512) FCD_SWEEP(128, 4);
-    // larger atlases (few patients per GPU when sharded): more warps, fewer regions per thread -- the
-    // step's latency is what one warp has to issue, occupancy is not the limit
-    else if (N <= 640) FCD_SWEEP(320, 2);
-    else if (N <= 768) FCD_SWEEP(384, 2);
-    else if (N <= 896) FCD_SWEEP(448, 2);
-    else if (N <= 1024) FCD_SWEEP(512, 2);
-    else if (N <= 1280) FCD_SWEEP(640, 2);
-    else if (N <= 1536) FCD_SWEEP(512, 3);
-    else if (N <= 2048) FCD_SWEEP(512, 4);
-    else if (N <= 4096) FCD_SWEEP(1024, 4);
+    // larger atlases: with few patients on this GPU (sharded fits) the launch lasts N dependent steps
+    // and a step lasts what one warp has to issue -- more warps, fewer regions per thread; with many
+    // patients the SMs are full and total instructions count -- the compact shapes
+    else if (Ul < 2 * sm_count()) {
+        if (N <= 640) FCD_SWEEP(320, 2);
+        else if (N <= 768) FCD_SWEEP(384, 2);
+        else if (N <= 896) FCD_SWEEP(448, 2);
+        else if (N <= 1024) FCD_SWEEP(512, 2);
+        else if (N <= 1280) FCD_SWEEP(640, 2);
+        else if (N <= 1536) FCD_SWEEP(512, 3);
+        else if (N <= 2048) FCD_SWEEP(512, 4);
+        else if (N <= 4096) FCD_SWEEP(1024, 4);
+        else FCD_SWEEP(1024, 8);
+    }
+    else if (N <= 1024) FCD_SWEEP(256, 4);
+    else if (N <= 2048) FCD_SWEEP(256, 8);
+    else if (N <= 4096) FCD_SWEEP(512, 8);
     else FCD_SWEEP(1024, 8);
 #undef FCD_SWEEP
     return check_launch("fcd_estep_qR");

@@ -219,7 +219,8 @@ def test_patient_gather_staging_roundtrip(N, U, world):
     nptest.assert_array_equal(ob.cpu().numpy().reshape(N, U, 2), b)
 
 
-@pytest.mark.parametrize("N,U,lookup", [(37, 5, 0), (600, 3, 0), (600, 2, 1), (1100, 2, 0), (1400, 2, 1), (2100, 1, 0)])
+@pytest.mark.parametrize("N,U,lookup", [(37, 5, 0), (600, 3, 0), (600, 2, 1), (1100, 2, 0), (1400, 2, 1), (2100, 1, 0),
+                                        (530, 300, 0)])             # U >= 2 x SMs: the compact launch shapes
 def test_sweep_launch_shapes_match_numpy(N, U, lookup):
     """Gauss-Seidel sweep of fit.py:184-197 over the two weight differences, for every launch shape of
     fcd_estep_qR (regions per thread / warps per patient depend on N), both edge lookups."""
