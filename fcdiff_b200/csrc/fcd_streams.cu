@@ -186,7 +186,6 @@ record_keys_kernel(const uint8_t* __restrict__ code, const uint8_t* __restrict__
                    unsigned long long* __restrict__ keysH, longlong2* __restrict__ rowoff) {
     __shared__ longlong2 s_off[kRowBlock];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned lt = (1u << lane) - 1u;
     for (int64_t blk = blockIdx.x; blk * kRowBlock < C; blk += gridDim.x) {
         const int64_t cb = blk * kRowBlock;
         __syncthreads();
@@ -226,31 +225,44 @@ record_keys_kernel(const uint8_t* __restrict__ code, const uint8_t* __restrict__
                 }
                 continue;
             }
-            const unsigned short* crow = reinterpret_cast<const unsigned short*>(code + c * pitchQ);
+            // a lane owns 16 consecutive patients per pass (one 128-bit load of their codes): it counts
+            // its keys, one warp scan of the packed counts gives its offsets, then it stores its keys in
+            // order -- no vote per element
+            const uint8_t* crow = code + c * pitchQ;
             uint32_t offF = 0, offH = 0;
-            // batches of 8 x 64 patients: all code loads first, then positions (ballots) and stores
             for (int ub = 0; ub < U; ub += 512) {
-                uint32_t c2[8];
+                const int u0 = ub + 16 * lane;
+                uint4 cw = make_uint4(0, 0, 0, 0);
+                if (u0 < U) cw = __ldg(reinterpret_cast<const uint4*>(crow + u0));           // pitchQ % 16 == 0
+                const uint32_t w4[4] = {cw.x, cw.y, cw.z, cw.w};
+                uint32_t nF = 0, nH = 0;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int u = ub + 64 * i + 2 * lane;
-                    c2[i] = u < U ? (uint32_t)__ldg(crow + (u >> 1)) : 0u;
+                for (int i = 0; i < 16; ++i) {
+                    const uint32_t cd = (w4[i >> 2] >> (8 * (i & 3))) & 0xff;
+                    const bool in = u0 + i < U;
+                    nF += in && cd == 3;
+                    nH += in && cd >= 4;
                 }
+                uint32_t pk = nF | (nH << 16), incl = pk;                                    // both < 2^16
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int u = ub + 64 * i + 2 * lane;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+                uint32_t pF = offF + ((incl - pk) & 0xffff), pH = offH + ((incl - pk) >> 16);
+                if (nF | nH) {
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int cd = u + e < U ? (int)((c2[i] >> (8 * e)) & 0xff) : 0;
-                        const unsigned balF = __ballot_sync(0xffffffffu, cd == 3);
-                        const unsigned balH = __ballot_sync(0xffffffffu, cd >= 4);
-                        if (cd == 3) dF[offF + __popc(balF & lt)] = ckey | (unsigned long long)(u + e);
-                        if (cd >= 4)
-                            dH[offH + __popc(balH & lt)] = ((unsigned long long)(cd - 4) << 48) | ckey | (unsigned long long)(u + e);
-                        offF += __popc(balF);
-                        offH += __popc(balH);
+                    for (int i = 0; i < 16; ++i) {
+                        const uint32_t cd = (w4[i >> 2] >> (8 * (i & 3))) & 0xff;
+                        if (u0 + i < U) {
+                            if (cd == 3) dF[pF++] = ckey | (unsigned long long)(u0 + i);
+                            else if (cd >= 4) dH[pH++] = ((unsigned long long)(cd - 4) << 48) | ckey | (unsigned long long)(u0 + i);
+                        }
                     }
                 }
+                offF += tot & 0xffff;
+                offH += tot >> 16;
             }
         }
     }

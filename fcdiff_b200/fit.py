@@ -372,6 +372,7 @@ class UnsharedRegionFit(object):
                                           _dev.stream()), "fcd_resp_cache")
         inp['Lsum'] = None                          # total of the L plane, formed on first use (code pass)
         inp['PsE'] = None                           # dominant-state plane of the code pass: rebuilt with the planes
+        inp['code_verR'] = None
         inp['cache_key'] = ckey
         inp['PT'] = None
         self._evals = []
