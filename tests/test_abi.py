@@ -56,3 +56,21 @@ def test_header_cites_reference_lines():
 
 def test_theta_struct_layout(lib):
     assert ctypes.sizeof(lib.FcdTheta) == 12 * 8
+
+
+def _prototypes():
+    """name -> parameter count of every FCD_API prototype in the header."""
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    out = {}
+    for m in re.finditer(r"FCD_API\s+[\w\s\*]+?\b(fcd_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+    return out
+
+
+def test_ctypes_argument_counts_match_the_prototypes(lib):
+    protos = _prototypes()
+    assert sorted(protos) == declared_symbols()
+    for (name, (_, argtypes)) in lib.SIGNATURES.items():
+        assert len(argtypes) == protos[name], "%s: ctypes table has %d arguments, the header %d" % (
+            name, len(argtypes), protos[name])
