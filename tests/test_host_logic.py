@@ -227,3 +227,38 @@ def test_time_series_file_loaders(tmp_path):
     np.save(tmp_path / "bad.npy", a[:, :7])
     with pytest.raises(ValueError):
         ns["load_timeseries"]([str(tmp_path / "s0.npy"), str(tmp_path / "bad.npy")])
+
+
+def test_uniform_start_is_lazy_on_the_host():
+    """_init_lps (fit.py:84-102) records a fill; the host array appears only when somebody reads it,
+    the values are the reference's, assignments replace it and bump the version."""
+    fit = fcdiff.fit.UnsharedRegionFit()
+    fit._init_lps(5, 3, 4)
+    (mR, mF) = (fit._mR, fit._mF)
+    assert mR.host is None and mR.fill == ((5, 4, 2), -np.log(2)) and mF.fill == ((10, 1, 3), -np.log(3))
+    v = mR.version
+    nptest.assert_array_equal(fit._lq_R, np.full((5, 4, 2), -np.log(2)))
+    nptest.assert_array_equal(fit._lq_F, np.full((10, 1, 3), -np.log(3)))
+    fit._lq_R = np.zeros((5, 4, 2))
+    assert mR.fill is None and mR.version == v + 1 and not fit._lq_R.any()
+
+
+def test_padded_edge_chunks_for_the_in_place_gather():
+    for (C, world) in [(45, 2), (79800, 8), (7, 3), (10, 1)]:
+        sh = EdgeShards(rank=0, world=world)
+        n = sh.edge_buffer_len(C)
+        ch = sh.chunk(C, world)
+        assert n == world * ch * 3 and n >= 3 * C
+        for r in range(world):
+            (start, length) = EdgeShards(rank=r, world=world).span(C)
+            assert start == min(r * ch, C) and 0 <= length <= ch and (start + length) * 3 <= n
+
+
+def test_small_vector_exchange_abi_limits():
+    """The exchange window covers 16 ranks x 8 doubles (include/fcdiff_b200.h 'small exchanges')."""
+    from fcdiff_b200 import _lib
+    lib = _lib.load()
+    assert lib.fcd_comm_max_world() >= 8 and lib.fcd_comm_max_vals() >= 6
+    assert lib.fcd_comm_window_bytes() >= 2 * lib.fcd_comm_max_world() * (lib.fcd_comm_max_vals() + 1) * 8
+    assert lib.fcd_comm_handle_bytes() == 64
+    assert lib.fcd_code_pitch(500) == 512 and lib.fcd_code_pitch(16) == 16 and lib.fcd_code_pitch(17) == 32
