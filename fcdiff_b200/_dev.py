@@ -4,6 +4,7 @@ Every arithmetic kernel of the hot path lives in ``libfcdiff_b200.so``.
 """
 import contextlib
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -114,6 +115,40 @@ def publisher():
     return _publisher[key]
 
 
+class SolverBlock(object):
+    """Device state + mapped host publication block of the device-resident (eta, epsilon)
+    solver (``fcd_solver_*``, csrc/fcd_solver.cuh), one per device."""
+
+    TIMEOUT_MS = 30000
+
+    def __init__(self):
+        lib = _lib.load()
+        self.lib = lib
+        self.state = torch.zeros(int(lib.fcd_solver_state_bytes()) // 8, dtype=torch.float64, device=device())
+        self.pub = ctypes.c_void_p(0)
+        _lib.check(lib.fcd_host_mapped_alloc(int(lib.fcd_solver_published_bytes()), ctypes.byref(self.pub)),
+                   "fcd_host_mapped_alloc")
+        self.seq = 0
+        self.host = _lib.SolverState()
+
+    def wait(self):
+        """Blocks until the last launched evaluation has published; returns the state."""
+        rc = self.lib.fcd_solver_wait(self.pub, self.seq, ctypes.byref(self.host), self.TIMEOUT_MS)
+        if rc != 0:
+            _lib.check(rc, "fcd_solver_wait")
+        return self.host
+
+
+_solver = {}
+
+
+def solver_block():
+    key = device().index
+    if key not in _solver:
+        _solver[key] = SolverBlock()
+    return _solver[key]
+
+
 class SmallResult(object):
     """A few doubles produced by a reduction kernel: one device vector reused for
     every call; reading it costs one publication kernel and a spin on mapped
@@ -153,14 +188,17 @@ class KernelTimers(object):
 
     @contextlib.contextmanager
     def __call__(self, name):
+        """Yields a one-element list: the number of kernel executions the bracket covers (default 1;
+        a batch of solver evaluations sets it once it knows how many of its launches did work)."""
         s = torch.cuda.Event(enable_timing=True)
         e = torch.cuda.Event(enable_timing=True)
+        count = [1]
         s.record()
         try:
-            yield
+            yield count
         finally:
             e.record()
-            self.events.setdefault(name, []).append((s, e))
+            self.events.setdefault(name, []).append((s, e, count))
 
     def reset(self):
         self.events = {}
@@ -170,13 +208,28 @@ class KernelTimers(object):
         torch.cuda.synchronize()
         out = {}
         for name, evs in self.events.items():
-            ms = [s.elapsed_time(e) for (s, e) in evs]
-            out[name] = (len(ms), float(sum(ms)), float(sum(ms) / max(len(ms), 1)))
+            ms = [s.elapsed_time(e) for (s, e, _) in evs]
+            n = sum(int(c[0]) for (_, _, c) in evs)
+            out[name] = (n, float(sum(ms)), float(sum(ms) / max(n, 1)))
         return out
 
 
 _NULL = contextlib.nullcontext()
+_NVTX = bool(os.environ.get("FCD_NVTX"))      # FCD_NVTX=1: an NVTX range per kernel family (ncu --nvtx, nsys)
+
+
+@contextlib.contextmanager
+def _nvtx_range(profile, name):
+    lib = _lib.load()
+    lib.fcd_nvtx_push(name.encode())
+    try:
+        with (_NULL if profile is None else profile(name)) as count:
+            yield count
+    finally:
+        lib.fcd_nvtx_pop()
 
 
 def timed(profile, name):
+    if _NVTX:
+        return _nvtx_range(profile, name)
     return _NULL if profile is None else profile(name)

@@ -31,6 +31,8 @@ SIGNATURES = {
     "fcd_download": (c_int, [_P, _P, c_int64, _P]),
     "fcd_launch_count": (c_int64, []),
     "fcd_launch_count_reset": (None, []),
+    "fcd_nvtx_push": (None, [c_char_p]),
+    "fcd_nvtx_pop": (None, []),
     "fcd_comm_window_bytes": (c_int64, []),
     "fcd_comm_handle_bytes": (c_int32, []),
     "fcd_comm_max_world": (c_int32, []),
@@ -75,6 +77,19 @@ SIGNATURES = {
     "fcd_estep_qF_coded": (c_int, [_P, _P, c_int32, _P, c_int64, c_int64, c_int32, c_int64, _P, c_int32, _P,
                                    _P, c_int64, _P, _P, _P, _P, _P, POINTER(FcdTheta), _P, _P, _P]),
     "fcd_elm_coded": (c_int, [_P, _P, c_int64, _P, c_int64, _P, c_int64, POINTER(FcdTheta), c_int32, _P, _P, _P]),
+    "fcd_solver_state_bytes": (c_int64, []),
+    "fcd_solver_published_bytes": (c_int64, []),
+    "fcd_host_mapped_alloc": (c_int, [c_int64, POINTER(c_void_p)]),
+    "fcd_host_mapped_free": (c_int, [_P]),
+    "fcd_solver_init": (c_int, [_P, c_double, c_double, _D3, _D3, c_double, c_int32, _P]),
+    "fcd_elm_coded_solve": (c_int, [_P, _P, c_int64, _P, c_int64, _P, c_int64, c_double, c_double, _P, _P,
+                                    POINTER(c_void_p), c_int32, c_int32, _P, c_uint64, c_int32, _P, _P]),
+    "fcd_elm_tiered_solve": (c_int, [_P, c_int64, c_int64, c_int32, c_int64, _P, _P, _P, _P, c_int64, c_int32, _P,
+                                     c_double, c_double, _P, _P, POINTER(c_void_p), c_int32, c_int32, _P, c_uint64,
+                                     c_int32, _P, _P]),
+    "fcd_solver_init_host": (c_int, [_P, c_double, c_double, _D3, _D3, c_double, c_int32]),
+    "fcd_solver_step_host": (c_int, [_P, _D3]),
+    "fcd_solver_wait": (c_int, [_P, c_uint64, _P, c_int32]),
     "fcd_energy_terms": (c_int, [_P, _P, c_int32, _P, _P, c_int64, _P, _P, c_int32, c_int32,
                                  POINTER(FcdTheta), c_double, _P, _P, _P]),
     "fcd_state_moments": (c_int, [_P, _P, c_int32, _P, _P, c_int64, c_int64, c_int32, c_int64, _P, _P, c_int32, _P,
@@ -98,6 +113,14 @@ SIGNATURES = {
     "fcd_corr_fisherz": (c_int, [_P, c_int32, c_int32, c_int32, _P, c_int64, c_int32, c_int32, _P, _P]),
 }
 
+class SolverState(ctypes.Structure):
+    """``fcd_solver_state`` (include/fcdiff_b200.h)."""
+    _fields_ = [("x", c_double * 2), ("xprev", c_double * 2), ("fprev", c_double), ("f", c_double),
+                ("g", c_double * 2), ("lo", c_double * 2), ("hi", c_double * 2), ("tol", c_double),
+                ("step", c_double), ("have_prev", c_int32), ("nfev", c_int32), ("nback", c_int32),
+                ("done", c_int32), ("max_evals", c_int32), ("pad_", c_int32)]
+
+
 _lib = None
 
 
@@ -119,7 +142,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the symbol is missing
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.fcd_version() < 110:
+    if lib.fcd_version() < 120:
         raise FcdError("fcdiff_b200: stale libfcdiff_b200.so (version %d)" % lib.fcd_version())
     _lib = lib
     return lib

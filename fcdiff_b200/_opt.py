@@ -73,14 +73,35 @@ def _minimize_direct(fun, x0, lower, upper, m=10, ftol=2.2204460492503131e-09, g
     return Result(x, float(f), nfev, nit)
 
 
+def _probe_direct():
+    """One solve of a tiny bounded quadratic through the private interface, compared with the public
+    ``scipy.optimize.minimize``: any exception (another ``setulb`` signature, dtype or shape checks of
+    another SciPy generation) or a different minimiser selects the public path for the whole process.
+    Developed against SciPy 1.15-1.18 (``setulb(m, x, l, u, nbd, f, g, factr, pgtol, wa, iwa, task,
+    lsave, isave, dsave, maxls, ln_task)``)."""
+    if not _direct_ok:
+        return False
+
+    def quad(x):
+        d = np.asarray(x) - np.array([0.3, 2.0])
+        return float(d @ d), 2.0 * d
+
+    try:
+        r = _minimize_direct(quad, [0.9, 0.1], [0.0, 0.0], [1.0, 1.0])
+        ref = scipy.optimize.minimize(quad, np.array([0.9, 0.1]), jac=True, method="L-BFGS-B",
+                                      bounds=[(0.0, 1.0), (0.0, 1.0)])
+        return bool(np.array_equal(r.x, ref.x) and r.nfev == ref.nfev)
+    except Exception:
+        return False
+
+
+_direct_ok = _probe_direct()
+
+
 def minimize_lbfgsb(fun, x0, lower, upper):
     """Minimises ``fun(x) -> (f, grad)`` on the box [lower, upper]."""
-    global _direct_ok
     if _direct_ok:
-        try:
-            return _minimize_direct(fun, x0, lower, upper)
-        except TypeError:               # a SciPy with another setulb signature
-            _direct_ok = False
+        return _minimize_direct(fun, x0, lower, upper)
     nfev = [0]
 
     def wrapped(x):

@@ -20,85 +20,30 @@
 #include <chrono>
 #include <cstring>
 
-#include "fcd_common.cuh"
+#include "fcd_comm.cuh"
 
 namespace fcd {
 
-constexpr int kCommMaxWorld = 16;
-constexpr int kCommMaxVals = 8;
-
-struct CommWindow {
-    double slot[2][kCommMaxWorld][kCommMaxVals];
-    unsigned long long flag[2][kCommMaxWorld];
-};
-
-struct CommPeers {
-    CommWindow* w[kCommMaxWorld];
-};
-
-constexpr unsigned long long kCommTimeoutBit = 1ull << 63;
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed_sys(double* p, double v) {
-    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-}
-__device__ __forceinline__ double ld_relaxed_sys(const double* p) {
-    double v;
-    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// result_host: [kCommMaxVals] doubles followed by one 64-bit flag (= seq, or seq | timeout bit)
+// result_host: [kCommMaxVals] doubles followed by one 64-bit flag (= seq, or seq | timeout bit).
+// `seq` names the PUBLICATION (what the host waits for); the slot sets of the windows follow the
+// rank's own exchange counter (fcd_comm.cuh).
 __global__ void __launch_bounds__(kCommMaxWorld* kCommMaxVals)
 allreduce_small_kernel(double* __restrict__ vec, int n, const __grid_constant__ CommPeers peers, int rank, int world,
                        unsigned long long seq, double* __restrict__ result_host, long long spin_cycles) {
-    __shared__ int s_timeout;
+    __shared__ double s_vals[kCommMaxVals];
     const int t = threadIdx.x;
-    const int par = (int)(seq & 1ull);
-    if (t == 0) s_timeout = 0;
+    if (t < n) s_vals[t] = vec[t];
     __syncthreads();
-    if (world > 1) {
-        if (t < world * n) {                                  // 1. my partial sums into every rank's window
-            const int p = t / n, i = t - p * n;
-            st_relaxed_sys(&peers.w[p]->slot[par][rank][i], vec[i]);
-            __threadfence_system();
-        }
-        __syncthreads();
-        if (t < world) {
-            st_release_sys(&peers.w[t]->flag[par][rank], seq);
-            const unsigned long long* f = &peers.w[rank]->flag[par][t];       // 2. everybody's flag in my window
-            const long long t0 = clock64();
-            while (ld_acquire_sys(f) != seq) {
-                if (clock64() - t0 > spin_cycles) {
-                    s_timeout = 1;
-                    break;
-                }
-            }
-        }
-        __syncthreads();
-    }
-    if (t < n) {                                              // 3. sum in rank order, publish
-        double s = 0.0;
-        if (world > 1) {
-            for (int r = 0; r < world; ++r) s += ld_relaxed_sys(&peers.w[rank]->slot[par][r][t]);
-            vec[t] = s;
-        } else {
-            s = vec[t];
-        }
-        st_relaxed_sys(result_host + t, s);
+    const bool ok = comm_exchange_cta(s_vals, n, peers, rank, world, spin_cycles);
+    if (t < n) {                                              // publish (a timed-out exchange leaves vec as it was)
+        if (ok && world > 1) vec[t] = s_vals[t];
+        st_relaxed_sys(result_host + t, s_vals[t]);
         __threadfence_system();
     }
     __syncthreads();
     if (t == 0)
         st_release_sys(reinterpret_cast<unsigned long long*>(result_host + kCommMaxVals),
-                       s_timeout ? (seq | kCommTimeoutBit) : seq);
+                       ok ? seq : (seq | kCommTimeoutBit));
 }
 
 // Staging of the patient all-gather: the region posteriors are (N, U, 2) arrays and a
@@ -213,17 +158,10 @@ int fcd_allreduce_small(double* vec, int32_t n, void* const* windows_host, int32
     FCD_REQUIRE(n >= 1 && n <= kCommMaxVals && world >= 1 && world <= kCommMaxWorld && rank >= 0 && rank < world &&
                 seq >= 1 && (seq & kCommTimeoutBit) == 0, "fcd_allreduce_small: bad shape");
     CommPeers peers;
-    memset(&peers, 0, sizeof(peers));
-    if (world > 1) {
-        FCD_REQUIRE(windows_host != nullptr, "fcd_allreduce_small: NULL windows");
-        for (int r = 0; r < world; ++r) {
-            FCD_REQUIRE(windows_host[r] != nullptr, "fcd_allreduce_small: NULL window");
-            peers.w[r] = static_cast<CommWindow*>(windows_host[r]);
-        }
-    }
+    FCD_REQUIRE(comm_peers_from_host(windows_host, world, peers), "fcd_allreduce_small: NULL window");
     double* result_dev = nullptr;
     FCD_CUDA(cudaHostGetDevicePointer((void**)&result_dev, result_host, 0), "fcd_allreduce_small(cudaHostGetDevicePointer)");
-    const long long spin_cycles = 20000000000ll;              // ~10 s at 2 GHz: a lost peer must not hang the GPU
+    const long long spin_cycles = kCommSpinCycles;
     allreduce_small_kernel<<<1, kCommMaxWorld * kCommMaxVals, 0, (cudaStream_t)stream>>>(
         vec, n, peers, rank, world, (unsigned long long)seq, result_dev, spin_cycles);
     return check_launch("fcd_allreduce_small");

@@ -25,6 +25,19 @@ int  sm_count();
         }                                                                        \
     } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: the opt-in is made
+// once per (call site, device), so a process that drives several GPUs gets it on each of them.
+#define FCD_ALLOW_BIG_SMEM(...)                                                                          \
+    do {                                                                                                 \
+        static bool done_[64] = {false};                                                                 \
+        int dev_ = -1;                                                                                   \
+        if (cudaGetDevice(&dev_) != cudaSuccess || dev_ < 0 || dev_ >= 64 || !done_[dev_]) {             \
+            cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize,               \
+                                 (int)::fcd::kSmemBudget);                                               \
+            if (dev_ >= 0 && dev_ < 64) done_[dev_] = true;                                              \
+        }                                                                                                \
+    } while (0)
+
 constexpr double kHalfLog2Pi = 0.91893853320467274178032973640562;   // log(sqrt(2 pi))
 
 // Workspace layout (doubles): [0, kWsPartials) per-CTA partial sums,
@@ -470,6 +483,65 @@ __device__ __forceinline__ void grid_reduce_store(double (&v)[NV], double* ws, d
         }
         if (lane == 0) *ticket = 0ull;
     }
+}
+
+// Same reduction, but the sums stay in the CTA that arrived last: returns true there (for all of
+// its threads, with s_out[0..NV) valid in shared memory after the internal barrier) and false in
+// every other CTA.  For kernels whose last CTA continues with an epilogue (fcd_solver.cuh).
+template <int NV, int THREADS>
+__device__ __forceinline__ bool grid_reduce_last(double (&v)[NV], double* ws, double* s_out) {
+    static_assert(NV <= kMaxReduceVals, "too many values");
+    __shared__ double s_part[NV][THREADS / 32];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double x = warp_sum(v[i]);
+        if (lane == 0) s_part[i][warp] = x;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double x = (lane < THREADS / 32) ? s_part[i][lane] : 0.0;
+            x = warp_sum(x);
+            if (lane == 0) ws[(int64_t)blockIdx.x * NV + i] = x;
+        }
+    }
+    unsigned long long* ticket = reinterpret_cast<unsigned long long*>(ws + kWsPartials);
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned long long t = atomicAdd(ticket, 1ull);
+        s_last = (t == (unsigned long long)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return false;
+    __threadfence();
+    double acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += THREADS) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) acc[i] += __ldcg(ws + (int64_t)b * NV + i);
+    }
+    __syncthreads();      // s_part reuse
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double x = warp_sum(acc[i]);
+        if (lane == 0) s_part[i][warp] = x;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double x = (lane < THREADS / 32) ? s_part[i][lane] : 0.0;
+            x = warp_sum(x);
+            if (lane == 0) s_out[i] = x;
+        }
+        if (lane == 0) *ticket = 0ull;
+    }
+    __syncthreads();
+    return true;
 }
 
 #endif  // __CUDACC__

@@ -1064,12 +1064,7 @@ int fcd_estep_qF_coded(const double* S1, const double* S2, int32_t H,
     if (grid > sm_count()) grid = sm_count();                       // one persistent CTA per SM
 #define FCD_K2C(F)                                                                                    \
     do {                                                                                              \
-        static bool attr_set = false;                                                                 \
-        if (!attr_set) {                                                                              \
-            cudaFuncSetAttribute(estep_qF_coded_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                 (int)kSmemBudget);                                                   \
-            attr_set = true;                                                                          \
-        }                                                                                             \
+        FCD_ALLOW_BIG_SMEM(estep_qF_coded_kernel<F>);                                                 \
         estep_qF_coded_kernel<F><<<(unsigned)grid, kStreamThreads, smem, st>>>(                       \
             S1, S2, P, planeStride, C, U, pitchU, qR, nm, code, pitchQ, reinterpret_cast<const int2*>(counts), \
             reinterpret_cast<const unsigned long long*>(keysF), reinterpret_cast<const unsigned long long*>(keysH), \

@@ -2,7 +2,10 @@
 // analytic gradient of the (eta, epsilon) sub-problem), K4 (energy terms).
 // All reductions accumulate in fp64: warp shuffle -> block -> deterministic
 // last-CTA grid reduction.
+#include <cstring>
+
 #include "fcd_common.cuh"
+#include "fcd_solver.cuh"
 
 namespace fcd {
 
@@ -39,30 +42,54 @@ mstep_stats_kernel(const double* __restrict__ lqF, int64_t C,
 // with num_k = (3 p_k - 1)/2.  Tiers T1 / T2 / T3 as described in fcd_common.cuh.
 struct ElmAcc {
     double obj, ge, gh;       // objective, sum s_l w_l d_l, sum w_2 d_2
+    double qa, qb;            // SOLVE: sum_{l < 2} w_l g_l^2, sum w_2 g_2^2 (fcd_solver.cuh)
 };
 
 constexpr int kElmSeg = 256;
 
-template <bool GRAD, bool FAST>
+// SOLVE: evaluation point from the solver state, Hessian sums, optimiser step in the last CTA
+// (see elm_coded_kernel, fcd_streams.cu).
+template <bool GRAD, bool FAST, bool SOLVE>
 __global__ void __launch_bounds__(kStreamThreads, 1)
 elm_kernel(const double* __restrict__ P, int64_t planeStride, int64_t C, int U, int64_t pitchU,
            const double* __restrict__ qF, const uint8_t* __restrict__ fstate,
            const double* __restrict__ qR, const uint8_t* __restrict__ rstate, int64_t pitchS,
            const int32_t* __restrict__ nm, const __grid_constant__ ThetaDev th,
            const __grid_constant__ LogTabWindow tab, int depth,
-           double* __restrict__ out, double* __restrict__ ws) {
+           double* __restrict__ out, double* __restrict__ ws,
+           SolverState* __restrict__ state, const double* __restrict__ konst_dev,
+           const __grid_constant__ CommPeers peers, int rank, int world, SolverPublished* pub,
+           unsigned long long seq) {
+    static_assert(!SOLVE || GRAD, "the solver needs the gradient sums");
     extern __shared__ __align__(128) double s_dyn[];
+    __shared__ double s_sums[kSolverVals];
+    if (SOLVE && solver_finished(state, pub, seq)) return;
+    SubTheta T;
+    if (SOLVE) {
+        T = sub_theta(state->x[0], state->x[1]);
+    } else {
+        T.eta = th.eta;
+        T.epsilon = th.epsilon;
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            T.al[l] = th.al[l];
+            T.bl[l] = th.bl[l];
+        }
+    }
     const double* s_tab = load_log_table<FAST>(tab, s_dyn);
     unsigned char* s_stream = reinterpret_cast<unsigned char*>(s_dyn + (FAST ? ((tab.n + 1) & ~1) : 0));
-    const double sl[3] = {-1.0, 1.0, 2.0 * th.eta - 1.0};
+    const double al[3] = {T.al[0], T.al[1], T.al[2]}, bl[3] = {T.bl[0], T.bl[1], T.bl[2]};
+    const double sl[3] = {-1.0, 1.0, 2.0 * T.eta - 1.0};
     const double2* qR2 = reinterpret_cast<const double2*>(qR);
-    ElmAcc acc = {0.0, 0.0, 0.0}, acc1 = {0.0, 0.0, 0.0};
-    // per-l constants of the T1 body {a_l, b_l, s_l, [l == 2]}; row 3 is the neutral
-    // element for deferred / padding slots: log(1 + 0 p) = 0 exactly, zero gradient weight
+    ElmAcc acc = {0.0, 0.0, 0.0, 0.0, 0.0}, acc1 = {0.0, 0.0, 0.0, 0.0, 0.0};
+    // per-l constants of the T1 body {a_l, b_l, s_l, [l == 2]} (+ [l < 2] for the Hessian sums); row 3 is
+    // the neutral element for deferred / padding slots: log(1 + 0 p) = 0 exactly, zero gradient weight
     __shared__ double4 s_lc[4];
+    __shared__ double s_lq[4];
     if (threadIdx.x < 4) {
         const int l = threadIdx.x;
-        s_lc[l] = l < 3 ? make_double4(th.al[l], th.bl[l], sl[l], l == 2 ? 1.0 : 0.0) : make_double4(1.0, 0.0, 0.0, 0.0);
+        s_lc[l] = l < 3 ? make_double4(sel3(l, al), sel3(l, bl), sel3(l, sl), l == 2 ? 1.0 : 0.0) : make_double4(1.0, 0.0, 0.0, 0.0);
+        s_lq[l] = l < 2 ? 1.0 : 0.0;
     }
     __syncthreads();
 
@@ -92,6 +119,11 @@ elm_kernel(const double* __restrict__ P, int64_t planeStride, int64_t C, int U, 
             const double d = mix_num(pv[0]) * rcp;
             a.ge = fma(k.z, d, a.ge);
             a.gh = fma(k.w, d, a.gh);
+            if (SOLVE) {
+                const double dd = d * d;
+                a.qa = fma(s_lq[lp], dd, a.qa);
+                a.qb = fma(k.w, dd, a.qb);
+            }
         }
         if (e == 1 && ++nf == kProdMax) flush();              // warp-uniform
     };
@@ -110,23 +142,32 @@ elm_kernel(const double* __restrict__ P, int64_t planeStride, int64_t C, int U, 
         }
         return o;
     };
+    // one element with the weights qw[l]: three logs, gradient and (SOLVE) Hessian sums
+    auto weighted3 = [&](double p, const double (&qw)[3]) {
+        const double num = mix_num(p);
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            const double M = fma(bl[l], p, al[l]);
+            if (GRAD) {
+                double rcp;
+                acc.obj = fma(qw[l], fast_log_rcp<FAST>(M, s_tab, rcp), acc.obj);
+                const double g = num * rcp;
+                const double d = qw[l] * g;
+                acc.ge = fma(sl[l], d, acc.ge);
+                if (l == 2) acc.gh += d;
+                if (SOLVE) {
+                    if (l == 2) acc.qb = fma(d, g, acc.qb);
+                    else acc.qa = fma(d, g, acc.qa);
+                }
+            } else {
+                acc.obj = fma(qw[l], fast_log<FAST>(M, s_tab), acc.obj);
+            }
+        }
+    };
     auto dcompute = [&](const Ops& o) {
         double w[3];
         pair_weights(o.qn, o.qm, w);
-        const double num = mix_num(o.p);
-#pragma unroll
-        for (int l = 0; l < 3; ++l) {
-            const double M = mix_rel(th, l, o.p);
-            if (GRAD) {
-                double rcp;
-                acc.obj = fma(w[l], fast_log_rcp<FAST>(M, s_tab, rcp), acc.obj);
-                const double d = w[l] * (num * rcp);
-                acc.ge = fma(sl[l], d, acc.ge);
-                if (l == 2) acc.gh += d;
-            } else {
-                acc.obj = fma(w[l], fast_log<FAST>(M, s_tab), acc.obj);
-            }
-        }
+        weighted3(o.p, w);
     };
     auto full = [&](int64_t c, int n, int m, int u0, int u1) {
         const double qf[3] = {__ldg(qF + c * 3), __ldg(qF + c * 3 + 1), __ldg(qF + c * 3 + 2)};
@@ -136,21 +177,8 @@ elm_kernel(const double* __restrict__ P, int64_t planeStride, int64_t C, int U, 
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 const double p = ldg_stream1(P + k * planeStride + c * pitchU + u);
-                const double num = mix_num(p);
-#pragma unroll
-                for (int l = 0; l < 3; ++l) {
-                    const double M = mix_rel(th, l, p);
-                    const double qw = qf[k] * w[l];
-                    if (GRAD) {
-                        double rcp;
-                        acc.obj = fma(qw, fast_log_rcp<FAST>(M, s_tab, rcp), acc.obj);
-                        const double d = qw * (num * rcp);
-                        acc.ge = fma(sl[l], d, acc.ge);
-                        if (l == 2) acc.gh += d;
-                    } else {
-                        acc.obj = fma(qw, fast_log<FAST>(M, s_tab), acc.obj);
-                    }
-                }
+                const double qw[3] = {qf[k] * w[0], qf[k] * w[1], qf[k] * w[2]};
+                weighted3(p, qw);
             }
         }
     };
@@ -158,8 +186,14 @@ elm_kernel(const double* __restrict__ P, int64_t planeStride, int64_t C, int U, 
                                                          s_stream, depth, live, dload, dcompute, full,
                                                          [](int64_t) {});
     flush();
-    double v[3] = {acc.obj + acc1.obj, -(2.0 * th.epsilon - 1.0) * (acc.gh + acc1.gh), -(acc.ge + acc1.ge)};
-    grid_reduce_store<3, kStreamThreads>(v, ws, out);
+    if (SOLVE) {
+        double v[5] = {acc.obj + acc1.obj, acc.ge + acc1.ge, acc.gh + acc1.gh, acc.qa + acc1.qa, acc.qb + acc1.qb};
+        if (grid_reduce_last<5, kStreamThreads>(v, ws, s_sums))
+            solver_epilogue(s_sums, state, konst_dev, peers, rank, world, pub, seq);
+    } else {
+        double v[3] = {acc.obj + acc1.obj, -(2.0 * T.epsilon - 1.0) * (acc.gh + acc1.gh), -(acc.ge + acc1.ge)};
+        grid_reduce_store<3, kStreamThreads>(v, ws, out);
+    }
 }
 
 // Theta-free part of E_lM: out[0] = sum_c (sum_k qF_k) sum_u (sum_l w_l) L[c,u]
@@ -375,17 +409,70 @@ int fcd_elm_obj_grad(const double* P, int64_t planeStride, int64_t C, int32_t U,
     FCD_REQUIRE(depth >= 2, "fcd_elm_obj_grad: shared memory budget exceeded");
     const size_t smem = tbytes + StreamGeom<1, kElmSeg>::bytes(kStreamWarps, depth);
     const int grid = stream_grid(C);
+    CommPeers nopeers;
+    comm_peers_from_host(nullptr, 1, nopeers);
 #define FCD_ELM(G, F)                                                                                  \
     do {                                                                                               \
-        cudaFuncSetAttribute(elm_kernel<G, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
-                             (int)kSmemBudget);                                                        \
-        elm_kernel<G, F><<<grid, kStreamThreads, smem, st>>>(P, planeStride, C, U, pitchU, qF, fstate, qR, \
-                                                             rstate, pitchS, nm, th, tab, depth, out3, ws); \
+        FCD_ALLOW_BIG_SMEM(elm_kernel<G, F, false>);                                                   \
+        elm_kernel<G, F, false><<<grid, kStreamThreads, smem, st>>>(P, planeStride, C, U, pitchU, qF, fstate, qR, \
+                                                                    rstate, pitchS, nm, th, tab, depth, out3, ws, \
+                                                                    nullptr, nullptr, nopeers, 0, 1, nullptr, 0ull); \
     } while (0)
     if (want_grad) { if (fast) FCD_ELM(true, true); else FCD_ELM(true, false); }
     else           { if (fast) FCD_ELM(false, true); else FCD_ELM(false, false); }
 #undef FCD_ELM
     return check_launch("fcd_elm_obj_grad");
+}
+
+int fcd_elm_tiered_solve(const double* P, int64_t planeStride, int64_t C, int32_t U, int64_t pitchU,
+                         const double* qF, const uint8_t* fstate, const double* qR, const uint8_t* rstate,
+                         int64_t pitchS, int32_t N, const int32_t* nm, double eps_lo, double eps_hi, void* state,
+                         const double* konst, void* const* windows_host, int32_t rank, int32_t world,
+                         void* published_host, uint64_t seq0, int32_t n_launches, double* ws, void* stream) {
+    FCD_REQUIRE(state != nullptr && ws != nullptr && P != nullptr && qF != nullptr && fstate != nullptr &&
+                qR != nullptr && rstate != nullptr && nm != nullptr, "fcd_elm_tiered_solve: NULL argument");
+    FCD_REQUIRE(C >= 0 && U >= 1 && U < 65536 && pitchU >= U && pitchS >= U && N >= 2 && N < 65536,
+                "fcd_elm_tiered_solve: bad shape");
+    FCD_REQUIRE(planes_ok(P, nullptr, pitchU, planeStride, pitchS),
+                "fcd_elm_tiered_solve: planes must be 16-byte aligned with even pitches (pitchS % 256 == 0)");
+    FCD_REQUIRE(n_launches >= 1 && n_launches <= 64 && world >= 1 && world <= kCommMaxWorld && rank >= 0 && rank < world &&
+                eps_lo > 0.0 && eps_lo <= eps_hi && eps_hi < 1.0, "fcd_elm_tiered_solve: bad launch / box arguments");
+    CommPeers peers;
+    FCD_REQUIRE(comm_peers_from_host(windows_host, world, peers), "fcd_elm_tiered_solve: NULL window");
+    SolverPublished* pub = nullptr;
+    if (published_host != nullptr) {
+        cudaError_t e = cudaHostGetDevicePointer((void**)&pub, published_host, 0);
+        FCD_REQUIRE(e == cudaSuccess, "fcd_elm_tiered_solve: cudaHostGetDevicePointer: %s", cudaGetErrorString(e));
+    }
+    const double m = eps_lo < 1.0 - eps_hi ? eps_lo : 1.0 - eps_hi;
+    const double epsl[3] = {m, m, m}, al[3] = {0.5 * m, 0.5 * m, 0.5 * m};
+    ThetaDev th;
+    memset(&th, 0, sizeof(th));
+    cudaStream_t st = (cudaStream_t)stream;
+    LogTabWindow tab;
+    FCD_REQUIRE(log_table_window(epsl, al, st, tab, true), "fcd_elm_tiered_solve: log table initialisation failed");
+    const bool fast = log_table_covers(epsl, al);
+    const size_t tbytes = fast ? (size_t)((tab.n + 1) & ~1) * sizeof(double) : 0;
+    const int depth = stream_depth<1, kElmSeg>(tbytes);
+    FCD_REQUIRE(depth >= 2, "fcd_elm_tiered_solve: shared memory budget exceeded");
+    const size_t smem = tbytes + StreamGeom<1, kElmSeg>::bytes(kStreamWarps, depth);
+    const int grid = stream_grid(C);
+    if (fast) FCD_ALLOW_BIG_SMEM(elm_kernel<true, true, true>);
+    else FCD_ALLOW_BIG_SMEM(elm_kernel<true, false, true>);
+    for (int i = 0; i < n_launches; ++i) {
+        const unsigned long long seq = (unsigned long long)seq0 + (unsigned long long)i;
+        if (fast)
+            elm_kernel<true, true, true><<<grid, kStreamThreads, smem, st>>>(
+                P, planeStride, C, U, pitchU, qF, fstate, qR, rstate, pitchS, nm, th, tab, depth, nullptr, ws,
+                static_cast<SolverState*>(state), konst, peers, rank, world, pub, seq);
+        else
+            elm_kernel<true, false, true><<<grid, kStreamThreads, smem, st>>>(
+                P, planeStride, C, U, pitchU, qF, fstate, qR, rstate, pitchS, nm, th, tab, depth, nullptr, ws,
+                static_cast<SolverState*>(state), konst, peers, rank, world, pub, seq);
+        int rc = check_launch("fcd_elm_tiered_solve");
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 int fcd_elm_const(const double* L, int64_t C, int32_t U, int64_t pitchU,

@@ -5,6 +5,8 @@
 #include <cstdio>
 #include <cstring>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "fcd_common.cuh"
 #include "fcd_math.cuh"
 
@@ -170,6 +172,10 @@ int fcd_download(void* dst_host, const void* src, int64_t bytes, void* stream) {
     }
     return 0;
 }
+
+void fcd_nvtx_push(const char* name_host) { nvtxRangePushA(name_host ? name_host : "fcd"); }
+
+void fcd_nvtx_pop(void) { nvtxRangePop(); }
 
 int64_t fcd_launch_count(void) { return fcd::g_launches.load(); }
 

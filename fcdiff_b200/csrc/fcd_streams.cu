@@ -23,7 +23,10 @@
 // peak-state decoding, no partition of the elements (an earlier form sorted the p
 // into three streams by l*: the sort cost as much per iteration as four evaluations).
 // Record order is fixed by per-row counts and an exclusive scan: results are deterministic.
+#include <cstring>
+
 #include "fcd_common.cuh"
+#include "fcd_solver.cuh"
 
 namespace fcd {
 
@@ -353,11 +356,12 @@ constexpr int kEvStage = kEvChunk * 8 + kEvChunk;            // bytes: p, then c
 constexpr size_t ev_ring_bytes(int depth) { return (size_t)kEvWarps * depth * (kEvStage + 8); }
 
 struct CodedAcc {
-    double obj, ge, gh, prod;
+    double obj, ge, gh, prod, qa, qb;
 };
 
-template <bool GRAD, bool FAST>
-__device__ __forceinline__ void coded_elem(double p, int code, const double2* s_ab, const double2* s_sh,
+// HESS: also the two sums of squares the Newton step needs (fcd_solver.cuh): qa over l < 2, qb over l = 2
+template <bool GRAD, bool FAST, bool HESS>
+__device__ __forceinline__ void coded_elem(double p, int code, const double2* s_ab, const double4* s_sh,
                                            const double* s_tab, CodedAcc& acc) {
     const double2 ab = s_ab[code];
     const double M = fma(ab.y, p, ab.x);
@@ -371,21 +375,49 @@ __device__ __forceinline__ void coded_elem(double p, int code, const double2* s_
         acc.obj += fast_log<FAST>(M, s_tab);
     }
     if (GRAD) {
-        const double2 sh = s_sh[code];
+        const double4 sh = s_sh[code];
         const double d = mix_num(p) * rcp;
         acc.ge = fma(sh.x, d, acc.ge);
         acc.gh = fma(sh.y, d, acc.gh);
+        if (HESS) {
+            const double dd = d * d;
+            acc.qa = fma(sh.z, dd, acc.qa);
+            acc.qb = fma(sh.y, dd, acc.qb);
+        }
     }
 }
 
-template <bool GRAD, bool FAST>
+// SOLVE: the evaluation point (eta, epsilon) is read from the solver state in device memory, the
+// kernel also accumulates the Hessian sums, and the CTA that arrives last exchanges the sums with
+// the other edge shards, takes the optimiser's step and publishes the state (fcd_solver.cuh); a
+// launch that finds the solve finished exits at once.
+template <bool GRAD, bool FAST, bool SOLVE>
 __global__ void __launch_bounds__(kEvThreads, 1)
 elm_coded_kernel(const double* __restrict__ PsE, const uint8_t* __restrict__ code, long long nE,
                  const Record* __restrict__ D, long long nd, const double2* __restrict__ Hh, long long nh,
                  const __grid_constant__ ThetaDev th, const __grid_constant__ LogTabWindow tab, int depth,
-                 double* __restrict__ out, double* __restrict__ ws) {
+                 double* __restrict__ out, double* __restrict__ ws,
+                 SolverState* __restrict__ state, const double* __restrict__ konst_dev,
+                 const __grid_constant__ CommPeers peers, int rank, int world, SolverPublished* pub,
+                 unsigned long long seq) {
+    static_assert(!SOLVE || GRAD, "the solver needs the gradient sums");
     extern __shared__ __align__(128) double s_dyn[];
-    __shared__ double2 s_ab[8], s_sh[8];
+    __shared__ double2 s_ab[8];
+    __shared__ double4 s_sh[8];
+    __shared__ double s_sums[kSolverVals];
+    if (SOLVE && solver_finished(state, pub, seq)) return;
+    SubTheta T;
+    if (SOLVE) {
+        T = sub_theta(state->x[0], state->x[1]);
+    } else {
+        T.eta = th.eta;
+        T.epsilon = th.epsilon;
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            T.al[l] = th.al[l];
+            T.bl[l] = th.bl[l];
+        }
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* ring0 = reinterpret_cast<unsigned char*>(s_dyn + (FAST ? ((tab.n + 15) & ~15) : 0));
     unsigned char* ring = ring0 + (size_t)warp * depth * kEvStage;
@@ -393,13 +425,13 @@ elm_coded_kernel(const double* __restrict__ PsE, const uint8_t* __restrict__ cod
     if (lane < depth) mbar_init(bars + lane, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (threadIdx.x < 8) {
-        // per-code constants {a_l, b_l} and {s_l, [l == 2]}, s = (-1, 1, 2 eta - 1) (fit.py:600-697);
+        // per-code constants {a_l, b_l} and {s_l, [l == 2], [l < 2]}, s = (-1, 1, 2 eta - 1) (fit.py:600-697);
         // code 3 is neutral: log(1 + 0 p) = 0 exactly, zero gradient weight; codes 4, 5 count as l = 2
         const int code = threadIdx.x;
         const int l = code >= 4 ? 2 : code;
-        const double sl = l == 0 ? -1.0 : (l == 1 ? 1.0 : 2.0 * th.eta - 1.0);
-        s_ab[code] = l < 3 ? make_double2(th.al[l], th.bl[l]) : make_double2(1.0, 0.0);
-        s_sh[code] = l < 3 ? make_double2(sl, l == 2 ? 1.0 : 0.0) : make_double2(0.0, 0.0);
+        const double sl = l == 0 ? -1.0 : (l == 1 ? 1.0 : 2.0 * T.eta - 1.0);
+        s_ab[code] = l < 3 ? make_double2(sel3(l, T.al), sel3(l, T.bl)) : make_double2(1.0, 0.0);
+        s_sh[code] = l < 3 ? make_double4(sl, l == 2 ? 1.0 : 0.0, l < 2 ? 1.0 : 0.0, 0.0) : make_double4(0.0, 0.0, 0.0, 0.0);
     }
     __syncwarp();
 
@@ -451,7 +483,7 @@ elm_coded_kernel(const double* __restrict__ PsE, const uint8_t* __restrict__ cod
     // the table and the constants are staged while the first chunks are in flight
     const double* s_tab = load_log_table<FAST>(tab, s_dyn);
 
-    CodedAcc a0 = {0.0, 0.0, 0.0, 1.0}, a1 = {0.0, 0.0, 0.0, 1.0};
+    CodedAcc a0 = {0.0, 0.0, 0.0, 1.0, 0.0, 0.0}, a1 = {0.0, 0.0, 0.0, 1.0, 0.0, 0.0};
     int nf = 0;                                              // factors in each running product
     int d = 0;
     uint32_t phase = 0;
@@ -479,8 +511,8 @@ elm_coded_kernel(const double* __restrict__ PsE, const uint8_t* __restrict__ cod
         for (int j = 0; j < kEvChunk / 64; ++j) {
             const double2 v = *reinterpret_cast<const double2*>(st + (64 * j + 2 * lane) * 8);
             const uint32_t c2 = *reinterpret_cast<const unsigned short*>(st + kEvChunk * 8 + 64 * j + 2 * lane);
-            coded_elem<GRAD, FAST>(v.x, c2 & 0xff, s_ab, s_sh, s_tab, a0);
-            coded_elem<GRAD, FAST>(v.y, c2 >> 8, s_ab, s_sh, s_tab, a1);
+            coded_elem<GRAD, FAST, SOLVE>(v.x, c2 & 0xff, s_ab, s_sh, s_tab, a0);
+            coded_elem<GRAD, FAST, SOLVE>(v.y, c2 >> 8, s_ab, s_sh, s_tab, a1);
         }
         nf += kEvChunk / 64;
         if (nf + kEvChunk / 64 > kProdMax) flush();
@@ -491,12 +523,12 @@ elm_coded_kernel(const double* __restrict__ PsE, const uint8_t* __restrict__ cod
         const unsigned char* st = ring + d * kEvStage;
         flush();
         for (int e = lane; e < left; e += 32)
-            coded_elem<GRAD, FAST>(reinterpret_cast<const double*>(st)[e], st[kEvChunk * 8 + e], s_ab, s_sh, s_tab, a0);
+            coded_elem<GRAD, FAST, SOLVE>(reinterpret_cast<const double*>(st)[e], st[kEvChunk * 8 + e], s_ab, s_sh, s_tab, a0);
     }
     flush();
-    double obj = a0.obj + a1.obj, ge = a0.ge + a1.ge, gh = a0.gh + a1.gh;
-    const double al[3] = {th.al[0], th.al[1], th.al[2]}, bl[3] = {th.bl[0], th.bl[1], th.bl[2]};
-    const double sl[3] = {-1.0, 1.0, 2.0 * th.eta - 1.0};
+    double obj = a0.obj + a1.obj, ge = a0.ge + a1.ge, gh = a0.gh + a1.gh, qa = a0.qa + a1.qa, qb = a0.qb + a1.qb;
+    const double al[3] = {T.al[0], T.al[1], T.al[2]}, bl[3] = {T.bl[0], T.bl[1], T.bl[2]};
+    const double sl[3] = {-1.0, 1.0, 2.0 * T.eta - 1.0};
     for (; cp < nq01; advance()) {                           // records {p, w_0, w_1, w_2}: real weights, three logs each
         const long long left = (n3 - (cp - nq0) * kEvChunk) >> 2;
         const int cnt = (int)(left < kEvChunk / 4 ? left : kEvChunk / 4);
@@ -515,9 +547,14 @@ elm_coded_kernel(const double* __restrict__ PsE, const uint8_t* __restrict__ cod
                     if (GRAD) {
                         double rcp;
                         obj = fma(w[l], fast_log_rcp<FAST>(M, s_tab, rcp), obj);
-                        const double dd = w[l] * (num * rcp);
+                        const double g = num * rcp;
+                        const double dd = w[l] * g;
                         ge = fma(sl[l], dd, ge);
                         if (l == 2) gh += dd;
+                        if (SOLVE) {
+                            if (l == 2) qb = fma(dd, g, qb);
+                            else qa = fma(dd, g, qa);
+                        }
                     } else {
                         obj = fma(w[l], fast_log<FAST>(M, s_tab), obj);
                     }
@@ -542,19 +579,30 @@ elm_coded_kernel(const double* __restrict__ PsE, const uint8_t* __restrict__ cod
                     double rx, r2;
                     const double lx = fast_log_rcp<FAST>(Mx, s_tab, rx), l2 = fast_log_rcp<FAST>(M2, s_tab, r2);
                     obj = fma(q, lx - l2, obj);
-                    const double qn = q * mix_num(r.x);
-                    const double dx = qn * rx, d2 = qn * r2;
+                    const double num = mix_num(r.x);
+                    const double gx = num * rx, g2 = num * r2;
+                    const double dx = q * gx, d2 = q * g2;
                     ge += fma(sx ? 1.0 : -1.0, dx, -sl[2] * d2);
                     gh -= d2;
+                    if (SOLVE) {
+                        qa = fma(dx, gx, qa);
+                        qb = fma(-d2, g2, qb);
+                    }
                 } else {
                     obj = fma(q, fast_log<FAST>(Mx, s_tab) - fast_log<FAST>(M2, s_tab), obj);
                 }
             }
         }
     }
-    // dE/d eta = -(2 eps - 1) sum_{l = 2} d;  dE/d eps = -sum s_l d                 (fit.py:600-697)
-    double v[3] = {obj, -(2.0 * th.epsilon - 1.0) * gh, -ge};
-    grid_reduce_store<3, kEvThreads>(v, ws, out);
+    if (SOLVE) {
+        double v[5] = {obj, ge, gh, qa, qb};
+        if (grid_reduce_last<5, kEvThreads>(v, ws, s_sums))
+            solver_epilogue(s_sums, state, konst_dev, peers, rank, world, pub, seq);
+    } else {
+        // dE/d eta = -(2 eps - 1) sum_{l = 2} d;  dE/d eps = -sum s_l d                 (fit.py:600-697)
+        double v[3] = {obj, -(2.0 * T.epsilon - 1.0) * gh, -ge};
+        grid_reduce_store<3, kEvThreads>(v, ws, out);
+    }
 }
 
 static inline int rows_grid(int64_t rows, int rows_per_block, int waves) {
@@ -683,22 +731,75 @@ int fcd_elm_coded(const double* PsE, const uint8_t* code, int64_t nE, const doub
     long long grid = (chunks + kEvWarps - 1) / kEvWarps;
     if (grid > sm_count()) grid = sm_count();                // one persistent CTA per SM
     if (grid < 1) grid = 1;
+    CommPeers nopeers;
+    comm_peers_from_host(nullptr, 1, nopeers);
 #define FCD_EC(G_, F_)                                                                                   \
     do {                                                                                                 \
-        static bool attr_set = false;                                                                    \
-        if (!attr_set) {                                                                                 \
-            cudaFuncSetAttribute(elm_coded_kernel<G_, F_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                 (int)kSmemBudget);                                                      \
-            attr_set = true;                                                                             \
-        }                                                                                                \
-        elm_coded_kernel<G_, F_><<<(unsigned)grid, kEvThreads, smem, st>>>(                              \
+        FCD_ALLOW_BIG_SMEM(elm_coded_kernel<G_, F_, false>);                                             \
+        elm_coded_kernel<G_, F_, false><<<(unsigned)grid, kEvThreads, smem, st>>>(                       \
             PsE, code, nE, reinterpret_cast<const Record*>(D), nd, reinterpret_cast<const double2*>(Hh), nh, th, \
-            tab, depth, out3, ws);                                                                       \
+            tab, depth, out3, ws, nullptr, nullptr, nopeers, 0, 1, nullptr, 0ull);                       \
     } while (0)
     if (want_grad) { if (fast) FCD_EC(true, true); else FCD_EC(true, false); }
     else           { if (fast) FCD_EC(false, true); else FCD_EC(false, false); }
 #undef FCD_EC
     return check_launch("fcd_elm_coded");
+}
+
+int fcd_elm_coded_solve(const double* PsE, const uint8_t* code, int64_t nE, const double* D, int64_t nd,
+                        const double* Hh, int64_t nh, double eps_lo, double eps_hi, void* state, const double* konst,
+                        void* const* windows_host, int32_t rank, int32_t world, void* published_host, uint64_t seq0,
+                        int32_t n_launches, double* ws, void* stream) {
+    FCD_REQUIRE(PsE != nullptr && code != nullptr && state != nullptr && ws != nullptr &&
+                (nd == 0 || D != nullptr) && (nh == 0 || Hh != nullptr) && nE >= 1 && nd >= 0 && nh >= 0,
+                "fcd_elm_coded_solve: bad argument");
+    FCD_REQUIRE(((reinterpret_cast<uintptr_t>(PsE) | reinterpret_cast<uintptr_t>(code) | reinterpret_cast<uintptr_t>(Hh)) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(D) & 31) == 0 && (reinterpret_cast<uintptr_t>(state) & 7) == 0,
+                "fcd_elm_coded_solve: plane / code / half records must be 16-byte aligned, records 32-byte aligned");
+    FCD_REQUIRE(n_launches >= 1 && n_launches <= 64 && world >= 1 && world <= kCommMaxWorld && rank >= 0 && rank < world &&
+                eps_lo > 0.0 && eps_lo <= eps_hi && eps_hi < 1.0, "fcd_elm_coded_solve: bad launch / box arguments");
+    CommPeers peers;
+    FCD_REQUIRE(comm_peers_from_host(windows_host, world, peers), "fcd_elm_coded_solve: NULL window");
+    SolverPublished* pub = nullptr;
+    if (published_host != nullptr) {
+        cudaError_t e = cudaHostGetDevicePointer((void**)&pub, published_host, 0);
+        FCD_REQUIRE(e == cudaSuccess, "fcd_elm_coded_solve: cudaHostGetDevicePointer: %s", cudaGetErrorString(e));
+    }
+    // every mixture weight the solve can form inside the box lies in [m / 2, 1], m = min(eps_lo, 1 - eps_hi)
+    const double m = eps_lo < 1.0 - eps_hi ? eps_lo : 1.0 - eps_hi;
+    const double epsl[3] = {m, m, m}, al[3] = {0.5 * m, 0.5 * m, 0.5 * m};
+    ThetaDev th;
+    memset(&th, 0, sizeof(th));
+    cudaStream_t st = (cudaStream_t)stream;
+    LogTabWindow tab;
+    FCD_REQUIRE(log_table_window(epsl, al, st, tab, true), "fcd_elm_coded_solve: log table initialisation failed");
+    const bool fast = log_table_covers(epsl, al);
+    const size_t tbytes = fast ? (size_t)((tab.n + 15) & ~15) * sizeof(double) : 0;
+    int depth = kEvMaxDepth;
+    while (depth > 2 && tbytes + ev_ring_bytes(depth) > kSmemBudget) --depth;
+    FCD_REQUIRE(tbytes + ev_ring_bytes(depth) <= kSmemBudget, "fcd_elm_coded_solve: shared memory budget exceeded");
+    const size_t smem = tbytes + ev_ring_bytes(depth);
+    const long long chunks = (nE + kEvChunk - 1) / kEvChunk + (nd * 4 + kEvChunk - 1) / kEvChunk +
+                             (nh * 2 + kEvChunk - 1) / kEvChunk;
+    long long grid = (chunks + kEvWarps - 1) / kEvWarps;
+    if (grid > sm_count()) grid = sm_count();                // one persistent CTA per SM
+    if (grid < 1) grid = 1;
+    if (fast) FCD_ALLOW_BIG_SMEM(elm_coded_kernel<true, true, true>);
+    else FCD_ALLOW_BIG_SMEM(elm_coded_kernel<true, false, true>);
+    for (int i = 0; i < n_launches; ++i) {
+        const unsigned long long seq = (unsigned long long)seq0 + (unsigned long long)i;
+        if (fast)
+            elm_coded_kernel<true, true, true><<<(unsigned)grid, kEvThreads, smem, st>>>(
+                PsE, code, nE, reinterpret_cast<const Record*>(D), nd, reinterpret_cast<const double2*>(Hh), nh, th, tab,
+                depth, nullptr, ws, static_cast<SolverState*>(state), konst, peers, rank, world, pub, seq);
+        else
+            elm_coded_kernel<true, false, true><<<(unsigned)grid, kEvThreads, smem, st>>>(
+                PsE, code, nE, reinterpret_cast<const Record*>(D), nd, reinterpret_cast<const double2*>(Hh), nh, th, tab,
+                depth, nullptr, ws, static_cast<SolverState*>(state), konst, peers, rank, world, pub, seq);
+        int rc = check_launch("fcd_elm_coded_solve");
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 }  // extern "C"

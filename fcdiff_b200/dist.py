@@ -52,32 +52,65 @@ class PeerWindow(object):
         self.seq = 0
         self._opened = []
         self._own = ctypes.c_void_p(0)
+        self._stream = None           # the ONE stream every exchange of this window is issued on
         self.windows = (ctypes.c_void_p * max(self.world, 1))()
+        self.ok = True
+        self.why = ""
         if self.world > 1:
-            self._check(self.lib.fcd_comm_window_create(ctypes.byref(self._own)), "fcd_comm_window_create")
+            # No exception may escape between two collectives (the other ranks would hang in the next
+            # one): every step records its outcome, the ranks exchange it, and all of them either
+            # keep the window or fall back together (EdgeShards.peer_window).
             hb = int(self.lib.fcd_comm_handle_bytes())
             handle = ctypes.create_string_buffer(hb)
-            self._check(self.lib.fcd_comm_window_export(self._own, handle), "fcd_comm_window_export")
+            try:
+                self._check(self.lib.fcd_comm_window_create(ctypes.byref(self._own)), "fcd_comm_window_create")
+                self._check(self.lib.fcd_comm_window_export(self._own, handle), "fcd_comm_window_export")
+            except Exception as exc:       # no IPC support, out of memory, ...
+                (self.ok, self.why) = (False, str(exc))
             handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(handle.raw), group=group)
-            for r in range(self.world):
-                if r == self.rank:
-                    self.windows[r] = self._own
-                    continue
-                peer = ctypes.c_void_p(0)
-                buf = ctypes.create_string_buffer(handles[r], hb)
-                self._check(self.lib.fcd_comm_window_open(buf, ctypes.byref(peer)), "fcd_comm_window_open")
-                self._opened.append(peer)
-                self.windows[r] = peer
-            dist.barrier(group=group)              # every window is open everywhere before the first exchange
+            dist.all_gather_object(handles, (self.ok, bytes(handle.raw)), group=group)
+            if all(h[0] for h in handles):
+                for r in range(self.world):
+                    if r == self.rank:
+                        self.windows[r] = self._own
+                        continue
+                    peer = ctypes.c_void_p(0)
+                    buf = ctypes.create_string_buffer(handles[r][1], hb)
+                    try:
+                        self._check(self.lib.fcd_comm_window_open(buf, ctypes.byref(peer)), "fcd_comm_window_open")
+                    except Exception as exc:   # a rank on another node, no peer access between the two GPUs
+                        (self.ok, self.why) = (False, str(exc))
+                        break
+                    self._opened.append(peer)
+                    self.windows[r] = peer
+            else:
+                (self.ok, self.why) = (False, self.why or "a peer rank could not create its window")
+            # every window is open everywhere before the first exchange -- or nobody uses them
+            flags = [None] * self.world
+            dist.all_gather_object(flags, self.ok, group=group)
+            if not all(flags):
+                (self.ok, self.why) = (False, self.why or "a peer rank could not open the windows")
         self._result = ctypes.c_void_p(0)
         self._check(self.lib.fcd_host_result_alloc(ctypes.byref(self._result)), "fcd_host_result_alloc")
         self._out = np.zeros(self.max_vals, dtype=np.float64)
         self._out_p = ctypes.c_void_p(self._out.ctypes.data)
 
+    def bind_stream(self, stream):
+        """The two-parity slot scheme (csrc/fcd_comm.cuh) is safe only if a rank issues its exchanges
+        in one order on ONE stream -- those launched here and those run inside the solver's evaluation
+        kernels alike: the window binds to the first stream it sees."""
+        sv = getattr(stream, "value", stream)
+        if self.world == 1:
+            return                                 # publication only: no peers, no slots to protect
+        if self._stream is None:
+            self._stream = sv
+        elif sv != self._stream:
+            raise RuntimeError("PeerWindow: exchanges of one window must all be issued on the same stream")
+
     def allreduce(self, vec_dev, n, stream):
         """Sums ``vec_dev[:n]`` (device, float64) over the ranks in place and returns
         the sums as a fresh host array."""
+        self.bind_stream(stream)
         self.seq += 1
         rc = self.lib.fcd_allreduce_small(self._ct.c_void_p(vec_dev.data_ptr()), n, self.windows, self.rank,
                                           self.world, self.seq, self._result, stream)
@@ -119,7 +152,12 @@ class EdgeShards(object):
         if not self._peer_tried:
             self._peer_tried = True
             if torch.cuda.is_available() and dist.is_initialized() and dist.get_backend(self.group) == "nccl":
-                self._peer = PeerWindow(self.group, self.rank, self.world)
+                pw = PeerWindow(self.group, self.rank, self.world)
+                if pw.ok:                  # all ranks agree (PeerWindow.__init__)
+                    self._peer = pw
+                else:                      # ranks on several nodes / no P2P: NCCL all-reduce + download instead
+                    self.peer_fallback_reason = pw.why
+                    pw.close()
         return self._peer
 
     def reduce_read(self, res, n=None, stream=None):

@@ -165,6 +165,14 @@ class UnsharedRegionFit(object):
     update_mu_sigma : bool
         Also re-estimate ``mu`` and ``sigma`` in ``_update_theta`` (new; the
         reference ships this step disabled, fit.py:232-237; default False).
+    theta_solver : "newton" | "lbfgsb"
+        Optimiser of the (eta, epsilon) sub-problem (fit.py:228-241).  ``"newton"`` (default):
+        the device-resident safeguarded projected Newton iteration of csrc/fcd_solver.cuh -- the
+        optimiser's step runs in the last CTA of every objective kernel, nothing returns to the
+        host between evaluations; converges to the minimiser of -E_lM on the reference's box to
+        ~1e-12.  ``"lbfgsb"``: SciPy's L-BFGS-B driven from the host with SciPy's default
+        tolerances, i.e. the reference's own optimiser call (iterate-for-iterate what the
+        golden trajectories under tests/golden were produced with).
     convergence_rule : "reference" | "magnitude"
         ``"reference"`` is fit.py:138-140 literally, ``(e - e*) / e < rel_tol``: with a
         negative free energy (the usual case: densities > 1) any *decrease* makes the
@@ -188,6 +196,9 @@ class UnsharedRegionFit(object):
         self.fused_sweep = False      # K2b: weights computed inside the sweep (no WT tensor; reference lookup, N <= 1024)
         self.elm_path = "auto"        # K3b form: "streams" (coded plane) | "tiered" | "auto" (coded unless most elements are undecided)
         self.convergence_rule = "reference"
+        self.theta_solver = "newton"  # (eta, epsilon): device-resident Newton | host-driven SciPy L-BFGS-B
+        self.solver_tol = 1e-7        # newton: a step below this is taken without another evaluation
+        self.solver_status = []       # newton: per solve (done code, evaluations)
         self.n_objective_evals = []
         self.profile = None           # _dev.KernelTimers for per-kernel CUDA-event timing
 
@@ -205,6 +216,8 @@ class UnsharedRegionFit(object):
         self.reuse_evaluations = True
         self._res = {}                # reusable device / pinned-host result vectors
         self._ctx = None              # cached argument list of the K3b evaluations
+        self._sctx = None             # the same for the device-resident solver
+        self._last_nfev = 4           # evaluations of the last device solve (sizes the first batch)
         self._keep_host = None        # host arrays an asynchronous upload is still reading
 
     # ------------------------------------------------------------------ private arrays
@@ -278,9 +291,10 @@ class UnsharedRegionFit(object):
         sufficient statistics.  The reference re-reads ``self.b`` / ``self.bt``
         at every ``_update_lps`` (fit.py:114-115); re-assign the attribute to
         have a changed array picked up."""
-        key = (id(self.b), id(self.bt), tuple(self.b.shape), tuple(self.bt.shape),
+        key = (self._input_stamp(self.b), self._input_stamp(self.bt),
                None if self.shards is None else self.shards.key())
-        if self._in is not None and self._in['key'] == key:
+        if (self._in is not None and self._in['key'] == key and self._in['src'][0] is self.b
+                and self._in['src'][1] is self.bt):
             return self._in
         lib = _lib.load()
         (C, H, U) = self._global_shape()
@@ -335,12 +349,33 @@ class UnsharedRegionFit(object):
             del b_dev
         nm = _dev.empty((max(Cl, 1),), torch.int32)
         _lib.check(lib.fcd_edge_table(c0, Cl, _dev.ptr(nm), _dev.stream()), "fcd_edge_table")
-        self._in = dict(key=key, C=C, H=H, U=U, c0=c0, Cl=Cl, u0=u0, Ul=Ul, pitchU=pitchU,
+        # `src` keeps the source objects alive: identity (`is`) cannot be faked by a recycled id()
+        self._in = dict(key=key, src=(self.b, self.bt), C=C, H=H, U=U, c0=c0, Cl=Cl, u0=u0, Ul=Ul, pitchU=pitchU,
                         bt=bt_dev, S1=S1, S2=S2, nm=nm, cache_key=None, P=None, L=None, PT=None, WT=None,
                         ev_S=ev_S, b_dev=(b_dev if ev_S is not None else None))
         self._evals = []
         self._const = None
         return self._in
+
+    @staticmethod
+    def _input_stamp(a):
+        """What identifies the CONTENT of an input as far as it can be known without reading it:
+        shape, and for tensors the storage address and torch's in-place version counter.  NumPy
+        arrays edited in place are not detectable: call ``invalidate_inputs()``."""
+        if torch.is_tensor(a):
+            return (tuple(a.shape), a.data_ptr(), a._version)
+        return (tuple(np.shape(a)),)
+
+    def invalidate_inputs(self):
+        """Forget the uploaded copies of ``b`` / ``bt`` (and everything derived from them): the next
+        step re-reads the arrays, as the reference does at every ``_update_lps`` (fit.py:114-115).
+        Needed only after editing an input array IN PLACE; re-assigning the attribute is enough
+        otherwise."""
+        self._in = None
+        self._evals = []
+        self._const = None
+        self._ctx = None
+        self._mat = None
 
     def _wait_healthy(self, inp):
         """Before the first kernel that reads S1 / S2: the main stream joins the side stream that
@@ -418,7 +453,7 @@ class UnsharedRegionFit(object):
             self._res[key] = _dev.SmallResult(n, dtype)
         return self._res[key]
 
-    def _build_streams(self, inp, res4):
+    def _build_streams(self, inp, res4, agree=True):
         """Code pass (csrc/fcd_streams.cu): dominant-state plane + one code byte per
         element + weighted records for the current (q_F, q_R); the theta-free part
         of E_lM lands in res4.dev[3].  Returns the argument head for
@@ -430,7 +465,7 @@ class UnsharedRegionFit(object):
         (c0, Cl, pitchU) = (inp['c0'], inp['Cl'], inp['pitchU'])
         inp['code_verR'] = None                     # the key lists are rebuilt below (or not at all)
         if Cl == 0:
-            if self.shards is not None and self.elm_path != "tiered":
+            if agree and self.shards is not None and self.elm_path != "tiered":
                 self.shards.any_rank(True)     # keep the collective sequence of _build_streams aligned
             return None
         (_, qF) = self._mF.get_dev()
@@ -455,7 +490,7 @@ class UnsharedRegionFit(object):
                 _dev.ptr(tot.dev), stream), "fcd_code_plane")
         (nd, nh) = (int(v) for v in tot.read(stream))
         use_tiered = self.elm_path == "auto" and nd * 4 + nh * 2 > Cl * U
-        if self.shards is not None:            # the ranks must take the same form: its collectives differ
+        if agree and self.shards is not None:  # the ranks must take the same form: its collectives differ
             use_tiered = self.shards.any_rank(use_tiered)
         if use_tiered:
             return None
@@ -536,6 +571,11 @@ class UnsharedRegionFit(object):
             self._ensure_patient_major()
 
         self.energy = [self._eval_energy()]
+        if not np.isfinite(self.energy[0]):
+            # a NaN / inf correlation (e.g. arctanh of |r| = 1 computed outside fcdiff_b200.corr) makes
+            # every sum it enters non-finite; the reference would iterate on NaNs (nothing is validated
+            # at fit.py:56-68) -- new check, raised before the first update
+            raise ValueError("Initial free energy is not finite: b / bt must hold finite correlations.")
         self.n_objective_evals = []
         for i in range(1, self.max_iters + 1):
             self._update_lq_F()
@@ -799,7 +839,9 @@ class UnsharedRegionFit(object):
         """
         # the code pass of the (eta, epsilon) solve does not depend on pi / gamma: it is enqueued
         # behind the K3a launch, so that one wait on the stream serves both results
-        early = self._objective_context if (self.optimise_theta_sub and self._lps_state == 'derived') else None
+        early = None
+        if self.optimise_theta_sub and self._lps_state == 'derived':
+            early = self._solver_context if self._use_device_solver() else self._objective_context
         self._update_pi_gamma(True, True, early)
         if self.optimise_theta_sub:
             self._update_theta_sub()
@@ -987,6 +1029,8 @@ class UnsharedRegionFit(object):
         eps = 1e-5
         if self._lps_state != 'derived':
             self._update_lps()
+        if self._use_device_solver():
+            return self._solve_theta_sub_device(theta_sub, eps)
         # scipy.optimize.minimize(..., method="L-BFGS-B", bounds=[(eps, 1 - eps)] * 2) of fit.py:228-241,
         # driven without SciPy's Python front end (same compiled routine, same iterates: _opt.py)
         # the optimiser's inner loop: everything pre-bound, one launch (+ one all-reduce of the
@@ -1030,6 +1074,114 @@ class UnsharedRegionFit(object):
         del self._evals[:-4]
         self.n_objective_evals.append(opt_result.nfev)
         self._unpack_theta_sub(opt_result.x)
+
+    def _use_device_solver(self):
+        """The device-resident solver needs the fused form and, with edge shards, the NVLink peer
+        window (the exchange runs inside the evaluation kernel); otherwise the host optimiser."""
+        if self.theta_solver not in ("newton", "lbfgsb"):
+            raise ValueError("theta_solver must be 'newton' or 'lbfgsb'")
+        if self.theta_solver != "newton":
+            return False
+        return self.shards is None or self.shards.peer_window() is not None
+
+    def _solver_context(self):
+        """Everything of a solve that is fixed for one (q_F, q_R, planes) state: the coded plane
+        and records of the code pass (or the tiered form's plane pointers), and THIS rank's
+        theta-free part of E_lM in device memory (the evaluation kernels add it themselves)."""
+        inp = self._ensure_cache()
+        key = (self._mF.version, self._mR.version, inp['cache_key'], id(inp), self.elm_path, "solver")
+        ctx = self._sctx
+        if ctx is not None and ctx['key'] == key:
+            return ctx
+        (N, H, U) = self._dims
+        (c0, Cl) = (inp['c0'], inp['Cl'])
+        (_, qF) = self._mF.get_dev()
+        (_, qR) = self._mR.get_dev()
+        (fstate, rstate) = (self._mF.get_state(), self._mR.get_state())
+        res = self._result(4, tag="elm")          # slot 3: theta-free part (this rank's share)
+        lib = _lib.load()
+        head = self._build_streams(inp, res, agree=False)
+        if head is not None:
+            (fn, name) = (lib.fcd_elm_coded_solve, "K3b_elm_streams")
+        else:
+            (fn, name) = (lib.fcd_elm_tiered_solve, "K3b_elm_obj_grad")
+            head = (_dev.ptr(inp['P']), max(Cl, 1) * inp['pitchU'], Cl, U, inp['pitchU'],
+                    _dev.ptr(qF[c0 * 3:]), _dev.ptr(fstate[c0:]), _dev.ptr(qR), _dev.ptr(rstate), rstate.shape[1],
+                    N, _dev.ptr(inp['nm']))
+            if Cl > 0:
+                with _dev.timed(self.profile, "K3b_elm_const"):
+                    _lib.check(lib.fcd_elm_const(
+                        _dev.ptr(inp['L']), Cl, U, inp['pitchU'], _dev.ptr(qF[c0 * 3:]), _dev.ptr(fstate[c0:]),
+                        _dev.ptr(qR), _dev.ptr(rstate), rstate.shape[1], N, _dev.ptr(inp['nm']),
+                        _dev.ptr(res.dev[3:]), _dev.ptr(_dev.workspace()), _dev.stream()), "fcd_elm_const")
+            else:
+                res.dev[3:].zero_()
+        self._sctx = dict(key=key, fn=fn, name=name, head=head, konst=_dev.ptr(res.dev[3:]),
+                          keep=(qF, qR, fstate, rstate, res), verF=self._mF.version, verR=self._mR.version)
+        return self._sctx
+
+    def _solve_theta_sub_device(self, theta_sub, eps):
+        """(eta, epsilon) = argmin -E_lM on [eps, 1 - eps]^2 (fcdiff/fit.py:228-241) by the
+        device-resident Newton iteration: batches of evaluation kernels are enqueued back to back,
+        each one's last CTA takes the optimiser's step (csrc/fcd_solver.cuh); the host waits once
+        per batch."""
+        lib = _lib.load()
+        ctx = self._solver_context()
+        sb = _dev.solver_block()
+        stream = _dev.stream()
+        ws = _dev.ptr(_dev.workspace())
+        if self.shards is None:
+            (windows, rank, world) = (None, 0, 1)
+        else:
+            pw = self.shards.peer_window()
+            (windows, rank, world) = (pw.windows, pw.rank, pw.world)
+            pw.bind_stream(stream)
+        (eta0, eps0) = (float(theta_sub[0]), float(theta_sub[1]))
+        (fn, head, konst, name) = (ctx['fn'], ctx['head'], ctx['konst'], ctx['name'])
+        budget = 60
+        nfev = 0
+        first = max(2, min(6, self._last_nfev))
+        while True:
+            # the epsilon box of this pass: the reference's bounds, at most a factor 8 towards 0 or 1
+            # from the start point -- it sizes the shared-memory logarithm table of the kernels
+            # (every mixture weight lies in [min(eps, 1 - eps) / 2, 1])
+            lo_e = max(eps, eps0 / 8.0)
+            hi_e = min(1.0 - eps, 1.0 - (1.0 - eps0) / 8.0)
+            eps0 = min(max(eps0, lo_e), hi_e)
+            _lib.check(lib.fcd_solver_init(_dev.ptr(sb.state), eta0, eps0, _lib.d3([eps, lo_e]),
+                                           _lib.d3([1.0 - eps, hi_e]), float(self.solver_tol), budget - nfev, stream),
+                       "fcd_solver_init")
+            batch = first
+            done_before = 0                      # evaluations this pass had consumed before the batch
+            while True:
+                with _dev.timed(self.profile, name) as count:
+                    rc = fn(*head, lo_e, hi_e, _dev.ptr(sb.state), konst, windows, rank, world, sb.pub,
+                            sb.seq + 1, batch, ws, stream)
+                if rc != 0:
+                    _lib.check(rc, name)
+                sb.seq += batch
+                st = sb.wait()
+                if count is not None:            # launches that did work (the rest exited at once)
+                    count[0] = max(1, int(st.nfev) - done_before)
+                done_before = int(st.nfev)
+                if st.done:
+                    break
+                batch = 2
+            nfev += int(st.nfev)
+            (eta0, eps0) = (float(st.x[0]), float(st.x[1]))
+            pinned = (eps0 <= lo_e and lo_e > eps) or (eps0 >= hi_e and hi_e < 1.0 - eps)
+            if st.done == 3:
+                raise _lib.FcdError("fcd_elm_*_solve: a peer rank did not arrive (device-side time-out)")
+            if not pinned or nfev >= budget:
+                break
+            first = 2
+        self._last_nfev = nfev
+        self.solver_status.append((int(st.done), nfev))
+        self.n_objective_evals.append(nfev)
+        self._unpack_theta_sub(np.array([eta0, eps0]))
+        if np.isfinite(st.f):
+            self._evals.append(dict(x=(float(eta0), float(eps0)), verF=ctx['verF'], verR=ctx['verR'], elm=-float(st.f)))
+            del self._evals[:-4]
 
     def _pack_theta_sub(self):
         """

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define FCD_VERSION 110
+#define FCD_VERSION 120
 
 #if defined(__GNUC__)
 #define FCD_API __attribute__((visibility("default")))
@@ -65,6 +65,10 @@ FCD_API int fcd_download(void* dst_host, const void* src, int64_t bytes, void* s
  * `gpu_launches`), and reset. */
 FCD_API int64_t fcd_launch_count(void);
 FCD_API void fcd_launch_count_reset(void);
+/* NVTX range around a kernel family (profiling aid, SURVEY 5 "tracing / profiling": the reference has
+ * none).  `name_host` is copied by the tools; ranges nest per thread.  No-ops without a profiler. */
+FCD_API void fcd_nvtx_push(const char* name_host);
+FCD_API void fcd_nvtx_pop(void);
 
 /* ------------------------------------------------------- small exchanges    */
 /* One-shot all-reduce (sum) of n <= fcd_comm_max_vals() doubles over NVLink peer
@@ -296,6 +300,61 @@ FCD_API int fcd_code_records(const double* P, int64_t planeStride, const double*
 FCD_API int fcd_elm_coded(const double* PsE, const uint8_t* code, int64_t nE, const double* D, int64_t nd,
                   const double* Hh, int64_t nh, const fcd_theta* theta_host, int32_t want_grad, double* out3,
                   double* ws, void* stream);
+
+/* ------------------------------------------- device-resident (eta, epsilon) solver */
+/* Replaces the host optimiser of fcdiff/fit.py:228-241 (scipy.optimize.minimize on
+ * [1e-5, 1 - 1e-5]^2, objective fit.py:270-286 = -E_lM, gradient fit.py:600-697): a safeguarded
+ * projected Newton iteration whose step is taken by the LAST CTA of every evaluation kernel
+ * (csrc/fcd_solver.cuh) -- the evaluations of one solve are enqueued back to back and read the
+ * iterate from device memory; nothing returns to the host between them.  With edge shards the
+ * same CTA first exchanges the six partial sums over the peer windows (fcd_comm_window_*), in rank
+ * order, so every rank takes bit-identical steps.
+ *   state: fcd_solver_state_bytes() of device memory, set by fcd_solver_init (box lo/hi per
+ *     parameter, start point, `tol`: a step of max |dx| <= tol is taken without another
+ *     evaluation and ends the solve; max_evals bounds the evaluations);
+ *   fcd_elm_coded_solve / fcd_elm_tiered_solve: n_launches evaluations of the coded-plane /
+ *     tiered form (arguments as fcd_elm_coded / fcd_elm_obj_grad) at the state's iterate; launches
+ *     after the solve has finished exit at once.  [eps_lo, eps_hi] must contain the box of epsilon
+ *     (it sizes the shared-memory logarithm table).  konst (device, may be NULL): this rank's
+ *     theta-free part of E_lM (fcd_code_records / fcd_elm_const), added to the objective.
+ *     published_host: fcd_host_mapped_alloc(fcd_solver_published_bytes()) -- every launch stores
+ *     the state there followed by its sequence number seq0 + i;
+ *   fcd_solver_wait spins (host) until launch `seq` has published and copies the state
+ *     (fcd_solver_state_bytes(), layout `fcd_solver_state` below) to state_out_host. */
+typedef struct fcd_solver_state {
+    double x[2];         /* (eta, epsilon): next evaluation point; the solution when done */
+    double xprev[2];
+    double fprev;
+    double f;            /* -E_lM at x when done (incl. the theta-free part) */
+    double g[2];         /* gradient at the last evaluated point */
+    double lo[2], hi[2];
+    double tol;
+    double step;
+    int32_t have_prev, nfev, nback;
+    int32_t done;        /* 0 running; 1 converged; 2 stopped (budget / no descent / non-finite); 3 peer time-out */
+    int32_t max_evals, pad_;
+} fcd_solver_state;
+FCD_API int64_t fcd_solver_state_bytes(void);
+FCD_API int64_t fcd_solver_published_bytes(void);
+FCD_API int fcd_host_mapped_alloc(int64_t bytes, void** out_host);
+FCD_API int fcd_host_mapped_free(void* p_host);
+FCD_API int fcd_solver_init(void* state, double eta0, double eps0, const double* lo2_host, const double* hi2_host,
+                    double tol, int32_t max_evals, void* stream);
+FCD_API int fcd_elm_coded_solve(const double* PsE, const uint8_t* code, int64_t nE, const double* D, int64_t nd,
+                        const double* Hh, int64_t nh, double eps_lo, double eps_hi, void* state, const double* konst,
+                        void* const* windows_host, int32_t rank, int32_t world, void* published_host, uint64_t seq0,
+                        int32_t n_launches, double* ws, void* stream);
+FCD_API int fcd_elm_tiered_solve(const double* P, int64_t planeStride, int64_t C, int32_t U, int64_t pitchU,
+                         const double* qF, const uint8_t* fstate, const double* qR, const uint8_t* rstate,
+                         int64_t pitchS, int32_t N, const int32_t* nm, double eps_lo, double eps_hi, void* state,
+                         const double* konst, void* const* windows_host, int32_t rank, int32_t world,
+                         void* published_host, uint64_t seq0, int32_t n_launches, double* ws, void* stream);
+/* Host-side twins of fcd_solver_init and of the optimiser transition the kernels' last CTA runs (same code):
+ * sums6_host = {obj, ge, G_2, Q_0 + Q_1, Q_2, theta-free part} at state.x (csrc/fcd_solver.cuh). */
+FCD_API int fcd_solver_init_host(void* state_host, double eta0, double eps0, const double* lo2_host,
+                         const double* hi2_host, double tol, int32_t max_evals);
+FCD_API int fcd_solver_step_host(void* state_host, const double* sums6_host);
+FCD_API int fcd_solver_wait(const void* published_host, uint64_t seq, void* state_out_host, int32_t timeout_ms);
 
 /* K4 -- free-energy terms; replaces `_eval_energy` and `_eval_E_*`
  * (fcdiff/fit.py:142-155, 447-539).  out[0..5] = E_lp_F, E_lp_B_g_F, E_lp_R,

@@ -163,11 +163,19 @@ def test_eval_energy_arrays_mode(unit_vectors):
 
 
 # ------------------------------------------------------------------ fused path vs the reference trajectory
-def _fit_for(b, bt, model=None, eta_shift=0.0):
+SOLVERS = ["newton", "lbfgsb"]
+
+
+def _fit_for(b, bt, model=None, eta_shift=0.0, solver="lbfgsb"):
+    """``solver``: "lbfgsb" = SciPy's L-BFGS-B with its default tolerances, the optimiser call the
+    reference-generated golden trajectories were produced with; "newton" = the device-resident
+    solver (the package default), which converges to the minimiser itself -- its oracle is
+    ``O.run(..., polish=True)``."""
     fit = F.UnsharedRegionFit()
     fit.b, fit.bt = b, bt
     fit.model = model or fcdiff.UnsharedRegionModel()
     fit.model.eta += eta_shift
+    fit.theta_solver = solver
     return fit
 
 
@@ -195,16 +203,16 @@ def test_cfg1_fused_iterations_without_optimiser(cfg1):
         nptest.assert_allclose(fit._opt_fun(np.array(x)), fg[0], rtol=1e-10)
 
 
-def _check_run(fit, g, final_only=False):
+def _check_run(fit, g, final_only=False, tol_theta=1e-6, tol_q=1e-6):
     nptest.assert_allclose(fit.energy, g["energy"], rtol=1e-6)
     assert len(fit.energy) == len(g["energy"])
     nptest.assert_allclose([fit.model.pi, fit.model.eta, fit.model.epsilon],
-                           [g["pi"][-1], g["eta"][-1], g["epsilon"][-1]], rtol=1e-6)
+                           [g["pi"][-1], g["eta"][-1], g["epsilon"][-1]], rtol=tol_theta)
     nptest.assert_allclose(fit.model.gamma, g["gamma"][-1], rtol=1e-6)
     lqF = g["lq_F_final"] if final_only else g["lq_F"][-1]
     lqR = g["lq_R_final"] if final_only else g["lq_R"][-1]
-    nptest.assert_allclose(np.exp(fit._lq_F), np.exp(lqF), rtol=1e-6, atol=1e-300)
-    nptest.assert_allclose(np.exp(fit._lq_R), np.exp(lqR), rtol=1e-6, atol=1e-300)
+    nptest.assert_allclose(np.exp(fit._lq_F), np.exp(lqF), rtol=tol_q, atol=1e-300)
+    nptest.assert_allclose(np.exp(fit._lq_R), np.exp(lqR), rtol=tol_q, atol=1e-300)
     # MAP labels bit-exact away from ties
     gap_F = np.sort(lqF, axis=2)
     clear = (gap_F[:, :, 2] - gap_F[:, :, 1]) > 1e-6
@@ -215,20 +223,87 @@ def _check_run(fit, g, final_only=False):
     assert clear.mean() > 0.99 and clear_R.mean() > 0.99
 
 
-def test_cfg1_full_run_matches_reference(cfg1):
+# The golden trajectories were produced by the reference's step functions with SciPy's L-BFGS-B at
+# its DEFAULT tolerances, which stops 1e-7 .. 2e-6 (relative) short of the minimiser of the (eta,
+# epsilon) sub-problem (measured with the oracle: tests/test_oracle_golden.py::test_polish_*).
+# "lbfgsb" repeats that optimiser call iterate for iterate and is held to 1e-6 everywhere; "newton"
+# converges to the minimiser itself, so against THESE files its theta / posteriors are held to the
+# optimiser slack of the golden run (and to 1e-6 against the polished oracle, test_newton_*).
+_GOLDEN_TOL = {"lbfgsb": dict(), "newton": dict(tol_theta=2e-5, tol_q=5e-4)}
+
+
+@pytest.mark.parametrize("solver", SOLVERS)
+def test_cfg1_full_run_matches_reference(cfg1, solver):
     g = cfg1
-    fit = _fit_for(g["b"], g["bt"], eta_shift=0.1)
+    fit = _fit_for(g["b"], g["bt"], eta_shift=0.1, solver=solver)
     fit.run()
-    _check_run(fit, g)
+    _check_run(fit, g, **_GOLDEN_TOL[solver])
     assert isinstance(fit.energy, list) and fit._lq_F.shape == (45, 1, 3) and fit._lq_R.shape == (10, 20, 2)
 
 
-def test_cfg2_full_run_matches_reference(cfg2):
+@pytest.mark.parametrize("solver", SOLVERS)
+def test_cfg2_full_run_matches_reference(cfg2, solver):
     g = cfg2
     (b, bt) = golden_inputs(90, 50, 50)
-    fit = _fit_for(b, bt, eta_shift=0.1)
+    fit = _fit_for(b, bt, eta_shift=0.1, solver=solver)
     fit.run()
-    _check_run(fit, g, final_only=True)
+    _check_run(fit, g, final_only=True, **_GOLDEN_TOL[solver])
+
+
+@pytest.mark.parametrize("N,H,U,iters", [(10, 20, 20, 6), (24, 9, 33, 4), (90, 50, 50, 3)])
+@pytest.mark.parametrize("lookup", ["reference", "symmetric"])
+def test_newton_solver_full_run_vs_polished_oracle(N, H, U, iters, lookup):
+    """The default (device-resident Newton) solver against the oracle whose (eta, epsilon) solve is
+    polished to the minimiser: energies, parameters and posteriors at 1e-6, MAP labels exact away
+    from ties; every solve must report convergence within a handful of evaluations."""
+    (_, _, _, _, b, bt) = O.sample(O.Theta(), N, H, U, np.random.RandomState(N + 1))
+    fit = _fit_for(b, bt, eta_shift=0.1, solver="newton")
+    fit.edge_lookup = lookup
+    fit.max_iters = iters
+    fit.rel_tol = -1.0
+    fit.run()
+    tho = O.Theta()
+    tho.eta += 0.1
+    out = O.run(b, bt, tho, max_iters=iters, rel_tol=-1.0, edge_lookup=lookup, polish=True)
+    nptest.assert_allclose(fit.energy, out["energy"], rtol=1e-6)
+    nptest.assert_allclose([fit.model.pi, fit.model.eta, fit.model.epsilon], [tho.pi, tho.eta, tho.epsilon], rtol=1e-6)
+    nptest.assert_allclose(fit.model.gamma, tho.gamma, rtol=1e-6)
+    nptest.assert_allclose(np.exp(fit._lq_F), np.exp(out["lq_F"]), rtol=1e-6, atol=1e-300)
+    nptest.assert_allclose(np.exp(fit._lq_R), np.exp(out["lq_R"]), rtol=1e-6, atol=1e-300)
+    assert len(fit.solver_status) == iters
+    assert all(done == 1 and nfev <= 12 for (done, nfev) in fit.solver_status), fit.solver_status
+
+
+def test_newton_solver_reaches_active_bounds_and_leaves_the_table_window():
+    """Start points far from the minimiser: epsilon has to travel more than the factor 8 one pass of
+    the solver may move it (the box that sizes the kernels' logarithm table), and a problem whose
+    minimiser sits ON the reference's bound 1e-5 (patients drawn with epsilon = 0: no edge deviates
+    from the template beyond the region effects)."""
+    th_true = O.Theta()
+    (_, _, _, _, b, bt) = O.sample(th_true, 20, 12, 40, np.random.RandomState(4))
+    for (eta0, eps0) in ((0.6, 0.3), (0.02, 0.0004), (0.7, 0.002)):     # all in the basin of the minimiser with epsilon < 1/2
+        model = fcdiff.UnsharedRegionModel()
+        (model.eta, model.epsilon) = (eta0, eps0)
+        fit = _fit_for(b, bt, model, solver="newton")
+        fit.max_iters = 2
+        fit.rel_tol = -1.0
+        fit.run()
+        tho = O.Theta(eta=eta0, epsilon=eps0)
+        out = O.run(b, bt, tho, max_iters=2, rel_tol=-1.0, polish=True)
+        nptest.assert_allclose([fit.model.eta, fit.model.epsilon], [tho.eta, tho.epsilon], rtol=1e-6)
+        nptest.assert_allclose(fit.energy, out["energy"], rtol=1e-6)
+    th0 = O.Theta(epsilon=1e-9, pi=0.0001)
+    (_, _, _, _, b, bt) = O.sample(th0, 12, 10, 30, np.random.RandomState(8))
+    fit = _fit_for(b, bt, solver="newton")
+    fit.max_iters = 3
+    fit.rel_tol = -1.0
+    fit.run()
+    tho = O.Theta()
+    out = O.run(b, bt, tho, max_iters=3, rel_tol=-1.0, polish=True)
+    nptest.assert_allclose(fit.energy, out["energy"], rtol=1e-6)
+    nptest.assert_allclose(fit.model.epsilon, tho.epsilon, rtol=1e-6, atol=1e-12)
+    assert tho.epsilon == 1e-5 and fit.model.epsilon == 1e-5          # both sit on the reference's lower bound
+    nptest.assert_allclose(fit.model.eta, tho.eta, rtol=1e-5)
 
 
 # ------------------------------------------------------------------ fused path vs the oracle on seeded inputs
@@ -314,7 +389,8 @@ def test_fused_steps_vs_oracle(N, H, U, lookup, peaked):
     nptest.assert_allclose(mom, momo, rtol=1e-9, atol=1e-9 * np.abs(momo).max())
 
 
-def test_mu_sigma_update_vs_oracle_and_lowers_energy():
+@pytest.mark.parametrize("solver", SOLVERS)
+def test_mu_sigma_update_vs_oracle_and_lowers_energy(solver):
     """mu / sigma re-estimation (disabled in the reference, fit.py:232-237): the
     GPU fit with ``update_mu_sigma`` follows the oracle's trajectory, and the
     generalised-EM step never raises the free energy."""
@@ -323,14 +399,15 @@ def test_mu_sigma_update_vs_oracle_and_lowers_energy():
     model = fcdiff.UnsharedRegionModel()
     model.mu = np.array([-0.2, 0.02, 0.25])
     model.sigma = np.array([0.04, 0.05, 0.07])
-    fit = _fit_for(b, bt, model)
+    fit = _fit_for(b, bt, model, solver=solver)
     fit.update_mu_sigma = True
     fit.edge_lookup = "symmetric"    # a true coordinate descent (the reference's lookup quirk is not)
     fit.max_iters = 4
     fit.rel_tol = -1.0               # run all iterations
     fit.run()
     tho = O.Theta(mu=(-0.2, 0.02, 0.25), sigma=(0.04, 0.05, 0.07))
-    out = O.run(b, bt, tho, max_iters=4, rel_tol=-1.0, update_mu_sigma=True, edge_lookup="symmetric")
+    out = O.run(b, bt, tho, max_iters=4, rel_tol=-1.0, update_mu_sigma=True, edge_lookup="symmetric",
+                polish=(solver == "newton"))
     nptest.assert_allclose(fit.energy, out["energy"], rtol=1e-6)
     nptest.assert_allclose(fit.model.mu, tho.mu, rtol=1e-6, atol=1e-9)
     nptest.assert_allclose(fit.model.sigma, tho.sigma, rtol=1e-6)
@@ -341,16 +418,17 @@ def test_mu_sigma_update_vs_oracle_and_lowers_energy():
     assert np.abs(fit.model.sigma - th_true.sigma).max() < 0.01
 
 
-def test_full_run_symmetric_lookup_vs_oracle():
+@pytest.mark.parametrize("solver", SOLVERS)
+def test_full_run_symmetric_lookup_vs_oracle(solver):
     th = O.Theta()
     (_, _, _, _, b, bt) = O.sample(th, 14, 12, 15, np.random.RandomState(5))
-    fit = _fit_for(b, bt, eta_shift=0.1)
+    fit = _fit_for(b, bt, eta_shift=0.1, solver=solver)
     fit.edge_lookup = "symmetric"
     fit.max_iters = 5
     fit.run()
     tho = O.Theta()
     tho.eta += 0.1
-    out = O.run(b, bt, tho, max_iters=5, edge_lookup="symmetric")
+    out = O.run(b, bt, tho, max_iters=5, edge_lookup="symmetric", polish=(solver == "newton"))
     nptest.assert_allclose(fit.energy, out["energy"], rtol=1e-6)
     nptest.assert_allclose(np.exp(fit._lq_F), np.exp(out["lq_F"]), rtol=1e-6, atol=1e-300)
     nptest.assert_allclose(np.exp(fit._lq_R), np.exp(out["lq_R"]), rtol=1e-6, atol=1e-300)
