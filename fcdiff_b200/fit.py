@@ -726,7 +726,7 @@ class UnsharedRegionFit(object):
         self._wait_healthy(inp)
         if self.coded_estep and Cl > 0 and inp.get('code_verR') == self._mR.version and inp.get('PsE') is not None:
             # the code plane and key lists of the last M-step still describe q_R (fcd_estep_qF_coded)
-            with _dev.timed(self.profile, "K2_estep_qF"):
+            with _dev.timed(self.profile, "K2_estep_qF_coded"):
                 _lib.check(lib.fcd_estep_qF_coded(
                     _dev.ptr(inp['S1']), _dev.ptr(inp['S2']), H, _dev.ptr(inp['P']), max(Cl, 1) * inp['pitchU'],
                     Cl, U, inp['pitchU'], _dev.ptr(qR), N, _dev.ptr(inp['nm']), _dev.ptr(inp['code']), inp['pitchQ'],
