@@ -203,6 +203,15 @@ class KernelTimers(object):
     def reset(self):
         self.events = {}
 
+    def relabel_last(self, name, k, new_name):
+        """Books the last ``k`` brackets of ``name`` under ``new_name`` (solver launches that found the
+        solve finished and exited at once are not evaluations)."""
+        if k <= 0 or name not in self.events:
+            return
+        moved = self.events[name][-k:]
+        del self.events[name][-k:]
+        self.events.setdefault(new_name, []).extend(moved)
+
     def summary(self):
         """name -> (launches, total_ms, mean_ms)."""
         torch.cuda.synchronize()

@@ -255,7 +255,9 @@ struct StreamGeom {
 
 constexpr int kStreamWarps = 16;
 constexpr int kStreamThreads = kStreamWarps * 32;
-constexpr size_t kSmemBudget = 226 * 1024;                   // dynamic shared memory of one CTA (1 CTA / SM)
+// dynamic shared memory of one CTA (1 CTA / SM): the 227 KB opt-in limit minus 2 KB for the kernels' static
+// shared memory (tables, reduction scratch: up to ~1.2 KB) -- the opt-in is refused if static + dynamic exceed it
+constexpr size_t kSmemBudget = 225 * 1024;
 
 // Ring depth that fits next to `other` bytes (log table) in the CTA's shared memory; 0 if none does.
 template <int NPL, int SEG>

@@ -367,13 +367,15 @@ estep_qF_coded_kernel(const double* __restrict__ S1, const double* __restrict__ 
         }
     };
     // an element with one undecided region: q (log M_s - log M_2) per template state (half record {p*, +-q})
-    auto half = [&](int64_t c, int u, bool sx, double q) {
-        const double p0 = __ldg(P + c * pitchU + u), p1 = __ldg(P + planeStride + c * pitchU + u);
+    auto half_p = [&](double p0, double p1, bool sx, double q) {
         const double p3[3] = {p0, p1, (1.0 - p0) - p1};
         const double ax = sx ? th.al[1] : th.al[0], bx = sx ? th.bl[1] : th.bl[0];
 #pragma unroll
         for (int k = 0; k < 3; ++k)
             acc[k] = fma(q, fast_log<FAST>(fma(bx, p3[k], ax), s_tab) - fast_log<FAST>(mix_rel(th, 2, p3[k]), s_tab), acc[k]);
+    };
+    auto half = [&](int64_t c, int u, bool sx, double q) {
+        half_p(__ldg(P + c * pitchU + u), __ldg(P + planeStride + c * pitchU + u), sx, q);
     };
     double keep[3] = {0.0, 0.0, 0.0};                        // row ends: see estep_qF_kernel
     int64_t keep_c = -1;
@@ -382,9 +384,41 @@ estep_qF_coded_kernel(const double* __restrict__ S1, const double* __restrict__ 
         if (keep_c >= 0) k2_finish(keep_c, keep, __ldg(S1 + keep_c), __ldg(S2 + keep_c), th, lqF, qF);
         keep_c = -1;
     };
+    // The half records of a row are taken off the critical path (they used to be a chain of dependent
+    // gathers after the row's stream: counts -> rowoff -> key -> p_0, p_1): the row's counts / offsets
+    // are requested one row ahead; at the start of a row every lane requests the key and the weight of
+    // the row's half records lane and lane + 32 (the common case: ~50 per row of 500 patients); while the
+    // segments stream through the ring, a lane whose record lies in the resident segment copies its
+    // p_0, p_1 from the STAGE (shared memory: no gather at all); after the row the 2 x 32 records are
+    // evaluated densely.  Records beyond 64 per row and full records (rare) keep the gather path.
+    int2 nxt_cnt = make_int2(0, 0);
+    longlong2 nxt_ro = make_longlong2(0, 0);
+    if (c_first < C) {
+        nxt_cnt = __ldg(counts + c_first);
+        if (nxt_cnt.x != 3 * U && (nxt_cnt.x > 0 || nxt_cnt.y > 0)) nxt_ro = __ldg(rowoff + c_first);
+    }
     int d = 0;
     uint32_t phase = 0;
     for (int64_t c = c_first; c < C; c += W) {
+        const int2 cnt = nxt_cnt;
+        const longlong2 ro = nxt_ro;
+        const bool listed = cnt.x != 3 * U && (cnt.x > 0 || cnt.y > 0);
+        int hu[2] = {-1, -1};
+        double hq[2] = {0.0, 0.0}, hp0[2] = {0.0, 0.0}, hp1[2] = {0.0, 0.0};
+        if (listed) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int i = lane + 32 * k;
+                if (i < cnt.y) {
+                    hu[k] = (int)(__ldg(keysH + ro.y + i) & 0xffffull);
+                    hq[k] = __ldg(Hh + ro.y + i).y;
+                }
+            }
+        }
+        if (c + W < C) {                                     // the next row's counts / offsets: in flight during this row
+            nxt_cnt = __ldg(counts + c + W);
+            nxt_ro = __ldg(rowoff + c + W);                  // (garbage for rows without records: not used then)
+        }
         for (int s = 0; s < nseg; ++s) {
             mbar_wait(bars + d, phase);
             const unsigned char* st = ring + d * kK2cStage;
@@ -413,6 +447,15 @@ estep_qF_coded_kernel(const double* __restrict__ S1, const double* __restrict__ 
                     if (++nf == kProdMax) flush();
                 }
             }
+            // my half records that lie in this segment: p_0, p_1 straight from the stage
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int o = hu[k] - s * kK2cSeg;
+                if (o >= 0 && o < kK2cSeg) {
+                    hp0[k] = *reinterpret_cast<const double*>(st + o * 8);
+                    hp1[k] = *reinterpret_cast<const double*>(st + kK2cSeg * 8 + o * 8);
+                }
+            }
             __syncwarp();
             issue();
             if (++d == depth) {
@@ -422,18 +465,24 @@ estep_qF_coded_kernel(const double* __restrict__ S1, const double* __restrict__ 
         }
         flush();
         // the row's elements with real weights
-        const int v = __ldg(nm + c);
-        const int n = v & 0xffff, m = (v >> 16) & 0xffff;
-        const int2 cnt = __ldg(counts + c);
         if (cnt.x == 3 * U) {                                // the edge was unpeaked at the code pass: every element
+            const int v = __ldg(nm + c);
+            const int n = v & 0xffff, m = (v >> 16) & 0xffff;
             for (int u = lane; u < U; u += 32) weighted(c, u, n, m);
-        } else if (cnt.x > 0 || cnt.y > 0) {
-            const longlong2 ro = __ldg(rowoff + c);
-            const unsigned long long* kf = keysF + ro.x;
-            for (int i = lane; i < cnt.x; i += 32) weighted(c, (int)(__ldg(kf + i) & 0xffffull), n, m);
+        } else if (listed) {
+            if (cnt.x > 0) {
+                const int v = __ldg(nm + c);
+                const int n = v & 0xffff, m = (v >> 16) & 0xffff;
+                const unsigned long long* kf = keysF + ro.x;
+                for (int i = lane; i < cnt.x; i += 32) weighted(c, (int)(__ldg(kf + i) & 0xffffull), n, m);
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+                if (32 * k < cnt.y && hu[k] >= 0)            // first condition warp-uniform
+                    half_p(hp0[k], hp1[k], __double2hiint(hq[k]) < 0, fabs(hq[k]));
             const unsigned long long* kh = keysH + ro.y;
             const double2* hr = Hh + ro.y;
-            for (int i = lane; i < cnt.y; i += 32) {
+            for (int i = 64 + lane; i < cnt.y; i += 32) {
                 const double qs = __ldg(hr + i).y;
                 half(c, (int)(__ldg(kh + i) & 0xffffull), __double2hiint(qs) < 0, fabs(qs));
             }

@@ -1154,15 +1154,22 @@ class UnsharedRegionFit(object):
             batch = first
             done_before = 0                      # evaluations this pass had consumed before the batch
             while True:
-                with _dev.timed(self.profile, name) as count:
+                if self.profile is None:
                     rc = fn(*head, lo_e, hi_e, _dev.ptr(sb.state), konst, windows, rank, world, sb.pub,
                             sb.seq + 1, batch, ws, stream)
-                if rc != 0:
-                    _lib.check(rc, name)
+                    if rc != 0:
+                        _lib.check(rc, name)
+                else:                            # per-launch CUDA-event brackets (still no wait in between)
+                    for i in range(batch):
+                        with _dev.timed(self.profile, name):
+                            rc = fn(*head, lo_e, hi_e, _dev.ptr(sb.state), konst, windows, rank, world, sb.pub,
+                                    sb.seq + 1 + i, 1, ws, stream)
+                        if rc != 0:
+                            _lib.check(rc, name)
                 sb.seq += batch
                 st = sb.wait()
-                if count is not None:            # launches that did work (the rest exited at once)
-                    count[0] = max(1, int(st.nfev) - done_before)
+                if self.profile is not None:     # launches that found the solve finished are not evaluations
+                    self.profile.relabel_last(name, batch - (int(st.nfev) - done_before), "K3b_solver_idle_launch")
                 done_before = int(st.nfev)
                 if st.done:
                     break
@@ -1230,6 +1237,14 @@ def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+def _qR2(q_R):
+    """(N, U, 2) contiguous view of a region-posterior argument.  The reference only ever reads
+    ``q_R[..., 0]`` and ``q_R[..., 1]`` (fit.py:398-405), and its own test passes an (N, U, 3) array
+    (test_fcdiff/test_fit.py:397, 403): further trailing entries are ignored, not mis-strided."""
+    q = np.asarray(q_R, dtype=np.float64)
+    return np.ascontiguousarray(q[..., :2])
+
+
 class _Keep(list):
     """Holds device temporaries alive until the call that reads them has been
     enqueued (a tensor freed earlier could be recycled by the caching allocator
@@ -1252,7 +1267,7 @@ def _eval_q_R_w(q_R, n, m):
     """
     lib = _lib.load()
     keep = _Keep()
-    q_R = _f64(q_R)
+    q_R = _qR2(q_R)
     (N, U) = q_R.shape[0:2]
     out = _dev.empty((U, 3))
     _lib.check(lib.fcd_pair_weights(keep.up(q_R), N, U, int(n), int(m), _dev.ptr(out),
@@ -1330,7 +1345,7 @@ def _eval_E_lM(q_F, q_R, lM):
     """E[log p(b~ | f, r; theta)] (fcdiff/fit.py:489-511)."""
     lib = _lib.load()
     keep = _Keep()
-    (q_F, q_R, lM) = (_f64(q_F), _f64(q_R), _f64(lM))
+    (q_F, q_R, lM) = (_f64(q_F), _qR2(q_R), _f64(lM))
     C = q_F.shape[0]
     (N, U) = q_R.shape[0:2]
     out = _scalar_out()
@@ -1355,7 +1370,7 @@ def _eval_E_lq_R(q_R, lq_R):
 def _dE(q_R, q_F, norm, mix, eta, epsilon):
     lib = _lib.load()
     keep = _Keep()
-    (q_R, q_F, norm, mix) = (_f64(q_R), _f64(q_F), _f64(norm), _f64(mix))
+    (q_R, q_F, norm, mix) = (_qR2(q_R), _f64(q_F), _f64(norm), _f64(mix))
     C = q_F.shape[0]
     (N, U) = q_R.shape[0:2]
     out = _scalar_out(2)
