@@ -259,6 +259,132 @@ def sharded_parity(fcdiff, shards, torch):
     return out
 
 
+def run_cfg4(fcdiff, _dev, shards, torch, dist, peak):
+    """BASELINE.json configs[3]: 1000-region parcellation (499,500 edges) x 2000 subjects (1000 + 1000), full
+    fit with free-energy tracking, the SAME problem at every GPU count (strong scaling: edges and the
+    sweep's patients are sharded over the ranks).  One warm-up fit, one timed fit of 10 iterations from
+    the uniform start."""
+    (N, H, U) = (1000, 1000, 1000)
+    C = N * (N - 1) // 2
+    world = 1 if shards is None else shards.world
+    (c0, Cl) = (0, C) if shards is None else shards.span(C)
+    need_gb = 8e-9 * Cl * (H + U) + 8e-9 * Cl * U * 7.2 + 8e-9 * C * (U / world) * 6.0
+    free_gb = torch.cuda.mem_get_info()[0] / 1e9 + torch.cuda.memory_reserved() / 1e9 - torch.cuda.memory_allocated() / 1e9
+    if need_gb > 0.9 * free_gb:
+        return {"skipped": "needs ~%.0f GB per GPU, %.0f GB free" % (need_gb, free_gb)}
+    torch.cuda.empty_cache()
+    model = fcdiff.UnsharedRegionModel()
+    (_, _, _, _, b_dev, bt_dev) = model.sample_device(N, H, U, c0=c0, C=Cl)
+
+    def one(profile):
+        f = fcdiff.fit.UnsharedRegionFit()
+        f.model = fcdiff.UnsharedRegionModel()
+        f.model.eta += 0.1
+        (f.b, f.bt) = (b_dev, bt_dev)
+        if shards is not None:
+            f.shards = shards
+            f.n_edges = C
+        f.max_iters = 10
+        f.rel_tol = -1.0
+        f.profile = profile
+        if shards is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        (e0, e1) = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        e0.record()
+        f.run()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if shards is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return f, float(t.item())
+
+    (f, _) = one(None)
+    del f
+    timers = _dev.KernelTimers()
+    (f, ms) = one(timers)
+    ks = timers.summary()
+    Ul = U if shards is None else shards.span(U)[1]
+    kernels = {}
+    for (name, (cnt, total_ms, mean_ms)) in sorted(ks.items()):
+        ab = algorithmic_bytes(name, Cl, N, H, Ul if name in ("K2b_region_weights", "K2b_sweep") else U)
+        ent = {"launches": cnt, "mean_ms": mean_ms, "share_of_step": total_ms / ms}
+        if ab:
+            ent["frac_of_hbm_peak"] = ab / (mean_ms * 1e-3) / 1e9 / peak
+        kernels[name] = ent
+    dom = max((k for k in kernels if "frac_of_hbm_peak" in kernels[k]), key=lambda k: kernels[k]["share_of_step"])
+    out = {"workload": "1000 regions (499,500 edges) x (1000 controls + 1000 patients), BASELINE.json configs[3]",
+           "scaling": "strong", "n_gpus": world, "iterations": len(f.energy) - 1, "ms_per_step": ms / (len(f.energy) - 1),
+           "value": C * (H + U) * (len(f.energy) - 1) / (ms * 1e-3), "unit": UNIT,
+           "objective_evals_per_step": float(np.mean(f.n_objective_evals)),
+           "energy_trace": [float(e) for e in f.energy], "energy_finite": bool(np.all(np.isfinite(f.energy))),
+           "dominant_kernel": dom, "dominant_frac_of_hbm_peak": kernels[dom]["frac_of_hbm_peak"],
+           "roofline_traffic": None,       # no ncu --set full capture at this configuration
+           "kernels": {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for (kk, vv) in v.items()}
+                       for (k, v) in kernels.items()},
+           "hbm_gb_allocated": torch.cuda.max_memory_allocated() / 1e9}
+    del f, b_dev, bt_dev
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_cfg5(fcdiff, shards, torch, dist, n_replicas):
+    """BASELINE.json configs[4]: Schaefer-400 x 1000 subjects, `n_replicas`-way group-label permutation
+    sweep.  The responsibility planes are built once for all 1000 subjects; a replica selects its
+    columns (fcdiff_b200/sweep.py: SharedPlanes); replicas are sharded over the ranks, nothing is
+    exchanged.  Every replica is a plain ``fit.run()`` with the reference's defaults."""
+    from fcdiff_b200 import sweep
+    (N, H, U) = (400, 500, 500)
+    C = N * (N - 1) // 2
+    (rank, world) = (0, 1) if shards is None else (shards.rank, shards.world)
+    model = fcdiff.UnsharedRegionModel()
+    (_, _, _, _, b, bt) = model.sample_device(N, H, U)            # the same matrix on every rank (same key)
+    corr = torch.cat([b, bt], dim=1)
+    labels = np.r_[np.zeros(H, bool), np.ones(U, bool)]
+    start = fcdiff.UnsharedRegionModel()
+    start.eta += 0.1
+
+    def sync():
+        if shards is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sweep.permutation_sweep(corr, labels, 2 * world - 1, model=start, rank=rank, world=world, gather=False)   # warm-up
+    sync()
+    t0 = time.perf_counter()
+    res = sweep.permutation_sweep(corr, labels, n_replicas - 1, model=start, rank=rank, world=world, gather=False)
+    sync()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    iters = torch.tensor([float(sum(r["iterations"] for r in res.values())), float(len(res))], dtype=torch.float64,
+                         device="cuda")
+    if shards is not None:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(iters)
+    out = {"workload": "Schaefer-400 (79,800 edges) x 1000 subjects, %d relabelings (replica 0 = observed labels), "
+                       "BASELINE.json configs[4]" % n_replicas,
+           "replicas": int(iters[1].item()), "n_gpus": world, "scaling": "strong (replicas sharded over ranks)",
+           "seconds": float(dt.item()), "replicas_per_second": float(iters[1].item() / dt.item()),
+           "em_iterations": int(iters[0].item()),
+           "value": float(C * (H + U) * iters[0].item() / dt.item()), "unit": UNIT,
+           "fit": "fit.run(), max_iters 10, rel_tol 1e-5, the reference's convergence rule; planes built once, "
+                  "per-replica column selection"}
+    if rank == 0:                                  # replica 0 is the plain fit of (b, bt)
+        f = fcdiff.fit.UnsharedRegionFit()
+        f.model = fcdiff.UnsharedRegionModel()
+        f.model.eta += 0.1
+        (f.b, f.bt) = (b, bt)
+        f.run()
+        e0 = np.asarray(res[0]["energy"])
+        out["replica0_vs_plain_fit_max_rel"] = float(np.max(np.abs(e0 - np.asarray(f.energy)) / np.abs(np.asarray(f.energy)))) \
+            if len(e0) == len(f.energy) else None
+        out["energy_final_observed_vs_permuted_mean"] = [float(e0[-1]), float(np.mean([r["energy"][-1] for (i, r) in res.items() if i > 0]))]
+        del f
+    del corr, b, bt, res
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -451,16 +577,34 @@ def run_gpu_arm(args):
            "what": "fit.run(max_iters=1) from pinned host arrays: H2D of b, bt + healthy stats + patient-major "
                    "copy + initial energy + one EM iteration + energy; D2H of energy, lq_F, lq_R"}
 
-    if rank != 0:
-        return 0
-
-    # ---- roofline of the dominant kernel (by time inside the timed region)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(peaks_path):
         peak = float(json.load(open(peaks_path))["hbm_gbs"])
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+    # ---- configs[3] at this GPU count (strong scaling), all ranks take part
+    cfg4 = None
+    if not args.no_cfg4:
+        b_host = bt_host = b_dev = bt_dev = None         # release the main workload's inputs
+        try:
+            cfg4 = run_cfg4(fcdiff, _dev, shards, torch, dist, peak)
+        except Exception as exc:                   # an extra block must never cost the headline line
+            cfg4 = {"error": "%s: %s" % (type(exc).__name__, exc)}
+
+    # ---- configs[4]: the permutation sweep, replicas sharded over the ranks
+    cfg5 = None
+    if args.replicas > 0:
+        try:
+            cfg5 = run_cfg5(fcdiff, shards, torch, dist, args.replicas)
+        except Exception as exc:
+            cfg5 = {"error": "%s: %s" % (type(exc).__name__, exc)}
+
+    if rank != 0:
+        return 0
+
+    # ---- roofline of the dominant kernel (by time inside the timed region)
     kernels = {}
     for (name, (cnt, total_ms, mean_ms)) in sorted(ksum.items()):
         ab = algorithmic_bytes(name, Cl, N, H, U if name != "K2b_region_weights" and name != "K2b_sweep"
@@ -516,7 +660,7 @@ def run_gpu_arm(args):
         "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roofline, "roofline_estep": roofline_estep,
         "cpu_baseline": cpu, "steady_state": steady, "time_to_converge": converge, "kernels": kernels,
         "kernel_share_of_step": float(sum(k["total_ms"] for k in kernels.values()) / ms),
-        "parity": parity,
+        "parity": parity, "cfg4": cfg4, "cfg5": cfg5,
         "energy_trace": [float(e) for e in energies],
     }
     _emit(json.dumps(line))
@@ -533,6 +677,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cfg4", action="store_true", help="skip the configs[3] (1000 regions x 2000 subjects) block")
+    ap.add_argument("--replicas", type=int, default=1000,
+                    help="relabelings of the configs[4] permutation sweep block (0 = skip)")
     ap.add_argument("--regions", type=int, default=0, help="override the atlas size (manual experiments)")
     ap.add_argument("--subjects", type=int, default=0, help="override controls = patients (manual experiments)")
     args = ap.parse_args()

@@ -217,6 +217,7 @@ class UnsharedRegionFit(object):
         self._res = {}                # reusable device / pinned-host result vectors
         self._ctx = None              # cached argument list of the K3b evaluations
         self._sctx = None             # the same for the device-resident solver
+        self._shared = None           # replica mode: (sweep.SharedPlanes, control columns, patient columns)
         self._last_nfev = 4           # evaluations of the last device solve (sizes the first batch)
         self._keep_host = None        # host arrays an asynchronous upload is still reading
 
@@ -277,6 +278,9 @@ class UnsharedRegionFit(object):
         full problem (the reference's contract), or CUDA tensors: the full
         arrays on one device, or -- when ``shards`` is set -- this rank's edge
         rows, with ``n_edges`` giving the global edge count."""
+        if self._shared is not None:
+            (sp, con, pat) = self._shared
+            return int(sp.C), int(con.numel()), int(pat.numel())
         (C, H) = tuple(self.b.shape)
         U = int(self.bt.shape[1])
         if self._device_shard_inputs():
@@ -291,6 +295,8 @@ class UnsharedRegionFit(object):
         sufficient statistics.  The reference re-reads ``self.b`` / ``self.bt``
         at every ``_update_lps`` (fit.py:114-115); re-assign the attribute to
         have a changed array picked up."""
+        if self._shared is not None:
+            return self._ensure_inputs_shared()
         key = (self._input_stamp(self.b), self._input_stamp(self.bt),
                None if self.shards is None else self.shards.key())
         if (self._in is not None and self._in['key'] == key and self._in['src'][0] is self.b
@@ -357,6 +363,40 @@ class UnsharedRegionFit(object):
         self._const = None
         return self._in
 
+    def set_shared_inputs(self, shared, controls, patients):
+        """Replica mode (new; BASELINE.json configs[4]): the fit's inputs are COLUMNS of a correlation
+        matrix whose responsibility planes already exist for all subjects (``sweep.SharedPlanes``) --
+        ``controls`` / ``patients``: int column indices.  Equivalent to assigning
+        ``b = corr[:, controls]``, ``bt = corr[:, patients]``; the planes are gathered instead of being
+        recomputed (no exponential is taken again).  Needs fixed mu, sigma (``update_mu_sigma`` off)
+        and no edge shards (replicas are sharded over ranks instead)."""
+        dev = _dev.device()
+        to_idx = lambda a: torch.as_tensor(np.asarray(a.cpu() if torch.is_tensor(a) else a), dtype=torch.int32).to(dev)
+        self._shared = (shared, to_idx(controls), to_idx(patients))
+        self.b = self.bt = None
+        self.invalidate_inputs()
+
+    def _ensure_inputs_shared(self):
+        (sp, con, pat) = self._shared
+        key = ("shared", id(sp), id(con), id(pat))
+        if self._in is not None and self._in['key'] == key:
+            return self._in
+        if self.shards is not None:
+            raise ValueError("shared-plane inputs cannot be combined with edge shards")
+        lib = _lib.load()
+        (C, H, U) = (int(sp.C), int(con.numel()), int(pat.numel()))
+        S1 = _dev.empty((C,))
+        S2 = _dev.empty((C,))
+        with _dev.timed(self.profile, "K0_healthy_stats"):
+            _lib.check(lib.fcd_healthy_stats_cols(_dev.ptr(sp.X), C, sp.pitchS, _dev.ptr(con), H, _dev.ptr(S1),
+                                                  _dev.ptr(S2), _dev.stream()), "fcd_healthy_stats_cols")
+        self._in = dict(key=key, src=(None, None), C=C, H=H, U=U, c0=0, Cl=C, u0=0, Ul=U, pitchU=_dev.even(U),
+                        bt=None, S1=S1, S2=S2, nm=sp.nm, cache_key=None, P=None, L=None, PT=None, WT=None,
+                        ev_S=None, b_dev=None)
+        self._evals = []
+        self._const = None
+        return self._in
+
     @staticmethod
     def _input_stamp(a):
         """What identifies the CONTENT of an input as far as it can be known without reading it:
@@ -397,14 +437,26 @@ class UnsharedRegionFit(object):
             return inp
         lib = _lib.load()
         (Cl, U, pitchU) = (inp['Cl'], inp['U'], inp['pitchU'])
-        if inp['P'] is None:
-            inp['P'] = _dev.empty((3, max(Cl, 1), pitchU))
-            inp['L'] = _dev.empty((max(Cl, 1), pitchU))
-        th = self._theta()
-        with _dev.timed(self.profile, "K0_resp_cache"):
-            _lib.check(lib.fcd_resp_cache(_dev.ptr(inp['bt']), Cl, U, pitchU, ctypes.byref(th),
-                                          _dev.ptr(inp['P']), max(Cl, 1) * pitchU, _dev.ptr(inp['L']),
-                                          _dev.stream()), "fcd_resp_cache")
+        if self._shared is not None:
+            (sp, con, pat) = self._shared
+            if sp.cache_key != ckey:
+                raise ValueError("shared planes were built for other (mu, sigma) than the model's")
+            if inp['P'] is None:
+                inp['PL'] = _dev.empty((4, Cl, pitchU))              # p_0, p_1, p_2, L of the patient columns
+                (inp['P'], inp['L']) = (inp['PL'][:3], inp['PL'][3])
+            with _dev.timed(self.profile, "K0_gather_planes"):
+                _lib.check(lib.fcd_gather_columns(_dev.ptr(sp.PL), sp.C * sp.pitchS, sp.pitchS, 4, Cl, _dev.ptr(pat), U,
+                                                  _dev.ptr(inp['PL']), Cl * pitchU, pitchU, _dev.stream()),
+                           "fcd_gather_columns")
+        else:
+            if inp['P'] is None:
+                inp['P'] = _dev.empty((3, max(Cl, 1), pitchU))
+                inp['L'] = _dev.empty((max(Cl, 1), pitchU))
+            th = self._theta()
+            with _dev.timed(self.profile, "K0_resp_cache"):
+                _lib.check(lib.fcd_resp_cache(_dev.ptr(inp['bt']), Cl, U, pitchU, ctypes.byref(th),
+                                              _dev.ptr(inp['P']), max(Cl, 1) * pitchU, _dev.ptr(inp['L']),
+                                              _dev.stream()), "fcd_resp_cache")
         inp['Lsum'] = None                          # total of the L plane, formed on first use (code pass)
         inp['PsE'] = None                           # dominant-state plane of the code pass: rebuilt with the planes
         inp['code_verR'] = None
@@ -421,6 +473,15 @@ class UnsharedRegionFit(object):
             return inp
         lib = _lib.load()
         (C, U, u0, Ul) = (inp['C'], inp['U'], inp['u0'], inp['Ul'])
+        if self._shared is not None:
+            (sp, con, pat) = self._shared
+            PT = _dev.empty((3, U, sp.pitchC))
+            with _dev.timed(self.profile, "K0_gather_patient_major"):
+                _lib.check(lib.fcd_gather_rows(_dev.ptr(sp.PT), sp.S * sp.pitchC, 3, _dev.ptr(pat), U, sp.pitchC,
+                                               _dev.ptr(PT), U * sp.pitchC, _dev.stream()), "fcd_gather_rows")
+            inp['PT'] = PT
+            inp['PsT'] = inp['kcache'] = None
+            return inp
         if self.shards is None:
             (src, pitchU, uu0, Us) = (inp['P'], inp['pitchU'], u0, U)
         else:
@@ -532,7 +593,10 @@ class UnsharedRegionFit(object):
         if self._mat is not None:
             return self._mat
         lib = _lib.load()
-        if torch.is_tensor(self.b):
+        if self._shared is not None:                 # the columns the caches are of (data movement only)
+            (sp, con, pat) = self._shared
+            (b_dev, bt_dev) = (sp.X[:, con.long()].contiguous(), sp.X[:, pat.long()].contiguous())
+        elif torch.is_tensor(self.b):
             (b_dev, bt_dev) = (self.b.to(_dev.device(), torch.float64).contiguous(),
                                self.bt.to(_dev.device(), torch.float64).contiguous())
         else:
@@ -887,6 +951,8 @@ class UnsharedRegionFit(object):
         current (q_F, q_R, theta): controls [n_j, sum x, sum x^2], then patients
         (K3c, ``fcd_state_moments``)."""
         lib = _lib.load()
+        if self._shared is not None:
+            raise ValueError("update_mu_sigma is not available with shared-plane inputs (the planes are fixed)")
         if self._lps_state != 'derived':
             self._update_lps()
         inp = self._ensure_cache()

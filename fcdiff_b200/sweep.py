@@ -19,6 +19,49 @@ from .fit import UnsharedRegionFit
 from .model import UnsharedRegionModel
 
 
+class SharedPlanes(object):
+    """Responsibility planes of ALL subjects of one (C, S) correlation matrix for fixed (mu, sigma),
+    built once: every relabelling of the subjects selects its controls' sufficient statistics and its
+    patients' planes from them (``UnsharedRegionFit.set_shared_inputs``, csrc/fcd_replica.cu) instead of
+    taking the exponentials again.
+
+    X  [C][pitchS]       the correlations (zero padded to an even pitch)
+    PL [4][C][pitchS]    p_0, p_1, p_2, L of every (edge, subject)      (fcd_resp_cache)
+    PT [3][S][pitchC]    p_k patient-major                              (fcd_transpose_patients)
+    nm [C]               edge table
+    """
+
+    def __init__(self, corr, model):
+        import ctypes
+        from . import _lib
+        from .util import C_to_N
+        lib = _lib.load()
+        dev = _dev.device()
+        x = corr if torch.is_tensor(corr) else torch.from_numpy(np.ascontiguousarray(corr, dtype=np.float64))
+        x = x.to(dev, torch.float64)
+        (C, S) = (int(x.shape[0]), int(x.shape[1]))
+        if (C_to_N(C) % 1) != 0:
+            raise ValueError("Number of connections (%u) must be a triangular number." % C)
+        (self.C, self.S, self.pitchS, self.pitchC) = (C, S, _dev.even(S), _dev.even(C))
+        if self.pitchS == S:
+            self.X = x.contiguous()
+        else:
+            self.X = _dev.zeros((C, self.pitchS))
+            self.X[:, :S].copy_(x)
+        th = _lib.make_theta(float(np.asarray(model.pi).reshape(-1)[-1]), model.eta, model.epsilon,
+                             np.asarray(model.gamma).reshape(-1), model.mu, model.sigma)
+        self.cache_key = (tuple(float(v) for v in model.mu), tuple(float(v) for v in model.sigma))
+        self.PL = _dev.empty((4, C, self.pitchS))
+        _lib.check(lib.fcd_resp_cache(_dev.ptr(self.X), C, S, self.pitchS, ctypes.byref(th), _dev.ptr(self.PL),
+                                      C * self.pitchS, _dev.ptr(self.PL[3]), _dev.stream()), "fcd_resp_cache")
+        self.PT = _dev.zeros((3, S, self.pitchC))
+        for k in range(3):
+            _lib.check(lib.fcd_transpose_patients(_dev.ptr(self.PL[k]), C, S, self.pitchS, 0, S, _dev.ptr(self.PT[k]),
+                                                  self.pitchC, _dev.stream()), "fcd_transpose_patients")
+        self.nm = _dev.empty((max(C, 1),), torch.int32)
+        _lib.check(lib.fcd_edge_table(0, C, _dev.ptr(self.nm), _dev.stream()), "fcd_edge_table")
+
+
 def replica_indices(n_replicas, rank=0, world=1):
     """Replicas handled by ``rank``: a strided split, so that every rank gets
     the same number (+-1) whatever ``n_replicas``."""
@@ -69,7 +112,7 @@ def _configure(fit, options):
 
 
 def permutation_sweep(corr, labels, n_permutations, model=None, seed=0, fit_options=None, rank=0, world=1,
-                      group=None, gather=True):
+                      group=None, gather=True, shared_planes=True):
     """
     Fits the model once per group labelling: the observed one and
     ``n_permutations`` random re-labellings of the subjects.
@@ -90,6 +133,12 @@ def permutation_sweep(corr, labels, n_permutations, model=None, seed=0, fit_opti
     rank, world, group
         Replica sharding (see the module docstring); ``gather`` merges the
         results of all ranks.
+    shared_planes : bool
+        Build the responsibility planes once for all S subjects and let every
+        replica select its columns from them (:class:`SharedPlanes`; default).
+        With ``update_mu_sigma`` in ``fit_options`` (the planes then change during a
+        fit) or ``shared_planes=False`` every replica uploads its own columns and
+        rebuilds its planes -- same results.
 
     Returns
     -------
@@ -101,6 +150,9 @@ def permutation_sweep(corr, labels, n_permutations, model=None, seed=0, fit_opti
     corr_dev = corr if torch.is_tensor(corr) else torch.from_numpy(np.ascontiguousarray(corr, dtype=np.float64))
     corr_dev = corr_dev.to(dev, torch.float64)
     model = UnsharedRegionModel() if model is None else model
+    shared = None
+    if shared_planes and not (fit_options or {}).get("update_mu_sigma"):
+        shared = SharedPlanes(corr_dev, model)
     results = {}
     for i in replica_indices(n_permutations + 1, rank, world):
         pat = torch.from_numpy(np.flatnonzero(lab[i])).to(dev)
@@ -108,8 +160,11 @@ def permutation_sweep(corr, labels, n_permutations, model=None, seed=0, fit_opti
         fit = UnsharedRegionFit()
         fit.model = copy.deepcopy(model)
         _configure(fit, fit_options)
-        fit.b = corr_dev.index_select(1, con)          # column gather: data movement only
-        fit.bt = corr_dev.index_select(1, pat)
+        if shared is not None:
+            fit.set_shared_inputs(shared, con, pat)
+        else:
+            fit.b = corr_dev.index_select(1, con)          # column gather: data movement only
+            fit.bt = corr_dev.index_select(1, pat)
         fit.run()
         results[i] = _summary(fit)
         del fit

@@ -178,6 +178,22 @@ FCD_API int fcd_estep_qF_coded(const double* S1, const double* S2, int32_t H,
                        const uint64_t* keysH, const int64_t* rowoff, const double* Hh,
                        const fcd_theta* theta_host, double* lqF, double* qF, void* stream);
 
+/* Replica sweeps (BASELINE.json configs[4]; no reference counterpart -- the reference stops at one
+ * fit, fcdiff/fit.py:56-82): the responsibility planes of ALL S subjects are built once
+ * (fcd_resp_cache on every column of the (C, S) correlation matrix, fcd_transpose_patients), and a
+ * relabelling selects from them (csrc/fcd_replica.cu):
+ *   fcd_healthy_stats_cols: S1 / S2 of fcd_healthy_stats over the columns cols[0..H) of X [C][pitchS];
+ *   fcd_gather_columns: dst[p][c][j] = src[p][c][cols[j]], j < U (columns U..pitchD-1 zero), p < nplanes;
+ *   fcd_gather_rows: dst[p][j][:] = src[p][rows[j]][:] (rows of `pitch` doubles, 16-byte aligned).
+ * cols / rows: int32 device arrays. */
+FCD_API int fcd_healthy_stats_cols(const double* X, int64_t C, int64_t pitchS, const int32_t* cols, int32_t H,
+                           double* S1, double* S2, void* stream);
+FCD_API int fcd_gather_columns(const double* src, int64_t planeStrideS, int64_t pitchS, int32_t nplanes, int64_t C,
+                       const int32_t* cols, int32_t U, double* dst, int64_t planeStrideD, int64_t pitchD,
+                       void* stream);
+FCD_API int fcd_gather_rows(const double* src, int64_t planeStrideS, int32_t nplanes, const int32_t* rows, int32_t U,
+                    int64_t pitch, double* dst, int64_t planeStrideD, void* stream);
+
 /* Patient-major copy of an edge-major plane: dst[u - u0][c] = src[c][u]
  * for u in [u0, u0+Ul), c in [0, C).  Built once per fit. */
 FCD_API int fcd_transpose_patients(const double* bt, int64_t C, int32_t U, int64_t pitchU,

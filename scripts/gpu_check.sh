@@ -22,4 +22,6 @@ print("roofline", d["roofline"]["kernel"], round(d["roofline"]["frac"],3), "este
 print("converge", json.dumps(d["time_to_converge"])[:900])
 print("cpu", d["cpu_baseline"] and d["cpu_baseline"]["value"], d["clocks"])
 print("energies", d["energy_trace"])
+c=d.get("cfg4") or {}; print("cfg4", {k:v for k,v in c.items() if k not in ("kernels","energy_trace")})
+print("cfg5", d.get("cfg5"))
 PY

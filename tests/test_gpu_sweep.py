@@ -42,6 +42,44 @@ def test_permutation_sweep_matches_individual_fits_and_the_oracle():
     assert 0.0 < sweep.permutation_p_value(res) <= 1.0
 
 
+@pytest.mark.parametrize("N,H,U", [(12, 14, 10), (9, 13, 10), (15, 8, 9)])
+def test_shared_planes_equal_per_replica_planes(N, H, U):
+    """configs[4]: planes built once for all subjects + per-replica column selection give the fit of
+    the plain path (own upload, own planes) -- replica 0 is the ordinary fit of (b, bt)."""
+    (b, bt, corr, labels) = _problem(N, H, U, seed=N)
+    opts = dict(max_iters=3, rel_tol=-1.0)
+    shared = sweep.permutation_sweep(corr, labels, 3, seed=2, fit_options=opts, shared_planes=True)
+    plain = sweep.permutation_sweep(corr, labels, 3, seed=2, fit_options=opts, shared_planes=False)
+    fit = fcdiff.fit.UnsharedRegionFit()
+    fit.model = fcdiff.UnsharedRegionModel()
+    (fit.b, fit.bt) = (b, bt)
+    (fit.max_iters, fit.rel_tol) = (3, -1.0)
+    fit.run()
+    nptest.assert_allclose(shared[0]["energy"], fit.energy, rtol=1e-12)
+    for i in plain:
+        nptest.assert_allclose(shared[i]["energy"], plain[i]["energy"], rtol=1e-12)
+        for k in ("pi", "eta", "epsilon", "expected_anomalous_regions"):
+            nptest.assert_allclose(shared[i][k], plain[i][k], rtol=1e-9)
+        nptest.assert_allclose(shared[i]["gamma"], plain[i]["gamma"], rtol=1e-9)
+    # the private caches of a shared-input fit are the reference's arrays of its columns
+    sp = sweep.SharedPlanes(corr, fcdiff.UnsharedRegionModel())
+    f2 = fcdiff.fit.UnsharedRegionFit()
+    f2.model = fcdiff.UnsharedRegionModel()
+    f2.set_shared_inputs(sp, np.flatnonzero(~labels), np.flatnonzero(labels))
+    f2._init_lps(N, H, U)
+    f2._update_lps()
+    f3 = fcdiff.fit.UnsharedRegionFit()
+    f3.model = fcdiff.UnsharedRegionModel()
+    (f3.b, f3.bt) = (b, bt)
+    f3._init_lps(N, H, U)
+    f3._update_lps()
+    nptest.assert_array_equal(f2._lM, f3._lM)
+    nptest.assert_array_equal(f2._lp_B_g_F, f3._lp_B_g_F)
+    with pytest.raises(ValueError):
+        f2.update_mu_sigma = True
+        f2._update_mu_sigma()
+
+
 def test_restart_sweep_returns_the_lowest_energy():
     (b, bt, _, _) = _problem()
     (res, best) = sweep.restart_sweep(b, bt, 3, seed=1, fit_options=dict(max_iters=4))
