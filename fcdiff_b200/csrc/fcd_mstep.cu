@@ -324,12 +324,14 @@ __global__ void __launch_bounds__(kRedThreads)
 energy_small_kernel(const double* __restrict__ S1, const double* __restrict__ S2,
                     const double* __restrict__ lqF, const double* __restrict__ qF, int64_t C,
                     const double* __restrict__ lqR, const double* __restrict__ qR, int64_t NU,
-                    const __grid_constant__ ThetaDev th, double elm_value,
+                    const __grid_constant__ ThetaDev th, double elm_value, const SolverState* __restrict__ solved,
                     double* __restrict__ out6, double* __restrict__ ws) {
     double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t nth = (int64_t)gridDim.x * blockDim.x;
-    if (tid == 0) v[3] = elm_value;
+    // E_lM: given by the host, or taken from the state of the device-resident (eta, epsilon) solve that
+    // finished just before this launch on the same stream (f = -E_lM at the solution; NaN if it has not)
+    if (tid == 0) v[3] = solved != nullptr ? (solved->done ? -solved->f : __longlong_as_double(0x7ff8000000000000ll)) : elm_value;
     for (int64_t c = tid; c < C; c += nth) {
         const double s1 = S1[c], s2 = S2[c];
 #pragma unroll
@@ -494,7 +496,7 @@ int fcd_elm_const(const double* L, int64_t C, int32_t U, int64_t pitchU,
 int fcd_energy_terms(const double* S1, const double* S2, int32_t H,
                      const double* lqF, const double* qF, int64_t C,
                      const double* lqR, const double* qR, int32_t N, int32_t U,
-                     const fcd_theta* theta_host, double elm,
+                     const fcd_theta* theta_host, double elm, const void* solver_state,
                      double* out6, double* ws, void* stream) {
     FCD_REQUIRE(theta_host != nullptr && ws != nullptr && out6 != nullptr, "fcd_energy_terms: NULL argument");
     FCD_REQUIRE(C >= 0 && U >= 1 && N >= 2 && H >= 1, "fcd_energy_terms: bad shape");
@@ -502,7 +504,7 @@ int fcd_energy_terms(const double* S1, const double* S2, int32_t H,
     const int64_t NU = (int64_t)N * U;
     const int64_t work = C > NU ? C : NU;
     energy_small_kernel<<<red_grid(work, kRedThreads), kRedThreads, 0, (cudaStream_t)stream>>>(
-        S1, S2, lqF, qF, C, lqR, qR, NU, th, elm, out6, ws);
+        S1, S2, lqF, qF, C, lqR, qR, NU, th, elm, static_cast<const SolverState*>(solver_state), out6, ws);
     return check_launch("fcd_energy_terms");
 }
 

@@ -110,13 +110,22 @@ class PeerWindow(object):
     def allreduce(self, vec_dev, n, stream):
         """Sums ``vec_dev[:n]`` (device, float64) over the ranks in place and returns
         the sums as a fresh host array."""
+        return self.allreduce_end(self.allreduce_begin(vec_dev, n, stream))
+
+    def allreduce_begin(self, vec_dev, n, stream):
+        """Enqueues the exchange (one kernel) and returns a ticket for ``allreduce_end``.  At most
+        one exchange may be outstanding per window (there is one host result block)."""
         self.bind_stream(stream)
         self.seq += 1
         rc = self.lib.fcd_allreduce_small(self._ct.c_void_p(vec_dev.data_ptr()), n, self.windows, self.rank,
                                           self.world, self.seq, self._result, stream)
         if rc != 0:
             self._check(rc, "fcd_allreduce_small")
-        rc = self.lib.fcd_wait_result(self._result, n, self.seq, self._out_p, self.TIMEOUT_MS)
+        return (self.seq, n)
+
+    def allreduce_end(self, ticket):
+        (seq, n) = ticket
+        rc = self.lib.fcd_wait_result(self._result, n, seq, self._out_p, self.TIMEOUT_MS)
         if rc != 0:
             self._check(rc, "fcd_wait_result")
         return self._out[:n].copy()
@@ -171,6 +180,20 @@ class EdgeShards(object):
             return pw.allreduce(res.dev, n, _dev.stream() if stream is None else stream)
         dist.all_reduce(res.dev, op=dist.ReduceOp.SUM, group=self.group)
         return res.read(stream)
+
+    def reduce_begin(self, res, n=None, stream=None):
+        """``reduce_read`` in two halves (peer window only): enqueue now, collect later."""
+        n = res.dev.numel() if n is None else n
+        pw = self.peer_window()
+        if pw is None or n > pw.max_vals:
+            return None
+        from . import _dev
+        return (pw, pw.allreduce_begin(res.dev, n, _dev.stream() if stream is None else stream))
+
+    @staticmethod
+    def reduce_end(handle):
+        (pw, ticket) = handle
+        return pw.allreduce_end(ticket)
 
     def key(self):
         return (self.rank, self.world)

@@ -198,6 +198,7 @@ class UnsharedRegionFit(object):
         self.convergence_rule = "reference"
         self.theta_solver = "newton"  # (eta, epsilon): device-resident Newton | host-driven SciPy L-BFGS-B
         self.solver_tol = 1e-7        # newton: a step below this is taken without another evaluation
+        self.energy_behind_solver = True   # newton: enqueue K4 behind the first batch of evaluations (one wait for both)
         self.solver_status = []       # newton: per solve (done code, evaluations)
         self.n_objective_evals = []
         self.profile = None           # _dev.KernelTimers for per-kernel CUDA-event timing
@@ -218,6 +219,9 @@ class UnsharedRegionFit(object):
         self._ctx = None              # cached argument list of the K3b evaluations
         self._sctx = None             # the same for the device-resident solver
         self._shared = None           # replica mode: (sweep.SharedPlanes, control columns, patient columns)
+        self._pending_energy = None   # (key, six terms) of the K4 pass enqueued behind the last device solve
+        self._mstep_vals = None       # K3a sums that arrived together with the code pass' record counts
+        self._tot_slot = None
         self._last_nfev = 4           # evaluations of the last device solve (sizes the first batch)
         self._keep_host = None        # host arrays an asynchronous upload is still reading
 
@@ -541,15 +545,22 @@ class UnsharedRegionFit(object):
             inp['bk_counts'] = _dev.empty((Cl, 2), torch.int32)      # {records, half records} per row
             inp['bk_rowoff'] = _dev.empty((Cl, 2), torch.int64)
             inp['bk_offs'] = _dev.empty((4 * int(lib.fcd_bucket_blocks(Cl)),), torch.int64)
-        tot = self._result(2, tag="records")
+        slot = self._tot_slot                       # (vector, offset): counts go beside the K3a sums
+        self._tot_slot = None
+        tot = self._result(2, tag="records") if slot is None else None
+        tot_dev = tot.dev if slot is None else slot[0].dev[slot[1]:]
         planeStride = max(Cl, 1) * pitchU
         with _dev.timed(self.profile, "K3b_code_plane"):
             _lib.check(lib.fcd_code_plane(
                 _dev.ptr(inp['P']), planeStride, Cl, U, pitchU, _dev.ptr(fstate[c0:]), _dev.ptr(rstate),
                 rstate.shape[1], _dev.ptr(inp['nm']), _dev.ptr(inp['PsE']), _dev.ptr(inp['kcE']),
                 _dev.ptr(inp['code']), pitchQ, _dev.ptr(inp['bk_counts']), _dev.ptr(inp['bk_offs']),
-                _dev.ptr(tot.dev), stream), "fcd_code_plane")
-        (nd, nh) = (int(v) for v in tot.read(stream))
+                _dev.ptr(tot_dev), stream), "fcd_code_plane")
+        if slot is None:
+            (nd, nh) = (int(v) for v in tot.read(stream))
+        else:
+            self._mstep_vals = slot[0].read(stream)
+            (nd, nh) = (int(v) for v in self._mstep_vals[slot[1]:slot[1] + 2])
         use_tiered = self.elm_path == "auto" and nd * 4 + nh * 2 > Cl * U
         if agree and self.shards is not None:  # the ranks must take the same form: its collectives differ
             use_tiered = self.shards.any_rank(use_tiered)
@@ -729,33 +740,60 @@ class UnsharedRegionFit(object):
                 return ev
         return None
 
-    def _energy_terms(self):
-        """The six terms of fit.py:149-154 from the fused K4 kernels."""
+    def _energy_key(self):
+        """What the six energy terms depend on besides the inputs: theta and the two posteriors."""
+        m = self.model
+        (mu, sigma, eta, epsilon) = self._theta_lps
+        return (float(eta), float(epsilon), tuple(float(v) for v in mu), tuple(float(v) for v in sigma),
+                tuple(float(v) for v in np.asarray(m.pi, dtype=np.float64).reshape(-1)),
+                tuple(float(v) for v in np.asarray(m.gamma, dtype=np.float64).reshape(-1)),
+                self._mF.version, self._mR.version)
+
+    def _energy_launch(self, elm=0.0, solver_state=None):
+        """Enqueues the K4 kernel and the exchange / publication of its six sums; returns a handle
+        for ``_energy_collect``.  ``solver_state``: take E_lM from the device-resident solve that was
+        enqueued before (the host does not know it yet)."""
         lib = _lib.load()
         inp = self._ensure_cache()
         (N, H, U) = self._dims
         (c0, Cl) = (inp['c0'], inp['Cl'])
-        ev = self._find_eval()
-        if ev is None:
-            (_, _, eta, epsilon) = self._theta_lps
-            self._objective(np.array([eta, epsilon]), want_grad=False, name="K4_elm")
-            ev = self._evals[-1]
         (lqF, qF) = self._mF.get_dev()
         (lqR, qR) = self._mR.get_dev()
         th = self._theta()
         res = self._result(6)
-        out = res.dev
         self._wait_healthy(inp)
         # the global E_lM is known: rank 0 contributes it, the others zero
         first = self.shards is None or self.shards.rank == 0
         with _dev.timed(self.profile, "K4_energy_small"):
             _lib.check(lib.fcd_energy_terms(
                 _dev.ptr(inp['S1']), _dev.ptr(inp['S2']), H, _dev.ptr(lqF[c0 * 3:]), _dev.ptr(qF[c0 * 3:]), Cl,
-                _dev.ptr(lqR), _dev.ptr(qR), N, U, ctypes.byref(th), ev['elm'] if first else 0.0,
-                _dev.ptr(out), _dev.ptr(_dev.workspace()), _dev.stream()), "fcd_energy_terms")
+                _dev.ptr(lqR), _dev.ptr(qR), N, U, ctypes.byref(th), float(elm) if first else 0.0,
+                solver_state if first else None,
+                _dev.ptr(res.dev), _dev.ptr(_dev.workspace()), _dev.stream()), "fcd_energy_terms")
         if self.shards is not None:
-            return self.shards.fix_replicated(self.shards.reduce_read(res), (0, 1, 3, 4))
-        return res.read()
+            h = self.shards.reduce_begin(res)
+            return ("shards", h, res)
+        return ("single", res.post(), res)
+
+    def _energy_collect(self, handle):
+        (kind, h, res) = handle
+        if kind == "shards":
+            vals = self.shards.reduce_end(h) if h is not None else self.shards.reduce_read(res)
+            return self.shards.fix_replicated(vals, (0, 1, 3, 4))
+        return res.collect(h)
+
+    def _energy_terms(self):
+        """The six terms of fit.py:149-154 from the fused K4 kernels."""
+        pend = self._pending_energy
+        if pend is not None and self._theta_lps is not None and pend[0] == self._energy_key():
+            return pend[1].copy()              # enqueued behind the (eta, epsilon) solve, collected with it
+        self._ensure_cache()
+        ev = self._find_eval()
+        if ev is None:
+            (_, _, eta, epsilon) = self._theta_lps
+            self._objective(np.array([eta, epsilon]), want_grad=False, name="K4_elm")
+            ev = self._evals[-1]
+        return self._energy_collect(self._energy_launch(ev['elm']))
 
     def _update_lq_F(self):
         """
@@ -925,19 +963,28 @@ class UnsharedRegionFit(object):
         if do_pi:
             (lqR, _) = self._mR.get_dev()
             NU = lqR.numel() // 2
-        res = self._result(5)
+        # one vector for the four K3a sums [0:4] and -- single GPU -- the code pass' record counts [5:7]: the
+        # host then waits ONCE for both (the counts are needed to size the record lists, the sums for pi, gamma)
+        res = self._result(8, tag="mstep")
         out = res.dev
         with _dev.timed(self.profile, "K3a_mstep_stats"):
             _lib.check(lib.fcd_mstep_stats(_dev.ptr(lqF), Cl, _dev.ptr(lqR), NU, _dev.ptr(out),
                                            _dev.ptr(_dev.workspace()), _dev.stream()), "fcd_mstep_stats")
         if do_gamma and self.shards is not None and self._in is not None:
-            red = self.shards.reduce_read(res)
+            red = self.shards.reduce_read(res, 5)
             if between is not None:
                 between()
             return self.shards.fix_replicated(red, (0, 1, 2)), C, NU
+        self._mstep_vals = None
         if between is not None:
-            between()
-        return res.read(), C, NU
+            self._tot_slot = (res, 5)
+            try:
+                between()
+            finally:
+                self._tot_slot = None
+        vals = self._mstep_vals if self._mstep_vals is not None else res.read()
+        self._mstep_vals = None
+        return vals, C, NU
 
     def _update_pi_gamma(self, do_pi, do_gamma, between=None):
         (s, C, NU) = self._mstep_sums(do_pi, do_gamma, between)
@@ -1206,6 +1253,7 @@ class UnsharedRegionFit(object):
         (fn, head, konst, name) = (ctx['fn'], ctx['head'], ctx['konst'], ctx['name'])
         budget = 60
         nfev = 0
+        terms = None
         first = max(2, min(6, self._last_nfev))
         while True:
             # the epsilon box of this pass: the reference's bounds, at most a factor 8 towards 0 or 1
@@ -1219,6 +1267,7 @@ class UnsharedRegionFit(object):
                        "fcd_solver_init")
             batch = first
             done_before = 0                      # evaluations this pass had consumed before the batch
+            pending = None
             while True:
                 if self.profile is None:
                     rc = fn(*head, lo_e, hi_e, _dev.ptr(sb.state), konst, windows, rank, world, sb.pub,
@@ -1233,6 +1282,12 @@ class UnsharedRegionFit(object):
                         if rc != 0:
                             _lib.check(rc, name)
                 sb.seq += batch
+                if self.energy_behind_solver and done_before == 0 and pending is None and nfev == 0:
+                    # K4 behind the first batch, E_lM taken from the solver state on the device: if the
+                    # solve finishes inside this batch (the usual case) ONE wait delivers theta_sub and
+                    # the free energy; otherwise the result is discarded (NaN E_lM) and K4 runs later
+                    pending = self._energy_launch(solver_state=_dev.ptr(sb.state))
+                    terms = self._energy_collect(pending)
                 st = sb.wait()
                 if self.profile is not None:     # launches that found the solve finished are not evaluations
                     self.profile.relabel_last(name, batch - (int(st.nfev) - done_before), "K3b_solver_idle_launch")
@@ -1248,10 +1303,20 @@ class UnsharedRegionFit(object):
             if not pinned or nfev >= budget:
                 break
             first = 2
+            terms = None                         # another pass follows: K4 saw an intermediate solution
         self._last_nfev = nfev
         self.solver_status.append((int(st.done), nfev))
         self.n_objective_evals.append(nfev)
         self._unpack_theta_sub(np.array([eta0, eps0]))
+        self._pending_energy = None
+        if (terms is not None and np.all(np.isfinite(terms)) and not self.update_mu_sigma
+                and self._theta_lps is not None):
+            # valid for the theta run() snapshots next (_update_lps): same mu, sigma, the solved (eta, epsilon)
+            (mu, sigma, _, _) = self._theta_lps
+            keep = self._theta_lps
+            self._theta_lps = (mu, sigma, float(eta0), float(eps0))
+            self._pending_energy = (self._energy_key(), np.array(terms, dtype=np.float64))
+            self._theta_lps = keep
         if np.isfinite(st.f):
             self._evals.append(dict(x=(float(eta0), float(eps0)), verF=ctx['verF'], verR=ctx['verR'], elm=-float(st.f)))
             del self._evals[:-4]

@@ -378,11 +378,13 @@ FCD_API int fcd_solver_wait(const void* published_host, uint64_t seq, void* stat
  * only and are complete on every rank).  qF = exp(lqF), qR = exp(lqR) as left
  * by fcd_estep_qF / fcd_estep_qR (fit.py:146-147); lqF / qF / S1 / S2 are the
  * shard's C rows.  `elm` = E_lM of the shard (fcd_elm_obj_grad + fcd_elm_const
- * at the same q_F, q_R, theta). */
+ * at the same q_F, q_R, theta); or, with `solver_state` != NULL (device, fcd_solver_init): the E_lM
+ * of the device-resident (eta, epsilon) solve enqueued before this call on the same stream (the
+ * GLOBAL value: pass it on one rank only) -- NaN if that solve has not finished. */
 FCD_API int fcd_energy_terms(const double* S1, const double* S2, int32_t H,
                      const double* lqF, const double* qF, int64_t C,
                      const double* lqR, const double* qR, int32_t N, int32_t U,
-                     const fcd_theta* theta_host, double elm,
+                     const fcd_theta* theta_host, double elm, const void* solver_state,
                      double* out6, double* ws, void* stream);
 
 /* K3c -- per-state sufficient statistics of the correlations for the control
