@@ -50,6 +50,9 @@ SIGNATURES = {
     "fcd_unpack_patients": (c_int, [_P, c_int32, c_int32, c_int32, c_int32, _P, _P, _P]),
     "fcd_c_to_nm": (c_int, [c_int64, c_int64, _P, _P, _P]),
     "fcd_healthy_stats": (c_int, [_P, c_int64, c_int32, c_int64, _P, _P, _P]),
+    "fcd_row_logsums": (c_int, [_P, c_int64, c_int64, c_int32, c_int64, POINTER(FcdTheta), _P, _P]),
+    "fcd_estep_qF_rowsums": (c_int, [_P, _P, c_int32, _P, c_int64, _D3, POINTER(FcdTheta), _P, _P, _P]),
+    "fcd_elm_rowsums": (c_int, [_P, _P, c_int64, _D3, _P, _P, _P]),
     "fcd_healthy_stats_cols": (c_int, [_P, c_int64, c_int64, _P, c_int32, _P, _P, _P]),
     "fcd_gather_columns": (c_int, [_P, c_int64, c_int64, c_int32, c_int64, _P, c_int32, _P, c_int64, c_int64, _P]),
     "fcd_gather_rows": (c_int, [_P, c_int64, c_int32, _P, c_int32, c_int64, _P, c_int64, _P]),

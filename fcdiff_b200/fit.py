@@ -199,6 +199,7 @@ class UnsharedRegionFit(object):
         self.theta_solver = "newton"  # (eta, epsilon): device-resident Newton | host-driven SciPy L-BFGS-B
         self.solver_tol = 1e-7        # newton: a step below this is taken without another evaluation
         self.energy_behind_solver = True   # newton: enqueue K4 behind the first batch of evaluations (one wait for both)
+        self.uniform_fast_path = True      # constant q_R (the start): row log-sums as running products (fcd_uniform.cu)
         self.solver_status = []       # newton: per solve (done code, evaluations)
         self.n_objective_evals = []
         self.profile = None           # _dev.KernelTimers for per-kernel CUDA-event timing
@@ -790,10 +791,84 @@ class UnsharedRegionFit(object):
         self._ensure_cache()
         ev = self._find_eval()
         if ev is None:
+            ev = self._elm_uniform()
+        if ev is None:
             (_, _, eta, epsilon) = self._theta_lps
             self._objective(np.array([eta, epsilon]), want_grad=False, name="K4_elm")
             ev = self._evals[-1]
         return self._energy_collect(self._energy_launch(ev['elm']))
+
+    # ------------------------------------------------------------------ the uniform start (csrc/fcd_uniform.cu)
+    def _uniform_rowsums(self):
+        """(S9, w3) when q_R is a constant array (the start of fit.py:97: every entry -ln 2): the nine row
+        sums S9[c][k][l] = sum_u log(a_l + b_l p_k(c,u)) at the current (eta, epsilon) snapshot -- nine
+        running products per row instead of nine logarithms per element -- and the constant pair weights
+        (fit.py:382-406).  None otherwise."""
+        if not self.uniform_fast_path or self._mR.fill is None or self._lps_state != 'derived':
+            return None
+        inp = self._ensure_cache()
+        (Cl, U) = (inp['Cl'], inp['U'])
+        if Cl == 0:
+            return None
+        (_, _, eta, epsilon) = self._theta_lps
+        key = (eta, epsilon, inp['cache_key'])
+        r = float(np.exp(np.float64(self._mR.fill[1])))
+        w3 = _lib.d3([r * r, r * r, 2.0 * r * r])
+        rs = inp.get('rowsums')
+        if rs is None or rs[0] != key:
+            lib = _lib.load()
+            S9 = _dev.empty((Cl, 9))
+            th = self._theta()
+            with _dev.timed(self.profile, "K2_row_logsums"):
+                _lib.check(lib.fcd_row_logsums(_dev.ptr(inp['P']), max(Cl, 1) * inp['pitchU'], Cl, U, inp['pitchU'],
+                                               ctypes.byref(th), _dev.ptr(S9), _dev.stream()), "fcd_row_logsums")
+            inp['rowsums'] = rs = (key, S9)
+        return rs[1], w3, 4.0 * r * r
+
+    def _elm_uniform(self):
+        """E_lM (fit.py:489-511) for a constant q_R from the row sums: no pass with nine logarithms per
+        element.  Returns the evaluation record ``_find_eval`` would, or None when not applicable."""
+        u = self._uniform_rowsums()
+        if u is None:
+            return None
+        (S9, w3, wsum) = u
+        lib = _lib.load()
+        inp = self._in
+        (c0, Cl, U) = (inp['c0'], inp['Cl'], inp['U'])
+        (_, qF) = self._mF.get_dev()
+        res = self._result(2, tag="elm_uniform")
+        ws = _dev.ptr(_dev.workspace())
+        stream = _dev.stream()
+        with _dev.timed(self.profile, "K4_elm_rowsums"):
+            _lib.check(lib.fcd_elm_rowsums(_dev.ptr(S9), _dev.ptr(qF[c0 * 3:]), Cl, w3, _dev.ptr(res.dev), ws, stream),
+                       "fcd_elm_rowsums")
+        # theta-free part: (sum_l w_l) sum_c (sum_k qF[c,k]) sum_u L[c,u]; with a constant q_F the middle factor
+        # is a number and the rest the total of the L plane (kept for the code pass)
+        if self._mF.fill is not None:
+            if inp.get('Lsum') is None:
+                inp['Lsum'] = _dev.empty((1,))
+                _lib.check(lib.fcd_plane_sum(_dev.ptr(inp['L']), Cl, U, inp['pitchU'], _dev.ptr(inp['Lsum']), ws, stream),
+                           "fcd_plane_sum")
+            res.dev[1:].copy_(inp['Lsum'])
+            cF = 3.0 * float(np.exp(np.float64(self._mF.fill[1])))
+        else:
+            (fstate, rstate) = (self._mF.get_state(), self._mR.get_state())
+            (_, qR) = self._mR.get_dev()
+            (N, H, U) = self._dims
+            with _dev.timed(self.profile, "K3b_elm_const"):
+                _lib.check(lib.fcd_elm_const(
+                    _dev.ptr(inp['L']), Cl, U, inp['pitchU'], _dev.ptr(qF[c0 * 3:]), _dev.ptr(fstate[c0:]),
+                    _dev.ptr(qR), _dev.ptr(rstate), rstate.shape[1], N, _dev.ptr(inp['nm']),
+                    _dev.ptr(res.dev[1:]), ws, stream), "fcd_elm_const")
+            (cF, wsum) = (1.0, 1.0)                # fcd_elm_const applies both factors itself
+        vals = res.read(stream) if self.shards is None else self.shards.reduce_read(res, 2, stream)
+        (_, _, eta, epsilon) = self._theta_lps
+        ev = dict(x=(eta, epsilon), verF=self._mF.version, verR=self._mR.version,
+                  elm=float(vals[0]) + cF * wsum * float(vals[1]))
+        self._evals.append(ev)
+        del self._evals[:-4]
+        return ev
+
 
     def _update_lq_F(self):
         """
@@ -826,6 +901,18 @@ class UnsharedRegionFit(object):
         (lqF, qF) = (lqF_buf[:C * 3], qF_buf[:C * 3])
         th = self._theta()
         self._wait_healthy(inp)
+        uni = self._uniform_rowsums() if Cl > 0 else None
+        if uni is not None:
+            # q_R is the constant start: the row sums (shared with the initial free energy) give lq_F directly
+            (S9, w3, _) = uni
+            with _dev.timed(self.profile, "K2_estep_qF_rowsums"):
+                _lib.check(lib.fcd_estep_qF_rowsums(_dev.ptr(inp['S1']), _dev.ptr(inp['S2']), H, _dev.ptr(S9), Cl, w3,
+                                                    ctypes.byref(th), _dev.ptr(lqF[c0 * 3:]), _dev.ptr(qF[c0 * 3:]),
+                                                    _dev.stream()), "fcd_estep_qF_rowsums")
+            if self.shards is not None:
+                self.shards.allgather_edges(lqF_buf, qF_buf, C)
+            self._mF.set_dev(lqF, qF, (C, 1, 3))
+            return
         if self.coded_estep and Cl > 0 and inp.get('code_verR') == self._mR.version and inp.get('PsE') is not None:
             # the code plane and key lists of the last M-step still describe q_R (fcd_estep_qF_coded)
             with _dev.timed(self.profile, "K2_estep_qF_coded"):

@@ -178,6 +178,21 @@ FCD_API int fcd_estep_qF_coded(const double* S1, const double* S2, int32_t H,
                        const uint64_t* keysH, const int64_t* rowoff, const double* Hh,
                        const fcd_theta* theta_host, double* lqF, double* qF, void* stream);
 
+/* The uniform start (fcdiff/fit.py:84-102: lq_R = -ln 2, lq_F = -ln 3 everywhere).  With a CONSTANT q_R every
+ * element has the same pair weights w (fit.py:382-406), and the sums of fit.py:165-173 / 489-511 factor through
+ *   S9[c][k*3 + l] = sum_u log(a_l + b_l p_k(c,u))       (a_l, b_l: fit.py:427-444 relative to the total density)
+ * -- nine running products per row instead of nine logarithms per element (csrc/fcd_uniform.cu):
+ *   fcd_row_logsums: S9 [C][9] from the planes P_0, P_1 ([C][pitchU], 16-byte aligned rows);
+ *   fcd_estep_qF_rowsums: `_update_lq_F` (fit.py:157-174) from S9 and w3_host = {q0^2, q1^2, 2 q0 q1};
+ *   fcd_elm_rowsums: out1[0] = sum_c sum_k qF[c,k] sum_l w_l S9[c][k][l], the theta-dependent part of E_lM
+ *     (fit.py:489-511); the theta-free part is (sum_l w_l) sum_c (sum_k qF[c,k]) sum_u L[c,u]. */
+FCD_API int fcd_row_logsums(const double* P, int64_t planeStride, int64_t C, int32_t U, int64_t pitchU,
+                    const fcd_theta* theta_host, double* S9, void* stream);
+FCD_API int fcd_estep_qF_rowsums(const double* S1, const double* S2, int32_t H, const double* S9, int64_t C,
+                         const double* w3_host, const fcd_theta* theta_host, double* lqF, double* qF, void* stream);
+FCD_API int fcd_elm_rowsums(const double* S9, const double* qF, int64_t C, const double* w3_host, double* out1,
+                    double* ws, void* stream);
+
 /* Replica sweeps (BASELINE.json configs[4]; no reference counterpart -- the reference stops at one
  * fit, fcdiff/fit.py:56-82): the responsibility planes of ALL S subjects are built once
  * (fcd_resp_cache on every column of the (C, S) correlation matrix, fcd_transpose_patients), and a

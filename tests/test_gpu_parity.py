@@ -632,6 +632,34 @@ def test_config3_properties(N, H, U):
     nptest.assert_allclose(fused, fit._lq_R, rtol=1e-9, atol=1e-9)
 
 
+@pytest.mark.parametrize("N,H,U", [(4, 2, 3), (10, 20, 20), (24, 8, 129), (33, 17, 300)])
+def test_uniform_start_fast_path_equals_general_kernels_and_oracle(N, H, U):
+    """The uniform start (fit.py:84-102): the row log-sums of csrc/fcd_uniform.cu (nine running products per
+    row) must give the initial free energy and the first E-step of the general kernels (nine
+    logarithms per element) and of the oracle."""
+    th = O.Theta()
+    (_, _, _, _, b, bt) = O.sample(th, N, H, U, np.random.RandomState(N))
+    out = {}
+    for fast in (True, False):
+        fit = _fit_for(b, bt, eta_shift=0.1)
+        fit.uniform_fast_path = fast
+        fit._init_lps(N, H, U)
+        fit._update_lps()
+        e0 = fit._eval_energy()
+        fit._update_lq_F()
+        out[fast] = (e0, fit._lq_F.copy())
+        if fast:
+            assert 'rowsums' in fit._in
+    nptest.assert_allclose(out[True][0], out[False][0], rtol=1e-12)
+    nptest.assert_allclose(out[True][1], out[False][1], rtol=1e-10, atol=1e-10)
+    tho = O.Theta()
+    tho.eta += 0.1
+    (lq_F, lq_R) = O.init_lps(N, U)
+    (lpB, p, lM) = O.update_lps(b, bt, tho)
+    nptest.assert_allclose(out[True][0], O.energy_from_terms(O.eval_energy_terms(tho, lq_F, lq_R, lpB, lM)), rtol=1e-10)
+    nptest.assert_allclose(out[True][1], O.update_lq_F(tho.gamma, lpB, lM, lq_R), rtol=1e-9, atol=1e-10)
+
+
 # ------------------------------------------------------------------ config 4 geometry: one edge shard vs the oracle
 class _RowWindow(object):
     """Stands in for ``dist.EdgeShards`` on ONE process: this 'rank' owns the edge rows
