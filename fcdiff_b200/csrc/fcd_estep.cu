@@ -1,6 +1,9 @@
 // E-step kernels: healthy sufficient statistics, responsibility planes, peak
 // states, K2 (template posterior q_F), K2b (region-weight tensor W and the
 // Gauss-Seidel sweep for q_R).
+#include <cstdlib>
+#include <cstring>
+
 #include "fcd_common.cuh"
 
 namespace fcd {
@@ -756,6 +759,125 @@ sweep_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int u0,
     }
 }
 
+// --------------------------------------------------------------- K2b/sweep, blocked
+// The same Gauss-Seidel sweep with the N dependent steps taken in blocks of 32 regions (blocked forward
+// substitution).  sweep_kernel pays, per region, one CTA-wide reduction + barrier + normalisation on the
+// critical path (~0.6 us: the launch lasts N of them whatever the GPU could do in parallel).  Here, per
+// block of regions [n0, n0 + 32):
+//   bulk   every thread accumulates, for ALL 32 rows at once, the terms of the regions outside the block
+//          (already updated before it, not yet updated after it: fit.py:185-194 with the q_R of the moment)
+//          -- 32 independent accumulators per thread, the loads of a whole block in flight together; one
+//          warp transpose-reduction (31 shuffles for 32 sums) and one barrier per BLOCK;
+//   solve  warp 0 alone runs the 32 dependent steps: lane i keeps region n0 + i's q_R in a register (new as
+//          soon as it is solved), the in-block weights W[n0+r][n0+i] come from shared memory, a step is one
+//          warp reduction and one normalisation -- no barrier, no other warp involved.
+// One CTA per patient; q_R of all regions in shared memory.  Same arithmetic per term as sweep_kernel (the
+// order of the additions differs).
+constexpr int kSwB = 32;
+
+template <int LOOKUP>
+__device__ __forceinline__ int64_t sweep_edge(int n, int m, int64_t base_n) {
+    if (LOOKUP == FCD_LOOKUP_REFERENCE) return base_n + m;                 // nm_to_c(n, m) even for m > n (fit.py:185-186)
+    return m < n ? base_n + m : (int64_t)m * (m - 1) / 2 + n;
+}
+
+template <int T, int LOOKUP>
+__global__ void __launch_bounds__(T)
+sweep_blocked_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int u0, double lp0, double lp1,
+                     double* __restrict__ qR, double* __restrict__ lqR) {
+    constexpr int NW = T / 32, B = kSwB;
+    extern __shared__ __align__(16) double s_sweep[];
+    double2* s_q = reinterpret_cast<double2*>(s_sweep);                    // [Npad] q_R of the moment
+    const int Npad = (N + 31) & ~31;
+    double2* s_wb = s_q + Npad;                                            // [B][B] in-block weights
+    double* s_part = reinterpret_cast<double*>(s_wb + B * B);             // [NW][B] per-warp bulk sums
+    const int ul = blockIdx.x, u = u0 + ul;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double2* Wu = reinterpret_cast<const double2*>(WT) + (int64_t)ul * C;     // {W_0 - W_2, W_2 - W_1}
+    const double2* qR2 = reinterpret_cast<const double2*>(qR);
+    for (int m = tid; m < Npad; m += T) s_q[m] = m < N ? qR2[(int64_t)m * U + u] : make_double2(0.0, 0.0);
+    __syncthreads();
+    const double dlp = lp0 - lp1;
+    for (int n0 = 0; n0 < N; n0 += B) {
+        const int nb = N - n0 < B ? N - n0 : B;
+        const int64_t base0 = (int64_t)n0 * (n0 - 1) / 2;
+        // in-block weights (requested first: they arrive under the bulk loop)
+        for (int e = tid; e < B * B; e += T) {
+            const int r = e / B, i = e - r * B;
+            double2 w = make_double2(0.0, 0.0);
+            if (r < nb && i < nb && i != r) {
+                const int n = n0 + r;
+                w = __ldg(Wu + sweep_edge<LOOKUP>(n, n0 + i, (int64_t)n * (n - 1) / 2));
+            }
+            s_wb[e] = w;
+        }
+        // bulk: the regions outside the block, all rows of the block at once
+        double acc[B];
+#pragma unroll
+        for (int r = 0; r < B; ++r) acc[r] = 0.0;
+        for (int m = tid; m < N; m += T) {
+            if (m >= n0 && m < n0 + nb) continue;
+            const double2 q = s_q[m];
+            int64_t base = base0;
+#pragma unroll
+            for (int r = 0; r < B; ++r) {
+                if (r < nb) {
+                    const double2 w = __ldg(Wu + sweep_edge<LOOKUP>(n0 + r, m, base));
+                    acc[r] += fma(q.x, w.x, q.y * w.y);                    // (fit.py:188-190) - (fit.py:192-194)
+                }
+                base += n0 + r;                                            // base(n + 1) - base(n) = n
+            }
+        }
+        // warp transpose-reduction: 32 sums over 32 lanes, lane r ends with row r
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < off; ++i) {
+                const double send = up ? acc[i] : acc[i + off];
+                const double keep = up ? acc[i + off] : acc[i];
+                acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+        }
+        s_part[warp * B + lane] = acc[0];
+        __syncthreads();
+        if (warp == 0) {
+            double t = dlp;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) t += s_part[w * B + lane];
+            double2 q = s_q[n0 + lane];                                    // Npad: in range; zero beyond N
+            double2 lq = make_double2(0.0, 0.0);
+            for (int r = 0; r < nb; ++r) {
+                const double2 w = s_wb[r * B + lane];
+                const double a = warp_sum(fma(q.x, w.x, q.y * w.y));
+                if (lane == r) {
+                    // lq = l - logsumexp(l), q = exp(lq) (fit.py:196-197) with one exponential (see sweep_kernel)
+                    const double D = t + a;
+                    const bool first = D >= 0.0;
+                    const double d = first ? -D : D;
+                    const double e = exp_nonpos(d);
+                    double lg = e, inv = 1.0;
+                    if (e >= 5.551115123125783e-17) {
+                        lg = log1p(e);
+                        inv = 1.0 / (1.0 + e);
+                    }
+                    const double lmax = -lg, lmin = d - lg;
+                    const double qmax = inv, qmin = e * inv;
+                    lq = first ? make_double2(lmax, lmin) : make_double2(lmin, lmax);
+                    q = first ? make_double2(qmax, qmin) : make_double2(qmin, qmax);
+                }
+            }
+            if (lane < nb) {
+                s_q[n0 + lane] = q;
+                const int64_t o = ((int64_t)(n0 + lane) * U + u) * 2;
+                *reinterpret_cast<double2*>(lqR + o) = lq;
+                *reinterpret_cast<double2*>(qR + o) = q;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // --------------------------------------------------------------- K2b fused
 // Gauss-Seidel sweep of fcdiff/fit.py:184-197 with the region weights computed
 // inside the kernel: no WT tensor (24 bytes per edge-patient written and read
@@ -1199,6 +1321,35 @@ int fcd_estep_qR(const double* WT, int64_t C, int32_t N, int32_t U, int32_t u0, 
     FCD_REQUIRE(N <= 8192, "fcd_estep_qR: N=%d exceeds the 8192 regions the sweep kernel supports", N);
     cudaStream_t st = (cudaStream_t)stream;
     const double lp0 = log_pi2_host[0], lp1 = log_pi2_host[1];
+    // blocked forward substitution (sweep_blocked_kernel) from 64 regions on; FCD_SWEEP=stepwise selects the
+    // one-region-per-step kernel everywhere (experiments, cross-checks)
+    static const bool stepwise = [] {
+        const char* e = getenv("FCD_SWEEP");
+        return e != nullptr && strcmp(e, "stepwise") == 0;
+    }();
+    if (N >= 64 && !stepwise) {
+        const int Npad = (N + 31) & ~31;
+        // with few patients on this GPU (sharded fits) more threads per patient shorten the bulk phases
+        const bool wide = Ul < 2 * sm_count() && N > 512;
+        const int T = wide ? 512 : (N > 1024 ? 256 : 128);
+        const size_t smem = (size_t)Npad * 16 + (size_t)kSwB * kSwB * 16 + (size_t)(T / 32) * kSwB * 8;
+        FCD_REQUIRE(smem <= 200 * 1024, "fcd_estep_qR: N=%d needs %zu bytes of shared memory", N, smem);
+#define FCD_SWB(T_)                                                                                          \
+        do {                                                                                                 \
+            if (edge_lookup == FCD_LOOKUP_REFERENCE) {                                                       \
+                if (smem > 48 * 1024) FCD_ALLOW_BIG_SMEM(sweep_blocked_kernel<T_, FCD_LOOKUP_REFERENCE>);    \
+                sweep_blocked_kernel<T_, FCD_LOOKUP_REFERENCE><<<Ul, T_, smem, st>>>(WT, C, N, U, u0, lp0, lp1, qR, lqR); \
+            } else {                                                                                         \
+                if (smem > 48 * 1024) FCD_ALLOW_BIG_SMEM(sweep_blocked_kernel<T_, FCD_LOOKUP_SYMMETRIC>);    \
+                sweep_blocked_kernel<T_, FCD_LOOKUP_SYMMETRIC><<<Ul, T_, smem, st>>>(WT, C, N, U, u0, lp0, lp1, qR, lqR); \
+            }                                                                                                \
+        } while (0)
+        if (T == 512) FCD_SWB(512);
+        else if (T == 256) FCD_SWB(256);
+        else FCD_SWB(128);
+#undef FCD_SWB
+        return check_launch("fcd_estep_qR(blocked)");
+    }
 #define FCD_SWEEP(T, M)                                                                            \
     do {                                                                                           \
         if (edge_lookup == FCD_LOOKUP_REFERENCE)                                                   \

@@ -220,7 +220,11 @@ def test_patient_gather_staging_roundtrip(N, U, world):
 
 
 @pytest.mark.parametrize("N,U,lookup", [(37, 5, 0), (600, 3, 0), (600, 2, 1), (1100, 2, 0), (1400, 2, 1), (2100, 1, 0),
-                                        (530, 300, 0)])             # U >= 2 x SMs: the compact launch shapes
+                                        (530, 300, 0),              # U >= 2 x SMs: the compact launch shapes
+                                        # blocked forward substitution (N >= 64): whole / ragged last blocks, both
+                                        # lookups, the three thread counts, shared memory beyond 48 KB
+                                        (64, 9, 0), (65, 4, 1), (96, 3, 0), (100, 3, 1), (400, 6, 0), (400, 5, 1),
+                                        (3300, 1, 1)])
 def test_sweep_launch_shapes_match_numpy(N, U, lookup):
     """Gauss-Seidel sweep of fit.py:184-197 over the two weight differences, for every launch shape of
     fcd_estep_qR (regions per thread / warps per patient depend on N), both edge lookups."""
