@@ -4,6 +4,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <type_traits>
+
 #include "fcd_common.cuh"
 
 namespace fcd {
@@ -760,20 +762,36 @@ sweep_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int u0,
 }
 
 // --------------------------------------------------------------- K2b/sweep, blocked
-// The same Gauss-Seidel sweep with the N dependent steps taken in blocks of 32 regions (blocked forward
-// substitution).  sweep_kernel pays, per region, one CTA-wide reduction + barrier + normalisation on the
-// critical path (~0.6 us: the launch lasts N of them whatever the GPU could do in parallel).  Here, per
-// block of regions [n0, n0 + 32):
-//   bulk   every thread accumulates, for ALL 32 rows at once, the terms of the regions outside the block
-//          (already updated before it, not yet updated after it: fit.py:185-194 with the q_R of the moment)
-//          -- 32 independent accumulators per thread, the loads of a whole block in flight together; one
-//          warp transpose-reduction (31 shuffles for 32 sums) and one barrier per BLOCK;
-//   solve  warp 0 alone runs the 32 dependent steps: lane i keeps region n0 + i's q_R in a register (new as
-//          soon as it is solved), the in-block weights W[n0+r][n0+i] come from shared memory, a step is one
-//          warp reduction and one normalisation -- no barrier, no other warp involved.
-// One CTA per patient; q_R of all regions in shared memory.  Same arithmetic per term as sweep_kernel (the
-// order of the additions differs).
-constexpr int kSwB = 32;
+// The same Gauss-Seidel sweep with the N dependent steps taken in blocks of B = 16 or 32 regions (blocked
+// forward substitution), software-pipelined inside the CTA.  sweep_kernel pays, per region, one CTA-wide
+// reduction + barrier + normalisation on the critical path (~0.6 us: the launch lasts N of them whatever the
+// GPU could do in parallel).  Here one CTA per patient, q_R of all regions in shared memory, and per block b
+// of regions [n0, n0 + B) two roles that run CONCURRENTLY, one barrier per block:
+//   prepare(b + 1), warps 1..: everything of block b + 1 that does not depend on block b's new q_R --
+//          (i)   the two B x B weight tiles the solver will need (rows of block b + 1 x columns of block b:
+//                "near"; rows x columns of block b + 1: "in-block"), by 16-byte cp.async straight into shared
+//                memory, transposed ([column][row]), no registers held while they fly;
+//          (ii)  the rows of block b + 2 are requested into L2 (bulk prefetch): the far loads are latency-
+//                bound, an L2 hit returns in a third of the time of an HBM access;
+//          (iii) "far": every thread accumulates, for 16 rows at once, the terms of the regions outside
+//                blocks b and b + 1 (already updated before, not yet updated after: fit.py:185-194 with the
+//                q_R of the moment) and of the regions of block b + 1 AFTER each row (old q_R, masked) -- 16
+//                independent accumulators and loads in flight per thread; one warp transpose-reduction per
+//                16 rows;
+//   solve(b), warp 0: lane i holds D_i = l_0 - l_1 of region n0 + i: far sums + the near tile times the
+//          q_R block b - 1 just received, then B right-looking steps: step r broadcasts D_r (final: every
+//          earlier region of the block has been added), ALL lanes form q_R[n0 + r] from it (warp-uniform: no
+//          divergence, no second broadcast) and add its term to their own D_i; weights from the in-block
+//          tile, requested one step ahead.  The chain of a step is one shuffle, the logistic function
+//          (exponential in Estrin form, reciprocal by MUFU + one cubic correction) and two FMAs -- for a
+//          decided region (|D| >= 37.5: exp(-|D|) < 2^-54) a shuffle, an integer compare and one addition.
+//          No reduction, no barrier, no logarithm on the chain;
+//   outputs(b - 1), last helper warp: lq_R = l - logsumexp(l), q_R = exp(lq_R) (fit.py:196-197) of the block
+//          solved in the previous phase, from its D values, one lane per region -- sweep_kernel's formulas.
+// Same arithmetic per term as sweep_kernel (the order of the additions differs; the q_R a later step of the
+// sweep uses comes from the chain's reciprocal and is exactly (1, 0) for a decided region, where the stored
+// output is the correctly rounded quotient and (1, exp(-|D|) < 5.2e-17): |dD| < 1e-15).
+constexpr int kSwRH = 16;                                                  // rows per far pass
 
 template <int LOOKUP>
 __device__ __forceinline__ int64_t sweep_edge(int n, int m, int64_t base_n) {
@@ -781,16 +799,30 @@ __device__ __forceinline__ int64_t sweep_edge(int n, int m, int64_t base_n) {
     return m < n ? base_n + m : (int64_t)m * (m - 1) / 2 + n;
 }
 
-template <int T, int LOOKUP>
-__global__ void __launch_bounds__(T)
+// q_R [Npad] | tiles [2 buffers][near, in-block][B x (B + 1)] | far sums [2][helper warps][B] | D [2][B]
+__host__ __device__ constexpr size_t sweep_blocked_smem(int N, int T, int B) {
+    return (size_t)((N + 31) & ~31) * 16 + (size_t)4 * B * (B + 1) * 16 + (size_t)2 * (T / 32 - 1) * B * 8 +
+           (size_t)2 * B * 8;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+template <int T, int B, int LOOKUP>
+__global__ void __launch_bounds__(T, 512 / T)
 sweep_blocked_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int u0, double lp0, double lp1,
                      double* __restrict__ qR, double* __restrict__ lqR) {
-    constexpr int NW = T / 32, B = kSwB;
+    constexpr int NWH = T / 32 - 1, H = T - 32, Bp = B + 1, RH = kSwRH, TILE = B * Bp;
+    constexpr int LB = B == 32 ? 5 : 4;
+    static_assert(B == 16 || B == 32, "block of 16 or 32 regions");
     extern __shared__ __align__(16) double s_sweep[];
     double2* s_q = reinterpret_cast<double2*>(s_sweep);                    // [Npad] q_R of the moment
     const int Npad = (N + 31) & ~31;
-    double2* s_wb = s_q + Npad;                                            // [B][B] in-block weights
-    double* s_part = reinterpret_cast<double*>(s_wb + B * B);             // [NW][B] per-warp bulk sums
+    double2* s_tiles = s_q + Npad;                                         // [2][2][B][Bp], [column][row]
+    double* s_part = reinterpret_cast<double*>(s_tiles + 4 * TILE);       // [2][NWH][B] per-warp far sums
+    double* s_D = s_part + 2 * NWH * B;                                    // [2][B] l_0 - l_1 of a solved block
     const int ul = blockIdx.x, u = u0 + ul;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double2* Wu = reinterpret_cast<const double2*>(WT) + (int64_t)ul * C;     // {W_0 - W_2, W_2 - W_1}
@@ -798,84 +830,188 @@ sweep_blocked_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int
     for (int m = tid; m < Npad; m += T) s_q[m] = m < N ? qR2[(int64_t)m * U + u] : make_double2(0.0, 0.0);
     __syncthreads();
     const double dlp = lp0 - lp1;
-    for (int n0 = 0; n0 < N; n0 += B) {
+    const int nblocks = (N + B - 1) / B;
+
+    // ---- prepare(b): helper warps only
+    auto prepare = [&](int b) {
+        const int ht = tid - 32, hw = warp - 1;
+        const int n0 = b * B;
         const int nb = N - n0 < B ? N - n0 : B;
+        double2* tiles = s_tiles + (b & 1) * 2 * TILE;
+        // (i) tiles: element e -> tile t (0 near, 1 in-block), row i, column j; lanes walk a row's columns
+        // (contiguous edges: both tiles have m < n, where the two lookups agree)
+        for (int e = ht; e < 2 * B * B; e += H) {
+            const int t = e >> (2 * LB), i = (e >> LB) & (B - 1), j = e & (B - 1);
+            double2* dst = tiles + t * TILE + j * Bp + i;
+            const int n = n0 + i;
+            const bool live = i < nb && (t == 0 ? b > 0 : j < i);
+            if (live) cp_async16(dst, Wu + (int64_t)n * (n - 1) / 2 + (n0 - (t == 0 ? B : 0)) + j);
+            else *dst = make_double2(0.0, 0.0);
+        }
+        // (ii) the rows of block b + 1 (what the NEXT prepare will read, one phase from now) into L2
+        if (b + 1 < nblocks && lane == 0) {                                // (the instruction takes warp-uniform operands)
+            const int n1 = n0 + B, nl = n1 + B - 1 < N - 1 ? n1 + B - 1 : N - 1;
+            const int64_t e0 = (int64_t)n1 * (n1 - 1) / 2;
+            int64_t e1 = (int64_t)nl * (nl - 1) / 2 + (LOOKUP == FCD_LOOKUP_REFERENCE ? N : nl);
+            if (e1 > C) e1 = C;
+            const char* g0 = reinterpret_cast<const char*>(Wu + e0);
+            const int64_t bytes = (e1 - e0) * 16;
+            for (int64_t off = (int64_t)hw * 8192; off < bytes; off += (int64_t)NWH * 8192) {
+                const uint32_t sz = (uint32_t)(bytes - off < 8192 ? bytes - off : 8192);
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g0 + off), "r"(sz) : "memory");
+            }
+        }
+        // (iii) far sums.  Row n0 + r of column m is the edge base(n0 + r) + m (reference lookup, and the
+        // symmetric one for m < n0): base(n0 + r) = base(n0) + r n0 + r (r - 1) / 2 -- one pointer per column,
+        // one 32-bit offset per row; for m > n (symmetric) the edges base(m) + n0 + r.  The rows are taken
+        // RH = 16 at a time: 16 accumulators leave the registers for 16 loads in flight per thread.
         const int64_t base0 = (int64_t)n0 * (n0 - 1) / 2;
-        // in-block weights (requested first: they arrive under the bulk loop)
-        for (int e = tid; e < B * B; e += T) {
-            const int r = e / B, i = e - r * B;
-            double2 w = make_double2(0.0, 0.0);
-            if (r < nb && i < nb && i != r) {
-                const int n = n0 + r;
-                w = __ldg(Wu + sweep_edge<LOOKUP>(n, n0 + i, (int64_t)n * (n - 1) / 2));
-            }
-            s_wb[e] = w;
-        }
-        // bulk: the regions outside the block, all rows of the block at once
-        double acc[B];
+        using yes = std::integral_constant<bool, true>;
+        using no = std::integral_constant<bool, false>;
+#pragma unroll 1
+        for (int h = 0; h < B; h += RH) {
+            double acc[RH];
 #pragma unroll
-        for (int r = 0; r < B; ++r) acc[r] = 0.0;
-        for (int m = tid; m < N; m += T) {
-            if (m >= n0 && m < n0 + nb) continue;
-            const double2 q = s_q[m];
-            int64_t base = base0;
+            for (int r = 0; r < RH; ++r) acc[r] = 0.0;
+            // `masked` = false is the common case (a whole block of rows, a column outside the block): no
+            // predicate per row -- a per-row predicate would cap the loads in flight at the 7 predicate registers
+            auto rows = [&](const double2* p, int stride, auto tri, auto masked, int lim, double2 q) {
+                p += h * stride + (decltype(tri)::value ? h * (h - 1) / 2 : 0);
 #pragma unroll
-            for (int r = 0; r < B; ++r) {
-                if (r < nb) {
-                    const double2 w = __ldg(Wu + sweep_edge<LOOKUP>(n0 + r, m, base));
-                    acc[r] += fma(q.x, w.x, q.y * w.y);                    // (fit.py:188-190) - (fit.py:192-194)
-                }
-                base += n0 + r;                                            // base(n + 1) - base(n) = n
-            }
-        }
-        // warp transpose-reduction: 32 sums over 32 lanes, lane r ends with row r
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-            const bool up = (lane & off) != 0;
-#pragma unroll
-            for (int i = 0; i < off; ++i) {
-                const double send = up ? acc[i] : acc[i + off];
-                const double keep = up ? acc[i + off] : acc[i];
-                acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-            }
-        }
-        s_part[warp * B + lane] = acc[0];
-        __syncthreads();
-        if (warp == 0) {
-            double t = dlp;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) t += s_part[w * B + lane];
-            double2 q = s_q[n0 + lane];                                    // Npad: in range; zero beyond N
-            double2 lq = make_double2(0.0, 0.0);
-            for (int r = 0; r < nb; ++r) {
-                const double2 w = s_wb[r * B + lane];
-                const double a = warp_sum(fma(q.x, w.x, q.y * w.y));
-                if (lane == r) {
-                    // lq = l - logsumexp(l), q = exp(lq) (fit.py:196-197) with one exponential (see sweep_kernel)
-                    const double D = t + a;
-                    const bool first = D >= 0.0;
-                    const double d = first ? -D : D;
-                    const double e = exp_nonpos(d);
-                    double lg = e, inv = 1.0;
-                    if (e >= 5.551115123125783e-17) {
-                        lg = log1p(e);
-                        inv = 1.0 / (1.0 + e);
+                for (int r = 0; r < RH; ++r) {
+                    if (!decltype(masked)::value || h + r < lim) {
+                        // base(n0 + h + r) - base(n0 + h) = r (n0 + h) + r (r - 1) / 2
+                        const double2 w = __ldg(p + (r * (stride + (decltype(tri)::value ? h : 0)) +
+                                                     (decltype(tri)::value ? r * (r - 1) / 2 : 0)));
+                        acc[r] = fma(q.x, w.x, fma(q.y, w.y, acc[r]));    // (fit.py:188-190) - (fit.py:192-194)
                     }
-                    const double lmax = -lg, lmin = d - lg;
-                    const double qmax = inv, qmin = e * inv;
-                    lq = first ? make_double2(lmax, lmin) : make_double2(lmin, lmax);
-                    q = first ? make_double2(qmax, qmin) : make_double2(qmin, qmax);
+                }
+            };
+            for (int m = ht; m < N; m += H) {
+                const int mb = m >> LB;
+                if (mb == b - 1) continue;                                 // near: the solver's (new q_R of block b - 1)
+                const double2 q = s_q[m];
+                const bool tri = LOOKUP == FCD_LOOKUP_REFERENCE || m < n0;
+                const double2* p = tri ? Wu + base0 + m : Wu + (int64_t)m * (m - 1) / 2 + n0;
+                if (mb != b && nb == B) {
+                    if (tri) rows(p, n0, yes(), no(), B, q);
+                    else rows(p, 1, no(), no(), B, q);
+                } else {
+                    // in-block column: only the rows before the column; last block: only the rows that exist
+                    const int lim = mb == b ? m - n0 : nb;
+                    if (tri) rows(p, n0, yes(), yes(), lim, q);
+                    else rows(p, 1, no(), yes(), lim, q);
                 }
             }
-            if (lane < nb) {
-                s_q[n0 + lane] = q;
-                const int64_t o = ((int64_t)(n0 + lane) * U + u) * 2;
-                *reinterpret_cast<double2*>(lqR + o) = lq;
-                *reinterpret_cast<double2*>(qR + o) = q;
+            // warp transpose-reduction: 16 sums over 32 lanes, lane r (and r + 16) ends with row h + r
+#pragma unroll
+            for (int i = 0; i < RH; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+#pragma unroll
+            for (int off = RH / 2; off >= 1; off >>= 1) {
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int i = 0; i < off; ++i) {
+                    const double send = up ? acc[i] : acc[i + off];
+                    const double keep = up ? acc[i + off] : acc[i];
+                    acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
             }
+            if (lane < RH) s_part[((b & 1) * NWH + hw) * B + h + lane] = acc[0];
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    };
+
+    // ---- solve(b): warp 0 only (B = 16: lanes 16.. mirror lanes 0..15)
+    auto solve = [&](int b) {
+        const int n0 = b * B, li = lane & (B - 1);
+        const int nb = N - n0 < B ? N - n0 : B;
+        const double2* near = s_tiles + (b & 1) * 2 * TILE;
+        const double2* wb = near + TILE;
+        double Da = dlp, Db = 0.0;
+#pragma unroll
+        for (int w = 0; w < NWH; w += 2) {
+            Da += s_part[((b & 1) * NWH + w) * B + li];
+            if (w + 1 < NWH) Db += s_part[((b & 1) * NWH + w + 1) * B + li];
+        }
+        double D = Da + Db;
+        if (b > 0) {                                                       // near tile x the block solved last
+            double d4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int j = 0; j < B; ++j) {
+                const double2 qj = s_q[n0 - B + j];                        // broadcast
+                const double2 w = near[j * Bp + li];
+                d4[j & 3] = fma(qj.x, w.x, fma(qj.y, w.y, d4[j & 3]));
+            }
+            D += (d4[0] + d4[1]) + (d4[2] + d4[3]);
+        }
+        double Dmine = 0.0;
+        double2 qmine = make_double2(0.0, 0.0);
+        double2 wn = wb[li];
+        for (int r = 0; r < nb; ++r) {
+            const double2 w = wn;
+            wn = wb[((r + 1) & (B - 1)) * Bp + li];                       // next step's weights: off the chain
+            const double Dr = __shfl_sync(0xffffffffu, D, r);
+            // q = exp(lq), lq = l - logsumexp(l) (fit.py:196-197): q_max = 1 / (1 + t), q_min = t / (1 + t),
+            // t = exp(-|D|); warp-uniform.  |D| >= 37.5 (an integer compare of the high word): t < 2^-54.
+            const int hi = __double2hiint(Dr);
+            const bool first = hi >= 0;
+            double q0, q1;
+            if ((hi & 0x7fffffff) >= 0x4042c000) {
+                q0 = first ? 1.0 : 0.0;
+                q1 = first ? 0.0 : 1.0;
+                D += first ? w.x : w.y;
+            } else {
+                const double t = exp_nonpos_short(-fabs(Dr));
+                const double qmax = rcp_newton(1.0 + t), qmin = t * qmax;
+                q0 = first ? qmax : qmin;
+                q1 = first ? qmin : qmax;
+                D = fma(q0, w.x, fma(q1, w.y, D));                         // rows <= r: zero weight (tile holds j < i only)
+            }
+            if (lane == r) {
+                Dmine = Dr;
+                qmine = make_double2(q0, q1);
+            }
+        }
+        if (lane < nb) {
+            s_q[n0 + lane] = qmine;
+            s_D[(b & 1) * B + lane] = Dmine;
+        }
+    };
+
+    // ---- outputs(b): one warp, a lane per region of a solved block; one exponential (see sweep_kernel)
+    auto outputs = [&](int b) {
+        const int n0 = b * B;
+        const int nb = N - n0 < B ? N - n0 : B;
+        if (lane < nb) {
+            const double Dm = s_D[(b & 1) * B + lane];
+            const bool first = Dm >= 0.0;
+            const double d = first ? -Dm : Dm;
+            const double e = exp_nonpos(d);
+            double lg = e, inv = 1.0;
+            if (e >= 5.551115123125783e-17) {
+                lg = log1p(e);
+                inv = 1.0 / (1.0 + e);
+            }
+            const double lmax = -lg, lmin = d - lg;
+            const double qmax = inv, qmin = e * inv;
+            const int64_t o = ((int64_t)(n0 + lane) * U + u) * 2;
+            *reinterpret_cast<double2*>(lqR + o) = first ? make_double2(lmax, lmin) : make_double2(lmin, lmax);
+            *reinterpret_cast<double2*>(qR + o) = first ? make_double2(qmax, qmin) : make_double2(qmin, qmax);
+        }
+    };
+
+    if (warp > 0) prepare(0);
+    __syncthreads();
+    for (int b = 0; b < nblocks; ++b) {
+        if (warp == 0) {
+            solve(b);
+        } else {
+            if (warp == NWH && b >= 1) outputs(b - 1);
+            if (b + 1 < nblocks) prepare(b + 1);
         }
         __syncthreads();
     }
+    if (warp == NWH) outputs(nblocks - 1);
 }
 
 // --------------------------------------------------------------- K2b fused
@@ -1328,25 +1464,34 @@ int fcd_estep_qR(const double* WT, int64_t C, int32_t N, int32_t U, int32_t u0, 
         return e != nullptr && strcmp(e, "stepwise") == 0;
     }();
     if (N >= 64 && !stepwise) {
-        const int Npad = (N + 31) & ~31;
-        // with few patients on this GPU (sharded fits) more threads per patient shorten the bulk phases
-        const bool wide = Ul < 2 * sm_count() && N > 512;
-        const int T = wide ? 512 : (N > 1024 ? 256 : 128);
-        const size_t smem = (size_t)Npad * 16 + (size_t)kSwB * kSwB * 16 + (size_t)(T / 32) * kSwB * 8;
-        FCD_REQUIRE(smem <= 200 * 1024, "fcd_estep_qR: N=%d needs %zu bytes of shared memory", N, smem);
-#define FCD_SWB(T_)                                                                                          \
+        // launch shape (scripts/sweep_bench.py, profiles/r02_sweep_shapes.txt): blocks of B = 16 regions
+        // everywhere (32 was measured, never faster).  Threads: 3 helper warps and FOUR CTAs per SM (25 KB of
+        // shared memory at N = 400) when the GPU has patients to fill them with -- every patient of the bench
+        // problem resident at once; 7 helper warps for mid-sized atlases or fewer patients; 15 (one CTA per SM)
+        // from ~700 regions on, where a patient's chain of blocks is what the launch lasts.
+        constexpr int B = 16;
+        int T = N >= 700 ? 512 : ((N <= 512 && Ul > 2 * sm_count()) ? 128 : 256);
+        while (T < 512 && sweep_blocked_smem(N, T, B) > (size_t)(T == 128 ? 54 : 110) * 1024) T *= 2;
+        static const int forced_T = [] {                      // FCD_SWEEP_T=128|256|512: launch-shape experiments
+            const char* e = getenv("FCD_SWEEP_T");
+            return e != nullptr ? atoi(e) : 0;
+        }();
+        if (forced_T == 128 || forced_T == 256 || forced_T == 512) T = forced_T;
+        const size_t smem = sweep_blocked_smem(N, T, B);
+        FCD_REQUIRE(smem <= kSmemBudget, "fcd_estep_qR: N=%d needs %zu bytes of shared memory", N, smem);
+#define FCD_SWB(T_, B_)                                                                                      \
         do {                                                                                                 \
             if (edge_lookup == FCD_LOOKUP_REFERENCE) {                                                       \
-                if (smem > 48 * 1024) FCD_ALLOW_BIG_SMEM(sweep_blocked_kernel<T_, FCD_LOOKUP_REFERENCE>);    \
-                sweep_blocked_kernel<T_, FCD_LOOKUP_REFERENCE><<<Ul, T_, smem, st>>>(WT, C, N, U, u0, lp0, lp1, qR, lqR); \
+                FCD_ALLOW_BIG_SMEM(sweep_blocked_kernel<T_, B_, FCD_LOOKUP_REFERENCE>);                      \
+                sweep_blocked_kernel<T_, B_, FCD_LOOKUP_REFERENCE><<<Ul, T_, smem, st>>>(WT, C, N, U, u0, lp0, lp1, qR, lqR); \
             } else {                                                                                         \
-                if (smem > 48 * 1024) FCD_ALLOW_BIG_SMEM(sweep_blocked_kernel<T_, FCD_LOOKUP_SYMMETRIC>);    \
-                sweep_blocked_kernel<T_, FCD_LOOKUP_SYMMETRIC><<<Ul, T_, smem, st>>>(WT, C, N, U, u0, lp0, lp1, qR, lqR); \
+                FCD_ALLOW_BIG_SMEM(sweep_blocked_kernel<T_, B_, FCD_LOOKUP_SYMMETRIC>);                      \
+                sweep_blocked_kernel<T_, B_, FCD_LOOKUP_SYMMETRIC><<<Ul, T_, smem, st>>>(WT, C, N, U, u0, lp0, lp1, qR, lqR); \
             }                                                                                                \
         } while (0)
-        if (T == 512) FCD_SWB(512);
-        else if (T == 256) FCD_SWB(256);
-        else FCD_SWB(128);
+        if (T == 512) FCD_SWB(512, 16);
+        else if (T == 256) FCD_SWB(256, 16);
+        else FCD_SWB(128, 16);
 #undef FCD_SWB
         return check_launch("fcd_estep_qR(blocked)");
     }

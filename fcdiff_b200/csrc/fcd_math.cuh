@@ -184,6 +184,33 @@ __device__ __forceinline__ double exp_nonpos(double d) {
     return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
 }
 
+// The same function with the polynomial in Estrin form: 4 dependent FMAs after the argument reduction
+// instead of 11 (for the one place where the exponential sits on a dependent chain: the in-block steps of
+// the blocked region sweep).  Same coefficients; the rounding differs from the Horner form by ~1e-16.
+__device__ __forceinline__ double exp_nonpos_short(double d) {
+    d = fmax(d, -700.0);
+    const double kMagic = 6755399441055744.0;                 // 1.5 * 2^52
+    const double t = fma(d, 1.4426950408889634074, kMagic);
+    const int n = __double2loint(t);
+    const double nd = t - kMagic;
+    double r = fma(nd, -6.93147180369123816490e-01, d);
+    r = fma(nd, -1.90821492927058770002e-10, r);
+    const double r2 = r * r;
+    const double p01 = 1.0 + r;
+    const double p23 = fma(r, 1.66666666666666666667e-01, 0.5);
+    const double p45 = fma(r, 8.33333333333333333333e-03, 4.16666666666666666667e-02);
+    const double p67 = fma(r, 1.98412698412698412698e-04, 1.38888888888888888889e-03);
+    const double p89 = fma(r, 2.75573192239858906526e-06, 2.48015873015873015873e-05);
+    const double pab = fma(r, 2.50521083854417187751e-08, 2.75573192239858906526e-07);
+    const double r4 = r2 * r2;
+    const double q0 = fma(r2, p23, p01);
+    const double q1 = fma(r2, p67, p45);
+    const double q2 = fma(r2, pab, p89);
+    const double r8 = r4 * r4;
+    const double p = fma(r8, q2, fma(r4, q1, q0));
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+
 #endif  // __CUDACC__
 
 }  // namespace fcd

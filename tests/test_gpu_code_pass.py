@@ -219,19 +219,25 @@ def test_patient_gather_staging_roundtrip(N, U, world):
     nptest.assert_array_equal(ob.cpu().numpy().reshape(N, U, 2), b)
 
 
-@pytest.mark.parametrize("N,U,lookup", [(37, 5, 0), (600, 3, 0), (600, 2, 1), (1100, 2, 0), (1400, 2, 1), (2100, 1, 0),
-                                        (530, 300, 0),              # U >= 2 x SMs: the compact launch shapes
-                                        # blocked forward substitution (N >= 64): whole / ragged last blocks, both
-                                        # lookups, the three thread counts, shared memory beyond 48 KB
-                                        (64, 9, 0), (65, 4, 1), (96, 3, 0), (100, 3, 1), (400, 6, 0), (400, 5, 1),
-                                        (3300, 1, 1)])
-def test_sweep_launch_shapes_match_numpy(N, U, lookup):
+@pytest.mark.parametrize("N,U,lookup,scale",
+                         [(37, 5, 0, 0.05), (600, 3, 0, 0.05), (600, 2, 1, 0.05), (1100, 2, 0, 0.05), (1400, 2, 1, 0.05),
+                          (2100, 1, 0, 0.05),
+                          (530, 300, 0, 0.05),              # U >= 2 x SMs: the compact launch shapes
+                          # blocked forward substitution (N >= 64): whole / ragged last blocks, both
+                          # lookups, the three thread counts, shared memory beyond 48 KB
+                          (64, 9, 0, 0.05), (65, 4, 1, 0.05), (96, 3, 0, 0.05), (100, 3, 1, 0.05), (400, 6, 0, 0.05),
+                          (400, 5, 1, 0.05), (3300, 1, 1, 0.05),
+                          # large weights: most regions come out decided (|l_0 - l_1| > 37.5, the short form of
+                          # the in-block step), a few do not
+                          (37, 5, 0, 2.0), (100, 3, 1, 2.0), (400, 6, 0, 2.0), (400, 5, 1, 2.0), (1100, 2, 0, 1.0),
+                          (600, 2, 1, 0.5)])
+def test_sweep_launch_shapes_match_numpy(N, U, lookup, scale):
     """Gauss-Seidel sweep of fit.py:184-197 over the two weight differences, for every launch shape of
     fcd_estep_qR (regions per thread / warps per patient depend on N), both edge lookups."""
     lib = _lib.load()
     rng = np.random.RandomState(N + U)
     C = N * (N - 1) // 2
-    WT = 0.05 * rng.randn(U, C + 1, 2)                       # {W_0 - W_2, W_2 - W_1}; one edge of slack (fit.py:186 quirk)
+    WT = scale * rng.randn(U, C + 1, 2)                      # {W_0 - W_2, W_2 - W_1}; one edge of slack (fit.py:186 quirk)
     q = rng.dirichlet([1.0, 1.0], size=(N, U))
     lp = np.log(np.array([0.7, 0.3]))
     WTd = _dev.upload(WT[:, :C].copy().reshape(-1))
