@@ -359,10 +359,13 @@ struct CodedAcc {
     double obj, ge, gh, prod, qa, qb;
 };
 
-// HESS: also the two sums of squares the Newton step needs (fcd_solver.cuh): qa over l < 2, qb over l = 2
+// HESS: also the two sums of squares the Newton step needs (fcd_solver.cuh): qa over l < 2, qb over l = 2.
+// The gradient weights are formed from the code in the ALU (it has the headroom; the shared-memory pipe,
+// with one 16-byte table read per element for {a_l, b_l} already, does not): sgn = -1, +1 for l = 0, 1 and
+// y = [l = 2] (codes 2, 4, 5) as the high words of 0 / +-1.0.  acc.ge collects sum sgn d only: the l = 2
+// part of sum s_l d is (2 eta - 1) acc.gh and is added once, after the plane.
 template <bool GRAD, bool FAST, bool HESS>
-__device__ __forceinline__ void coded_elem(double p, int code, const double2* s_ab, const double4* s_sh,
-                                           const double* s_tab, CodedAcc& acc) {
+__device__ __forceinline__ void coded_elem(double p, int code, const double2* s_ab, const double* s_tab, CodedAcc& acc) {
     const double2 ab = s_ab[code];
     const double M = fma(ab.y, p, ab.x);
     double rcp = 0.0;
@@ -375,14 +378,15 @@ __device__ __forceinline__ void coded_elem(double p, int code, const double2* s_
         acc.obj += fast_log<FAST>(M, s_tab);
     }
     if (GRAD) {
-        const double4 sh = s_sh[code];
         const double d = mix_num(p) * rcp;
-        acc.ge = fma(sh.x, d, acc.ge);
-        acc.gh = fma(sh.y, d, acc.gh);
+        const double sgn = __hiloint2double(code < 2 ? (code == 0 ? (int)0xbff00000 : 0x3ff00000) : 0, 0);
+        const double y = __hiloint2double(((0x34 >> code) & 1) * 0x3ff00000, 0);
+        const double t = sgn * d, v = y * d;
+        acc.ge += t;
+        acc.gh += v;
         if (HESS) {
-            const double dd = d * d;
-            acc.qa = fma(sh.z, dd, acc.qa);
-            acc.qb = fma(sh.y, dd, acc.qb);
+            acc.qa = fma(t, t, acc.qa);
+            acc.qb = fma(v, v, acc.qb);
         }
     }
 }
@@ -403,7 +407,6 @@ elm_coded_kernel(const double* __restrict__ PsE, const uint8_t* __restrict__ cod
     static_assert(!SOLVE || GRAD, "the solver needs the gradient sums");
     extern __shared__ __align__(128) double s_dyn[];
     __shared__ double2 s_ab[8];
-    __shared__ double4 s_sh[8];
     __shared__ double s_sums[kSolverVals];
     if (SOLVE && solver_finished(state, pub, seq)) return;
     SubTheta T;
@@ -425,13 +428,11 @@ elm_coded_kernel(const double* __restrict__ PsE, const uint8_t* __restrict__ cod
     if (lane < depth) mbar_init(bars + lane, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (threadIdx.x < 8) {
-        // per-code constants {a_l, b_l} and {s_l, [l == 2], [l < 2]}, s = (-1, 1, 2 eta - 1) (fit.py:600-697);
-        // code 3 is neutral: log(1 + 0 p) = 0 exactly, zero gradient weight; codes 4, 5 count as l = 2
+        // per-code constants {a_l, b_l}; code 3 is neutral: log(1 + 0 p) = 0 exactly (and zero gradient
+        // weight, coded_elem); the codes 4, 5 count as l = 2
         const int code = threadIdx.x;
         const int l = code >= 4 ? 2 : code;
-        const double sl = l == 0 ? -1.0 : (l == 1 ? 1.0 : 2.0 * T.eta - 1.0);
         s_ab[code] = l < 3 ? make_double2(sel3(l, T.al), sel3(l, T.bl)) : make_double2(1.0, 0.0);
-        s_sh[code] = l < 3 ? make_double4(sl, l == 2 ? 1.0 : 0.0, l < 2 ? 1.0 : 0.0, 0.0) : make_double4(0.0, 0.0, 0.0, 0.0);
     }
     __syncwarp();
 
@@ -511,8 +512,8 @@ elm_coded_kernel(const double* __restrict__ PsE, const uint8_t* __restrict__ cod
         for (int j = 0; j < kEvChunk / 64; ++j) {
             const double2 v = *reinterpret_cast<const double2*>(st + (64 * j + 2 * lane) * 8);
             const uint32_t c2 = *reinterpret_cast<const unsigned short*>(st + kEvChunk * 8 + 64 * j + 2 * lane);
-            coded_elem<GRAD, FAST, SOLVE>(v.x, c2 & 0xff, s_ab, s_sh, s_tab, a0);
-            coded_elem<GRAD, FAST, SOLVE>(v.y, c2 >> 8, s_ab, s_sh, s_tab, a1);
+            coded_elem<GRAD, FAST, SOLVE>(v.x, c2 & 0xff, s_ab, s_tab, a0);
+            coded_elem<GRAD, FAST, SOLVE>(v.y, c2 >> 8, s_ab, s_tab, a1);
         }
         nf += kEvChunk / 64;
         if (nf + kEvChunk / 64 > kProdMax) flush();
@@ -523,12 +524,13 @@ elm_coded_kernel(const double* __restrict__ PsE, const uint8_t* __restrict__ cod
         const unsigned char* st = ring + d * kEvStage;
         flush();
         for (int e = lane; e < left; e += 32)
-            coded_elem<GRAD, FAST, SOLVE>(reinterpret_cast<const double*>(st)[e], st[kEvChunk * 8 + e], s_ab, s_sh, s_tab, a0);
+            coded_elem<GRAD, FAST, SOLVE>(reinterpret_cast<const double*>(st)[e], st[kEvChunk * 8 + e], s_ab, s_tab, a0);
     }
     flush();
-    double obj = a0.obj + a1.obj, ge = a0.ge + a1.ge, gh = a0.gh + a1.gh, qa = a0.qa + a1.qa, qb = a0.qb + a1.qb;
     const double al[3] = {T.al[0], T.al[1], T.al[2]}, bl[3] = {T.bl[0], T.bl[1], T.bl[2]};
     const double sl[3] = {-1.0, 1.0, 2.0 * T.eta - 1.0};
+    double obj = a0.obj + a1.obj, gh = a0.gh + a1.gh, qa = a0.qa + a1.qa, qb = a0.qb + a1.qb;
+    double ge = fma(sl[2], gh, a0.ge + a1.ge);               // sum s_l d over the plane: l < 2 signed, l = 2 through gh
     for (; cp < nq01; advance()) {                           // records {p, w_0, w_1, w_2}: real weights, three logs each
         const long long left = (n3 - (cp - nq0) * kEvChunk) >> 2;
         const int cnt = (int)(left < kEvChunk / 4 ? left : kEvChunk / 4);
