@@ -329,6 +329,69 @@ def run_cfg4(fcdiff, _dev, shards, torch, dist, peak):
     return out
 
 
+def run_k1(fcdiff, torch, peaks):
+    """The stage in front of the fit in BASELINE.json configs[1], [2] ("1200-TR time series -> correlations ->
+    EM fit"; the reference starts at correlations, fcdiff/fit.py:20-23): Schaefer-400 x 1200 TRs x (500 + 500)
+    subjects, fp32 time series resident in HBM -> standardise -> split-TF32 Gram on tcgen05 -> Fisher z ->
+    edge-major (C, S) fp64 correlations (csrc/fcd_corr*.cu).  Tensor roofline: TF32 dense = half the measured
+    bf16 rate; the error-compensated product costs three MMAs, only the lower triangle is needed."""
+    from fcdiff_b200 import corr
+    (S, N, T) = (H_SUBJ + U_SUBJ, 400, 1200)
+    C = N * (N - 1) // 2
+    g = torch.Generator(device="cuda").manual_seed(1)
+    ts = torch.randn((S, N, T), dtype=torch.float32, device="cuda", generator=g)
+    out = torch.empty((C, S), dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        corr.correlations_device(ts, fisher=True, out=out)
+    (e0, e1) = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    R = 3
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(R):
+        corr.correlations_device(ts, fisher=True, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / R
+    useful = 2.0 * S * C * T                                   # one multiply-add per (edge, time point)
+    nt = (N + 127) // 128
+    tail = N - (nt - 1) * 128
+    tailpad = (tail + 15) // 16 * 16
+    cols = sum((tailpad if (ti == nt - 1 and tailpad < 128) else 128) for ti in range(nt) for tj in range(ti + 1))
+    issued = 3 * 2.0 * S * 128 * cols * ((T + 31) // 32 * 32)  # three MMAs per product over the computed tiles
+    tf32_peak = 0.5 * peaks.get("bf16_tflops", 2250.0)
+    res = {"workload": "Schaefer-400 x 1200 TRs x %d subjects: time series -> Fisher-z correlations" % S,
+           "ms": ms, "subjects_per_s": S / (ms * 1e-3),
+           "useful_tflops": useful / (ms * 1e-3) / 1e12, "issued_tf32_tflops": issued / (ms * 1e-3) / 1e12,
+           "roofline": {"bound": "tensor", "achieved": issued / (ms * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+                        "frac": issued / (ms * 1e-3) / 1e12 / tf32_peak,
+                        "peak_source": "half the measured dense bf16 rate (MEASURED_PEAKS.json bf16_tflops): TF32",
+                        "note": "issued = 3 MMAs (hh, hl, lh) x the tiles computed; useful = the lower triangle once"},
+           "includes": "standardise (fp64 mean / norm, TF32 hi / lo planes) + Gram + atanh epilogue"}
+    # configs[2] end to end from time series: K1, then one fit.run() on its output (device resident)
+    f = fcdiff.fit.UnsharedRegionFit()
+    f.model = fcdiff.UnsharedRegionModel()
+    (f.b, f.bt) = (out[:, :H_SUBJ].contiguous(), out[:, H_SUBJ:].contiguous())
+    f.max_iters = 3
+    f.run()                                                     # warm
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    corr.correlations_device(ts, fisher=True, out=out)
+    f = fcdiff.fit.UnsharedRegionFit()
+    f.model = fcdiff.UnsharedRegionModel()
+    (f.b, f.bt) = (out[:, :H_SUBJ].contiguous(), out[:, H_SUBJ:].contiguous())
+    f.max_iters = 3
+    f.rel_tol = -1.0
+    f.run()
+    torch.cuda.synchronize()
+    res["timeseries_to_fit_ms"] = 1e3 * (time.perf_counter() - t0)
+    res["timeseries_to_fit_what"] = ("K1 on %d subjects + fit.run() with 3 EM iterations on its output (white-noise "
+                                     "series: the fit has nothing to find, the time is what counts)" % S)
+    res["energy_finite"] = bool(np.all(np.isfinite(f.energy)))
+    del ts, out, f
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_cfg5(fcdiff, shards, torch, dist, n_replicas):
     """BASELINE.json configs[4]: Schaefer-400 x 1000 subjects, `n_replicas`-way group-label permutation
     sweep.  The responsibility planes are built once for all 1000 subjects; a replica selects its
@@ -584,6 +647,16 @@ def run_gpu_arm(args):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
+    # ---- K1 (time series -> correlations), one GPU: the stage in front of the fit in configs[1], [2]
+    k1 = None
+    if world == 1 and not args.no_k1:
+        b_host = bt_host = b_dev = bt_dev = None
+        torch.cuda.empty_cache()
+        try:
+            k1 = run_k1(fcdiff, torch, json.load(open(peaks_path)) if os.path.isfile(peaks_path) else {})
+        except Exception as exc:
+            k1 = {"error": "%s: %s" % (type(exc).__name__, exc)}
+
     # ---- configs[3] at this GPU count (strong scaling), all ranks take part
     cfg4 = None
     if not args.no_cfg4:
@@ -660,7 +733,7 @@ def run_gpu_arm(args):
         "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roofline, "roofline_estep": roofline_estep,
         "cpu_baseline": cpu, "steady_state": steady, "time_to_converge": converge, "kernels": kernels,
         "kernel_share_of_step": float(sum(k["total_ms"] for k in kernels.values()) / ms),
-        "parity": parity, "cfg4": cfg4, "cfg5": cfg5,
+        "parity": parity, "k1": k1, "cfg4": cfg4, "cfg5": cfg5,
         "energy_trace": [float(e) for e in energies],
     }
     _emit(json.dumps(line))
@@ -677,6 +750,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-k1", action="store_true", help="skip the K1 (time series -> correlations) block")
     ap.add_argument("--no-cfg4", action="store_true", help="skip the configs[3] (1000 regions x 2000 subjects) block")
     ap.add_argument("--replicas", type=int, default=1000,
                     help="relabelings of the configs[4] permutation sweep block (0 = skip)")

@@ -24,4 +24,5 @@ print("cpu", d["cpu_baseline"] and d["cpu_baseline"]["value"], d["clocks"])
 print("energies", d["energy_trace"])
 c=d.get("cfg4") or {}; print("cfg4", {k:v for k,v in c.items() if k not in ("kernels","energy_trace")})
 print("cfg5", d.get("cfg5"))
+print("k1", d.get("k1"))
 PY

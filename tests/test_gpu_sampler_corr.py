@@ -138,7 +138,11 @@ def test_joint_sample_matches_oracle_sampler_in_distribution():
 
 
 # ------------------------------------------------------------------ K1
-@pytest.mark.parametrize("S,N,T", [(1, 2, 2), (3, 6, 50), (5, 33, 97), (2, 90, 200), (4, 128, 256), (2, 130, 64)])
+@pytest.mark.parametrize("S,N,T", [(1, 2, 2), (3, 6, 50), (5, 33, 97), (2, 90, 200), (4, 128, 256), (2, 130, 64),
+                                   # tensor-core path: odd subject counts (a lone subject in the last pair), tail
+                                   # blocks of 2 / 16 / 72 rows (transposed tiles, UMMA N = 16 / 16 / 80), no tail,
+                                   # more work items than SMs (persistent CTAs, both TMEM buffers reused)
+                                   (5, 130, 64), (3, 272, 96), (7, 200, 128), (1, 256, 64), (61, 300, 40)])
 @pytest.mark.parametrize("fisher", [True, False])
 def test_corr_fisherz_vs_numpy(S, N, T, fisher):
     rng = np.random.RandomState(S * 1000 + N)
@@ -156,6 +160,21 @@ def test_corr_fisherz_vs_numpy(S, N, T, fisher):
     # tolerance of the stage (parity unpinned by the reference): fp32 inputs,
     # split-TF32 products with fp32 accumulation -> |dr| <= 2e-6
     nptest.assert_allclose(r_got, r_exp, rtol=0, atol=2e-6)
+
+
+def test_corr_config3_shape():
+    """BASELINE.json configs[2]'s time series: Schaefer-400, 1200 TRs (8 subjects of the 1000).  The fp32
+    accumulation over T / 8 = 150 MMAs per product bounds |dr| by 2.4e-6; N = 400 has a
+    16-row tail block."""
+    (S, N, T) = (8, 400, 1200)
+    rng = np.random.RandomState(7)
+    mix = rng.standard_normal((N, N)) * 0.2 + np.eye(N)
+    ts = np.einsum("nm,smt->snt", mix, rng.standard_normal((S, N, T))).astype(np.float32)
+    got = corr.correlations(ts, fisher=False)
+    exp = O.corr_fisherz(ts, fisher=False)
+    nptest.assert_allclose(got, exp, rtol=0, atol=2.4e-6)
+    z = corr.correlations(ts, fisher=True)
+    nptest.assert_allclose(np.tanh(z), exp, rtol=0, atol=2.4e-6)
 
 
 def test_corr_feeds_fit():
