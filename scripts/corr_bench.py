@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""K1 only (for ncu): one tensor-core correlation pass at a slice of config 3."""
+"""K1 only (for ncu and quick timing): tensor-core correlation passes at a slice of config 3.
+    python scripts/corr_bench.py [subjects] [regions] [time points]"""
 import os
 import sys
 
@@ -9,8 +10,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from fcdiff_b200 import corr          # noqa: E402
 
-ts = torch.randn((64, 400, 1200), dtype=torch.float32, device="cuda")
-for _ in range(2):
-    out = corr.correlations_device(ts, fisher=True)
+S = int(sys.argv[1]) if len(sys.argv) > 1 else 296
+N = int(sys.argv[2]) if len(sys.argv) > 2 else 400
+T = int(sys.argv[3]) if len(sys.argv) > 3 else 1200
+ts = torch.randn((S, N, T), dtype=torch.float32, device="cuda")
+out = corr.correlations_device(ts, fisher=True)
+(e0, e1) = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
 torch.cuda.synchronize()
-print("ok", out.shape)
+e0.record()
+for _ in range(3):
+    corr.correlations_device(ts, fisher=True, out=out)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 3
+print("S=%d N=%d T=%d: %.3f ms per pass (standardise + Gram), %.0f subjects/ms, useful %.1f TFLOP/s"
+      % (S, N, T, ms, S / ms, 2.0 * S * (N * (N - 1) // 2) * T / (ms * 1e-3) / 1e12))
