@@ -279,10 +279,10 @@ estep_qF_kernel(const double* __restrict__ S1, const double* __restrict__ S2,
 constexpr int kK2cSeg = 128;
 constexpr int kK2cStage = 2 * kK2cSeg * 8 + kK2cSeg;          // bytes: p_0, p_1, codes
 constexpr int kK2cMaxDepth = 5;
-constexpr size_t k2c_ring_bytes(int depth) { return (size_t)kStreamWarps * depth * (kK2cStage + 8); }
+constexpr size_t k2c_ring_bytes(int depth, int nw) { return (size_t)nw * depth * (kK2cStage + 8); }
 
-template <bool FAST>
-__global__ void __launch_bounds__(kStreamThreads, 1)
+template <bool FAST, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
 estep_qF_coded_kernel(const double* __restrict__ S1, const double* __restrict__ S2,
                       const double* __restrict__ P, int64_t planeStride, int64_t C, int U, int64_t pitchU,
                       const double* __restrict__ qR, const int32_t* __restrict__ nm,
@@ -296,7 +296,7 @@ estep_qF_coded_kernel(const double* __restrict__ S1, const double* __restrict__ 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* ring0 = reinterpret_cast<unsigned char*>(s_dyn + (FAST ? ((tab.n + 15) & ~15) : 0));
     unsigned char* ring = ring0 + (size_t)warp * depth * kK2cStage;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ring0 + (size_t)kStreamWarps * depth * kK2cStage) + warp * depth;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring0 + (size_t)NW * depth * kK2cStage) + warp * depth;
     // the ring starts zeroed: lanes beyond the copied bytes of a short segment read stale but finite
     // responsibilities (their code is forced to 3)
     for (int i = lane; i < depth * kK2cStage / 16; i += 32) reinterpret_cast<int4*>(ring)[i] = make_int4(0, 0, 0, 0);
@@ -312,32 +312,41 @@ estep_qF_coded_kernel(const double* __restrict__ S1, const double* __restrict__ 
     __syncwarp();
 
     const int nseg = (int)((pitchU + kK2cSeg - 1) / kK2cSeg);
-    const int64_t W = (int64_t)gridDim.x * kStreamWarps;
-    const int64_t c_first = (int64_t)blockIdx.x * kStreamWarps + warp;
+    const int64_t W = (int64_t)gridDim.x * NW;
+    const int64_t c_first = (int64_t)blockIdx.x * NW + warp;
     const uint32_t ring_s = smem_u32(ring), bars_s = smem_u32(bars);
-    int64_t pc = c_first;                                    // next (row, segment) to issue
+    // Issue side: running global pointers (lane 0), segment sizes known in advance -- a segment is a
+    // full 128 patients except the row's last one.
+    const uint32_t np_last = (uint32_t)(pitchU - (int64_t)(nseg - 1) * kK2cSeg);        // even, 2 .. 128
+    const uint32_t cb_last = (np_last + 15) & ~15u;                                      // pitchQ % 16 == 0
+    const int64_t skipP = W * pitchU - (int64_t)(nseg - 1) * kK2cSeg, skipC = W * pitchQ - (int64_t)(nseg - 1) * kK2cSeg;
+    const double* gp = P + c_first * pitchU;                 // next segment of plane 0 (meaningful in lane 0)
+    const uint8_t* gc = code + c_first * pitchQ;
+    int rows_to_issue = c_first < C ? (int)((C - c_first + W - 1) / W) : 0;
     int ps = 0, pd = 0;
     auto issue = [&]() {
-        if (pc >= C) return;
+        if (rows_to_issue <= 0) return;
+        const bool last = ps == nseg - 1;
         if (lane == 0) {
-            const int u0 = ps * kK2cSeg;
-            const uint32_t np = (uint32_t)(pitchU - u0 < kK2cSeg ? pitchU - u0 : kK2cSeg);      // even
-            const uint32_t cb = (np + 15) & ~15u;                                               // pitchQ % 16 == 0
+            const uint32_t np = last ? np_last : (uint32_t)kK2cSeg, cb = last ? cb_last : (uint32_t)kK2cSeg;
             const uint32_t st = ring_s + pd * kK2cStage, bar = bars_s + pd * 8;
-            const double* src = P + pc * pitchU + u0;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * np * 8 + cb) : "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(16 * np + cb) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(st), "l"(src), "r"(np * 8), "r"(bar) : "memory");
+                         ::"r"(st), "l"(gp), "r"(np * 8), "r"(bar) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(st + kK2cSeg * 8), "l"(src + planeStride), "r"(np * 8), "r"(bar) : "memory");
+                         ::"r"(st + kK2cSeg * 8), "l"(gp + planeStride), "r"(np * 8), "r"(bar) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(st + 2 * kK2cSeg * 8), "l"(code + pc * pitchQ + u0), "r"(cb), "r"(bar) : "memory");
+                         ::"r"(st + 2 * kK2cSeg * 8), "l"(gc), "r"(cb), "r"(bar) : "memory");
+            gp += last ? skipP : (int64_t)kK2cSeg;
+            gc += last ? skipC : (int64_t)kK2cSeg;
         }
-        if (++pd == depth) pd = 0;
-        if (++ps == nseg) {
+        pd = pd + 1 == depth ? 0 : pd + 1;
+        if (last) {
             ps = 0;
-            pc += W;
+            --rows_to_issue;
+        } else {
+            ++ps;
         }
     };
 #pragma unroll 1
@@ -408,7 +417,7 @@ estep_qF_coded_kernel(const double* __restrict__ S1, const double* __restrict__ 
         const int2 cnt = nxt_cnt;
         const longlong2 ro = nxt_ro;
         const bool listed = cnt.x != 3 * U && (cnt.x > 0 || cnt.y > 0);
-        int hu[2] = {-1, -1};
+        int hu[2] = {-1, -1}, hseg[2] = {-1, -1};
         double hq[2] = {0.0, 0.0}, hp0[2] = {0.0, 0.0}, hp1[2] = {0.0, 0.0};
         if (listed) {
 #pragma unroll
@@ -417,6 +426,7 @@ estep_qF_coded_kernel(const double* __restrict__ S1, const double* __restrict__ 
                 if (i < cnt.y) {
                     hu[k] = (int)(__ldg(keysH + ro.y + i) & 0xffffull);
                     hq[k] = __ldg(Hh + ro.y + i).y;
+                    hseg[k] = hu[k] / kK2cSeg;
                 }
             }
         }
@@ -424,39 +434,48 @@ estep_qF_coded_kernel(const double* __restrict__ S1, const double* __restrict__ 
             nxt_cnt = __ldg(counts + c + W);
             nxt_ro = __ldg(rowoff + c + W);                  // (garbage for rows without records: not used then)
         }
+        // two elements of the stage per lane: running products of the three template states' factors
+        auto pair = [&](const unsigned char* st, int j, uint32_t c2) {
+            const double2 a0 = *reinterpret_cast<const double2*>(st + (64 * j + 2 * lane) * 8);
+            const double2 a1 = *reinterpret_cast<const double2*>(st + kK2cSeg * 8 + (64 * j + 2 * lane) * 8);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const double2 k = s_lc[(c2 >> (8 * e)) & 0xff];
+                const double p0 = e ? a0.y : a0.x, p1 = e ? a1.y : a1.x;
+                const double p3[3] = {p0, p1, (1.0 - p0) - p1};
+                if (FAST) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) pr[e][i] *= fma(k.y, p3[i], k.x);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) acc[i] += log(fma(k.y, p3[i], k.x));
+                }
+            }
+        };
         for (int s = 0; s < nseg; ++s) {
             mbar_wait(bars + d, phase);
             const unsigned char* st = ring + d * kK2cStage;
+            const unsigned short* cs = reinterpret_cast<const unsigned short*>(st + 2 * kK2cSeg * 8) + lane;
+            if (s < nseg - 1 || np_last == (uint32_t)kK2cSeg) {          // a full segment (warp-uniform): no bounds
+                if (nf + kK2cSeg / 64 > kProdMax) flush();
 #pragma unroll
-            for (int j = 0; j < kK2cSeg / 64; ++j) {
-                if (s * kK2cSeg + 64 * j < pitchU) {         // warp-uniform
-                    const double2 a0 = *reinterpret_cast<const double2*>(st + (64 * j + 2 * lane) * 8);
-                    const double2 a1 = *reinterpret_cast<const double2*>(st + kK2cSeg * 8 + (64 * j + 2 * lane) * 8);
-                    // beyond pitchU the stage holds stale (finite) responsibilities: force their code to 3
-                    const bool in = s * kK2cSeg + 64 * j + 2 * lane < pitchU;
-                    const uint32_t c2 = in ? *reinterpret_cast<const unsigned short*>(st + 2 * kK2cSeg * 8 + 64 * j + 2 * lane)
-                                           : 0x0303u;
+                for (int j = 0; j < kK2cSeg / 64; ++j) pair(st, j, cs[32 * j]);
+                nf += kK2cSeg / 64;
+            } else {
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const double2 k = s_lc[(c2 >> (8 * e)) & 0xff];
-                        const double p0 = e ? a0.y : a0.x, p1 = e ? a1.y : a1.x;
-                        const double p3[3] = {p0, p1, (1.0 - p0) - p1};
-                        if (FAST) {
-#pragma unroll
-                            for (int i = 0; i < 3; ++i) pr[e][i] *= fma(k.y, p3[i], k.x);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 3; ++i) acc[i] += log(fma(k.y, p3[i], k.x));
-                        }
+                for (int j = 0; j < kK2cSeg / 64; ++j) {
+                    if (64 * j < (int)np_last) {                        // warp-uniform
+                        // beyond pitchU the stage holds stale (finite) responsibilities: force their code to 3
+                        pair(st, j, 64 * j + 2 * lane < (int)np_last ? (uint32_t)cs[32 * j] : 0x0303u);
+                        if (++nf == kProdMax) flush();
                     }
-                    if (++nf == kProdMax) flush();
                 }
             }
             // my half records that lie in this segment: p_0, p_1 straight from the stage
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                const int o = hu[k] - s * kK2cSeg;
-                if (o >= 0 && o < kK2cSeg) {
+                if (hseg[k] == s) {
+                    const int o = hu[k] - s * kK2cSeg;
                     hp0[k] = *reinterpret_cast<const double*>(st + o * 8);
                     hp1[k] = *reinterpret_cast<const double*>(st + kK2cSeg * 8 + o * 8);
                 }
@@ -1363,22 +1382,36 @@ int fcd_estep_qF_coded(const double* S1, const double* S2, int32_t H,
     FCD_REQUIRE(log_table_window(th.epsl, th.al, st, tab, true), "fcd_estep_qF_coded: log table initialisation failed");
     const bool fast = log_table_covers(th.epsl, th.al);
     const size_t tbytes = fast ? (size_t)((tab.n + 15) & ~15) * sizeof(double) : 0;
+    // 16 warps per SM (127 registers each).  FCD_K2C_WARPS=24 selects the 24-warp build (80 registers, three
+    // ring stages per warp): measured no faster (0.199 vs 0.193 ms at config 3) -- the kernel is bound by
+    // the instructions of its row-level work, not by the warps available to hide latency.
+    static const int forced_nw = [] {
+        const char* e = getenv("FCD_K2C_WARPS");
+        return e != nullptr ? atoi(e) : 0;
+    }();
+    int nw = 16;
+    if (forced_nw == 24 && tbytes + k2c_ring_bytes(2, 24) <= kSmemBudget) nw = 24;
     int depth = kK2cMaxDepth;
-    while (depth > 2 && tbytes + k2c_ring_bytes(depth) > kSmemBudget) --depth;
-    FCD_REQUIRE(tbytes + k2c_ring_bytes(depth) <= kSmemBudget, "fcd_estep_qF_coded: shared memory budget exceeded");
-    const size_t smem = tbytes + k2c_ring_bytes(depth);
-    int64_t grid = (C + kStreamWarps - 1) / kStreamWarps;
+    while (depth > 2 && tbytes + k2c_ring_bytes(depth, nw) > kSmemBudget) --depth;
+    FCD_REQUIRE(tbytes + k2c_ring_bytes(depth, nw) <= kSmemBudget, "fcd_estep_qF_coded: shared memory budget exceeded");
+    const size_t smem = tbytes + k2c_ring_bytes(depth, nw);
+    int64_t grid = (C + nw - 1) / nw;
     if (grid > sm_count()) grid = sm_count();                       // one persistent CTA per SM
-#define FCD_K2C(F)                                                                                    \
+#define FCD_K2C_(F, NW_)                                                                              \
     do {                                                                                              \
-        FCD_ALLOW_BIG_SMEM(estep_qF_coded_kernel<F>);                                                 \
-        estep_qF_coded_kernel<F><<<(unsigned)grid, kStreamThreads, smem, st>>>(                       \
+        FCD_ALLOW_BIG_SMEM(estep_qF_coded_kernel<F, NW_>);                                            \
+        estep_qF_coded_kernel<F, NW_><<<(unsigned)grid, NW_ * 32, smem, st>>>(                        \
             S1, S2, P, planeStride, C, U, pitchU, qR, nm, code, pitchQ, reinterpret_cast<const int2*>(counts), \
             reinterpret_cast<const unsigned long long*>(keysF), reinterpret_cast<const unsigned long long*>(keysH), \
             reinterpret_cast<const longlong2*>(rowoff), reinterpret_cast<const double2*>(Hh), th, tab, depth, lqF, qF); \
     } while (0)
+#define FCD_K2C(F)                                                                                    \
+    do {                                                                                              \
+        if (nw == 24) FCD_K2C_(F, 24); else FCD_K2C_(F, 16);                                          \
+    } while (0)
     if (fast) FCD_K2C(true); else FCD_K2C(false);
 #undef FCD_K2C
+#undef FCD_K2C_
     return check_launch("fcd_estep_qF_coded");
 }
 
