@@ -78,6 +78,12 @@ code_plane_kernel(const double* __restrict__ P, int64_t planeStride, double* __r
             if (k == kStateMixedF) {
                 for (int u = 2 * lane; u < pitchQ; u += 64) crow[u >> 1] = 0x0303;
                 cnt = 3 * U;
+                if (kcache[c] == 255) {                      // never gathered: the plane's row is uninitialised memory,
+                    double* dst = PsE + c * pitchQ;          // and the neutral code's factor 1 + 0 p needs a finite p
+                    for (int64_t u = 2 * lane; u < pitchU; u += 64) *reinterpret_cast<double2*>(dst + u) = make_double2(0.0, 0.0);
+                    __syncwarp();
+                    if (lane == 0) kcache[c] = 254;
+                }
             } else {
                 const int v = __ldg(nm + c);
                 if (k != kcache[c]) {                        // warp-uniform; rare once q_F has settled
@@ -362,7 +368,7 @@ struct CodedAcc {
 // HESS: also the two sums of squares the Newton step needs (fcd_solver.cuh): qa over l < 2, qb over l = 2.
 // The gradient weights are formed from the code in the ALU (it has the headroom; the shared-memory pipe,
 // with one 16-byte table read per element for {a_l, b_l} already, does not): sgn = -1, +1 for l = 0, 1 and
-// y = [l = 2] (codes 2, 4, 5) as the high words of 0 / +-1.0.  acc.ge collects sum sgn d only: the l = 2
+// y = [l = 2] (codes 2, 4, 5).  acc.ge collects sum sgn d only: the l = 2
 // part of sum s_l d is (2 eta - 1) acc.gh and is added once, after the plane.
 template <bool GRAD, bool FAST, bool HESS>
 __device__ __forceinline__ void coded_elem(double p, int code, const double2* s_ab, const double* s_tab, CodedAcc& acc) {
@@ -378,10 +384,14 @@ __device__ __forceinline__ void coded_elem(double p, int code, const double2* s_
         acc.obj += fast_log<FAST>(M, s_tab);
     }
     if (GRAD) {
-        const double d = mix_num(p) * rcp;
-        const double sgn = __hiloint2double(code < 2 ? (code == 0 ? (int)0xbff00000 : 0x3ff00000) : 0, 0);
-        const double y = __hiloint2double(((0x34 >> code) & 1) * 0x3ff00000, 0);
-        const double t = sgn * d, v = y * d;
+        // the weights as +-2.0 / 0 -- one nibble per code, shifted into the top of the high word (2.0 =
+        // 0x4000..., -2.0 = 0xC000...) -- against HALF the derivative factor: exact, three ALU
+        // instructions per weight
+        const double dh = fma(0.75, p, -0.25) * rcp;                      // mix_num(p) / 2 * rcp
+        const int sh = code << 2;
+        const double sgn2 = __hiloint2double((int)(((0x4cu >> sh) & 0xfu) << 28), 0);          // l = 0: -2, l = 1: +2
+        const double y2 = __hiloint2double((int)(((0x440400u >> sh) & 0xfu) << 28), 0);        // codes 2, 4, 5: 2
+        const double t = sgn2 * dh, v = y2 * dh;
         acc.ge += t;
         acc.gh += v;
         if (HESS) {

@@ -502,7 +502,9 @@ class UnsharedRegionFit(object):
                                               C * max(Ul, 1), None, _dev.stream()), "fcd_resp_cache")
             (pitchU, uu0, Us) = (Ul, 0, Ul)
         pitchC = _dev.even(C)                      # rows are moved by 16-byte-granular bulk copies
-        PT = _dev.zeros((3, max(Ul, 1), pitchC))
+        PT = _dev.empty((3, max(Ul, 1), pitchC))       # every edge column is written below; only the pad is zeroed
+        if pitchC != C or Ul == 0:
+            PT[:, :, C:].zero_() if Ul > 0 else PT.zero_()
         if Ul > 0:
             with _dev.timed(self.profile, "K0_transpose"):
                 for k in range(3):
@@ -540,7 +542,11 @@ class UnsharedRegionFit(object):
         stream = _dev.stream()
         pitchQ = int(lib.fcd_code_pitch(U))        # code rows 16-byte aligned; PsE shares the pitch
         if inp.get('PsE') is None:
-            inp['PsE'] = _dev.zeros((Cl, pitchQ))
+            # rows are gathered by the code pass (an unpeaked edge's row is zeroed there on first sight);
+            # the columns beyond U are read with the neutral code and only have to be finite
+            inp['PsE'] = _dev.empty((Cl, pitchQ))
+            if pitchQ > U:
+                inp['PsE'][:, U:].zero_()
             inp['kcE'] = torch.full((Cl,), 255, dtype=torch.uint8, device=_dev.device())
             inp['code'] = _dev.empty((Cl * pitchQ + 256,), torch.uint8)
             inp['bk_counts'] = _dev.empty((Cl, 2), torch.int32)      # {records, half records} per row
