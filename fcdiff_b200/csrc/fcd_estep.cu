@@ -562,9 +562,16 @@ pstar_refresh_kernel(const double* __restrict__ PT, int64_t planeStride, int Ul,
     const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c >= C) return;
     const int k = fstate[c];
-    if (k >= 3 || k == kcache[c]) return;
+    if ((k >= 3 ? 3 : k) == kcache[c]) return;
     const int per = (Ul + gridDim.y - 1) / gridDim.y;
     const int u1 = min(Ul, (int)(blockIdx.y + 1) * per);
+    if (k >= 3) {
+        // unpeaked edge: its column is marked with a negative "responsibility" -- the fused sweep, which reads
+        // nothing but this plane in its inner loop, takes the three-plane path for it (the other readers
+        // look at the edge's state first and never use the entry)
+        for (int u = blockIdx.y * per; u < u1; ++u) PsT[(int64_t)u * pitchC + c] = -1.0;
+        return;
+    }
     const double* src = PT + (int64_t)k * planeStride + c;
     // a thread that has to copy keeps eight loads in flight (the launch lasts as long as its slowest column)
     int u = blockIdx.y * per;
@@ -581,7 +588,7 @@ pstar_refresh_kernel(const double* __restrict__ PT, int64_t planeStride, int Ul,
 __global__ void __launch_bounds__(256)
 pstar_commit_kernel(const uint8_t* __restrict__ fstate, int64_t C, uint8_t* __restrict__ kcache) {
     const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (c < C && fstate[c] < 3) kcache[c] = fstate[c];
+    if (c < C) kcache[c] = fstate[c] < 3 ? fstate[c] : 3;
 }
 
 // ------------------------------------------------------------------- K2b/W
@@ -606,20 +613,21 @@ region_weights_kernel(const double* __restrict__ PT, int64_t planeStride,
     extern __shared__ __align__(16) double s_dyn[];
     const double* s_tab = load_log_table<FAST>(tab, s_dyn);
     // persistent CTAs over (patient, 1024-edge tile) work items: no wave tail, one table load per
-    // CTA.  The kernel is bound by load latency, so (a) with the dominant-state plane the
-    // responsibility is requested together with the edge's state, not after it (the address does
-    // not depend on the state; an unpeaked edge's value is simply not used), and (b) the loads of the
-    // CTA's next tile are in flight while the logs of the current one are taken.
-    const int64_t tiles_per_row = (C + 1023) / 1024;
-    const int64_t ntiles = tiles_per_row * Ul;
+    // CTA.  The kernel is bound by load latency, so (a) with the dominant-state plane ONE load per element
+    // says everything: the responsibility of a peaked edge, or the negative mark of an unpeaked one
+    // (fcd_pstar_refresh) -- no state byte is fetched; and (b) the loads of the CTA's next tile are in
+    // flight while the logs of the current one are taken.  Tile indices are 32-bit (the host checks the
+    // count): no 64-bit division per tile.
+    const unsigned tiles_per_row = (unsigned)((C + 1023) / 1024);
+    const unsigned ntiles = tiles_per_row * (unsigned)Ul;
     struct Tile {
         double pk[4];
         int ks[4];
     };
-    auto load = [&](int64_t t) {
+    auto load = [&](unsigned t) {
         Tile tl;
-        const int u = (int)(t / tiles_per_row);
-        const int64_t cbase = (t - (int64_t)u * tiles_per_row) * 1024;
+        const unsigned u = t / tiles_per_row;
+        const int64_t cbase = (int64_t)(t - u * tiles_per_row) * 1024;
         const double* row = PT + (int64_t)u * pitchC;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -627,18 +635,22 @@ region_weights_kernel(const double* __restrict__ PT, int64_t planeStride,
             tl.pk[j] = 0.0;
             tl.ks[j] = -1;
             if (t < ntiles && c < C) {
-                tl.ks[j] = __ldg(fstate + c);
-                if (PsT) tl.pk[j] = ldg_stream1(PsT + (int64_t)u * pitchC + c);
-                else if (tl.ks[j] < 3) tl.pk[j] = ldg_stream1(row + tl.ks[j] * planeStride + c);
+                if (PsT) {
+                    tl.pk[j] = ldg_stream1(PsT + (int64_t)u * pitchC + c);
+                    tl.ks[j] = 0;                             // (peaked or not: read off pk when it is used)
+                } else {
+                    tl.ks[j] = __ldg(fstate + c);
+                    if (tl.ks[j] < 3) tl.pk[j] = ldg_stream1(row + tl.ks[j] * planeStride + c);
+                }
             }
         }
         return tl;
     };
     Tile cur = load(blockIdx.x);
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    for (unsigned t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const Tile nxt = load(t + gridDim.x);
-        const int u = (int)(t / tiles_per_row);
-        const int64_t cbase = (t - (int64_t)u * tiles_per_row) * 1024;
+        const unsigned u = t / tiles_per_row;
+        const int64_t cbase = (int64_t)(t - u * tiles_per_row) * 1024;
         const double* row = PT + (int64_t)u * pitchC;
         double2* out = reinterpret_cast<double2*>(WT) + (int64_t)u * C;
 #pragma unroll
@@ -646,7 +658,7 @@ region_weights_kernel(const double* __restrict__ PT, int64_t planeStride,
             const int64_t c = cbase + threadIdx.x + 256 * j;
             if (cur.ks[j] < 0) continue;
             double w[3];
-            if (cur.ks[j] < 3) {
+            if (PsT ? cur.pk[j] >= 0.0 : cur.ks[j] < 3) {
 #pragma unroll
                 for (int l = 0; l < 3; ++l) w[l] = fast_log<FAST>(mix_rel(th, l, cur.pk[j]), s_tab);
             } else {
@@ -819,9 +831,9 @@ __device__ __forceinline__ int64_t sweep_edge(int n, int m, int64_t base_n) {
 }
 
 // q_R [Npad] | tiles [2 buffers][near, in-block][B x (B + 1)] | far sums [2][helper warps][B] | D [2][B]
-__host__ __device__ constexpr size_t sweep_blocked_smem(int N, int T, int B) {
+__host__ __device__ constexpr size_t sweep_blocked_smem(int N, int T, int B, int n7 = 0) {
     return (size_t)((N + 31) & ~31) * 16 + (size_t)4 * B * (B + 1) * 16 + (size_t)2 * (T / 32 - 1) * B * 8 +
-           (size_t)2 * B * 8;
+           (size_t)2 * B * 8 + (size_t)n7 * 8;
 }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -829,13 +841,63 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
                  ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
 
-template <int T, int B, int LOOKUP>
+// FUSED: no weight tensor.  The kernel reads the patient-major dominant-state plane PsT (8 bytes per
+// edge-patient instead of WT's 16, and no region_weights pass that writes them) and forms
+//     {W_0 - W_2, W_2 - W_1},  W_l = log(a_l + b_l p*)                       (peaked edge: fcd_region_weights)
+// where it needs them: the far loop is bound by the latency of its loads and has the issue slots.  An
+// unpeaked edge is marked by a NEGATIVE entry of PsT (fcd_pstar_refresh) and takes all three planes and q_F
+// (rare after the first E-step).  The logarithm uses a 7-bit rounded reciprocal (every fourth slot of the
+// 9-bit table: a quarter of the shared memory, so that four CTAs still fit an SM) and two more terms of
+// log1p: |u| <= 2^-8, truncation u^6 / 6 < 6e-16.
+struct SweepFusedArgs {
+    const double* PT;          // [3][Ul][pitchC] responsibility planes, patient-major (unpeaked edges)
+    int64_t planeStride;
+    int64_t pitchC;
+    const double* qF;          // [C][3]
+    double al[3], bl[3];
+    const double* tab;         // 9-bit table (all slots)
+    int lo7, n7;               // window in 7-bit slots
+};
+
+constexpr int kLogTab7Base = (1023 + kLogTabMinExp) << 7;
+
+template <bool FAST>
+__device__ __forceinline__ double sweep_log7(double y, const double* s_tab7) {
+    if (!FAST) return log(y);
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(y));                // MUFU.RCP64H
+    const int hi = (__double2hiint(r0) + (1 << 12)) & ~((1 << 13) - 1);
+    const double r7 = __hiloint2double(hi, 0);
+    const double u = fma(y, r7, -1.0);
+    // log1p(u) = u - u^2/2 + u^3/3 - u^4/4 + u^5/5
+    double q = fma(u, 0.2, -0.25);
+    q = fma(u, q, 1.0 / 3.0);
+    q = fma(u, q, -0.5);
+    return s_tab7[(hi >> 13) - kLogTab7Base] + fma(u * u, q, u);
+}
+
+// The weights of an UNPEAKED edge e of patient row ul: sum_k q_F[e,k] log(a_l + b_l p_k) (rare: kept out of line)
+template <bool FAST>
+__device__ __noinline__ double2 sweep_weights_unpeaked(const SweepFusedArgs& fa, int ul, int64_t e, const double* tab7) {
+    const double* pk = fa.PT + (int64_t)ul * fa.pitchC + e;
+    double w0 = 0.0, w1 = 0.0, w2 = 0.0;
+    for (int k = 0; k < 3; ++k) {
+        const double q = __ldg(fa.qF + e * 3 + k), pp = __ldg(pk + k * fa.planeStride);
+        w0 = fma(q, sweep_log7<FAST>(fma(fa.bl[0], pp, fa.al[0]), tab7), w0);
+        w1 = fma(q, sweep_log7<FAST>(fma(fa.bl[1], pp, fa.al[1]), tab7), w1);
+        w2 = fma(q, sweep_log7<FAST>(fma(fa.bl[2], pp, fa.al[2]), tab7), w2);
+    }
+    return make_double2(w0 - w2, w2 - w1);
+}
+
+template <int T, int B, int LOOKUP, bool FUSED, bool FAST>
 __global__ void __launch_bounds__(T, 512 / T)
 sweep_blocked_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int u0, double lp0, double lp1,
-                     double* __restrict__ qR, double* __restrict__ lqR) {
+                     double* __restrict__ qR, double* __restrict__ lqR, const __grid_constant__ SweepFusedArgs fa) {
     constexpr int NWH = T / 32 - 1, H = T - 32, Bp = B + 1, RH = kSwRH, TILE = B * Bp;
     constexpr int LB = B == 32 ? 5 : 4;
     static_assert(B == 16 || B == 32, "block of 16 or 32 regions");
+    static_assert(!FUSED || LOOKUP == FCD_LOOKUP_REFERENCE, "the fused form reads contiguous windows (reference lookup)");
     extern __shared__ __align__(16) double s_sweep[];
     double2* s_q = reinterpret_cast<double2*>(s_sweep);                    // [Npad] q_R of the moment
     const int Npad = (N + 31) & ~31;
@@ -844,9 +906,24 @@ sweep_blocked_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int
     double* s_D = s_part + 2 * NWH * B;                                    // [2][B] l_0 - l_1 of a solved block
     const int ul = blockIdx.x, u = u0 + ul;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const double2* Wu = reinterpret_cast<const double2*>(WT) + (int64_t)ul * C;     // {W_0 - W_2, W_2 - W_1}
+    using Elem = typename std::conditional<FUSED, double, double2>::type;  // what the far loop loads per edge
+    // WT form: {W_0 - W_2, W_2 - W_1} of this patient's edges; fused form: the patient's row of PsT
+    const Elem* Wu = reinterpret_cast<const Elem*>(WT) + (int64_t)ul * (FUSED ? fa.pitchC : C);
     const double2* qR2 = reinterpret_cast<const double2*>(qR);
     for (int m = tid; m < Npad; m += T) s_q[m] = m < N ? qR2[(int64_t)m * U + u] : make_double2(0.0, 0.0);
+    double* s_tab7 = s_D + 2 * B;                                          // [n7] -log r7 (fused form)
+    if (FUSED && FAST)
+        for (int i = tid; i < fa.n7; i += T) s_tab7[i] = fa.tab[(int64_t)(fa.lo7 + i) << 2];
+    const double* tab7 = s_tab7 - fa.lo7;
+    // weights of one edge from its dominant-state responsibility (fused form)
+    auto weights = [&](double pv, const double* addr) {
+        if (pv < 0.0)                                                      // unpeaked edge (marked by fcd_pstar_refresh)
+            return sweep_weights_unpeaked<FAST>(fa, ul, addr - reinterpret_cast<const double*>(Wu), tab7);
+        const double w0 = sweep_log7<FAST>(fma(fa.bl[0], pv, fa.al[0]), tab7);
+        const double w1 = sweep_log7<FAST>(fma(fa.bl[1], pv, fa.al[1]), tab7);
+        const double w2 = sweep_log7<FAST>(fma(fa.bl[2], pv, fa.al[2]), tab7);
+        return make_double2(w0 - w2, w2 - w1);
+    };
     __syncthreads();
     const double dlp = lp0 - lp1;
     const int nblocks = (N + B - 1) / B;
@@ -859,13 +936,17 @@ sweep_blocked_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int
         double2* tiles = s_tiles + (b & 1) * 2 * TILE;
         // (i) tiles: element e -> tile t (0 near, 1 in-block), row i, column j; lanes walk a row's columns
         // (contiguous edges: both tiles have m < n, where the two lookups agree)
-        for (int e = ht; e < 2 * B * B; e += H) {
-            const int t = e >> (2 * LB), i = (e >> LB) & (B - 1), j = e & (B - 1);
-            double2* dst = tiles + t * TILE + j * Bp + i;
-            const int n = n0 + i;
-            const bool live = i < nb && (t == 0 ? b > 0 : j < i);
-            if (live) cp_async16(dst, Wu + (int64_t)n * (n - 1) / 2 + (n0 - (t == 0 ? B : 0)) + j);
-            else *dst = make_double2(0.0, 0.0);
+        // (fused form: the tiles are formed after the far loop, from responsibilities the previous phase's
+        // prefetch has already brought into L2)
+        if constexpr (!FUSED) {
+            for (int e = ht; e < 2 * B * B; e += H) {
+                const int t = e >> (2 * LB), i = (e >> LB) & (B - 1), j = e & (B - 1);
+                double2* dst = tiles + t * TILE + j * Bp + i;
+                const int n = n0 + i;
+                const bool live = i < nb && (t == 0 ? b > 0 : j < i);
+                if (live) cp_async16(dst, Wu + (int64_t)n * (n - 1) / 2 + (n0 - (t == 0 ? B : 0)) + j);
+                else *dst = make_double2(0.0, 0.0);
+            }
         }
         // (ii) the rows of block b + 1 (what the NEXT prepare will read, one phase from now) into L2
         if (b + 1 < nblocks && lane == 0) {                                // (the instruction takes warp-uniform operands)
@@ -874,7 +955,7 @@ sweep_blocked_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int
             int64_t e1 = (int64_t)nl * (nl - 1) / 2 + (LOOKUP == FCD_LOOKUP_REFERENCE ? N : nl);
             if (e1 > C) e1 = C;
             const char* g0 = reinterpret_cast<const char*>(Wu + e0);
-            const int64_t bytes = (e1 - e0) * 16;
+            const int64_t bytes = ((e1 - e0) * (int64_t)sizeof(Elem)) & ~(int64_t)15;
             for (int64_t off = (int64_t)hw * 8192; off < bytes; off += (int64_t)NWH * 8192) {
                 const uint32_t sz = (uint32_t)(bytes - off < 8192 ? bytes - off : 8192);
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g0 + off), "r"(sz) : "memory");
@@ -894,15 +975,31 @@ sweep_blocked_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int
             for (int r = 0; r < RH; ++r) acc[r] = 0.0;
             // `masked` = false is the common case (a whole block of rows, a column outside the block): no
             // predicate per row -- a per-row predicate would cap the loads in flight at the 7 predicate registers
-            auto rows = [&](const double2* p, int stride, auto tri, auto masked, int lim, double2 q) {
+            auto rows = [&](const Elem* p, int stride, auto tri, auto masked, int lim, double2 q) {
                 p += h * stride + (decltype(tri)::value ? h * (h - 1) / 2 : 0);
+                // base(n0 + h + r) - base(n0 + h) = r (n0 + h) + r (r - 1) / 2
+                auto off = [&](int r) {
+                    return r * (stride + (decltype(tri)::value ? h : 0)) + (decltype(tri)::value ? r * (r - 1) / 2 : 0);
+                };
+                if constexpr (FUSED) {
+                    double v[RH];                                          // all loads first, then the logarithms
 #pragma unroll
-                for (int r = 0; r < RH; ++r) {
-                    if (!decltype(masked)::value || h + r < lim) {
-                        // base(n0 + h + r) - base(n0 + h) = r (n0 + h) + r (r - 1) / 2
-                        const double2 w = __ldg(p + (r * (stride + (decltype(tri)::value ? h : 0)) +
-                                                     (decltype(tri)::value ? r * (r - 1) / 2 : 0)));
-                        acc[r] = fma(q.x, w.x, fma(q.y, w.y, acc[r]));    // (fit.py:188-190) - (fit.py:192-194)
+                    for (int r = 0; r < RH; ++r)
+                        if (!decltype(masked)::value || h + r < lim) v[r] = __ldg(p + off(r));
+#pragma unroll
+                    for (int r = 0; r < RH; ++r) {
+                        if (!decltype(masked)::value || h + r < lim) {
+                            const double2 w = weights(v[r], p + off(r));
+                            acc[r] = fma(q.x, w.x, fma(q.y, w.y, acc[r]));
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < RH; ++r) {
+                        if (!decltype(masked)::value || h + r < lim) {
+                            const double2 w = __ldg(p + off(r));
+                            acc[r] = fma(q.x, w.x, fma(q.y, w.y, acc[r]));    // (fit.py:188-190) - (fit.py:192-194)
+                        }
                     }
                 }
             };
@@ -911,7 +1008,7 @@ sweep_blocked_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int
                 if (mb == b - 1) continue;                                 // near: the solver's (new q_R of block b - 1)
                 const double2 q = s_q[m];
                 const bool tri = LOOKUP == FCD_LOOKUP_REFERENCE || m < n0;
-                const double2* p = tri ? Wu + base0 + m : Wu + (int64_t)m * (m - 1) / 2 + n0;
+                const Elem* p = tri ? Wu + base0 + m : Wu + (int64_t)m * (m - 1) / 2 + n0;
                 if (mb != b && nb == B) {
                     if (tri) rows(p, n0, yes(), no(), B, q);
                     else rows(p, 1, no(), no(), B, q);
@@ -937,7 +1034,17 @@ sweep_blocked_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int
             }
             if (lane < RH) s_part[((b & 1) * NWH + hw) * B + h + lane] = acc[0];
         }
-        asm volatile("cp.async.wait_all;" ::: "memory");
+        if constexpr (FUSED) {
+            for (int e = ht; e < 2 * B * B; e += H) {
+                const int t = e >> (2 * LB), i = (e >> LB) & (B - 1), j = e & (B - 1);
+                const int n = n0 + i;
+                const bool live = i < nb && (t == 0 ? b > 0 : j < i);
+                const double* src = reinterpret_cast<const double*>(Wu + (int64_t)n * (n - 1) / 2 + (n0 - (t == 0 ? B : 0)) + j);
+                tiles[t * TILE + j * Bp + i] = live ? weights(__ldg(src), src) : make_double2(0.0, 0.0);
+            }
+        } else {
+            asm volatile("cp.async.wait_all;" ::: "memory");
+        }
     };
 
     // ---- solve(b): warp 0 only (B = 16: lanes 16.. mirror lanes 0..15)
@@ -1456,6 +1563,8 @@ int fcd_region_weights(const double* PT, int64_t planeStride, int32_t Ul, int64_
     LogTabWindow tab;
     FCD_REQUIRE(log_table_window(th.epsl, th.al, st, tab), "fcd_region_weights: log table initialisation failed");
     int64_t ntiles = ((C + 1023) / 1024) * (int64_t)Ul;
+    FCD_REQUIRE(ntiles < ((int64_t)1 << 31) - 8 * sm_count(), "fcd_region_weights: %lld tiles exceed the 32-bit tile index",
+                (long long)ntiles);
     if (log_table_covers(th.epsl, th.al)) {
         int per_sm = (int)((200 * 1024) / (tab.bytes() + 1024));
         if (per_sm > 8) per_sm = 8;
@@ -1512,14 +1621,16 @@ int fcd_estep_qR(const double* WT, int64_t C, int32_t N, int32_t U, int32_t u0, 
         if (forced_T == 128 || forced_T == 256 || forced_T == 512) T = forced_T;
         const size_t smem = sweep_blocked_smem(N, T, B);
         FCD_REQUIRE(smem <= kSmemBudget, "fcd_estep_qR: N=%d needs %zu bytes of shared memory", N, smem);
+        SweepFusedArgs nofuse;
+        memset(&nofuse, 0, sizeof(nofuse));
 #define FCD_SWB(T_, B_)                                                                                      \
         do {                                                                                                 \
             if (edge_lookup == FCD_LOOKUP_REFERENCE) {                                                       \
-                FCD_ALLOW_BIG_SMEM(sweep_blocked_kernel<T_, B_, FCD_LOOKUP_REFERENCE>);                      \
-                sweep_blocked_kernel<T_, B_, FCD_LOOKUP_REFERENCE><<<Ul, T_, smem, st>>>(WT, C, N, U, u0, lp0, lp1, qR, lqR); \
+                FCD_ALLOW_BIG_SMEM(sweep_blocked_kernel<T_, B_, FCD_LOOKUP_REFERENCE, false, false>);                      \
+                sweep_blocked_kernel<T_, B_, FCD_LOOKUP_REFERENCE, false, false><<<Ul, T_, smem, st>>>(WT, C, N, U, u0, lp0, lp1, qR, lqR, nofuse); \
             } else {                                                                                         \
-                FCD_ALLOW_BIG_SMEM(sweep_blocked_kernel<T_, B_, FCD_LOOKUP_SYMMETRIC>);                      \
-                sweep_blocked_kernel<T_, B_, FCD_LOOKUP_SYMMETRIC><<<Ul, T_, smem, st>>>(WT, C, N, U, u0, lp0, lp1, qR, lqR); \
+                FCD_ALLOW_BIG_SMEM(sweep_blocked_kernel<T_, B_, FCD_LOOKUP_SYMMETRIC, false, false>);                      \
+                sweep_blocked_kernel<T_, B_, FCD_LOOKUP_SYMMETRIC, false, false><<<Ul, T_, smem, st>>>(WT, C, N, U, u0, lp0, lp1, qR, lqR, nofuse); \
             }                                                                                                \
         } while (0)
         if (T == 512) FCD_SWB(512, 16);
@@ -1569,8 +1680,8 @@ int fcd_estep_qR_fused(const double* PsT, const double* PT, int64_t planeStride,
                        double* qR, double* lqR, void* stream) {
     FCD_REQUIRE(PsT != nullptr && PT != nullptr && qF != nullptr && fstate != nullptr && log_pi2_host != nullptr &&
                 theta_host != nullptr && qR != nullptr && lqR != nullptr, "fcd_estep_qR_fused: NULL argument");
-    FCD_REQUIRE(N >= 3 && N <= 1024 && C == (int64_t)N * (N - 1) / 2,
-                "fcd_estep_qR_fused: needs 3 <= N <= 1024 and C = N(N-1)/2 (got N=%d, C=%lld)", N, (long long)C);
+    FCD_REQUIRE(N >= 3 && N <= 8192 && C == (int64_t)N * (N - 1) / 2,
+                "fcd_estep_qR_fused: needs 3 <= N <= 8192 and C = N(N-1)/2 (got N=%d, C=%lld)", N, (long long)C);
     FCD_REQUIRE(u0 >= 0 && Ul >= 0 && u0 + Ul <= U, "fcd_estep_qR_fused: bad patient range");
     FCD_REQUIRE(pitchC >= C && pitchC % 2 == 0 && pitchF >= pitchC && pitchF % 16 == 0 &&
                 ((reinterpret_cast<uintptr_t>(PsT) | reinterpret_cast<uintptr_t>(fstate)) & 15) == 0,
@@ -1583,6 +1694,52 @@ int fcd_estep_qR_fused(const double* PsT, const double* PT, int64_t planeStride,
     const bool fast = log_table_covers(th.epsl, th.al);
     const size_t tbytes = fast ? (size_t)((tab.n + 15) & ~15) * sizeof(double) : 0;
     const double lp0 = log_pi2_host[0], lp1 = log_pi2_host[1];
+    static const bool ring_form = [] {                       // FCD_SWEEP=ring: the shared-memory-ring kernel everywhere
+        const char* e = getenv("FCD_SWEEP");
+        return e != nullptr && strcmp(e, "ring") == 0;
+    }();
+    if (N >= 64 && !ring_form) {
+        // blocked forward substitution with the weights formed in the far loop (sweep_blocked_kernel<FUSED>)
+        constexpr int B = 16;
+        SweepFusedArgs fa;
+        fa.PT = PT;
+        fa.planeStride = planeStride;
+        fa.pitchC = pitchC;
+        fa.qF = qF;
+        for (int l = 0; l < 3; ++l) {
+            fa.al[l] = th.al[l];
+            fa.bl[l] = th.bl[l];
+        }
+        fa.tab = tab.g;
+        fa.lo7 = fast ? tab.lo >> 2 : 0;
+        fa.n7 = fast ? ((tab.lo + tab.n + 3) >> 2) - fa.lo7 : 0;
+        int T = N >= 700 ? 512 : ((N <= 512 && Ul > 2 * sm_count()) ? 128 : 256);
+        while (T < 512 && sweep_blocked_smem(N, T, B, fa.n7) > (size_t)(T == 128 ? 54 : 110) * 1024) T *= 2;
+        static const int forced_T = [] {
+            const char* e = getenv("FCD_SWEEP_T");
+            return e != nullptr ? atoi(e) : 0;
+        }();
+        if (forced_T == 128 || forced_T == 256 || forced_T == 512) T = forced_T;
+        const size_t smem = sweep_blocked_smem(N, T, B, fa.n7);
+        FCD_REQUIRE(smem <= kSmemBudget, "fcd_estep_qR_fused: N=%d needs %zu bytes of shared memory", N, smem);
+#define FCD_SWBF(T_, F_)                                                                                     \
+        do {                                                                                                 \
+            FCD_ALLOW_BIG_SMEM(sweep_blocked_kernel<T_, B, FCD_LOOKUP_REFERENCE, true, F_>);                 \
+            sweep_blocked_kernel<T_, B, FCD_LOOKUP_REFERENCE, true, F_><<<Ul, T_, smem, st>>>(               \
+                PsT, C, N, U, u0, lp0, lp1, qR, lqR, fa);                                                    \
+        } while (0)
+#define FCD_SWBF_T(F_)                                                                                       \
+        do {                                                                                                 \
+            if (T == 512) FCD_SWBF(512, F_);                                                                 \
+            else if (T == 256) FCD_SWBF(256, F_);                                                            \
+            else FCD_SWBF(128, F_);                                                                          \
+        } while (0)
+        if (fast) FCD_SWBF_T(true); else FCD_SWBF_T(false);
+#undef FCD_SWBF_T
+#undef FCD_SWBF
+        return check_launch("fcd_estep_qR_fused(blocked)");
+    }
+    FCD_REQUIRE(N <= 1024, "fcd_estep_qR_fused: the ring form needs N <= 1024 (got %d)", N);
 #define FCD_SWF(T, TC, PPC, RR, F)                                                                      \
     do {                                                                                                \
         const size_t smem = tbytes + (size_t)(PPC) * SweepSmem<T, RR>::padded;                          \

@@ -977,7 +977,7 @@ class UnsharedRegionFit(object):
         if inp.get('PsT') is None:                 # dominant-state plane, gathered on first use (q_F settles early)
             inp['PsT'] = _dev.empty((max(Ul, 1), pitchC))
             inp['kcache'] = torch.full((max(C, 1),), 255, dtype=torch.uint8, device=_dev.device())
-        if lookup == 0 and 3 <= N <= 1024 and self.fused_sweep:
+        if lookup == 0 and 3 <= N <= 8192 and self.fused_sweep:
             # every edge's weights are computed once inside the sweep and kept in a shared-memory ring: no WT tensor
             with _dev.timed(self.profile, "K2b_sweep_fused"):
                 _lib.check(lib.fcd_pstar_refresh(_dev.ptr(PT), max(Ul, 1) * pitchC, Ul, C, pitchC, _dev.ptr(fstate),

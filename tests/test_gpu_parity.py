@@ -333,7 +333,10 @@ def _oracle_state(b, bt, th, seed, peaked=False):
 
 
 @pytest.mark.parametrize("N,H,U", [(3, 1, 1), (4, 2, 3), (7, 5, 9), (10, 20, 20), (33, 17, 31), (40, 64, 128),
-                                   (24, 8, 300)])
+                                   (24, 8, 300),
+                                   # N >= 64: the blocked sweep, and its fused form (weights formed in the far loop;
+                                   # unpeaked edges -- peaked = False -- take its three-plane path)
+                                   (70, 4, 9), (100, 3, 33)])
 @pytest.mark.parametrize("lookup", ["reference", "symmetric"])
 @pytest.mark.parametrize("peaked", [False, True])
 def test_fused_steps_vs_oracle(N, H, U, lookup, peaked):
