@@ -1542,7 +1542,9 @@ int fcd_pstar_refresh(const double* PT, int64_t planeStride, int32_t Ul, int64_t
     FCD_REQUIRE(C >= 0 && Ul >= 0 && pitchC >= C, "fcd_pstar_refresh: bad shape");
     if (C == 0 || Ul == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 rgrid((unsigned)((C + 255) / 256), (unsigned)(Ul < 64 ? Ul : 64));
+    // (in most iterations no edge changes its state and every CTA leaves at once: 16 slices of the patients, not
+    // 64, keep that launch short -- 20,000 CTAs took 41 us to do nothing; a thread that does copy has Ul / 16 rows)
+    dim3 rgrid((unsigned)((C + 255) / 256), (unsigned)(Ul < 16 ? Ul : 16));
     pstar_refresh_kernel<<<rgrid, 256, 0, st>>>(PT, planeStride, Ul, C, pitchC, fstate, kcache, PsT);
     int rc = check_launch("fcd_pstar_refresh");
     if (rc) return rc;
