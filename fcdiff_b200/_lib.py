@@ -45,6 +45,8 @@ SIGNATURES = {
     "fcd_host_result_alloc": (c_int, [POINTER(c_void_p)]),
     "fcd_host_result_free": (c_int, [_P]),
     "fcd_allreduce_small": (c_int, [_P, c_int32, POINTER(c_void_p), c_int32, c_int32, c_uint64, _P, _P]),
+    "fcd_allreduce_small_keep": (c_int, [_P, c_int32, c_int32, c_int32, POINTER(c_void_p), c_int32, c_int32, c_uint64,
+                                         _P, _P]),
     "fcd_wait_result": (c_int, [_P, c_int32, c_uint64, _P, c_int32]),
     "fcd_pack_patients": (c_int, [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     "fcd_unpack_patients": (c_int, [_P, c_int32, c_int32, c_int32, c_int32, _P, _P, _P]),

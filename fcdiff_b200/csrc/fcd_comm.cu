@@ -27,12 +27,20 @@ namespace fcd {
 // result_host: [kCommMaxVals] doubles followed by one 64-bit flag (= seq, or seq | timeout bit).
 // `seq` names the PUBLICATION (what the host waits for); the slot sets of the windows follow the
 // rank's own exchange counter (fcd_comm.cuh).
+// keep0, nkeep: this rank's OWN values vec[keep0 .. keep0 + nkeep) (before the sum) are published behind the
+// n sums -- one publication then answers "what is the total" and "what is my share" (the record counts of the
+// code pass: the total decides the kernel form on all ranks alike, the share sizes this rank's lists).
 __global__ void __launch_bounds__(kCommMaxWorld* kCommMaxVals)
-allreduce_small_kernel(double* __restrict__ vec, int n, const __grid_constant__ CommPeers peers, int rank, int world,
-                       unsigned long long seq, double* __restrict__ result_host, long long spin_cycles) {
+allreduce_small_kernel(double* __restrict__ vec, int n, int keep0, int nkeep, const __grid_constant__ CommPeers peers,
+                       int rank, int world, unsigned long long seq, double* __restrict__ result_host,
+                       long long spin_cycles) {
     __shared__ double s_vals[kCommMaxVals];
     const int t = threadIdx.x;
     if (t < n) s_vals[t] = vec[t];
+    if (t < nkeep) {
+        st_relaxed_sys(result_host + n + t, vec[keep0 + t]);
+        __threadfence_system();
+    }
     __syncthreads();
     const bool ok = comm_exchange_cta(s_vals, n, peers, rank, world, spin_cycles);
     if (t < n) {                                              // publish (a timed-out exchange leaves vec as it was)
@@ -163,8 +171,24 @@ int fcd_allreduce_small(double* vec, int32_t n, void* const* windows_host, int32
     FCD_CUDA(cudaHostGetDevicePointer((void**)&result_dev, result_host, 0), "fcd_allreduce_small(cudaHostGetDevicePointer)");
     const long long spin_cycles = kCommSpinCycles;
     allreduce_small_kernel<<<1, kCommMaxWorld * kCommMaxVals, 0, (cudaStream_t)stream>>>(
-        vec, n, peers, rank, world, (unsigned long long)seq, result_dev, spin_cycles);
+        vec, n, 0, 0, peers, rank, world, (unsigned long long)seq, result_dev, spin_cycles);
     return check_launch("fcd_allreduce_small");
+}
+
+int fcd_allreduce_small_keep(double* vec, int32_t n, int32_t keep0, int32_t nkeep, void* const* windows_host,
+                             int32_t rank, int32_t world, uint64_t seq, double* result_host, void* stream) {
+    FCD_REQUIRE(vec != nullptr && result_host != nullptr, "fcd_allreduce_small_keep: NULL argument");
+    FCD_REQUIRE(n >= 1 && nkeep >= 0 && keep0 >= 0 && n + nkeep <= kCommMaxVals && keep0 + nkeep <= kCommMaxVals &&
+                world >= 1 && world <= kCommMaxWorld && rank >= 0 && rank < world && seq >= 1 &&
+                (seq & kCommTimeoutBit) == 0, "fcd_allreduce_small_keep: bad shape");
+    CommPeers peers;
+    FCD_REQUIRE(comm_peers_from_host(windows_host, world, peers), "fcd_allreduce_small_keep: NULL window");
+    double* result_dev = nullptr;
+    FCD_CUDA(cudaHostGetDevicePointer((void**)&result_dev, result_host, 0),
+             "fcd_allreduce_small_keep(cudaHostGetDevicePointer)");
+    allreduce_small_kernel<<<1, kCommMaxWorld * kCommMaxVals, 0, (cudaStream_t)stream>>>(
+        vec, n, keep0, nkeep, peers, rank, world, (unsigned long long)seq, result_dev, kCommSpinCycles);
+    return check_launch("fcd_allreduce_small_keep");
 }
 
 int fcd_pack_patients(const double* lqR, const double* qR, int32_t N, int32_t U, int32_t u0, int32_t Ul, int32_t ch,

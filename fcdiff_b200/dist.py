@@ -123,6 +123,17 @@ class PeerWindow(object):
             self._check(rc, "fcd_allreduce_small")
         return (self.seq, n)
 
+    def allreduce_keep(self, vec_dev, n, keep0, nkeep, stream):
+        """``allreduce`` of ``vec_dev[:n]``; returns the n sums followed by this rank's own
+        ``vec_dev[keep0:keep0 + nkeep]`` as they were before the sum (one publication, one wait)."""
+        self.bind_stream(stream)
+        self.seq += 1
+        rc = self.lib.fcd_allreduce_small_keep(self._ct.c_void_p(vec_dev.data_ptr()), n, keep0, nkeep, self.windows,
+                                               self.rank, self.world, self.seq, self._result, stream)
+        if rc != 0:
+            self._check(rc, "fcd_allreduce_small_keep")
+        return self.allreduce_end((self.seq, n + nkeep))
+
     def allreduce_end(self, ticket):
         (seq, n) = ticket
         rc = self.lib.fcd_wait_result(self._result, n, seq, self._out_p, self.TIMEOUT_MS)
@@ -180,6 +191,15 @@ class EdgeShards(object):
             return pw.allreduce(res.dev, n, _dev.stream() if stream is None else stream)
         dist.all_reduce(res.dev, op=dist.ReduceOp.SUM, group=self.group)
         return res.read(stream)
+
+    def reduce_read_keep(self, res, n, keep0, nkeep, stream=None):
+        """``reduce_read`` of ``res.dev[:n]`` that also returns this rank's own ``res.dev[keep0:keep0 + nkeep]``
+        (before the sum) behind the sums, or None where no peer window exists."""
+        pw = self.peer_window()
+        if pw is None or n + nkeep > pw.max_vals:
+            return None
+        from . import _dev
+        return pw.allreduce_keep(res.dev, n, keep0, nkeep, _dev.stream() if stream is None else stream)
 
     def reduce_begin(self, res, n=None, stream=None):
         """``reduce_read`` in two halves (peer window only): enqueue now, collect later."""

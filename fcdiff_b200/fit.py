@@ -533,6 +533,12 @@ class UnsharedRegionFit(object):
         (c0, Cl, pitchU) = (inp['c0'], inp['Cl'], inp['pitchU'])
         inp['code_verR'] = None                     # the key lists are rebuilt below (or not at all)
         if Cl == 0:
+            slot = self._tot_slot
+            self._tot_slot = None
+            if slot is not None and self.shards is not None:
+                # no edges here, but the other ranks wait for this rank in the exchange that carries the K3a sums
+                slot[0].dev[slot[1]:slot[1] + 2].zero_()
+                self._mstep_vals = self.shards.reduce_read_keep(slot[0], slot[1], slot[1], 2)
             if agree and self.shards is not None and self.elm_path != "tiered":
                 self.shards.any_rank(True)     # keep the collective sequence of _build_streams aligned
             return None
@@ -565,6 +571,10 @@ class UnsharedRegionFit(object):
                 _dev.ptr(tot_dev), stream), "fcd_code_plane")
         if slot is None:
             (nd, nh) = (int(v) for v in tot.read(stream))
+        elif self.shards is not None:
+            # ONE exchange: the K3a sums of all ranks [0:k] and, behind them, this rank's own record counts
+            self._mstep_vals = self.shards.reduce_read_keep(slot[0], slot[1], slot[1], 2, stream)
+            (nd, nh) = (int(v) for v in self._mstep_vals[slot[1]:slot[1] + 2])
         else:
             self._mstep_vals = slot[0].read(stream)
             (nd, nh) = (int(v) for v in self._mstep_vals[slot[1]:slot[1] + 2])
@@ -1064,9 +1074,21 @@ class UnsharedRegionFit(object):
             _lib.check(lib.fcd_mstep_stats(_dev.ptr(lqF), Cl, _dev.ptr(lqR), NU, _dev.ptr(out),
                                            _dev.ptr(_dev.workspace()), _dev.stream()), "fcd_mstep_stats")
         if do_gamma and self.shards is not None and self._in is not None:
-            red = self.shards.reduce_read(res, 5)
-            if between is not None:
-                between()
+            if between is not None and self.shards.peer_window() is not None:
+                # the code pass is enqueued behind K3a and its record counts ride the same exchange as the
+                # four sums (fcd_allreduce_small_keep): one host wait instead of two
+                self._mstep_vals = None
+                self._tot_slot = (res, 4)
+                try:
+                    between()
+                finally:
+                    self._tot_slot = None
+                red = self._mstep_vals[:4].copy() if self._mstep_vals is not None else self.shards.reduce_read(res, 4)
+                self._mstep_vals = None
+            else:
+                red = self.shards.reduce_read(res, 5)
+                if between is not None:
+                    between()
             return self.shards.fix_replicated(red, (0, 1, 2)), C, NU
         self._mstep_vals = None
         if between is not None:

@@ -100,6 +100,12 @@ FCD_API int fcd_host_result_alloc(void** result_out_host);
 FCD_API int fcd_host_result_free(void* result_host);
 FCD_API int fcd_allreduce_small(double* vec, int32_t n, void* const* windows_host, int32_t rank, int32_t world,
                         uint64_t seq, double* result_host, void* stream);
+/* The same exchange; behind the n sums, result_host also receives this rank's OWN values
+ * vec[keep0 .. keep0 + nkeep) as they were before the sum (n + nkeep <= fcd_comm_max_vals()): one wait
+ * serves the M-step sums of fit.py:208-220, the record counts of all ranks (total: which form the
+ * (eta, epsilon) evaluations take, identical on every rank) and of this rank (the size of its lists). */
+FCD_API int fcd_allreduce_small_keep(double* vec, int32_t n, int32_t keep0, int32_t nkeep, void* const* windows_host,
+                             int32_t rank, int32_t world, uint64_t seq, double* result_host, void* stream);
 FCD_API int fcd_wait_result(const double* result_host, int32_t n, uint64_t seq, double* out_host, int32_t timeout_ms);
 /* Staging of the all-gather of the region posteriors `_lq_R` / exp(_lq_R) ((N, U, 2), fcdiff/fit.py:176-198)
  * when patients are sharded: pack this rank's columns [u0, u0+Ul) of both arrays into one
