@@ -171,6 +171,27 @@ __device__ __forceinline__ void pair_weights(double2 qn, double2 qm, double (&w)
 
 __device__ __forceinline__ double sel3(int l, const double (&v)[3]) { return l == 0 ? v[0] : (l == 1 ? v[1] : v[2]); }
 
+// ---------------------------------------------------------------- K2 row end
+// lane 0 of the warp that owns edge c: log gamma + healthy quadratic + A, then
+// scipy.special.logsumexp: a_max + log(sum exp(a - a_max))           (fit.py:165-174)
+__device__ __forceinline__ void k2_finish(int64_t c, const double (&A)[3], double s1, double s2,
+                                          const ThetaDev& th, double* __restrict__ lqF,
+                                          double* __restrict__ qF) {
+    double l[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        l[k] = th.log_gamma[k] + fma(th.hq_a[k], s2, fma(th.hq_b[k], s1, th.hq_c[k])) + A[k];
+    const double mx = fmax(l[0], fmax(l[1], l[2]));
+    const double lse = mx + log(exp(l[0] - mx) + exp(l[1] - mx) + exp(l[2] - mx));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double v = l[k] - lse;
+        lqF[c * 3 + k] = v;
+        if (qF) qF[c * 3 + k] = exp(v);
+    }
+}
+
+
 // ---------------------------------------------------------------- mbarrier / TMA helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

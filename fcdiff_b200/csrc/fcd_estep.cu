@@ -7,6 +7,7 @@
 #include <type_traits>
 
 #include "fcd_common.cuh"
+#include "fcd_estep_rows.cuh"
 
 namespace fcd {
 
@@ -141,25 +142,6 @@ map_labels_kernel(const double* __restrict__ lq, int64_t n, int width, uint8_t* 
 // The per-(c,u) term L * sum_l w_l is common to the three states k and cancels in
 // the normalisation, so it is never formed.  T1: both regions of the element
 // peaked -> the three logs of l*; deferred: all nine with the real pair weights.
-
-// lane 0 of the warp that owns edge c: log gamma + healthy quadratic + A, then
-// scipy.special.logsumexp: a_max + log(sum exp(a - a_max))           (fit.py:165-174)
-__device__ __forceinline__ void k2_finish(int64_t c, const double (&A)[3], double s1, double s2,
-                                          const ThetaDev& th, double* __restrict__ lqF,
-                                          double* __restrict__ qF) {
-    double l[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
-        l[k] = th.log_gamma[k] + fma(th.hq_a[k], s2, fma(th.hq_b[k], s1, th.hq_c[k])) + A[k];
-    const double mx = fmax(l[0], fmax(l[1], l[2]));
-    const double lse = mx + log(exp(l[0] - mx) + exp(l[1] - mx) + exp(l[2] - mx));
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const double v = l[k] - lse;
-        lqF[c * 3 + k] = v;
-        if (qF) qF[c * 3 + k] = exp(v);
-    }
-}
 
 constexpr int kK2Seg = 128;
 
@@ -1492,6 +1474,18 @@ int fcd_estep_qF_coded(const double* S1, const double* S2, int32_t H,
     FCD_REQUIRE(log_table_window(th.epsl, th.al, st, tab, true), "fcd_estep_qF_coded: log table initialisation failed");
     const bool fast = log_table_covers(th.epsl, th.al);
     const size_t tbytes = fast ? (size_t)((tab.n + 15) & ~15) * sizeof(double) : 0;
+    // Row-group form (fcd_estep_rows.cu; FCD_K2=rows): four lanes per row, eight rows per warp, 2-D TMA tiles, the
+    // half records taken from the tiles -- HALF the warp-instructions of the warp-per-row kernel below, and the
+    // same time (0.190 against 0.193 ms at config 3 with 16 warps; 0.208 / 0.242 with 12 / 8): with 122 registers
+    // and 4.3 KB stages an SM holds 16 warps with two stages each, and the kernel waits (shared-memory table
+    // reads of the half records' logarithms, tile arrival) instead of issuing.  Kept as a tested alternative.
+    static const bool rows_form = [] {
+        const char* e = getenv("FCD_K2");
+        return e != nullptr && strcmp(e, "rows") == 0;
+    }();
+    if (rows_form && estep_rows_supported(U, pitchU, pitchQ))
+        return estep_rows_launch(S1, S2, P, planeStride, C, U, pitchU, qR, nm, code, pitchQ, counts, keysF, keysH, rowoff,
+                                 Hh, th, tab, fast, lqF, qF, st);
     // 16 warps per SM (127 registers each).  FCD_K2C_WARPS=24 selects the 24-warp build (80 registers, three
     // ring stages per warp): measured no faster (0.199 vs 0.193 ms at config 3) -- the kernel is bound by
     // the instructions of its row-level work, not by the warps available to hide latency.

@@ -41,7 +41,9 @@ def main():
     if dist_mode:
         from fcdiff_b200 import dist as fdist
         shards = fdist.init_from_env("nccl")
-    for (N, H, U) in ((10, 20, 20), (40, 50, 50)):             # config 1; a cut of config 2 (AAL-90)
+    # config 1; a cut of config 2 (AAL-90); 70 regions: the blocked region sweep (N >= 64: cp.async tiles, L2 bulk
+    # prefetch, double-buffered shared-memory tiles between the solver warp and the helper warps) and its fused form
+    for (N, H, U) in ((10, 20, 20), (40, 50, 50), (70, 12, 16)):
         (b, bt) = problem(N, H, U, N)
         one_fit(b, bt, shards)
         if dist_mode:
@@ -58,6 +60,10 @@ def main():
         ts = np.random.RandomState(0).standard_normal((4, 90, 200)).astype(np.float32)      # config 2's K1 shape
         z = corr.correlations(ts)
         assert np.all(np.isfinite(z))
+        # persistent tcgen05 Gram kernel: a 16-row tail block (transposed tiles), a lone subject in the last pair,
+        # both TMEM buffers reused
+        ts = np.random.RandomState(2).standard_normal((5, 144, 96)).astype(np.float32)
+        assert np.all(np.isfinite(corr.correlations(ts)))
         ts = np.random.RandomState(1).standard_normal((3, 20, 64)).astype(np.float32)       # SIMT Gram path
         assert np.all(np.isfinite(corr.correlations(ts, fisher=False)))
     torch.cuda.synchronize()

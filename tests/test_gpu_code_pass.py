@@ -262,3 +262,24 @@ def test_sweep_launch_shapes_match_numpy(N, U, lookup, scale):
             want_q[n, u] = np.exp(l)
     nptest.assert_allclose(lqd.cpu().numpy().reshape(N, U, 2), want_lq, rtol=1e-9, atol=1e-11)
     nptest.assert_allclose(qd.cpu().numpy().reshape(N, U, 2), want_q, rtol=1e-9, atol=1e-13)
+
+
+def test_alternative_kernel_forms_in_a_child_process():
+    """Kernel forms selected by an environment variable read once per process: the row-group form of the coded
+    E-step (FCD_K2=rows, csrc/fcd_estep_rows.cu) and the one-region-per-step sweep (FCD_SWEEP=stepwise) run
+    the same parity tests as the defaults, in a child interpreter."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("FCD_CHILD_FORMS"):
+        pytest.skip("already inside the child run")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FCD_K2="rows", FCD_SWEEP="stepwise", FCD_CHILD_FORMS="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
+                        os.path.join(root, "tests", "test_gpu_code_pass.py"),
+                        os.path.join(root, "tests", "test_gpu_parity.py"),
+                        "-k", "code_plane_and_evaluator or sweep_launch_shapes or fused_steps or config3_properties "
+                              "or config3_two_iterations or cfg2_full_run or config4_edge_shard"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=1500)
+    tail = "\n".join(r.stdout.splitlines()[-25:]) + "\n" + "\n".join(r.stderr.splitlines()[-5:])
+    assert r.returncode == 0, tail
