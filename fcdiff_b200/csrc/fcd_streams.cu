@@ -244,13 +244,19 @@ record_keys_kernel(const uint8_t* __restrict__ code, const uint8_t* __restrict__
                 uint4 cw = make_uint4(0, 0, 0, 0);
                 if (u0 < U) cw = __ldg(reinterpret_cast<const uint4*>(crow + u0));           // pitchQ % 16 == 0
                 const uint32_t w4[4] = {cw.x, cw.y, cw.z, cw.w};
-                uint32_t nF = 0, nH = 0;
+                // four codes per 32-bit word, all below 8: code == 3 <=> bit0 & bit1 & ~bit2, code >= 4 <=> bit2 --
+                // one flag bit per byte, counted with popc (no loop over the 16 codes)
+                const int nvalid = U - u0;                   // codes of this lane that exist (<= 0: none, >= 16: all)
+                uint32_t mF[4], mH[4], nF = 0, nH = 0;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const uint32_t cd = (w4[i >> 2] >> (8 * (i & 3))) & 0xff;
-                    const bool in = u0 + i < U;
-                    nF += in && cd == 3;
-                    nH += in && cd >= 4;
+                for (int k = 0; k < 4; ++k) {
+                    const int v = nvalid - 4 * k;
+                    const uint32_t bm = v >= 4 ? 0x01010101u : (v <= 0 ? 0u : (0x01010101u >> (8 * (4 - v))));
+                    const uint32_t x = w4[k];
+                    mF[k] = x & (x >> 1) & ~(x >> 2) & bm;
+                    mH[k] = (x >> 2) & bm;
+                    nF += __popc(mF[k]);
+                    nH += __popc(mH[k]);
                 }
                 uint32_t pk = nF | (nH << 16), incl = pk;                                    // both < 2^16
 #pragma unroll
@@ -262,11 +268,14 @@ record_keys_kernel(const uint8_t* __restrict__ code, const uint8_t* __restrict__
                 uint32_t pF = offF + ((incl - pk) & 0xffff), pH = offH + ((incl - pk) >> 16);
                 if (nF | nH) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const uint32_t cd = (w4[i >> 2] >> (8 * (i & 3))) & 0xff;
-                        if (u0 + i < U) {
-                            if (cd == 3) dF[pF++] = ckey | (unsigned long long)(u0 + i);
-                            else if (cd >= 4) dH[pH++] = ((unsigned long long)(cd - 4) << 48) | ckey | (unsigned long long)(u0 + i);
+                    for (int k = 0; k < 4; ++k) {
+                        uint32_t m = mF[k] | mH[k];          // ascending patients: bit 8 i of word k = patient u0 + 4 k + i
+                        while (m) {
+                            const int b = __ffs(m) - 1;
+                            m &= m - 1;
+                            const unsigned long long u = (unsigned long long)(u0 + 4 * k + (b >> 3));
+                            if ((mF[k] >> b) & 1u) dF[pF++] = ckey | u;
+                            else dH[pH++] = ((unsigned long long)(((w4[k] >> b) & 0xffu) - 4) << 48) | ckey | u;
                         }
                     }
                 }
