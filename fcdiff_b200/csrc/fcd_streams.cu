@@ -51,9 +51,37 @@ __device__ __forceinline__ int pair_code(int sn, int sm) {
 // kernel -- no pass over per-row arrays by a single CTA.
 constexpr int kRowBlock = 16;
 
+// Codes of TWO patients at once: a 4096-entry table indexed by the four 3-bit states (sn_a | sm_a << 3 |
+// sn_b << 6 | sm_b << 9), entry = the two code bytes; padding (a state above 4, or a dead state) is stored as
+// 3 | 8: bit 3 = "do not count".  Built once per device, staged in shared memory per CTA (8 KB).
+__device__ unsigned short g_pair_lut[4096];
+
+__global__ void build_pair_lut_kernel() {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 4096) return;
+    auto enc = [](int sn, int sm) {
+        const int c = (sn > 4 || sm > 4) ? 6 : pair_code(sn, sm);
+        return c == 6 ? 0x0b : c;
+    };
+    g_pair_lut[idx] = (unsigned short)(enc(idx & 7, (idx >> 3) & 7) | (enc((idx >> 6) & 7, (idx >> 9) & 7) << 8));
+}
+
+static bool ensure_pair_lut(cudaStream_t st) {
+    static bool done[64] = {false};
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+    if (!done[dev]) {
+        build_pair_lut_kernel<<<16, 256, 0, st>>>();
+        if (cudaGetLastError() != cudaSuccess) return false;
+        done[dev] = true;
+    }
+    return true;
+}
+
 // code[c][u] for u in [0, pitchQ) and counts[c] = {full records, half records} of row c; blocktot[b]
 // = their sums over the rows of block b.  On the way: PsE[c][:] = P[k*(c)][c][:] for the rows whose dominant
 // state changed since the last call (kcache).
+template <bool WIDE>
 __global__ void __launch_bounds__(kBucketThreads)
 code_plane_kernel(const double* __restrict__ P, int64_t planeStride, double* __restrict__ PsE,
                   uint8_t* __restrict__ kcache,
@@ -62,11 +90,15 @@ code_plane_kernel(const double* __restrict__ P, int64_t planeStride, double* __r
                   uint8_t* __restrict__ code, int2* __restrict__ counts, longlong2* __restrict__ blocktot) {
     __shared__ int2 s_cnt[kRowBlock];
     __shared__ uint8_t s_lut[64];                            // pair_code by (sn << 3 | sm): one LDS per element
+    __shared__ __align__(16) unsigned short s_lut2[WIDE ? 4096 : 8];   // two elements per read (g_pair_lut)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 64) {
         const int sn = threadIdx.x >> 3, sm = threadIdx.x & 7;
         s_lut[threadIdx.x] = (uint8_t)((sn > 4 || sm > 4) ? 6 : pair_code(sn, sm));
     }
+    if (WIDE)
+        for (int i = threadIdx.x; i < 4096 / 8; i += kBucketThreads)
+            reinterpret_cast<uint4*>(s_lut2)[i] = reinterpret_cast<const uint4*>(g_pair_lut)[i];
     __syncthreads();
     const int64_t cb = (int64_t)blockIdx.x * kRowBlock;
     for (int r = warp; r < kRowBlock; r += kBucketThreads / 32) {
@@ -96,6 +128,24 @@ code_plane_kernel(const double* __restrict__ P, int64_t planeStride, double* __r
                 }
                 const uint8_t* rn = rstate + (int64_t)(v & 0xffff) * pitchS;
                 const uint8_t* rm = rstate + (int64_t)((v >> 16) & 0xffff) * pitchS;
+                if (WIDE) {
+                    // four patients per lane and pass: two table reads give four codes; the record flags of the
+                    // four bytes (code == 3: bit0 & bit1 & ~bit2; code >= 4: bit2; bit 3 = padding) are counted
+                    // with popc.  The state rows are padded with 4 up to pitchS >= pitchQ.
+                    uint32_t* crow4 = reinterpret_cast<uint32_t*>(crow);
+                    for (int u = 4 * lane; u < pitchQ; u += 128) {
+                        const uint32_t sn4 = __ldg(reinterpret_cast<const uint32_t*>(rn + u));
+                        const uint32_t sm4 = __ldg(reinterpret_cast<const uint32_t*>(rm + u));
+                        const uint32_t ia = (sn4 & 7u) | ((sm4 & 7u) << 3) | ((sn4 >> 2) & 0x1c0u) | ((sm4 << 1) & 0xe00u);
+                        const uint32_t sh = sn4 >> 16, th2 = sm4 >> 16;
+                        const uint32_t ib = (sh & 7u) | ((th2 & 7u) << 3) | ((sh >> 2) & 0x1c0u) | ((th2 << 1) & 0xe00u);
+                        const uint32_t x = (uint32_t)s_lut2[ia] | ((uint32_t)s_lut2[ib] << 16);
+                        const uint32_t live = ~(x >> 3) & 0x01010101u;
+                        cnt += __popc(x & (x >> 1) & ~(x >> 2) & live);
+                        cnh += __popc((x >> 2) & live);
+                        crow4[u >> 2] = x & 0x07070707u;
+                    }
+                } else
                 // two patients per lane; the state rows are padded with 4 up to pitchS >= pitchQ
                 for (int u = 2 * lane; u < pitchQ; u += 64) {
                     const uint32_t sn2 = __ldg(reinterpret_cast<const unsigned short*>(rn + u));
@@ -671,7 +721,9 @@ int fcd_code_plane(const double* P, int64_t planeStride, int64_t C, int32_t U, i
     const int64_t nblocks = (C + kRowBlock - 1) / kRowBlock;
     // blockoff doubles as the block totals' storage: [nblocks] totals followed by [nblocks] offsets (pairs)
     longlong2* bt = reinterpret_cast<longlong2*>(blockoff);
-    code_plane_kernel<<<(unsigned)nblocks, kBucketThreads, 0, st>>>(P, planeStride, PsE, kcache, fstate, rstate, pitchS,
+    const bool wide = pitchS % 4 == 0 && (reinterpret_cast<uintptr_t>(rstate) & 3) == 0 && ensure_pair_lut(st);
+    (wide ? code_plane_kernel<true> : code_plane_kernel<false>)<<<(unsigned)nblocks, kBucketThreads, 0, st>>>(
+                                                                    P, planeStride, PsE, kcache, fstate, rstate, pitchS,
                                                                     nm, C, U, pitchU, pitchQ, code,
                                                                     reinterpret_cast<int2*>(counts), bt);
     int rc = check_launch("fcd_code_plane");
