@@ -190,7 +190,7 @@ def run_reference_arm(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         # `config` names what RAN: a sub-network of the GPU arm's atlas (the oracle needs ~13 GB and ~15 min
         # per EM iteration on the full Schaefer-400 x 500+500 problem; the rate is per edge-subject)
-        "config": dict(workload_config(args.gpus), regions=n_regions, edges=r["C"],
+        "config": dict({k: v for (k, v) in workload_config(args.gpus).items() if k != "l2"}, regions=n_regions, edges=r["C"],
                        workload="bounded sample of the GPU arm's workload: sub-network of the first %d regions "
                                 "(%d edges) x (%d controls + %d patients); the GPU arm runs %d regions"
                                 % (n_regions, r["C"], H_SUBJ, U_SUBJ, regions_for(args.gpus)),
