@@ -413,10 +413,13 @@ def run_cfg5(fcdiff, shards, torch, dist, n_replicas):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sweep.permutation_sweep(corr, labels, 2 * world - 1, model=start, rank=rank, world=world, gather=False)   # warm-up
+    streams = sweep.default_streams(world)              # replicas in flight per GPU (2 when the host has the cores)
+    sweep.permutation_sweep(corr, labels, 4 * streams * world - 1, model=start, rank=rank, world=world, gather=False,
+                            streams=streams)              # warm-up: every stream's buffers and per-stream state
     sync()
     t0 = time.perf_counter()
-    res = sweep.permutation_sweep(corr, labels, n_replicas - 1, model=start, rank=rank, world=world, gather=False)
+    res = sweep.permutation_sweep(corr, labels, n_replicas - 1, model=start, rank=rank, world=world, gather=False,
+                                  streams=streams)
     sync()
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     iters = torch.tensor([float(sum(r["iterations"] for r in res.values())), float(len(res))], dtype=torch.float64,
@@ -430,6 +433,7 @@ def run_cfg5(fcdiff, shards, torch, dist, n_replicas):
            "seconds": float(dt.item()), "replicas_per_second": float(iters[1].item() / dt.item()),
            "em_iterations": int(iters[0].item()),
            "value": float(C * (H + U) * iters[0].item() / dt.item()), "unit": UNIT,
+           "replicas_in_flight_per_gpu": streams,
            "fit": "fit.run(), max_iters 10, rel_tol 1e-5, the reference's convergence rule; planes built once, "
                   "per-replica column selection"}
     if rank == 0:                                  # replica 0 is the plain fit of (b, bt)

@@ -50,10 +50,18 @@ def ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
-def workspace():
-    """Per-device reduction workspace (zero-filled once; calls restore it)."""
+def _stream_key():
+    """(device, stream): state that kernels of ONE stream use in order -- the reduction workspace, the
+    publication window, the solver block -- exists once per stream, so that fits running on different
+    streams of a device (replica sweeps, fcdiff_b200/sweep.py) do not share it."""
     dev = device()
-    key = dev.index
+    return (dev.index, int(torch.cuda.current_stream().cuda_stream))
+
+
+def workspace():
+    """Per-(device, stream) reduction workspace (zero-filled once; calls restore it)."""
+    dev = device()
+    key = _stream_key()
     if key not in _ws:
         n = _lib.load().fcd_workspace_bytes() // 8
         _ws[key] = torch.zeros(n, dtype=torch.float64, device=dev)
@@ -105,10 +113,10 @@ _publisher = {}
 
 
 def publisher():
-    """Per-device world-1 ``PeerWindow``: reduction results reach the host through
+    """Per-(device, stream) world-1 ``PeerWindow``: reduction results reach the host through
     mapped pinned memory (one tiny kernel + a host-side spin) instead of a
     cudaMemcpyAsync + stream synchronisation."""
-    key = device().index
+    key = _stream_key()
     if key not in _publisher:
         from .dist import PeerWindow
         _publisher[key] = PeerWindow()
@@ -117,7 +125,7 @@ def publisher():
 
 class SolverBlock(object):
     """Device state + mapped host publication block of the device-resident (eta, epsilon)
-    solver (``fcd_solver_*``, csrc/fcd_solver.cuh), one per device."""
+    solver (``fcd_solver_*``, csrc/fcd_solver.cuh), one per (device, stream)."""
 
     TIMEOUT_MS = 30000
 
@@ -143,7 +151,7 @@ _solver = {}
 
 
 def solver_block():
-    key = device().index
+    key = _stream_key()
     if key not in _solver:
         _solver[key] = SolverBlock()
     return _solver[key]

@@ -104,6 +104,53 @@ def _summary(fit):
                 expected_anomalous_regions=float(np.exp(fit._lq_R[:, :, 1]).sum()))
 
 
+def default_streams(world=1):
+    """Replicas in flight per GPU: two when the host has the cores for it (every fit in flight has one
+    thread that spins on mapped memory while it waits for a result), else one."""
+    import os
+    return 2 if (os.cpu_count() or 1) >= 4 * max(int(world), 1) else 1
+
+
+def _run_replicas(indices, run_one, streams):
+    """``run_one(i) -> summary`` for every replica index, ``streams`` of them in flight on this GPU: each worker
+    thread owns a CUDA stream (and, through ``_dev``, its own reduction workspace, publication window and
+    solver block); while one replica's host side waits for a result, the other's kernels fill the GPU.  The
+    ctypes calls and the waits release the GIL.  Results do not depend on ``streams`` (every fit is
+    deterministic and self-contained)."""
+    results = {}
+    if streams <= 1 or len(indices) <= 1:
+        for i in indices:
+            results[i] = run_one(i)
+        return results
+    import threading
+    dev = _dev.device()
+    main = torch.cuda.current_stream()
+    errors = []
+
+    def worker(k, s):
+        try:
+            torch.cuda.set_device(dev)                   # the current device is per thread
+            s.wait_stream(main)                          # the shared planes were built on the caller's stream
+            with torch.cuda.stream(s):
+                for i in indices[k::streams]:
+                    results[i] = run_one(i)
+                s.synchronize()
+        except BaseException as exc:                     # re-raised by the caller
+            errors.append(exc)
+
+    ss = [torch.cuda.Stream(device=dev) for _ in range(streams)]
+    threads = [threading.Thread(target=worker, args=(k, ss[k]), daemon=True) for k in range(streams)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for s in ss:
+        main.wait_stream(s)
+    if errors:
+        raise errors[0]
+    return results
+
+
 def _configure(fit, options):
     for (k, v) in (options or {}).items():
         if not hasattr(fit, k):
@@ -112,7 +159,7 @@ def _configure(fit, options):
 
 
 def permutation_sweep(corr, labels, n_permutations, model=None, seed=0, fit_options=None, rank=0, world=1,
-                      group=None, gather=True, shared_planes=True):
+                      group=None, gather=True, shared_planes=True, streams=None):
     """
     Fits the model once per group labelling: the observed one and
     ``n_permutations`` random re-labellings of the subjects.
@@ -139,6 +186,9 @@ def permutation_sweep(corr, labels, n_permutations, model=None, seed=0, fit_opti
         With ``update_mu_sigma`` in ``fit_options`` (the planes then change during a
         fit) or ``shared_planes=False`` every replica uploads its own columns and
         rebuilds its planes -- same results.
+    streams : int or None
+        Replicas in flight on this GPU (one CUDA stream and one host thread each; default
+        :func:`default_streams`).  Same results for any value.
 
     Returns
     -------
@@ -153,8 +203,7 @@ def permutation_sweep(corr, labels, n_permutations, model=None, seed=0, fit_opti
     shared = None
     if shared_planes and not (fit_options or {}).get("update_mu_sigma"):
         shared = SharedPlanes(corr_dev, model)
-    results = {}
-    for i in replica_indices(n_permutations + 1, rank, world):
+    def run_one(i):
         pat = torch.from_numpy(np.flatnonzero(lab[i])).to(dev)
         con = torch.from_numpy(np.flatnonzero(~lab[i])).to(dev)
         fit = UnsharedRegionFit()
@@ -166,8 +215,10 @@ def permutation_sweep(corr, labels, n_permutations, model=None, seed=0, fit_opti
             fit.b = corr_dev.index_select(1, con)          # column gather: data movement only
             fit.bt = corr_dev.index_select(1, pat)
         fit.run()
-        results[i] = _summary(fit)
-        del fit
+        return _summary(fit)
+
+    results = _run_replicas(replica_indices(n_permutations + 1, rank, world), run_one,
+                            default_streams(world) if streams is None else int(streams))
     return _gather(results, group) if gather else results
 
 

@@ -42,6 +42,22 @@ def test_permutation_sweep_matches_individual_fits_and_the_oracle():
     assert 0.0 < sweep.permutation_p_value(res) <= 1.0
 
 
+@pytest.mark.parametrize("N,H,U", [(12, 14, 10), (70, 9, 40)])
+def test_replicas_in_flight_do_not_change_results(N, H, U):
+    """Two replicas in flight on the GPU (two host threads, two CUDA streams, per-stream reduction workspace /
+    publication window / solver block) give bit for bit what one after the other gives."""
+    (b, bt, corr, labels) = _problem(N, H, U, seed=N + 1)
+    opts = dict(max_iters=4, rel_tol=-1.0)
+    one = sweep.permutation_sweep(corr, labels, 6, seed=5, fit_options=opts, streams=1)
+    for streams in (2, 3):
+        two = sweep.permutation_sweep(corr, labels, 6, seed=5, fit_options=opts, streams=streams)
+        assert sorted(one) == sorted(two)
+        for i in one:
+            assert one[i]["energy"] == two[i]["energy"], (streams, i)
+            assert (one[i]["pi"], one[i]["eta"], one[i]["epsilon"]) == (two[i]["pi"], two[i]["eta"], two[i]["epsilon"])
+            assert one[i]["expected_anomalous_regions"] == two[i]["expected_anomalous_regions"]
+
+
 @pytest.mark.parametrize("N,H,U", [(12, 14, 10), (9, 13, 10), (15, 8, 9)])
 def test_shared_planes_equal_per_replica_planes(N, H, U):
     """configs[4]: planes built once for all subjects + per-replica column selection give the fit of
