@@ -258,7 +258,7 @@ estep_qF_kernel(const double* __restrict__ S1, const double* __restrict__ S2,
 // queue) and the row's key list names the elements with a mixed region (evaluated densely after
 // the row, nine logs each with the real pair weights).  One persistent CTA of 16 warps per SM, warp
 // per row; per 128-patient segment three bulk copies (p_0, p_1, codes) into the warp's private ring.
-constexpr int kK2cSeg = 128;
+constexpr int kK2cSeg = 256;
 constexpr int kK2cStage = 2 * kK2cSeg * 8 + kK2cSeg;          // bytes: p_0, p_1, codes
 constexpr int kK2cMaxDepth = 5;
 constexpr size_t k2c_ring_bytes(int depth, int nw) { return (size_t)nw * depth * (kK2cStage + 8); }
@@ -275,7 +275,15 @@ estep_qF_coded_kernel(const double* __restrict__ S1, const double* __restrict__ 
                       double* __restrict__ lqF, double* __restrict__ qF) {
     extern __shared__ __align__(128) double s_dyn[];
     __shared__ double2 s_lc[8];
+    __shared__ uint64_t s_tabbar;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // the logarithm table first: one bulk copy at the head of this SM's queue (loaded by every thread
+    // after the ring fills, it waited behind ~200 KB of them: 5 % of the kernel's stall samples)
+    if (threadIdx.x == 0) {
+        mbar_init(&s_tabbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        issue_log_table<FAST>(tab, s_dyn, &s_tabbar);
+    }
     unsigned char* ring0 = reinterpret_cast<unsigned char*>(s_dyn + (FAST ? ((tab.n + 15) & ~15) : 0));
     unsigned char* ring = ring0 + (size_t)warp * depth * kK2cStage;
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring0 + (size_t)NW * depth * kK2cStage) + warp * depth;
@@ -333,7 +341,9 @@ estep_qF_coded_kernel(const double* __restrict__ S1, const double* __restrict__ 
     };
 #pragma unroll 1
     for (int i = 0; i < depth; ++i) issue();
-    const double* s_tab = load_log_table<FAST>(tab, s_dyn);  // staged while the first segments are in flight
+    const double* s_tab = s_dyn - tab.lo;
+    __syncthreads();                                         // s_tabbar initialised
+    if (FAST) mbar_wait(&s_tabbar, 0);
 
     const double2* qR2 = reinterpret_cast<const double2*>(qR);
     double acc[3] = {0.0, 0.0, 0.0};
@@ -399,17 +409,17 @@ estep_qF_coded_kernel(const double* __restrict__ S1, const double* __restrict__ 
         const int2 cnt = nxt_cnt;
         const longlong2 ro = nxt_ro;
         const bool listed = cnt.x != 3 * U && (cnt.x > 0 || cnt.y > 0);
-        int hu[2] = {-1, -1}, hseg[2] = {-1, -1};
+        // (the key is not touched before the first segment has been consumed: its latency hides there)
+        bool hv[2];
+        uint32_t hkey[2] = {0u, 0u};
         double hq[2] = {0.0, 0.0}, hp0[2] = {0.0, 0.0}, hp1[2] = {0.0, 0.0};
-        if (listed) {
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const int i = lane + 32 * k;
-                if (i < cnt.y) {
-                    hu[k] = (int)(__ldg(keysH + ro.y + i) & 0xffffull);
-                    hq[k] = __ldg(Hh + ro.y + i).y;
-                    hseg[k] = hu[k] / kK2cSeg;
-                }
+        for (int k = 0; k < 2; ++k) {
+            const int i = lane + 32 * k;
+            hv[k] = listed && i < cnt.y;
+            if (hv[k]) {
+                hkey[k] = __ldg(reinterpret_cast<const uint32_t*>(keysH + ro.y + i));      // low word: u in bits 0-15
+                hq[k] = __ldg(Hh + ro.y + i).y;
             }
         }
         if (c + W < C) {                                     // the next row's counts / offsets: in flight during this row
@@ -456,10 +466,12 @@ estep_qF_coded_kernel(const double* __restrict__ S1, const double* __restrict__ 
             // my half records that lie in this segment: p_0, p_1 straight from the stage
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                if (hseg[k] == s) {
-                    const int o = hu[k] - s * kK2cSeg;
-                    hp0[k] = *reinterpret_cast<const double*>(st + o * 8);
-                    hp1[k] = *reinterpret_cast<const double*>(st + kK2cSeg * 8 + o * 8);
+                if (hv[k]) {
+                    const uint32_t o = (hkey[k] & 0xffffu) - (uint32_t)(s * kK2cSeg);
+                    if (o < (uint32_t)kK2cSeg) {
+                        hp0[k] = *reinterpret_cast<const double*>(st + o * 8);
+                        hp1[k] = *reinterpret_cast<const double*>(st + kK2cSeg * 8 + o * 8);
+                    }
                 }
             }
             __syncwarp();
@@ -484,7 +496,7 @@ estep_qF_coded_kernel(const double* __restrict__ S1, const double* __restrict__ 
             }
 #pragma unroll
             for (int k = 0; k < 2; ++k)
-                if (32 * k < cnt.y && hu[k] >= 0)            // first condition warp-uniform
+                if (32 * k < cnt.y && hv[k])                 // first condition warp-uniform
                     half_p(hp0[k], hp1[k], __double2hiint(hq[k]) < 0, fabs(hq[k]));
             const unsigned long long* kh = keysH + ro.y;
             const double2* hr = Hh + ro.y;

@@ -72,6 +72,18 @@ __device__ __forceinline__ const double* load_log_table(const LogTabWindow& w, d
     return s_tab - w.lo;
 }
 
+// The same staging as ONE bulk copy (window slots and size are even, log_table_window): issued by a
+// single thread ahead of a kernel's own ring fills, so that the table does not queue behind them;
+// every thread waits on `bar` (phase 0) before its first logarithm.
+template <bool FAST>
+__device__ __forceinline__ void issue_log_table(const LogTabWindow& w, double* s_tab, uint64_t* bar) {
+    if (!FAST) return;
+    const uint32_t bytes = (uint32_t)w.n * 8u, b = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(s_tab)), "l"(w.g + w.lo), "r"(bytes), "r"(b) : "memory");
+}
+
 struct LogParts {
     double r8;      // 8-bit reciprocal
     double u;       // y * r8 - 1

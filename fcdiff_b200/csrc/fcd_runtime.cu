@@ -46,7 +46,7 @@ int sm_count() {
 
 // -log(r8) table of fast_log (fcd_math.cuh): theta-independent, built once per
 // device in static device memory (no runtime allocation).
-__device__ double g_log_tab[kLogTabSize];
+__device__ __align__(128) double g_log_tab[kLogTabSize];
 
 __global__ void build_log_table_kernel() {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kLogTabSize; i += gridDim.x * blockDim.x)
@@ -100,8 +100,9 @@ bool log_table_window(const double epsl[3], const double al[3], cudaStream_t st,
     int lo = slot(ymax) - 4, hi = slot(ymin) + 4;           // slack: MUFU.RCP64H error, FMA rounding
     if (lo < 0 || with_mantissa) lo = 0;
     if (hi > kLogTabSize - 1) hi = kLogTabSize - 1;
+    lo &= ~1;                                               // 16-byte granules: the window can be staged by one bulk copy
     w.lo = lo;
-    w.n = hi - lo + 1;
+    w.n = (hi - lo + 2) & ~1;                               // kLogTabSize is even: lo + n stays inside the table
     return true;
 }
 
