@@ -687,6 +687,9 @@ def run_gpu_arm(args):
         ab = algorithmic_bytes(name, Cl, N, H, U if name != "K2b_region_weights" and name != "K2b_sweep"
                                else (U if shards is None else shards.span(U)[1]))
         ent = {"launches": cnt, "total_ms": total_ms, "mean_ms": mean_ms, "share_of_step": total_ms / ms}
+        lm = sorted(timers.launch_ms(name))
+        if lm and len(lm) == cnt:                     # one bracket per launch: the spread over the fits' iterations
+            ent["min_ms"], ent["median_ms"], ent["max_ms"] = lm[0], lm[len(lm) // 2], lm[-1]
         if ab:
             ent["algorithmic_bytes"] = int(ab)
             ent["achieved_gbs"] = ab / (mean_ms * 1e-3) / 1e9

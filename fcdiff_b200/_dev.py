@@ -239,6 +239,12 @@ class KernelTimers(object):
             out[name] = (n, float(sum(ms)), float(sum(ms) / max(n, 1)))
         return out
 
+    def launch_ms(self, name):
+        """Durations of the individual brackets of ``name`` in launch order (a mean hides that the first
+        iterations after the uniform start carry more records than the settled ones)."""
+        torch.cuda.synchronize()
+        return [float(s.elapsed_time(e)) for (s, e, _) in self.events.get(name, [])]
+
 
 _NULL = contextlib.nullcontext()
 _NVTX = bool(os.environ.get("FCD_NVTX"))      # FCD_NVTX=1: an NVTX range per kernel family (ncu --nvtx, nsys)

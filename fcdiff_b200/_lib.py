@@ -84,6 +84,9 @@ SIGNATURES = {
                                  c_int32, _P, _P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, _P, _P, _P]),
     "fcd_estep_qF_coded": (c_int, [_P, _P, c_int32, _P, c_int64, c_int64, c_int32, c_int64, _P, c_int32, _P,
                                    _P, c_int64, _P, _P, _P, _P, _P, POINTER(FcdTheta), _P, _P, _P]),
+    "fcd_estep_qF_coded_solved": (c_int, [_P, _P, c_int32, _P, c_int64, c_int64, c_int32, c_int64, _P, c_int32, _P,
+                                          _P, c_int64, _P, _P, _P, _P, _P, POINTER(FcdTheta), _P, c_double, c_double,
+                                          _P, _P, _P]),
     "fcd_elm_coded": (c_int, [_P, _P, c_int64, _P, c_int64, _P, c_int64, POINTER(FcdTheta), c_int32, _P, _P, _P]),
     "fcd_solver_state_bytes": (c_int64, []),
     "fcd_solver_published_bytes": (c_int64, []),

@@ -8,6 +8,7 @@
 
 #include "fcd_common.cuh"
 #include "fcd_estep_rows.cuh"
+#include "fcd_solver.cuh"
 
 namespace fcd {
 
@@ -271,7 +272,8 @@ estep_qF_coded_kernel(const double* __restrict__ S1, const double* __restrict__ 
                       const uint8_t* __restrict__ code, int64_t pitchQ, const int2* __restrict__ counts,
                       const unsigned long long* __restrict__ keysF, const unsigned long long* __restrict__ keysH,
                       const longlong2* __restrict__ rowoff, const double2* __restrict__ Hh,
-                      const __grid_constant__ ThetaDev th, const __grid_constant__ LogTabWindow tab, int depth,
+                      const __grid_constant__ ThetaDev th, const SolverState* __restrict__ solved,
+                      const __grid_constant__ LogTabWindow tab, int depth,
                       double* __restrict__ lqF, double* __restrict__ qF) {
     extern __shared__ __align__(128) double s_dyn[];
     __shared__ double2 s_lc[8];
@@ -295,15 +297,36 @@ estep_qF_coded_kernel(const double* __restrict__ S1, const double* __restrict__ 
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     // per-code constants {a_l, b_l}; code 3 is neutral: the factor 1 + 0 p = 1 exactly; the codes 4, 5
     // (one undecided region) count as l = 2 here, their correction comes from the half records
+    // `solved` != NULL: (eta, epsilon) are the ones the device-resident solve enqueued before this launch
+    // left in its state block (the host does not know them yet: the E-step of the NEXT iteration runs
+    // while the host waits for that solve, fcdiff_b200/fit.py: _speculative_estep)
     if (threadIdx.x < 8) {
         const int l = threadIdx.x >= 4 ? 2 : threadIdx.x;
-        s_lc[threadIdx.x] = l < 3 ? make_double2(th.al[l], th.bl[l]) : make_double2(1.0, 0.0);
+        double2 ab = make_double2(1.0, 0.0);
+        if (l < 3) {
+            if (solved != nullptr) {
+                // make_theta_dev's arithmetic (fcd_runtime.cu) operation by operation, no contraction: the
+                // launch is bit-identical to the one the host would make after reading the solution
+                const double eta = solved->x[0], eps = solved->x[1];
+                const double e = l == 0 ? __dadd_rn(1.0, -eps)
+                               : l == 1 ? eps
+                               : __dadd_rn(__dmul_rn(eta, eps), __dmul_rn(__dadd_rn(1.0, -eta), __dadd_rn(1.0, -eps)));
+                const double a = __dmul_rn(__dadd_rn(1.0, -e), 0.5);
+                ab = make_double2(a, __dadd_rn(e, -a));
+            } else {
+                ab = make_double2(th.al[l], th.bl[l]);
+            }
+        }
+        s_lc[threadIdx.x] = ab;
     }
     __syncwarp();
 
     const int nseg = (int)((pitchU + kK2cSeg - 1) / kK2cSeg);
     const int64_t W = (int64_t)gridDim.x * NW;
-    const int64_t c_first = (int64_t)blockIdx.x * NW + warp;
+    // consecutive rows go to different SMs: the rows of one region are consecutive, and a region that is
+    // undecided for many patients makes ALL its rows expensive (half records); at config 3 the launch
+    // times are the same as with 16 consecutive rows per CTA
+    const int64_t c_first = (int64_t)warp * gridDim.x + blockIdx.x;
     const uint32_t ring_s = smem_u32(ring), bars_s = smem_u32(bars);
     // Issue side: running global pointers (lane 0), segment sizes known in advance -- a segment is a
     // full 128 patients except the row's last one.
@@ -368,17 +391,17 @@ estep_qF_coded_kernel(const double* __restrict__ S1, const double* __restrict__ 
         for (int k = 0; k < 3; ++k) {
             double a = acc[k];
 #pragma unroll
-            for (int l = 0; l < 3; ++l) a = fma(w[l], fast_log<FAST>(mix_rel(th, l, p3[k]), s_tab), a);
+            for (int l = 0; l < 3; ++l) a = fma(w[l], fast_log<FAST>(fma(s_lc[l].y, p3[k], s_lc[l].x), s_tab), a);
             acc[k] = a;
         }
     };
     // an element with one undecided region: q (log M_s - log M_2) per template state (half record {p*, +-q})
     auto half_p = [&](double p0, double p1, bool sx, double q) {
         const double p3[3] = {p0, p1, (1.0 - p0) - p1};
-        const double ax = sx ? th.al[1] : th.al[0], bx = sx ? th.bl[1] : th.bl[0];
+        const double2 x = s_lc[sx ? 1 : 0], z = s_lc[2];
 #pragma unroll
         for (int k = 0; k < 3; ++k)
-            acc[k] = fma(q, fast_log<FAST>(fma(bx, p3[k], ax), s_tab) - fast_log<FAST>(mix_rel(th, 2, p3[k]), s_tab), acc[k]);
+            acc[k] = fma(q, fast_log<FAST>(fma(x.y, p3[k], x.x), s_tab) - fast_log<FAST>(fma(z.y, p3[k], z.x), s_tab), acc[k]);
     };
     auto half = [&](int64_t c, int u, bool sx, double q) {
         half_p(__ldg(P + c * pitchU + u), __ldg(P + planeStride + c * pitchU + u), sx, q);
@@ -448,10 +471,16 @@ estep_qF_coded_kernel(const double* __restrict__ S1, const double* __restrict__ 
             mbar_wait(bars + d, phase);
             const unsigned char* st = ring + d * kK2cStage;
             const unsigned short* cs = reinterpret_cast<const unsigned short*>(st + 2 * kK2cSeg * 8) + lane;
-            if (s < nseg - 1 || np_last == (uint32_t)kK2cSeg) {          // a full segment (warp-uniform): no bounds
+            if (s < nseg - 1 || np_last > (uint32_t)(kK2cSeg - 64)) {
+                // every pair of the stage has elements (warp-uniform): one straight-line block, no flush
+                // inside; beyond the row's end the stage holds stale (finite) responsibilities and the code
+                // is forced to 3 (the row's last segment used to take the bounded path below, a branch and
+                // a flush test per pair: half of all segments at 500 patients)
+                const int lim = s < nseg - 1 ? kK2cSeg : (int)np_last;
                 if (nf + kK2cSeg / 64 > kProdMax) flush();
 #pragma unroll
-                for (int j = 0; j < kK2cSeg / 64; ++j) pair(st, j, cs[32 * j]);
+                for (int j = 0; j < kK2cSeg / 64; ++j)
+                    pair(st, j, 64 * j + 2 * lane < lim ? (uint32_t)cs[32 * j] : 0x0303u);
                 nf += kK2cSeg / 64;
             } else {
 #pragma unroll
@@ -1465,12 +1494,16 @@ int fcd_estep_qF(const double* S1, const double* S2, int32_t H,
     return check_launch("fcd_estep_qF");
 }
 
-int fcd_estep_qF_coded(const double* S1, const double* S2, int32_t H,
-                       const double* P, int64_t planeStride, int64_t C, int32_t U, int64_t pitchU,
-                       const double* qR, int32_t N, const int32_t* nm,
-                       const uint8_t* code, int64_t pitchQ, const int32_t* counts, const uint64_t* keysF,
-                       const uint64_t* keysH, const int64_t* rowoff, const double* Hh,
-                       const fcd_theta* theta_host, double* lqF, double* qF, void* stream) {
+// `solved` == NULL: (eta, epsilon) of theta_host; otherwise the solver state block a device-resident solve
+// enqueued BEFORE this launch leaves its solution in, with [eps_lo, eps_hi] the box of that solve (it
+// sizes the logarithm table like fcd_elm_coded_solve does).
+static int estep_qF_coded_launch(const double* S1, const double* S2, int32_t H,
+                                 const double* P, int64_t planeStride, int64_t C, int32_t U, int64_t pitchU,
+                                 const double* qR, int32_t N, const int32_t* nm,
+                                 const uint8_t* code, int64_t pitchQ, const int32_t* counts, const uint64_t* keysF,
+                                 const uint64_t* keysH, const int64_t* rowoff, const double* Hh,
+                                 const fcd_theta* theta_host, const SolverState* solved, double eps_lo, double eps_hi,
+                                 double* lqF, double* qF, void* stream) {
     FCD_REQUIRE(theta_host != nullptr && S1 != nullptr && S2 != nullptr && P != nullptr && qR != nullptr &&
                 nm != nullptr && code != nullptr && counts != nullptr && keysF != nullptr && keysH != nullptr &&
                 rowoff != nullptr && Hh != nullptr && lqF != nullptr, "fcd_estep_qF_coded: NULL argument");
@@ -1483,8 +1516,18 @@ int fcd_estep_qF_coded(const double* S1, const double* S2, int32_t H,
     const ThetaDev th = make_theta_dev(*theta_host, H);
     cudaStream_t st = (cudaStream_t)stream;
     LogTabWindow tab;
-    FCD_REQUIRE(log_table_window(th.epsl, th.al, st, tab, true), "fcd_estep_qF_coded: log table initialisation failed");
-    const bool fast = log_table_covers(th.epsl, th.al);
+    double w_eps[3] = {th.epsl[0], th.epsl[1], th.epsl[2]}, w_al[3] = {th.al[0], th.al[1], th.al[2]};
+    if (solved != nullptr) {
+        // every mixture weight the solve can have ended at lies in [m / 2, 1], m = min(eps_lo, 1 - eps_hi)
+        FCD_REQUIRE(eps_lo > 0.0 && eps_lo <= eps_hi && eps_hi < 1.0, "fcd_estep_qF_coded_solved: bad box");
+        const double m = eps_lo < 1.0 - eps_hi ? eps_lo : 1.0 - eps_hi;
+        for (int l = 0; l < 3; ++l) {
+            w_eps[l] = m;
+            w_al[l] = 0.5 * m;
+        }
+    }
+    FCD_REQUIRE(log_table_window(w_eps, w_al, st, tab, true), "fcd_estep_qF_coded: log table initialisation failed");
+    const bool fast = log_table_covers(w_eps, w_al);
     const size_t tbytes = fast ? (size_t)((tab.n + 15) & ~15) * sizeof(double) : 0;
     // Row-group form (fcd_estep_rows.cu; FCD_K2=rows): four lanes per row, eight rows per warp, 2-D TMA tiles, the
     // half records taken from the tiles -- HALF the warp-instructions of the warp-per-row kernel below, and the
@@ -1495,7 +1538,7 @@ int fcd_estep_qF_coded(const double* S1, const double* S2, int32_t H,
         const char* e = getenv("FCD_K2");
         return e != nullptr && strcmp(e, "rows") == 0;
     }();
-    if (rows_form && estep_rows_supported(U, pitchU, pitchQ))
+    if (rows_form && solved == nullptr && estep_rows_supported(U, pitchU, pitchQ))
         return estep_rows_launch(S1, S2, P, planeStride, C, U, pitchU, qR, nm, code, pitchQ, counts, keysF, keysH, rowoff,
                                  Hh, th, tab, fast, lqF, qF, st);
     // 16 warps per SM (127 registers each).  FCD_K2C_WARPS=24 selects the 24-warp build (80 registers, three
@@ -1506,7 +1549,7 @@ int fcd_estep_qF_coded(const double* S1, const double* S2, int32_t H,
         return e != nullptr ? atoi(e) : 0;
     }();
     int nw = 16;
-    if (forced_nw == 24 && tbytes + k2c_ring_bytes(2, 24) <= kSmemBudget) nw = 24;
+    if ((forced_nw == 24 || forced_nw == 20) && tbytes + k2c_ring_bytes(2, forced_nw) <= kSmemBudget) nw = forced_nw;
     int depth = kK2cMaxDepth;
     while (depth > 2 && tbytes + k2c_ring_bytes(depth, nw) > kSmemBudget) --depth;
     FCD_REQUIRE(tbytes + k2c_ring_bytes(depth, nw) <= kSmemBudget, "fcd_estep_qF_coded: shared memory budget exceeded");
@@ -1519,16 +1562,40 @@ int fcd_estep_qF_coded(const double* S1, const double* S2, int32_t H,
         estep_qF_coded_kernel<F, NW_><<<(unsigned)grid, NW_ * 32, smem, st>>>(                        \
             S1, S2, P, planeStride, C, U, pitchU, qR, nm, code, pitchQ, reinterpret_cast<const int2*>(counts), \
             reinterpret_cast<const unsigned long long*>(keysF), reinterpret_cast<const unsigned long long*>(keysH), \
-            reinterpret_cast<const longlong2*>(rowoff), reinterpret_cast<const double2*>(Hh), th, tab, depth, lqF, qF); \
+            reinterpret_cast<const longlong2*>(rowoff), reinterpret_cast<const double2*>(Hh), th, solved, tab, depth, lqF, qF); \
     } while (0)
 #define FCD_K2C(F)                                                                                    \
     do {                                                                                              \
-        if (nw == 24) FCD_K2C_(F, 24); else FCD_K2C_(F, 16);                                          \
+        if (nw == 24) FCD_K2C_(F, 24); else if (nw == 20) FCD_K2C_(F, 20); else FCD_K2C_(F, 16);      \
     } while (0)
     if (fast) FCD_K2C(true); else FCD_K2C(false);
 #undef FCD_K2C
 #undef FCD_K2C_
     return check_launch("fcd_estep_qF_coded");
+}
+
+int fcd_estep_qF_coded(const double* S1, const double* S2, int32_t H,
+                       const double* P, int64_t planeStride, int64_t C, int32_t U, int64_t pitchU,
+                       const double* qR, int32_t N, const int32_t* nm,
+                       const uint8_t* code, int64_t pitchQ, const int32_t* counts, const uint64_t* keysF,
+                       const uint64_t* keysH, const int64_t* rowoff, const double* Hh,
+                       const fcd_theta* theta_host, double* lqF, double* qF, void* stream) {
+    return estep_qF_coded_launch(S1, S2, H, P, planeStride, C, U, pitchU, qR, N, nm, code, pitchQ, counts, keysF, keysH,
+                                 rowoff, Hh, theta_host, nullptr, 0.0, 0.0, lqF, qF, stream);
+}
+
+int fcd_estep_qF_coded_solved(const double* S1, const double* S2, int32_t H,
+                              const double* P, int64_t planeStride, int64_t C, int32_t U, int64_t pitchU,
+                              const double* qR, int32_t N, const int32_t* nm,
+                              const uint8_t* code, int64_t pitchQ, const int32_t* counts, const uint64_t* keysF,
+                              const uint64_t* keysH, const int64_t* rowoff, const double* Hh,
+                              const fcd_theta* theta_host, const void* solver_state, double eps_lo, double eps_hi,
+                              double* lqF, double* qF, void* stream) {
+    FCD_REQUIRE(solver_state != nullptr && (reinterpret_cast<uintptr_t>(solver_state) & 7) == 0,
+                "fcd_estep_qF_coded_solved: solver state must be a device pointer (fcd_solver_init)");
+    return estep_qF_coded_launch(S1, S2, H, P, planeStride, C, U, pitchU, qR, N, nm, code, pitchQ, counts, keysF, keysH,
+                                 rowoff, Hh, theta_host, static_cast<const SolverState*>(solver_state), eps_lo, eps_hi,
+                                 lqF, qF, stream);
 }
 
 int fcd_transpose_patients(const double* bt, int64_t C, int32_t U, int64_t pitchU,

@@ -200,6 +200,7 @@ class UnsharedRegionFit(object):
         self.solver_tol = 1e-7        # newton: a step below this is taken without another evaluation
         self.energy_behind_solver = True   # newton: enqueue K4 behind the first batch of evaluations (one wait for both)
         self.uniform_fast_path = True      # constant q_R (the start): row log-sums as running products (fcd_uniform.cu)
+        self.speculative_estep = True      # newton, inside run(): the next iteration's K2 enqueued behind the solve
         self.solver_status = []       # newton: per solve (done code, evaluations)
         self.n_objective_evals = []
         self.profile = None           # _dev.KernelTimers for per-kernel CUDA-event timing
@@ -225,6 +226,9 @@ class UnsharedRegionFit(object):
         self._tot_slot = None
         self._last_nfev = 4           # evaluations of the last device solve (sizes the first batch)
         self._keep_host = None        # host arrays an asynchronous upload is still reading
+        self._spec = None             # E-step launched behind the last device solve (_speculative_estep)
+        self.spec_stats = [0, 0]      # such launches made / adopted by the following _update_lq_F
+        self._more_iters = False      # run(): another iteration may follow the M-step being taken
 
     # ------------------------------------------------------------------ private arrays
     @property
@@ -669,14 +673,21 @@ class UnsharedRegionFit(object):
             # at fit.py:56-68) -- new check, raised before the first update
             raise ValueError("Initial free energy is not finite: b / bt must hold finite correlations.")
         self.n_objective_evals = []
-        for i in range(1, self.max_iters + 1):
-            self._update_lq_F()
-            self._update_lq_R()
-            self._update_theta()
-            self._update_lps()
-            self.energy.append(self._eval_energy())
-            if self._is_converged(i):
-                break
+        self._spec = None
+        try:
+            for i in range(1, self.max_iters + 1):
+                self._update_lq_F()
+                self._update_lq_R()
+                self._more_iters = i < self.max_iters
+                self._update_theta()
+                self._more_iters = False
+                self._update_lps()
+                self.energy.append(self._eval_energy())
+                if self._is_converged(i):
+                    break
+        finally:
+            self._more_iters = False
+            self._spec = None             # (an E-step launched for an iteration that does not follow is dropped)
 
     def _init_lps(self, N, H, U):
         """
@@ -929,6 +940,17 @@ class UnsharedRegionFit(object):
                 self.shards.allgather_edges(lqF_buf, qF_buf, C)
             self._mF.set_dev(lqF, qF, (C, 1, 3))
             return
+        spec = self._spec
+        self._spec = None
+        if spec is not None and self._spec_matches(spec, inp, th):
+            # this E-step ran on the GPU while the host waited for the (eta, epsilon) solve and the free energy
+            (lqF_buf, qF_buf) = spec['bufs']
+            (lqF, qF) = (lqF_buf[:C * 3], qF_buf[:C * 3])
+            self.spec_stats[1] += 1
+            if self.shards is not None:
+                self.shards.allgather_edges(lqF_buf, qF_buf, C)
+            self._mF.set_dev(lqF, qF, (C, 1, 3))
+            return
         if self.coded_estep and Cl > 0 and inp.get('code_verR') == self._mR.version and inp.get('PsE') is not None:
             # the code plane and key lists of the last M-step still describe q_R (fcd_estep_qF_coded)
             with _dev.timed(self.profile, "K2_estep_qF_coded"):
@@ -950,6 +972,47 @@ class UnsharedRegionFit(object):
         if self.shards is not None:
             self.shards.allgather_edges(lqF_buf, qF_buf, C)
         self._mF.set_dev(lqF, qF, (C, 1, 3))
+
+    def _speculative_estep(self, solver_state, lo_e, hi_e):
+        """The NEXT iteration's `_update_lq_F` (fcdiff/fit.py:157-174), enqueued behind the device-resident
+        (eta, epsilon) solve whose result the host has not read yet: the kernel takes eta and epsilon from the
+        solver's state block, pi / gamma are this M-step's (already final, fit.py:200-206 updates them first),
+        q_R and the code plane are the ones the solve itself works on.  Returns the handle `_update_lq_F`
+        adopts when nothing it depends on has changed by then, or None when the coded form does not apply."""
+        if not (self.speculative_estep and self.coded_estep and not self.update_mu_sigma
+                and self._lps_state == 'derived' and self._theta_lps is not None):
+            return None
+        inp = self._in
+        if inp is None or inp.get('PsE') is None or inp.get('code_verR') != self._mR.version or inp['Cl'] <= 0:
+            return None
+        lib = _lib.load()
+        (N, H, U) = self._dims
+        (C, c0, Cl) = (inp['C'], inp['c0'], inp['Cl'])
+        (_, qR) = self._mR.get_dev()
+        nbuf = C * 3 if self.shards is None else self.shards.edge_buffer_len(C)
+        (lqF_buf, qF_buf) = (_dev.empty((nbuf,)), _dev.empty((nbuf,)))
+        th = self._theta()
+        self._wait_healthy(inp)
+        with _dev.timed(self.profile, "K2_estep_qF_coded"):
+            _lib.check(lib.fcd_estep_qF_coded_solved(
+                _dev.ptr(inp['S1']), _dev.ptr(inp['S2']), H, _dev.ptr(inp['P']), max(Cl, 1) * inp['pitchU'],
+                Cl, U, inp['pitchU'], _dev.ptr(qR), N, _dev.ptr(inp['nm']), _dev.ptr(inp['code']), inp['pitchQ'],
+                _dev.ptr(inp['bk_counts']), _dev.ptr(inp['bk_K']), _dev.ptr(inp['bk_KH']), _dev.ptr(inp['bk_rowoff']),
+                _dev.ptr(inp['bk_H']), ctypes.byref(th), solver_state, float(lo_e), float(hi_e),
+                _dev.ptr(lqF_buf[c0 * 3:]), _dev.ptr(qF_buf[c0 * 3:]), _dev.stream()), "fcd_estep_qF_coded_solved")
+        self.spec_stats[0] += 1
+        return dict(bufs=(lqF_buf, qF_buf), inp=inp, cache_key=inp['cache_key'], verR=self._mR.version, qR=qR,
+                    dims=self._dims, rest=(tuple(th.gamma), tuple(th.mu), tuple(th.sigma)), x=None)
+
+    def _spec_matches(self, spec, inp, th):
+        """The launch of `_speculative_estep` is the one `_update_lq_F` would make now: same inputs and planes,
+        same q_R (version and code plane), same gamma / mu / sigma, and (eta, epsilon) exactly the solution the
+        solver left in its state block."""
+        return (spec['x'] is not None and spec['inp'] is inp and spec['cache_key'] == inp['cache_key']
+                and inp.get('code_verR') == spec['verR'] and self._mR.version == spec['verR']
+                and spec['dims'] == self._dims and self.coded_estep
+                and spec['x'] == (float(th.eta), float(th.epsilon))
+                and spec['rest'] == (tuple(th.gamma), tuple(th.mu), tuple(th.sigma)))
 
     def _update_lq_R(self):
         """
@@ -1369,6 +1432,8 @@ class UnsharedRegionFit(object):
         budget = 60
         nfev = 0
         terms = None
+        spec = None
+        self._spec = None
         first = max(2, min(6, self._last_nfev))
         while True:
             # the epsilon box of this pass: the reference's bounds, at most a factor 8 towards 0 or 1
@@ -1402,6 +1467,9 @@ class UnsharedRegionFit(object):
                     # solve finishes inside this batch (the usual case) ONE wait delivers theta_sub and
                     # the free energy; otherwise the result is discarded (NaN E_lM) and K4 runs later
                     pending = self._energy_launch(solver_state=_dev.ptr(sb.state))
+                    if self._more_iters:
+                        # ... and the next iteration's E-step behind K4: it fills the GPU while the host waits
+                        spec = self._speculative_estep(_dev.ptr(sb.state), lo_e, hi_e)
                     terms = self._energy_collect(pending)
                 st = sb.wait()
                 if self.profile is not None:     # launches that found the solve finished are not evaluations
@@ -1409,6 +1477,7 @@ class UnsharedRegionFit(object):
                 done_before = int(st.nfev)
                 if st.done:
                     break
+                spec = None                      # it read an intermediate iterate
                 batch = 2
             nfev += int(st.nfev)
             (eta0, eps0) = (float(st.x[0]), float(st.x[1]))
@@ -1419,10 +1488,14 @@ class UnsharedRegionFit(object):
                 break
             first = 2
             terms = None                         # another pass follows: K4 saw an intermediate solution
+            spec = None
         self._last_nfev = nfev
         self.solver_status.append((int(st.done), nfev))
         self.n_objective_evals.append(nfev)
         self._unpack_theta_sub(np.array([eta0, eps0]))
+        if spec is not None and st.done in (1, 2):
+            spec['x'] = (float(eta0), float(eps0))
+            self._spec = spec
         self._pending_energy = None
         if (terms is not None and np.all(np.isfinite(terms)) and not self.update_mu_sigma
                 and self._theta_lps is not None):

@@ -184,6 +184,21 @@ FCD_API int fcd_estep_qF_coded(const double* S1, const double* S2, int32_t H,
                        const uint64_t* keysH, const int64_t* rowoff, const double* Hh,
                        const fcd_theta* theta_host, double* lqF, double* qF, void* stream);
 
+/* The same launch for the E-step of the NEXT iteration, enqueued behind a device-resident (eta, epsilon) solve
+ * (fcd_elm_coded_solve / fcd_elm_tiered_solve, fcdiff/fit.py:228-241) whose result the host has not read yet:
+ * eta and epsilon are taken from `solver_state` on the device when the kernel starts (theta_host supplies gamma,
+ * mu, sigma; its eta / epsilon are ignored); [eps_lo, eps_hi] is the epsilon box of that solve and sizes the
+ * logarithm table.  The reference runs these steps one after the other (fit.py:73-79); here the E-step fills the
+ * GPU while the host waits for the solve and the free energy.  The caller discards lqF / qF when the solve had not
+ * finished in the launches enqueued before (state.done == 0), ended pinned at the box, or the fit stops. */
+FCD_API int fcd_estep_qF_coded_solved(const double* S1, const double* S2, int32_t H,
+                       const double* P, int64_t planeStride, int64_t C, int32_t U, int64_t pitchU,
+                       const double* qR, int32_t N, const int32_t* nm,
+                       const uint8_t* code, int64_t pitchQ, const int32_t* counts, const uint64_t* keysF,
+                       const uint64_t* keysH, const int64_t* rowoff, const double* Hh,
+                       const fcd_theta* theta_host, const void* solver_state, double eps_lo, double eps_hi,
+                       double* lqF, double* qF, void* stream);
+
 /* The uniform start (fcdiff/fit.py:84-102: lq_R = -ln 2, lq_F = -ln 3 everywhere).  With a CONSTANT q_R every
  * element has the same pair weights w (fit.py:382-406), and the sums of fit.py:165-173 / 489-511 factor through
  *   S9[c][k*3 + l] = sum_u log(a_l + b_l p_k(c,u))       (a_l, b_l: fit.py:427-444 relative to the total density)

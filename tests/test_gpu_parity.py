@@ -274,6 +274,40 @@ def test_newton_solver_full_run_vs_polished_oracle(N, H, U, iters, lookup):
     assert all(done == 1 and nfev <= 12 for (done, nfev) in fit.solver_status), fit.solver_status
 
 
+@pytest.mark.parametrize("N,H,U,iters", [(24, 9, 33, 5), (90, 50, 50, 4), (160, 40, 400, 10)])
+def test_speculative_estep_is_bit_identical(N, H, U, iters):
+    """`run()` enqueues the next iteration's E-step behind the device-resident (eta, epsilon) solve
+    (fcd_estep_qF_coded_solved: theta read from the solver's state block on the device) and adopts it
+    when nothing changed: the same fit with the feature off must give the same numbers bit for bit, the
+    launches must actually be adopted, and a fit that stops leaves no stray result behind."""
+    (_, _, _, _, b, bt) = O.sample(O.Theta(), N, H, U, np.random.RandomState(3 * N + 1))
+
+    def run(spec, stop=None):
+        fit = _fit_for(b, bt, eta_shift=0.1, solver="newton")
+        fit.speculative_estep = spec
+        fit.max_iters = iters if stop is None else stop
+        fit.rel_tol = -1.0
+        fit.run()
+        return fit
+
+    (f1, f0) = (run(True), run(False))
+    assert f0.spec_stats == [0, 0]
+    # the first iteration's E-step takes the uniform-start path and the last M-step launches none
+    assert f1.spec_stats[1] <= f1.spec_stats[0] <= iters - 1, f1.spec_stats
+    if N >= 160:           # (small problems keep the tiered forms -- no code plane, nothing to launch early -- or
+        #                     need more evaluations than the first batch holds: the launch is dropped)
+        assert f1.spec_stats[1] >= 1, (f1.spec_stats, f1.solver_status)
+    assert f1.energy == f0.energy
+    assert (f1.model.pi, f1.model.eta, f1.model.epsilon) == (f0.model.pi, f0.model.eta, f0.model.epsilon)
+    nptest.assert_array_equal(f1._lq_F, f0._lq_F)
+    nptest.assert_array_equal(f1._lq_R, f0._lq_R)
+    # stepping by hand after run(): nothing speculative is pending, the step functions behave as before
+    f1._update_lq_F()
+    f0._update_lq_F()
+    nptest.assert_array_equal(f1._lq_F, f0._lq_F)
+    assert f1._spec is None
+
+
 def test_newton_solver_reaches_active_bounds_and_leaves_the_table_window():
     """Start points far from the minimiser: epsilon has to travel more than the factor 8 one pass of
     the solver may move it (the box that sizes the kernels' logarithm table), and a problem whose
