@@ -289,6 +289,17 @@ class EdgeShards(object):
         lqF[:C * 3].copy_(gathered[:, 0].reshape(-1)[:C * 3])
         qF[:C * 3].copy_(gathered[:, 1].reshape(-1)[:C * 3])
 
+    def allgather_edge_array(self, t, C):
+        """One flat [C*3] edge array padded to ``edge_buffer_len(C)``, gathered in place (this rank's
+        rows valid on entry).  Inside ``run()`` only q_F travels every iteration -- the region sweep
+        reads all edges of its patients -- while every device-side reader of lq_F (K3a, K4) keeps to
+        this rank's rows: lq_F is completed once, when ``run()`` ends."""
+        ch = self.chunk(C, self.world)
+        if t.numel() < self.world * ch * 3 or not t.is_cuda:
+            raise ValueError("allgather_edge_array: the array must be a padded device buffer (edge_buffer_len)")
+        full = t[:self.world * ch * 3]
+        dist.all_gather_into_tensor(full, full[self.rank * ch * 3:(self.rank + 1) * ch * 3], group=self.group)
+
     def allgather_patients(self, lqR, qR, N, U):
         """lqR, qR: flat [N*U*2]; this rank's patient columns are valid on entry, all
         columns on exit.  One collective for both arrays; on the GPU the staging is one

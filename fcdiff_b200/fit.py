@@ -62,6 +62,7 @@ class _Mirror(object):
         self.fill = None     # (shape, value) of a constant array not yet materialised
         self.dev = None      # (lq, q) device tensors, flat
         self.state = None    # peak-state bytes of q (fstate / rstate, include/fcdiff_b200.h)
+        self.complete = None # pending collective that fills the other ranks' rows of the log array
         self.version = 0
 
     def set_host(self, a):
@@ -69,6 +70,7 @@ class _Mirror(object):
         self.fill = None
         self.dev = None
         self.state = None
+        self.complete = None
         self.version += 1
 
     def set_fill(self, shape, value):
@@ -78,13 +80,21 @@ class _Mirror(object):
         self.fill = (tuple(shape), float(value))
         self.shape = tuple(shape)
 
-    def set_dev(self, lq, q, shape):
+    def set_dev(self, lq, q, shape, complete=None):
+        """``complete``: a collective that fills the rows of ``lq`` other ranks own (edge shards inside
+        ``run()``: only q is gathered every iteration); called once before ``lq`` is read whole."""
         self.dev = (lq, q)
         self.shape = shape
         self.host = None
         self.fill = None
         self.state = None
+        self.complete = complete
         self.version += 1
+
+    def finish(self):
+        if self.dev is not None and self.complete is not None:
+            (f, self.complete) = (self.complete, None)
+            f()
 
     def get_state(self):
         """Peak states of the probabilities: (C,) bytes for a (C, 1, 3) array,
@@ -109,6 +119,7 @@ class _Mirror(object):
         if self.host is None and self.fill is not None:
             self.host = np.full(self.fill[0], self.fill[1])
         if self.host is None and self.dev is not None:
+            self.finish()
             self.host = _dev.download(self.dev[0]).reshape(self.shape)
         return self.host
 
@@ -229,6 +240,7 @@ class UnsharedRegionFit(object):
         self._spec = None             # E-step launched behind the last device solve (_speculative_estep)
         self.spec_stats = [0, 0]      # such launches made / adopted by the following _update_lq_F
         self._more_iters = False      # run(): another iteration may follow the M-step being taken
+        self._in_run = False          # inside run()'s loop (every rank executes the same steps)
 
     # ------------------------------------------------------------------ private arrays
     @property
@@ -674,6 +686,7 @@ class UnsharedRegionFit(object):
             raise ValueError("Initial free energy is not finite: b / bt must hold finite correlations.")
         self.n_objective_evals = []
         self._spec = None
+        self._in_run = True
         try:
             for i in range(1, self.max_iters + 1):
                 self._update_lq_F()
@@ -687,7 +700,9 @@ class UnsharedRegionFit(object):
                     break
         finally:
             self._more_iters = False
+            self._in_run = False
             self._spec = None             # (an E-step launched for an iteration that does not follow is dropped)
+        self._mF.finish()                 # edge shards: the other ranks' rows of lq_F (collective, every rank is here)
 
     def _init_lps(self, N, H, U):
         """
@@ -936,9 +951,7 @@ class UnsharedRegionFit(object):
                 _lib.check(lib.fcd_estep_qF_rowsums(_dev.ptr(inp['S1']), _dev.ptr(inp['S2']), H, _dev.ptr(S9), Cl, w3,
                                                     ctypes.byref(th), _dev.ptr(lqF[c0 * 3:]), _dev.ptr(qF[c0 * 3:]),
                                                     _dev.stream()), "fcd_estep_qF_rowsums")
-            if self.shards is not None:
-                self.shards.allgather_edges(lqF_buf, qF_buf, C)
-            self._mF.set_dev(lqF, qF, (C, 1, 3))
+            self._set_lq_F_dev(lqF_buf, qF_buf, C)
             return
         spec = self._spec
         self._spec = None
@@ -947,9 +960,7 @@ class UnsharedRegionFit(object):
             (lqF_buf, qF_buf) = spec['bufs']
             (lqF, qF) = (lqF_buf[:C * 3], qF_buf[:C * 3])
             self.spec_stats[1] += 1
-            if self.shards is not None:
-                self.shards.allgather_edges(lqF_buf, qF_buf, C)
-            self._mF.set_dev(lqF, qF, (C, 1, 3))
+            self._set_lq_F_dev(lqF_buf, qF_buf, C)
             return
         if self.coded_estep and Cl > 0 and inp.get('code_verR') == self._mR.version and inp.get('PsE') is not None:
             # the code plane and key lists of the last M-step still describe q_R (fcd_estep_qF_coded)
@@ -960,18 +971,30 @@ class UnsharedRegionFit(object):
                     _dev.ptr(inp['bk_counts']), _dev.ptr(inp['bk_K']), _dev.ptr(inp['bk_KH']), _dev.ptr(inp['bk_rowoff']),
                     _dev.ptr(inp['bk_H']), ctypes.byref(th), _dev.ptr(lqF[c0 * 3:]), _dev.ptr(qF[c0 * 3:]), _dev.stream()),
                     "fcd_estep_qF_coded")
-            if self.shards is not None:
-                self.shards.allgather_edges(lqF_buf, qF_buf, C)
-            self._mF.set_dev(lqF, qF, (C, 1, 3))
+            self._set_lq_F_dev(lqF_buf, qF_buf, C)
             return
         with _dev.timed(self.profile, "K2_estep_qF"):
             _lib.check(lib.fcd_estep_qF(
                 _dev.ptr(inp['S1']), _dev.ptr(inp['S2']), H, _dev.ptr(inp['P']), max(Cl, 1) * inp['pitchU'],
                 Cl, U, inp['pitchU'], _dev.ptr(qR), _dev.ptr(rstate), rstate.shape[1], N, _dev.ptr(inp['nm']),
                 ctypes.byref(th), _dev.ptr(lqF[c0 * 3:]), _dev.ptr(qF[c0 * 3:]), _dev.stream()), "fcd_estep_qF")
-        if self.shards is not None:
+        self._set_lq_F_dev(lqF_buf, qF_buf, C)
+
+    def _set_lq_F_dev(self, lqF_buf, qF_buf, C):
+        """Publishes an E-step's result.  Edge shards: q_F is gathered now (the region sweep reads every
+        edge of its patients); lq_F -- whose device-side readers K3a and K4 keep to this rank's rows --
+        inside ``run()`` only when the loop ends, otherwise now as well (a rank may read ``_lq_F`` alone)."""
+        (lqF, qF) = (lqF_buf[:C * 3], qF_buf[:C * 3])
+        if self.shards is None:
+            self._mF.set_dev(lqF, qF, (C, 1, 3))
+            return
+        if not self._in_run:
             self.shards.allgather_edges(lqF_buf, qF_buf, C)
-        self._mF.set_dev(lqF, qF, (C, 1, 3))
+            self._mF.set_dev(lqF, qF, (C, 1, 3))
+            return
+        self.shards.allgather_edge_array(qF_buf, C)
+        shards = self.shards
+        self._mF.set_dev(lqF, qF, (C, 1, 3), complete=lambda: shards.allgather_edge_array(lqF_buf, C))
 
     def _speculative_estep(self, solver_state, lo_e, hi_e):
         """The NEXT iteration's `_update_lq_F` (fcdiff/fit.py:157-174), enqueued behind the device-resident
@@ -1078,6 +1101,7 @@ class UnsharedRegionFit(object):
     # ------------------------------------------------------------------ posterior summaries (new)
     def _map_labels(self, mirror, width):
         lib = _lib.load()
+        mirror.finish()
         (lq, _) = mirror.get_dev()
         n = lq.numel() // width
         out = _dev.empty((max(n, 1),), torch.uint8)
