@@ -158,7 +158,9 @@ __device__ __forceinline__ double log_pos(double x, const double* s_tab) {
     const int e = (hi >> 20) - 1023;
     const double m = __hiloint2double((hi & 0x000fffff) | (1023 << 20), __double2loint(x));
     const LogParts p = log_reduce(m);
-    return fma((double)e, 6.93147180559945286227e-01, s_tab[p.idx] + log1p_small(p.u));
+    // (double)e without the conversion pipe: 2^52 + 2^31 + e as an integer bit pattern, minus the bias (exact)
+    const double ed = __hiloint2double(0x43300000, e ^ 0x80000000) - 4503601774854144.0;
+    return fma(ed, 6.93147180559945286227e-01, s_tab[p.idx] + log1p_small(p.u));
 }
 
 // 1 / y to rounding: MUFU.RCP64H (relative error e ~ 2^-18) and r0 (1 + e + e^2), e = 1 - y r0 exact

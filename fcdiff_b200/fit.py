@@ -208,7 +208,8 @@ class UnsharedRegionFit(object):
         self.elm_path = "auto"        # K3b form: "streams" (coded plane) | "tiered" | "auto" (coded unless most elements are undecided)
         self.convergence_rule = "reference"
         self.theta_solver = "newton"  # (eta, epsilon): device-resident Newton | host-driven SciPy L-BFGS-B
-        self.solver_tol = 1e-7        # newton: a step below this is taken without another evaluation
+        self.solver_tol = 2e-4        # newton: a step with |dx_i| <= tol * min(x_i, 1 - x_i) is taken without another
+        #                               evaluation (leaves a relative error ~ tol^2 = 4e-8 in eta, epsilon)
         self.energy_behind_solver = True   # newton: enqueue K4 behind the first batch of evaluations (one wait for both)
         self.uniform_fast_path = True      # constant q_R (the start): row log-sums as running products (fcd_uniform.cu)
         self.speculative_estep = True      # newton, inside run(): the next iteration's K2 enqueued behind the solve

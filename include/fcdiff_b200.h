@@ -362,8 +362,9 @@ FCD_API int fcd_elm_coded(const double* PsE, const uint8_t* code, int64_t nE, co
  * same CTA first exchanges the six partial sums over the peer windows (fcd_comm_window_*), in rank
  * order, so every rank takes bit-identical steps.
  *   state: fcd_solver_state_bytes() of device memory, set by fcd_solver_init (box lo/hi per
- *     parameter, start point, `tol`: a step of max |dx| <= tol is taken without another
- *     evaluation and ends the solve; max_evals bounds the evaluations);
+ *     parameter, start point, `tol`: a step with |dx_i| <= tol * min(x_i, 1 - x_i) for both parameters is
+ *     taken without another evaluation and ends the solve -- it leaves a relative error ~ tol^2 behind;
+ *     max_evals bounds the evaluations);
  *   fcd_elm_coded_solve / fcd_elm_tiered_solve: n_launches evaluations of the coded-plane /
  *     tiered form (arguments as fcd_elm_coded / fcd_elm_obj_grad) at the state's iterate; launches
  *     after the solve has finished exit at once.  [eps_lo, eps_hi] must contain the box of epsilon

@@ -166,6 +166,17 @@ ldg_kernel(const double* __restrict__ P, int64_t planeStride, int64_t C, int U, 
     if (acc == 123.456) out[0] = acc;
 }
 
+// fills with pseudo-random responsibilities in (0, 1) / codes in 0..5 (the planes of a real fit are not zeros)
+__global__ void fill_kernel(double* P, int64_t n, uint8_t* code, int64_t nc) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t x = (uint64_t)i * 0x9E3779B97F4A7C15ull;
+        x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;
+        P[i] = (double)(x >> 11) * (1.0 / 9007199254740992.0);
+    }
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nc; i += (int64_t)gridDim.x * blockDim.x)
+        code[i] = (uint8_t)(((uint64_t)i * 0x9E3779B97F4A7C15ull >> 40) % 6);
+}
+
 template <typename F>
 static float time_it(F f, int reps) {
     cudaEvent_t e0, e1;
@@ -204,6 +215,14 @@ int main() {
     CK(cudaMemset(code, 0, C * Q));
     int sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+    for (int pass = 0; pass < 2; ++pass) {
+    if (pass == 1) {
+        printf("---- planes filled with pseudo-random values\n");
+        fill_kernel<<<sms * 8, 256>>>(P, 3 * planeStride, code, C * Q);
+        CK(cudaDeviceSynchronize());
+    } else {
+        printf("---- planes of zeros\n");
+    }
     const double bytes2 = (double)C * (16.0 * U), bytesC = (double)C * 512.0;
     auto report = [&](const char* name, float ms, double bytes) { printf("  %-44s %.0f GB/s\n", name, bytes / (ms * 1e-3) / 1e9); };
     const int reps = 10;
@@ -248,6 +267,7 @@ int main() {
         CK(cudaMalloc(&D, 2 * planeStride * 8));
         float ms = time_it([&] { CK(cudaMemcpyAsync(D, P, 2 * planeStride * 8, cudaMemcpyDeviceToDevice)); }, reps);
         report("cudaMemcpy D2D of the two planes (rd+wr)", ms, 2.0 * 2 * planeStride * 8);
+    }
     }
     return 0;
 }
