@@ -339,7 +339,20 @@ def run_k1(fcdiff, torch, peaks):
     (S, N, T) = (H_SUBJ + U_SUBJ, 400, 1200)
     C = N * (N - 1) // 2
     g = torch.Generator(device="cuda").manual_seed(1)
+    # planted structure instead of white noise: eight latent signals, every region loads on one of them with
+    # +0.55 or -0.27 (same signal: correlations +0.30 / -0.15 / +0.07 -- the model's positive and negative
+    # states -- different signals: 0); a patient's region is anomalous with probability 0.05 (loading sign flipped)
+    K = 8
+    fac = torch.arange(N, device="cuda") % K
+    load = torch.where(torch.rand((N,), device="cuda", generator=g) < 0.5, 0.55, -0.27).to(torch.float32)
+    a = load[None, :].repeat(S, 1)
+    flip = torch.rand((U_SUBJ, N), device="cuda", generator=g) < 0.05
+    a[H_SUBJ:][flip] *= -1.0
     ts = torch.randn((S, N, T), dtype=torch.float32, device="cuda", generator=g)
+    ts *= torch.sqrt(1.0 - a * a)[:, :, None]
+    z = torch.randn((S, K, T), dtype=torch.float32, device="cuda", generator=g)
+    ts += a[:, :, None] * z[:, fac, :]
+    del z
     out = torch.empty((C, S), dtype=torch.float64, device="cuda")
     for _ in range(2):
         corr.correlations_device(ts, fisher=True, out=out)
@@ -384,8 +397,9 @@ def run_k1(fcdiff, torch, peaks):
     f.run()
     torch.cuda.synchronize()
     res["timeseries_to_fit_ms"] = 1e3 * (time.perf_counter() - t0)
-    res["timeseries_to_fit_what"] = ("K1 on %d subjects + fit.run() with 3 EM iterations on its output (white-noise "
-                                     "series: the fit has nothing to find, the time is what counts)" % S)
+    res["timeseries_to_fit_what"] = ("K1 on %d subjects + fit.run() with 3 EM iterations on its output (series with "
+                                     "planted positive / negative correlations and 5 %% anomalous patient regions)" % S)
+    res["energy_trace"] = [float(e) for e in f.energy]
     res["energy_finite"] = bool(np.all(np.isfinite(f.energy)))
     del ts, out, f
     torch.cuda.empty_cache()

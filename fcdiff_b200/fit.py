@@ -504,6 +504,40 @@ class UnsharedRegionFit(object):
             inp['PT'] = PT
             inp['PsT'] = inp['kcache'] = None
             return inp
+        pre = inp.pop('PT_pre', None)
+        if pre is not None:
+            # built on the side stream while the main stream formed the edge shard's planes (_prefetch_patient_major)
+            torch.cuda.current_stream().wait_event(pre['ev'])
+            if pre['key'] == inp['cache_key']:
+                inp['PT'] = pre['PT']
+                inp['PsT'] = inp['kcache'] = None
+                return inp
+        inp['PT'] = self._build_patient_major(inp)
+        inp['PsT'] = inp['kcache'] = None
+        return inp
+
+    def _prefetch_patient_major(self):
+        """Edge shards with device-resident inputs: the all-to-all that turns the edge-sharded `bt` into this
+        rank's patient block, the planes of that block and their transposes are enqueued on the side stream at
+        the START of run(): NVLink traffic and its kernels overlap the main stream's set-up (the edge shard's
+        planes, the uniform start's row sums, the initial free energy) instead of preceding the first sweep."""
+        inp = self._ensure_inputs()
+        if (self.shards is None or self._shared is not None or not torch.is_tensor(self.bt)
+                or inp.get('PT') is not None or inp.get('PT_pre') is not None):
+            return
+        (cur, side) = (torch.cuda.current_stream(), _dev.side_stream())
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            PT = self._build_patient_major(inp)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        PT.record_stream(cur)                      # allocated under the side stream, used by the main one
+        inp['PT_pre'] = dict(PT=PT, ev=ev, key=self._cache_key)
+
+    def _build_patient_major(self, inp):
+        """PT [3][U_local][pitchC] on the CURRENT stream."""
+        lib = _lib.load()
+        (C, U, u0, Ul) = (inp['C'], inp['U'], inp['u0'], inp['Ul'])
         if self.shards is None:
             (src, pitchU, uu0, Us) = (inp['P'], inp['pitchU'], u0, U)
         else:
@@ -528,9 +562,7 @@ class UnsharedRegionFit(object):
                     _lib.check(lib.fcd_transpose_patients(_dev.ptr(src[k]), C, Us, pitchU, uu0, Ul,
                                                           _dev.ptr(PT[k]), pitchC, _dev.stream()),
                                "fcd_transpose_patients")
-        inp['PT'] = PT
-        inp['PsT'] = inp['kcache'] = None
-        return inp
+        return PT
 
     def _result(self, n, dtype=torch.float64, tag=""):
         key = (n, dtype, tag, torch.cuda.current_device())
@@ -678,6 +710,8 @@ class UnsharedRegionFit(object):
             # host inputs still uploading: everything that needs the patient correlations only
             # (planes, patient-major planes of the region sweep) is enqueued under the upload
             self._ensure_patient_major()
+        elif self.shards is not None and torch.is_tensor(self.bt):
+            self._prefetch_patient_major()
 
         self.energy = [self._eval_energy()]
         if not np.isfinite(self.energy[0]):
