@@ -413,7 +413,7 @@ record_weights_kernel(const unsigned long long* __restrict__ keys, long long nd,
 // the half records as chunks of 128;
 // warp g takes the chunks g, g + G, ...; every warp runs a private ring of kEvDepth stages and
 // refills a stage as soon as it has consumed it: the bytes in flight do not depend on registers.
-constexpr int kEvChunk = 256;
+constexpr int kEvChunk = 512;
 constexpr int kEvMaxDepth = 4;                                // stages per warp ring (fewer when the log table window is large)
 constexpr int kEvWarps = 16;
 constexpr int kEvThreads = kEvWarps * 32;
