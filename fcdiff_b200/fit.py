@@ -726,7 +726,7 @@ class UnsharedRegionFit(object):
             for i in range(1, self.max_iters + 1):
                 self._update_lq_F()
                 self._update_lq_R()
-                self._more_iters = i < self.max_iters
+                self._more_iters = i < self.max_iters and not self._expect_stop()
                 self._update_theta()
                 self._more_iters = False
                 self._update_lps()
@@ -768,6 +768,21 @@ class UnsharedRegionFit(object):
         self._lps_state = 'derived'
         self._explicit = {}
         self._mat = None
+
+    def _expect_stop(self):
+        """Will `_is_converged` most likely end the loop after the iteration being taken?  (Then the next
+        iteration's E-step is not launched ahead, `_speculative_estep`.)  The reference's rule
+        (fit.py:138-140) divides by the signed energy: ANY decrease of a negative energy stops the fit;
+        the magnitude rule stops when the relative decrease falls below `rel_tol` -- EM's decreases shrink
+        from iteration to iteration, so a last decrease within 4 x of the tolerance predicts the stop."""
+        if not (self.rel_tol > 0) or not self.energy or not np.isfinite(self.energy[-1]):
+            return False
+        e = self.energy[-1]
+        if self.convergence_rule != "magnitude" and e < 0:
+            return True
+        if len(self.energy) < 2 or e == 0:
+            return False
+        return (self.energy[-2] - e) / abs(e) < 4.0 * self.rel_tol
 
     def _is_converged(self, s):
         """
