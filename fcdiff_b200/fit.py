@@ -1117,9 +1117,10 @@ class UnsharedRegionFit(object):
         (lqF, qF) = self._mF.get_dev()
         (lqR, qR) = self._mR.get_dev()
         th = self._theta()
-        fstate = self._mF.get_state()
+        with _dev.timed(self.profile, "K2b_prepare"):          # peak states of the new q_F, the sweep's in-place arrays
+            fstate = self._mF.get_state()
+            lqR_new, qR_new = lqR.clone(), qR.clone()
         (PT, pitchC) = (inp['PT'], inp['PT'].shape[2])
-        lqR_new, qR_new = lqR.clone(), qR.clone()
         if inp.get('PsT') is None:                 # dominant-state plane, gathered on first use (q_F settles early)
             inp['PsT'] = _dev.empty((max(Ul, 1), pitchC))
             inp['kcache'] = torch.full((max(C, 1),), 255, dtype=torch.uint8, device=_dev.device())

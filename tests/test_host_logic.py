@@ -262,3 +262,51 @@ def test_small_vector_exchange_abi_limits():
     assert lib.fcd_comm_window_bytes() >= 2 * lib.fcd_comm_max_world() * (lib.fcd_comm_max_vals() + 1) * 8
     assert lib.fcd_comm_handle_bytes() == 64
     assert lib.fcd_code_pitch(500) == 512 and lib.fcd_code_pitch(16) == 16 and lib.fcd_code_pitch(17) == 32
+
+
+def test_expect_stop_predicts_the_convergence_rules():
+    """`_expect_stop` decides whether run() launches the next iteration's E-step ahead (fit.py:124-140 is the
+    rule it predicts): never with the test disabled, always once the energy is negative under the reference's
+    signed rule, under the magnitude rule when the last relative decrease is within 4 x of the tolerance."""
+    fit = fcdiff.fit.UnsharedRegionFit()
+    fit.rel_tol = -1.0
+    fit.energy = [6.0e8, -1.4e8]
+    assert not fit._expect_stop()
+    fit.rel_tol = 1e-5
+    assert fit._expect_stop()                      # reference rule: any decrease of a negative energy stops
+    fit.energy = [6.0e8]
+    assert not fit._expect_stop()                  # positive energy, no history
+    fit.energy = [6.0e8, 5.9e8]
+    assert not fit._expect_stop()                  # positive energy still falling fast
+    fit.convergence_rule = "magnitude"
+    fit.energy = [6.0e8, -1.4e8]
+    assert not fit._expect_stop()
+    fit.energy = [-1.4452e8, -1.44521e8]           # relative decrease 7e-6 < 4e-5
+    assert fit._expect_stop()
+    fit.energy = [-1.44e8, -1.45e8]                # 7e-3
+    assert not fit._expect_stop()
+    fit.energy = [float("nan")]
+    assert not fit._expect_stop()
+
+
+def test_speculative_estep_handle_is_dropped_on_any_change():
+    """`_spec_matches`: the E-step launched behind the device solve is adopted only for the same inputs / planes /
+    q_R and exactly the published (eta, epsilon); no GPU involved -- the handle is a dict."""
+    from fcdiff_b200 import _lib
+    fit = fcdiff.fit.UnsharedRegionFit()
+    fit._dims = (4, 3, 5)
+    inp = {"cache_key": ("k",), "code_verR": fit._mR.version}
+    th = _lib.make_theta(0.05, 0.3, 0.03, [0.1, 0.8, 0.1], [-0.15, 0.0, 0.3], [0.025, 0.035, 0.05])
+    rest = (tuple(th.gamma), tuple(th.mu), tuple(th.sigma))
+    spec = dict(bufs=None, inp=inp, cache_key=("k",), verR=fit._mR.version, dims=(4, 3, 5), rest=rest, x=(0.3, 0.03))
+    assert fit._spec_matches(spec, inp, th)
+    assert not fit._spec_matches(dict(spec, x=None), inp, th)                   # the solve had not finished
+    assert not fit._spec_matches(dict(spec, x=(0.3, 0.030000001)), inp, th)      # another solution
+    assert not fit._spec_matches(spec, dict(inp), th)                            # other input set
+    assert not fit._spec_matches(dict(spec, cache_key=("other",)), inp, th)      # planes rebuilt
+    th2 = _lib.make_theta(0.05, 0.3, 0.03, [0.2, 0.7, 0.1], [-0.15, 0.0, 0.3], [0.025, 0.035, 0.05])
+    assert not fit._spec_matches(spec, inp, th2)                                 # gamma changed
+    fit._mR.set_host(np.zeros((4, 5, 2)))                                        # q_R assigned: version moves on
+    assert not fit._spec_matches(spec, inp, th)
+    fit.coded_estep = False
+    assert not fit._spec_matches(dict(spec, verR=fit._mR.version), dict(inp, code_verR=fit._mR.version), th)
