@@ -176,36 +176,62 @@ code_plane_kernel(const double* __restrict__ P, int64_t planeStride, double* __r
     }
 }
 
-// blockoff[b] = exclusive prefix sums of blocktot, total[0..1] the sums (as doubles: < 2^53).  One CTA.
+// blockoff[b] = exclusive prefix sums of blocktot, total[0..1] the sums (as doubles: < 2^53).  One CTA: every
+// thread takes a run of consecutive blocks (serial sums), the runs are scanned by warp shuffles and the 32 warp
+// totals by the first warp -- three barriers in all (the first form, a Hillis-Steele scan of 1024 entries per pass
+// with two barriers per step, took 17 us on the wait the host makes for the record counts).
 __global__ void __launch_bounds__(1024)
 record_scan_kernel(const longlong2* __restrict__ blocktot, int64_t nblocks, longlong2* __restrict__ blockoff,
                    double* __restrict__ total) {
-    __shared__ long long s_part[2][1024];
-    const int t = threadIdx.x;
-    long long carry[2] = {0, 0};
-    for (int64_t b0 = 0; b0 < nblocks; b0 += 1024) {
-        const int64_t b = b0 + t;
-        const longlong2 v = b < nblocks ? blocktot[b] : make_longlong2(0, 0);
-        const long long mine[2] = {v.x, v.y};
-        s_part[0][t] = mine[0];
-        s_part[1][t] = mine[1];
-        __syncthreads();
-        for (int d = 1; d < 1024; d <<= 1) {                 // Hillis-Steele inclusive scan
-            const long long w0 = t >= d ? s_part[0][t - d] : 0, w1 = t >= d ? s_part[1][t - d] : 0;
-            __syncthreads();
-            s_part[0][t] += w0;
-            s_part[1][t] += w1;
-            __syncthreads();
-        }
-        if (b < nblocks)
-            blockoff[b] = make_longlong2(carry[0] + s_part[0][t] - mine[0], carry[1] + s_part[1][t] - mine[1]);
-        carry[0] += s_part[0][1023];
-        carry[1] += s_part[1][1023];
-        __syncthreads();
+    __shared__ long long s_warp[2][32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int64_t per = (nblocks + 1023) / 1024;
+    const int64_t b0 = (int64_t)t * per, b1 = b0 + per < nblocks ? b0 + per : nblocks;
+    long long run[2] = {0, 0};
+    for (int64_t b = b0; b < b1; ++b) {
+        const longlong2 v = blocktot[b];
+        run[0] += v.x;
+        run[1] += v.y;
     }
-    if (t == 0) {
-        total[0] = (double)carry[0];
-        total[1] = (double)carry[1];
+    long long inc[2] = {run[0], run[1]};                      // inclusive scan of the runs inside the warp
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const long long w0 = __shfl_up_sync(0xffffffffu, inc[0], d), w1 = __shfl_up_sync(0xffffffffu, inc[1], d);
+        if (lane >= d) {
+            inc[0] += w0;
+            inc[1] += w1;
+        }
+    }
+    if (lane == 31) {
+        s_warp[0][warp] = inc[0];
+        s_warp[1][warp] = inc[1];
+    }
+    __syncthreads();
+    if (warp == 0) {                                          // exclusive scan of the 32 warp totals
+        long long w[2] = {s_warp[0][lane], s_warp[1][lane]};
+        const long long mine[2] = {w[0], w[1]};
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long v0 = __shfl_up_sync(0xffffffffu, w[0], d), v1 = __shfl_up_sync(0xffffffffu, w[1], d);
+            if (lane >= d) {
+                w[0] += v0;
+                w[1] += v1;
+            }
+        }
+        s_warp[0][lane] = w[0] - mine[0];
+        s_warp[1][lane] = w[1] - mine[1];
+        if (lane == 31) {
+            total[0] = (double)w[0];
+            total[1] = (double)w[1];
+        }
+    }
+    __syncthreads();
+    long long off[2] = {s_warp[0][warp] + inc[0] - run[0], s_warp[1][warp] + inc[1] - run[1]};
+    for (int64_t b = b0; b < b1; ++b) {
+        const longlong2 v = blocktot[b];
+        blockoff[b] = make_longlong2(off[0], off[1]);
+        off[0] += v.x;
+        off[1] += v.y;
     }
 }
 

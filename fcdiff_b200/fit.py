@@ -986,12 +986,20 @@ class UnsharedRegionFit(object):
         inp = self._ensure_cache()
         (N, H, U) = self._dims
         (C, c0, Cl) = (inp['C'], inp['c0'], inp['Cl'])
+        th = self._theta()
+        spec = self._spec
+        self._spec = None
+        if spec is not None and self._spec_matches(spec, inp, th):
+            # this E-step ran on the GPU while the host waited for the (eta, epsilon) solve and the free energy
+            # (first thing here: the host is on the critical path until the next sweep is enqueued)
+            self.spec_stats[1] += 1
+            self._set_lq_F_dev(spec['bufs'][0], spec['bufs'][1], C)
+            return
         (lqR, qR) = self._mR.get_dev()
         rstate = self._mR.get_state()
         nbuf = C * 3 if self.shards is None else self.shards.edge_buffer_len(C)   # padded: gathered in place
         (lqF_buf, qF_buf) = (_dev.empty((nbuf,)), _dev.empty((nbuf,)))
         (lqF, qF) = (lqF_buf[:C * 3], qF_buf[:C * 3])
-        th = self._theta()
         self._wait_healthy(inp)
         uni = self._uniform_rowsums() if Cl > 0 else None
         if uni is not None:
@@ -1001,15 +1009,6 @@ class UnsharedRegionFit(object):
                 _lib.check(lib.fcd_estep_qF_rowsums(_dev.ptr(inp['S1']), _dev.ptr(inp['S2']), H, _dev.ptr(S9), Cl, w3,
                                                     ctypes.byref(th), _dev.ptr(lqF[c0 * 3:]), _dev.ptr(qF[c0 * 3:]),
                                                     _dev.stream()), "fcd_estep_qF_rowsums")
-            self._set_lq_F_dev(lqF_buf, qF_buf, C)
-            return
-        spec = self._spec
-        self._spec = None
-        if spec is not None and self._spec_matches(spec, inp, th):
-            # this E-step ran on the GPU while the host waited for the (eta, epsilon) solve and the free energy
-            (lqF_buf, qF_buf) = spec['bufs']
-            (lqF, qF) = (lqF_buf[:C * 3], qF_buf[:C * 3])
-            self.spec_stats[1] += 1
             self._set_lq_F_dev(lqF_buf, qF_buf, C)
             return
         if self.coded_estep and Cl > 0 and inp.get('code_verR') == self._mR.version and inp.get('PsE') is not None:
@@ -1117,15 +1116,15 @@ class UnsharedRegionFit(object):
         (lqF, qF) = self._mF.get_dev()
         (lqR, qR) = self._mR.get_dev()
         th = self._theta()
-        with _dev.timed(self.profile, "K2b_prepare"):          # peak states of the new q_F, the sweep's in-place arrays
+        with _dev.timed(self.profile, "K2b_prepare"):          # peak states of the new q_F
             fstate = self._mF.get_state()
-            lqR_new, qR_new = lqR.clone(), qR.clone()
         (PT, pitchC) = (inp['PT'], inp['PT'].shape[2])
         if inp.get('PsT') is None:                 # dominant-state plane, gathered on first use (q_F settles early)
             inp['PsT'] = _dev.empty((max(Ul, 1), pitchC))
             inp['kcache'] = torch.full((max(C, 1),), 255, dtype=torch.uint8, device=_dev.device())
         if lookup == 0 and 3 <= N <= 8192 and self.fused_sweep:
             # every edge's weights are computed once inside the sweep and kept in a shared-memory ring: no WT tensor
+            lqR_new, qR_new = lqR.clone(), qR.clone()
             with _dev.timed(self.profile, "K2b_sweep_fused"):
                 _lib.check(lib.fcd_pstar_refresh(_dev.ptr(PT), max(Ul, 1) * pitchC, Ul, C, pitchC, _dev.ptr(fstate),
                                                  _dev.ptr(inp['PsT']), _dev.ptr(inp['kcache']), _dev.stream()),
@@ -1142,6 +1141,9 @@ class UnsharedRegionFit(object):
                                                   _dev.ptr(qF), _dev.ptr(fstate), _dev.ptr(inp['PsT']),
                                                   _dev.ptr(inp['kcache']), ctypes.byref(th),
                                                   _dev.ptr(inp['WT']), _dev.stream()), "fcd_region_weights")
+            # (the sweep's in-place arrays are copied in the shadow of the weights kernel: until that launch the
+            # host is on the critical path -- the GPU has only the E-step launched ahead to work on)
+            lqR_new, qR_new = lqR.clone(), qR.clone()
             with _dev.timed(self.profile, "K2b_sweep"):
                 _lib.check(lib.fcd_estep_qR(_dev.ptr(inp['WT']), C, N, U, u0, Ul, log_pi2, lookup,
                                             _dev.ptr(qR_new), _dev.ptr(lqR_new), _dev.stream()), "fcd_estep_qR")
