@@ -71,6 +71,9 @@ SIGNATURES = {
     "fcd_estep_qR_fused": (c_int, [_P, _P, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32,
                                    _D3, POINTER(FcdTheta), _P, _P, _P]),
     "fcd_pstar_refresh": (c_int, [_P, c_int64, c_int32, c_int64, c_int64, _P, _P, _P, _P]),
+    "fcd_pstar_refresh_em": (c_int, [_P, c_int64, c_int64, c_int32, c_int32, c_int64, c_int64, _P, _P, _P, _P]),
+    "fcd_region_weights_em": (c_int, [_P, c_int64, c_int64, c_int32, c_int32, c_int64, c_int64, _P, _P, _P, _P,
+                                      POINTER(FcdTheta), _P, _P]),
     "fcd_mstep_stats": (c_int, [_P, c_int64, _P, c_int64, _P, _P, _P]),
     "fcd_elm_obj_grad": (c_int, [_P, c_int64, c_int64, c_int32, c_int64, _P, _P, _P, _P, c_int64, c_int32, _P,
                                  POINTER(FcdTheta), c_int32, _P, _P, _P]),

@@ -614,6 +614,55 @@ pstar_commit_kernel(const uint8_t* __restrict__ fstate, int64_t C, uint8_t* __re
     if (c < C) kcache[c] = fstate[c] < 3 ? fstate[c] : 3;
 }
 
+// The same plane gathered straight from the E-step's EDGE-major planes Pe[k][c][u0 + u] (the patient-major copies
+// PT existed for this gather alone once every edge is peaked: three transposes and a gather, 1.9 GB + 0.6 GB of
+// traffic per fit, for what is ONE transposing pass over the dominant-state rows).  One CTA per 32 edges: it leaves
+// at once when none of its columns changed state (the usual launch), otherwise walks the patients in 32 x 32 tiles
+// through padded shared memory -- reads coalesced along u, writes along c; columns that did not change are
+// neither read nor written.
+__global__ void __launch_bounds__(256)
+pstar_refresh_em_kernel(const double* __restrict__ Pe, int64_t planeStride, int64_t pitchU, int u0, int Ul, int64_t C,
+                        int64_t pitchC, const uint8_t* __restrict__ fstate, const uint8_t* __restrict__ kcache,
+                        double* __restrict__ PsT) {
+    __shared__ double tile[32][33];
+    __shared__ int s_k[32];
+    __shared__ int s_any;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+    const int64_t cb = (int64_t)blockIdx.x * 32;
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int64_t c = cb + threadIdx.x;
+        int k = -1;                                               // -1: unchanged or beyond C
+        if (c < C) {
+            const int f = fstate[c];
+            const int kk = f >= 3 ? 3 : f;
+            if (kk != kcache[c]) k = kk;
+        }
+        s_k[threadIdx.x] = k;
+        if (k >= 0) s_any = 1;
+    }
+    __syncthreads();
+    if (!s_any) return;
+    for (int ub = 0; ub < Ul; ub += 32) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {                         // tile[c][u]: coalesced along u
+            const int k = s_k[ty + j];
+            const int u = ub + tx;
+            double v = -1.0;                                      // unpeaked edge: the negative mark (pstar_refresh_kernel)
+            if (k >= 0 && k < 3 && u < Ul) v = ldg_stream1(Pe + (int64_t)k * planeStride + (cb + ty + j) * pitchU + u0 + u);
+            tile[ty + j][tx] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+            const int u = ub + ty + j;
+            if (s_k[tx] >= 0 && u < Ul) PsT[(int64_t)u * pitchC + cb + tx] = tile[tx][ty + j];
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------- K2b/W
 // W_l[c,u] = sum_k qF[c,k] log(a_l + b_l p_k(c,u)) from the patient-major
 // responsibility planes PT[k][u][c].  The omitted per-(c,u) constant L sum_k qF[c,k]
@@ -627,7 +676,7 @@ pstar_commit_kernel(const uint8_t* __restrict__ fstate, int64_t C, uint8_t* __re
 // Edges whose q_F is peaked (fstate < 3) need the plane of k* only: 3 logs.
 template <bool FAST>
 __global__ void __launch_bounds__(256)
-region_weights_kernel(const double* __restrict__ PT, int64_t planeStride,
+region_weights_kernel(const double* __restrict__ PT, int64_t planeStride, int64_t strideU, int64_t strideC,
                       int Ul, int64_t C, int64_t pitchC,
                       const double* __restrict__ qF, const uint8_t* __restrict__ fstate,
                       const double* __restrict__ PsT,
@@ -651,7 +700,7 @@ region_weights_kernel(const double* __restrict__ PT, int64_t planeStride,
         Tile tl;
         const unsigned u = t / tiles_per_row;
         const int64_t cbase = (int64_t)(t - u * tiles_per_row) * 1024;
-        const double* row = PT + (int64_t)u * pitchC;
+        const double* row = PT + (int64_t)u * strideU;        // element (k, u, c): PT[k planeStride + u strideU + c strideC]
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int64_t c = cbase + threadIdx.x + 256 * j;
@@ -663,7 +712,7 @@ region_weights_kernel(const double* __restrict__ PT, int64_t planeStride,
                     tl.ks[j] = 0;                             // (peaked or not: read off pk when it is used)
                 } else {
                     tl.ks[j] = __ldg(fstate + c);
-                    if (tl.ks[j] < 3) tl.pk[j] = ldg_stream1(row + tl.ks[j] * planeStride + c);
+                    if (tl.ks[j] < 3) tl.pk[j] = ldg_stream1(row + tl.ks[j] * planeStride + c * strideC);
                 }
             }
         }
@@ -676,7 +725,7 @@ region_weights_kernel(const double* __restrict__ PT, int64_t planeStride,
         const Tile nxt2 = load(t + 2 * gridDim.x);
         const unsigned u = t / tiles_per_row;
         const int64_t cbase = (int64_t)(t - u * tiles_per_row) * 1024;
-        const double* row = PT + (int64_t)u * pitchC;
+        const double* row = PT + (int64_t)u * strideU;
         double2* out = reinterpret_cast<double2*>(WT) + (int64_t)u * C;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -691,7 +740,7 @@ region_weights_kernel(const double* __restrict__ PT, int64_t planeStride,
                 w[0] = w[1] = w[2] = 0.0;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    const double p = ldg_stream1(row + k * planeStride + c);
+                    const double p = ldg_stream1(row + k * planeStride + c * strideC);
 #pragma unroll
                     for (int l = 0; l < 3; ++l) w[l] = fma(q[k], fast_log<FAST>(mix_rel(th, l, p), s_tab), w[l]);
                 }
@@ -1625,19 +1674,12 @@ int fcd_pstar_refresh(const double* PT, int64_t planeStride, int32_t Ul, int64_t
     return check_launch("fcd_pstar_refresh(commit)");
 }
 
-int fcd_region_weights(const double* PT, int64_t planeStride, int32_t Ul, int64_t C, int64_t pitchC,
-                       const double* qF, const uint8_t* fstate, double* PsT, uint8_t* kcache,
-                       const fcd_theta* theta_host, double* WT, void* stream) {
-    FCD_REQUIRE(theta_host != nullptr && fstate != nullptr, "fcd_region_weights: NULL argument");
-    FCD_REQUIRE(C >= 0 && Ul >= 0 && pitchC >= C, "fcd_region_weights: bad shape");
-    FCD_REQUIRE((PsT == nullptr) == (kcache == nullptr), "fcd_region_weights: PsT and kcache go together");
-    if (C == 0 || Ul == 0) return 0;
+// The planes as (base, planeStride, strideU, strideC): patient-major PT [3][Ul][pitchC] is (PT, Ul pitchC, pitchC, 1),
+// the E-step's edge-major planes [3][C][pitchU] from patient u0 on are (Pe + u0, C pitchU, 1, pitchU).
+static int region_weights_launch(const double* PT, int64_t planeStride, int64_t strideU, int64_t strideC, int32_t Ul,
+                                 int64_t C, int64_t pitchC, const double* qF, const uint8_t* fstate, const double* PsT,
+                                 const fcd_theta* theta_host, double* WT, cudaStream_t st) {
     const ThetaDev th = make_theta_dev(*theta_host, 0);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (PsT != nullptr) {                                     // refresh the columns of edges whose state changed
-        int rc = fcd_pstar_refresh(PT, planeStride, Ul, C, pitchC, fstate, PsT, kcache, stream);
-        if (rc) return rc;
-    }
     LogTabWindow tab;
     FCD_REQUIRE(log_table_window(th.epsl, th.al, st, tab), "fcd_region_weights: log table initialisation failed");
     int64_t ntiles = ((C + 1023) / 1024) * (int64_t)Ul;
@@ -1652,14 +1694,57 @@ int fcd_region_weights(const double* PT, int64_t planeStride, int32_t Ul, int64_
         cudaFuncSetAttribute(region_weights_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)kLogTabBytes);
         region_weights_kernel<true><<<(unsigned)grid, 256, tab.bytes(), st>>>(
-            PT, planeStride, Ul, C, pitchC, qF, fstate, PsT, th, tab, WT);
+            PT, planeStride, strideU, strideC, Ul, C, pitchC, qF, fstate, PsT, th, tab, WT);
     } else {
         int64_t grid = (int64_t)sm_count() * 4;
         if (grid > ntiles) grid = ntiles;
         region_weights_kernel<false><<<(unsigned)grid, 256, 0, st>>>(
-            PT, planeStride, Ul, C, pitchC, qF, fstate, PsT, th, tab, WT);
+            PT, planeStride, strideU, strideC, Ul, C, pitchC, qF, fstate, PsT, th, tab, WT);
     }
     return check_launch("fcd_region_weights");
+}
+
+int fcd_region_weights(const double* PT, int64_t planeStride, int32_t Ul, int64_t C, int64_t pitchC,
+                       const double* qF, const uint8_t* fstate, double* PsT, uint8_t* kcache,
+                       const fcd_theta* theta_host, double* WT, void* stream) {
+    FCD_REQUIRE(theta_host != nullptr && fstate != nullptr, "fcd_region_weights: NULL argument");
+    FCD_REQUIRE(C >= 0 && Ul >= 0 && pitchC >= C, "fcd_region_weights: bad shape");
+    FCD_REQUIRE((PsT == nullptr) == (kcache == nullptr), "fcd_region_weights: PsT and kcache go together");
+    if (C == 0 || Ul == 0) return 0;
+    if (PsT != nullptr) {                                     // refresh the columns of edges whose state changed
+        int rc = fcd_pstar_refresh(PT, planeStride, Ul, C, pitchC, fstate, PsT, kcache, stream);
+        if (rc) return rc;
+    }
+    return region_weights_launch(PT, planeStride, pitchC, 1, Ul, C, pitchC, qF, fstate, PsT, theta_host, WT,
+                                 (cudaStream_t)stream);
+}
+
+int fcd_pstar_refresh_em(const double* Pe, int64_t planeStride, int64_t pitchU, int32_t u0, int32_t Ul, int64_t C,
+                         int64_t pitchC, const uint8_t* fstate, double* PsT, uint8_t* kcache, void* stream) {
+    FCD_REQUIRE(Pe != nullptr && fstate != nullptr && PsT != nullptr && kcache != nullptr,
+                "fcd_pstar_refresh_em: NULL argument");
+    FCD_REQUIRE(C >= 0 && Ul >= 0 && u0 >= 0 && pitchU >= (int64_t)u0 + Ul && pitchC >= C, "fcd_pstar_refresh_em: bad shape");
+    if (C == 0 || Ul == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    pstar_refresh_em_kernel<<<(unsigned)((C + 31) / 32), 256, 0, st>>>(Pe, planeStride, pitchU, u0, Ul, C, pitchC, fstate,
+                                                                        kcache, PsT);
+    int rc = check_launch("fcd_pstar_refresh_em");
+    if (rc) return rc;
+    pstar_commit_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(fstate, C, kcache);
+    return check_launch("fcd_pstar_refresh_em(commit)");
+}
+
+int fcd_region_weights_em(const double* Pe, int64_t planeStride, int64_t pitchU, int32_t u0, int32_t Ul, int64_t C,
+                          int64_t pitchC, const double* qF, const uint8_t* fstate, double* PsT, uint8_t* kcache,
+                          const fcd_theta* theta_host, double* WT, void* stream) {
+    FCD_REQUIRE(theta_host != nullptr && fstate != nullptr && Pe != nullptr && PsT != nullptr && kcache != nullptr,
+                "fcd_region_weights_em: NULL argument");
+    FCD_REQUIRE(C >= 0 && Ul >= 0 && u0 >= 0 && pitchU >= (int64_t)u0 + Ul && pitchC >= C, "fcd_region_weights_em: bad shape");
+    if (C == 0 || Ul == 0) return 0;
+    int rc = fcd_pstar_refresh_em(Pe, planeStride, pitchU, u0, Ul, C, pitchC, fstate, PsT, kcache, stream);
+    if (rc) return rc;
+    return region_weights_launch(Pe + u0, planeStride, 1, pitchU, Ul, C, pitchC, qF, fstate, PsT, theta_host, WT,
+                                 (cudaStream_t)stream);
 }
 
 int fcd_estep_qR(const double* WT, int64_t C, int32_t N, int32_t U, int32_t u0, int32_t Ul,

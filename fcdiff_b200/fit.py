@@ -205,6 +205,8 @@ class UnsharedRegionFit(object):
         self.update_mu_sigma = False  # re-estimate mu, sigma (disabled in the reference, fit.py:232-237)
         self.coded_estep = True       # K2 from the previous M-step's code plane when it still describes q_R
         self.fused_sweep = False      # K2b: weights computed inside the sweep (no WT tensor; reference lookup, N <= 1024)
+        self.patient_major_planes = False  # K2b weights from patient-major copies of the planes (the first form) instead of
+        #                                    the E-step's edge-major planes (fcd_region_weights_em)
         self.elm_path = "auto"        # K3b form: "streams" (coded plane) | "tiered" | "auto" (coded unless most elements are undecided)
         self.convergence_rule = "reference"
         self.theta_solver = "newton"  # (eta, epsilon): device-resident Newton | host-driven SciPy L-BFGS-B
@@ -484,12 +486,16 @@ class UnsharedRegionFit(object):
         inp['code_verR'] = None
         inp['cache_key'] = ckey
         inp['PT'] = None
+        inp['Pblk'] = None
+        inp['PsT'] = inp['kcache'] = None
         self._evals = []
         self._const = None
         return inp
 
     def _ensure_patient_major(self):
-        """Patient-major responsibility planes PT [3][U_local][C] of ALL edges (K2b)."""
+        """Patient-major responsibility planes PT [3][U_local][C] of ALL edges: the fused sweep's input, and the
+        region weights' when ``patient_major_planes`` is set (the default path reads the edge-major planes,
+        `_ensure_patient_planes`)."""
         inp = self._ensure_cache()
         if inp['PT'] is not None:
             return inp
@@ -504,54 +510,7 @@ class UnsharedRegionFit(object):
             inp['PT'] = PT
             inp['PsT'] = inp['kcache'] = None
             return inp
-        pre = inp.pop('PT_pre', None)
-        if pre is not None:
-            # built on the side stream while the main stream formed the edge shard's planes (_prefetch_patient_major)
-            torch.cuda.current_stream().wait_event(pre['ev'])
-            if pre['key'] == inp['cache_key']:
-                inp['PT'] = pre['PT']
-                inp['PsT'] = inp['kcache'] = None
-                return inp
-        inp['PT'] = self._build_patient_major(inp)
-        inp['PsT'] = inp['kcache'] = None
-        return inp
-
-    def _prefetch_patient_major(self):
-        """Edge shards with device-resident inputs: the all-to-all that turns the edge-sharded `bt` into this
-        rank's patient block, the planes of that block and their transposes are enqueued on the side stream at
-        the START of run(): NVLink traffic and its kernels overlap the main stream's set-up (the edge shard's
-        planes, the uniform start's row sums, the initial free energy) instead of preceding the first sweep."""
-        inp = self._ensure_inputs()
-        if (self.shards is None or self._shared is not None or not torch.is_tensor(self.bt)
-                or inp.get('PT') is not None or inp.get('PT_pre') is not None):
-            return
-        (cur, side) = (torch.cuda.current_stream(), _dev.side_stream())
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            PT = self._build_patient_major(inp)
-            ev = torch.cuda.Event()
-            ev.record(side)
-        PT.record_stream(cur)                      # allocated under the side stream, used by the main one
-        inp['PT_pre'] = dict(PT=PT, ev=ev, key=self._cache_key)
-
-    def _build_patient_major(self, inp):
-        """PT [3][U_local][pitchC] on the CURRENT stream."""
-        lib = _lib.load()
-        (C, U, u0, Ul) = (inp['C'], inp['U'], inp['u0'], inp['Ul'])
-        if self.shards is None:
-            (src, pitchU, uu0, Us) = (inp['P'], inp['pitchU'], u0, U)
-        else:
-            if torch.is_tensor(self.bt):
-                # edge-sharded device input: one all-to-all of (C_local x U_peer) blocks of bt
-                blk = self.shards.exchange_patient_blocks(inp['bt'], inp['Cl'], C, U)
-            else:   # edge-sharded host input: this rank uploads every edge of its own patients
-                blk = _dev.upload(np.ascontiguousarray(np.asarray(self.bt)[:, u0:u0 + Ul]))
-            src = _dev.empty((3, C, max(Ul, 1)))
-            if Ul > 0:
-                th = self._theta()
-                _lib.check(lib.fcd_resp_cache(_dev.ptr(blk), C, Ul, Ul, ctypes.byref(th), _dev.ptr(src),
-                                              C * max(Ul, 1), None, _dev.stream()), "fcd_resp_cache")
-            (pitchU, uu0, Us) = (Ul, 0, Ul)
+        (src, planeStride, pitchU, uu0) = self._ensure_patient_planes()
         pitchC = _dev.even(C)                      # rows are moved by 16-byte-granular bulk copies
         PT = _dev.empty((3, max(Ul, 1), pitchC))       # every edge column is written below; only the pad is zeroed
         if pitchC != C or Ul == 0:
@@ -559,10 +518,70 @@ class UnsharedRegionFit(object):
         if Ul > 0:
             with _dev.timed(self.profile, "K0_transpose"):
                 for k in range(3):
-                    _lib.check(lib.fcd_transpose_patients(_dev.ptr(src[k]), C, Us, pitchU, uu0, Ul,
+                    _lib.check(lib.fcd_transpose_patients(_dev.ptr(src[k]), C, uu0 + Ul, pitchU, uu0, Ul,
                                                           _dev.ptr(PT[k]), pitchC, _dev.stream()),
                                "fcd_transpose_patients")
-        return PT
+        inp['PT'] = PT
+        inp['PsT'] = inp['kcache'] = None
+        return inp
+
+    def _ensure_patient_planes(self):
+        """(Pe, planeStride, pitchU, u0): EDGE-major planes Pe[k][c][u0 + u] of ALL edges for this rank's
+        patients -- the E-step's own planes on one GPU (and in replica mode); with edge shards the planes of
+        the patient block the set-up all-to-all delivers (`_build_patient_block`, normally already in flight
+        on the side stream: `_prefetch_patient_block`)."""
+        inp = self._ensure_cache()
+        if self.shards is None:
+            return (inp['P'], max(inp['Cl'], 1) * inp['pitchU'], inp['pitchU'], inp['u0'])
+        blk = inp.get('Pblk')
+        if blk is None:
+            pre = inp.pop('Pblk_pre', None)
+            if pre is not None:
+                torch.cuda.current_stream().wait_event(pre['ev'])
+                if pre['key'] == inp['cache_key']:
+                    blk = pre['blk']
+            if blk is None:
+                blk = self._build_patient_block(inp)
+            inp['Pblk'] = blk
+            inp['PsT'] = inp['kcache'] = None
+        return (blk, blk.shape[1] * blk.shape[2], blk.shape[2], 0)
+
+    def _prefetch_patient_block(self):
+        """Edge shards with device-resident inputs: the all-to-all that turns the edge-sharded `bt` into this
+        rank's patient block and the planes of that block are enqueued on the side stream at the START of
+        run(): NVLink traffic and the plane kernel overlap the main stream's set-up (the edge shard's planes,
+        the uniform start's row sums, the initial free energy) instead of preceding the first sweep."""
+        inp = self._ensure_inputs()
+        if (self.shards is None or self._shared is not None or not torch.is_tensor(self.bt)
+                or inp.get('Pblk') is not None or inp.get('Pblk_pre') is not None):
+            return
+        (cur, side) = (torch.cuda.current_stream(), _dev.side_stream())
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            blk = self._build_patient_block(inp)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        blk.record_stream(cur)                     # allocated under the side stream, used by the main one
+        inp['Pblk_pre'] = dict(blk=blk, ev=ev, key=self._cache_key)
+
+    def _build_patient_block(self, inp):
+        """Edge shards: responsibility planes [3][C][U_local] of every edge for this rank's patients, on the
+        CURRENT stream."""
+        lib = _lib.load()
+        (C, U, u0, Ul) = (inp['C'], inp['U'], inp['u0'], inp['Ul'])
+        if torch.is_tensor(self.bt):
+            # edge-sharded device input: one all-to-all of (C_local x U_peer) blocks of bt
+            blk = self.shards.exchange_patient_blocks(inp['bt'], inp['Cl'], C, U)
+        else:   # edge-sharded host input: this rank uploads every edge of its own patients
+            blk = _dev.upload(np.ascontiguousarray(np.asarray(self.bt)[:, u0:u0 + Ul]))
+        src = _dev.empty((3, C, max(Ul, 1)))
+        if Ul > 0:
+            th = self._theta()
+            _lib.check(lib.fcd_resp_cache(_dev.ptr(blk), C, Ul, Ul, ctypes.byref(th), _dev.ptr(src),
+                                          C * max(Ul, 1), None, _dev.stream()), "fcd_resp_cache")
+        else:
+            src.zero_()
+        return src
 
     def _result(self, n, dtype=torch.float64, tag=""):
         key = (n, dtype, tag, torch.cuda.current_device())
@@ -709,9 +728,12 @@ class UnsharedRegionFit(object):
         if self._in is not None and self._in.get('ev_S') is not None:
             # host inputs still uploading: everything that needs the patient correlations only
             # (planes, patient-major planes of the region sweep) is enqueued under the upload
-            self._ensure_patient_major()
+            if self.fused_sweep or self.patient_major_planes:
+                self._ensure_patient_major()
+            else:
+                self._ensure_patient_planes()
         elif self.shards is not None and torch.is_tensor(self.bt):
-            self._prefetch_patient_major()
+            self._prefetch_patient_block()
 
         self.energy = [self._eval_energy()]
         if not np.isfinite(self.energy[0]):
@@ -1110,7 +1132,15 @@ class UnsharedRegionFit(object):
                                             _dev.ptr(lqR_new), _dev.stream()), "fcd_estep_qR")
             self._mR.set_dev(lqR_new, qR_new, (N, U, 2))
             return
-        inp = self._ensure_patient_major()
+        fused = lookup == 0 and self.fused_sweep
+        use_pt = fused or self.patient_major_planes
+        if use_pt:
+            inp = self._ensure_patient_major()
+            (PT, pitchC) = (inp['PT'], inp['PT'].shape[2])
+        else:
+            (Pe, peStride, pePitch, pe_u0) = self._ensure_patient_planes()
+            inp = self._in
+            pitchC = _dev.even(inp['C'])
         (N, H, U) = self._dims
         (C, u0, Ul) = (inp['C'], inp['u0'], inp['Ul'])
         (lqF, qF) = self._mF.get_dev()
@@ -1118,11 +1148,10 @@ class UnsharedRegionFit(object):
         th = self._theta()
         with _dev.timed(self.profile, "K2b_prepare"):          # peak states of the new q_F
             fstate = self._mF.get_state()
-        (PT, pitchC) = (inp['PT'], inp['PT'].shape[2])
         if inp.get('PsT') is None:                 # dominant-state plane, gathered on first use (q_F settles early)
             inp['PsT'] = _dev.empty((max(Ul, 1), pitchC))
             inp['kcache'] = torch.full((max(C, 1),), 255, dtype=torch.uint8, device=_dev.device())
-        if lookup == 0 and 3 <= N <= 8192 and self.fused_sweep:
+        if fused and 3 <= N <= 8192:
             # every edge's weights are computed once inside the sweep and kept in a shared-memory ring: no WT tensor
             lqR_new, qR_new = lqR.clone(), qR.clone()
             with _dev.timed(self.profile, "K2b_sweep_fused"):
@@ -1137,10 +1166,16 @@ class UnsharedRegionFit(object):
             if inp['WT'] is None:
                 inp['WT'] = _dev.empty((Ul, C, 2))
             with _dev.timed(self.profile, "K2b_region_weights"):
-                _lib.check(lib.fcd_region_weights(_dev.ptr(PT), max(Ul, 1) * pitchC, Ul, C, pitchC,
-                                                  _dev.ptr(qF), _dev.ptr(fstate), _dev.ptr(inp['PsT']),
-                                                  _dev.ptr(inp['kcache']), ctypes.byref(th),
-                                                  _dev.ptr(inp['WT']), _dev.stream()), "fcd_region_weights")
+                if use_pt:
+                    _lib.check(lib.fcd_region_weights(_dev.ptr(PT), max(Ul, 1) * pitchC, Ul, C, pitchC,
+                                                      _dev.ptr(qF), _dev.ptr(fstate), _dev.ptr(inp['PsT']),
+                                                      _dev.ptr(inp['kcache']), ctypes.byref(th),
+                                                      _dev.ptr(inp['WT']), _dev.stream()), "fcd_region_weights")
+                else:
+                    _lib.check(lib.fcd_region_weights_em(_dev.ptr(Pe), peStride, pePitch, pe_u0, Ul, C, pitchC,
+                                                         _dev.ptr(qF), _dev.ptr(fstate), _dev.ptr(inp['PsT']),
+                                                         _dev.ptr(inp['kcache']), ctypes.byref(th),
+                                                         _dev.ptr(inp['WT']), _dev.stream()), "fcd_region_weights_em")
             # (the sweep's in-place arrays are copied in the shadow of the weights kernel: until that launch the
             # host is on the critical path -- the GPU has only the E-step launched ahead to work on)
             lqR_new, qR_new = lqR.clone(), qR.clone()

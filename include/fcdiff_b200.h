@@ -281,6 +281,18 @@ FCD_API int fcd_estep_qR_fused(const double* PsT, const double* PT, int64_t plan
 FCD_API int fcd_pstar_refresh(const double* PT, int64_t planeStride, int32_t Ul, int64_t C, int64_t pitchC,
                       const uint8_t* fstate, double* PsT, uint8_t* kcache, void* stream);
 
+/* The same two entries on the E-step's EDGE-major planes Pe [3][C][pitchU] (fcd_resp_cache), patients
+ * [u0, u0 + Ul): no patient-major copy of the planes is needed -- the dominant-state plane PsT [Ul][pitchC] is
+ * gathered by one transposing pass over the rows of the edges whose state changed (all of them the first time),
+ * and the three-plane path of an unpeaked edge reads Pe with a stride.  Same results as fcd_region_weights /
+ * fcd_pstar_refresh on the transposed planes (fcdiff/fit.py:176-198 needs the weights of every edge of a patient;
+ * the layout they are read from is this implementation's business). */
+FCD_API int fcd_pstar_refresh_em(const double* Pe, int64_t planeStride, int64_t pitchU, int32_t u0, int32_t Ul, int64_t C,
+                         int64_t pitchC, const uint8_t* fstate, double* PsT, uint8_t* kcache, void* stream);
+FCD_API int fcd_region_weights_em(const double* Pe, int64_t planeStride, int64_t pitchU, int32_t u0, int32_t Ul, int64_t C,
+                          int64_t pitchC, const double* qF, const uint8_t* fstate, double* PsT, uint8_t* kcache,
+                          const fcd_theta* theta_host, double* WT, void* stream);
+
 /* K3a -- M-step sums; replaces `_update_pi` / `_update_gamma`
  * (fcdiff/fit.py:208-220).  out[0..2] = sum_c exp(lqF[c,k]),
  * out[3] = sum_{n,u} exp(lqR[n,u,1]).  The caller divides by counts (after an

@@ -45,7 +45,7 @@ def fresh(profile):
 
     ph("init_lps+update_lps (inputs, planes)", lambda: (fit._init_lps(N, H, U), fit._update_lps()))
     ph("ensure_cache", fit._ensure_cache)
-    ph("ensure_patient_major", fit._ensure_patient_major)
+    ph("ensure_patient_planes", fit._ensure_patient_planes)
     ph("initial energy", lambda: fit.energy.append(fit._eval_energy()))
     for i in range(1, ITERS + 1):
         ph("it%d lq_F" % i, fit._update_lq_F)

@@ -308,6 +308,38 @@ def test_speculative_estep_is_bit_identical(N, H, U, iters):
     assert f1._spec is None
 
 
+@pytest.mark.parametrize("N,H,U,iters,lookup", [(12, 9, 11, 3, "reference"), (33, 20, 70, 4, "symmetric"),
+                                                 (90, 50, 50, 4, "reference"), (120, 30, 333, 5, "reference")])
+def test_region_weights_from_edge_major_planes_is_bit_identical(N, H, U, iters, lookup):
+    """The region weights read the E-step's edge-major planes (fcd_region_weights_em: the dominant-state plane
+    gathered by a transposing pass, unpeaked edges through strided reads); the first form made patient-major
+    copies of the three planes for it (`patient_major_planes = True`).  Same numbers bit for bit -- the small
+    problems keep unpeaked edges and undecided regions for several iterations, the odd sizes exercise the
+    partial 32 x 32 tiles of the gather."""
+    (_, _, _, _, b, bt) = O.sample(O.Theta(), N, H, U, np.random.RandomState(7 * N + U))
+
+    def run(pm):
+        fit = _fit_for(b, bt, eta_shift=0.1, solver="newton")
+        fit.patient_major_planes = pm
+        fit.edge_lookup = lookup
+        fit.max_iters = iters
+        fit.rel_tol = -1.0
+        fit.run()
+        return fit
+
+    (f0, f1) = (run(False), run(True))
+    assert f0.energy == f1.energy
+    nptest.assert_array_equal(f0._lq_R, f1._lq_R)
+    nptest.assert_array_equal(f0._lq_F, f1._lq_F)
+    assert f0._in.get('PT') is None and f1._in.get('PT') is not None
+    # and against the oracle (polished optimiser = the device Newton solver's fixed point)
+    tho = O.Theta()
+    tho.eta += 0.1
+    out = O.run(b, bt, tho, max_iters=iters, rel_tol=-1.0, edge_lookup=lookup, polish=True)
+    nptest.assert_allclose(f0.energy, out["energy"], rtol=1e-6)
+    nptest.assert_allclose(np.exp(f0._lq_R), np.exp(out["lq_R"]), rtol=1e-6, atol=1e-300)
+
+
 def test_newton_solver_reaches_active_bounds_and_leaves_the_table_window():
     """Start points far from the minimiser: epsilon has to travel more than the factor 8 one pass of
     the solver may move it (the box that sizes the kernels' logarithm table), and a problem whose
