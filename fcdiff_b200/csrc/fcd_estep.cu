@@ -906,9 +906,31 @@ __device__ __forceinline__ int64_t sweep_edge(int n, int m, int64_t base_n) {
 }
 
 // q_R [Npad] | tiles [2 buffers][near, in-block][B x (B + 1)] | far sums [2][helper warps][B] | D [2][B]
-__host__ __device__ constexpr size_t sweep_blocked_smem(int N, int T, int B, int n7 = 0) {
-    return (size_t)((N + 31) & ~31) * 16 + (size_t)4 * B * (B + 1) * 16 + (size_t)2 * (T / 32 - 1) * B * 8 +
+__host__ __device__ constexpr size_t sweep_blocked_smem(int N, int T, int B, int n7 = 0, int cs = 1) {
+    return (size_t)((N + 31) & ~31) * 16 + (size_t)4 * B * (B + 1) * 16 + (size_t)2 * cs * (T / 32 - 1) * B * 8 +
            (size_t)2 * B * 8 + (size_t)n7 * 8;
+}
+
+// Thread-block cluster helpers (CS > 1 form of the blocked sweep: the CTAs of a cluster share one patient).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t dsmem_addr(const void* local, uint32_t rank) {
+    uint32_t a;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"((uint32_t)__cvta_generic_to_shared(local)), "r"(rank));
+    return a;
+}
+__device__ __forceinline__ void dsmem_store(uint32_t addr, double v) {
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void dsmem_store2(uint32_t addr, double2 v) {
+    asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
 }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -965,11 +987,17 @@ __device__ __noinline__ double2 sweep_weights_unpeaked(const SweepFusedArgs& fa,
     return make_double2(w0 - w2, w2 - w1);
 }
 
-template <int T, int B, int LOOKUP, bool FUSED, bool FAST>
+// CS > 1 (few patients on this GPU -- sharded fits: 63 patients on 148 SMs): the CS CTAs of a thread-block cluster
+// share ONE patient.  The launch lasts a patient's chain of blocks and a block lasts what its far sums take one SM to
+// pull from L2; the cluster splits the far columns over its CTAs, CTA r > 0 stores its warps' partial sums into CTA
+// 0's shared memory (DSMEM), CTA 0 alone holds the tiles, solves and writes the outputs, and sends every solved
+// block's q_R to the others' copies of s_q; the per-block barrier becomes a cluster barrier.
+template <int T, int B, int LOOKUP, bool FUSED, bool FAST, int CS = 1>
 __global__ void __launch_bounds__(T, 512 / T)
 sweep_blocked_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int u0, double lp0, double lp1,
                      double* __restrict__ qR, double* __restrict__ lqR, const __grid_constant__ SweepFusedArgs fa) {
-    constexpr int NWH = T / 32 - 1, H = T - 32, Bp = B + 1, RH = kSwRH, TILE = B * Bp;
+    static_assert(CS == 1 || !FUSED, "the cluster form exists for the WT sweep");
+    constexpr int NWH = T / 32 - 1, H = T - 32, Bp = B + 1, RH = kSwRH, TILE = B * Bp, NWP = CS * NWH;
     constexpr int LB = B == 32 ? 5 : 4;
     static_assert(B == 16 || B == 32, "block of 16 or 32 regions");
     static_assert(!FUSED || LOOKUP == FCD_LOOKUP_REFERENCE, "the fused form reads contiguous windows (reference lookup)");
@@ -977,9 +1005,10 @@ sweep_blocked_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int
     double2* s_q = reinterpret_cast<double2*>(s_sweep);                    // [Npad] q_R of the moment
     const int Npad = (N + 31) & ~31;
     double2* s_tiles = s_q + Npad;                                         // [2][2][B][Bp], [column][row]
-    double* s_part = reinterpret_cast<double*>(s_tiles + 4 * TILE);       // [2][NWH][B] per-warp far sums
-    double* s_D = s_part + 2 * NWH * B;                                    // [2][B] l_0 - l_1 of a solved block
-    const int ul = blockIdx.x, u = u0 + ul;
+    double* s_part = reinterpret_cast<double*>(s_tiles + 4 * TILE);       // [2][CS NWH][B] per-warp far sums
+    double* s_D = s_part + 2 * NWP * B;                                    // [2][B] l_0 - l_1 of a solved block
+    const int crank = CS > 1 ? (int)cluster_ctarank() : 0;
+    const int ul = CS > 1 ? blockIdx.x / CS : blockIdx.x, u = u0 + ul;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     using Elem = typename std::conditional<FUSED, double, double2>::type;  // what the far loop loads per edge
     // WT form: {W_0 - W_2, W_2 - W_1} of this patient's edges; fused form: the patient's row of PsT
@@ -999,7 +1028,7 @@ sweep_blocked_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int
         const double w2 = sweep_log7<FAST>(fma(fa.bl[2], pv, fa.al[2]), tab7);
         return make_double2(w0 - w2, w2 - w1);
     };
-    __syncthreads();
+    if (CS > 1) cluster_sync_all(); else __syncthreads();
     const double dlp = lp0 - lp1;
     const int nblocks = (N + B - 1) / B;
 
@@ -1014,6 +1043,7 @@ sweep_blocked_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int
         // (fused form: the tiles are formed after the far loop, from responsibilities the previous phase's
         // prefetch has already brought into L2)
         if constexpr (!FUSED) {
+            if (crank == 0)
             for (int e = ht; e < 2 * B * B; e += H) {
                 const int t = e >> (2 * LB), i = (e >> LB) & (B - 1), j = e & (B - 1);
                 double2* dst = tiles + t * TILE + j * Bp + i;
@@ -1024,7 +1054,7 @@ sweep_blocked_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int
             }
         }
         // (ii) the rows of block b + 1 (what the NEXT prepare will read, one phase from now) into L2
-        if (b + 1 < nblocks && lane == 0) {                                // (the instruction takes warp-uniform operands)
+        if (b + 1 < nblocks && lane == 0 && crank == 0) {                  // (the instruction takes warp-uniform operands)
             const int n1 = n0 + B, nl = n1 + B - 1 < N - 1 ? n1 + B - 1 : N - 1;
             const int64_t e0 = (int64_t)n1 * (n1 - 1) / 2;
             int64_t e1 = (int64_t)nl * (nl - 1) / 2 + (LOOKUP == FCD_LOOKUP_REFERENCE ? N : nl);
@@ -1078,7 +1108,7 @@ sweep_blocked_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int
                     }
                 }
             };
-            for (int m = ht; m < N; m += H) {
+            for (int m = ht + crank * H; m < N; m += CS * H) {
                 const int mb = m >> LB;
                 if (mb == b - 1) continue;                                 // near: the solver's (new q_R of block b - 1)
                 const double2 q = s_q[m];
@@ -1107,7 +1137,11 @@ sweep_blocked_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int
                     acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
                 }
             }
-            if (lane < RH) s_part[((b & 1) * NWH + hw) * B + h + lane] = acc[0];
+            if (lane < RH) {
+                double* dst = s_part + ((b & 1) * NWP + crank * NWH + hw) * B + h + lane;
+                if (CS == 1 || crank == 0) *dst = acc[0];
+                else dsmem_store(dsmem_addr(dst, 0), acc[0]);              // into CTA 0's copy
+            }
         }
         if constexpr (FUSED) {
             for (int e = ht; e < 2 * B * B; e += H) {
@@ -1130,9 +1164,9 @@ sweep_blocked_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int
         const double2* wb = near + TILE;
         double Da = dlp, Db = 0.0;
 #pragma unroll
-        for (int w = 0; w < NWH; w += 2) {
-            Da += s_part[((b & 1) * NWH + w) * B + li];
-            if (w + 1 < NWH) Db += s_part[((b & 1) * NWH + w + 1) * B + li];
+        for (int w = 0; w < NWP; w += 2) {
+            Da += s_part[((b & 1) * NWP + w) * B + li];
+            if (w + 1 < NWP) Db += s_part[((b & 1) * NWP + w + 1) * B + li];
         }
         double D = Da + Db;
         if (b > 0) {                                                       // near tile x the block solved last
@@ -1176,6 +1210,10 @@ sweep_blocked_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int
         if (lane < nb) {
             s_q[n0 + lane] = qmine;
             s_D[(b & 1) * B + lane] = Dmine;
+            if constexpr (CS > 1) {                                        // the other CTAs' far sums read their own s_q
+#pragma unroll
+                for (int r = 1; r < CS; ++r) dsmem_store2(dsmem_addr(s_q + n0 + lane, r), qmine);
+            }
         }
     };
 
@@ -1202,17 +1240,17 @@ sweep_blocked_kernel(const double* __restrict__ WT, int64_t C, int N, int U, int
     };
 
     if (warp > 0) prepare(0);
-    __syncthreads();
+    if (CS > 1) cluster_sync_all(); else __syncthreads();
     for (int b = 0; b < nblocks; ++b) {
         if (warp == 0) {
-            solve(b);
+            if (crank == 0) solve(b);
         } else {
-            if (warp == NWH && b >= 1) outputs(b - 1);
+            if (warp == NWH && b >= 1 && crank == 0) outputs(b - 1);
             if (b + 1 < nblocks) prepare(b + 1);
         }
-        __syncthreads();
-    }
-    if (warp == NWH) outputs(nblocks - 1);
+        if (CS > 1) cluster_sync_all(); else __syncthreads();     // (the last one also keeps every CTA alive while
+    }                                                             //  CTA 0 may still store into its shared memory)
+    if (warp == NWH && crank == 0) outputs(nblocks - 1);
 }
 
 // --------------------------------------------------------------- K2b fused
@@ -1782,10 +1820,54 @@ int fcd_estep_qR(const double* WT, int64_t C, int32_t N, int32_t U, int32_t u0, 
             return e != nullptr ? atoi(e) : 0;
         }();
         if (forced_T == 128 || forced_T == 256 || forced_T == 512) T = forced_T;
-        const size_t smem = sweep_blocked_smem(N, T, B);
+        // Cluster form: two CTAs per patient when that still fits one wave (sharded fits: 63 patients on 148 SMs);
+        // FCD_SWEEP_CLUSTER=1|2 overrides.  Measured (scripts/sweep_bench.py, us, one CTA -> cluster of two):
+        // 1131 regions x 63 patients 310 -> 294 (undecided regime) / 290 -> 252 (decided); 400 x 63: 86 -> 91 /
+        // 74 -> 74; 800 x 125 (does not fit one wave): 204 -> 407.  At 63 patients the launch already moves
+        // the patients' 644 MB of weights at ~4 TB/s -- it is closer to the memory system's limit than to a single
+        // SM's, so the second SM buys little: used from ~700 regions on (512 threads), where it does gain.
+        static const int forced_cs = [] {
+            const char* e = getenv("FCD_SWEEP_CLUSTER");
+            return e != nullptr ? atoi(e) : 0;
+        }();
+        int cs = (T == 512 && 2 * (int64_t)Ul <= (int64_t)sm_count()) ? 2 : 1;
+        if (forced_cs == 1 || (forced_cs == 2 && T >= 256)) cs = forced_cs;
+        const size_t smem = sweep_blocked_smem(N, T, B, 0, cs);
         FCD_REQUIRE(smem <= kSmemBudget, "fcd_estep_qR: N=%d needs %zu bytes of shared memory", N, smem);
         SweepFusedArgs nofuse;
         memset(&nofuse, 0, sizeof(nofuse));
+        if (cs == 2) {
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3((unsigned)(2 * Ul));
+            cfg.blockDim = dim3((unsigned)T);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = st;
+            cudaLaunchAttribute attr;
+            attr.id = cudaLaunchAttributeClusterDimension;
+            attr.val.clusterDim.x = 2;
+            attr.val.clusterDim.y = 1;
+            attr.val.clusterDim.z = 1;
+            cfg.attrs = &attr;
+            cfg.numAttrs = 1;
+            cudaError_t e = cudaSuccess;
+#define FCD_SWC(T_, L_)                                                                                       \
+            do {                                                                                              \
+                FCD_ALLOW_BIG_SMEM((sweep_blocked_kernel<T_, 16, L_, false, false, 2>));                      \
+                e = cudaLaunchKernelEx(&cfg, sweep_blocked_kernel<T_, 16, L_, false, false, 2>, WT, C, N, U, u0, lp0, lp1, \
+                                       qR, lqR, nofuse);                                                      \
+            } while (0)
+            if (T == 512) {
+                if (edge_lookup == FCD_LOOKUP_REFERENCE) FCD_SWC(512, FCD_LOOKUP_REFERENCE);
+                else FCD_SWC(512, FCD_LOOKUP_SYMMETRIC);
+            } else {
+                if (edge_lookup == FCD_LOOKUP_REFERENCE) FCD_SWC(256, FCD_LOOKUP_REFERENCE);
+                else FCD_SWC(256, FCD_LOOKUP_SYMMETRIC);
+            }
+#undef FCD_SWC
+            FCD_REQUIRE(e == cudaSuccess, "fcd_estep_qR(cluster): %s", cudaGetErrorString(e));
+            return check_launch("fcd_estep_qR(blocked, cluster)");
+        }
 #define FCD_SWB(T_, B_)                                                                                      \
         do {                                                                                                 \
             if (edge_lookup == FCD_LOOKUP_REFERENCE) {                                                       \

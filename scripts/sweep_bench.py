@@ -11,8 +11,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SHAPES = [(400, 500), (400, 63), (566, 250), (800, 125), (1131, 63), (1000, 1000), (1000, 125)]
 if os.environ.get("FCD_SWEEP_SHAPES"):                       # e.g. "400x63,1131x63" (profiling one shape under ncu)
     SHAPES = [tuple(int(v) for v in t.split("x")) for t in os.environ["FCD_SWEEP_SHAPES"].split(",")]
-VARIANTS = [("stepwise", {"FCD_SWEEP": "stepwise"}), ("blocked/auto", {})] + \
-           [("blocked/%d" % t, {"FCD_SWEEP_T": str(t)}) for t in (128, 256, 512)]
+VARIANTS = [("stepwise", {"FCD_SWEEP": "stepwise"}), ("blocked/auto", {}), ("auto, 1 CTA", {"FCD_SWEEP_CLUSTER": "1"})] + \
+           [("blocked/%d" % t, {"FCD_SWEEP_T": str(t), "FCD_SWEEP_CLUSTER": "1"}) for t in (128, 256, 512)] + \
+           [("cluster/%d" % t, {"FCD_SWEEP_T": str(t), "FCD_SWEEP_CLUSTER": "2"}) for t in (256, 512)]
 
 
 def child():

@@ -230,7 +230,10 @@ def test_patient_gather_staging_roundtrip(N, U, world):
                           # large weights: most regions come out decided (|l_0 - l_1| > 37.5, the short form of
                           # the in-block step), a few do not
                           (37, 5, 0, 2.0), (100, 3, 1, 2.0), (400, 6, 0, 2.0), (400, 5, 1, 2.0), (1100, 2, 0, 1.0),
-                          (600, 2, 1, 0.5)])
+                          (600, 2, 1, 0.5),
+                          # from 700 regions on and with few patients two CTAs of a cluster share a patient
+                          # (partial sums and solved blocks travel through distributed shared memory)
+                          (800, 3, 1, 0.5), (715, 2, 0, 0.02)])
 def test_sweep_launch_shapes_match_numpy(N, U, lookup, scale):
     """Gauss-Seidel sweep of fit.py:184-197 over the two weight differences, for every launch shape of
     fcd_estep_qR (regions per thread / warps per patient depend on N), both edge lookups."""
