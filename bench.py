@@ -23,7 +23,7 @@ value  = C*(H+U)*K / t over FRESH FITS FROM THE UNIFORM START (fit.py:84-102) wi
          ceil(K / 10) calls of ``fit.run()`` with ``max_iters = 10`` (the reference's
          default, fit.py:36) and the convergence test disabled (``rel_tol = -1``), so
          every fit runs all its iterations -- set-up (responsibility planes,
-         patient-major planes, initial energy) and the expensive first iterations,
+         dominant-state plane, initial energy) and the expensive first iterations,
          where no posterior is decided yet, are inside the timed region.  CUDA
          events, max over ranks.
 steady_state = the same metric over consecutive iterations of ONE fit after the
@@ -210,7 +210,7 @@ def workload_config(n_gpus):
                         "%d-region atlas (%d edges over %d GPU) x (%d controls + %d patients)" % (N, N * (N - 1) // 2, n_gpus, H_SUBJ, U_SUBJ),
             "regions": N, "edges": N * (N - 1) // 2, "controls": H_SUBJ, "patients": U_SUBJ,
             "edge_lookup": "reference", "storage": "f64",
-            "l2": "per-step working set (responsibility planes, patient-major planes, WT, coded plane and records: > 2 GB per GPU) "
+            "l2": "per-step working set (responsibility planes, dominant-state planes, WT, coded plane and records: > 2 GB per GPU) "
                   "exceeds the 126 MB L2; no flush needed",
             "parallelism": "edge shards x%d, patient-sharded region sweep" % n_gpus}
 
@@ -608,7 +608,7 @@ def run_gpu_arm(args):
     converge = timed_fit()
     converge.update({"rel_tol": 1e-5,
                      "what": "fit.run() to the reference's convergence rule (fit.py:138-140) incl. set-up "
-                             "(healthy stats, responsibility planes, patient-major planes)"})
+                             "(healthy stats, responsibility planes, dominant-state planes)"})
     converge["magnitude_rule"] = dict(timed_fit(convergence_rule="magnitude"),
                                       what="same with (e - e*)/|e| < rel_tol (the reference's rule stops at the first "
                                            "decrease of a negative energy)")
