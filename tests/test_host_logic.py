@@ -310,3 +310,23 @@ def test_speculative_estep_handle_is_dropped_on_any_change():
     assert not fit._spec_matches(spec, inp, th)
     fit.coded_estep = False
     assert not fit._spec_matches(dict(spec, verR=fit._mR.version), dict(inp, code_verR=fit._mR.version), th)
+
+
+def test_mirror_completes_a_pending_gather_exactly_once():
+    """Edge shards inside run(): lq_F's other-rank rows are gathered lazily (`_Mirror.finish`).  The pending
+    collective runs once, before the array is read whole, and any new assignment drops it."""
+    from fcdiff_b200.fit import _Mirror
+    calls = []
+    m = _Mirror()
+    m.set_dev("lq", "q", (3, 1, 3), complete=lambda: calls.append(1))
+    m.finish()
+    m.finish()
+    assert calls == [1]
+    m.set_dev("lq", "q", (3, 1, 3), complete=lambda: calls.append(2))
+    m.set_dev("lq2", "q2", (3, 1, 3))                 # a newer E-step result: the old array is never completed
+    m.finish()
+    assert calls == [1]
+    m.set_dev("lq", "q", (3, 1, 3), complete=lambda: calls.append(3))
+    m.set_host(np.zeros((3, 1, 3)))                   # user assignment
+    m.finish()
+    assert calls == [1] and m.complete is None
