@@ -655,8 +655,8 @@ def run_gpu_arm(args):
            "h2d_bytes_per_step": int(8 * Cl * (H + U)),
            "d2h_bytes_per_step": int(8 * (1 + lqF_h.size + lqR_h.size)),
            "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
-           "what": "fit.run(max_iters=1) from pinned host arrays: H2D of b, bt + healthy stats + patient-major "
-                   "copy + initial energy + one EM iteration + energy; D2H of energy, lq_F, lq_R"}
+           "what": "fit.run(max_iters=1) from pinned host arrays: H2D of b, bt + healthy stats + responsibility "
+                   "planes + initial energy + one EM iteration + energy; D2H of energy, lq_F, lq_R"}
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(peaks_path):
